@@ -1,0 +1,813 @@
+/* context.cu -- host side of libugrt.so: lifetime, the Model, persistent device arenas, the per-frame
+ * sequencing that display() (main.cu:59-302) does in the reference, CUDA-graph capture of the frame,
+ * read-backs.  Mirrors per_frame_funcs.h / frustum_grid.h / frustum_tracer.h / decision_data.h /
+ * shader.h call for call, minus every cudaThreadSynchronize(), D2H scalar read-back, per-frame
+ * cudaMalloc/cudaFree and cudppPlan of the reference (frustum_grid.h:221-272,285-290,317-337).
+ */
+#include "ugrt_internal.h"
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+int ug_fail(ug_context *ctx, int code, const char *fmt, ...)
+{
+	char buf[1024];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	if (ctx) ctx->err = buf;
+	else fprintf(stderr, "ugrt: %s\n", buf);
+	return code;
+}
+
+template <class T> static cudaError_t dmalloc(T **p, size_t count)
+{
+	if (*p) { cudaFree(*p); *p = nullptr; }
+	return cudaMalloc((void **)p, sizeof(T) * (count ? count : 1));
+}
+template <class T> static void dfree(T *&p) { if (p) cudaFree(p); p = nullptr; }
+
+static int bits_for(unsigned max_key_exclusive) /* number of key bits needed for keys in [0, max) */
+{
+	int b = 1;
+	while (b < 32 && (1ull << b) < max_key_exclusive) b++;
+	return b;
+}
+
+/* ------------------------------------------------------------------ lifetime */
+extern "C" const char *ug_version(void) { return "ugrt 0.1 (sm_100a)"; }
+
+extern "C" int ug_create(ug_context **out, int device)
+{
+	if (!out) return UG_ERR_ARG;
+	*out = nullptr;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count <= 0)
+		return ug_fail(nullptr, UG_ERR_CUDA, "no CUDA device: %s (this library has no CPU path)", cudaGetErrorString(e));
+	if (device < 0 || device >= count) return ug_fail(nullptr, UG_ERR_ARG, "device %d out of range (%d devices)", device, count);
+	ug_context *ctx = new ug_context();
+	ctx->device = device;
+	UG_CUDA(ctx, cudaSetDevice(device));
+	cudaDeviceProp prop;
+	UG_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
+	ctx->num_sms = prop.multiProcessorCount;
+	UG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+	ctx->stream = ctx->own_stream;
+	for (int i = 0; i < UG_MAX_LIGHTS; i++) {
+		UG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking));
+		UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
+	}
+	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_trace, cudaEventDisableTiming));
+	UG_CUDA(ctx, cudaEventCreate(&ctx->ev_t0));
+	UG_CUDA(ctx, cudaEventCreate(&ctx->ev_t1));
+	for (auto &ev : ctx->ev_stage) UG_CUDA(ctx, cudaEventCreate(&ev));
+	UG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_fc, sizeof(FrameConst)));
+	memset(ctx->h_fc, 0, sizeof(FrameConst));
+	UG_CUDA(ctx, cudaMalloc((void **)&ctx->d_fc, sizeof(FrameConst)));
+	*out = ctx;
+	return UG_OK;
+}
+
+static void free_grid(GridBuffers &g)
+{
+	dfree(g.tri_rec); dfree(g.rect); dfree(g.count); dfree(g.scan);
+	dfree(g.keys[0]); dfree(g.keys[1]); dfree(g.vals[0]); dfree(g.vals[1]);
+	dfree(g.span); dfree(g.offset); dfree(g.counters);
+	dfree(g.sort.tile_hist); dfree(g.sort.tile_base); dfree(g.sort.scan_state);
+	g = GridBuffers();
+}
+static void free_rays(LightRays &r)
+{
+	dfree(r.cell); dfree(r.pix); dfree(r.span); dfree(r.offset); dfree(r.cursor); dfree(r.scan_state);
+	r = LightRays();
+}
+
+extern "C" void ug_destroy(ug_context *ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaDeviceSynchronize();
+	if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+	free_grid(ctx->cam_grid);
+	for (int i = 0; i < UG_MAX_LIGHTS; i++) { free_grid(ctx->light_grid[i]); free_rays(ctx->rays[i]); }
+	dfree(ctx->d_vertexlist); dfree(ctx->d_materiallist); dfree(ctx->d_vertex_orig_list); dfree(ctx->d_facelist); dfree(ctx->d_materiallist_index);
+	dfree(ctx->d_t); dfree(ctx->d_id); dfree(ctx->d_shadowed); dfree(ctx->d_matid); dfree(ctx->d_normal); dfree(ctx->d_dir); dfree(ctx->d_rgb);
+	if (ctx->h_rgb_pinned) cudaFreeHost(ctx->h_rgb_pinned);
+	if (ctx->h_fc) cudaFreeHost(ctx->h_fc);
+	dfree(ctx->d_fc);
+	for (int i = 0; i < UG_MAX_LIGHTS; i++) { cudaStreamDestroy(ctx->side[i]); cudaEventDestroy(ctx->ev_join[i]); }
+	cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_trace); cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
+	for (auto &ev : ctx->ev_stage) cudaEventDestroy(ev);
+	cudaStreamDestroy(ctx->own_stream);
+	delete ctx;
+}
+
+extern "C" const char *ug_last_error(const ug_context *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int ug_set_stream(ug_context *ctx, void *cuda_stream)
+{
+	if (!ctx) return UG_ERR_ARG;
+	ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+	if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+	return UG_OK;
+}
+
+extern "C" int ug_synchronize(ug_context *ctx)
+{
+	if (!ctx) return UG_ERR_ARG;
+	UG_CUDA(ctx, cudaSetDevice(ctx->device));
+	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return UG_OK;
+}
+
+/* ------------------------------------------------------------------ arenas */
+static int alloc_grid(ug_context *ctx, GridBuffers &g, int T, int C, size_t cap)
+{
+	if (g.T == T && g.C == C && g.cap >= cap && g.tri_rec) return UG_OK;
+	const size_t keep_cap = g.cap > cap ? g.cap : cap;
+	free_grid(g);
+	g.T = T; g.C = C; g.cap = keep_cap;
+	g.key_bits = bits_for((unsigned)C);
+	UG_CUDA(ctx, dmalloc(&g.tri_rec, 4 * (size_t)T));
+	UG_CUDA(ctx, dmalloc(&g.rect, (size_t)T));
+	UG_CUDA(ctx, dmalloc(&g.count, (size_t)T));
+	UG_CUDA(ctx, dmalloc(&g.scan, (size_t)T + 1));
+	for (int k = 0; k < 2; k++) {
+		UG_CUDA(ctx, dmalloc(&g.keys[k], g.cap));
+		UG_CUDA(ctx, dmalloc(&g.vals[k], g.cap));
+	}
+	UG_CUDA(ctx, dmalloc(&g.span, (size_t)C));
+	UG_CUDA(ctx, dmalloc(&g.offset, (size_t)C + 1));
+	UG_CUDA(ctx, dmalloc(&g.counters, 8));
+	UG_CUDA(ctx, cudaMemset(g.counters, 0, 8 * sizeof(u32)));
+	const size_t he = ugk_sort_hist_entries(ctx->num_sms);
+	UG_CUDA(ctx, dmalloc(&g.sort.tile_hist, he));
+	UG_CUDA(ctx, dmalloc(&g.sort.tile_base, he));
+	const size_t biggest = (size_t)(T > C ? T : C) + 2;
+	g.sort.scan_tiles = ugk_scan_tiles(biggest) + 1;
+	UG_CUDA(ctx, dmalloc(&g.sort.scan_state, g.sort.scan_tiles + 1));
+	return UG_OK;
+}
+
+static int alloc_rays(ug_context *ctx, LightRays &r, int N, int C)
+{
+	free_rays(r);
+	UG_CUDA(ctx, dmalloc(&r.cell, (size_t)N));
+	UG_CUDA(ctx, dmalloc(&r.pix, (size_t)N));
+	UG_CUDA(ctx, dmalloc(&r.span, (size_t)C + 1));
+	UG_CUDA(ctx, dmalloc(&r.offset, (size_t)C + 2));
+	UG_CUDA(ctx, dmalloc(&r.cursor, (size_t)C + 1));
+	r.scan_tiles = ugk_scan_tiles((size_t)C + 2) + 1;
+	UG_CUDA(ctx, dmalloc(&r.scan_state, r.scan_tiles + 1));
+	return UG_OK;
+}
+
+static size_t default_cap(int T, int C) { return (size_t)16 * (size_t)T + (size_t)C + (1u << 20); }
+
+/* make every buffer the current (model, screen, strip, lights, flags) needs exist */
+static int ensure_buffers(ug_context *ctx, int num_lights, bool full)
+{
+	if (ctx->num_faces <= 0) return ug_fail(ctx, UG_ERR_ARG, "no model loaded");
+	if (ctx->W <= 0) return ug_fail(ctx, UG_ERR_ARG, "screen size not set");
+	UG_CUDA(ctx, cudaSetDevice(ctx->device));
+	bool changed = false;
+	const int T = ctx->num_faces;
+	if (ctx->pix_alloc != (size_t)ctx->N || !ctx->d_t) {
+		const size_t N = (size_t)ctx->N;
+		UG_CUDA(ctx, dmalloc(&ctx->d_t, N));
+		UG_CUDA(ctx, dmalloc(&ctx->d_id, N));
+		UG_CUDA(ctx, dmalloc(&ctx->d_shadowed, N));
+		UG_CUDA(ctx, dmalloc(&ctx->d_matid, N));
+		UG_CUDA(ctx, dmalloc(&ctx->d_rgb, 3 * N));
+		if (ctx->h_rgb_pinned) cudaFreeHost(ctx->h_rgb_pinned);
+		ctx->h_rgb_pinned = nullptr;
+		UG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_rgb_pinned, 3 * N));
+		dfree(ctx->d_normal); dfree(ctx->d_dir);
+		ctx->full_alloc = false;
+		ctx->pix_alloc = N;
+		for (int l = 0; l < UG_MAX_LIGHTS; l++) free_rays(ctx->rays[l]); /* sized by N */
+		changed = true;
+	}
+	if (ctx->cam_grid.T != T || ctx->cam_grid.C != ctx->C_cam || !ctx->cam_grid.tri_rec) {
+		int rc = alloc_grid(ctx, ctx->cam_grid, T, ctx->C_cam, default_cap(T, ctx->C_cam));
+		if (rc) return rc;
+		changed = true;
+	}
+	for (int l = 0; l < num_lights; l++) {
+		if (ctx->light_grid[l].T != T || ctx->light_grid[l].C != ctx->C_light || !ctx->light_grid[l].tri_rec) {
+			int rc = alloc_grid(ctx, ctx->light_grid[l], T, ctx->C_light, default_cap(T, ctx->C_light));
+			if (rc) return rc;
+			free_rays(ctx->rays[l]);
+			changed = true;
+		}
+		if (!ctx->rays[l].cell) {
+			int rc = alloc_rays(ctx, ctx->rays[l], ctx->N, ctx->C_light);
+			if (rc) return rc;
+			changed = true;
+		}
+	}
+	if (full && !ctx->full_alloc) {
+		UG_CUDA(ctx, dmalloc(&ctx->d_normal, 3 * (size_t)ctx->N));
+		UG_CUDA(ctx, dmalloc(&ctx->d_dir, 3 * (size_t)ctx->N));
+		ctx->full_alloc = true;
+		changed = true;
+	}
+	if (changed && ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+	return UG_OK;
+}
+
+/* ------------------------------------------------------------------ Model (scene.h) */
+extern "C" int ug_model_set(ug_context *ctx, const float *vertexlist, int num_vertices, const int *facelist, int num_faces,
+                            const int *materiallist_index, const float *materiallist, int num_materials)
+{
+	if (!ctx || !vertexlist || !facelist || num_vertices <= 0 || num_faces <= 0) return ug_fail(ctx, UG_ERR_ARG, "ug_model_set: bad arguments");
+	for (size_t i = 0; i < 3 * (size_t)num_faces; i++)
+		if (facelist[i] < 0 || facelist[i] >= num_vertices) return ug_fail(ctx, UG_ERR_ARG, "face %zu references vertex %d (have %d)", i / 3, facelist[i], num_vertices);
+	UG_CUDA(ctx, cudaSetDevice(ctx->device));
+	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ctx->h_vertexlist.assign(vertexlist, vertexlist + 3 * (size_t)num_vertices);
+	ctx->h_facelist.assign(facelist, facelist + 3 * (size_t)num_faces);
+	if (materiallist_index) ctx->h_materiallist_index.assign(materiallist_index, materiallist_index + num_faces);
+	else ctx->h_materiallist_index.assign(num_faces, -1);
+	if (materiallist && num_materials > 0) ctx->h_materiallist.assign(materiallist, materiallist + (size_t)UG_MATERIAL_SIZE * num_materials);
+	else { ctx->h_materiallist.clear(); num_materials = 0; }
+	ctx->num_vertices = num_vertices; ctx->num_faces = num_faces; ctx->num_materials = num_materials;
+	UG_CUDA(ctx, dmalloc(&ctx->d_vertexlist, 3 * (size_t)num_vertices + 4));
+	UG_CUDA(ctx, dmalloc(&ctx->d_facelist, 3 * (size_t)num_faces));
+	UG_CUDA(ctx, dmalloc(&ctx->d_materiallist_index, (size_t)num_faces));
+	UG_CUDA(ctx, dmalloc(&ctx->d_materiallist, (size_t)UG_MATERIAL_SIZE * (num_materials ? num_materials : 1)));
+	UG_CUDA(ctx, cudaMemcpy(ctx->d_vertexlist, ctx->h_vertexlist.data(), sizeof(float) * 3 * (size_t)num_vertices, cudaMemcpyHostToDevice));
+	UG_CUDA(ctx, cudaMemcpy(ctx->d_facelist, ctx->h_facelist.data(), sizeof(int) * 3 * (size_t)num_faces, cudaMemcpyHostToDevice));
+	UG_CUDA(ctx, cudaMemcpy(ctx->d_materiallist_index, ctx->h_materiallist_index.data(), sizeof(int) * (size_t)num_faces, cudaMemcpyHostToDevice));
+	if (num_materials)
+		UG_CUDA(ctx, cudaMemcpy(ctx->d_materiallist, ctx->h_materiallist.data(), sizeof(float) * UG_MATERIAL_SIZE * (size_t)num_materials, cudaMemcpyHostToDevice));
+	dfree(ctx->d_vertex_orig_list);
+	ctx->size_orig_list = ctx->offset_orig_list = 0;
+	if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+	ctx->frame_valid = false;
+	return UG_OK;
+}
+
+extern "C" int ug_model_load(ug_context *ctx, const char *obj_path, const char *material_file)
+{
+	if (!ctx || !obj_path) return ug_fail(ctx, UG_ERR_ARG, "ug_model_load: bad arguments");
+	int nv = 0, nf = 0, nm = 0;
+	std::vector<float> mats;
+	/* per_app_funcs.h:33-34: materials first, then the model */
+	if (material_file) {
+		if (ug_material_parse(material_file, &nm, nullptr) != UG_OK) return ug_fail(ctx, UG_ERR_IO, "cannot read material file %s", material_file);
+		mats.resize((size_t)UG_MATERIAL_SIZE * (nm ? nm : 1));
+		ug_material_parse(material_file, &nm, mats.data());
+	}
+	if (ug_obj_parse(obj_path, &nv, &nf, nullptr, nullptr, nullptr) != UG_OK) return ug_fail(ctx, UG_ERR_IO, "cannot read %s", obj_path);
+	if (nv <= 0 || nf <= 0) return ug_fail(ctx, UG_ERR_IO, "%s: %d vertices, %d faces", obj_path, nv, nf);
+	std::vector<float> V(3 * (size_t)nv);
+	std::vector<int> F(3 * (size_t)nf), M(nf);
+	ug_obj_parse(obj_path, &nv, &nf, V.data(), F.data(), M.data());
+	return ug_model_set(ctx, V.data(), nv, F.data(), nf, M.data(), nm ? mats.data() : nullptr, nm);
+}
+
+extern "C" int ug_model_init_orig_list(ug_context *ctx, int vertices_size, int vertices_offset)
+{
+	if (!ctx || ctx->num_vertices <= 0) return ug_fail(ctx, UG_ERR_ARG, "init_orig_list: no model");
+	if (vertices_size < 0 || vertices_offset < 0 || vertices_offset + vertices_size > ctx->num_vertices)
+		return ug_fail(ctx, UG_ERR_ARG, "init_orig_list: range [%d,+%d) outside %d vertices", vertices_offset, vertices_size, ctx->num_vertices);
+	UG_CUDA(ctx, cudaSetDevice(ctx->device));
+	UG_CUDA(ctx, dmalloc(&ctx->d_vertex_orig_list, 3 * (size_t)vertices_size + 4));
+	UG_CUDA(ctx, cudaMemcpy(ctx->d_vertex_orig_list, ctx->h_vertexlist.data() + 3 * (size_t)vertices_offset, sizeof(float) * 3 * (size_t)vertices_size,
+	                        cudaMemcpyHostToDevice));
+	ctx->size_orig_list = vertices_size;
+	ctx->offset_orig_list = vertices_offset;
+	if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+	return UG_OK;
+}
+
+static void set_rotation(ug_context *ctx, float rot)
+{
+	ctx->h_fc->rot_cos = cosf(rot); /* glibc, like the host-compiled reference (transformation_kernel.cu:14-15) */
+	ctx->h_fc->rot_sin = sinf(rot);
+}
+
+static int upload_consts(ug_context *ctx)
+{
+	UG_CUDA(ctx, cudaMemcpyAsync(ctx->d_fc, ctx->h_fc, sizeof(FrameConst), cudaMemcpyHostToDevice, ctx->stream));
+	return UG_OK;
+}
+
+extern "C" int ug_model_rotate_bunny(ug_context *ctx, float rot_factor)
+{
+	if (!ctx || !ctx->d_vertex_orig_list) return ug_fail(ctx, UG_ERR_ARG, "rotate_bunny: init_orig_list not called");
+	UG_CUDA(ctx, cudaSetDevice(ctx->device));
+	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); /* the pinned constant block is about to be rewritten */
+	set_rotation(ctx, rot_factor);
+	int rc = upload_consts(ctx);
+	if (rc) return rc;
+	ugk_transform(ctx->stream, ctx->d_vertexlist, ctx->d_vertex_orig_list, ctx->size_orig_list, ctx->offset_orig_list, ctx->d_fc, ctx->num_sms);
+	UG_CUDA(ctx, cudaGetLastError());
+	return UG_OK;
+}
+
+/* ------------------------------------------------------------------ screen / strip */
+static void update_geometry(ug_context *ctx)
+{
+	ctx->nbx = ctx->W / UG_TILE;
+	ctx->nby = ctx->H / UG_TILE;
+	const int sc = ctx->strip_count > 0 ? ctx->strip_count : 1;
+	ctx->gy_lo = (int)((long long)ctx->nby * ctx->strip_index / sc);
+	const int hi = (int)((long long)ctx->nby * (ctx->strip_index + 1) / sc);
+	ctx->gy_cnt = hi - ctx->gy_lo;
+	ctx->C_cam = ctx->nbx * ctx->gy_cnt;
+	ctx->C_light = ctx->nbx * ctx->nby;
+	ctx->N = ctx->W * ctx->gy_cnt * UG_TILE;
+}
+
+extern "C" int ug_set_screen(ug_context *ctx, int width, int height, float fovy)
+{
+	if (!ctx || width <= 0 || height <= 0 || width % UG_TILE || height % UG_TILE || width / UG_TILE > 65535 || height / UG_TILE > 65535)
+		return ug_fail(ctx, UG_ERR_ARG, "screen %dx%d must be positive multiples of %d", width, height, UG_TILE);
+	if (ctx->W == width && ctx->H == height && ctx->fovy == fovy) return UG_OK;
+	ctx->W = width; ctx->H = height; ctx->fovy = fovy;
+	update_geometry(ctx);
+	ctx->frame_valid = false;
+	return UG_OK;
+}
+
+extern "C" int ug_set_strip(ug_context *ctx, int strip_index, int strip_count)
+{
+	if (!ctx || strip_count <= 0 || strip_index < 0 || strip_index >= strip_count) return ug_fail(ctx, UG_ERR_ARG, "bad strip %d/%d", strip_index, strip_count);
+	if (ctx->strip_index == strip_index && ctx->strip_count == strip_count) return UG_OK;
+	ctx->strip_index = strip_index; ctx->strip_count = strip_count;
+	if (ctx->W > 0) update_geometry(ctx);
+	ctx->frame_valid = false;
+	return UG_OK;
+}
+
+/* ------------------------------------------------------------------ stage sequencing */
+struct Launches { int n = 0; };
+
+/* FrustumGrid::buildGrid, frustum_grid.h:210-366, on stream s */
+static void enqueue_grid(ug_context *ctx, cudaStream_t s, const ViewConst *vc, GridBuffers &g, Launches &L)
+{
+	const int sms = ctx->num_sms;
+	ugk_setup_bin(s, vc, ctx->d_facelist, ctx->d_vertexlist, g.T, g, sms);                              L.n += 1;
+	ugk_scan_counts(s, g, sms);                                                                         L.n += 1;
+	ugk_emit_pairs(s, vc, g, sms);                                                                      L.n += 1;
+	g.final_buf = ugk_radix_sort_pairs(s, g.keys, g.vals, g.counters, g.cap, g.key_bits, g.sort, sms, &L.n);
+	ugk_cell_offsets(s, g, sms);                                                                        L.n += 1;
+}
+
+/* main.cu:148-203 for one light, after its ViewConst is resident: ray->cell map, light grid, regroup, shadow rays */
+static void enqueue_light_grid(ug_context *ctx, cudaStream_t s, int l, Launches &L)
+{
+	enqueue_grid(ctx, s, &ctx->d_fc->light[l], ctx->light_grid[l], L);
+}
+static void enqueue_light_rays(ug_context *ctx, cudaStream_t s, int l, Launches &L)
+{
+	LightRays &r = ctx->rays[l];
+	const int sms = ctx->num_sms, C = ctx->C_light;
+	cudaMemsetAsync(r.span, 0, sizeof(u32) * ((size_t)C + 1), s);
+	cudaMemsetAsync(r.cursor, 0, sizeof(u32) * ((size_t)C + 1), s);
+	ugk_map_rays(s, ctx->d_fc, l, ctx->d_t, r.cell, r.span, ctx->N, sms);                               L.n += 1;
+	ugk_exclusive_scan(s, r.span, r.offset, (size_t)C + 1, r.scan_state, r.scan_tiles, sms);            L.n += 1;
+	ugk_scatter_rays(s, r.cell, r.offset, r.cursor, r.pix, ctx->N, sms);                                L.n += 1;
+	ugk_shadow(s, ctx->d_fc, l, ctx->light_grid[l], r.pix, r.span, r.offset, ctx->d_t, ctx->d_shadowed, C, sms); L.n += 1;
+}
+
+static void stage_mark(ug_context *ctx, int &k, bool on)
+{
+	if (on) cudaEventRecord(ctx->ev_stage[k++], ctx->stream);
+}
+
+/* the whole frame; `parallel` forks the light-grid builds onto side streams */
+static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool parallel, bool stage_events, Launches &L)
+{
+	cudaStream_t s = ctx->stream;
+	const int sms = ctx->num_sms, nl = p->num_lights;
+	const bool full = (p->flags & UG_FLAG_FULL_BUFFERS) != 0;
+	int k = 0;
+	UG_CUDA(ctx, cudaMemcpyAsync(ctx->d_fc, ctx->h_fc, sizeof(FrameConst), cudaMemcpyHostToDevice, s));
+	stage_mark(ctx, k, stage_events); /* 0 */
+	if (p->transform && ctx->d_vertex_orig_list) {
+		ugk_transform(s, ctx->d_vertexlist, ctx->d_vertex_orig_list, ctx->size_orig_list, ctx->offset_orig_list, ctx->d_fc, sms);
+		L.n += 1;
+	}
+	stage_mark(ctx, k, stage_events); /* 1: transform done */
+	if (parallel && nl > 0) {
+		UG_CUDA(ctx, cudaEventRecord(ctx->ev_fork, s));
+		for (int l = 0; l < nl; l++) {
+			UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side[l], ctx->ev_fork, 0));
+			enqueue_light_grid(ctx, ctx->side[l], l, L);
+		}
+	}
+	enqueue_grid(ctx, s, &ctx->d_fc->cam, ctx->cam_grid, L);
+	stage_mark(ctx, k, stage_events); /* 2: camera grid done */
+	ugk_trace(s, ctx->d_fc, ctx->cam_grid, ctx->d_t, ctx->d_id, ctx->d_shadowed, full ? ctx->d_normal : nullptr, full ? ctx->d_dir : nullptr, ctx->C_cam, sms);
+	L.n += 1;
+	stage_mark(ctx, k, stage_events); /* 3: primary rays done */
+	if (parallel && nl > 0) {
+		UG_CUDA(ctx, cudaEventRecord(ctx->ev_trace, s));
+		for (int l = 0; l < nl; l++) {
+			UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side[l], ctx->ev_trace, 0));
+			enqueue_light_rays(ctx, ctx->side[l], l, L);
+			UG_CUDA(ctx, cudaEventRecord(ctx->ev_join[l], ctx->side[l]));
+			UG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join[l], 0));
+		}
+	} else {
+		for (int l = 0; l < nl; l++) {
+			enqueue_light_grid(ctx, s, l, L);
+			stage_mark(ctx, k, stage_events && l == nl - 1); /* 4: light grids (last light's mark) */
+			enqueue_light_rays(ctx, s, l, L);
+		}
+	}
+	stage_mark(ctx, k, stage_events); /* 4 or 5: shadows done */
+	ugk_shade(s, ctx->d_fc, ctx->d_t, ctx->d_id, ctx->d_shadowed, ctx->cam_grid.tri_rec, ctx->d_materiallist_index, ctx->d_materiallist, ctx->num_materials,
+	          ctx->d_rgb, ctx->d_matid, ctx->N, 1, sms);
+	L.n += 1;
+	stage_mark(ctx, k, stage_events);
+	UG_CUDA(ctx, cudaGetLastError());
+	return UG_OK;
+}
+
+/* fill the pinned constant block from the frame parameters (host math only) */
+static int prepare_frame(ug_context *ctx, const ug_frame_params *p)
+{
+	if (!p) return ug_fail(ctx, UG_ERR_ARG, "null frame params");
+	if (p->num_lights < 0 || p->num_lights > UG_MAX_LIGHTS) return ug_fail(ctx, UG_ERR_ARG, "num_lights %d not in [0,%d]", p->num_lights, UG_MAX_LIGHTS);
+	int rc = ug_set_screen(ctx, p->width, p->height, p->fovy);
+	if (rc) return rc;
+	rc = ug_set_strip(ctx, p->strip_count > 0 ? p->strip_index : 0, p->strip_count > 0 ? p->strip_count : 1);
+	if (rc) return rc;
+	rc = ensure_buffers(ctx, p->num_lights, (p->flags & UG_FLAG_FULL_BUFFERS) != 0);
+	if (rc) return rc;
+	/* the previous frame may still be reading the pinned block through its H2D copy */
+	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	FrameConst *fc = ctx->h_fc;
+	ug_camera cam;
+	memset(&cam, 0, sizeof(cam));
+	ug_camera_setCameraCenter(&cam, p->eye[0], p->eye[1], p->eye[2]);
+	ug_camera_setCameraLookAt(&cam, p->look[0], p->look[1], p->look[2]);
+	ug_camera_setCameraUp(&cam, p->up[0], p->up[1], p->up[2]);
+	ug_camera_setNearFar(&cam, p->nearPlane, p->farPlane);
+	cam.fovy = p->fovy;
+	cam.aspect = (float)p->width / (float)p->height; /* camera.h:137 */
+	ug_camera_adjustCameraAndPosition(&cam);
+	ugh_view_const(&fc->cam, &cam, ctx->W, ctx->H, ctx->nbx, ctx->nby, ctx->gy_lo, ctx->gy_cnt);
+	memcpy(fc->shade_mv, cam.modelview_matrix, sizeof(fc->shade_mv));
+	for (int l = 0; l < p->num_lights; l++) {
+		ug_camera lc;
+		memset(&lc, 0, sizeof(lc));
+		ug_camera_setCameraCenter(&lc, p->lights[l].pos[0], p->lights[l].pos[1], p->lights[l].pos[2]);
+		ug_camera_setCameraLookAt(&lc, p->lights[l].look[0], p->lights[l].look[1], p->lights[l].look[2]);
+		ug_camera_setCameraUp(&lc, p->lights[l].up[0], p->lights[l].up[1], p->lights[l].up[2]);
+		ug_camera_setNearFar(&lc, p->nearPlane, p->farPlane);
+		lc.fovy = p->fovy;
+		lc.aspect = 1.0f;
+		ug_camera_adjustCameraAndPosition(&lc);
+		ugh_view_const(&fc->light[l], &lc, ctx->W, ctx->H, ctx->nbx, ctx->nby, 0, ctx->nby);
+		for (int k = 0; k < 3; k++) fc->light_pos[3 * l + k] = p->lights[l].pos[k];
+		/* shading runs with the LAST light camera's modelview resident in dd_camcoords (main.cu:205-211) */
+		memcpy(fc->shade_mv, lc.modelview_matrix, sizeof(fc->shade_mv));
+	}
+	for (int l = p->num_lights; l < UG_MAX_LIGHTS; l++)
+		for (int k = 0; k < 3; k++) fc->light_pos[3 * l + k] = 0.0f;
+	fc->num_lights = p->num_lights;
+	ctx->num_lights = p->num_lights;
+	set_rotation(ctx, p->rot_factor);
+	return UG_OK;
+}
+
+static unsigned long long frame_key(const ug_context *ctx, const ug_frame_params *p)
+{
+	unsigned long long k = 1469598103934665603ull;
+	auto mix = [&](unsigned long long v) { k = (k ^ v) * 1099511628211ull; };
+	mix((unsigned long long)ctx->W); mix((unsigned long long)ctx->H); mix((unsigned long long)ctx->gy_lo); mix((unsigned long long)ctx->gy_cnt);
+	mix((unsigned long long)ctx->num_faces); mix((unsigned long long)p->num_lights); mix((unsigned long long)(p->flags & UG_FLAG_FULL_BUFFERS));
+	mix((unsigned long long)(p->transform && ctx->d_vertex_orig_list ? 1 : 0)); mix((unsigned long long)ctx->cam_grid.cap);
+	for (int l = 0; l < p->num_lights; l++) mix((unsigned long long)ctx->light_grid[l].cap);
+	mix((unsigned long long)(uintptr_t)ctx->stream);
+	return k;
+}
+
+static int run_frame_once(ug_context *ctx, const ug_frame_params *p)
+{
+	const bool stage_events = (p->flags & UG_FLAG_STAGE_EVENTS) != 0;
+	const bool use_graph = !(p->flags & UG_FLAG_NO_GRAPH) && !stage_events;
+	if (use_graph) {
+		const unsigned long long key = frame_key(ctx, p);
+		if (!ctx->graph_exec || ctx->graph_key != key) {
+			if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+			cudaGraph_t graph = nullptr;
+			Launches L;
+			UG_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+			int rc = enqueue_frame(ctx, p, true, false, L);
+			cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+			if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+			if (e != cudaSuccess) return ug_fail(ctx, UG_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+			e = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+			cudaGraphDestroy(graph);
+			if (e != cudaSuccess) return ug_fail(ctx, UG_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+			ctx->graph_key = key;
+			ctx->graph_launches = L.n;
+		}
+		UG_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
+		UG_CUDA(ctx, cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+		UG_CUDA(ctx, cudaEventRecord(ctx->ev_t1, ctx->stream));
+		ctx->stats.kernel_launches = ctx->graph_launches;
+	} else {
+		Launches L;
+		UG_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
+		int rc = enqueue_frame(ctx, p, !stage_events, stage_events, L);
+		if (rc) return rc;
+		UG_CUDA(ctx, cudaEventRecord(ctx->ev_t1, ctx->stream));
+		ctx->stats.kernel_launches = L.n;
+	}
+	ctx->frame_valid = true;
+	return UG_OK;
+}
+
+/* after a synchronise: did any pair arena overflow?  If so grow it (the caller re-runs the frame). */
+static int check_overflow(ug_context *ctx, int num_lights, bool *grew)
+{
+	*grew = false;
+	GridBuffers *gs[1 + UG_MAX_LIGHTS];
+	int n = 0;
+	gs[n++] = &ctx->cam_grid;
+	for (int l = 0; l < num_lights; l++) gs[n++] = &ctx->light_grid[l];
+	for (int i = 0; i < n; i++) {
+		u32 c[4] = {0, 0, 0, 0};
+		UG_CUDA(ctx, cudaMemcpy(c, gs[i]->counters, sizeof(c), cudaMemcpyDeviceToHost));
+		if (c[1]) {
+			const size_t want = (size_t)c[2] + (size_t)c[2] / 4 + 1024;
+			int rc = alloc_grid(ctx, *gs[i], gs[i]->T, gs[i]->C, want);
+			if (rc) return rc;
+			*grew = true;
+		}
+	}
+	if (*grew && ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+	return UG_OK;
+}
+
+extern "C" int ug_render_frame(ug_context *ctx, const ug_frame_params *p)
+{
+	if (!ctx) return UG_ERR_ARG;
+	int rc = prepare_frame(ctx, p);
+	if (rc) return rc;
+	ctx->stats.overflowed = 0;
+	return run_frame_once(ctx, p);
+}
+
+extern "C" int ug_render_frame_host(ug_context *ctx, const ug_frame_params *p, uint8_t *host_rgb)
+{
+	if (!ctx || !host_rgb) return ug_fail(ctx, UG_ERR_ARG, "ug_render_frame_host: null argument");
+	int rc = prepare_frame(ctx, p);
+	if (rc) return rc;
+	ctx->stats.overflowed = 0;
+	for (int attempt = 0; attempt < 3; attempt++) {
+		rc = run_frame_once(ctx, p);
+		if (rc) return rc;
+		/* main.cu:245: image back to the host (pinned staging, then the caller's buffer) */
+		UG_CUDA(ctx, cudaMemcpyAsync(ctx->h_rgb_pinned, ctx->d_rgb, 3 * (size_t)ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
+		UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		bool grew = false;
+		rc = check_overflow(ctx, p->num_lights, &grew);
+		if (rc) return rc;
+		if (!grew) {
+			memcpy(host_rgb, ctx->h_rgb_pinned, 3 * (size_t)ctx->N);
+			return UG_OK;
+		}
+		ctx->stats.overflowed = 1;
+	}
+	return ug_fail(ctx, UG_ERR_OVERFLOW, "pair arena still too small after growing");
+}
+
+/* ------------------------------------------------------------------ per_frame_funcs.h, call by call */
+extern "C" int ug_update_light_position(ug_context *ctx, const float *xyz, int num_lights)
+{
+	if (!ctx || !xyz || num_lights < 0 || num_lights > UG_MAX_LIGHTS) return ug_fail(ctx, UG_ERR_ARG, "updateLightPosition: bad arguments");
+	UG_CUDA(ctx, cudaSetDevice(ctx->device));
+	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	for (int i = 0; i < 3 * UG_MAX_LIGHTS; i++) ctx->h_fc->light_pos[i] = i < 3 * num_lights ? xyz[i] : 0.0f;
+	ctx->h_fc->num_lights = num_lights;
+	return upload_consts(ctx);
+}
+
+extern "C" int ug_fill_coordinates_data(ug_context *ctx, const ug_camera *cam)
+{
+	if (!ctx || !cam) return ug_fail(ctx, UG_ERR_ARG, "fillCoordinatesData: bad arguments");
+	if (ctx->W <= 0) return ug_fail(ctx, UG_ERR_ARG, "fillCoordinatesData: ug_set_screen first");
+	UG_CUDA(ctx, cudaSetDevice(ctx->device));
+	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ugh_view_const(&ctx->h_fc->cam, cam, ctx->W, ctx->H, ctx->nbx, ctx->nby, ctx->gy_lo, ctx->gy_cnt);
+	memcpy(ctx->h_fc->shade_mv, cam->modelview_matrix, sizeof(ctx->h_fc->shade_mv));
+	return upload_consts(ctx);
+}
+
+extern "C" int ug_build_frustum_grid(ug_context *ctx)
+{
+	if (!ctx) return UG_ERR_ARG;
+	int rc = ensure_buffers(ctx, ctx->num_lights, ctx->full_alloc);
+	if (rc) return rc;
+	for (int attempt = 0; attempt < 3; attempt++) {
+		Launches L;
+		enqueue_grid(ctx, ctx->stream, &ctx->d_fc->cam, ctx->cam_grid, L);
+		UG_CUDA(ctx, cudaGetLastError());
+		UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		bool grew = false;
+		rc = check_overflow(ctx, 0, &grew);
+		if (rc) return rc;
+		if (!grew) return UG_OK;
+	}
+	return ug_fail(ctx, UG_ERR_OVERFLOW, "pair arena still too small after growing");
+}
+
+extern "C" int ug_trace(ug_context *ctx)
+{
+	if (!ctx || !ctx->cam_grid.tri_rec) return ug_fail(ctx, UG_ERR_ARG, "trace: build_frustum_grid first");
+	int rc = ensure_buffers(ctx, ctx->num_lights, true);
+	if (rc) return rc;
+	ugk_trace(ctx->stream, ctx->d_fc, ctx->cam_grid, ctx->d_t, ctx->d_id, ctx->d_shadowed, ctx->d_normal, ctx->d_dir, ctx->C_cam, ctx->num_sms);
+	UG_CUDA(ctx, cudaGetLastError());
+	return UG_OK;
+}
+
+extern "C" int ug_shadow_pass(ug_context *ctx, int light_id, const ug_camera *light_cam)
+{
+	if (!ctx || !light_cam || light_id < 0 || light_id >= UG_MAX_LIGHTS) return ug_fail(ctx, UG_ERR_ARG, "shadow pass: bad arguments");
+	if (!ctx->d_t) return ug_fail(ctx, UG_ERR_ARG, "shadow pass: trace first");
+	if (ctx->num_lights <= light_id) ctx->num_lights = light_id + 1;
+	int rc = ensure_buffers(ctx, ctx->num_lights, ctx->full_alloc);
+	if (rc) return rc;
+	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ugh_view_const(&ctx->h_fc->light[light_id], light_cam, ctx->W, ctx->H, ctx->nbx, ctx->nby, 0, ctx->nby);
+	memcpy(ctx->h_fc->shade_mv, light_cam->modelview_matrix, sizeof(ctx->h_fc->shade_mv)); /* fillCoordinatesData with the light camera */
+	rc = upload_consts(ctx);
+	if (rc) return rc;
+	for (int attempt = 0; attempt < 3; attempt++) {
+		Launches L;
+		enqueue_light_grid(ctx, ctx->stream, light_id, L);
+		UG_CUDA(ctx, cudaGetLastError());
+		UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		bool grew = false;
+		GridBuffers &g = ctx->light_grid[light_id];
+		u32 c[4];
+		UG_CUDA(ctx, cudaMemcpy(c, g.counters, sizeof(c), cudaMemcpyDeviceToHost));
+		if (c[1]) {
+			rc = alloc_grid(ctx, g, g.T, g.C, (size_t)c[2] + (size_t)c[2] / 4 + 1024);
+			if (rc) return rc;
+			grew = true;
+		}
+		if (!grew) {
+			enqueue_light_rays(ctx, ctx->stream, light_id, L);
+			UG_CUDA(ctx, cudaGetLastError());
+			return UG_OK;
+		}
+	}
+	return ug_fail(ctx, UG_ERR_OVERFLOW, "pair arena still too small after growing");
+}
+
+extern "C" int ug_simple_shade(ug_context *ctx)
+{
+	if (!ctx || !ctx->d_t) return ug_fail(ctx, UG_ERR_ARG, "simpleShade: trace first");
+	ugk_shade(ctx->stream, ctx->d_fc, ctx->d_t, ctx->d_id, ctx->d_shadowed, ctx->cam_grid.tri_rec, ctx->d_materiallist_index, ctx->d_materiallist,
+	          ctx->num_materials, ctx->d_rgb, ctx->d_matid, ctx->N, 0, ctx->num_sms);
+	UG_CUDA(ctx, cudaGetLastError());
+	ctx->frame_valid = true;
+	return UG_OK;
+}
+
+extern "C" int ug_add_shadows(ug_context *ctx)
+{
+	if (!ctx || !ctx->d_rgb) return ug_fail(ctx, UG_ERR_ARG, "add_shadows: shade first");
+	ugk_add_shadows(ctx->stream, ctx->d_shadowed, ctx->d_rgb, ctx->N, ctx->num_sms);
+	UG_CUDA(ctx, cudaGetLastError());
+	return UG_OK;
+}
+
+/* ------------------------------------------------------------------ read-back */
+static int buffer_info(ug_context *ctx, int buffer, int index, void **ptr, size_t *bytes)
+{
+	const size_t N = (size_t)ctx->N;
+	u32 c[4] = {0, 0, 0, 0};
+	GridBuffers *g = nullptr;
+	if (buffer == UG_BUF_CAM_VALUES || buffer == UG_BUF_CAM_SPAN || buffer == UG_BUF_CAM_OFFSET || buffer == UG_BUF_SIZELIST) g = &ctx->cam_grid;
+	if (buffer == UG_BUF_LIGHT_VALUES || buffer == UG_BUF_LIGHT_SPAN || buffer == UG_BUF_LIGHT_OFFSET) {
+		if (index < 0 || index >= UG_MAX_LIGHTS) return ug_fail(ctx, UG_ERR_ARG, "light index %d", index);
+		g = &ctx->light_grid[index];
+	}
+	if (g && !g->tri_rec) return ug_fail(ctx, UG_ERR_ARG, "buffer %d not built yet", buffer);
+	switch (buffer) {
+	case UG_BUF_VERTEXLIST: *ptr = ctx->d_vertexlist; *bytes = sizeof(float) * 3 * (size_t)ctx->num_vertices; break;
+	case UG_BUF_CAM_VALUES:
+	case UG_BUF_LIGHT_VALUES:
+		UG_CUDA(ctx, cudaMemcpy(c, g->counters, sizeof(c), cudaMemcpyDeviceToHost));
+		*ptr = g->vals[g->final_buf]; *bytes = sizeof(u32) * (size_t)c[0];
+		break;
+	case UG_BUF_CAM_SPAN:
+	case UG_BUF_LIGHT_SPAN: *ptr = g->span; *bytes = sizeof(u32) * (size_t)g->C; break;
+	case UG_BUF_CAM_OFFSET:
+	case UG_BUF_LIGHT_OFFSET: *ptr = g->offset; *bytes = sizeof(u32) * (size_t)g->C; break;
+	case UG_BUF_SIZELIST: *ptr = g->count; *bytes = sizeof(u32) * (size_t)g->T; break;
+	case UG_BUF_T: *ptr = ctx->d_t; *bytes = sizeof(float) * N; break;
+	case UG_BUF_ID: *ptr = ctx->d_id; *bytes = sizeof(int) * N; break;
+	case UG_BUF_NORMAL: *ptr = ctx->d_normal; *bytes = sizeof(float) * 3 * N; break;
+	case UG_BUF_DIR: *ptr = ctx->d_dir; *bytes = sizeof(float) * 3 * N; break;
+	case UG_BUF_SHADOWED: *ptr = ctx->d_shadowed; *bytes = sizeof(int) * N; break;
+	case UG_BUF_RGB: *ptr = ctx->d_rgb; *bytes = 3 * N; break;
+	case UG_BUF_LIGHT_CELL:
+		if (index < 0 || index >= UG_MAX_LIGHTS) return ug_fail(ctx, UG_ERR_ARG, "light index %d", index);
+		*ptr = ctx->rays[index].cell; *bytes = sizeof(u32) * N;
+		break;
+	default: return ug_fail(ctx, UG_ERR_ARG, "unknown buffer %d", buffer);
+	}
+	if (!*ptr) return ug_fail(ctx, UG_ERR_ARG, "buffer %d not allocated (flags?)", buffer);
+	return UG_OK;
+}
+
+extern "C" int ug_device_ptr(ug_context *ctx, int buffer, int index, void **ptr, size_t *bytes)
+{
+	if (!ctx || !ptr || !bytes) return UG_ERR_ARG;
+	UG_CUDA(ctx, cudaSetDevice(ctx->device));
+	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return buffer_info(ctx, buffer, index, ptr, bytes);
+}
+
+extern "C" int ug_read(ug_context *ctx, int buffer, int index, void *dst, size_t bytes)
+{
+	if (!ctx || !dst) return UG_ERR_ARG;
+	void *ptr = nullptr;
+	size_t have = 0;
+	int rc = ug_device_ptr(ctx, buffer, index, &ptr, &have);
+	if (rc) return rc;
+	if (bytes > have) return ug_fail(ctx, UG_ERR_ARG, "buffer %d holds %zu bytes, %zu requested", buffer, have, bytes);
+	UG_CUDA(ctx, cudaMemcpy(dst, ptr, bytes, cudaMemcpyDeviceToHost));
+	return UG_OK;
+}
+
+extern "C" int ug_get_stats(ug_context *ctx, ug_stats *out)
+{
+	if (!ctx || !out) return UG_ERR_ARG;
+	UG_CUDA(ctx, cudaSetDevice(ctx->device));
+	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ug_stats &s = ctx->stats;
+	s.num_faces = ctx->num_faces; s.num_vertices = ctx->num_vertices; s.num_materials = ctx->num_materials;
+	s.width = ctx->W; s.height = ctx->gy_cnt * UG_TILE; s.num_cells = ctx->C_cam; s.num_pixels = ctx->N;
+	s.pair_capacity = (unsigned)ctx->cam_grid.cap;
+	u32 c[4] = {0, 0, 0, 0};
+	if (ctx->cam_grid.counters) {
+		UG_CUDA(ctx, cudaMemcpy(c, ctx->cam_grid.counters, sizeof(c), cudaMemcpyDeviceToHost));
+		s.cam_pairs = c[0];
+		if (c[1]) s.overflowed = 1;
+	}
+	for (int l = 0; l < UG_MAX_LIGHTS; l++) {
+		s.light_pairs[l] = 0;
+		if (l < ctx->num_lights && ctx->light_grid[l].counters) {
+			UG_CUDA(ctx, cudaMemcpy(c, ctx->light_grid[l].counters, sizeof(c), cudaMemcpyDeviceToHost));
+			s.light_pairs[l] = c[0];
+			if (c[1]) s.overflowed = 1;
+		}
+	}
+	if (ctx->frame_valid) {
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1) == cudaSuccess) s.ms_frame = ms;
+		else cudaGetLastError();
+	}
+	*out = s;
+	return UG_OK;
+}
+
+/* stage timings of the last UG_FLAG_STAGE_EVENTS frame: ms between consecutive marks */
+extern "C" int ug_stage_times(ug_context *ctx, float *out, int max)
+{
+	if (!ctx || !out) return UG_ERR_ARG;
+	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	int n = 0;
+	for (int k = 0; k + 1 < 24 && n < max; k++) {
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, ctx->ev_stage[k], ctx->ev_stage[k + 1]) != cudaSuccess) { cudaGetLastError(); break; }
+		out[n++] = ms;
+	}
+	return n;
+}
+
+extern "C" int ug_write_ppm(ug_context *ctx, const char *filename)
+{
+	if (!ctx || !filename || !ctx->d_rgb) return ug_fail(ctx, UG_ERR_ARG, "writePPM: nothing rendered");
+	const size_t bytes = 3 * (size_t)ctx->N;
+	std::vector<unsigned char> img(bytes);
+	int rc = ug_read(ctx, UG_BUF_RGB, 0, img.data(), bytes);
+	if (rc) return rc;
+	FILE *fp = fopen(filename, "w");
+	if (!fp) return ug_fail(ctx, UG_ERR_IO, "cannot open %s", filename);
+	/* per_app_funcs.h:39-66: ASCII P3, a newline before every image row, buffer order (bottom row first) */
+	fprintf(fp, "P3\n%d %d\n%d\n", ctx->W, ctx->gy_cnt * UG_TILE, 255);
+	for (size_t i = 0; i < bytes; i++) {
+		if (i % (3 * (size_t)ctx->W) == 0) fprintf(fp, "\n");
+		fprintf(fp, "%d ", (int)img[i]);
+	}
+	fprintf(fp, "\n");
+	fclose(fp);
+	return UG_OK;
+}

@@ -1,0 +1,103 @@
+/* k_common.cuh -- device helpers shared by the kernels.
+ *
+ * Arithmetic contract: results must be bit-identical to the reference's
+ * device code compiled as host C (x86-64 SSE2, no FMA).  The whole library is compiled with
+ * -fmad=false (no FFMA/DFMA contraction), IEEE division and square root (nvcc defaults
+ * -prec-div=true -prec-sqrt=true -ftz=false); evaluation order below is the reference's.
+ */
+#ifndef UG_K_COMMON_CUH
+#define UG_K_COMMON_CUH
+
+#include "ugrt_internal.h"
+
+#define UG_FULL_MASK 0xffffffffu
+
+/* main.cu.h:44-56 */
+__device__ __forceinline__ float ug_dot(float ax, float ay, float az, float bx, float by, float bz)
+{
+	return ax * bx + ay * by + az * bz; /* ((ax*bx + ay*by) + az*bz), no contraction */
+}
+__device__ __forceinline__ void ug_cross(float &dx, float &dy, float &dz, float ax, float ay, float az, float bx, float by, float bz)
+{
+	dx = ay * bz - az * by;
+	dy = az * bx - ax * bz;
+	dz = ax * by - ay * bx;
+}
+__device__ __forceinline__ void ug_normalize(float &x, float &y, float &z)
+{
+	const float l = 1.0f / sqrtf(x * x + y * y + z * z); /* NORMALIZE: 1/sqrtf, then three multiplies */
+	x *= l; y *= l; z *= l;
+}
+
+/* float -> int the way the host-compiled reference does it (x86 cvttss2si: NaN, +-inf and
+ * out-of-range give INT_MIN; PTX cvt.rzi saturates instead) - grid_kernel.cu:208-215 */
+__device__ __forceinline__ int ug_f2i(float f)
+{
+	return (f >= 2147483648.0f || f < -2147483648.0f || f != f) ? (int)0x80000000 : (int)f;
+}
+__device__ __forceinline__ int ug_d2i(double f)
+{
+	return (f >= 2147483648.0 || f < -2147483648.0 || f != f) ? (int)0x80000000 : (int)f;
+}
+
+/* grid_kernel.cu:4-11: one row of a column-major 4x4 times (x,y,z,w), summed left to right */
+__device__ __forceinline__ float ug_row(const float *m, int r, float x, float y, float z, float w)
+{
+	return m[r] * x + m[4 + r] * y + m[8 + r] * z + m[12 + r] * w;
+}
+
+/* a9: primary ray through pixel (px,py) - trace_kernel.cu:96-114 with the texture fetch done in
+ * software: CUDA linear filtering (xB = s*5-0.5, i = floor, alpha = frac, clamp), exact float weights.
+ * `lat` = the 5x5 float4 lattice, `eye` = cc[0..2]. */
+__device__ __forceinline__ void ug_primary_dir(const float *lat, float ex, float ey, float ez, int px, int py, int Wfull, int Hfull,
+                                               float &dx, float &dy, float &dz)
+{
+	float ftx = (float)px / (float)Wfull;
+	float fty = (float)py / (float)Hfull;
+	ftx = 1.0f - ftx;
+	ftx = (float)__dadd_rn(__dmul_rn((double)ftx, 0.9 - 0.1), 0.1); /* double, trace_kernel.cu:102-103 */
+	fty = (float)__dadd_rn(__dmul_rn((double)fty, 0.9 - 0.1), 0.1);
+	const float xB = ftx * 5.0f - 0.5f, yB = fty * 5.0f - 0.5f;
+	const float fi = floorf(xB), fj = floorf(yB);
+	const float a = xB - fi, b = yB - fj;
+	int i0 = (int)fi, j0 = (int)fj, i1 = i0 + 1, j1 = j0 + 1;
+	i0 = min(max(i0, 0), 4); i1 = min(max(i1, 0), 4);
+	j0 = min(max(j0, 0), 4); j1 = min(max(j1, 0), 4);
+	const float *T00 = lat + 4 * (j0 * 5 + i0), *T10 = lat + 4 * (j0 * 5 + i1);
+	const float *T01 = lat + 4 * (j1 * 5 + i0), *T11 = lat + 4 * (j1 * 5 + i1);
+	const float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
+	dx = w00 * T00[0] + w10 * T10[0] + w01 * T01[0] + w11 * T11[0];
+	dy = w00 * T00[1] + w10 * T10[1] + w01 * T01[1] + w11 * T11[1];
+	dz = w00 * T00[2] + w10 * T10[2] + w01 * T01[2] + w11 * T11[2];
+	dx -= ex; dy -= ey; dz -= ez;
+	ug_normalize(dx, dy, dz);
+}
+
+/* Per-triangle record for one ray origin O (the eye or a light): everything of Moeller-Trumbore that
+ * does not depend on the ray.  r0 = (O-v0, dot(e2,q)), r1 = (e1, 0), r2 = (e2, 0), r3 = (q = cross(O-v0,e1), 0).
+ * trace_kernel.cu:4-45 / light_kernel.cu:13-50 evaluate q and dot(e2,q) per ray from the same inputs
+ * with the same operations, so hoisting them is bit-exact. */
+struct TriRec { float4 r0, r1, r2, r3; };
+
+/* ray-dependent part; returns false on a miss, else t (signed) */
+__device__ __forceinline__ bool ug_intersect(const float4 &r0, const float4 &r1, const float4 &r2, const float4 &r3,
+                                             float dx, float dy, float dz, float &t)
+{
+	float px, py, pz;
+	ug_cross(px, py, pz, dx, dy, dz, r2.x, r2.y, r2.z);     /* pvec = dir x e2 */
+	const float det = ug_dot(r1.x, r1.y, r1.z, px, py, pz); /* e1 . pvec */
+	/* `det > -EPSILON && det < EPSILON` compares against the DOUBLE 1e-21 (main.cu.h:42).  float(1e-21)
+	 * = 0x1c971da0 lies just below it, so the double test is true exactly when |det| <= float(1e-21). */
+	if (fabsf(det) <= 1e-21f) return false;
+	const float inv = 1.0f / det;                           /* (float)(1.0/det): one correctly rounded divide */
+	const float u = ug_dot(r0.x, r0.y, r0.z, px, py, pz) * inv;
+	if (u < 0.0f || u > 1.0f) return false;
+	const float v = ug_dot(dx, dy, dz, r3.x, r3.y, r3.z) * inv;
+	if (v < 0.0f || u + v > 1.0f) return false;
+	t = r0.w * inv;
+	return true;
+}
+
+__device__ __forceinline__ u32 ug_lane() { return threadIdx.x & 31u; }
+
+#endif

@@ -1,0 +1,129 @@
+/* k_shade.cu -- K1 vertex transform (a1) and K10 shading (a19, a20).
+ *
+ *   k_transform   transformation_kernel.cu:4-18 copy_data_transform (Model::rotate_bunny, scene.h:122-139):
+ *                 pure HBM streaming, 12 B in + 12 B out per vertex; threads move float4s over the
+ *                 packed float3 array (4 vertices = 3 float4) when the sub-range is 16-byte aligned.
+ *   k_shade       shader_kernel.cu:165-221 lambertian_shade + :46-86 lambert_color_pixel, with
+ *                 shader_kernel.cu:347-359 shadow_kernel fused in (apply_shadow) so the image is
+ *                 written once.  Direction and normal are recomputed from (pixel, triangle id) with the
+ *                 reference's arithmetic instead of being read back from 24 B/pixel of buffers.
+ */
+#include "k_common.cuh"
+
+/* one vertex, transformation_kernel.cu:10-16; cos/sin come from the host (same glibc values the
+ * host-compiled reference gets; CUDA's cosf/sinf differ in the last ulp) */
+static __device__ __forceinline__ void xform(float ix, float iy, float iz, float c, float s, float &ox, float &oy, float &oz)
+{
+	const float x = (ix - 12.0f) / 12.0f;
+	const float y = (iy - 11.0f) / 12.0f;
+	const float z = (iz - 4.5f) / 12.0f;
+	ox = (x * c - y * s) * 9.0f + 14.5f;
+	oy = (x * s + y * c) * 9.0f + 13.0f;
+	oz = z * 9.0f + 4.0f;
+}
+
+__global__ void __launch_bounds__(256) k_transform_vec4(float4 *__restrict__ dst, const float4 *__restrict__ src, int groups, const FrameConst *__restrict__ fc)
+{
+	const float c = fc->rot_cos, s = fc->rot_sin;
+	for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
+		const float4 a = src[3 * (size_t)g], b = src[3 * (size_t)g + 1], d = src[3 * (size_t)g + 2];
+		float4 oa, ob, od;
+		xform(a.x, a.y, a.z, c, s, oa.x, oa.y, oa.z);
+		xform(a.w, b.x, b.y, c, s, oa.w, ob.x, ob.y);
+		xform(b.z, b.w, d.x, c, s, ob.z, ob.w, od.x);
+		xform(d.y, d.z, d.w, c, s, od.y, od.z, od.w);
+		dst[3 * (size_t)g] = oa; dst[3 * (size_t)g + 1] = ob; dst[3 * (size_t)g + 2] = od;
+	}
+}
+__global__ void __launch_bounds__(256) k_transform_scalar(float *__restrict__ dst, const float *__restrict__ src, int first, int count, const FrameConst *__restrict__ fc)
+{
+	const float c = fc->rot_cos, s = fc->rot_sin;
+	for (int v = first + blockIdx.x * blockDim.x + threadIdx.x; v < first + count; v += gridDim.x * blockDim.x)
+		xform(src[3 * (size_t)v], src[3 * (size_t)v + 1], src[3 * (size_t)v + 2], c, s, dst[3 * (size_t)v], dst[3 * (size_t)v + 1], dst[3 * (size_t)v + 2]);
+}
+
+void ugk_transform(cudaStream_t s, float *vertexlist, const float *orig, int size, int offset, const FrameConst *fc, int sms)
+{
+	if (size <= 0) return;
+	float *dst = vertexlist + 3 * (size_t)offset;
+	const bool aligned = (((uintptr_t)dst | (uintptr_t)orig) & 15u) == 0;
+	const int groups = aligned ? size / 4 : 0;
+	if (groups) k_transform_vec4<<<min((groups + 255) / 256, sms * 8), 256, 0, s>>>((float4 *)dst, (const float4 *)orig, groups, fc);
+	const int rest = size - 4 * groups;
+	if (rest) k_transform_scalar<<<min((rest + 255) / 256, sms * 8), 256, 0, s>>>(dst, orig, 4 * groups, rest, fc);
+}
+
+__global__ void __launch_bounds__(256) k_shade(const FrameConst *__restrict__ fc, const float *__restrict__ t, const int *__restrict__ id,
+                                              const int *__restrict__ shadowed, const float4 *__restrict__ rec, const int *__restrict__ mat_idx,
+                                              const float *__restrict__ mat_list, int mat_count, unsigned char *__restrict__ rgb, int *__restrict__ mat_out,
+                                              int N, int apply_shadow)
+{
+	__shared__ float s_lat[100];
+	const ViewConst &cam = fc->cam;
+	for (int i = threadIdx.x; i < 100; i += blockDim.x) s_lat[i] = cam.lattice[i];
+	__syncthreads();
+	const float *R = fc->shade_mv;
+	const float ex = cam.cc[0], ey = cam.cc[1], ez = cam.cc[2];
+	const int W = cam.W, row0 = cam.gy_lo * UG_TILE;
+	/* shader_kernel.cu:54-57: light 0 through the rotation part of the resident modelview */
+	const float l0 = fc->light_pos[0], l1 = fc->light_pos[1], l2 = fc->light_pos[2];
+	const float Lvx = R[0] * l0 + R[4] * l1 + R[8] * l2;
+	const float Lvy = R[1] * l0 + R[5] * l1 + R[9] * l2;
+	const float Lvz = R[2] * l0 + R[6] * l1 + R[10] * l2;
+	for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < N; pix += gridDim.x * blockDim.x) {
+		float cr = 0.0f, cg = 0.0f, cb = 0.0f;
+		const int tri = id[pix];
+		const int idx = (tri >= 0) ? mat_idx[tri] : -1; /* the reference reads mat_idx[-2] on a miss; ours: black */
+		if (mat_out) mat_out[pix] = idx;                /* shader_kernel.cu:176 */
+		const float tv = t[pix];
+		if (idx >= 0 && idx < mat_count && tv > 0.0f) {
+			const int pyl = pix / W, px = pix - pyl * W;
+			float dx, dy, dz;
+			ug_primary_dir(s_lat, ex, ey, ez, px, pyl + row0, W, cam.H, dx, dy, dz);
+			const float Px = ex + tv * dx, Py = ey + tv * dy, Pz = ez + tv * dz;
+			/* normal as rckernel_alpha left it: abs(normalize(cross(normalize(e1), normalize(e2)))), trace_kernel.cu:234-243 */
+			const float4 r1 = rec[4 * (size_t)tri + 1], r2 = rec[4 * (size_t)tri + 2];
+			float ax = r1.x, ay = r1.y, az = r1.z, bx = r2.x, by = r2.y, bz = r2.z, nx, ny, nz;
+			ug_normalize(ax, ay, az);
+			ug_normalize(bx, by, bz);
+			ug_cross(nx, ny, nz, ax, ay, az, bx, by, bz);
+			ug_normalize(nx, ny, nz);
+			nx = (nx < 0) ? nx * -1.0f : nx; ny = (ny < 0) ? ny * -1.0f : ny; nz = (nz < 0) ? nz * -1.0f : nz;
+			/* lambert_color_pixel */
+			const float Pvx = R[0] * Px + R[4] * Py + R[8] * Pz, Pvy = R[1] * Px + R[5] * Py + R[9] * Pz, Pvz = R[2] * Px + R[6] * Py + R[10] * Pz;
+			float Nvx = R[0] * nx + R[4] * ny + R[8] * nz, Nvy = R[1] * nx + R[5] * ny + R[9] * nz, Nvz = R[2] * nx + R[6] * ny + R[10] * nz;
+			ug_normalize(Nvx, Nvy, Nvz);
+			float ldx = Pvx - Lvx, ldy = Pvy - Lvy, ldz = Pvz - Lvz;
+			ug_normalize(ldx, ldy, ldz);
+			const float kr = mat_list[idx * UG_MATERIAL_SIZE + 3], kg = mat_list[idx * UG_MATERIAL_SIZE + 4], kb = mat_list[idx * UG_MATERIAL_SIZE + 5];
+			cr += kr * 0.5f; cg += kg * 0.5f; cb += kb * 0.5f;  /* ambient term uses the DIFFUSE colour, :180-186 */
+			float dd = ug_dot(ldx, ldy, ldz, Nvx, Nvy, Nvz);
+			if (!(dd > 0)) dd *= -1.0f;
+			if (dd > 0) { cr += kr * 1.0f * dd; cg += kg * 1.0f * dd; cb += kb * 1.0f * dd; }
+			cr = cr > 1.0f ? 1.0f : cr; cg = cg > 1.0f ? 1.0f : cg; cb = cb > 1.0f ? 1.0f : cb;
+		}
+		unsigned char r8 = (unsigned char)(cr * 255.0f), g8 = (unsigned char)(cg * 255.0f), b8 = (unsigned char)(cb * 255.0f);
+		if (apply_shadow && shadowed[pix] == 1) { r8 /= 3; g8 /= 3; b8 /= 3; } /* shader_kernel.cu:351-356 */
+		rgb[3 * (size_t)pix + 0] = r8; rgb[3 * (size_t)pix + 1] = g8; rgb[3 * (size_t)pix + 2] = b8;
+	}
+}
+
+__global__ void __launch_bounds__(256) k_add_shadows(const int *__restrict__ shadowed, unsigned char *__restrict__ rgb, int N)
+{
+	for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < N; pix += gridDim.x * blockDim.x)
+		if (shadowed[pix] == 1) {
+			rgb[3 * (size_t)pix + 0] /= 3; rgb[3 * (size_t)pix + 1] /= 3; rgb[3 * (size_t)pix + 2] /= 3;
+		}
+}
+
+void ugk_shade(cudaStream_t s, const FrameConst *fc, const float *t, const int *id, const int *shadowed, const float4 *rec, const int *mat_idx,
+               const float *mat_list, int mat_count, unsigned char *rgb, int *mat_out, int N, int apply_shadow, int sms)
+{
+	if (N <= 0) return;
+	k_shade<<<min((N + 255) / 256, sms * 8), 256, 0, s>>>(fc, t, id, shadowed, rec, mat_idx, mat_list, mat_count, rgb, mat_out, N, apply_shadow);
+}
+void ugk_add_shadows(cudaStream_t s, const int *shadowed, unsigned char *rgb, int N, int sms)
+{
+	if (N <= 0) return;
+	k_add_shadows<<<min((N + 255) / 256, sms * 8), 256, 0, s>>>(shadowed, rgb, N);
+}

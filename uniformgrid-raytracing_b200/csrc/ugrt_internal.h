@@ -1,0 +1,166 @@
+/* ugrt_internal.h -- private declarations shared by the .cu/.cpp files of libugrt.so */
+#ifndef UGRT_INTERNAL_H
+#define UGRT_INTERNAL_H
+
+#include "ugrt.h"
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+/* ---------------------------------------------------------------- device-visible constants
+ * One ViewConst per "camera" (the eye, and every light treated as a camera - main.cu:148-170).
+ * Lives in global memory and is refreshed by ONE pinned H2D copy per frame, so the captured CUDA
+ * graph never needs its kernel parameters patched. */
+struct ViewConst {
+	float cc[64];       /* dd_camcoords layout, per_frame_funcs.h:18-39 */
+	float lattice[100]; /* texdir, 5x5 float4 */
+	float tan_half;     /* tanf(FOVY*M_PI/360.0f), evaluated on the host (glibc) - misc_kernel.cu:115 */
+	float near_plane;
+	int nbx, nby;       /* cells of the full grid */
+	int gy_lo, gy_cnt;  /* owned cell rows (image strip); lights own everything */
+	int W, H;           /* full screen */
+};
+
+struct FrameConst {
+	ViewConst cam;
+	ViewConst light[UG_MAX_LIGHTS];
+	float light_pos[3 * UG_MAX_LIGHTS]; /* dd_light_position, main.cu.h:63 */
+	float shade_mv[16];                 /* the modelview resident in dd_camcoords when shading runs (last light's) */
+	float rot_cos, rot_sin;             /* cosf/sinf(rot_factor) from the host - transformation_kernel.cu:14-15 */
+	int num_lights;
+	int pad_;
+};
+
+/* ---------------------------------------------------------------- device buffers */
+struct SortScratch {
+	u32 *tile_hist = nullptr; /* [256 * G] digit-major block histograms of one radix pass */
+	u32 *tile_base = nullptr; /* their exclusive scan */
+	u64 *scan_state = nullptr; /* decoupled look-back descriptors of ugk_exclusive_scan */
+	size_t scan_tiles = 0;
+};
+
+struct GridBuffers {       /* FrustumGrid, frustum_grid.h:15-68 */
+	float4 *tri_rec = nullptr; /* [4*T]: (tvec.xyz,e2q) (e1.xyz,0) (e2.xyz,0) (qvec.xyz,0) for this view's origin */
+	uint2 *rect = nullptr;     /* [T]: gx0 | gx1<<16, gy0 | gy1<<16 (owned-row clipped) */
+	u32 *count = nullptr;      /* [T] d_sizeList */
+	u32 *scan = nullptr;       /* [T+1] exclusive; [T] = P */
+	u32 *keys[2] = {nullptr, nullptr};
+	u32 *vals[2] = {nullptr, nullptr}; /* vals[final_buf] = d_triangle_value_list */
+	u32 *span = nullptr;       /* [C] */
+	u32 *offset = nullptr;     /* [C+1] */
+	u32 *counters = nullptr;   /* [8]: 0 = P (clamped), 1 = overflow flag, 2 = P wanted */
+	SortScratch sort;
+	size_t cap = 0;            /* pair capacity */
+	int final_buf = 0;         /* which of vals[] holds the sorted list */
+	int key_bits = 0;
+	int C = 0, T = 0;
+};
+
+struct LightRays {         /* DecisionData's regroup state (decision_data.h:72-80), one per light */
+	u32 *cell = nullptr;   /* [N]   d_map[N..2N): light cell per pixel, C = outside the light frustum */
+	u32 *pix = nullptr;    /* [N]   d_map[0..N) after the regroup: pixel ids grouped by light cell */
+	u32 *span = nullptr;   /* [C+1] rays per light cell (last = outside) */
+	u32 *offset = nullptr; /* [C+2] */
+	u32 *cursor = nullptr; /* [C+1] */
+	u64 *scan_state = nullptr;
+	size_t scan_tiles = 0;
+};
+
+struct ug_context {
+	int device = 0;
+	cudaStream_t own_stream = nullptr, stream = nullptr;
+	cudaStream_t side[UG_MAX_LIGHTS] = {};
+	cudaEvent_t ev_fork = nullptr, ev_trace = nullptr, ev_join[UG_MAX_LIGHTS] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
+	cudaEvent_t ev_stage[24] = {};
+	std::string err;
+	int num_sms = 148;
+
+	/* Model (scene.h:13-57) */
+	std::vector<float> h_vertexlist, h_materiallist;
+	std::vector<int> h_facelist, h_materiallist_index;
+	float *d_vertexlist = nullptr, *d_materiallist = nullptr, *d_vertex_orig_list = nullptr;
+	int *d_facelist = nullptr, *d_materiallist_index = nullptr;
+	int num_faces = 0, num_vertices = 0, num_materials = 0;
+	int size_orig_list = 0, offset_orig_list = 0;
+
+	/* screen (main.cu.h:10-30 made runtime) */
+	int W = 0, H = 0, nbx = 0, nby = 0;
+	float fovy = 45.0f;
+	int strip_index = 0, strip_count = 1, gy_lo = 0, gy_cnt = 0;
+	int N = 0, C_cam = 0, C_light = 0; /* pixels / cells of this strip; cells of a (full) light grid */
+
+	/* frame constants */
+	FrameConst *h_fc = nullptr; /* pinned */
+	FrameConst *d_fc = nullptr;
+	int num_lights = 0;
+
+	/* grids */
+	GridBuffers cam_grid;
+	GridBuffers light_grid[UG_MAX_LIGHTS];
+	LightRays rays[UG_MAX_LIGHTS];
+	int lights_allocated = 0;
+
+	/* DecisionData (decision_data.h:66-82) */
+	float *d_t = nullptr;
+	int *d_id = nullptr, *d_shadowed = nullptr, *d_matid = nullptr;
+	float *d_normal = nullptr, *d_dir = nullptr; /* FULL_BUFFERS only */
+	unsigned char *d_rgb = nullptr;
+	unsigned char *h_rgb_pinned = nullptr;
+	size_t pix_alloc = 0;
+	bool full_alloc = false;
+
+	/* CUDA graph of the frame */
+	cudaGraphExec_t graph_exec = nullptr;
+	unsigned long long graph_key = 0;
+	int graph_launches = 0;
+
+	ug_stats stats = {};
+	bool frame_valid = false;
+};
+
+/* ---------------------------------------------------------------- error helpers */
+int ug_fail(ug_context *ctx, int code, const char *fmt, ...);
+#define UG_CUDA(ctx, call)                                                                              \
+	do {                                                                                                \
+		cudaError_t e_ = (call);                                                                        \
+		if (e_ != cudaSuccess) return ug_fail(ctx, UG_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+
+/* ---------------------------------------------------------------- kernel launchers (k_*.cu) */
+/* K1 transform */
+void ugk_transform(cudaStream_t s, float *vertexlist, const float *orig, int size, int offset, const FrameConst *fc, int sms);
+/* K2 setup+bin, scan, emit */
+void ugk_setup_bin(cudaStream_t s, const ViewConst *vc, const int *faces, const float *verts, int T, GridBuffers &g, int sms);
+void ugk_scan_counts(cudaStream_t s, GridBuffers &g, int sms);
+void ugk_emit_pairs(cudaStream_t s, const ViewConst *vc, GridBuffers &g, int sms);
+void ugk_cell_offsets(cudaStream_t s, GridBuffers &g, int sms);
+/* radix sort / scan primitives (k_sort.cu) */
+size_t ugk_scan_tiles(size_t n);
+/* stable LSD radix sort of (key,val) pairs on `bits` key bits; n read from *n_dev (<= n_max).
+ * Returns the index (0/1) of the buffer pair that ends up holding the result. */
+int ugk_radix_sort_pairs(cudaStream_t s, u32 *keys[2], u32 *vals[2], const u32 *n_dev, size_t n_max, int bits, SortScratch &sc, int sms, int *launches);
+size_t ugk_sort_hist_entries(int sms);
+/* out[i] = exclusive_sum(in[0..i)), i in [0,n]; out has n+1 entries */
+void ugk_exclusive_scan(cudaStream_t s, const u32 *in, u32 *out, size_t n, u64 *state, size_t state_tiles, int sms);
+/* K6 primary */
+void ugk_trace(cudaStream_t s, const FrameConst *fc, const GridBuffers &g, float *t, int *id, int *shadowed, float *normal, float *dir, int C, int sms);
+/* K7/K8 shadow */
+void ugk_map_rays(cudaStream_t s, const FrameConst *fc, int light, const float *t, u32 *light_cell, u32 *ray_span, int N, int sms);
+void ugk_scatter_rays(cudaStream_t s, const u32 *light_cell, const u32 *ray_offset, u32 *cursor, u32 *ray_pix, int N, int sms);
+void ugk_shadow(cudaStream_t s, const FrameConst *fc, int light, const GridBuffers &g, const u32 *ray_pix, const u32 *ray_span, const u32 *ray_offset,
+                const float *t, int *shadowed, int C, int sms);
+/* K10 shade */
+void ugk_shade(cudaStream_t s, const FrameConst *fc, const float *t, const int *id, const int *shadowed, const float4 *rec, const int *mat_idx,
+               const float *mat_list, int mat_count, unsigned char *rgb, int *mat_out, int N, int apply_shadow, int sms);
+void ugk_add_shadows(cudaStream_t s, const int *shadowed, unsigned char *rgb, int N, int sms);
+void ugk_fill_u32(cudaStream_t s, u32 *p, u32 v, size_t n, int sms);
+
+/* host helpers (camera_host.cpp, obj_loader.cpp) */
+void ugh_view_const(ViewConst *vc, const ug_camera *cam, int W, int H, int nbx, int nby, int gy_lo, int gy_cnt);
+
+#endif
