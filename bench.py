@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- Mrays/s and ms/frame INCLUDING the per-frame grid rebuild (BASELINE.json `metric`).
+
+    python bench.py --gpus N --steps K --warmup W [--config B] [--impl reference]
+
+One "step" = one frame of the hot path: [vertex transform ->] camera-grid rebuild -> primary rays -> per light
+(light-grid rebuild, shadow-ray regroup, shadow rays) -> shading to RGB8.  rays/frame = pixels * (1 + lights)
+(the reference shoots a shadow ray for every pixel, misses included).
+
+  value     device-resident frames through the C-ABI (ug_render_frame), timed per frame with CUDA events on the
+            stream the library launches on; L2 is flushed (256 MiB write) between timed frames.
+  e2e       the same frames through the host-buffer C-ABI call (ug_render_frame_host): pinned H2D of the frame
+            constants and D2H of the RGB8 image inside the timed region, wall clock.
+  N > 1     one process per GPU (torchrun); the frame is cut into N strips of cell rows, the scene is replicated,
+            every rank renders its strip straight into an NCCL buffer and the strips are gathered to rank 0
+            (NCCL over NVLink) inside the timed step.  Strong scaling: the frame is fixed.
+  roofline  the dominant kernel (timed live with one CUDA event per stage): algorithmic bytes/launch vs the
+            measured HBM peak, plus the FP32-issue roofline that actually bounds ray traversal.
+  cpu_baseline / --impl reference
+            the reference's own kernel code compiled as host C++ (oracle/_ref/libugref.so) on the box's host cores.
+
+There is no CPU fallback on the product arm: without a GPU or without libugrt.so this script fails.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mrays/s incl. per-frame grid rebuild"
+FP32_ISSUE_PER_TEST = 48  # FP32 instructions of one Moeller-Trumbore test without FMA
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured", float(p.get("sm_max_mhz", 1965.0))
+    except Exception:
+        return 6650.0, "fallback", 1965.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_scene(name: str):
+    import ugrt  # noqa: F401
+    from uniformgrid_raytracing_b200 import scenes
+    if name == "A":
+        return scenes.scene_a()
+    s = scenes.SCENES[name]()
+    return s
+
+
+def workload_name(scene, world):
+    return (f"config {scene.name}: {scene.num_tris} triangles, {scene.width}x{scene.height}, primary + shadow rays, "
+            f"{len(scene.lights)} light(s), full grid rebuild every frame"
+            + (", per-frame vertex transform" if scene.dyn_size else "") + (f", {world} image strips" if world > 1 else ""))
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def cpu_reference(scene, frames: int, warmup: int):
+    """Time the reference's own CPU code (host-compiled kernels, oracle/_ref) - falls back to the C port."""
+    from oracle import harness
+    kind = "ref" if harness.available("ref") else "oracle"
+    if kind == "oracle" and not harness.available("oracle"):
+        harness.build("oracle")
+    lib = harness.load(kind)
+    cores = os.cpu_count() or 1
+    for _ in range(max(warmup, 0)):
+        harness.run_frame(lib, scene, threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(frames):
+        harness.run_frame(lib, scene, threads=cores)
+    dt = time.perf_counter() - t0
+    rays = scene.rays_per_frame() * frames
+    return {"value": rays / dt / 1e6, "unit": "Mrays/s", "cores": lib.get_threads(), "kind": "reference" if kind == "ref" else "port",
+            "sample": f"{frames} full frame(s) of the same workload ({scene.rays_per_frame()} rays each), {dt:.2f} s",
+            "ms_per_frame": dt / frames * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    scene = make_scene(args.config)
+    frames = max(1, min(args.steps, 5))
+    base = cpu_reference(scene, frames, min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": frames,
+            "warmup": min(args.warmup, 1), "ms_per_step": base["ms_per_frame"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(scene, 1), "note": "reference kernel sources compiled as host C++ (oracle/_ref), OpenMP over "
+                       "cells/pixels; each step = one full frame; steps capped at 5 to bound the run"},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------- product arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import ugrt  # noqa: F401
+    import uniformgrid_raytracing_b200 as ug
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    hbm_peak, peak_kind, sm_max = load_peaks()
+
+    scene = make_scene(args.config)
+    r = ug.Renderer(local)
+    r.set_scene(scene)
+    r.set_stream(torch.cuda.current_stream().cuda_stream)
+    nby = scene.height // 8
+    lo, hi = nby * rank // world, nby * (rank + 1) // world
+    rows = [(nby * (k + 1) // world - nby * k // world) * 8 for k in range(world)]
+    n_local = scene.width * (hi - lo) * 8
+    strip_bytes_max = 3 * scene.width * max(rows)
+    strip = torch.zeros(strip_bytes_max, dtype=torch.uint8, device=dev)      # NCCL send buffer the shade kernel writes into
+    r.set_rgb_buffer(strip.data_ptr(), strip.numel())
+    gathered = [torch.zeros(strip_bytes_max, dtype=torch.uint8, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)            # > 126 MB L2
+    host_img = torch.empty(3 * scene.num_pixels, dtype=torch.uint8).pin_memory()
+    rays_frame = scene.rays_per_frame()
+
+    def step(i, flags=0):
+        r.render(r.params(scene, frame=i, flags=flags, strip=(rank, world)))
+        if world > 1:
+            dist.gather(strip, gathered, dst=0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also captures the CUDA graph and grows the pair arena if the scene needs it)
+    r.render_host(r.params(scene, frame=0, strip=(rank, world)), np.zeros(3 * n_local, np.uint8))
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+
+    # ---- timed: K frames, one CUDA-event pair per frame, L2 flushed between frames
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        if not args.no_flush:
+            flush.zero_()
+        ev[i][0].record()
+        step(i)
+        ev[i][1].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+    per = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(per, op=dist.ReduceOp.MAX)   # a frame is done when its slowest strip (and the gather) is
+    per = per.cpu().numpy()
+    total_ms = float(per.sum())
+    st = r.stats()
+    launches_per_frame = st.kernel_launches + (0 if args.no_flush else 0)
+
+    # ---- e2e: host buffers in, host image out, wall clock
+    e2e_steps = max(3, min(args.steps, 50))
+    out_np = np.zeros(3 * n_local, np.uint8)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        if world == 1:
+            r.render_host(r.params(scene, frame=i), out_np)          # H2D consts + kernels + D2H image + sync
+        else:
+            step(i)
+            if rank == 0:
+                off = 0
+                for k in range(world):
+                    nb = 3 * scene.width * rows[k]
+                    host_img[off:off + nb].copy_(gathered[k][:nb], non_blocking=True)
+                    off += nb
+            torch.cuda.synchronize()
+    barrier()
+    e2e_dt = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_dt = float(e2e_t.item())
+
+    # ---- per-stage timing (one event per stage, no graph) -> dominant kernel + rooflines
+    stage = {}
+    reps = 5
+    for i in range(reps):
+        r.render(r.params(scene, frame=i, flags=ug.FLAG_STAGE_EVENTS, strip=(rank, world)))
+        for k, v in r.stage_times().items():
+            stage[k] = stage.get(k, 0.0) + v / reps
+    st2 = r.stats()
+
+    if rank == 0:
+        P, N, Cc = st2.cam_pairs, st2.num_pixels, st2.num_cells
+        T = scene.num_tris
+        # single-kernel stages only (grid builds / regroup are several kernels)
+        kern = {"trace": ("k_trace", 8 * Cc + 52 * P + 8 * N, 64 * P)}
+        for l in range(len(scene.lights)):
+            kern[f"light{l}_shadow"] = ("k_shadow", None, None)
+        kern["shade"] = ("k_shade", (8 + 4 * 1) * N + 3 * N, None)
+        dom = max((k for k in kern if k in stage), key=lambda k: stage[k])
+        name, alg_bytes, tests = kern[dom]
+        if alg_bytes is None:   # shadow traversal: report the primary-traversal kernel instead (same inner loop, exact counts)
+            dom, (name, alg_bytes, tests) = "trace", kern["trace"]
+        t_s = stage[dom] * 1e-3
+        achieved = alg_bytes / t_s / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(name)
+        except Exception:
+            pass
+        roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "traffic": traffic, "peak_source": peak_kind, "algorithmic_bytes_per_launch": alg_bytes,
+                    "kernel_ms": stage[dom], "note": "ray traversal is FP32-issue bound, not HBM bound: see fp32_issue"}
+        if tests:
+            issue_peak = 148 * 128 * sm_max * 1e6 / 1e12   # T lane-ops/s at the max SM clock
+            ach = tests * FP32_ISSUE_PER_TEST / t_s / 1e12
+            roofline["fp32_issue"] = {"achieved": ach, "peak": issue_peak, "unit": "T lane-ops/s", "frac": ach / issue_peak,
+                                      "ray_triangle_tests_per_launch": tests, "fp32_instr_per_test": FP32_ISSUE_PER_TEST}
+        frame_bytes = 0
+        for nm, Pg, Cg in [("cam", P, Cc)] + [(f"l{l}", st2.light_pairs[l], (scene.width // 8) * (scene.height // 8)) for l in range(len(scene.lights))]:
+            frame_bytes += 48 * T + 4 * Pg + 8 * Cg
+        frame_bytes += 8 * Cc + 52 * P + 8 * N + len(scene.lights) * 16 * N + (8 + 4) * N + 3 * N
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cpu = cpu_reference(scene, 3, 1)
+                cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as e:  # the checker is optional for the bench line
+                cpu = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
+        line = {
+            "metric": METRIC, "value": rays_frame * args.steps / (total_ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(scene, world), "rays_per_frame": rays_frame,
+                       "l2": "flushed between timed frames (256 MiB write)" if not args.no_flush else "not flushed",
+                       "timing": "CUDA events per frame on the launching stream, max over ranks, summed over the K frames",
+                       "pairs_camera_grid": int(P), "pairs_light_grids": [int(st2.light_pairs[l]) for l in range(len(scene.lights))]},
+            "ms_per_frame_p50": float(np.median(per)), "ms_per_frame_p10": float(np.percentile(per, 10)),
+            "ms_per_frame_p90": float(np.percentile(per, 90)), "wall_s_timed_region": wall,
+            "e2e": {"value": rays_frame * e2e_steps / e2e_dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(ug.lib().ug_frame_const_bytes()) * world,
+                    "d2h_bytes_per_step": 3 * scene.num_pixels, "steps": e2e_steps, "ms_per_step": e2e_dt / e2e_steps * 1e3},
+            "gpu_launches": int(launches_per_frame) * args.steps * world,
+            "kernels_per_frame": int(launches_per_frame),
+            "stage_ms": {k: round(v, 4) for k, v in stage.items()},
+            "frame_algorithmic_bytes": frame_bytes,
+            "frame_hbm_frac": frame_bytes / (total_ms / args.steps * 1e-3) / 1e9 / hbm_peak,
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    r.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="B", choices=["A", "B", "C", "D", "E"])
+    ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "ours" and world != args.gpus and args.gpus > 1:
+        raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+    return run_reference(args) if args.impl == "reference" else run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -128,8 +128,12 @@ int ug_create(ug_context **out, int device);
 void ug_destroy(ug_context *ctx);
 const char *ug_last_error(const ug_context *ctx);
 const char *ug_version(void);
+size_t ug_frame_const_bytes(void); /* bytes of per-frame constants ug_render_frame* uploads (pinned H2D) */
 int ug_set_stream(ug_context *ctx, void *cuda_stream); /* NULL: the context's own non-blocking stream */
 int ug_synchronize(ug_context *ctx);
+/* render into a caller-owned device buffer (e.g. the NCCL send buffer of the strip gather) instead of the
+ * context's own d_image; NULL restores the internal buffer.  Must hold 3*W*H_strip bytes. */
+int ug_set_rgb_buffer(ug_context *ctx, void *device_ptr, size_t bytes);
 
 /* ---- scene.h `class Model` */
 /* per_app_funcs.h:8-37 init_model: argv[1] OBJ, argv[2] material description (scene.h:370-439);
@@ -170,8 +174,9 @@ int ug_get_stats(ug_context *ctx, ug_stats *out);                               
 int ug_read(ug_context *ctx, int buffer, int index, void *dst, size_t bytes);            /* synchronises; D2H */
 int ug_device_ptr(ug_context *ctx, int buffer, int index, void **ptr, size_t *bytes);    /* no copy */
 int ug_write_ppm(ug_context *ctx, const char *filename);                                 /* per_app_funcs.h:39-66, ASCII P3 */
-/* ms between the stage marks of the last UG_FLAG_STAGE_EVENTS frame (upload, transform, camera grid, primary rays,
- * light grids + shadows ..., shade); returns the number of intervals written (the cutCreateTimer printf's of the reference) */
+/* ms between the stage marks of the last UG_FLAG_STAGE_EVENTS frame, in order: transform, camera grid, primary rays,
+ * then per light (light grid, ray->cell map + regroup, shadow rays), then shade; returns the number of intervals
+ * written (these are the cutCreateTimer printf's of the reference) */
 int ug_stage_times(ug_context *ctx, float *out_ms, int max_entries);
 
 /* ---- the reference's own entry points on a process-wide default context */

@@ -83,7 +83,7 @@ def lib() -> C.CDLL:
         vp, f, i = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)
         sig = {
             "ug_create": (C.c_int, [C.POINTER(vp), C.c_int]), "ug_destroy": (None, [vp]), "ug_last_error": (C.c_char_p, [vp]),
-            "ug_version": (C.c_char_p, []), "ug_set_stream": (C.c_int, [vp, vp]), "ug_synchronize": (C.c_int, [vp]),
+            "ug_version": (C.c_char_p, []), "ug_frame_const_bytes": (C.c_size_t, []), "ug_set_stream": (C.c_int, [vp, vp]), "ug_set_rgb_buffer": (C.c_int, [vp, vp, C.c_size_t]), "ug_synchronize": (C.c_int, [vp]),
             "ug_model_load": (C.c_int, [vp, C.c_char_p, C.c_char_p]),
             "ug_model_set": (C.c_int, [vp, f, C.c_int, i, C.c_int, i, f, C.c_int]),
             "ug_obj_parse": (C.c_int, [C.c_char_p, i, i, f, i, i]), "ug_material_parse": (C.c_int, [C.c_char_p, i, f]),
@@ -230,6 +230,12 @@ class Renderer:
         assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"]
         self._ck(self.L.ug_render_frame_host(self.ctx, C.byref(p), out.ctypes.data_as(C.c_void_p)), "ug_render_frame_host")
 
+    def set_stream(self, cuda_stream: int):
+        self._ck(self.L.ug_set_stream(self.ctx, C.c_void_p(cuda_stream)), "ug_set_stream")
+
+    def set_rgb_buffer(self, device_ptr: int, nbytes: int):
+        self._ck(self.L.ug_set_rgb_buffer(self.ctx, C.c_void_p(device_ptr), nbytes), "ug_set_rgb_buffer")
+
     def synchronize(self):
         self._ck(self.L.ug_synchronize(self.ctx), "ug_synchronize")
 
@@ -239,9 +245,14 @@ class Renderer:
         return st
 
     def stage_times(self):
-        buf = (C.c_float * 24)()
-        n = self.L.ug_stage_times(self.ctx, buf, 24)
-        return [buf[k] for k in range(max(n, 0))]
+        """{stage name: ms} of the last FLAG_STAGE_EVENTS frame."""
+        buf = (C.c_float * 40)()
+        n = self.L.ug_stage_times(self.ctx, buf, 40)
+        names = ["transform", "cam_grid", "trace"]
+        for l in range((max(n, 0) - 4) // 3):
+            names += [f"light{l}_grid", f"light{l}_regroup", f"light{l}_shadow"]
+        names.append("shade")
+        return {names[k]: buf[k] for k in range(min(max(n, 0), len(names)))}
 
     def read(self, buffer: int, index: int = 0) -> np.ndarray:
         ptr, nbytes = C.c_void_p(), C.c_size_t()

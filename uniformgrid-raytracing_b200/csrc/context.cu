@@ -37,6 +37,7 @@ static int bits_for(unsigned max_key_exclusive) /* number of key bits needed for
 
 /* ------------------------------------------------------------------ lifetime */
 extern "C" const char *ug_version(void) { return "ugrt 0.1 (sm_100a)"; }
+extern "C" size_t ug_frame_const_bytes(void) { return sizeof(FrameConst); }
 
 extern "C" int ug_create(ug_context **out, int device)
 {
@@ -94,7 +95,7 @@ extern "C" void ug_destroy(ug_context *ctx)
 	free_grid(ctx->cam_grid);
 	for (int i = 0; i < UG_MAX_LIGHTS; i++) { free_grid(ctx->light_grid[i]); free_rays(ctx->rays[i]); }
 	dfree(ctx->d_vertexlist); dfree(ctx->d_materiallist); dfree(ctx->d_vertex_orig_list); dfree(ctx->d_facelist); dfree(ctx->d_materiallist_index);
-	dfree(ctx->d_t); dfree(ctx->d_id); dfree(ctx->d_shadowed); dfree(ctx->d_matid); dfree(ctx->d_normal); dfree(ctx->d_dir); dfree(ctx->d_rgb);
+	dfree(ctx->d_t); dfree(ctx->d_id); dfree(ctx->d_shadowed); dfree(ctx->d_matid); dfree(ctx->d_normal); dfree(ctx->d_dir); dfree(ctx->d_rgb_own);
 	if (ctx->h_rgb_pinned) cudaFreeHost(ctx->h_rgb_pinned);
 	if (ctx->h_fc) cudaFreeHost(ctx->h_fc);
 	dfree(ctx->d_fc);
@@ -111,6 +112,17 @@ extern "C" int ug_set_stream(ug_context *ctx, void *cuda_stream)
 {
 	if (!ctx) return UG_ERR_ARG;
 	ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+	if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+	return UG_OK;
+}
+
+extern "C" int ug_set_rgb_buffer(ug_context *ctx, void *device_ptr, size_t bytes)
+{
+	if (!ctx) return UG_ERR_ARG;
+	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ctx->d_rgb_ext = (unsigned char *)device_ptr;
+	ctx->rgb_ext_bytes = device_ptr ? bytes : 0;
+	if (!device_ptr) ctx->d_rgb = ctx->d_rgb_own;
 	if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
 	return UG_OK;
 }
@@ -181,7 +193,7 @@ static int ensure_buffers(ug_context *ctx, int num_lights, bool full)
 		UG_CUDA(ctx, dmalloc(&ctx->d_id, N));
 		UG_CUDA(ctx, dmalloc(&ctx->d_shadowed, N));
 		UG_CUDA(ctx, dmalloc(&ctx->d_matid, N));
-		UG_CUDA(ctx, dmalloc(&ctx->d_rgb, 3 * N));
+		UG_CUDA(ctx, dmalloc(&ctx->d_rgb_own, 3 * N));
 		if (ctx->h_rgb_pinned) cudaFreeHost(ctx->h_rgb_pinned);
 		ctx->h_rgb_pinned = nullptr;
 		UG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_rgb_pinned, 3 * N));
@@ -208,6 +220,11 @@ static int ensure_buffers(ug_context *ctx, int num_lights, bool full)
 			if (rc) return rc;
 			changed = true;
 		}
+	}
+	{
+		unsigned char *want = (ctx->d_rgb_ext && ctx->rgb_ext_bytes >= 3 * (size_t)ctx->N) ? ctx->d_rgb_ext : ctx->d_rgb_own;
+		if (ctx->d_rgb_ext && want != ctx->d_rgb_ext) return ug_fail(ctx, UG_ERR_ARG, "external RGB buffer holds %zu bytes, need %zu", ctx->rgb_ext_bytes, 3 * (size_t)ctx->N);
+		if (want != ctx->d_rgb) { ctx->d_rgb = want; changed = true; }
 	}
 	if (full && !ctx->full_alloc) {
 		UG_CUDA(ctx, dmalloc(&ctx->d_normal, 3 * (size_t)ctx->N));
@@ -364,7 +381,7 @@ static void enqueue_light_grid(ug_context *ctx, cudaStream_t s, int l, Launches 
 {
 	enqueue_grid(ctx, s, &ctx->d_fc->light[l], ctx->light_grid[l], L);
 }
-static void enqueue_light_rays(ug_context *ctx, cudaStream_t s, int l, Launches &L)
+static void enqueue_light_regroup(ug_context *ctx, cudaStream_t s, int l, Launches &L)
 {
 	LightRays &r = ctx->rays[l];
 	const int sms = ctx->num_sms, C = ctx->C_light;
@@ -373,7 +390,16 @@ static void enqueue_light_rays(ug_context *ctx, cudaStream_t s, int l, Launches 
 	ugk_map_rays(s, ctx->d_fc, l, ctx->d_t, r.cell, r.span, ctx->N, sms);                               L.n += 1;
 	ugk_exclusive_scan(s, r.span, r.offset, (size_t)C + 1, r.scan_state, r.scan_tiles, sms);            L.n += 1;
 	ugk_scatter_rays(s, r.cell, r.offset, r.cursor, r.pix, ctx->N, sms);                                L.n += 1;
-	ugk_shadow(s, ctx->d_fc, l, ctx->light_grid[l], r.pix, r.span, r.offset, ctx->d_t, ctx->d_shadowed, C, sms); L.n += 1;
+}
+static void enqueue_light_shadow(ug_context *ctx, cudaStream_t s, int l, Launches &L)
+{
+	LightRays &r = ctx->rays[l];
+	ugk_shadow(s, ctx->d_fc, l, ctx->light_grid[l], r.pix, r.span, r.offset, ctx->d_t, ctx->d_shadowed, ctx->C_light, ctx->num_sms); L.n += 1;
+}
+static void enqueue_light_rays(ug_context *ctx, cudaStream_t s, int l, Launches &L)
+{
+	enqueue_light_regroup(ctx, s, l, L);
+	enqueue_light_shadow(ctx, s, l, L);
 }
 
 static void stage_mark(ug_context *ctx, int &k, bool on)
@@ -418,15 +444,18 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 	} else {
 		for (int l = 0; l < nl; l++) {
 			enqueue_light_grid(ctx, s, l, L);
-			stage_mark(ctx, k, stage_events && l == nl - 1); /* 4: light grids (last light's mark) */
-			enqueue_light_rays(ctx, s, l, L);
+			stage_mark(ctx, k, stage_events); /* 4+3l: light grid */
+			enqueue_light_regroup(ctx, s, l, L);
+			stage_mark(ctx, k, stage_events); /* 5+3l: ray -> light cell map + regroup */
+			enqueue_light_shadow(ctx, s, l, L);
+			stage_mark(ctx, k, stage_events); /* 6+3l: shadow rays */
 		}
 	}
-	stage_mark(ctx, k, stage_events); /* 4 or 5: shadows done */
 	ugk_shade(s, ctx->d_fc, ctx->d_t, ctx->d_id, ctx->d_shadowed, ctx->cam_grid.tri_rec, ctx->d_materiallist_index, ctx->d_materiallist, ctx->num_materials,
 	          ctx->d_rgb, ctx->d_matid, ctx->N, 1, sms);
 	L.n += 1;
-	stage_mark(ctx, k, stage_events);
+	stage_mark(ctx, k, stage_events); /* shade */
+	if (stage_events) ctx->stage_marks = k;
 	UG_CUDA(ctx, cudaGetLastError());
 	return UG_OK;
 }
@@ -487,7 +516,7 @@ static unsigned long long frame_key(const ug_context *ctx, const ug_frame_params
 	mix((unsigned long long)ctx->num_faces); mix((unsigned long long)p->num_lights); mix((unsigned long long)(p->flags & UG_FLAG_FULL_BUFFERS));
 	mix((unsigned long long)(p->transform && ctx->d_vertex_orig_list ? 1 : 0)); mix((unsigned long long)ctx->cam_grid.cap);
 	for (int l = 0; l < p->num_lights; l++) mix((unsigned long long)ctx->light_grid[l].cap);
-	mix((unsigned long long)(uintptr_t)ctx->stream);
+	mix((unsigned long long)(uintptr_t)ctx->stream); mix((unsigned long long)(uintptr_t)ctx->d_rgb);
 	return k;
 }
 
@@ -784,7 +813,7 @@ extern "C" int ug_stage_times(ug_context *ctx, float *out, int max)
 	if (!ctx || !out) return UG_ERR_ARG;
 	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	int n = 0;
-	for (int k = 0; k + 1 < 24 && n < max; k++) {
+	for (int k = 0; k + 1 < ctx->stage_marks && n < max; k++) {
 		float ms = 0;
 		if (cudaEventElapsedTime(&ms, ctx->ev_stage[k], ctx->ev_stage[k + 1]) != cudaSuccess) { cudaGetLastError(); break; }
 		out[n++] = ms;

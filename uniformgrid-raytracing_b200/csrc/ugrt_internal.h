@@ -76,7 +76,8 @@ struct ug_context {
 	cudaStream_t own_stream = nullptr, stream = nullptr;
 	cudaStream_t side[UG_MAX_LIGHTS] = {};
 	cudaEvent_t ev_fork = nullptr, ev_trace = nullptr, ev_join[UG_MAX_LIGHTS] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
-	cudaEvent_t ev_stage[24] = {};
+	cudaEvent_t ev_stage[40] = {};
+	int stage_marks = 0;
 	std::string err;
 	int num_sms = 148;
 
@@ -109,7 +110,9 @@ struct ug_context {
 	float *d_t = nullptr;
 	int *d_id = nullptr, *d_shadowed = nullptr, *d_matid = nullptr;
 	float *d_normal = nullptr, *d_dir = nullptr; /* FULL_BUFFERS only */
-	unsigned char *d_rgb = nullptr;
+	unsigned char *d_rgb = nullptr;      /* where frames are written (own buffer or the caller's) */
+	unsigned char *d_rgb_own = nullptr, *d_rgb_ext = nullptr;
+	size_t rgb_ext_bytes = 0;
 	unsigned char *h_rgb_pinned = nullptr;
 	size_t pix_alloc = 0;
 	bool full_alloc = false;
