@@ -82,7 +82,7 @@ static void free_grid(GridBuffers &g)
 }
 static void free_rays(LightRays &r)
 {
-	dfree(r.cell); dfree(r.pix); dfree(r.span); dfree(r.offset); dfree(r.cursor); dfree(r.scan_state);
+	dfree(r.cell); dfree(r.pix); dfree(r.span); dfree(r.offset); dfree(r.cursor); dfree(r.scan_state); dfree(r.queue); dfree(r.queue_count);
 	r = LightRays();
 }
 
@@ -95,7 +95,7 @@ extern "C" void ug_destroy(ug_context *ctx)
 	free_grid(ctx->cam_grid);
 	for (int i = 0; i < UG_MAX_LIGHTS; i++) { free_grid(ctx->light_grid[i]); free_rays(ctx->rays[i]); }
 	dfree(ctx->d_vertexlist); dfree(ctx->d_materiallist); dfree(ctx->d_vertex_orig_list); dfree(ctx->d_facelist); dfree(ctx->d_materiallist_index);
-	dfree(ctx->d_t); dfree(ctx->d_id); dfree(ctx->d_shadowed); dfree(ctx->d_matid); dfree(ctx->d_normal); dfree(ctx->d_dir); dfree(ctx->d_rgb_own);
+	dfree(ctx->d_t); dfree(ctx->d_id); dfree(ctx->d_shadowed); dfree(ctx->d_matid); dfree(ctx->d_best); dfree(ctx->d_cell_done); dfree(ctx->d_normal); dfree(ctx->d_dir); dfree(ctx->d_rgb_own);
 	if (ctx->h_rgb_pinned) cudaFreeHost(ctx->h_rgb_pinned);
 	if (ctx->h_fc) cudaFreeHost(ctx->h_fc);
 	dfree(ctx->d_fc);
@@ -157,8 +157,9 @@ static int alloc_grid(ug_context *ctx, GridBuffers &g, int T, int C, size_t cap)
 	UG_CUDA(ctx, cudaMemset(g.counters, 0, 8 * sizeof(u32)));
 	const size_t he = ugk_sort_hist_entries(ctx->num_sms);
 	UG_CUDA(ctx, dmalloc(&g.sort.tile_hist, he));
-	UG_CUDA(ctx, dmalloc(&g.sort.tile_base, he));
-	const size_t biggest = (size_t)(T > C ? T : C) + 2;
+	UG_CUDA(ctx, dmalloc(&g.sort.tile_base, he + 1));
+	size_t biggest = (size_t)(T > C ? T : C) + 2;
+	if (biggest < he + 2) biggest = he + 2;
 	g.sort.scan_tiles = ugk_scan_tiles(biggest) + 1;
 	UG_CUDA(ctx, dmalloc(&g.sort.scan_state, g.sort.scan_tiles + 1));
 	return UG_OK;
@@ -172,6 +173,9 @@ static int alloc_rays(ug_context *ctx, LightRays &r, int N, int C)
 	UG_CUDA(ctx, dmalloc(&r.span, (size_t)C + 1));
 	UG_CUDA(ctx, dmalloc(&r.offset, (size_t)C + 2));
 	UG_CUDA(ctx, dmalloc(&r.cursor, (size_t)C + 1));
+	r.queue_cap = (size_t)N / 16 + 4096;
+	UG_CUDA(ctx, dmalloc(&r.queue, r.queue_cap));
+	UG_CUDA(ctx, dmalloc(&r.queue_count, 1));
 	r.scan_tiles = ugk_scan_tiles((size_t)C + 2) + 1;
 	UG_CUDA(ctx, dmalloc(&r.scan_state, r.scan_tiles + 1));
 	return UG_OK;
@@ -193,6 +197,7 @@ static int ensure_buffers(ug_context *ctx, int num_lights, bool full)
 		UG_CUDA(ctx, dmalloc(&ctx->d_id, N));
 		UG_CUDA(ctx, dmalloc(&ctx->d_shadowed, N));
 		UG_CUDA(ctx, dmalloc(&ctx->d_matid, N));
+		UG_CUDA(ctx, dmalloc(&ctx->d_best, N));
 		UG_CUDA(ctx, dmalloc(&ctx->d_rgb_own, 3 * N));
 		if (ctx->h_rgb_pinned) cudaFreeHost(ctx->h_rgb_pinned);
 		ctx->h_rgb_pinned = nullptr;
@@ -206,6 +211,8 @@ static int ensure_buffers(ug_context *ctx, int num_lights, bool full)
 	if (ctx->cam_grid.T != T || ctx->cam_grid.C != ctx->C_cam || !ctx->cam_grid.tri_rec) {
 		int rc = alloc_grid(ctx, ctx->cam_grid, T, ctx->C_cam, default_cap(T, ctx->C_cam));
 		if (rc) return rc;
+		UG_CUDA(ctx, dmalloc(&ctx->d_cell_done, (size_t)ctx->C_cam));
+		UG_CUDA(ctx, cudaMemset(ctx->d_cell_done, 0, sizeof(u32) * (size_t)ctx->C_cam));
 		changed = true;
 	}
 	for (int l = 0; l < num_lights; l++) {
@@ -394,7 +401,7 @@ static void enqueue_light_regroup(ug_context *ctx, cudaStream_t s, int l, Launch
 static void enqueue_light_shadow(ug_context *ctx, cudaStream_t s, int l, Launches &L)
 {
 	LightRays &r = ctx->rays[l];
-	ugk_shadow(s, ctx->d_fc, l, ctx->light_grid[l], r.pix, r.span, r.offset, ctx->d_t, ctx->d_shadowed, ctx->C_light, ctx->num_sms); L.n += 1;
+	ugk_shadow(s, ctx->d_fc, l, ctx->light_grid[l], r, ctx->d_t, ctx->d_shadowed, ctx->N, ctx->C_light, ctx->num_sms); L.n += 2;
 }
 static void enqueue_light_rays(ug_context *ctx, cudaStream_t s, int l, Launches &L)
 {
@@ -428,9 +435,11 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 			enqueue_light_grid(ctx, ctx->side[l], l, L);
 		}
 	}
+	ugk_init_pixels(s, ctx->d_fc, ctx->d_t, ctx->d_id, ctx->d_shadowed, ctx->d_best, full ? ctx->d_normal : nullptr, full ? ctx->d_dir : nullptr, ctx->N, sms);
+	L.n += 1;
 	enqueue_grid(ctx, s, &ctx->d_fc->cam, ctx->cam_grid, L);
 	stage_mark(ctx, k, stage_events); /* 2: camera grid done */
-	ugk_trace(s, ctx->d_fc, ctx->cam_grid, ctx->d_t, ctx->d_id, ctx->d_shadowed, full ? ctx->d_normal : nullptr, full ? ctx->d_dir : nullptr, ctx->C_cam, sms);
+	ugk_trace(s, ctx->d_fc, ctx->cam_grid, ctx->d_best, ctx->d_cell_done, ctx->d_t, ctx->d_id, full ? ctx->d_normal : nullptr, sms);
 	L.n += 1;
 	stage_mark(ctx, k, stage_events); /* 3: primary rays done */
 	if (parallel && nl > 0) {
@@ -657,7 +666,8 @@ extern "C" int ug_trace(ug_context *ctx)
 	if (!ctx || !ctx->cam_grid.tri_rec) return ug_fail(ctx, UG_ERR_ARG, "trace: build_frustum_grid first");
 	int rc = ensure_buffers(ctx, ctx->num_lights, true);
 	if (rc) return rc;
-	ugk_trace(ctx->stream, ctx->d_fc, ctx->cam_grid, ctx->d_t, ctx->d_id, ctx->d_shadowed, ctx->d_normal, ctx->d_dir, ctx->C_cam, ctx->num_sms);
+	ugk_init_pixels(ctx->stream, ctx->d_fc, ctx->d_t, ctx->d_id, ctx->d_shadowed, ctx->d_best, ctx->d_normal, ctx->d_dir, ctx->N, ctx->num_sms);
+	ugk_trace(ctx->stream, ctx->d_fc, ctx->cam_grid, ctx->d_best, ctx->d_cell_done, ctx->d_t, ctx->d_id, ctx->d_normal, ctx->num_sms);
 	UG_CUDA(ctx, cudaGetLastError());
 	return UG_OK;
 }

@@ -91,62 +91,147 @@ __global__ void __launch_bounds__(256) k_scatter_rays(const u32 *__restrict__ li
 	}
 }
 
-__global__ void __launch_bounds__(64) k_shadow(const FrameConst *__restrict__ fc, int light, const u32 *__restrict__ span, const u32 *__restrict__ offset,
+/* Work decomposition (same idea as k_trace): the unit of work is 64 CONSECUTIVE rays of the regrouped
+ * ray array, not a light cell.  Rays are grouped by cell, so a packet holds a few runs of equal cell;
+ * each run walks its cell's triangle list with any-hit early termination.  Lists longer than SH_SEG
+ * (border cells of the light grid collect every clamped triangle) are cut into segments: segment 0 is
+ * done inline, the others are queued as (ray range, cell, segment) entries and traced by a second launch
+ * of the same inner loop, so no packet ever owns more than SH_SEG tests per ray.  The shadow bit is an
+ * OR, so segments need no merge step. */
+#define SH_SEG 256
+
+struct ShadowRay { float Lx, Ly, Lz, dist_b; int pix; };
+
+/* rays [r0,r1) of the packet against triangles [t0,t1) of one cell's list */
+static __device__ __forceinline__ void shadow_run(float4 *s_rec, const float4 *__restrict__ rec, const u32 *__restrict__ value_list, u32 t0, u32 t1,
+                                                  bool mine, const ShadowRay &ray, float lx, float ly, float lz, bool &done, int *__restrict__ shadowed)
+{
+	const int tid = threadIdx.x;
+	for (u32 base = t0; base < t1; base += SH_BATCH) {
+		const u32 cnt = min((u32)SH_BATCH, t1 - base);
+		__syncthreads();
+		if ((u32)tid < cnt) {
+			const float4 *src = rec + 4 * (size_t)value_list[base + tid];
+			s_rec[4 * tid + 0] = src[0];
+			s_rec[4 * tid + 1] = src[1];
+			s_rec[4 * tid + 2] = src[2];
+			s_rec[4 * tid + 3] = src[3];
+		}
+		__syncthreads();
+		if (mine && !done) {
+			for (u32 k = 0; k < cnt; k++) {
+				float tt;
+				if (!ug_intersect(s_rec[4 * k], s_rec[4 * k + 1], s_rec[4 * k + 2], s_rec[4 * k + 3], ray.Lx, ray.Ly, ray.Lz, tt)) continue;
+				if (!(tt < 999999.9f) || tt == 0.0f) continue; /* intersectTri returns t only if t < oldt; `if (value)` */
+				/* light_kernel.cu:193-202 + isSmaller :1-11 */
+				const float qx = lx + tt * ray.Lx, qy = ly + tt * ray.Ly, qz = lz + tt * ray.Lz;
+				const float ax = qx - lx, ay = qy - ly, az = qz - lz;
+				const float dist_a = sqrtf(ax * ax + ay * ay + az * az);
+				if (dist_a + 1e-03f < ray.dist_b) { done = true; shadowed[ray.pix] = 1; break; }
+			}
+		}
+		if (__syncthreads_and(done || !mine)) break; /* every ray of the run is occluded */
+	}
+}
+
+static __device__ __forceinline__ ShadowRay make_shadow_ray(const float *s_lat, const ViewConst &cam, float lx, float ly, float lz, int pix, const float *__restrict__ t)
+{
+	ShadowRay r;
+	const int W = cam.W, pyl = pix / W, px = pix - pyl * W;
+	float Px, Py, Pz; /* light_kernel.cu:164-184 */
+	shadow_ray(s_lat, cam, lx, ly, lz, px, pyl + cam.gy_lo * UG_TILE, t[pix], Px, Py, Pz, r.Lx, r.Ly, r.Lz);
+	const float bx = Px - lx, by = Py - ly, bz = Pz - lz;
+	r.dist_b = sqrtf(bx * bx + by * by + bz * bz); /* isSmaller's distance_b, light_kernel.cu:5 */
+	r.pix = pix;
+	return r;
+}
+
+__global__ void __launch_bounds__(64) k_shadow(const FrameConst *__restrict__ fc, int light, int C, const u32 *__restrict__ span, const u32 *__restrict__ offset,
                                                const u32 *__restrict__ value_list, const float4 *__restrict__ rec, const u32 *__restrict__ ray_pix,
-                                               const u32 *__restrict__ ray_span, const u32 *__restrict__ ray_offset, const float *__restrict__ t,
-                                               int *__restrict__ shadowed)
+                                               const u32 *__restrict__ light_cell, const u32 *__restrict__ ray_offset, const float *__restrict__ t,
+                                               int *__restrict__ shadowed, uint4 *__restrict__ queue, u32 *__restrict__ queue_count, u32 queue_cap)
 {
 	__shared__ float4 s_rec[SH_BATCH * 4];
 	__shared__ float s_lat[100];
-	const int cell = blockIdx.x;
-	const u32 nrays = ray_span[cell], ntri = span[cell];
-	if (nrays == 0 || ntri == 0) return;
+	__shared__ u32 s_cell[64];
+	__shared__ u32 s_slot;
 	const ViewConst &cam = fc->cam;
 	const ViewConst &lv = fc->light[light];
 	const int tid = threadIdx.x;
 	for (int i = tid; i < 100; i += 64) s_lat[i] = cam.lattice[i];
-	__syncthreads();
 	const float lx = lv.cc[0], ly = lv.cc[1], lz = lv.cc[2];
-	const int W = cam.W, row0 = cam.gy_lo * UG_TILE;
-	const u32 roff = ray_offset[cell], toff = offset[cell];
-	for (u32 rbase = 0; rbase < nrays; rbase += 64) {
-		const bool active = rbase + tid < nrays;
-		int pix = 0;
-		float Lx = 0, Ly = 0, Lz = 1, dist_b = 0;
-		if (active) { /* light_kernel.cu:164-184 */
-			pix = (int)ray_pix[roff + rbase + tid];
-			const int pyl = pix / W, px = pix - pyl * W;
-			float Px, Py, Pz;
-			shadow_ray(s_lat, cam, lx, ly, lz, px, pyl + row0, t[pix], Px, Py, Pz, Lx, Ly, Lz);
-			const float bx = Px - lx, by = Py - ly, bz = Pz - lz;
-			dist_b = sqrtf(bx * bx + by * by + bz * bz); /* isSmaller's distance_b, light_kernel.cu:5 */
+	const u32 R = ray_offset[C]; /* rays that fall inside the light frustum; the rest stay lit */
+	const u32 nitems = (R + 63u) / 64u;
+	for (u32 item = blockIdx.x; item < nitems; item += gridDim.x) {
+		const u32 first = item * 64u, nact = min(64u, R - first);
+		__syncthreads();
+		ShadowRay ray = {0.0f, 0.0f, 1.0f, 0.0f, 0};
+		if ((u32)tid < nact) {
+			const int pix = (int)ray_pix[first + tid];
+			s_cell[tid] = light_cell[pix];
+			ray = make_shadow_ray(s_lat, cam, lx, ly, lz, pix, t);
 		}
-		bool done = !active;
-		for (u32 base = 0; base < ntri; base += SH_BATCH) {
-			const u32 cnt = min((u32)SH_BATCH, ntri - base);
-			__syncthreads();
-			if ((u32)tid < cnt) {
-				const float4 *src = rec + 4 * (size_t)value_list[toff + base + tid];
-				s_rec[4 * tid + 0] = src[0];
-				s_rec[4 * tid + 1] = src[1];
-				s_rec[4 * tid + 2] = src[2];
-				s_rec[4 * tid + 3] = src[3];
-			}
-			__syncthreads();
-			if (!done) {
-				for (u32 k = 0; k < cnt; k++) {
-					float tt;
-					if (!ug_intersect(s_rec[4 * k], s_rec[4 * k + 1], s_rec[4 * k + 2], s_rec[4 * k + 3], Lx, Ly, Lz, tt)) continue;
-					if (!(tt < 999999.9f) || tt == 0.0f) continue; /* intersectTri returns t only if t < oldt; `if (value)` */
-					/* light_kernel.cu:193-202 + isSmaller :1-11 */
-					const float qx = lx + tt * Lx, qy = ly + tt * Ly, qz = lz + tt * Lz;
-					const float ax = qx - lx, ay = qy - ly, az = qz - lz;
-					const float dist_a = sqrtf(ax * ax + ay * ay + az * az);
-					if (dist_a + 1e-03f < dist_b) { done = true; shadowed[pix] = 1; break; }
+		__syncthreads();
+		bool done = (u32)tid >= nact;
+		u32 r0 = 0;
+		while (r0 < nact) {
+			const u32 cell = s_cell[r0];
+			u32 r1 = r0 + 1;
+			while (r1 < nact && s_cell[r1] == cell) r1++;
+			const u32 ntri = span[cell], toff = offset[cell];
+			const bool mine = (u32)tid >= r0 && (u32)tid < r1;
+			if (ntri) {
+				const u32 segs = (ntri + SH_SEG - 1) / SH_SEG;
+				u32 inline_segs = 1;
+				if (segs > 1) { /* queue segments 1.. for the second launch; if the queue is full do them here */
+					__syncthreads();
+					if (tid == 0) {
+						const u32 slot = atomicAdd(queue_count, segs - 1);
+						if (slot + (segs - 1) <= queue_cap) {
+							for (u32 k = 1; k < segs; k++) queue[slot + k - 1] = make_uint4(first + r0, r1 - r0, cell, k);
+							s_slot = 1;
+						} else {
+							atomicSub(queue_count, segs - 1);
+							s_slot = 0;
+						}
+					}
+					__syncthreads();
+					if (!s_slot) inline_segs = segs;
 				}
+				shadow_run(s_rec, rec, value_list, toff, toff + min(ntri, inline_segs * SH_SEG), mine, ray, lx, ly, lz, done, shadowed);
 			}
-			if (__syncthreads_and(done)) break; /* every ray of the packet is occluded (or idle) */
+			r0 = r1;
 		}
+	}
+}
+
+__global__ void __launch_bounds__(64) k_shadow_queue(const FrameConst *__restrict__ fc, int light, const u32 *__restrict__ span, const u32 *__restrict__ offset,
+                                                     const u32 *__restrict__ value_list, const float4 *__restrict__ rec, const u32 *__restrict__ ray_pix,
+                                                     const float *__restrict__ t, int *__restrict__ shadowed, const uint4 *__restrict__ queue,
+                                                     const u32 *__restrict__ queue_count, u32 queue_cap)
+{
+	__shared__ float4 s_rec[SH_BATCH * 4];
+	__shared__ float s_lat[100];
+	const ViewConst &cam = fc->cam;
+	const ViewConst &lv = fc->light[light];
+	const int tid = threadIdx.x;
+	for (int i = tid; i < 100; i += 64) s_lat[i] = cam.lattice[i];
+	const float lx = lv.cc[0], ly = lv.cc[1], lz = lv.cc[2];
+	const u32 n = min(*queue_count, queue_cap);
+	for (u32 e = blockIdx.x; e < n; e += gridDim.x) {
+		const uint4 q = queue[e]; /* (first ray, ray count, cell, segment) */
+		__syncthreads();
+		ShadowRay ray = {0.0f, 0.0f, 1.0f, 0.0f, 0};
+		const bool mine = (u32)tid < q.y;
+		bool done = true;
+		if (mine) {
+			const int pix = (int)ray_pix[q.x + tid];
+			done = shadowed[pix] == 1; /* already occluded (by another segment or light): nothing to add to an OR */
+			if (!done) ray = make_shadow_ray(s_lat, cam, lx, ly, lz, pix, t);
+		}
+		const u32 ntri = span[q.z], toff = offset[q.z];
+		const u32 t0 = q.w * SH_SEG, t1 = min(ntri, t0 + SH_SEG);
+		shadow_run(s_rec, rec, value_list, toff + t0, toff + t1, mine, ray, lx, ly, lz, done, shadowed);
 	}
 }
 
@@ -164,9 +249,14 @@ void ugk_scatter_rays(cudaStream_t s, const u32 *light_cell, const u32 *ray_offs
 	k_scatter_rays<<<blocks, 256, 0, s>>>(light_cell, ray_offset, cursor, ray_pix, N);
 }
 
-void ugk_shadow(cudaStream_t s, const FrameConst *fc, int light, const GridBuffers &g, const u32 *ray_pix, const u32 *ray_span, const u32 *ray_offset,
-                const float *t, int *shadowed, int C, int)
+void ugk_shadow(cudaStream_t s, const FrameConst *fc, int light, const GridBuffers &g, const LightRays &r, const float *t, int *shadowed, int N, int C, int sms)
 {
-	if (C <= 0) return;
-	k_shadow<<<C, 64, 0, s>>>(fc, light, g.span, g.offset, g.vals[g.final_buf], g.tri_rec, ray_pix, ray_span, ray_offset, t, shadowed);
+	if (C <= 0 || N <= 0) return;
+	const size_t items = ((size_t)N + 63) / 64;
+	const unsigned blocks = (unsigned)(items < (size_t)sms * 32 ? items : (size_t)sms * 32);
+	const u32 *vals = g.vals[g.final_buf];
+	cudaMemsetAsync(r.queue_count, 0, sizeof(u32), s);
+	k_shadow<<<blocks, 64, 0, s>>>(fc, light, C, g.span, g.offset, vals, g.tri_rec, r.pix, r.cell, r.offset, t, shadowed, r.queue, r.queue_count, (u32)r.queue_cap);
+	const unsigned qblocks = (unsigned)(r.queue_cap < (size_t)sms * 32 ? r.queue_cap : (size_t)sms * 32);
+	k_shadow_queue<<<qblocks, 64, 0, s>>>(fc, light, g.span, g.offset, vals, g.tri_rec, r.pix, t, shadowed, r.queue, r.queue_count, (u32)r.queue_cap);
 }

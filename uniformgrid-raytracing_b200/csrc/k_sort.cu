@@ -148,7 +148,7 @@ int ugk_radix_sort_pairs(cudaStream_t s, u32 *keys[2], u32 *vals[2], const u32 *
 	int cur = 0;
 	for (int shift = 0; shift < bits; shift += 8) {
 		rs_hist<<<G, RS_THREADS, 0, s>>>(keys[cur], n_dev, (u32)n_max, shift, sc.tile_hist);
-		rs_scan<<<1, 1024, 0, s>>>(sc.tile_hist, sc.tile_base, (u32)(256 * G));
+		ugk_exclusive_scan(s, sc.tile_hist, sc.tile_base, (size_t)256 * G, sc.scan_state, sc.scan_tiles, sms);
 		rs_scatter<<<G, RS_THREADS, 0, s>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n_dev, (u32)n_max, shift, sc.tile_base);
 		cur ^= 1;
 		if (launches) *launches += 3;

@@ -1,108 +1,181 @@
 /* k_trace.cu -- primary rays (a9-a12): rckernel_alpha, trace_kernel.cu:84-270, launched by
  * FrustumTracer::trace (frustum_tracer.h:35-58).
  *
- * One 8x8 pixel tile = one cell of the perspective grid = one ray packet of 64 threads.  The cell's
- * triangle list (a contiguous run of d_triangle_value_list) is walked in batches: each thread of the
- * packet fetches one 64-byte ray-independent triangle record (4 x LDG.128, written by k_setup_bin)
- * into shared memory, then every ray tests every staged triangle (broadcast LDS.128).
- * Nearest hit = smallest |t| with 0 < |t| < best, strict '<' so the FIRST triangle in list order wins
- * ties, and list order inside a cell is ascending triangle id (trace_kernel.cu:35-38).
+ * One 8x8 pixel tile = one cell of the perspective grid = one ray packet of 64 threads, as in the
+ * reference.  What differs is the work decomposition: the reference gives every cell one CTA, so the
+ * frame time is the time of the longest cell list (border cells collect every triangle that was
+ * clamped into the frustum, grid_kernel.cu:217-229 - thousands of entries).  Here the unit of work is
+ * a fixed-size RANGE of the sorted (cell,triangle) pair array:
  *
- * Compute bound (FP32 issue): ~40 FP32 instructions per ray-triangle test after hoisting the
- * ray-independent cross/dot products; see DESIGN.md for the roofline.
+ *   item i  = pairs [i*S, (i+1)*S)                      (S = TR_ITEM, all items cost the same)
+ *   a range covers a few whole cells and at most two partial ones; the cell of every pair is the
+ *   sorted key, so runs are found from shared memory without touching span/offset.
+ *   whole cell   -> nearest hit is final: isWithin + write-out straight from registers
+ *   partial cell -> per-pixel 64-bit atomicMin of (t bits << 32 | pair position); the last of the
+ *                   cell's items to arrive (atomic counter) finalises the 64 pixels.
+ *
+ * Nearest hit = smallest |t| with 0 < |t| < best, strict '<' so the FIRST triangle in list order wins
+ * ties (trace_kernel.cu:35-38); positive floats order like their bit patterns and pair positions
+ * ascend in list order, so min over (t bits, position) is exactly that rule.
+ *
+ * Triangle data: each thread of the packet fetches one 64-byte ray-independent record (4 x LDG.128,
+ * written by k_setup_bin) into shared memory, every ray then tests every staged triangle with
+ * broadcast LDS.128.  Compute bound (FP32 issue); see DESIGN.md for the roofline.
  */
 #include "k_common.cuh"
 
-#define TR_BATCH 64
+#define TR_ITEM 128   /* pairs per work item */
+#define TR_BATCH 64   /* triangles staged per round = threads per packet */
 
-template <bool FULL>
-__global__ void __launch_bounds__(64) k_trace(const FrameConst *__restrict__ fc, const u32 *__restrict__ span, const u32 *__restrict__ offset,
-                                              const u32 *__restrict__ value_list, const float4 *__restrict__ rec, float *__restrict__ out_t,
-                                              int *__restrict__ out_id, int *__restrict__ out_shadowed, float *__restrict__ out_normal,
-                                              float *__restrict__ out_dir)
+__global__ void __launch_bounds__(256) k_init_pixels(const FrameConst *__restrict__ fc, float *__restrict__ t, int *__restrict__ id,
+                                                    int *__restrict__ shadowed, u64 *__restrict__ best, float *__restrict__ normal,
+                                                    float *__restrict__ dir, int N)
 {
-	__shared__ float4 s_rec[TR_BATCH * 4];
-	__shared__ u32 s_tri[TR_BATCH];
 	__shared__ float s_lat[100];
 	const ViewConst &vc = fc->cam;
-	const int tid = threadIdx.x;
-	for (int i = tid; i < 100; i += 64) s_lat[i] = vc.lattice[i];
-	const int gy_cnt = vc.gy_cnt, gy_lo = vc.gy_lo, W = vc.W, H = vc.H;
-	const float ex = vc.cc[0], ey = vc.cc[1], ez = vc.cc[2];
-	const int cell = blockIdx.x;                 /* local cell id = gx*gy_cnt + (gy-gy_lo); trace_kernel.cu:138 */
-	const int gx = cell / gy_cnt, gyl = cell - gx * gy_cnt;
-	const int px = gx * UG_TILE + (tid & 7), pyl = gyl * UG_TILE + (tid >> 3); /* strip-local row */
-	const int py = pyl + gy_lo * UG_TILE;
-	const int pix = pyl * W + px;                /* trace_kernel.cu:91 */
-	__syncthreads();
-	float dx, dy, dz;
-	ug_primary_dir(s_lat, ex, ey, ez, px, py, W, H, dx, dy, dz);
-
-	const u32 n = span[cell], off = offset[cell];
-	float best = 99999999.9f; /* trace_kernel.cu:126 */
-	int hit = -1;             /* position in the batch-relative list: off + k */
-	for (u32 base = 0; base < n; base += TR_BATCH) {
-		const u32 cnt = min((u32)TR_BATCH, n - base);
-		if ((u32)tid < cnt) {
-			const u32 tri = value_list[off + base + tid];
-			const float4 *src = rec + 4 * (size_t)tri;
-			s_tri[tid] = tri;
-			s_rec[4 * tid + 0] = src[0];
-			s_rec[4 * tid + 1] = src[1];
-			s_rec[4 * tid + 2] = src[2];
-			s_rec[4 * tid + 3] = src[3];
-		}
-		__syncthreads();
-		for (u32 k = 0; k < cnt; k++) {
-			float t;
-			if (ug_intersect(s_rec[4 * k], s_rec[4 * k + 1], s_rec[4 * k + 2], s_rec[4 * k + 3], dx, dy, dz, t)) {
-				t = fabsf(t);                    /* trace_kernel.cu:35 */
-				if (t < best && t > 0.0f) {      /* :38 */
-					best = t;
-					hit = (int)s_tri[k];
-				}
-			}
-		}
+	if (dir) {
+		for (int i = threadIdx.x; i < 100; i += blockDim.x) s_lat[i] = vc.lattice[i];
 		__syncthreads();
 	}
-	/* `hit` is remembered as the triangle id of the staged slot; since s_tri is overwritten per batch
-	 * the id itself (not the slot) is kept. */
-	bool keep = false;
-	if (hit >= 0) { /* isWithin, trace_kernel.cu:56-82 with NUM_SLABS 1 */
-		const float X = ex + best * dx, Y = ey + best * dy, Z = ez + best * dz;
-		const float *M = vc.cc + 48;
-		const float z = ug_row(M, 2, X, Y, Z, 1.0f) / ug_row(M, 3, X, Y, Z, 1.0f);
-		keep = ug_f2i(floorf(z * 1.0f)) == 0;
-	}
-	if (keep) {
-		out_t[pix] = best;
-		out_id[pix] = hit;
-	} else {
-		out_t[pix] = -1.0f;
-		out_id[pix] = -2;
-	}
-	out_shadowed[pix] = 0;
-	if (FULL) { /* reference buffers, decision_data.h:66-70 */
-		float nx = -1.0f, ny = -1.0f, nz = -1.0f;
-		if (keep) {
-			const float4 r1 = rec[4 * (size_t)hit + 1], r2 = rec[4 * (size_t)hit + 2];
-			float ax = r1.x, ay = r1.y, az = r1.z, bx = r2.x, by = r2.y, bz = r2.z;
-			ug_normalize(ax, ay, az);
-			ug_normalize(bx, by, bz);
-			ug_cross(nx, ny, nz, ax, ay, az, bx, by, bz);
-			ug_normalize(nx, ny, nz);
-			nx = (nx < 0) ? nx * -1.0f : nx; ny = (ny < 0) ? ny * -1.0f : ny; nz = (nz < 0) ? nz * -1.0f : nz;
+	for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < N; pix += gridDim.x * blockDim.x) {
+		t[pix] = -1.0f;      /* trace_kernel.cu:257-263: the miss encoding; hits overwrite it */
+		id[pix] = -2;
+		shadowed[pix] = 0;
+		best[pix] = ~0ull;
+		if (dir) { /* reference buffers (UG_FLAG_FULL_BUFFERS): dir is written for every pixel, :264-266 */
+			const int W = vc.W, pyl = pix / W, px = pix - pyl * W;
+			float dx, dy, dz;
+			ug_primary_dir(s_lat, vc.cc[0], vc.cc[1], vc.cc[2], px, pyl + vc.gy_lo * UG_TILE, W, vc.H, dx, dy, dz);
+			dir[3 * (size_t)pix + 0] = dx; dir[3 * (size_t)pix + 1] = dy; dir[3 * (size_t)pix + 2] = dz;
+			normal[3 * (size_t)pix + 0] = -1.0f; normal[3 * (size_t)pix + 1] = -1.0f; normal[3 * (size_t)pix + 2] = -1.0f;
 		}
-		out_normal[3 * (size_t)pix + 0] = nx; out_normal[3 * (size_t)pix + 1] = ny; out_normal[3 * (size_t)pix + 2] = nz;
-		out_dir[3 * (size_t)pix + 0] = dx; out_dir[3 * (size_t)pix + 1] = dy; out_dir[3 * (size_t)pix + 2] = dz;
 	}
 }
 
-void ugk_trace(cudaStream_t s, const FrameConst *fc, const GridBuffers &g, float *t, int *id, int *shadowed, float *normal, float *dir, int C, int)
+/* isWithin (trace_kernel.cu:56-82, NUM_SLABS 1) + write-out (:232-253) of one pixel's final hit */
+static __device__ __forceinline__ void finalize_pixel(const float *cc, float dx, float dy, float dz, float best, u32 tri, int pix,
+                                                      const float4 *__restrict__ rec, float *__restrict__ out_t, int *__restrict__ out_id,
+                                                      float *__restrict__ out_normal)
 {
-	if (C <= 0) return;
-	if (normal && dir)
-		k_trace<true><<<C, 64, 0, s>>>(fc, g.span, g.offset, g.vals[g.final_buf], g.tri_rec, t, id, shadowed, normal, dir);
-	else
-		k_trace<false><<<C, 64, 0, s>>>(fc, g.span, g.offset, g.vals[g.final_buf], g.tri_rec, t, id, shadowed, nullptr, nullptr);
+	const float X = cc[0] + best * dx, Y = cc[1] + best * dy, Z = cc[2] + best * dz;
+	const float *M = cc + 48;
+	const float z = ug_row(M, 2, X, Y, Z, 1.0f) / ug_row(M, 3, X, Y, Z, 1.0f);
+	if (ug_f2i(floorf(z * 1.0f)) != 0) return; /* outside NDC z [0,1): stays a miss, even if a farther hit existed */
+	out_t[pix] = best;
+	out_id[pix] = (int)tri;
+	if (out_normal) {
+		const float4 r1 = rec[4 * (size_t)tri + 1], r2 = rec[4 * (size_t)tri + 2];
+		float ax = r1.x, ay = r1.y, az = r1.z, bx = r2.x, by = r2.y, bz = r2.z, nx, ny, nz;
+		ug_normalize(ax, ay, az);
+		ug_normalize(bx, by, bz);
+		ug_cross(nx, ny, nz, ax, ay, az, bx, by, bz);
+		ug_normalize(nx, ny, nz);
+		nx = (nx < 0) ? nx * -1.0f : nx; ny = (ny < 0) ? ny * -1.0f : ny; nz = (nz < 0) ? nz * -1.0f : nz;
+		out_normal[3 * (size_t)pix + 0] = nx; out_normal[3 * (size_t)pix + 1] = ny; out_normal[3 * (size_t)pix + 2] = nz;
+	}
+}
+
+__global__ void __launch_bounds__(64) k_trace(const FrameConst *__restrict__ fc, const u32 *__restrict__ counters, const u32 *__restrict__ keys,
+                                              const u32 *__restrict__ vals, const u32 *__restrict__ span, const u32 *__restrict__ offset,
+                                              const float4 *__restrict__ rec, u64 *__restrict__ best_buf, u32 *__restrict__ cell_done,
+                                              float *__restrict__ out_t, int *__restrict__ out_id, float *__restrict__ out_normal)
+{
+	__shared__ float4 s_rec[TR_BATCH * 4];
+	__shared__ u32 s_key[TR_ITEM + 2]; /* keys[lo-1 .. hi], so both ends can tell whole cells from partial ones */
+	__shared__ u32 s_val[TR_ITEM];
+	__shared__ float s_lat[100];
+	__shared__ float s_cc[64];
+	__shared__ u32 s_ticket;
+	const ViewConst &vc = fc->cam;
+	const int tid = threadIdx.x;
+	for (int i = tid; i < 100; i += 64) s_lat[i] = vc.lattice[i];
+	s_cc[tid] = vc.cc[tid];
+	const int gy_cnt = vc.gy_cnt, gy_lo = vc.gy_lo, W = vc.W, H = vc.H;
+	const u32 P = counters[0];
+	const u32 nitems = (P + TR_ITEM - 1) / TR_ITEM;
+	__syncthreads();
+	const float ex = s_cc[0], ey = s_cc[1], ez = s_cc[2];
+
+	for (u32 item = blockIdx.x; item < nitems; item += gridDim.x) {
+		const u32 lo = item * TR_ITEM, hi = min(lo + TR_ITEM, P);
+		__syncthreads(); /* previous item's shared data is dead */
+		for (u32 i = tid; i < hi - lo + 2; i += 64) {
+			const u32 g = lo + i; /* s_key[i] = keys[lo - 1 + i] */
+			s_key[i] = (g == 0 || g > P) ? 0xffffffffu : keys[g - 1];
+		}
+		for (u32 i = tid; i < hi - lo; i += 64) s_val[i] = vals[lo + i];
+		__syncthreads();
+
+		u32 pos = lo;
+		while (pos < hi) { /* one run = the part of one cell's list that lies inside this item */
+			const u32 cell = s_key[pos - lo + 1];
+			u32 end = pos + 1;
+			while (end < hi && s_key[end - lo + 1] == cell) end++;
+			const bool whole = (s_key[pos - lo] != cell) && (s_key[end - lo + 1] != cell);
+
+			const int gx = (int)cell / gy_cnt, gyl = (int)cell - gx * gy_cnt;   /* trace_kernel.cu:138 (strip-local) */
+			const int px = gx * UG_TILE + (tid & 7), pyl = gyl * UG_TILE + (tid >> 3);
+			const int pix = pyl * W + px;                                        /* trace_kernel.cu:91 */
+			float dx, dy, dz;
+			ug_primary_dir(s_lat, ex, ey, ez, px, pyl + gy_lo * UG_TILE, W, H, dx, dy, dz);
+
+			float best = 99999999.9f; /* trace_kernel.cu:126 */
+			u32 hit = 0xffffffffu;    /* absolute pair position of the best hit */
+			for (u32 base = pos; base < end; base += TR_BATCH) {
+				const u32 cnt = min((u32)TR_BATCH, end - base);
+				__syncthreads();
+				if ((u32)tid < cnt) {
+					const float4 *src = rec + 4 * (size_t)s_val[base - lo + tid];
+					s_rec[4 * tid + 0] = src[0];
+					s_rec[4 * tid + 1] = src[1];
+					s_rec[4 * tid + 2] = src[2];
+					s_rec[4 * tid + 3] = src[3];
+				}
+				__syncthreads();
+				for (u32 k = 0; k < cnt; k++) {
+					float t;
+					if (ug_intersect(s_rec[4 * k], s_rec[4 * k + 1], s_rec[4 * k + 2], s_rec[4 * k + 3], dx, dy, dz, t)) {
+						t = fabsf(t);                    /* trace_kernel.cu:35 */
+						if (t < best && t > 0.0f) {      /* :38 */
+							best = t;
+							hit = base + k;
+						}
+					}
+				}
+			}
+
+			if (whole) {
+				if (hit != 0xffffffffu) finalize_pixel(s_cc, dx, dy, dz, best, s_val[hit - lo], pix, rec, out_t, out_id, out_normal);
+			} else {
+				if (hit != 0xffffffffu) atomicMin((unsigned long long *)&best_buf[pix], ((u64)__float_as_uint(best) << 32) | (u64)hit);
+				const u32 c_lo = offset[cell], c_hi = c_lo + span[cell];
+				const u32 parts = (c_hi - 1) / TR_ITEM - c_lo / TR_ITEM + 1;
+				__threadfence();
+				__syncthreads();
+				if (tid == 0) s_ticket = atomicAdd(&cell_done[cell], 1u);
+				__syncthreads();
+				if (s_ticket == parts - 1) { /* last item of this cell: every partial result is in best_buf */
+					__threadfence();
+					const u64 m = __ldcg((const unsigned long long *)&best_buf[pix]);
+					if (m != ~0ull)
+						finalize_pixel(s_cc, dx, dy, dz, __uint_as_float((u32)(m >> 32)), __ldg(&vals[(u32)m]), pix, rec, out_t, out_id, out_normal);
+					if (tid == 0) cell_done[cell] = 0; /* ready for the next frame */
+				}
+			}
+			pos = end;
+		}
+	}
+}
+
+void ugk_init_pixels(cudaStream_t s, const FrameConst *fc, float *t, int *id, int *shadowed, u64 *best, float *normal, float *dir, int N, int sms)
+{
+	if (N <= 0) return;
+	k_init_pixels<<<min((N + 255) / 256, sms * 8), 256, 0, s>>>(fc, t, id, shadowed, best, normal, dir, N);
+}
+
+void ugk_trace(cudaStream_t s, const FrameConst *fc, const GridBuffers &g, u64 *best, u32 *cell_done, float *t, int *id, float *normal, int sms)
+{
+	const size_t want = (g.cap + TR_ITEM - 1) / TR_ITEM;
+	const unsigned blocks = (unsigned)(want < (size_t)sms * 32 ? (want ? want : 1) : (size_t)sms * 32);
+	k_trace<<<blocks, 64, 0, s>>>(fc, g.counters, g.keys[g.final_buf], g.vals[g.final_buf], g.span, g.offset, g.tri_rec, best, cell_done, t, id, normal);
 }

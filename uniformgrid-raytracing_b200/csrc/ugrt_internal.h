@@ -67,6 +67,9 @@ struct LightRays {         /* DecisionData's regroup state (decision_data.h:72-8
 	u32 *span = nullptr;   /* [C+1] rays per light cell (last = outside) */
 	u32 *offset = nullptr; /* [C+2] */
 	u32 *cursor = nullptr; /* [C+1] */
+	uint4 *queue = nullptr; /* long-list segments of the shadow pass: (first ray, ray count, cell, segment) */
+	u32 *queue_count = nullptr;
+	size_t queue_cap = 0;
 	u64 *scan_state = nullptr;
 	size_t scan_tiles = 0;
 };
@@ -110,6 +113,8 @@ struct ug_context {
 	float *d_t = nullptr;
 	int *d_id = nullptr, *d_shadowed = nullptr, *d_matid = nullptr;
 	float *d_normal = nullptr, *d_dir = nullptr; /* FULL_BUFFERS only */
+	u64 *d_best = nullptr;      /* [N] per-pixel (t bits, pair position) merge word of split cells */
+	u32 *d_cell_done = nullptr; /* [C_cam] arrival counters of split cells (self-resetting) */
 	unsigned char *d_rgb = nullptr;      /* where frames are written (own buffer or the caller's) */
 	unsigned char *d_rgb_own = nullptr, *d_rgb_ext = nullptr;
 	size_t rgb_ext_bytes = 0;
@@ -151,12 +156,12 @@ size_t ugk_sort_hist_entries(int sms);
 /* out[i] = exclusive_sum(in[0..i)), i in [0,n]; out has n+1 entries */
 void ugk_exclusive_scan(cudaStream_t s, const u32 *in, u32 *out, size_t n, u64 *state, size_t state_tiles, int sms);
 /* K6 primary */
-void ugk_trace(cudaStream_t s, const FrameConst *fc, const GridBuffers &g, float *t, int *id, int *shadowed, float *normal, float *dir, int C, int sms);
+void ugk_init_pixels(cudaStream_t s, const FrameConst *fc, float *t, int *id, int *shadowed, u64 *best, float *normal, float *dir, int N, int sms);
+void ugk_trace(cudaStream_t s, const FrameConst *fc, const GridBuffers &g, u64 *best, u32 *cell_done, float *t, int *id, float *normal, int sms);
 /* K7/K8 shadow */
 void ugk_map_rays(cudaStream_t s, const FrameConst *fc, int light, const float *t, u32 *light_cell, u32 *ray_span, int N, int sms);
 void ugk_scatter_rays(cudaStream_t s, const u32 *light_cell, const u32 *ray_offset, u32 *cursor, u32 *ray_pix, int N, int sms);
-void ugk_shadow(cudaStream_t s, const FrameConst *fc, int light, const GridBuffers &g, const u32 *ray_pix, const u32 *ray_span, const u32 *ray_offset,
-                const float *t, int *shadowed, int C, int sms);
+void ugk_shadow(cudaStream_t s, const FrameConst *fc, int light, const GridBuffers &g, const LightRays &r, const float *t, int *shadowed, int N, int C, int sms);
 /* K10 shade */
 void ugk_shade(cudaStream_t s, const FrameConst *fc, const float *t, const int *id, const int *shadowed, const float4 *rec, const int *mat_idx,
                const float *mat_list, int mat_count, unsigned char *rgb, int *mat_out, int N, int apply_shadow, int sms);
