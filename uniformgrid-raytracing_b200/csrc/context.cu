@@ -175,7 +175,7 @@ static int alloc_rays(ug_context *ctx, LightRays &r, int N, int C)
 	UG_CUDA(ctx, dmalloc(&r.cursor, (size_t)C + 1));
 	r.queue_cap = (size_t)N / 16 + 4096;
 	UG_CUDA(ctx, dmalloc(&r.queue, r.queue_cap));
-	UG_CUDA(ctx, dmalloc(&r.queue_count, 1));
+	UG_CUDA(ctx, dmalloc(&r.queue_count, 4));
 	r.scan_tiles = ugk_scan_tiles((size_t)C + 2) + 1;
 	UG_CUDA(ctx, dmalloc(&r.scan_state, r.scan_tiles + 1));
 	return UG_OK;
@@ -198,11 +198,12 @@ static int ensure_buffers(ug_context *ctx, int num_lights, bool full)
 		UG_CUDA(ctx, dmalloc(&ctx->d_shadowed, N));
 		UG_CUDA(ctx, dmalloc(&ctx->d_matid, N));
 		UG_CUDA(ctx, dmalloc(&ctx->d_best, N));
+		UG_CUDA(ctx, dmalloc(&ctx->d_dir, 3 * N));
 		UG_CUDA(ctx, dmalloc(&ctx->d_rgb_own, 3 * N));
 		if (ctx->h_rgb_pinned) cudaFreeHost(ctx->h_rgb_pinned);
 		ctx->h_rgb_pinned = nullptr;
 		UG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_rgb_pinned, 3 * N));
-		dfree(ctx->d_normal); dfree(ctx->d_dir);
+		dfree(ctx->d_normal);
 		ctx->full_alloc = false;
 		ctx->pix_alloc = N;
 		for (int l = 0; l < UG_MAX_LIGHTS; l++) free_rays(ctx->rays[l]); /* sized by N */
@@ -235,7 +236,6 @@ static int ensure_buffers(ug_context *ctx, int num_lights, bool full)
 	}
 	if (full && !ctx->full_alloc) {
 		UG_CUDA(ctx, dmalloc(&ctx->d_normal, 3 * (size_t)ctx->N));
-		UG_CUDA(ctx, dmalloc(&ctx->d_dir, 3 * (size_t)ctx->N));
 		ctx->full_alloc = true;
 		changed = true;
 	}
@@ -394,14 +394,14 @@ static void enqueue_light_regroup(ug_context *ctx, cudaStream_t s, int l, Launch
 	const int sms = ctx->num_sms, C = ctx->C_light;
 	cudaMemsetAsync(r.span, 0, sizeof(u32) * ((size_t)C + 1), s);
 	cudaMemsetAsync(r.cursor, 0, sizeof(u32) * ((size_t)C + 1), s);
-	ugk_map_rays(s, ctx->d_fc, l, ctx->d_t, r.cell, r.span, ctx->N, sms);                               L.n += 1;
+	ugk_map_rays(s, ctx->d_fc, l, ctx->d_t, ctx->d_dir, r.cell, r.span, ctx->N, sms);                               L.n += 1;
 	ugk_exclusive_scan(s, r.span, r.offset, (size_t)C + 1, r.scan_state, r.scan_tiles, sms);            L.n += 1;
 	ugk_scatter_rays(s, r.cell, r.offset, r.cursor, r.pix, ctx->N, sms);                                L.n += 1;
 }
 static void enqueue_light_shadow(ug_context *ctx, cudaStream_t s, int l, Launches &L)
 {
 	LightRays &r = ctx->rays[l];
-	ugk_shadow(s, ctx->d_fc, l, ctx->light_grid[l], r, ctx->d_t, ctx->d_shadowed, ctx->N, ctx->C_light, ctx->num_sms); L.n += 2;
+	ugk_shadow(s, ctx->d_fc, l, ctx->light_grid[l], r, ctx->d_t, ctx->d_dir, ctx->d_shadowed, ctx->N, ctx->C_light, ctx->num_sms); L.n += 2;
 }
 static void enqueue_light_rays(ug_context *ctx, cudaStream_t s, int l, Launches &L)
 {
@@ -435,11 +435,11 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 			enqueue_light_grid(ctx, ctx->side[l], l, L);
 		}
 	}
-	ugk_init_pixels(s, ctx->d_fc, ctx->d_t, ctx->d_id, ctx->d_shadowed, ctx->d_best, full ? ctx->d_normal : nullptr, full ? ctx->d_dir : nullptr, ctx->N, sms);
+	ugk_init_pixels(s, ctx->d_fc, ctx->d_t, ctx->d_id, ctx->d_shadowed, ctx->d_best, full ? ctx->d_normal : nullptr, ctx->d_dir, ctx->N, sms);
 	L.n += 1;
 	enqueue_grid(ctx, s, &ctx->d_fc->cam, ctx->cam_grid, L);
 	stage_mark(ctx, k, stage_events); /* 2: camera grid done */
-	ugk_trace(s, ctx->d_fc, ctx->cam_grid, ctx->d_best, ctx->d_cell_done, ctx->d_t, ctx->d_id, full ? ctx->d_normal : nullptr, sms);
+	ugk_trace(s, ctx->d_fc, ctx->cam_grid, ctx->d_best, ctx->d_cell_done, ctx->d_dir, ctx->d_t, ctx->d_id, full ? ctx->d_normal : nullptr, sms);
 	L.n += 1;
 	stage_mark(ctx, k, stage_events); /* 3: primary rays done */
 	if (parallel && nl > 0) {
@@ -460,7 +460,7 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 			stage_mark(ctx, k, stage_events); /* 6+3l: shadow rays */
 		}
 	}
-	ugk_shade(s, ctx->d_fc, ctx->d_t, ctx->d_id, ctx->d_shadowed, ctx->cam_grid.tri_rec, ctx->d_materiallist_index, ctx->d_materiallist, ctx->num_materials,
+	ugk_shade(s, ctx->d_fc, ctx->d_t, ctx->d_dir, ctx->d_id, ctx->d_shadowed, ctx->cam_grid.tri_rec, ctx->d_materiallist_index, ctx->d_materiallist, ctx->num_materials,
 	          ctx->d_rgb, ctx->d_matid, ctx->N, 1, sms);
 	L.n += 1;
 	stage_mark(ctx, k, stage_events); /* shade */
@@ -667,7 +667,7 @@ extern "C" int ug_trace(ug_context *ctx)
 	int rc = ensure_buffers(ctx, ctx->num_lights, true);
 	if (rc) return rc;
 	ugk_init_pixels(ctx->stream, ctx->d_fc, ctx->d_t, ctx->d_id, ctx->d_shadowed, ctx->d_best, ctx->d_normal, ctx->d_dir, ctx->N, ctx->num_sms);
-	ugk_trace(ctx->stream, ctx->d_fc, ctx->cam_grid, ctx->d_best, ctx->d_cell_done, ctx->d_t, ctx->d_id, ctx->d_normal, ctx->num_sms);
+	ugk_trace(ctx->stream, ctx->d_fc, ctx->cam_grid, ctx->d_best, ctx->d_cell_done, ctx->d_dir, ctx->d_t, ctx->d_id, ctx->d_normal, ctx->num_sms);
 	UG_CUDA(ctx, cudaGetLastError());
 	return UG_OK;
 }
@@ -710,7 +710,7 @@ extern "C" int ug_shadow_pass(ug_context *ctx, int light_id, const ug_camera *li
 extern "C" int ug_simple_shade(ug_context *ctx)
 {
 	if (!ctx || !ctx->d_t) return ug_fail(ctx, UG_ERR_ARG, "simpleShade: trace first");
-	ugk_shade(ctx->stream, ctx->d_fc, ctx->d_t, ctx->d_id, ctx->d_shadowed, ctx->cam_grid.tri_rec, ctx->d_materiallist_index, ctx->d_materiallist,
+	ugk_shade(ctx->stream, ctx->d_fc, ctx->d_t, ctx->d_dir, ctx->d_id, ctx->d_shadowed, ctx->cam_grid.tri_rec, ctx->d_materiallist_index, ctx->d_materiallist,
 	          ctx->num_materials, ctx->d_rgb, ctx->d_matid, ctx->N, 0, ctx->num_sms);
 	UG_CUDA(ctx, cudaGetLastError());
 	ctx->frame_valid = true;

@@ -98,6 +98,32 @@ __device__ __forceinline__ bool ug_intersect(const float4 &r0, const float4 &r1,
 	return true;
 }
 
+/* same test with the record read from shared memory by 32-bit shared address (broadcast LDS.128);
+ * the loads are issued only when the value is needed, so a ray rejected by the u test never reads qvec */
+__device__ __forceinline__ float4 ug_lds128(u32 addr)
+{
+	float4 v;
+	asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ bool ug_intersect_lds(u32 addr, float dx, float dy, float dz, float &t)
+{
+	const float4 r2 = ug_lds128(addr + 32), r1 = ug_lds128(addr + 16);
+	float px, py, pz;
+	ug_cross(px, py, pz, dx, dy, dz, r2.x, r2.y, r2.z);
+	const float det = ug_dot(r1.x, r1.y, r1.z, px, py, pz);
+	if (fabsf(det) <= 1e-21f) return false;
+	const float inv = 1.0f / det;
+	const float4 r0 = ug_lds128(addr);
+	const float u = ug_dot(r0.x, r0.y, r0.z, px, py, pz) * inv;
+	if (u < 0.0f || u > 1.0f) return false;
+	const float4 r3 = ug_lds128(addr + 48);
+	const float v = ug_dot(dx, dy, dz, r3.x, r3.y, r3.z) * inv;
+	if (v < 0.0f || u + v > 1.0f) return false;
+	t = r0.w * inv;
+	return true;
+}
+
 __device__ __forceinline__ u32 ug_lane() { return threadIdx.x & 31u; }
 
 #endif

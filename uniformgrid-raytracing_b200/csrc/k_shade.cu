@@ -5,8 +5,8 @@
  *                 packed float3 array (4 vertices = 3 float4) when the sub-range is 16-byte aligned.
  *   k_shade       shader_kernel.cu:165-221 lambertian_shade + :46-86 lambert_color_pixel, with
  *                 shader_kernel.cu:347-359 shadow_kernel fused in (apply_shadow) so the image is
- *                 written once.  Direction and normal are recomputed from (pixel, triangle id) with the
- *                 reference's arithmetic instead of being read back from 24 B/pixel of buffers.
+ *                 written once.  The normal is recomputed from the triangle id with the reference's
+ *                 arithmetic instead of being stored per pixel; the direction comes from d_primary_ray_direction.
  */
 #include "k_common.cuh"
 
@@ -53,18 +53,15 @@ void ugk_transform(cudaStream_t s, float *vertexlist, const float *orig, int siz
 	if (rest) k_transform_scalar<<<min((rest + 255) / 256, sms * 8), 256, 0, s>>>(dst, orig, 4 * groups, rest, fc);
 }
 
-__global__ void __launch_bounds__(256) k_shade(const FrameConst *__restrict__ fc, const float *__restrict__ t, const int *__restrict__ id,
-                                              const int *__restrict__ shadowed, const float4 *__restrict__ rec, const int *__restrict__ mat_idx,
+__global__ void __launch_bounds__(256) k_shade(const FrameConst *__restrict__ fc, const float *__restrict__ t, const float *__restrict__ dir,
+                                              const int *__restrict__ id, const int *__restrict__ shadowed, const float4 *__restrict__ rec,
+                                              const int *__restrict__ mat_idx,
                                               const float *__restrict__ mat_list, int mat_count, unsigned char *__restrict__ rgb, int *__restrict__ mat_out,
                                               int N, int apply_shadow)
 {
-	__shared__ float s_lat[100];
 	const ViewConst &cam = fc->cam;
-	for (int i = threadIdx.x; i < 100; i += blockDim.x) s_lat[i] = cam.lattice[i];
-	__syncthreads();
 	const float *R = fc->shade_mv;
 	const float ex = cam.cc[0], ey = cam.cc[1], ez = cam.cc[2];
-	const int W = cam.W, row0 = cam.gy_lo * UG_TILE;
 	/* shader_kernel.cu:54-57: light 0 through the rotation part of the resident modelview */
 	const float l0 = fc->light_pos[0], l1 = fc->light_pos[1], l2 = fc->light_pos[2];
 	const float Lvx = R[0] * l0 + R[4] * l1 + R[8] * l2;
@@ -77,9 +74,7 @@ __global__ void __launch_bounds__(256) k_shade(const FrameConst *__restrict__ fc
 		if (mat_out) mat_out[pix] = idx;                /* shader_kernel.cu:176 */
 		const float tv = t[pix];
 		if (idx >= 0 && idx < mat_count && tv > 0.0f) {
-			const int pyl = pix / W, px = pix - pyl * W;
-			float dx, dy, dz;
-			ug_primary_dir(s_lat, ex, ey, ez, px, pyl + row0, W, cam.H, dx, dy, dz);
+			const float dx = dir[3 * (size_t)pix], dy = dir[3 * (size_t)pix + 1], dz = dir[3 * (size_t)pix + 2];
 			const float Px = ex + tv * dx, Py = ey + tv * dy, Pz = ez + tv * dz;
 			/* normal as rckernel_alpha left it: abs(normalize(cross(normalize(e1), normalize(e2)))), trace_kernel.cu:234-243 */
 			const float4 r1 = rec[4 * (size_t)tri + 1], r2 = rec[4 * (size_t)tri + 2];
@@ -116,11 +111,11 @@ __global__ void __launch_bounds__(256) k_add_shadows(const int *__restrict__ sha
 		}
 }
 
-void ugk_shade(cudaStream_t s, const FrameConst *fc, const float *t, const int *id, const int *shadowed, const float4 *rec, const int *mat_idx,
+void ugk_shade(cudaStream_t s, const FrameConst *fc, const float *t, const float *dir, const int *id, const int *shadowed, const float4 *rec, const int *mat_idx,
                const float *mat_list, int mat_count, unsigned char *rgb, int *mat_out, int N, int apply_shadow, int sms)
 {
 	if (N <= 0) return;
-	k_shade<<<min((N + 255) / 256, sms * 8), 256, 0, s>>>(fc, t, id, shadowed, rec, mat_idx, mat_list, mat_count, rgb, mat_out, N, apply_shadow);
+	k_shade<<<min((N + 255) / 256, sms * 8), 256, 0, s>>>(fc, t, dir, id, shadowed, rec, mat_idx, mat_list, mat_count, rgb, mat_out, N, apply_shadow);
 }
 void ugk_add_shadows(cudaStream_t s, const int *shadowed, unsigned char *rgb, int N, int sms)
 {

@@ -33,22 +33,22 @@ __global__ void __launch_bounds__(256) k_init_pixels(const FrameConst *__restric
 {
 	__shared__ float s_lat[100];
 	const ViewConst &vc = fc->cam;
-	if (dir) {
-		for (int i = threadIdx.x; i < 100; i += blockDim.x) s_lat[i] = vc.lattice[i];
-		__syncthreads();
-	}
+	for (int i = threadIdx.x; i < 100; i += blockDim.x) s_lat[i] = vc.lattice[i];
+	__syncthreads();
+	const int W = vc.W, H = vc.H, row0 = vc.gy_lo * UG_TILE;
+	const float ex = vc.cc[0], ey = vc.cc[1], ez = vc.cc[2];
 	for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < N; pix += gridDim.x * blockDim.x) {
 		t[pix] = -1.0f;      /* trace_kernel.cu:257-263: the miss encoding; hits overwrite it */
 		id[pix] = -2;
 		shadowed[pix] = 0;
 		best[pix] = ~0ull;
-		if (dir) { /* reference buffers (UG_FLAG_FULL_BUFFERS): dir is written for every pixel, :264-266 */
-			const int W = vc.W, pyl = pix / W, px = pix - pyl * W;
-			float dx, dy, dz;
-			ug_primary_dir(s_lat, vc.cc[0], vc.cc[1], vc.cc[2], px, pyl + vc.gy_lo * UG_TILE, W, vc.H, dx, dy, dz);
-			dir[3 * (size_t)pix + 0] = dx; dir[3 * (size_t)pix + 1] = dy; dir[3 * (size_t)pix + 2] = dz;
-			normal[3 * (size_t)pix + 0] = -1.0f; normal[3 * (size_t)pix + 1] = -1.0f; normal[3 * (size_t)pix + 2] = -1.0f;
-		}
+		/* d_primary_ray_direction (decision_data.h:14) is written for every pixel, hit or miss (trace_kernel.cu:264-266);
+		 * the primary, shadow-map, shadow and shade kernels all read it instead of recomputing it */
+		const int pyl = pix / W, px = pix - pyl * W;
+		float dx, dy, dz;
+		ug_primary_dir(s_lat, ex, ey, ez, px, pyl + row0, W, H, dx, dy, dz);
+		dir[3 * (size_t)pix + 0] = dx; dir[3 * (size_t)pix + 1] = dy; dir[3 * (size_t)pix + 2] = dz;
+		if (normal) { normal[3 * (size_t)pix + 0] = -1.0f; normal[3 * (size_t)pix + 1] = -1.0f; normal[3 * (size_t)pix + 2] = -1.0f; }
 	}
 }
 
@@ -78,24 +78,23 @@ static __device__ __forceinline__ void finalize_pixel(const float *cc, float dx,
 __global__ void __launch_bounds__(64) k_trace(const FrameConst *__restrict__ fc, const u32 *__restrict__ counters, const u32 *__restrict__ keys,
                                               const u32 *__restrict__ vals, const u32 *__restrict__ span, const u32 *__restrict__ offset,
                                               const float4 *__restrict__ rec, u64 *__restrict__ best_buf, u32 *__restrict__ cell_done,
-                                              float *__restrict__ out_t, int *__restrict__ out_id, float *__restrict__ out_normal)
+                                              const float *__restrict__ dir, float *__restrict__ out_t, int *__restrict__ out_id,
+                                              float *__restrict__ out_normal)
 {
 	__shared__ float4 s_rec[TR_BATCH * 4];
 	__shared__ u32 s_key[TR_ITEM + 2]; /* keys[lo-1 .. hi], so both ends can tell whole cells from partial ones */
 	__shared__ u32 s_val[TR_ITEM];
-	__shared__ float s_lat[100];
+	__shared__ u32 s_head[TR_ITEM / 32]; /* bit p = pair lo+p starts a run (its key differs from the previous pair's) */
 	__shared__ float s_cc[64];
 	__shared__ u32 s_ticket;
 	const ViewConst &vc = fc->cam;
 	const int tid = threadIdx.x;
-	for (int i = tid; i < 100; i += 64) s_lat[i] = vc.lattice[i];
 	s_cc[tid] = vc.cc[tid];
-	const int gy_cnt = vc.gy_cnt, gy_lo = vc.gy_lo, W = vc.W, H = vc.H;
+	const int gy_cnt = vc.gy_cnt, W = vc.W;
+	const u32 rec_base = (u32)__cvta_generic_to_shared(s_rec);
 	const u32 P = counters[0];
 	const u32 nitems = (P + TR_ITEM - 1) / TR_ITEM;
 	__syncthreads();
-	const float ex = s_cc[0], ey = s_cc[1], ez = s_cc[2];
-
 	for (u32 item = blockIdx.x; item < nitems; item += gridDim.x) {
 		const u32 lo = item * TR_ITEM, hi = min(lo + TR_ITEM, P);
 		__syncthreads(); /* previous item's shared data is dead */
@@ -105,19 +104,37 @@ __global__ void __launch_bounds__(64) k_trace(const FrameConst *__restrict__ fc,
 		}
 		for (u32 i = tid; i < hi - lo; i += 64) s_val[i] = vals[lo + i];
 		__syncthreads();
+#pragma unroll
+		for (u32 w = 0; w < TR_ITEM / 64; w++) { /* run heads, 32 pairs per ballot */
+			const u32 p = w * 64 + tid;
+			const bool head = (p < hi - lo) && (p == 0 || s_key[p + 1] != s_key[p]);
+			const u32 bits = __ballot_sync(UG_FULL_MASK, head);
+			if ((tid & 31) == 0) s_head[p >> 5] = bits;
+		}
+		__syncthreads();
 
 		u32 pos = lo;
 		while (pos < hi) { /* one run = the part of one cell's list that lies inside this item */
 			const u32 cell = s_key[pos - lo + 1];
-			u32 end = pos + 1;
-			while (end < hi && s_key[end - lo + 1] == cell) end++;
+			u32 end = hi; /* next run head after pos */
+			{
+				u32 q = pos - lo + 1, w = q >> 5;
+				if (w < TR_ITEM / 32) {
+					u32 bits = s_head[w] & (0xffffffffu << (q & 31));
+					if ((q & 31) == 0) bits = s_head[w];
+					while (true) {
+						if (bits) { end = min(hi, lo + (w << 5) + (u32)__ffs(bits) - 1); break; }
+						if (++w >= TR_ITEM / 32) break;
+						bits = s_head[w];
+					}
+				}
+			}
 			const bool whole = (s_key[pos - lo] != cell) && (s_key[end - lo + 1] != cell);
 
 			const int gx = (int)cell / gy_cnt, gyl = (int)cell - gx * gy_cnt;   /* trace_kernel.cu:138 (strip-local) */
 			const int px = gx * UG_TILE + (tid & 7), pyl = gyl * UG_TILE + (tid >> 3);
 			const int pix = pyl * W + px;                                        /* trace_kernel.cu:91 */
-			float dx, dy, dz;
-			ug_primary_dir(s_lat, ex, ey, ez, px, pyl + gy_lo * UG_TILE, W, H, dx, dy, dz);
+			const float dx = dir[3 * (size_t)pix], dy = dir[3 * (size_t)pix + 1], dz = dir[3 * (size_t)pix + 2];
 
 			float best = 99999999.9f; /* trace_kernel.cu:126 */
 			u32 hit = 0xffffffffu;    /* absolute pair position of the best hit */
@@ -134,7 +151,7 @@ __global__ void __launch_bounds__(64) k_trace(const FrameConst *__restrict__ fc,
 				__syncthreads();
 				for (u32 k = 0; k < cnt; k++) {
 					float t;
-					if (ug_intersect(s_rec[4 * k], s_rec[4 * k + 1], s_rec[4 * k + 2], s_rec[4 * k + 3], dx, dy, dz, t)) {
+					if (ug_intersect_lds(rec_base + k * 64u, dx, dy, dz, t)) {
 						t = fabsf(t);                    /* trace_kernel.cu:35 */
 						if (t < best && t > 0.0f) {      /* :38 */
 							best = t;
@@ -173,9 +190,10 @@ void ugk_init_pixels(cudaStream_t s, const FrameConst *fc, float *t, int *id, in
 	k_init_pixels<<<min((N + 255) / 256, sms * 8), 256, 0, s>>>(fc, t, id, shadowed, best, normal, dir, N);
 }
 
-void ugk_trace(cudaStream_t s, const FrameConst *fc, const GridBuffers &g, u64 *best, u32 *cell_done, float *t, int *id, float *normal, int sms)
+void ugk_trace(cudaStream_t s, const FrameConst *fc, const GridBuffers &g, u64 *best, u32 *cell_done, const float *dir, float *t, int *id, float *normal,
+               int sms)
 {
 	const size_t want = (g.cap + TR_ITEM - 1) / TR_ITEM;
 	const unsigned blocks = (unsigned)(want < (size_t)sms * 32 ? (want ? want : 1) : (size_t)sms * 32);
-	k_trace<<<blocks, 64, 0, s>>>(fc, g.counters, g.keys[g.final_buf], g.vals[g.final_buf], g.span, g.offset, g.tri_rec, best, cell_done, t, id, normal);
+	k_trace<<<blocks, 64, 0, s>>>(fc, g.counters, g.keys[g.final_buf], g.vals[g.final_buf], g.span, g.offset, g.tri_rec, best, cell_done, dir, t, id, normal);
 }

@@ -112,7 +112,8 @@ struct ug_context {
 	/* DecisionData (decision_data.h:66-82) */
 	float *d_t = nullptr;
 	int *d_id = nullptr, *d_shadowed = nullptr, *d_matid = nullptr;
-	float *d_normal = nullptr, *d_dir = nullptr; /* FULL_BUFFERS only */
+	float *d_dir = nullptr;     /* [3N] d_primary_ray_direction, always kept */
+	float *d_normal = nullptr;  /* [3N] FULL_BUFFERS only */
 	u64 *d_best = nullptr;      /* [N] per-pixel (t bits, pair position) merge word of split cells */
 	u32 *d_cell_done = nullptr; /* [C_cam] arrival counters of split cells (self-resetting) */
 	unsigned char *d_rgb = nullptr;      /* where frames are written (own buffer or the caller's) */
@@ -157,13 +158,15 @@ size_t ugk_sort_hist_entries(int sms);
 void ugk_exclusive_scan(cudaStream_t s, const u32 *in, u32 *out, size_t n, u64 *state, size_t state_tiles, int sms);
 /* K6 primary */
 void ugk_init_pixels(cudaStream_t s, const FrameConst *fc, float *t, int *id, int *shadowed, u64 *best, float *normal, float *dir, int N, int sms);
-void ugk_trace(cudaStream_t s, const FrameConst *fc, const GridBuffers &g, u64 *best, u32 *cell_done, float *t, int *id, float *normal, int sms);
+void ugk_trace(cudaStream_t s, const FrameConst *fc, const GridBuffers &g, u64 *best, u32 *cell_done, const float *dir, float *t, int *id, float *normal,
+               int sms);
 /* K7/K8 shadow */
-void ugk_map_rays(cudaStream_t s, const FrameConst *fc, int light, const float *t, u32 *light_cell, u32 *ray_span, int N, int sms);
+void ugk_map_rays(cudaStream_t s, const FrameConst *fc, int light, const float *t, const float *dir, u32 *light_cell, u32 *ray_span, int N, int sms);
 void ugk_scatter_rays(cudaStream_t s, const u32 *light_cell, const u32 *ray_offset, u32 *cursor, u32 *ray_pix, int N, int sms);
-void ugk_shadow(cudaStream_t s, const FrameConst *fc, int light, const GridBuffers &g, const LightRays &r, const float *t, int *shadowed, int N, int C, int sms);
+void ugk_shadow(cudaStream_t s, const FrameConst *fc, int light, const GridBuffers &g, const LightRays &r, const float *t, const float *dir, int *shadowed,
+                int N, int C, int sms);
 /* K10 shade */
-void ugk_shade(cudaStream_t s, const FrameConst *fc, const float *t, const int *id, const int *shadowed, const float4 *rec, const int *mat_idx,
+void ugk_shade(cudaStream_t s, const FrameConst *fc, const float *t, const float *dir, const int *id, const int *shadowed, const float4 *rec, const int *mat_idx,
                const float *mat_list, int mat_count, unsigned char *rgb, int *mat_out, int N, int apply_shadow, int sms);
 void ugk_add_shadows(cudaStream_t s, const int *shadowed, unsigned char *rgb, int N, int sms);
 void ugk_fill_u32(cudaStream_t s, u32 *p, u32 v, size_t n, int sms);
