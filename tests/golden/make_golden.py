@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Generate the committed golden vectors from the REFERENCE build (oracle/_ref/libugref.so = the reference's own
+kernel sources compiled as host C++, see oracle/Makefile).  Run in the build container, where /root/reference exists:
+
+    python tests/golden/make_golden.py
+
+For each scene: sha256 of every stage buffer, plus the full arrays of the small scenes, in tests/golden/<name>.npz.
+tests/test_golden.py checks the oracle (CPU) and the CUDA path (GPU) against these files; nothing at test time
+reads /root/reference."""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+import ugrt  # noqa: E402,F401
+from oracle import harness  # noqa: E402
+from uniformgrid_raytracing_b200 import scenes  # noqa: E402
+
+STAGES = ["camcoords", "dirtex", "cam_values", "cam_span", "cam_offset", "t", "id", "normal", "dir", "light0_camcoords", "light0_cell",
+          "light0_values", "light0_span", "light0_offset", "shadowed", "rgb_unshadowed", "material_id", "rgb"]
+
+
+def golden_scenes():
+    out = {f"tiny_{k}": scenes.scene_tiny(k) for k in ("one", "tie", "behind", "near", "outside", "ka")}
+    out["rand_11"] = scenes.scene_random(11, 800, 96, 64, nlights=1)
+    out["a_256"] = scenes.scene_a(256, 256)
+    return out
+
+
+def digest(a) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def main():
+    harness.build("ref")
+    ref = harness.load("ref")
+    for name, scene in golden_scenes().items():
+        res = harness.run_frame(ref, scene, threads=0)
+        data = {"stages": np.array([s for s in STAGES if s in res]), "sha256": np.array([digest(res[s]) for s in STAGES if s in res]),
+                "P": np.array([res["cam_P"], res.get("light0_P", 0)], dtype=np.int64)}
+        small = scene.num_pixels <= 96 * 64
+        keep = STAGES if small else ["camcoords", "dirtex", "cam_span", "light0_span"]
+        for s in keep:
+            if s in res:
+                data["full_" + s] = np.asarray(res[s])
+        if not small:  # a strided sample of the per-pixel buffers
+            idx = np.arange(0, scene.num_pixels, 97)
+            data["sample_idx"] = idx
+            for s in ("t", "id", "shadowed", "light0_cell"):
+                data["sample_" + s] = np.asarray(res[s])[idx]
+            data["sample_rgb"] = np.asarray(res["rgb"]).reshape(-1, 3)[idx]
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **data)
+        print(name, "P", data["P"].tolist(), "hits", int((res["id"] >= 0).sum()), "shadowed", int(res["shadowed"].sum()))
+
+
+if __name__ == "__main__":
+    main()

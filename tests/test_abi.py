@@ -1,0 +1,86 @@
+"""The drop-in boundary: libugrt.so loads without a GPU, exports every function include/ugrt.h declares, its host-only
+entry points (camera.h mirror, direction lattice, loader) agree with the oracle, and it FAILS LOUDLY - no CPU fallback -
+when no CUDA device is present."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import parity
+from oracle import harness
+from uniformgrid_raytracing_b200 import scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "ugrt.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"^\s*(?:const\s+)?[A-Za-z_][A-Za-z_0-9]*\s*\**\s*\b([A-Za-z_][A-Za-z_0-9]*)\s*\([^;{]*\)\s*;", src, flags=re.M)
+    return sorted(set(names))
+
+
+def test_header_symbols_are_exported(ug):
+    lib = C.CDLL(ug.LIB_PATH)
+    names = declared_functions()
+    assert len(names) >= 40 and {"ug_create", "ug_render_frame", "ug_render_frame_host", "init_model", "build_frustum_grid", "check_for_shadows",
+                                 "writePPM", "fillCoordinatesData", "processData"} <= set(names)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in include/ugrt.h but not exported: {missing}"
+
+
+def test_no_oracle_in_product(ug):
+    """The product library must not link against (or dlopen) anything under oracle/."""
+    blob = open(ug.LIB_PATH, "rb").read()
+    assert b"libugoracle" not in blob and b"libugref" not in blob and b"orc_" not in blob
+
+
+def test_create_fails_loudly_without_gpu(ug):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(ug.UgError):
+        ug.Renderer(0)
+    ctx = C.c_void_p()
+    assert ug.lib().ug_create(C.byref(ctx), 0) == 2 and not ctx.value      # UG_ERR_CUDA, no context
+
+
+@pytest.mark.parametrize("w,h,eye,look,up", [(512, 512, (0, -30, 12), (0, 0, 2), (0, 0, 1)), (1920, 1080, (14.5, -14, 13), (14.5, 13, 2), (0, 0, 1)),
+                                              (64, 64, (3, 15, 5), (13, 13, 3), (0, 0, 1))])
+def test_camera_matches_oracle(ug, oracle, w, h, eye, look, up):
+    """camera.h mirror: modelview/projection/MVP, Gribb-Hartmann planes, near corners, and the 5x5 direction lattice."""
+    oracle.configure(w, h, 45, 0)
+    want = oracle.camera_setup(eye, look, up, 0.1, 100.0)
+    cam = ug.make_camera(eye, look, up, 0.1, 100.0, 45.0, float(np.float32(w) / np.float32(h)))
+    got = ug.camcoords(cam)
+    assert np.array_equal(parity.bits(got), parity.bits(want))
+    assert np.array_equal(parity.bits(ug.direction_lattice(got)), parity.bits(oracle.dirtex()))
+    want_l = oracle.camera_setup(eye, look, up, 0.1, 100.0, square=True)     # light cameras: aspect 1
+    got_l = ug.camcoords(ug.make_camera(eye, look, up, 0.1, 100.0, 45.0, 1.0))
+    assert np.array_equal(parity.bits(got_l), parity.bits(want_l))
+
+
+def test_frame_params_layout(ug):
+    """ctypes mirrors of the PODs in include/ugrt.h have the sizes the C compiler gives them."""
+    import subprocess, tempfile, textwrap
+    prog = textwrap.dedent('''
+        #include <stdio.h>
+        #include "ugrt.h"
+        int main(void){ printf("%zu %zu %zu %zu\\n", sizeof(ug_camera), sizeof(ug_light), sizeof(ug_frame_params), sizeof(ug_stats)); return 0; }''')
+    with tempfile.TemporaryDirectory() as d:
+        src, exe = os.path.join(d, "s.c"), os.path.join(d, "s")
+        open(src, "w").write(prog)
+        subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)   # the header is plain C
+        sizes = list(map(int, subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()))
+    assert sizes == [C.sizeof(ug.Camera), C.sizeof(ug.LightS), C.sizeof(ug.FrameParams), C.sizeof(ug.Stats)]
+
+
+def test_strip_bounds_cover_the_frame(ug):
+    from uniformgrid_raytracing_b200 import strips
+    for h, world in [(1024, 1), (1024, 8), (1080, 4), (1080, 8), (64, 3), (4096, 8)]:
+        nby = h // 8
+        b = [strips.strip_bounds(nby, k, world) for k in range(world)]
+        assert b[0][0] == 0 and b[-1][1] == nby and all(b[k][1] == b[k + 1][0] for k in range(world - 1))
+        assert sum(strips.strip_nbytes(640, h, world)) == 3 * 640 * h

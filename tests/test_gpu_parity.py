@@ -1,0 +1,200 @@
+"""Parity of the CUDA path (through the C-ABI, libugrt.so) against the CPU oracle.
+
+Bars from BASELINE.json: cell/triangle index lists, hit-triangle ids and shadow bits BIT-EXACT (ties at equal t ->
+lower triangle id); hit t to 1e-5 relative; RGB within 1/255 on >= 99.9 % of pixels.  The CUDA path follows the
+reference's arithmetic operation for operation (no FMA contraction, IEEE div/sqrt, x86 float->int rule), so these
+tests demand bit-exact t and RGB as well and report the looser bars only in the assertion messages."""
+import numpy as np
+import pytest
+
+import parity
+from oracle import harness
+from uniformgrid_raytracing_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+T_REL_TOL = 1e-5        # north_star tolerance for hit t
+RGB_TOL, RGB_FRAC = 1, 0.999
+
+
+def assert_frame(gpu, cpu, what):
+    bad = parity.compare(gpu, cpu, verbose=False)
+    # the stated bars, for the message
+    rel = parity.rel_err_t(gpu["t"], cpu["t"])
+    close = np.mean(np.abs(gpu["rgb"].astype(np.int16) - cpu["rgb"].astype(np.int16)).reshape(-1, 3).max(axis=1) <= RGB_TOL)
+    assert rel <= T_REL_TOL and close >= RGB_FRAC, f"{what}: t rel err {rel}, rgb within 1/255 on {close:.5f}"
+    assert not bad, f"{what}: stages not bit-exact: {bad}"
+
+
+def cpu_frame(oracle, scene, frame=0):
+    out = harness.run_frame(oracle, scene, frame=frame, threads=0)
+    oracle.configure(scene.width, scene.height, scene.fovy, 0)
+    oracle.camera_setup(scene.eye, scene.look, scene.up, scene.near, scene.far)
+    out["sizelist"] = oracle.grid_count(np.ascontiguousarray(scene.faces, np.int32), np.ascontiguousarray(out["verts"], np.float32))[0]
+    return out
+
+
+@pytest.mark.parametrize("kind", ["one", "tie", "behind", "near", "outside", "ka"])
+def test_micro_scenes(renderer, ug, oracle, kind):
+    s = scenes.scene_tiny(kind)
+    renderer.set_scene(s)
+    assert_frame(parity.gpu_frame(renderer, s), cpu_frame(oracle, s), s.name)
+
+
+@pytest.mark.parametrize("seed,ntris,w,h,nl", [(1, 2000, 128, 64, 2), (2, 500, 96, 160, 1), (3, 6000, 256, 256, 1), (4, 50, 64, 64, 0),
+                                              (5, 20000, 320, 200, 3)])
+def test_random_soups(renderer, ug, oracle, seed, ntris, w, h, nl):
+    s = scenes.scene_random(seed, ntris, w, h, nlights=nl)
+    renderer.set_scene(s)
+    assert_frame(parity.gpu_frame(renderer, s), cpu_frame(oracle, s), s.name)
+
+
+def test_config_a(renderer, ug, oracle):
+    """BASELINE config A: 16 370-triangle icosphere on a plane, 512x512, primary + shadow, 1 light - every stage."""
+    s = scenes.scene_a()
+    renderer.set_scene(s)
+    cpu = cpu_frame(oracle, s)
+    assert_frame(parity.gpu_frame(renderer, s), cpu, "config A (graph)")
+    assert_frame(parity.gpu_frame(renderer, s, flags=ug.FLAG_FULL_BUFFERS | ug.FLAG_NO_GRAPH), cpu, "config A (direct launches)")
+    assert_frame(parity.gpu_frame(renderer, s, stepwise=True), cpu, "config A (per_frame_funcs call sequence)")
+
+
+def test_config_b(renderer, ug, oracle):
+    """BASELINE config B geometry (80 000 triangles, 1024x1024, 1 light): every stage."""
+    s = scenes.scene_b()
+    renderer.set_scene(s)
+    assert_frame(parity.gpu_frame(renderer, s), cpu_frame(oracle, s), "config B")
+
+
+def test_config_c_dynamic_two_lights(renderer, ug, oracle):
+    """BASELINE config C at reduced resolution: per-frame vertex transform + rebuild of the camera grid and two light grids."""
+    s = scenes.scene_c(480, 272)
+    renderer.set_scene(s)
+    for frame in (0, 2):
+        assert_frame(parity.gpu_frame(renderer, s, frame=frame), cpu_frame(oracle, s, frame=frame), f"config C frame {frame}")
+
+
+def test_idempotent_and_graph_replay(renderer, ug):
+    """Rendering the same frame again (graph replay, self-resetting counters) gives the same bytes."""
+    s = scenes.scene_random(9, 5000, 256, 128, nlights=2)
+    renderer.set_scene(s)
+    a = parity.gpu_frame(renderer, s, flags=0)
+    for _ in range(3):
+        b = parity.gpu_frame(renderer, s, flags=0)
+        assert not parity.compare(b, a, verbose=False)
+
+
+def test_strips_equal_full_frame(renderer, ug, oracle):
+    """Image-strip sharding: every strip's lists, hits, shadow bits and pixels equal the corresponding
+    rows of the single-context frame; the strips concatenate to the full image byte for byte."""
+    s = scenes.scene_a(256, 264)        # 33 cell rows: uneven strips
+    renderer.set_scene(s)
+    full = parity.gpu_frame(renderer, s, flags=0)
+    cpu = cpu_frame(oracle, s)
+    assert not parity.compare(full, cpu, keys=["t", "id", "shadowed", "rgb"], verbose=False)
+    nbx, nby = s.width // 8, s.height // 8
+    for world in (2, 3, 8):
+        rows_done, img = 0, []
+        for rank in range(world):
+            part = parity.gpu_frame(renderer, s, flags=0, strip=(rank, world))
+            lo, hi = nby * rank // world, nby * (rank + 1) // world
+            npix = s.width * (hi - lo) * 8
+            sl = slice(s.width * lo * 8, s.width * hi * 8)
+            assert part["t"].size == npix
+            for k in ("t", "id", "shadowed"):
+                assert np.array_equal(parity.bits(part[k]), parity.bits(full[k][sl])), (world, rank, k)
+            assert np.array_equal(part["rgb"], full["rgb"][3 * sl.start:3 * sl.stop])
+            # the strip's cell lists are the global lists of the owned cells
+            span_full = full["cam_span"].reshape(nbx, nby)[:, lo:hi]
+            assert np.array_equal(part["cam_span"].reshape(nbx, hi - lo), span_full)
+            off_f, off_p = full["cam_offset"].reshape(nbx, nby), part["cam_offset"].reshape(nbx, hi - lo)
+            for gx in range(0, nbx, 5):
+                for gy in range(lo, hi):
+                    n = int(span_full[gx, gy - lo])
+                    a = full["cam_values"][off_f[gx, gy]:off_f[gx, gy] + n]
+                    b = part["cam_values"][off_p[gx, gy - lo]:off_p[gx, gy - lo] + n]
+                    assert np.array_equal(a, b)
+            img.append(part["rgb"])
+            rows_done += hi - lo
+        assert rows_done == nby and np.array_equal(np.concatenate(img), full["rgb"])
+    renderer.render(renderer.params(s, strip=(0, 1)))
+
+
+def test_host_path_and_ppm(renderer, ug, oracle, tmp_path):
+    """ug_render_frame_host (pinned H2D constants, D2H image) and the P3 writer (per_app_funcs.h:39-66)."""
+    s = scenes.scene_random(12, 3000, 128, 96, nlights=1)
+    renderer.set_scene(s)
+    cpu = cpu_frame(oracle, s)
+    out = np.zeros(3 * s.num_pixels, np.uint8)
+    renderer.render_host(renderer.params(s), out)
+    assert np.array_equal(out, cpu["rgb"])
+    path = str(tmp_path / "f.ppm")
+    renderer.write_ppm(path)
+    tok = open(path).read().split()
+    assert tok[:4] == ["P3", str(s.width), str(s.height), "255"]
+    assert np.array_equal(np.asarray(tok[4:], dtype=np.int64).astype(np.uint8), cpu["rgb"])
+
+
+def test_model_load_through_obj(renderer, ug, oracle, tmp_path):
+    """init_model path: OBJ + material file -> Model -> frame; same result as uploading the arrays."""
+    s = scenes.scene_a(128, 128)
+    obj, mtl = scenes.write_obj(s, str(tmp_path / "a.obj"))
+    renderer.load(obj, mtl)
+    renderer.scene = s
+    assert_frame(parity.gpu_frame(renderer, s), cpu_frame(oracle, s), "config A via OBJ loader")
+
+
+def test_pair_arena_overflow_regrows(ug, oracle):
+    """P is data dependent: a scene whose pair count exceeds the initial arena must be re-run with a larger one."""
+    # 24 huge triangles at 1024x1024: each covers most of the 16 384 cells -> P far above 16*T + C + 2^20
+    rng = np.random.default_rng(3)
+    T = 96
+    V = np.zeros((T, 3, 3), np.float32)
+    for k in range(T):
+        y = 20.0 + 0.25 * k
+        V[k] = [[-60 - rng.random(), y, -60], [60 + rng.random(), y, -60], [0, y, 70 + rng.random()]]
+    s = scenes.scene_random(1, 10, 1024, 1024, nlights=1)
+    s.verts, s.faces, s.face_mat = V.reshape(-1, 3), np.arange(3 * T, dtype=np.int32).reshape(-1, 3), np.zeros(T, np.int32)
+    r = ug.Renderer(0)
+    try:
+        r.set_scene(s)
+        out = np.zeros(3 * s.num_pixels, np.uint8)
+        r.render_host(r.params(s), out)
+        st = r.stats()
+        assert st.cam_pairs > 16 * T + 16384 + (1 << 20) and st.overflowed == 1
+        cpu = cpu_frame(oracle, s)
+        assert st.cam_pairs == cpu["cam_P"] and np.array_equal(out, cpu["rgb"])
+        assert np.array_equal(r.read(ug.BUF_ID), cpu["id"])
+    finally:
+        r.close()
+
+
+def test_full_size_properties(renderer, ug):
+    """Size-independent properties at a BASELINE full size (config C, 174 000 triangles, 1920x1080, 2 lights, dynamic):
+    span sums to P, offset is the exclusive scan over ALL cells, lists ascend inside a cell, every hit id is in the
+    pixel's own cell list, t > 0 exactly where id >= 0, shadow bits only 0/1, unshadowed pixels are not darker."""
+    s = scenes.scene_c()
+    renderer.set_scene(s)
+    g = parity.gpu_frame(renderer, s, frame=1, flags=0)
+    st = renderer.stats()
+    span, off, vals = g["cam_span"], g["cam_offset"], g["cam_values"]
+    assert span.sum() == st.cam_pairs == vals.size
+    assert np.array_equal(off, np.concatenate([[0], np.cumsum(span, dtype=np.uint64)[:-1]]).astype(np.uint32))
+    starts = np.zeros(vals.size, bool)
+    starts[off[span > 0]] = True
+    assert np.all((np.diff(vals.astype(np.int64)) > 0) | starts[1:])            # ascending ids inside every cell
+    hit = g["id"] >= 0
+    assert np.array_equal(hit, g["t"] > 0) and np.all(g["id"][~hit] == -2) and np.all(g["t"][~hit] == -1.0)
+    assert set(np.unique(g["shadowed"]).tolist()) <= {0, 1}
+    nby = s.height // 8
+    pix = np.flatnonzero(hit)[:: max(1, hit.sum() // 4000)]
+    for p in pix:
+        py, px = divmod(int(p), s.width)
+        c = (px // 8) * nby + py // 8
+        assert g["id"][p] in vals[off[c]:off[c] + span[c]]
+    for li in range(2):
+        ls, lo_ = g[f"light{li}_span"], g[f"light{li}_offset"]
+        assert ls.sum() == st.light_pairs[li] and lo_[0] == 0
+        assert g[f"light{li}_cell"].max() <= (s.width // 8) * nby
+    renderer.render(renderer.params(s, frame=1, flags=0))
+    assert np.array_equal(renderer.read(ug.BUF_RGB), g["rgb"])                   # same frame again -> same bytes

@@ -1,0 +1,121 @@
+"""Pin the oracle: oracle/ug_oracle.c (plain-C restatement) must reproduce, bit for bit, what the reference's own
+kernel sources compute when compiled as host C++ (oracle/_ref/libugref.so, built from /root/reference by
+oracle/Makefile) - every stage of display(): camera block, direction lattice, grid lists, hit ids, t, shadow-ray
+cells, shadow bits, RGB.  The reference ships no tests or golden vectors of its own."""
+import os
+
+import numpy as np
+import pytest
+
+import parity  # noqa: F401  (sets sys.path)
+from oracle import harness
+from uniformgrid_raytracing_b200 import scenes
+
+
+def same(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return a.shape == b.shape and np.array_equal(parity.bits(a.reshape(-1)), parity.bits(b.reshape(-1)))
+
+
+def check_frame(ref, oracle, scene, frame=0):
+    want = harness.run_frame(ref, scene, frame=frame, threads=0)
+    got = harness.run_frame(oracle, scene, frame=frame, threads=0)
+    assert set(want) == set(got)
+    bad = [k for k in want if not same(want[k], got[k])]
+    assert not bad, f"{scene.name}: oracle differs from the reference build in {bad}"
+    return want
+
+
+@pytest.mark.parametrize("kind", ["one", "tie", "behind", "near", "outside", "ka"])
+def test_micro_scenes(ref, oracle, kind):
+    out = check_frame(ref, oracle, scenes.scene_tiny(kind))
+    if kind == "tie":       # coincident triangles: the lower id takes every hit (trace_kernel.cu:38 + stable sort)
+        assert (out["id"] == 0).sum() > 0 and (out["id"] == 1).sum() == 0
+    if kind == "behind":    # |t| mirrors geometry behind the eye into the image (trace_kernel.cu:35)
+        assert (out["id"] == 1).sum() > 0
+    if kind == "outside":   # a triangle outside the frustum is clamped into border cells, never culled
+        assert out["cam_P"] > 16 and (out["id"] == 1).sum() == 0
+    if kind == "ka":        # the occluder casts a shadow on the floor
+        assert out["shadowed"].sum() > 0
+
+
+@pytest.mark.parametrize("seed,ntris,w,h,nl", [(1, 2000, 128, 64, 2), (2, 500, 96, 160, 1), (3, 6000, 256, 256, 1), (4, 50, 64, 64, 0)])
+def test_random_soups(ref, oracle, seed, ntris, w, h, nl):
+    check_frame(ref, oracle, scenes.scene_random(seed, ntris, w, h, nlights=nl))
+
+
+def test_config_a_reduced(ref, oracle):
+    out = check_frame(ref, oracle, scenes.scene_a(256, 256))
+    assert out["cam_P"] > 16370 and out["shadowed"].sum() > 1000
+
+
+def test_dynamic_transform(ref, oracle):
+    """copy_data_transform (transformation_kernel.cu:4-18) on a vertex sub-range, two different frames."""
+    s = scenes.scene_random(7, 1200, 128, 128, nlights=1)
+    s.verts = (s.verts * np.float32(0.5) + np.array([12.0, 5.0, 4.0], np.float32)).astype(np.float32)
+    s.eye, s.look = (12.0, -12.0, 6.0), (14.0, 12.0, 4.0)
+    s.dyn_offset, s.dyn_size = 300, 2100
+    a = check_frame(ref, oracle, s, frame=0)
+    b = check_frame(ref, oracle, s, frame=3)
+    assert not np.array_equal(a["verts"], b["verts"])
+
+
+def test_grid_is_sorted_and_complete(oracle):
+    """Structural invariants of the cell lists (what the reference's sort+compact+histogram guarantee)."""
+    s = scenes.scene_random(5, 3000, 128, 128)
+    out = harness.run_frame(oracle, s, stages="grid")
+    span, off, vals = out["cam_span"], out["cam_offset"], out["cam_values"]
+    assert span.sum() == out["cam_P"] == vals.size
+    assert np.array_equal(off, np.concatenate([[0], np.cumsum(span)[:-1]]).astype(np.uint32))   # exclusive scan over ALL cells
+    for c in np.flatnonzero(span > 1)[:200]:
+        seg = vals[off[c]:off[c] + span[c]]
+        assert np.all(np.diff(seg.astype(np.int64)) > 0)          # ascending triangle ids, no duplicates
+
+
+def test_grid_lists_are_conservative(oracle):
+    """The grid result equals a brute-force nearest hit over ALL triangles wherever the brute-force hit exists
+     - checked on a sample of pixels of a well-formed scene."""
+    s = scenes.scene_a(128, 128)
+    out = harness.run_frame(oracle, s, stages="trace")
+    # brute force: one giant cell holding every triangle, traced with the same code
+    T, C = s.num_tris, (s.width // 8) * (s.height // 8)
+    grid = {"P": T * C, "values": np.tile(np.arange(T, dtype=np.uint32), C), "span": np.full(C, T, np.uint32),
+            "offset": (np.arange(C, dtype=np.uint32) * T).astype(np.uint32)}
+    oracle.configure(s.width, s.height, s.fovy, 0)
+    oracle.camera_setup(s.eye, s.look, s.up, s.near, s.far)
+    brute = oracle.trace(grid, np.ascontiguousarray(s.faces), np.ascontiguousarray(s.verts))
+    assert np.array_equal(brute["id"], out["id"])
+    assert np.array_equal(parity.bits(brute["t"]), parity.bits(out["t"]))
+
+
+def test_loader_matches_obj_parser(ref, oracle, ug, tmp_path):
+    """OBJ/MTL semantics of obj_parser/: first three corners of a face, v/vt/vn forms, negative (relative) indices,
+    prefix match of usemtl against material names that keep their trailing newline, -1 without usemtl."""
+    mtl = tmp_path / "m.mtl"
+    scenes.write_material_file(str(mtl), [scenes.Material("floor2", (.1, .2, .3), (.4, .5, .6)), scenes.Material("floor", (.2, .2, .2), (.7, .8, .9)),
+                                          scenes.Material("wall", (.3, .3, .3), (.15, .25, .35), reflect=0.5)])
+    obj = tmp_path / "q.obj"
+    obj.write_text(f"# quirks\nmtllib {mtl}\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nv 0.5 0.5 1.25e0\nf 1 2 3\nusemtl floor\nf 1/1/1 2/2/2 3/3/3 4/4/4\n"
+                   "usemtl wall\nf -1 -2 -3\nusemtl flo\nf 1//1 3//2 5//3\nusemtl nosuch\nf 2 3 4\ng grp\ns off\nf 5 4 3\n")
+    want = ref.load_obj(str(obj))
+    for got in (oracle.load_obj(str(obj)), ug.parse_obj(str(obj))):
+        for a, b in zip(want, got):
+            assert same(a, b)
+    V, F, M = want
+    assert F.tolist()[1] == [0, 1, 2] and F.tolist()[2] == [4, 3, 2]      # quad truncated; relative indices
+    assert M.tolist() == [-1, 0, 2, 0, -1, -1]                            # 'floor' and 'flo' prefix-match 'floor2' (first in the list)
+    wm = ref.load_materials(str(mtl))
+    assert same(wm, oracle.load_materials(str(mtl))) and same(wm, ug.parse_materials(str(mtl)))
+    assert wm.shape == (3, 6) and abs(wm[2, 5] - 0.35) < 1e-6
+
+
+def test_generated_scene_roundtrip(ref, ug, tmp_path):
+    """Scenes written by the generator come back identical through both loaders (triangle id = file order)."""
+    s = scenes.scene_a(64, 64)
+    obj, mtl = scenes.write_obj(s, str(tmp_path / "a.obj"))
+    Vr, Fr, Mr = ref.load_obj(obj)
+    Vu, Fu, Mu = ug.parse_obj(obj)
+    assert same(Vr, Vu) and same(Fr, Fu) and same(Mr, Mu)
+    assert same(Fr, s.faces) and same(Mr, s.face_mat)
+    assert np.allclose(Vr, s.verts, rtol=0, atol=0)                      # %.9g round-trips float32 exactly
+    assert same(ref.load_materials(mtl), harness.material_table(s))
