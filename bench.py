@@ -220,7 +220,7 @@ def run_ours(args):
 
     # ---- e2e: host buffers in, host image out, wall clock
     e2e_steps = max(3, min(args.steps, 50))
-    out_np = np.zeros(3 * n_local, np.uint8)
+    out_np = host_img.numpy()[:3 * n_local]          # pinned: the copy engine writes it directly
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):

@@ -108,6 +108,7 @@ enum ug_buffer {
 	UG_BUF_LIGHT_OFFSET,     /* u32[C] */
 	UG_BUF_LIGHT_CELL,       /* u32[N]   d_map[N..2N): light cell of every pixel's shadow ray, C = outside */
 	UG_BUF_SIZELIST,         /* u32[T]   frustum_grid.h:32 d_sizeList of the camera grid */
+	UG_BUF_CAM_COUNTERS,     /* u32[32]  debug: pair counters and phase time stamps of the camera-grid build */
 	UG_BUF_COUNT_
 };
 

@@ -24,12 +24,12 @@ UG_TILE = 8
 FLAG_FULL_BUFFERS, FLAG_NO_GRAPH, FLAG_STAGE_EVENTS = 1, 2, 4
 
 (BUF_VERTEXLIST, BUF_CAM_VALUES, BUF_CAM_SPAN, BUF_CAM_OFFSET, BUF_T, BUF_ID, BUF_NORMAL, BUF_DIR, BUF_SHADOWED, BUF_RGB,
- BUF_LIGHT_VALUES, BUF_LIGHT_SPAN, BUF_LIGHT_OFFSET, BUF_LIGHT_CELL, BUF_SIZELIST) = range(15)
+ BUF_LIGHT_VALUES, BUF_LIGHT_SPAN, BUF_LIGHT_OFFSET, BUF_LIGHT_CELL, BUF_SIZELIST, BUF_CAM_COUNTERS) = range(16)
 
 _BUF_DTYPE = {BUF_VERTEXLIST: np.float32, BUF_CAM_VALUES: np.uint32, BUF_CAM_SPAN: np.uint32, BUF_CAM_OFFSET: np.uint32,
               BUF_T: np.float32, BUF_ID: np.int32, BUF_NORMAL: np.float32, BUF_DIR: np.float32, BUF_SHADOWED: np.int32,
               BUF_RGB: np.uint8, BUF_LIGHT_VALUES: np.uint32, BUF_LIGHT_SPAN: np.uint32, BUF_LIGHT_OFFSET: np.uint32,
-              BUF_LIGHT_CELL: np.uint32, BUF_SIZELIST: np.uint32}
+              BUF_LIGHT_CELL: np.uint32, BUF_SIZELIST: np.uint32, BUF_CAM_COUNTERS: np.uint32}
 
 
 class Camera(C.Structure):  # ug_camera == camera.h:7-47

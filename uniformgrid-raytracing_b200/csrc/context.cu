@@ -7,6 +7,7 @@
 #include "ugrt_internal.h"
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 int ug_fail(ug_context *ctx, int code, const char *fmt, ...)
@@ -54,6 +55,7 @@ extern "C" int ug_create(ug_context **out, int device)
 	cudaDeviceProp prop;
 	UG_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
 	ctx->num_sms = prop.multiProcessorCount;
+	ctx->use_fused = ugk_grid_fused_supported(device) && !getenv("UG_NO_FUSED");
 	UG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
 	ctx->stream = ctx->own_stream;
 	for (int i = 0; i < UG_MAX_LIGHTS; i++) {
@@ -67,6 +69,8 @@ extern "C" int ug_create(ug_context **out, int device)
 	for (auto &ev : ctx->ev_stage) UG_CUDA(ctx, cudaEventCreate(&ev));
 	UG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_fc, sizeof(FrameConst)));
 	memset(ctx->h_fc, 0, sizeof(FrameConst));
+	UG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_counters, sizeof(u32) * 4 * (1 + UG_MAX_LIGHTS)));
+	memset(ctx->h_counters, 0, sizeof(u32) * 4 * (1 + UG_MAX_LIGHTS));
 	UG_CUDA(ctx, cudaMalloc((void **)&ctx->d_fc, sizeof(FrameConst)));
 	*out = ctx;
 	return UG_OK;
@@ -78,6 +82,7 @@ static void free_grid(GridBuffers &g)
 	dfree(g.keys[0]); dfree(g.keys[1]); dfree(g.vals[0]); dfree(g.vals[1]);
 	dfree(g.span); dfree(g.offset); dfree(g.counters);
 	dfree(g.sort.tile_hist); dfree(g.sort.tile_base); dfree(g.sort.scan_state);
+	dfree(g.fused_hist); dfree(g.fused_tot); dfree(g.fused_state_a); dfree(g.fused_state_b);
 	g = GridBuffers();
 }
 static void free_rays(LightRays &r)
@@ -98,6 +103,7 @@ extern "C" void ug_destroy(ug_context *ctx)
 	dfree(ctx->d_t); dfree(ctx->d_id); dfree(ctx->d_shadowed); dfree(ctx->d_matid); dfree(ctx->d_best); dfree(ctx->d_cell_done); dfree(ctx->d_normal); dfree(ctx->d_dir); dfree(ctx->d_rgb_own);
 	if (ctx->h_rgb_pinned) cudaFreeHost(ctx->h_rgb_pinned);
 	if (ctx->h_fc) cudaFreeHost(ctx->h_fc);
+	if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
 	dfree(ctx->d_fc);
 	for (int i = 0; i < UG_MAX_LIGHTS; i++) { cudaStreamDestroy(ctx->side[i]); cudaEventDestroy(ctx->ev_join[i]); }
 	cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_trace); cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
@@ -153,8 +159,8 @@ static int alloc_grid(ug_context *ctx, GridBuffers &g, int T, int C, size_t cap)
 	}
 	UG_CUDA(ctx, dmalloc(&g.span, (size_t)C));
 	UG_CUDA(ctx, dmalloc(&g.offset, (size_t)C + 1));
-	UG_CUDA(ctx, dmalloc(&g.counters, 8));
-	UG_CUDA(ctx, cudaMemset(g.counters, 0, 8 * sizeof(u32)));
+	UG_CUDA(ctx, dmalloc(&g.counters, 32));
+	UG_CUDA(ctx, cudaMemset(g.counters, 0, 32 * sizeof(u32)));
 	const size_t he = ugk_sort_hist_entries(ctx->num_sms);
 	UG_CUDA(ctx, dmalloc(&g.sort.tile_hist, he));
 	UG_CUDA(ctx, dmalloc(&g.sort.tile_base, he + 1));
@@ -162,6 +168,15 @@ static int alloc_grid(ug_context *ctx, GridBuffers &g, int T, int C, size_t cap)
 	if (biggest < he + 2) biggest = he + 2;
 	g.sort.scan_tiles = ugk_scan_tiles(biggest) + 1;
 	UG_CUDA(ctx, dmalloc(&g.sort.scan_state, g.sort.scan_tiles + 1));
+	{ /* fused build scratch; the look-back descriptors start zeroed and are re-zeroed by the kernel itself */
+		const size_t na = ugk_grid_fused_state_a(T), nb = ugk_grid_fused_state_b(C);
+		UG_CUDA(ctx, dmalloc(&g.fused_hist, ugk_grid_fused_hist(ctx->num_sms)));
+		UG_CUDA(ctx, dmalloc(&g.fused_tot, 4 * 256));
+		UG_CUDA(ctx, dmalloc(&g.fused_state_a, na));
+		UG_CUDA(ctx, dmalloc(&g.fused_state_b, nb));
+		UG_CUDA(ctx, cudaMemset(g.fused_state_a, 0, sizeof(u64) * na));
+		UG_CUDA(ctx, cudaMemset(g.fused_state_b, 0, sizeof(u64) * nb));
+	}
 	return UG_OK;
 }
 
@@ -376,6 +391,12 @@ struct Launches { int n = 0; };
 static void enqueue_grid(ug_context *ctx, cudaStream_t s, const ViewConst *vc, GridBuffers &g, Launches &L)
 {
 	const int sms = ctx->num_sms;
+	if (ctx->use_fused && g.key_bits <= 32) {
+		const int fb = ugk_grid_fused(s, vc, ctx->d_facelist, ctx->d_vertexlist, g, sms);
+		if (fb >= 0) { g.final_buf = fb; L.n += 1; return; }
+		cudaGetLastError();   /* cooperative launch refused: fall back to the multi-kernel chain for good */
+		ctx->use_fused = false;
+	}
 	ugk_setup_bin(s, vc, ctx->d_facelist, ctx->d_vertexlist, g.T, g, sms);                              L.n += 1;
 	ugk_scan_counts(s, g, sms);                                                                         L.n += 1;
 	ugk_emit_pairs(s, vc, g, sms);                                                                      L.n += 1;
@@ -464,6 +485,10 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 	          ctx->d_rgb, ctx->d_matid, ctx->N, 1, sms);
 	L.n += 1;
 	stage_mark(ctx, k, stage_events); /* shade */
+	/* pair counts + overflow flags of every grid ride back with the frame (no extra synchronisation later) */
+	UG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->cam_grid.counters, 4 * sizeof(u32), cudaMemcpyDeviceToHost, s));
+	for (int l = 0; l < nl; l++)
+		UG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 4 * (1 + l), ctx->light_grid[l].counters, 4 * sizeof(u32), cudaMemcpyDeviceToHost, s));
 	if (stage_events) ctx->stage_marks = k;
 	UG_CUDA(ctx, cudaGetLastError());
 	return UG_OK;
@@ -575,8 +600,7 @@ static int check_overflow(ug_context *ctx, int num_lights, bool *grew)
 	gs[n++] = &ctx->cam_grid;
 	for (int l = 0; l < num_lights; l++) gs[n++] = &ctx->light_grid[l];
 	for (int i = 0; i < n; i++) {
-		u32 c[4] = {0, 0, 0, 0};
-		UG_CUDA(ctx, cudaMemcpy(c, gs[i]->counters, sizeof(c), cudaMemcpyDeviceToHost));
+		const u32 *c = ctx->h_counters + 4 * i; /* copied by the frame itself; the caller has synchronised */
 		if (c[1]) {
 			const size_t want = (size_t)c[2] + (size_t)c[2] / 4 + 1024;
 			int rc = alloc_grid(ctx, *gs[i], gs[i]->T, gs[i]->C, want);
@@ -603,17 +627,22 @@ extern "C" int ug_render_frame_host(ug_context *ctx, const ug_frame_params *p, u
 	int rc = prepare_frame(ctx, p);
 	if (rc) return rc;
 	ctx->stats.overflowed = 0;
+	/* main.cu:245: image back to the host.  A pinned / registered destination is written by the copy engine
+	 * directly; pageable memory goes through the context's pinned staging buffer. */
+	cudaPointerAttributes attr;
+	bool direct = cudaPointerGetAttributes(&attr, host_rgb) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+	cudaGetLastError();
+	unsigned char *dst = direct ? host_rgb : ctx->h_rgb_pinned;
 	for (int attempt = 0; attempt < 3; attempt++) {
 		rc = run_frame_once(ctx, p);
 		if (rc) return rc;
-		/* main.cu:245: image back to the host (pinned staging, then the caller's buffer) */
-		UG_CUDA(ctx, cudaMemcpyAsync(ctx->h_rgb_pinned, ctx->d_rgb, 3 * (size_t)ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
+		UG_CUDA(ctx, cudaMemcpyAsync(dst, ctx->d_rgb, 3 * (size_t)ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
 		UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 		bool grew = false;
 		rc = check_overflow(ctx, p->num_lights, &grew);
 		if (rc) return rc;
 		if (!grew) {
-			memcpy(host_rgb, ctx->h_rgb_pinned, 3 * (size_t)ctx->N);
+			if (!direct) memcpy(host_rgb, ctx->h_rgb_pinned, 3 * (size_t)ctx->N);
 			return UG_OK;
 		}
 		ctx->stats.overflowed = 1;
@@ -652,6 +681,7 @@ extern "C" int ug_build_frustum_grid(ug_context *ctx)
 		Launches L;
 		enqueue_grid(ctx, ctx->stream, &ctx->d_fc->cam, ctx->cam_grid, L);
 		UG_CUDA(ctx, cudaGetLastError());
+		UG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->cam_grid.counters, 4 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
 		UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 		bool grew = false;
 		rc = check_overflow(ctx, 0, &grew);
@@ -749,6 +779,7 @@ static int buffer_info(ug_context *ctx, int buffer, int index, void **ptr, size_
 	case UG_BUF_CAM_OFFSET:
 	case UG_BUF_LIGHT_OFFSET: *ptr = g->offset; *bytes = sizeof(u32) * (size_t)g->C; break;
 	case UG_BUF_SIZELIST: *ptr = g->count; *bytes = sizeof(u32) * (size_t)g->T; break;
+	case UG_BUF_CAM_COUNTERS: *ptr = ctx->cam_grid.counters; *bytes = sizeof(u32) * 32; break;
 	case UG_BUF_T: *ptr = ctx->d_t; *bytes = sizeof(float) * N; break;
 	case UG_BUF_ID: *ptr = ctx->d_id; *bytes = sizeof(int) * N; break;
 	case UG_BUF_NORMAL: *ptr = ctx->d_normal; *bytes = sizeof(float) * 3 * N; break;

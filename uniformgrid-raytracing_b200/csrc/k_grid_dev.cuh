@@ -1,0 +1,161 @@
+/* k_grid_dev.cuh -- device functions of the perspective-grid build shared by the multi-kernel path
+ * (k_grid.cu, k_sort.cu) and the fused persistent kernel (k_gridfused.cu). */
+#ifndef UG_K_GRID_DEV_CUH
+#define UG_K_GRID_DEV_CUH
+
+#include "k_common.cuh"
+
+/* grid_kernel.cu:132-146 - the exact ternaries (NaN behaviour differs from fminf/fmaxf) */
+static __device__ __forceinline__ float ug_min3(float a, float b, float c) { return (a < b) ? ((a < c) ? a : c) : ((b < c) ? b : c); }
+static __device__ __forceinline__ float ug_max3(float a, float b, float c) { return (a > b) ? ((a > c) ? a : c) : ((b > c) ? b : c); }
+static __device__ __forceinline__ int ug_clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* grid_kernel.cu:13-36 getTransformedVertex: modelview, divide by w, projection, divide by w */
+static __device__ __forceinline__ void ug_project(const float *cc, float x, float y, float z, float &nx, float &ny, float &nz)
+{
+	const float *MV = cc + 16, *P = cc + 32;
+	float a = ug_row(MV, 0, x, y, z, 1.0f), b = ug_row(MV, 1, x, y, z, 1.0f), c = ug_row(MV, 2, x, y, z, 1.0f), w = ug_row(MV, 3, x, y, z, 1.0f);
+	a = a / w; b = b / w; c = c / w;
+	const float qx = ug_row(P, 0, a, b, c, 1.0f), qy = ug_row(P, 1, a, b, c, 1.0f), qz = ug_row(P, 2, a, b, c, 1.0f), qw = ug_row(P, 3, a, b, c, 1.0f);
+	nx = qx / qw; ny = qy / qw; nz = qz / qw;
+}
+
+struct GridGeo { int nbx, nby, gy_lo, gy_hi; float ox, oy, oz; };
+
+/* One triangle of one view: the ray-independent Moeller-Trumbore record (trace_kernel.cu:158-174 /
+ * light_kernel.cu:133-148 staging arithmetic + the hoisted qvec and dot(e2,qvec)), its clamped cell
+ * rectangle (grid_kernel.cu:180-229) clipped to the owned cell rows, and its pair count (:231). */
+static __device__ __forceinline__ u32 ug_tri_setup(const float *s_cc, const GridGeo &g, const int *__restrict__ faces, const float *__restrict__ verts, int t,
+                                                   float4 *__restrict__ rec, uint2 *__restrict__ rect)
+{
+	const int i0 = faces[3 * t], i1 = faces[3 * t + 1], i2 = faces[3 * t + 2];
+	const float *p0 = verts + 3 * (size_t)i0, *p1 = verts + 3 * (size_t)i1, *p2 = verts + 3 * (size_t)i2;
+	const float ax = p0[0], ay = p0[1], az = p0[2];
+	const float bx = p1[0], by = p1[1], bz = p1[2];
+	const float cx = p2[0], cy = p2[1], cz = p2[2];
+	const float e1x = bx - ax, e1y = by - ay, e1z = bz - az;
+	const float e2x = cx - ax, e2y = cy - ay, e2z = cz - az;
+	const float tx = g.ox - ax, ty = g.oy - ay, tz = g.oz - az;
+	float qx, qy, qz;
+	ug_cross(qx, qy, qz, tx, ty, tz, e1x, e1y, e1z);       /* qvec = tvec x e1 */
+	const float e2q = ug_dot(e2x, e2y, e2z, qx, qy, qz);   /* numerator of t */
+	rec[4 * (size_t)t + 0] = make_float4(tx, ty, tz, e2q);
+	rec[4 * (size_t)t + 1] = make_float4(e1x, e1y, e1z, 0.0f);
+	rec[4 * (size_t)t + 2] = make_float4(e2x, e2y, e2z, 0.0f);
+	rec[4 * (size_t)t + 3] = make_float4(qx, qy, qz, 0.0f);
+	float n0x, n0y, n0z, n1x, n1y, n1z, n2x, n2y, n2z;
+	ug_project(s_cc, ax, ay, az, n0x, n0y, n0z);
+	ug_project(s_cc, bx, by, bz, n1x, n1y, n1z);
+	ug_project(s_cc, cx, cy, cz, n2x, n2y, n2z);
+	const float xmin = ug_min3(n0x, n1x, n2x), ymin = ug_min3(n0y, n1y, n2y);
+	const float xmax = ug_max3(n0x, n1x, n2x), ymax = ug_max3(n0y, n1y, n2y);
+	const int gx0 = ug_clampi(ug_f2i(floorf(((xmin + 1.0f) / 2.0f) * (float)g.nbx)), 0, g.nbx - 1);
+	const int gy0 = ug_clampi(ug_f2i(floorf(((ymin + 1.0f) / 2.0f) * (float)g.nby)), 0, g.nby - 1);
+	const int gx1 = ug_clampi(ug_f2i(floorf(((xmax + 1.0f) / 2.0f) * (float)g.nbx)), 0, g.nbx - 1);
+	const int gy1 = ug_clampi(ug_f2i(floorf(((ymax + 1.0f) / 2.0f) * (float)g.nby)), 0, g.nby - 1);
+	/* image-strip sharding: keep only the owned cell rows; the rectangle itself is the global one */
+	const int ry0 = max(gy0, g.gy_lo), ry1 = min(gy1, g.gy_hi);
+	const int sx = gx1 - gx0 + 1, sy = ry1 - ry0 + 1;
+	const u32 c = (sx > 0 && sy > 0) ? (u32)(sx * sy) : 0u; /* NaN vertices can invert the rectangle: no cells */
+	rect[t] = make_uint2((u32)gx0 | ((u32)gx1 << 16), (u32)ry0 | ((u32)(c ? ry1 : ry0) << 16));
+	return c;
+}
+
+/* first index in [lo,hi) with a[idx] > x */
+static __device__ __forceinline__ int ug_upper_bound(const u32 *__restrict__ a, int lo, int hi, u32 x)
+{
+	while (lo < hi) {
+		const int mid = (lo + hi) >> 1;
+		if (a[mid] > x) hi = mid; else lo = mid + 1;
+	}
+	return lo;
+}
+
+/* pair p of triangle t (grid_kernel.cu:318-325: i over x, j over y inside the rectangle) -> local cell key */
+static __device__ __forceinline__ u32 ug_pair_key(uint2 r, u32 local, int gy_lo, int gy_cnt)
+{
+	const u32 gx0 = r.x & 0xffffu, ry0 = r.y & 0xffffu, ry1 = r.y >> 16;
+	const u32 sy = ry1 - ry0 + 1;
+	const u32 i = local / sy, j = local - i * sy;
+	return (gx0 + i) * (u32)gy_cnt + (ry0 - (u32)gy_lo + j);
+}
+
+/* ---- radix sort building blocks (k_sort.cu, k_gridfused.cu); NT = threads per block, ROUNDS = keys per thread and sub-tile */
+#define RS_THREADS 256
+#define RS_ROUNDS 8
+
+static __device__ __forceinline__ void rs_chunk(u32 n, u32 G, u32 b, u32 &lo, u32 &hi)
+{
+	u32 chunk = (n + G - 1) / G;
+	chunk = (chunk + 31u) & ~31u; /* warp rounds stay 128-byte aligned */
+	const u64 l = (u64)chunk * b, h = l + chunk;
+	lo = (u32)(l < n ? l : n);
+	hi = (u32)(h < n ? h : n);
+}
+
+/* digit histogram of keys[lo,hi) into s_hist[256] (zeroed by the caller); warp-aggregated because
+ * neighbouring pairs mostly carry the same cell id */
+template <int NT>
+static __device__ __forceinline__ void rs_block_hist(const u32 *__restrict__ keys, u32 lo, u32 hi, int shift, u32 *s_hist)
+{
+	for (u32 base = lo; base < hi; base += NT) {
+		const u32 i = base + threadIdx.x;
+		const bool valid = i < hi;
+		const u32 d = valid ? ((keys[i] >> shift) & 255u) : 256u;
+		const u32 peers = __match_any_sync(UG_FULL_MASK, d);
+		if (valid && (peers & ((1u << ug_lane()) - 1u)) == 0) atomicAdd(&s_hist[d], __popc(peers));
+	}
+}
+
+/* stable scatter of the block's chunk [lo,hi): s_run[d] holds where the block's next key of digit d
+ * goes; s_cnt is (NT/32) x 257 scratch.  Order inside the block = (sub-tile, warp, round, lane) = input order. */
+template <int NT, int ROUNDS>
+static __device__ __forceinline__ void rs_block_scatter(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in, u32 *__restrict__ keys_out,
+                                                        u32 *__restrict__ vals_out, u32 lo, u32 hi, int shift, u32 (*s_cnt)[257], u32 *s_run)
+{
+	constexpr int WARPS = NT / 32;
+	const u32 warp = threadIdx.x >> 5, lane = ug_lane(), lt = (1u << lane) - 1u;
+	for (u32 tile = lo; tile < hi; tile += NT * ROUNDS) {
+		for (u32 i = threadIdx.x; i < WARPS * 257; i += NT) (&s_cnt[0][0])[i] = 0;
+		__syncthreads();
+		u32 key[ROUNDS], rank[ROUNDS];
+#pragma unroll
+		for (int r = 0; r < ROUNDS; r++) { /* warp w owns keys [tile + w*32*ROUNDS, +32*ROUNDS): round r covers 32 consecutive keys */
+			const u32 i = tile + warp * (32 * ROUNDS) + r * 32 + lane;
+			const bool valid = i < hi;
+			key[r] = valid ? keys_in[i] : 0xffffffffu;
+			const u32 d = valid ? ((key[r] >> shift) & 255u) : 256u;
+			const u32 peers = __match_any_sync(UG_FULL_MASK, d);
+			const u32 prev = s_cnt[warp][d];
+			__syncwarp();
+			if ((peers & lt) == 0) s_cnt[warp][d] = prev + __popc(peers);
+			__syncwarp();
+			rank[r] = prev + __popc(peers & lt);
+		}
+		__syncthreads();
+		for (u32 d = threadIdx.x; d < 256; d += NT) { /* per-warp counts -> per-warp start positions; advance the block's run */
+			u32 run = s_run[d];
+#pragma unroll
+			for (int w = 0; w < WARPS; w++) {
+				const u32 c = s_cnt[w][d];
+				s_cnt[w][d] = run;
+				run += c;
+			}
+			s_run[d] = run;
+		}
+		__syncthreads();
+#pragma unroll
+		for (int r = 0; r < ROUNDS; r++) {
+			const u32 i = tile + warp * (32 * ROUNDS) + r * 32 + lane;
+			if (i < hi) {
+				const u32 d = (key[r] >> shift) & 255u;
+				const u32 pos = s_cnt[warp][d] + rank[r];
+				keys_out[pos] = key[r];
+				vals_out[pos] = vals_in[i];
+			}
+		}
+		__syncthreads();
+	}
+}
+
+#endif

@@ -13,131 +13,35 @@
  *                      inside a cell (frustum_grid.h:298 relies on cudppSort being stable).
  * Memory-bound: 2 reads + 1 write of 8 B per pair and pass.
  */
-#include "k_common.cuh"
+#include "k_grid_dev.cuh"
 
-#define RS_THREADS 256
-#define RS_WARPS (RS_THREADS / 32)
-#define RS_ROUNDS 8                       /* keys per thread and sub-tile */
-#define RS_TILE (RS_THREADS * RS_ROUNDS)  /* 2048 */
 #define RS_BLOCKS_PER_SM 2
-
-static __device__ __forceinline__ void rs_chunk(u32 n, u32 G, u32 b, u32 &lo, u32 &hi)
-{
-	u32 chunk = (n + G - 1) / G;
-	chunk = (chunk + 31u) & ~31u; /* warp rounds stay 128-byte aligned */
-	const u64 l = (u64)chunk * b, h = l + chunk;
-	lo = (u32)(l < n ? l : n);
-	hi = (u32)(h < n ? h : n);
-}
 
 __global__ void __launch_bounds__(RS_THREADS) rs_hist(const u32 *__restrict__ keys, const u32 *__restrict__ n_dev, u32 n_max, int shift,
                                                       u32 *__restrict__ hist)
 {
-	__shared__ u32 s_hist[256];
+	__shared__ u32 s_hist[257];
 	const u32 n = min(*n_dev, n_max), G = gridDim.x, b = blockIdx.x;
 	s_hist[threadIdx.x] = 0;
 	__syncthreads();
 	u32 lo, hi;
 	rs_chunk(n, G, b, lo, hi);
-	for (u32 base = lo; base < hi; base += RS_THREADS) {
-		const u32 i = base + threadIdx.x;
-		const bool valid = i < hi;
-		const u32 d = valid ? ((keys[i] >> shift) & 255u) : 256u;
-		/* warp-aggregated: neighbouring pairs mostly carry the same cell id */
-		const u32 peers = __match_any_sync(UG_FULL_MASK, d);
-		if (valid && (peers & ((1u << ug_lane()) - 1u)) == 0) atomicAdd(&s_hist[d], __popc(peers));
-	}
+	rs_block_hist<RS_THREADS>(keys, lo, hi, shift, s_hist);
 	__syncthreads();
 	hist[(size_t)threadIdx.x * G + b] = s_hist[threadIdx.x];
-}
-
-/* exclusive scan of m = 256*G counters by ONE block (m is a few 10^4) */
-__global__ void __launch_bounds__(1024) rs_scan(const u32 *__restrict__ in, u32 *__restrict__ out, u32 m)
-{
-	__shared__ u32 s_warp[32];
-	const u32 per = (m + 1023u) / 1024u;
-	const u32 lo = min(threadIdx.x * per, m), hi = min(lo + per, m);
-	u32 sum = 0;
-	for (u32 i = lo; i < hi; i++) sum += in[i];
-	/* block exclusive scan of the per-thread sums */
-	u32 incl = sum;
-	for (int o = 1; o < 32; o <<= 1) {
-		const u32 v = __shfl_up_sync(UG_FULL_MASK, incl, o);
-		if ((int)ug_lane() >= o) incl += v;
-	}
-	if (ug_lane() == 31) s_warp[threadIdx.x >> 5] = incl;
-	__syncthreads();
-	if (threadIdx.x < 32) {
-		u32 w = s_warp[threadIdx.x], wi = w;
-		for (int o = 1; o < 32; o <<= 1) {
-			const u32 v = __shfl_up_sync(UG_FULL_MASK, wi, o);
-			if ((int)threadIdx.x >= o) wi += v;
-		}
-		s_warp[threadIdx.x] = wi - w;
-	}
-	__syncthreads();
-	u32 run = s_warp[threadIdx.x >> 5] + incl - sum;
-	for (u32 i = lo; i < hi; i++) {
-		const u32 v = in[i];
-		out[i] = run;
-		run += v;
-	}
 }
 
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in, u32 *__restrict__ keys_out,
                                                          u32 *__restrict__ vals_out, const u32 *__restrict__ n_dev, u32 n_max, int shift,
                                                          const u32 *__restrict__ base)
 {
-	__shared__ u32 s_cnt[RS_WARPS][257]; /* per warp, per digit; [256] = dummy bin of out-of-range lanes */
+	__shared__ u32 s_cnt[RS_THREADS / 32][257]; /* per warp, per digit; [256] = dummy bin of out-of-range lanes */
 	__shared__ u32 s_run[256];           /* where the block's next key of each digit goes */
 	const u32 n = min(*n_dev, n_max), G = gridDim.x, b = blockIdx.x;
-	const u32 warp = threadIdx.x >> 5, lane = ug_lane(), lt = (1u << lane) - 1u;
 	s_run[threadIdx.x] = base[(size_t)threadIdx.x * G + b];
 	u32 lo, hi;
 	rs_chunk(n, G, b, lo, hi);
-	for (u32 tile = lo; tile < hi; tile += RS_TILE) {
-		for (u32 i = threadIdx.x; i < RS_WARPS * 257; i += RS_THREADS) (&s_cnt[0][0])[i] = 0;
-		__syncthreads();
-		u32 key[RS_ROUNDS], rank[RS_ROUNDS];
-		/* warp w owns keys [tile + w*256, +256): round r covers 32 consecutive keys */
-#pragma unroll
-		for (int r = 0; r < RS_ROUNDS; r++) {
-			const u32 i = tile + warp * (32 * RS_ROUNDS) + r * 32 + lane;
-			const bool valid = i < hi;
-			key[r] = valid ? keys_in[i] : 0xffffffffu;
-			const u32 d = valid ? ((key[r] >> shift) & 255u) : 256u;
-			const u32 peers = __match_any_sync(UG_FULL_MASK, d);
-			const u32 prev = s_cnt[warp][d];
-			__syncwarp();
-			if ((peers & lt) == 0) s_cnt[warp][d] = prev + __popc(peers);
-			__syncwarp();
-			rank[r] = prev + __popc(peers & lt);
-		}
-		__syncthreads();
-		{ /* thread d: turn per-warp counts into per-warp start positions, advance the block's run */
-			const u32 d = threadIdx.x;
-			u32 run = s_run[d];
-#pragma unroll
-			for (int w = 0; w < RS_WARPS; w++) {
-				const u32 c = s_cnt[w][d];
-				s_cnt[w][d] = run;
-				run += c;
-			}
-			s_run[d] = run;
-		}
-		__syncthreads();
-#pragma unroll
-		for (int r = 0; r < RS_ROUNDS; r++) {
-			const u32 i = tile + warp * (32 * RS_ROUNDS) + r * 32 + lane;
-			if (i < hi) {
-				const u32 d = (key[r] >> shift) & 255u;
-				const u32 pos = s_cnt[warp][d] + rank[r];
-				keys_out[pos] = key[r];
-				vals_out[pos] = vals_in[i];
-			}
-		}
-		__syncthreads();
-	}
+	rs_block_scatter<RS_THREADS, RS_ROUNDS>(keys_in, vals_in, keys_out, vals_out, lo, hi, shift, s_cnt, s_run);
 }
 
 size_t ugk_sort_hist_entries(int sms) { return (size_t)256 * sms * RS_BLOCKS_PER_SM; }

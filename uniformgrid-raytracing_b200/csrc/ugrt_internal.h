@@ -55,6 +55,8 @@ struct GridBuffers {       /* FrustumGrid, frustum_grid.h:15-68 */
 	u32 *offset = nullptr;     /* [C+1] */
 	u32 *counters = nullptr;   /* [8]: 0 = P (clamped), 1 = overflow flag, 2 = P wanted */
 	SortScratch sort;
+	u32 *fused_hist = nullptr, *fused_tot = nullptr; /* scratch of the fused build (k_gridfused.cu) */
+	u64 *fused_state_a = nullptr, *fused_state_b = nullptr;
 	size_t cap = 0;            /* pair capacity */
 	int final_buf = 0;         /* which of vals[] holds the sorted list */
 	int key_bits = 0;
@@ -83,6 +85,7 @@ struct ug_context {
 	int stage_marks = 0;
 	std::string err;
 	int num_sms = 148;
+	bool use_fused = true;      /* fused cooperative grid build when the device supports it (UG_NO_FUSED=1 disables) */
 
 	/* Model (scene.h:13-57) */
 	std::vector<float> h_vertexlist, h_materiallist;
@@ -101,6 +104,7 @@ struct ug_context {
 	/* frame constants */
 	FrameConst *h_fc = nullptr; /* pinned */
 	FrameConst *d_fc = nullptr;
+	u32 *h_counters = nullptr;  /* pinned [1+UG_MAX_LIGHTS][4]: counters of every grid, copied back by the frame */
 	int num_lights = 0;
 
 	/* grids */
@@ -148,6 +152,12 @@ void ugk_setup_bin(cudaStream_t s, const ViewConst *vc, const int *faces, const 
 void ugk_scan_counts(cudaStream_t s, GridBuffers &g, int sms);
 void ugk_emit_pairs(cudaStream_t s, const ViewConst *vc, GridBuffers &g, int sms);
 void ugk_cell_offsets(cudaStream_t s, GridBuffers &g, int sms);
+/* fused single-kernel build (k_gridfused.cu) */
+bool ugk_grid_fused_supported(int device);
+size_t ugk_grid_fused_state_a(int T);
+size_t ugk_grid_fused_state_b(int C);
+size_t ugk_grid_fused_hist(int sms);
+int ugk_grid_fused(cudaStream_t s, const ViewConst *vc, const int *faces, const float *verts, GridBuffers &g, int sms);
 /* radix sort / scan primitives (k_sort.cu) */
 size_t ugk_scan_tiles(size_t n);
 /* stable LSD radix sort of (key,val) pairs on `bits` key bits; n read from *n_dev (<= n_max).
