@@ -56,6 +56,7 @@ extern "C" int ug_create(ug_context **out, int device)
 	UG_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
 	ctx->num_sms = prop.multiProcessorCount;
 	ctx->use_fused = ugk_grid_fused_supported(device) && !getenv("UG_NO_FUSED");
+	ctx->use_fused_regroup = ugk_regroup_fused_supported(device) && !getenv("UG_NO_FUSED");
 	UG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
 	ctx->stream = ctx->own_stream;
 	for (int i = 0; i < UG_MAX_LIGHTS; i++) {
@@ -63,6 +64,9 @@ extern "C" int ug_create(ug_context **out, int device)
 		UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
 	}
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming));
+	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_init, cudaEventDisableTiming));
+	UG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_init, cudaStreamNonBlocking));
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_trace, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaEventCreate(&ctx->ev_t0));
 	UG_CUDA(ctx, cudaEventCreate(&ctx->ev_t1));
@@ -87,7 +91,8 @@ static void free_grid(GridBuffers &g)
 }
 static void free_rays(LightRays &r)
 {
-	dfree(r.cell); dfree(r.pix); dfree(r.span); dfree(r.offset); dfree(r.cursor); dfree(r.scan_state); dfree(r.queue); dfree(r.queue_count);
+	dfree(r.cell); dfree(r.pix); dfree(r.span); dfree(r.offset); dfree(r.cursor);
+	dfree(r.item_off); dfree(r.items); dfree(r.counters); dfree(r.state_a); dfree(r.state_b);
 	r = LightRays();
 }
 
@@ -106,7 +111,7 @@ extern "C" void ug_destroy(ug_context *ctx)
 	if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
 	dfree(ctx->d_fc);
 	for (int i = 0; i < UG_MAX_LIGHTS; i++) { cudaStreamDestroy(ctx->side[i]); cudaEventDestroy(ctx->ev_join[i]); }
-	cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_trace); cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
+	cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_fork2); cudaEventDestroy(ctx->ev_init); cudaStreamDestroy(ctx->side_init); cudaEventDestroy(ctx->ev_trace); cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
 	for (auto &ev : ctx->ev_stage) cudaEventDestroy(ev);
 	cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
@@ -188,11 +193,16 @@ static int alloc_rays(ug_context *ctx, LightRays &r, int N, int C)
 	UG_CUDA(ctx, dmalloc(&r.span, (size_t)C + 1));
 	UG_CUDA(ctx, dmalloc(&r.offset, (size_t)C + 2));
 	UG_CUDA(ctx, dmalloc(&r.cursor, (size_t)C + 1));
-	r.queue_cap = (size_t)N / 16 + 4096;
-	UG_CUDA(ctx, dmalloc(&r.queue, r.queue_cap));
-	UG_CUDA(ctx, dmalloc(&r.queue_count, 4));
-	r.scan_tiles = ugk_scan_tiles((size_t)C + 2) + 1;
-	UG_CUDA(ctx, dmalloc(&r.scan_state, r.scan_tiles + 1));
+	UG_CUDA(ctx, dmalloc(&r.item_off, (size_t)C + 2));
+	r.item_cap = (size_t)N + (size_t)C; /* worst case: one item per ray (every list longer than 1024) */
+	UG_CUDA(ctx, dmalloc(&r.items, r.item_cap));
+	UG_CUDA(ctx, dmalloc(&r.counters, 4));
+	UG_CUDA(ctx, cudaMemset(r.counters, 0, 4 * sizeof(u32)));
+	const size_t ns = ugk_regroup_state_entries(C);
+	UG_CUDA(ctx, dmalloc(&r.state_a, ns));
+	UG_CUDA(ctx, dmalloc(&r.state_b, ns));
+	UG_CUDA(ctx, cudaMemset(r.state_a, 0, sizeof(u64) * ns));
+	UG_CUDA(ctx, cudaMemset(r.state_b, 0, sizeof(u64) * ns));
 	return UG_OK;
 }
 
@@ -409,20 +419,23 @@ static void enqueue_light_grid(ug_context *ctx, cudaStream_t s, int l, Launches 
 {
 	enqueue_grid(ctx, s, &ctx->d_fc->light[l], ctx->light_grid[l], L);
 }
+static void enqueue_light_zero(ug_context *ctx, cudaStream_t s, int l)
+{ /* independent of the primary rays: issued early on the light's branch */
+	LightRays &r = ctx->rays[l];
+	cudaMemsetAsync(r.span, 0, sizeof(u32) * ((size_t)ctx->C_light + 1), s);
+	cudaMemsetAsync(r.cursor, 0, sizeof(u32) * ((size_t)ctx->C_light + 1), s);
+}
 static void enqueue_light_regroup(ug_context *ctx, cudaStream_t s, int l, Launches &L)
 {
 	LightRays &r = ctx->rays[l];
-	const int sms = ctx->num_sms, C = ctx->C_light;
-	cudaMemsetAsync(r.span, 0, sizeof(u32) * ((size_t)C + 1), s);
-	cudaMemsetAsync(r.cursor, 0, sizeof(u32) * ((size_t)C + 1), s);
-	ugk_map_rays(s, ctx->d_fc, l, ctx->d_t, ctx->d_dir, r.cell, r.span, ctx->N, sms);                               L.n += 1;
-	ugk_exclusive_scan(s, r.span, r.offset, (size_t)C + 1, r.scan_state, r.scan_tiles, sms);            L.n += 1;
-	ugk_scatter_rays(s, r.cell, r.offset, r.cursor, r.pix, ctx->N, sms);                                L.n += 1;
+	if (!ugk_regroup(s, ctx->d_fc, l, ctx->light_grid[l], r, ctx->d_t, ctx->d_dir, ctx->N, ctx->C_light, ctx->num_sms, ctx->use_fused_regroup, &L.n)) {
+		ctx->use_fused_regroup = false; /* cooperative launch refused: phase-by-phase launches from now on */
+		ugk_regroup(s, ctx->d_fc, l, ctx->light_grid[l], r, ctx->d_t, ctx->d_dir, ctx->N, ctx->C_light, ctx->num_sms, false, &L.n);
+	}
 }
 static void enqueue_light_shadow(ug_context *ctx, cudaStream_t s, int l, Launches &L)
 {
-	LightRays &r = ctx->rays[l];
-	ugk_shadow(s, ctx->d_fc, l, ctx->light_grid[l], r, ctx->d_t, ctx->d_dir, ctx->d_shadowed, ctx->N, ctx->C_light, ctx->num_sms); L.n += 2;
+	ugk_shadow(s, ctx->d_fc, l, ctx->light_grid[l], ctx->rays[l], ctx->d_t, ctx->d_dir, ctx->d_shadowed, ctx->N, ctx->C_light, ctx->num_sms); L.n += 1;
 }
 static void enqueue_light_rays(ug_context *ctx, cudaStream_t s, int l, Launches &L)
 {
@@ -453,12 +466,21 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 		UG_CUDA(ctx, cudaEventRecord(ctx->ev_fork, s));
 		for (int l = 0; l < nl; l++) {
 			UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side[l], ctx->ev_fork, 0));
+			enqueue_light_zero(ctx, ctx->side[l], l);
 			enqueue_light_grid(ctx, ctx->side[l], l, L);
 		}
 	}
-	ugk_init_pixels(s, ctx->d_fc, ctx->d_t, ctx->d_id, ctx->d_shadowed, ctx->d_best, full ? ctx->d_normal : nullptr, ctx->d_dir, ctx->N, sms);
+	if (parallel) { /* the per-pixel reset + ray directions do not depend on the grid: their own branch of the graph */
+		UG_CUDA(ctx, cudaEventRecord(ctx->ev_fork2, s));
+		UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_init, ctx->ev_fork2, 0));
+		ugk_init_pixels(ctx->side_init, ctx->d_fc, ctx->d_t, ctx->d_id, ctx->d_shadowed, ctx->d_best, full ? ctx->d_normal : nullptr, ctx->d_dir, ctx->N, sms);
+		UG_CUDA(ctx, cudaEventRecord(ctx->ev_init, ctx->side_init));
+	} else {
+		ugk_init_pixels(s, ctx->d_fc, ctx->d_t, ctx->d_id, ctx->d_shadowed, ctx->d_best, full ? ctx->d_normal : nullptr, ctx->d_dir, ctx->N, sms);
+	}
 	L.n += 1;
 	enqueue_grid(ctx, s, &ctx->d_fc->cam, ctx->cam_grid, L);
+	if (parallel) UG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_init, 0));
 	stage_mark(ctx, k, stage_events); /* 2: camera grid done */
 	ugk_trace(s, ctx->d_fc, ctx->cam_grid, ctx->d_best, ctx->d_cell_done, ctx->d_dir, ctx->d_t, ctx->d_id, full ? ctx->d_normal : nullptr, sms);
 	L.n += 1;
@@ -473,6 +495,7 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 		}
 	} else {
 		for (int l = 0; l < nl; l++) {
+			enqueue_light_zero(ctx, s, l);
 			enqueue_light_grid(ctx, s, l, L);
 			stage_mark(ctx, k, stage_events); /* 4+3l: light grid */
 			enqueue_light_regroup(ctx, s, l, L);
@@ -716,6 +739,7 @@ extern "C" int ug_shadow_pass(ug_context *ctx, int light_id, const ug_camera *li
 	if (rc) return rc;
 	for (int attempt = 0; attempt < 3; attempt++) {
 		Launches L;
+		enqueue_light_zero(ctx, ctx->stream, light_id);
 		enqueue_light_grid(ctx, ctx->stream, light_id, L);
 		UG_CUDA(ctx, cudaGetLastError());
 		UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

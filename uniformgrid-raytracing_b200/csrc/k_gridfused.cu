@@ -42,69 +42,6 @@ struct GridFusedArgs {
 	u64 *state_b;   /* look-back descriptors of the offset scan (tiles of GF_THREADS*4 cells) */
 };
 
-/* Decoupled look-back: tile `tile` publishes `total`, returns the sum of all earlier tiles.  Called by
- * warp 0 of the block.  All tiles < `tile` are either finished or held by a resident block. */
-/* phase time stamps for profiling (ns, low 32 bits of %globaltimer), written by block 0 into counters[8..] */
-static __device__ __forceinline__ void gf_stamp(u32 *counters, int k)
-{
-	if (blockIdx.x == 0 && threadIdx.x == 0) {
-		unsigned long long t;
-		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-		counters[8 + k] = (u32)t;
-	}
-}
-
-static __device__ __forceinline__ u32 gf_lookback(volatile u64 *desc, u32 tile, u32 total)
-{
-	const u32 lane = ug_lane();
-	u32 prefix = 0;
-	if (tile == 0) {
-		if (lane == 0) desc[0] = (2ull << 32) | total;
-		return 0;
-	}
-	if (lane == 0) desc[tile] = (1ull << 32) | total;
-	int look = (int)tile - 1;
-	while (true) {
-		const int idx = look - (int)lane;
-		u64 d = 2ull << 32; /* before tile 0: inclusive prefix 0 */
-		if (idx >= 0) {
-			do { d = desc[idx]; } while ((d >> 32) == 0);
-		}
-		const u32 flag = (u32)(d >> 32), val = (u32)d;
-		const u32 incl = __ballot_sync(UG_FULL_MASK, flag == 2);
-		u32 part = val;
-		if (incl) part = ((int)lane <= __ffs(incl) - 1) ? val : 0u;
-		for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(UG_FULL_MASK, part, o);
-		prefix += part;
-		if (incl) break;
-		look -= 32;
-	}
-	if (lane == 0) desc[tile] = (2ull << 32) | (u64)(prefix + total);
-	return prefix;
-}
-
-/* block-wide exclusive scan of one value per thread; returns the thread's exclusive prefix, total in `total` */
-static __device__ __forceinline__ u32 gf_block_scan(u32 v, u32 *s_warp, u32 &total)
-{
-	u32 incl = v;
-	for (int o = 1; o < 32; o <<= 1) {
-		const u32 x = __shfl_up_sync(UG_FULL_MASK, incl, o);
-		if ((int)ug_lane() >= o) incl += x;
-	}
-	__syncthreads();
-	if (ug_lane() == 31) s_warp[threadIdx.x >> 5] = incl;
-	__syncthreads();
-	u32 off = 0;
-	total = 0;
-#pragma unroll
-	for (int w = 0; w < GF_THREADS / 32; w++) {
-		const u32 c = s_warp[w];
-		if (w < (int)(threadIdx.x >> 5)) off += c;
-		total += c;
-	}
-	return off + incl - v;
-}
-
 __global__ void __launch_bounds__(GF_THREADS, 2) k_grid_fused(const GridFusedArgs a)
 {
 	cg::grid_group grid = cg::this_grid();
@@ -139,9 +76,9 @@ __global__ void __launch_bounds__(GF_THREADS, 2) k_grid_fused(const GridFusedArg
 			a.count[t] = c;
 		}
 		u32 total;
-		const u32 excl = gf_block_scan(c, s_warp, total);
+		const u32 excl = ug_block_scan<GF_THREADS>(c, s_warp, total);
 		if (tid < 32) {
-			const u32 p = gf_lookback(a.state_a, tile, total);
+			const u32 p = ug_lookback(a.state_a, tile, total);
 			if (tid == 0) s_pref = p;
 		}
 		__syncthreads();
@@ -204,9 +141,9 @@ __global__ void __launch_bounds__(GF_THREADS, 2) k_grid_fused(const GridFusedArg
 #pragma unroll
 			for (int k = 0; k < 4; k++) { v[k] = (base + k < (u32)C) ? a.span[base + k] : 0u; sum += v[k]; }
 			u32 total;
-			u32 run = gf_block_scan(sum, s_warp, total);
+			u32 run = ug_block_scan<GF_THREADS>(sum, s_warp, total);
 			if (tid < 32) {
-				const u32 p = gf_lookback(a.state_b, tile, total);
+				const u32 p = ug_lookback(a.state_b, tile, total);
 				if (tid == 0) s_pref = p;
 			}
 			__syncthreads();
@@ -237,7 +174,7 @@ __global__ void __launch_bounds__(GF_THREADS, 2) k_grid_fused(const GridFusedArg
 		}
 		{ /* where this block's keys of digit `tid` go: all smaller digits + the same digit in earlier blocks */
 			u32 total;
-			const u32 digit_start = gf_block_scan(tid < 256 ? a.tot[pass * 256 + tid] : 0u, s_warp, total);
+			const u32 digit_start = ug_block_scan<GF_THREADS>(tid < 256 ? a.tot[pass * 256 + tid] : 0u, s_warp, total);
 			if (tid < 256) {
 				u32 before = 0;
 #pragma unroll 8

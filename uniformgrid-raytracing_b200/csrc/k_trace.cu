@@ -111,75 +111,92 @@ __global__ void __launch_bounds__(64) k_trace(const FrameConst *__restrict__ fc,
 			const u32 bits = __ballot_sync(UG_FULL_MASK, head);
 			if ((tid & 31) == 0) s_head[p >> 5] = bits;
 		}
-		__syncthreads();
+		/* Staging is decoupled from the runs: windows of 64 consecutive pairs, the next window's records in
+		 * flight in registers while the current one is tested. */
+		float4 p0 = make_float4(0, 0, 0, 0), p1 = p0, p2 = p0, p3 = p0;
+		if (lo + tid < hi) {
+			const float4 *src = rec + 4 * (size_t)s_val[tid];
+			p0 = src[0]; p1 = src[1]; p2 = src[2]; p3 = src[3];
+		}
 
-		u32 pos = lo;
-		while (pos < hi) { /* one run = the part of one cell's list that lies inside this item */
-			const u32 cell = s_key[pos - lo + 1];
-			u32 end = hi; /* next run head after pos */
-			{
-				u32 q = pos - lo + 1, w = q >> 5;
-				if (w < TR_ITEM / 32) {
-					u32 bits = s_head[w] & (0xffffffffu << (q & 31));
-					if ((q & 31) == 0) bits = s_head[w];
-					while (true) {
-						if (bits) { end = min(hi, lo + (w << 5) + (u32)__ffs(bits) - 1); break; }
-						if (++w >= TR_ITEM / 32) break;
-						bits = s_head[w];
-					}
-				}
+		/* state of the run being walked (a run = the part of one cell's list inside this item) */
+		bool have = false;
+		u32 cell = 0, run_start = lo, hit = 0xffffffffu;
+		int pix = 0;
+		float dx = 0.0f, dy = 0.0f, dz = 1.0f, best = 99999999.9f;
+
+		for (u32 wlo = lo; wlo < hi; wlo += TR_BATCH) { /* the last window (whi == hi) also closes the last run */
+			const u32 whi = min(wlo + TR_BATCH, hi);
+			__syncthreads();
+			if (wlo + tid < whi) { s_rec[4 * tid + 0] = p0; s_rec[4 * tid + 1] = p1; s_rec[4 * tid + 2] = p2; s_rec[4 * tid + 3] = p3; }
+			__syncthreads();
+			if (whi + tid < hi) {
+				const float4 *src = rec + 4 * (size_t)s_val[whi - lo + tid];
+				p0 = src[0]; p1 = src[1]; p2 = src[2]; p3 = src[3];
 			}
-			const bool whole = (s_key[pos - lo] != cell) && (s_key[end - lo + 1] != cell);
-
-			const int gx = (int)cell / gy_cnt, gyl = (int)cell - gx * gy_cnt;   /* trace_kernel.cu:138 (strip-local) */
-			const int px = gx * UG_TILE + (tid & 7), pyl = gyl * UG_TILE + (tid >> 3);
-			const int pix = pyl * W + px;                                        /* trace_kernel.cu:91 */
-			const float dx = dir[3 * (size_t)pix], dy = dir[3 * (size_t)pix + 1], dz = dir[3 * (size_t)pix + 2];
-
-			float best = 99999999.9f; /* trace_kernel.cu:126 */
-			u32 hit = 0xffffffffu;    /* absolute pair position of the best hit */
-			for (u32 base = pos; base < end; base += TR_BATCH) {
-				const u32 cnt = min((u32)TR_BATCH, end - base);
-				__syncthreads();
-				if ((u32)tid < cnt) {
-					const float4 *src = rec + 4 * (size_t)s_val[base - lo + tid];
-					s_rec[4 * tid + 0] = src[0];
-					s_rec[4 * tid + 1] = src[1];
-					s_rec[4 * tid + 2] = src[2];
-					s_rec[4 * tid + 3] = src[3];
+			u32 p = wlo;
+			while (true) {
+				const bool at_end = p >= hi;
+				const bool head = at_end || ((s_head[(p - lo) >> 5] >> ((p - lo) & 31)) & 1u);
+				if (head && have) { /* the run [run_start, p) is complete */
+					const bool whole = (s_key[run_start - lo] != cell) && (s_key[p - lo + 1] != cell);
+					if (whole) {
+						if (hit != 0xffffffffu) finalize_pixel(s_cc, dx, dy, dz, best, s_val[hit - lo], pix, rec, out_t, out_id, out_normal);
+					} else {
+						if (hit != 0xffffffffu) atomicMin((unsigned long long *)&best_buf[pix], ((u64)__float_as_uint(best) << 32) | (u64)hit);
+						const u32 c_lo = offset[cell], c_hi = c_lo + span[cell];
+						const u32 parts = (c_hi - 1) / TR_ITEM - c_lo / TR_ITEM + 1;
+						__threadfence();
+						__syncthreads();
+						if (tid == 0) s_ticket = atomicAdd(&cell_done[cell], 1u);
+						__syncthreads();
+						if (s_ticket == parts - 1) { /* last item of this cell: every partial result is in best_buf */
+							__threadfence();
+							const u64 m = __ldcg((const unsigned long long *)&best_buf[pix]);
+							if (m != ~0ull)
+								finalize_pixel(s_cc, dx, dy, dz, __uint_as_float((u32)(m >> 32)), __ldg(&vals[(u32)m]), pix, rec, out_t, out_id, out_normal);
+							if (tid == 0) cell_done[cell] = 0; /* ready for the next frame */
+						}
+					}
+					have = false;
 				}
-				__syncthreads();
-				for (u32 k = 0; k < cnt; k++) {
-					float t;
-					if (ug_intersect_lds(rec_base + k * 64u, dx, dy, dz, t)) {
-						t = fabsf(t);                    /* trace_kernel.cu:35 */
-						if (t < best && t > 0.0f) {      /* :38 */
-							best = t;
-							hit = base + k;
+				if (at_end || p >= whi) break;
+				if (head) { /* a new run starts at p */
+					cell = s_key[p - lo + 1];
+					const int gx = (int)cell / gy_cnt, gyl = (int)cell - gx * gy_cnt;   /* trace_kernel.cu:138 (strip-local) */
+					const int px = gx * UG_TILE + (tid & 7), pyl = gyl * UG_TILE + (tid >> 3);
+					pix = pyl * W + px;                                                  /* trace_kernel.cu:91 */
+					dx = dir[3 * (size_t)pix]; dy = dir[3 * (size_t)pix + 1]; dz = dir[3 * (size_t)pix + 2];
+					best = 99999999.9f; /* trace_kernel.cu:126 */
+					hit = 0xffffffffu;  /* absolute pair position of the best hit */
+					run_start = p;
+					have = true;
+				}
+				u32 e = whi; /* next run head after p, inside this window */
+				{
+					const u32 q = p - lo + 1;
+					u32 w = q >> 5;
+					if (w < TR_ITEM / 32) {
+						u32 bits = s_head[w] & (0xffffffffu << (q & 31));
+						while (true) {
+							if (bits) { e = min(whi, lo + (w << 5) + (u32)__ffs(bits) - 1); break; }
+							if (++w >= TR_ITEM / 32) break;
+							bits = s_head[w];
 						}
 					}
 				}
-			}
-
-			if (whole) {
-				if (hit != 0xffffffffu) finalize_pixel(s_cc, dx, dy, dz, best, s_val[hit - lo], pix, rec, out_t, out_id, out_normal);
-			} else {
-				if (hit != 0xffffffffu) atomicMin((unsigned long long *)&best_buf[pix], ((u64)__float_as_uint(best) << 32) | (u64)hit);
-				const u32 c_lo = offset[cell], c_hi = c_lo + span[cell];
-				const u32 parts = (c_hi - 1) / TR_ITEM - c_lo / TR_ITEM + 1;
-				__threadfence();
-				__syncthreads();
-				if (tid == 0) s_ticket = atomicAdd(&cell_done[cell], 1u);
-				__syncthreads();
-				if (s_ticket == parts - 1) { /* last item of this cell: every partial result is in best_buf */
-					__threadfence();
-					const u64 m = __ldcg((const unsigned long long *)&best_buf[pix]);
-					if (m != ~0ull)
-						finalize_pixel(s_cc, dx, dy, dz, __uint_as_float((u32)(m >> 32)), __ldg(&vals[(u32)m]), pix, rec, out_t, out_id, out_normal);
-					if (tid == 0) cell_done[cell] = 0; /* ready for the next frame */
+				for (u32 k = p; k < e; k++) {
+					float t;
+					if (ug_intersect_lds(rec_base + (k - wlo) * 64u, dx, dy, dz, t)) {
+						t = fabsf(t);                    /* trace_kernel.cu:35 */
+						if (t < best && t > 0.0f) {      /* :38 */
+							best = t;
+							hit = k;
+						}
+					}
 				}
+				p = e;
 			}
-			pos = end;
 		}
 	}
 }

@@ -69,22 +69,25 @@ struct LightRays {         /* DecisionData's regroup state (decision_data.h:72-8
 	u32 *span = nullptr;   /* [C+1] rays per light cell (last = outside) */
 	u32 *offset = nullptr; /* [C+2] */
 	u32 *cursor = nullptr; /* [C+1] */
-	uint4 *queue = nullptr; /* long-list segments of the shadow pass: (first ray, ray count, cell, segment) */
-	u32 *queue_count = nullptr;
-	size_t queue_cap = 0;
-	u64 *scan_state = nullptr;
-	size_t scan_tiles = 0;
+	u32 *item_off = nullptr; /* [C+1] first work item of every cell */
+	uint2 *items = nullptr;  /* work items of the shadow pass: (cell, local index) */
+	u32 *counters = nullptr; /* [0] number of items, [1] ticket */
+	u64 *state_a = nullptr, *state_b = nullptr; /* look-back descriptors (self-resetting) */
+	size_t item_cap = 0;
 };
 
 struct ug_context {
 	int device = 0;
 	cudaStream_t own_stream = nullptr, stream = nullptr;
 	cudaStream_t side[UG_MAX_LIGHTS] = {};
+	cudaStream_t side_init = nullptr;
+	cudaEvent_t ev_fork2 = nullptr, ev_init = nullptr;
 	cudaEvent_t ev_fork = nullptr, ev_trace = nullptr, ev_join[UG_MAX_LIGHTS] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
 	cudaEvent_t ev_stage[40] = {};
 	int stage_marks = 0;
 	std::string err;
 	int num_sms = 148;
+	bool use_fused_regroup = true;
 	bool use_fused = true;      /* fused cooperative grid build when the device supports it (UG_NO_FUSED=1 disables) */
 
 	/* Model (scene.h:13-57) */
@@ -170,9 +173,11 @@ void ugk_exclusive_scan(cudaStream_t s, const u32 *in, u32 *out, size_t n, u64 *
 void ugk_init_pixels(cudaStream_t s, const FrameConst *fc, float *t, int *id, int *shadowed, u64 *best, float *normal, float *dir, int N, int sms);
 void ugk_trace(cudaStream_t s, const FrameConst *fc, const GridBuffers &g, u64 *best, u32 *cell_done, const float *dir, float *t, int *id, float *normal,
                int sms);
-/* K7/K8 shadow */
-void ugk_map_rays(cudaStream_t s, const FrameConst *fc, int light, const float *t, const float *dir, u32 *light_cell, u32 *ray_span, int N, int sms);
-void ugk_scatter_rays(cudaStream_t s, const u32 *light_cell, const u32 *ray_offset, u32 *cursor, u32 *ray_pix, int N, int sms);
+/* K7/K8 shadow (k_shadow.cu) */
+bool ugk_regroup_fused_supported(int device);
+size_t ugk_regroup_state_entries(int C);
+bool ugk_regroup(cudaStream_t s, const FrameConst *fc, int light, const GridBuffers &g, const LightRays &r, const float *t, const float *dir, int N, int C,
+                 int sms, bool fused, int *launches);
 void ugk_shadow(cudaStream_t s, const FrameConst *fc, int light, const GridBuffers &g, const LightRays &r, const float *t, const float *dir, int *shadowed,
                 int N, int C, int sms);
 /* K10 shade */
