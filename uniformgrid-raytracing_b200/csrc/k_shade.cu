@@ -53,11 +53,48 @@ void ugk_transform(cudaStream_t s, float *vertexlist, const float *orig, int siz
 	if (rest) k_transform_scalar<<<min((rest + 255) / 256, sms * 8), 256, 0, s>>>(dst, orig, 4 * groups, rest, fc);
 }
 
+/* one pixel: shader_kernel.cu:165-221 + :46-86 (+ :347-359 when apply_shadow) */
+static __device__ __forceinline__ u32 shade_pixel(const float *R, float ex, float ey, float ez, float Lvx, float Lvy, float Lvz, float tv, float dx, float dy,
+                                                  float dz, int tri, int is_shadowed, const float4 *__restrict__ rec, const int *__restrict__ mat_idx,
+                                                  const float *__restrict__ mat_list, int mat_count, int apply_shadow, int &idx_out)
+{
+	float cr = 0.0f, cg = 0.0f, cb = 0.0f;
+	const int idx = (tri >= 0) ? mat_idx[tri] : -1; /* the reference reads mat_idx[-2] on a miss; ours: black */
+	idx_out = idx;
+	if (idx >= 0 && idx < mat_count && tv > 0.0f) {
+		const float Px = ex + tv * dx, Py = ey + tv * dy, Pz = ez + tv * dz;
+		/* normal as rckernel_alpha left it: abs(normalize(cross(normalize(e1), normalize(e2)))), trace_kernel.cu:234-243 */
+		const float4 r1 = rec[4 * (size_t)tri + 1], r2 = rec[4 * (size_t)tri + 2];
+		float ax = r1.x, ay = r1.y, az = r1.z, bx = r2.x, by = r2.y, bz = r2.z, nx, ny, nz;
+		ug_normalize(ax, ay, az);
+		ug_normalize(bx, by, bz);
+		ug_cross(nx, ny, nz, ax, ay, az, bx, by, bz);
+		ug_normalize(nx, ny, nz);
+		nx = (nx < 0) ? nx * -1.0f : nx; ny = (ny < 0) ? ny * -1.0f : ny; nz = (nz < 0) ? nz * -1.0f : nz;
+		/* lambert_color_pixel */
+		const float Pvx = R[0] * Px + R[4] * Py + R[8] * Pz, Pvy = R[1] * Px + R[5] * Py + R[9] * Pz, Pvz = R[2] * Px + R[6] * Py + R[10] * Pz;
+		float Nvx = R[0] * nx + R[4] * ny + R[8] * nz, Nvy = R[1] * nx + R[5] * ny + R[9] * nz, Nvz = R[2] * nx + R[6] * ny + R[10] * nz;
+		ug_normalize(Nvx, Nvy, Nvz);
+		float ldx = Pvx - Lvx, ldy = Pvy - Lvy, ldz = Pvz - Lvz;
+		ug_normalize(ldx, ldy, ldz);
+		const float kr = mat_list[idx * UG_MATERIAL_SIZE + 3], kg = mat_list[idx * UG_MATERIAL_SIZE + 4], kb = mat_list[idx * UG_MATERIAL_SIZE + 5];
+		cr += kr * 0.5f; cg += kg * 0.5f; cb += kb * 0.5f;  /* ambient term uses the DIFFUSE colour, :180-186 */
+		float dd = ug_dot(ldx, ldy, ldz, Nvx, Nvy, Nvz);
+		if (!(dd > 0)) dd *= -1.0f;
+		if (dd > 0) { cr += kr * 1.0f * dd; cg += kg * 1.0f * dd; cb += kb * 1.0f * dd; }
+		cr = cr > 1.0f ? 1.0f : cr; cg = cg > 1.0f ? 1.0f : cg; cb = cb > 1.0f ? 1.0f : cb;
+	}
+	unsigned char r8 = (unsigned char)(cr * 255.0f), g8 = (unsigned char)(cg * 255.0f), b8 = (unsigned char)(cb * 255.0f);
+	if (apply_shadow && is_shadowed == 1) { r8 /= 3; g8 /= 3; b8 /= 3; } /* shader_kernel.cu:351-356 */
+	return (u32)r8 | ((u32)g8 << 8) | ((u32)b8 << 16);
+}
+
+/* 4 consecutive pixels per thread: 16-byte loads of t/id/shadowed, 3 x 16-byte loads of dir, the 12 RGB bytes leave
+ * as three 32-bit stores (N is a multiple of 64, every buffer is 16-byte aligned) */
 __global__ void __launch_bounds__(256) k_shade(const FrameConst *__restrict__ fc, const float *__restrict__ t, const float *__restrict__ dir,
                                               const int *__restrict__ id, const int *__restrict__ shadowed, const float4 *__restrict__ rec,
-                                              const int *__restrict__ mat_idx,
-                                              const float *__restrict__ mat_list, int mat_count, unsigned char *__restrict__ rgb, int *__restrict__ mat_out,
-                                              int N, int apply_shadow)
+                                              const int *__restrict__ mat_idx, const float *__restrict__ mat_list, int mat_count,
+                                              unsigned char *__restrict__ rgb, int *__restrict__ mat_out, int N, int apply_shadow)
 {
 	const ViewConst &cam = fc->cam;
 	const float *R = fc->shade_mv;
@@ -67,39 +104,22 @@ __global__ void __launch_bounds__(256) k_shade(const FrameConst *__restrict__ fc
 	const float Lvx = R[0] * l0 + R[4] * l1 + R[8] * l2;
 	const float Lvy = R[1] * l0 + R[5] * l1 + R[9] * l2;
 	const float Lvz = R[2] * l0 + R[6] * l1 + R[10] * l2;
-	for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < N; pix += gridDim.x * blockDim.x) {
-		float cr = 0.0f, cg = 0.0f, cb = 0.0f;
-		const int tri = id[pix];
-		const int idx = (tri >= 0) ? mat_idx[tri] : -1; /* the reference reads mat_idx[-2] on a miss; ours: black */
-		if (mat_out) mat_out[pix] = idx;                /* shader_kernel.cu:176 */
-		const float tv = t[pix];
-		if (idx >= 0 && idx < mat_count && tv > 0.0f) {
-			const float dx = dir[3 * (size_t)pix], dy = dir[3 * (size_t)pix + 1], dz = dir[3 * (size_t)pix + 2];
-			const float Px = ex + tv * dx, Py = ey + tv * dy, Pz = ez + tv * dz;
-			/* normal as rckernel_alpha left it: abs(normalize(cross(normalize(e1), normalize(e2)))), trace_kernel.cu:234-243 */
-			const float4 r1 = rec[4 * (size_t)tri + 1], r2 = rec[4 * (size_t)tri + 2];
-			float ax = r1.x, ay = r1.y, az = r1.z, bx = r2.x, by = r2.y, bz = r2.z, nx, ny, nz;
-			ug_normalize(ax, ay, az);
-			ug_normalize(bx, by, bz);
-			ug_cross(nx, ny, nz, ax, ay, az, bx, by, bz);
-			ug_normalize(nx, ny, nz);
-			nx = (nx < 0) ? nx * -1.0f : nx; ny = (ny < 0) ? ny * -1.0f : ny; nz = (nz < 0) ? nz * -1.0f : nz;
-			/* lambert_color_pixel */
-			const float Pvx = R[0] * Px + R[4] * Py + R[8] * Pz, Pvy = R[1] * Px + R[5] * Py + R[9] * Pz, Pvz = R[2] * Px + R[6] * Py + R[10] * Pz;
-			float Nvx = R[0] * nx + R[4] * ny + R[8] * nz, Nvy = R[1] * nx + R[5] * ny + R[9] * nz, Nvz = R[2] * nx + R[6] * ny + R[10] * nz;
-			ug_normalize(Nvx, Nvy, Nvz);
-			float ldx = Pvx - Lvx, ldy = Pvy - Lvy, ldz = Pvz - Lvz;
-			ug_normalize(ldx, ldy, ldz);
-			const float kr = mat_list[idx * UG_MATERIAL_SIZE + 3], kg = mat_list[idx * UG_MATERIAL_SIZE + 4], kb = mat_list[idx * UG_MATERIAL_SIZE + 5];
-			cr += kr * 0.5f; cg += kg * 0.5f; cb += kb * 0.5f;  /* ambient term uses the DIFFUSE colour, :180-186 */
-			float dd = ug_dot(ldx, ldy, ldz, Nvx, Nvy, Nvz);
-			if (!(dd > 0)) dd *= -1.0f;
-			if (dd > 0) { cr += kr * 1.0f * dd; cg += kg * 1.0f * dd; cb += kb * 1.0f * dd; }
-			cr = cr > 1.0f ? 1.0f : cr; cg = cg > 1.0f ? 1.0f : cg; cb = cb > 1.0f ? 1.0f : cb;
-		}
-		unsigned char r8 = (unsigned char)(cr * 255.0f), g8 = (unsigned char)(cg * 255.0f), b8 = (unsigned char)(cb * 255.0f);
-		if (apply_shadow && shadowed[pix] == 1) { r8 /= 3; g8 /= 3; b8 /= 3; } /* shader_kernel.cu:351-356 */
-		rgb[3 * (size_t)pix + 0] = r8; rgb[3 * (size_t)pix + 1] = g8; rgb[3 * (size_t)pix + 2] = b8;
+	const int groups = N / 4;
+	for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
+		const float4 tv = ((const float4 *)t)[g];
+		const int4 tri = ((const int4 *)id)[g];
+		const int4 sh = ((const int4 *)shadowed)[g];
+		const float4 d0 = ((const float4 *)dir)[3 * (size_t)g], d1 = ((const float4 *)dir)[3 * (size_t)g + 1], d2 = ((const float4 *)dir)[3 * (size_t)g + 2];
+		int m0, m1, m2, m3;
+		const u32 c0 = shade_pixel(R, ex, ey, ez, Lvx, Lvy, Lvz, tv.x, d0.x, d0.y, d0.z, tri.x, sh.x, rec, mat_idx, mat_list, mat_count, apply_shadow, m0);
+		const u32 c1 = shade_pixel(R, ex, ey, ez, Lvx, Lvy, Lvz, tv.y, d0.w, d1.x, d1.y, tri.y, sh.y, rec, mat_idx, mat_list, mat_count, apply_shadow, m1);
+		const u32 c2 = shade_pixel(R, ex, ey, ez, Lvx, Lvy, Lvz, tv.z, d1.z, d1.w, d2.x, tri.z, sh.z, rec, mat_idx, mat_list, mat_count, apply_shadow, m2);
+		const u32 c3 = shade_pixel(R, ex, ey, ez, Lvx, Lvy, Lvz, tv.w, d2.y, d2.z, d2.w, tri.w, sh.w, rec, mat_idx, mat_list, mat_count, apply_shadow, m3);
+		if (mat_out) ((int4 *)mat_out)[g] = make_int4(m0, m1, m2, m3); /* shader_kernel.cu:176 */
+		u32 *out = (u32 *)rgb + 3 * (size_t)g;
+		out[0] = c0 | (c1 << 24);
+		out[1] = (c1 >> 8) | (c2 << 16);
+		out[2] = (c2 >> 16) | (c3 << 8);
 	}
 }
 
@@ -115,7 +135,7 @@ void ugk_shade(cudaStream_t s, const FrameConst *fc, const float *t, const float
                const float *mat_list, int mat_count, unsigned char *rgb, int *mat_out, int N, int apply_shadow, int sms)
 {
 	if (N <= 0) return;
-	k_shade<<<min((N + 255) / 256, sms * 8), 256, 0, s>>>(fc, t, dir, id, shadowed, rec, mat_idx, mat_list, mat_count, rgb, mat_out, N, apply_shadow);
+	k_shade<<<min((N / 4 + 255) / 256, sms * 8), 256, 0, s>>>(fc, t, dir, id, shadowed, rec, mat_idx, mat_list, mat_count, rgb, mat_out, N, apply_shadow);
 }
 void ugk_add_shadows(cudaStream_t s, const int *shadowed, unsigned char *rgb, int N, int sms)
 {

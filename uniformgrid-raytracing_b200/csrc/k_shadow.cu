@@ -278,7 +278,7 @@ bool ugk_regroup_fused_supported(int device)
 	cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
 	if (!coop) return false;
 	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_regroup, RG_THREADS, 0) != cudaSuccess) return false;
-	return n >= 1;
+	return n >= 2;
 }
 size_t ugk_regroup_state_entries(int C) { return ((size_t)C + 2 + RG_THREADS * 4 - 1) / (RG_THREADS * 4) + 2; }
 
@@ -294,7 +294,7 @@ bool ugk_regroup(cudaStream_t s, const FrameConst *fc, int light, const GridBuff
 	if (fused) {
 		int phase = -1;
 		void *args[] = {(void *)&a, (void *)&phase};
-		if (cudaLaunchCooperativeKernel((const void *)k_regroup, dim3((unsigned)sms), dim3(RG_THREADS), args, 0, s) == cudaSuccess) {
+		if (cudaLaunchCooperativeKernel((const void *)k_regroup, dim3((unsigned)sms * 2), dim3(RG_THREADS), args, 0, s) == cudaSuccess) {
 			if (launches) *launches += 1;
 			return true;
 		}
