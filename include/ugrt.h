@@ -85,6 +85,7 @@ typedef struct ug_frame_params {
 	int strip_index, strip_count; /* image-strip sharding: this context renders cell rows
 	                                 [strip_index*NBY/strip_count, (strip_index+1)*NBY/strip_count); 0,1 = whole frame */
 	int flags;          /* UG_FLAG_* */
+	int bounces;        /* row R: reflection bounces after shading (0 = the reference's committed display()); needs ug_model_set_reflect */
 } ug_frame_params;
 
 #define UG_FLAG_FULL_BUFFERS 1 /* also fill the reference's normal/dir/shadowed buffers (decision_data.h:66-82) */
@@ -146,6 +147,9 @@ int ug_model_set(ug_context *ctx, const float *vertexlist, int num_vertices, con
 /* host-side parse only (no device): two-call protocol, pass NULL arrays to get the counts */
 int ug_obj_parse(const char *obj_path, int *num_vertices, int *num_faces, float *vertexlist, int *facelist, int *matidx);
 int ug_material_parse(const char *file, int *num_materials, float *materiallist);
+/* reflectivity per material: the MTL `r` value (obj_parser/obj_parser.cpp:262-266 keeps it in obj_material.reflect; the
+ * 6-float material file of scene.h:370-439 has no slot for it).  Row R is an authored spec - see DESIGN.md. */
+int ug_model_set_reflect(ug_context *ctx, const float *reflect, int num_materials);
 int ug_model_init_orig_list(ug_context *ctx, int vertices_size, int vertices_offset); /* scene.h:336-368 */
 int ug_model_rotate_bunny(ug_context *ctx, float rot_factor);                         /* scene.h:122-139 */
 

@@ -61,6 +61,8 @@ class CpuLib:
             "load_obj": (C.c_int, [C.c_char_p, _i, _i, _f, _i, _i]),
             "load_materials": (C.c_int, [C.c_char_p, _i, _f]),
         }
+        if kind == "oracle":   # row R has no reference code: only the restatement carries the (authored) spec
+            sig["reflect"] = (None, [_f, _i, C.c_int, _f, _f, _i, _b, _f, _i, _f, C.c_int, _f, C.c_int])
         for name, (res, args) in sig.items():
             fn = getattr(self.lib, p + name)
             fn.restype, fn.argtypes = res, args
@@ -165,6 +167,16 @@ class CpuLib:
     def add_shadows(self, img, shadowed):
         self._add_shadows(self._p(img, _b), self._p(shadowed, _i))
 
+    def reflect(self, verts, faces, t, d, ids, img, cam_pos, mat_idx, mat_list, mat_reflect, bounces: int):
+        """Row R (authored spec): reflection bounces on top of the shaded + shadowed frame `img` (modified in place)."""
+        cam_pos = np.ascontiguousarray(cam_pos, dtype=np.float32)
+        mat_idx = np.ascontiguousarray(mat_idx, np.int32)
+        mat_list = np.ascontiguousarray(mat_list, np.float32)
+        mat_reflect = np.ascontiguousarray(mat_reflect, np.float32)
+        self._reflect(self._p(verts, _f), self._p(faces, _i), faces.shape[0], self._p(t, _f), self._p(d, _f), self._p(ids, _i),
+                      self._p(img, _b), self._p(cam_pos, _f), self._p(mat_idx, _i), self._p(mat_list, _f), mat_list.size // 6,
+                      self._p(mat_reflect, _f), bounces)
+
     def load_obj(self, path: str):
         nv, nf = C.c_int(0), C.c_int(0)
         rc = self._load_obj(path.encode(), C.byref(nv), C.byref(nf), None, None, None)
@@ -203,8 +215,13 @@ def material_table(scene) -> np.ndarray:
     return np.asarray(rows, dtype=np.float32)
 
 
+def reflect_table(scene) -> np.ndarray:
+    """Reflectivity per material as the MTL `r` line carries it (%.6f round trip)."""
+    return np.asarray([float("%.6f" % m.reflect) for m in scene.materials], dtype=np.float32)
+
+
 def run_frame(lib: CpuLib, scene, frame: int = 0, threads: int = 0, stages: str = "all",
-              timings: Optional[dict] = None) -> Dict[str, np.ndarray]:
+              timings: Optional[dict] = None, reflect: bool = False) -> Dict[str, np.ndarray]:
     """One display() (main.cu:59-302) on the CPU: [transform ->] camera grid -> primary rays -> per
     light (light camera, ray->cell map, light grid, shadow rays) -> shade -> shadow modulation.
     Returns every stage's output for bit-exact comparison."""
@@ -274,6 +291,13 @@ def run_frame(lib: CpuLib, scene, frame: int = 0, threads: int = 0, stages: str 
     tick("shade", t0)
     out["material_id"] = ids
     out["rgb"] = img
+    if getattr(scene, "bounces", 0) > 0 and lib.kind == "oracle" and reflect:
+        t0 = time.perf_counter()
+        img2 = img.copy()
+        lib.reflect(verts.reshape(-1), faces, prim["t"], prim["dir"], prim["id"], img2, cam_pos, scene.face_mat, mat_list,
+                    reflect_table(scene), scene.bounces)
+        tick("reflect", t0)
+        out["rgb_reflect"] = img2
     return out
 
 

@@ -466,6 +466,111 @@ void orc_add_shadows(unsigned char *img, int *is_shadowed)
 			for (int k = 0; k < 3; k++) img[3 * (size_t)pix + k] /= 3;
 }
 
+/* ------------------------------------------------------------------ row R: reflection (AUTHORED SPEC, parity unpinned)
+ * The reference has no reflection / uniform-grid / DDA code, so this is the specification the CUDA
+ * path is tested against, written with the reference's own arithmetic (intersectTri, light_kernel.cu:13-50, and
+ * lambert_color_pixel, shader_kernel.cu:46-86).  It is grid independent: the nearest hit is the minimum over ALL
+ * triangles, ties to the lower triangle id, so any conservative acceleration structure must reproduce it.
+ *
+ *   local0 = the shaded + shadowed RGB8 of the primary hit, as floats;  k0 = reflectivity of its material
+ *   if bounces == 0, the pixel is a miss, or !(k0 > 0): the pixel is left as it is
+ *   acc = (1-k0)*local0;  w = k0;  ray = reflect(P0, d0, tri0)
+ *   for b = 1..bounces:  hit = nearest(ray) or stop;  local = RGB8 of the lambert shade of the hit (no shadow test);
+ *        k = (b < bounces) ? reflectivity(hit) : 0;   if !(k > 0) { acc += w*local; stop }
+ *        acc += (w*(1-k))*local;  w *= k;  ray = reflect(P, r, tri)
+ *   pixel = (uchar)acc
+ *   reflect(P, d, tri): n = normalize(cross(e1,e2)), flipped to face the incoming ray (dot(n,d) > 0 => n = -n);
+ *                       origin O = P + 1e-3*n;  direction r = d - (2*dot(d,n))*n  (not renormalised)
+ *   nearest(O, r): triangles in ascending id, tvec = O - v0, Moeller-Trumbore as intersectTri; accept signed t with
+ *                  t > 0 and t < best (best starts at 99999999.9f, strict '<': the lower id wins ties) */
+static void lambert_u8(const float *P, const float *v0, const float *v1, const float *v2, const float *kd, float *out)
+{
+	const float *R = g_cc + 16;
+	float e1[3], e2[3], n[3], Lv[3], Pv[3], Nv[3], ld[3], color[3] = {0.0f, 0.0f, 0.0f};
+	for (int k = 0; k < 3; k++) { e1[k] = v1[k] - v0[k]; e2[k] = v2[k] - v0[k]; }
+	normalize3(e1); normalize3(e2);
+	cross3(n, e1, e2);
+	normalize3(n);
+	for (int k = 0; k < 3; k++) n[k] = (n[k] < 0) ? n[k] * -1 : n[k]; /* trace_kernel.cu:241-243 */
+	for (int k = 0; k < 3; k++) {
+		Lv[k] = R[k] * g_light[0] + R[4 + k] * g_light[1] + R[8 + k] * g_light[2];
+		Pv[k] = R[k] * P[0] + R[4 + k] * P[1] + R[8 + k] * P[2];
+		Nv[k] = R[k] * n[0] + R[4 + k] * n[1] + R[8 + k] * n[2];
+	}
+	normalize3(Nv);
+	for (int k = 0; k < 3; k++) ld[k] = Pv[k] - Lv[k];
+	normalize3(ld);
+	for (int k = 0; k < 3; k++) color[k] += kd[k] * 0.5f;
+	float dd = dot3(ld, Nv);
+	if (!(dd > 0)) dd *= -1;
+	if (dd > 0)
+		for (int k = 0; k < 3; k++) color[k] += kd[k] * 1.0f * dd;
+	for (int k = 0; k < 3; k++) {
+		if (color[k] > 1.0f) color[k] = 1.0f;
+		out[k] = (float)(unsigned char)(color[k] * 255);
+	}
+}
+
+static void reflect_ray(const float *P, const float *d, const float *v0, const float *v1, const float *v2, float *O, float *r)
+{
+	float e1[3], e2[3], n[3];
+	for (int k = 0; k < 3; k++) { e1[k] = v1[k] - v0[k]; e2[k] = v2[k] - v0[k]; }
+	cross3(n, e1, e2);
+	normalize3(n);
+	if (dot3(n, d) > 0) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
+	const float s = 2.0f * dot3(d, n);
+	for (int k = 0; k < 3; k++) { O[k] = P[k] + 1e-3f * n[k]; r[k] = d[k] - s * n[k]; }
+}
+
+void orc_reflect(float *verts, int *tris, int T, float *t, float *dir, int *id, unsigned char *rgb, float *cam_pos, int *mat_idx, float *mat_list,
+                 int mat_count, float *mat_reflect, int bounces)
+{
+	const int N = g_W * g_H;
+	if (bounces <= 0) return;
+#pragma omp parallel for schedule(dynamic, 64) num_threads(g_threads)
+	for (int pix = 0; pix < N; pix++) {
+		int tri = id[pix];
+		if (tri < 0 || !(t[pix] > 0)) continue;
+		int m = mat_idx[tri];
+		float k = (m >= 0 && m < mat_count) ? mat_reflect[m] : 0.0f;
+		if (!(k > 0)) continue;
+		float P[3], d[3], O[3], r[3], acc[3], w = k;
+		for (int c = 0; c < 3; c++) {
+			d[c] = dir[3 * (size_t)pix + c];
+			P[c] = cam_pos[c] + t[pix] * d[c];
+			acc[c] = (1.0f - k) * (float)rgb[3 * (size_t)pix + c];
+		}
+		const float *v0 = verts + 3 * (size_t)tris[3 * tri], *v1 = verts + 3 * (size_t)tris[3 * tri + 1], *v2 = verts + 3 * (size_t)tris[3 * tri + 2];
+		reflect_ray(P, d, v0, v1, v2, O, r);
+		for (int b = 1; b <= bounces; b++) {
+			float best = 99999999.9f;
+			int hit = -1;
+			for (int q = 0; q < T; q++) {
+				float tv[3], e1[3], e2[3], tt;
+				stage_triangle(verts, tris, q, O, tv, e1, e2);
+				if (!moller_trumbore(tv, e1, e2, r, &tt)) continue;
+				if (tt > 0 && tt < best) { best = tt; hit = q; }
+			}
+			if (hit < 0) break;
+			float local[3];
+			for (int c = 0; c < 3; c++) { P[c] = O[c] + best * r[c]; d[c] = r[c]; }
+			v0 = verts + 3 * (size_t)tris[3 * hit]; v1 = verts + 3 * (size_t)tris[3 * hit + 1]; v2 = verts + 3 * (size_t)tris[3 * hit + 2];
+			m = mat_idx[hit];
+			if (m >= 0 && m < mat_count) lambert_u8(P, v0, v1, v2, mat_list + 6 * m + 3, local);
+			else local[0] = local[1] = local[2] = 0.0f;
+			k = (b < bounces && m >= 0 && m < mat_count) ? mat_reflect[m] : 0.0f;
+			if (!(k > 0)) {
+				for (int c = 0; c < 3; c++) acc[c] = acc[c] + w * local[c];
+				break;
+			}
+			for (int c = 0; c < 3; c++) acc[c] = acc[c] + (w * (1.0f - k)) * local[c];
+			w = w * k;
+			reflect_ray(P, d, v0, v1, v2, O, r);
+		}
+		for (int c = 0; c < 3; c++) rgb[3 * (size_t)pix + c] = (unsigned char)acc[c];
+	}
+}
+
 /* ------------------------------------------------------------------ a22: loader semantics
  * obj_parser/obj_parser.cpp:296-421 (OBJ), :177-294 (MTL), obj_parser/list.cpp:115-126 (prefix
  * match on usemtl), scene.h:225-331 (flatten: first three indices of each face, 0-based). */

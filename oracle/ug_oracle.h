@@ -38,6 +38,10 @@ void orc_shadow(unsigned *value_list, float *verts, int *tris, unsigned *span, u
 void orc_shade(unsigned char *img, float *normal, float *t, float *dir, int *id, float *cam_pos, int *mat_idx,
                float *mat_list, int mat_count);
 void orc_add_shadows(unsigned char *img, int *is_shadowed);
+/* row R (reflection): authored spec, parity unpinned - see ug_oracle.c.  `rgb` holds the shaded + shadowed frame on
+ * entry and the final frame on return; g_cc / g_light must be what was resident when orc_shade ran. */
+void orc_reflect(float *verts, int *tris, int T, float *t, float *dir, int *id, unsigned char *rgb, float *cam_pos, int *mat_idx, float *mat_list,
+                 int mat_count, float *mat_reflect, int bounces);
 int orc_load_obj(char *path, int *num_vertices, int *num_faces, float *vertexlist, int *facelist, int *matidx);
 int orc_load_materials(char *file, int *num_materials, float *materiallist);
 

@@ -169,6 +169,34 @@ def test_pair_arena_overflow_regrows(ug, oracle):
         r.close()
 
 
+def reflective(scene, ks, bounces):
+    for m, k in zip(scene.materials, ks):
+        m.reflect = k
+    scene.bounces = bounces
+    return scene
+
+
+@pytest.mark.parametrize("make,bounces", [(lambda: reflective(scenes.scene_random(31, 1500, 160, 96, nlights=1), (0.5, 0.25), 2), 2),
+                                          (lambda: reflective(scenes.scene_random(32, 4000, 128, 128, nlights=2), (0.75, 0.0), 1), 1),
+                                          (lambda: reflective(scenes.scene_a(128, 128), (0.5, 0.3), 2), 2),
+                                          (lambda: reflective(scenes.scene_tiny("ka", 96, 96), (0.6, 0.6), 3), 3)])
+def test_reflection_row_r(renderer, ug, oracle, make, bounces):
+    """Row R (authored spec, parity unpinned: the reference has no reflection code): uniform grid + 3-D DDA + scan
+    compaction on the GPU against the oracle's brute-force nearest hit over ALL triangles, bit-exact RGB."""
+    s = make()
+    renderer.set_scene(s)
+    cpu = harness.run_frame(oracle, s, threads=0, reflect=True)
+    gpu = parity.gpu_frame(renderer, s, flags=0, bounces=bounces)
+    assert np.count_nonzero(cpu["rgb_reflect"] != cpu["rgb"]) > 50                    # the bounce changes pixels
+    assert not parity.compare(gpu, cpu, keys=["t", "id", "shadowed"], verbose=False)  # the primary pass is untouched
+    diff = np.flatnonzero(gpu["rgb"] != cpu["rgb_reflect"])
+    assert diff.size == 0, f"{diff.size} bytes differ, first at {diff[:8]}"
+    again = parity.gpu_frame(renderer, s, flags=0, bounces=bounces)                   # replay
+    assert np.array_equal(again["rgb"], gpu["rgb"])
+    plain = parity.gpu_frame(renderer, s, flags=0, bounces=0)                         # bounces off -> the reference frame
+    assert np.array_equal(plain["rgb"], cpu["rgb"])
+
+
 def test_full_size_properties(renderer, ug):
     """Size-independent properties at a BASELINE full size (config C, 174 000 triangles, 1920x1080, 2 lights, dynamic):
     span sums to P, offset is the exclusive scan over ALL cells, lists ascend inside a cell, every hit id is in the

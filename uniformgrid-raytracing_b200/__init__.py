@@ -48,7 +48,7 @@ class FrameParams(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("fovy", C.c_float), ("nearPlane", C.c_float), ("farPlane", C.c_float),
                 ("eye", C.c_float * 3), ("look", C.c_float * 3), ("up", C.c_float * 3), ("num_lights", C.c_int),
                 ("lights", LightS * UG_MAX_LIGHTS), ("transform", C.c_int), ("rot_factor", C.c_float),
-                ("strip_index", C.c_int), ("strip_count", C.c_int), ("flags", C.c_int)]
+                ("strip_index", C.c_int), ("strip_count", C.c_int), ("flags", C.c_int), ("bounces", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -87,7 +87,7 @@ def lib() -> C.CDLL:
             "ug_model_load": (C.c_int, [vp, C.c_char_p, C.c_char_p]),
             "ug_model_set": (C.c_int, [vp, f, C.c_int, i, C.c_int, i, f, C.c_int]),
             "ug_obj_parse": (C.c_int, [C.c_char_p, i, i, f, i, i]), "ug_material_parse": (C.c_int, [C.c_char_p, i, f]),
-            "ug_model_init_orig_list": (C.c_int, [vp, C.c_int, C.c_int]), "ug_model_rotate_bunny": (C.c_int, [vp, C.c_float]),
+            "ug_model_init_orig_list": (C.c_int, [vp, C.c_int, C.c_int]), "ug_model_set_reflect": (C.c_int, [vp, f, C.c_int]), "ug_model_rotate_bunny": (C.c_int, [vp, C.c_float]),
             "ug_set_screen": (C.c_int, [vp, C.c_int, C.c_int, C.c_float]), "ug_set_strip": (C.c_int, [vp, C.c_int, C.c_int]),
             "ug_update_light_position": (C.c_int, [vp, f, C.c_int]),
             "ug_fill_coordinates_data": (C.c_int, [vp, C.POINTER(Camera)]), "ug_build_frustum_grid": (C.c_int, [vp]),
@@ -206,10 +206,13 @@ class Renderer:
         self.set_model(scene.verts, scene.faces, scene.face_mat, mat_list)
         if scene.dyn_size:
             self._ck(self.L.ug_model_init_orig_list(self.ctx, scene.dyn_size, scene.dyn_offset), "ug_model_init_orig_list")
+        if any(m.reflect > 0 for m in scene.materials):
+            refl = np.asarray([float("%.6f" % m.reflect) for m in scene.materials], np.float32)
+            self._ck(self.L.ug_model_set_reflect(self.ctx, refl.ctypes.data_as(C.POINTER(C.c_float)), refl.size), "ug_model_set_reflect")
         self.scene = scene
 
     # ---- frames
-    def params(self, scene=None, frame: int = 0, flags: int = 0, strip=(0, 1)) -> FrameParams:
+    def params(self, scene=None, frame: int = 0, flags: int = 0, strip=(0, 1), bounces: int = 0) -> FrameParams:
         s = scene or self.scene
         p = FrameParams()
         p.width, p.height, p.fovy, p.nearPlane, p.farPlane = s.width, s.height, float(s.fovy), s.near, s.far
@@ -221,6 +224,7 @@ class Renderer:
         p.rot_factor = float(np.float32(np.float32(s.rot_step) * np.float32(frame + 1)))
         p.strip_index, p.strip_count = strip
         p.flags = flags
+        p.bounces = bounces
         return p
 
     def render(self, p: FrameParams):

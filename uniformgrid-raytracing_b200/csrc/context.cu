@@ -73,8 +73,8 @@ extern "C" int ug_create(ug_context **out, int device)
 	for (auto &ev : ctx->ev_stage) UG_CUDA(ctx, cudaEventCreate(&ev));
 	UG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_fc, sizeof(FrameConst)));
 	memset(ctx->h_fc, 0, sizeof(FrameConst));
-	UG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_counters, sizeof(u32) * 4 * (1 + UG_MAX_LIGHTS)));
-	memset(ctx->h_counters, 0, sizeof(u32) * 4 * (1 + UG_MAX_LIGHTS));
+	UG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_counters, sizeof(u32) * 4 * (2 + UG_MAX_LIGHTS)));
+	memset(ctx->h_counters, 0, sizeof(u32) * 4 * (2 + UG_MAX_LIGHTS));
 	UG_CUDA(ctx, cudaMalloc((void **)&ctx->d_fc, sizeof(FrameConst)));
 	*out = ctx;
 	return UG_OK;
@@ -96,12 +96,24 @@ static void free_rays(LightRays &r)
 	r = LightRays();
 }
 
+static void free_reflect(ReflectState &r)
+{
+	free_grid(r.grid);
+	dfree(r.box); dfree(r.geo); dfree(r.rect); dfree(r.O); dfree(r.r); dfree(r.acc); dfree(r.w); dfree(r.live); dfree(r.live_scan); dfree(r.list);
+	dfree(r.scan_state);
+	if (r.uc) cudaFree(r.uc);
+	r.uc = nullptr;
+	r.N = 0;
+}
+
 extern "C" void ug_destroy(ug_context *ctx)
 {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
 	if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+	free_reflect(ctx->refl);
+	dfree(ctx->d_reflect);
 	free_grid(ctx->cam_grid);
 	for (int i = 0; i < UG_MAX_LIGHTS; i++) { free_grid(ctx->light_grid[i]); free_rays(ctx->rays[i]); }
 	dfree(ctx->d_vertexlist); dfree(ctx->d_materiallist); dfree(ctx->d_vertex_orig_list); dfree(ctx->d_facelist); dfree(ctx->d_materiallist_index);
@@ -206,10 +218,39 @@ static int alloc_rays(ug_context *ctx, LightRays &r, int N, int C)
 	return UG_OK;
 }
 
+static int alloc_reflect(ug_context *ctx, int T, int N)
+{
+	ReflectState &r = ctx->refl;
+	if (r.grid.T == T && r.N == N && r.geo) return UG_OK;
+	const size_t keep = r.grid.cap;
+	free_reflect(r);
+	long long cells = 4ll * T;
+	if (cells < 4096) cells = 4096;
+	if (cells > (1ll << 21)) cells = 1ll << 21;
+	const size_t cap = (size_t)24 * (size_t)T + (size_t)cells + (1u << 20);
+	int rc = alloc_grid(ctx, r.grid, T, (int)cells, keep > cap ? keep : cap);
+	if (rc) return rc;
+	UG_CUDA(ctx, dmalloc(&r.box, 8));
+	UG_CUDA(ctx, cudaMalloc((void **)&r.uc, ugk_ugrid_const_bytes()));
+	UG_CUDA(ctx, dmalloc(&r.geo, 3 * (size_t)T));
+	UG_CUDA(ctx, dmalloc(&r.rect, (size_t)T));
+	UG_CUDA(ctx, dmalloc(&r.O, 3 * (size_t)N));
+	UG_CUDA(ctx, dmalloc(&r.r, 3 * (size_t)N));
+	UG_CUDA(ctx, dmalloc(&r.acc, 3 * (size_t)N));
+	UG_CUDA(ctx, dmalloc(&r.w, (size_t)N));
+	UG_CUDA(ctx, dmalloc(&r.live, (size_t)N));
+	UG_CUDA(ctx, dmalloc(&r.live_scan, (size_t)N + 1));
+	UG_CUDA(ctx, dmalloc(&r.list, (size_t)N));
+	r.scan_tiles = ugk_scan_tiles((size_t)N + 2) + 1;
+	UG_CUDA(ctx, dmalloc(&r.scan_state, r.scan_tiles + 1));
+	r.N = N;
+	return UG_OK;
+}
+
 static size_t default_cap(int T, int C) { return (size_t)16 * (size_t)T + (size_t)C + (1u << 20); }
 
 /* make every buffer the current (model, screen, strip, lights, flags) needs exist */
-static int ensure_buffers(ug_context *ctx, int num_lights, bool full)
+static int ensure_buffers(ug_context *ctx, int num_lights, bool full, bool reflect = false)
 {
 	if (ctx->num_faces <= 0) return ug_fail(ctx, UG_ERR_ARG, "no model loaded");
 	if (ctx->W <= 0) return ug_fail(ctx, UG_ERR_ARG, "screen size not set");
@@ -259,6 +300,11 @@ static int ensure_buffers(ug_context *ctx, int num_lights, bool full)
 		if (ctx->d_rgb_ext && want != ctx->d_rgb_ext) return ug_fail(ctx, UG_ERR_ARG, "external RGB buffer holds %zu bytes, need %zu", ctx->rgb_ext_bytes, 3 * (size_t)ctx->N);
 		if (want != ctx->d_rgb) { ctx->d_rgb = want; changed = true; }
 	}
+	if (reflect && (ctx->refl.grid.T != T || ctx->refl.N != ctx->N || !ctx->refl.geo)) {
+		int rc = alloc_reflect(ctx, T, ctx->N);
+		if (rc) return rc;
+		changed = true;
+	}
 	if (full && !ctx->full_alloc) {
 		UG_CUDA(ctx, dmalloc(&ctx->d_normal, 3 * (size_t)ctx->N));
 		ctx->full_alloc = true;
@@ -294,6 +340,8 @@ extern "C" int ug_model_set(ug_context *ctx, const float *vertexlist, int num_ve
 	if (num_materials)
 		UG_CUDA(ctx, cudaMemcpy(ctx->d_materiallist, ctx->h_materiallist.data(), sizeof(float) * UG_MATERIAL_SIZE * (size_t)num_materials, cudaMemcpyHostToDevice));
 	dfree(ctx->d_vertex_orig_list);
+	dfree(ctx->d_reflect);
+	ctx->h_reflect.clear();
 	ctx->size_orig_list = ctx->offset_orig_list = 0;
 	if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
 	ctx->frame_valid = false;
@@ -317,6 +365,18 @@ extern "C" int ug_model_load(ug_context *ctx, const char *obj_path, const char *
 	std::vector<int> F(3 * (size_t)nf), M(nf);
 	ug_obj_parse(obj_path, &nv, &nf, V.data(), F.data(), M.data());
 	return ug_model_set(ctx, V.data(), nv, F.data(), nf, M.data(), nm ? mats.data() : nullptr, nm);
+}
+
+extern "C" int ug_model_set_reflect(ug_context *ctx, const float *reflect, int num_materials)
+{
+	if (!ctx || !reflect || num_materials != ctx->num_materials || num_materials <= 0) return ug_fail(ctx, UG_ERR_ARG, "ug_model_set_reflect: need %d values", ctx ? ctx->num_materials : 0);
+	UG_CUDA(ctx, cudaSetDevice(ctx->device));
+	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ctx->h_reflect.assign(reflect, reflect + num_materials);
+	UG_CUDA(ctx, dmalloc(&ctx->d_reflect, (size_t)num_materials));
+	UG_CUDA(ctx, cudaMemcpy(ctx->d_reflect, reflect, sizeof(float) * (size_t)num_materials, cudaMemcpyHostToDevice));
+	if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+	return UG_OK;
 }
 
 extern "C" int ug_model_init_orig_list(ug_context *ctx, int vertices_size, int vertices_offset)
@@ -508,6 +568,11 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 	          ctx->d_rgb, ctx->d_matid, ctx->N, 1, sms);
 	L.n += 1;
 	stage_mark(ctx, k, stage_events); /* shade */
+	if (p->bounces > 0 && ctx->d_reflect) { /* row R: reflection bounces on top of the shaded frame */
+		ugk_reflect(s, ctx, p->bounces, &L.n);
+		stage_mark(ctx, k, stage_events);
+		UG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 4 * (1 + UG_MAX_LIGHTS), ctx->refl.grid.counters, 4 * sizeof(u32), cudaMemcpyDeviceToHost, s));
+	}
 	/* pair counts + overflow flags of every grid ride back with the frame (no extra synchronisation later) */
 	UG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->cam_grid.counters, 4 * sizeof(u32), cudaMemcpyDeviceToHost, s));
 	for (int l = 0; l < nl; l++)
@@ -526,7 +591,7 @@ static int prepare_frame(ug_context *ctx, const ug_frame_params *p)
 	if (rc) return rc;
 	rc = ug_set_strip(ctx, p->strip_count > 0 ? p->strip_index : 0, p->strip_count > 0 ? p->strip_count : 1);
 	if (rc) return rc;
-	rc = ensure_buffers(ctx, p->num_lights, (p->flags & UG_FLAG_FULL_BUFFERS) != 0);
+	rc = ensure_buffers(ctx, p->num_lights, (p->flags & UG_FLAG_FULL_BUFFERS) != 0, p->bounces > 0 && ctx->d_reflect);
 	if (rc) return rc;
 	/* the previous frame may still be reading the pinned block through its H2D copy */
 	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -573,6 +638,7 @@ static unsigned long long frame_key(const ug_context *ctx, const ug_frame_params
 	mix((unsigned long long)ctx->num_faces); mix((unsigned long long)p->num_lights); mix((unsigned long long)(p->flags & UG_FLAG_FULL_BUFFERS));
 	mix((unsigned long long)(p->transform && ctx->d_vertex_orig_list ? 1 : 0)); mix((unsigned long long)ctx->cam_grid.cap);
 	for (int l = 0; l < p->num_lights; l++) mix((unsigned long long)ctx->light_grid[l].cap);
+	mix((unsigned long long)(p->bounces > 0 && ctx->d_reflect ? p->bounces : 0)); mix((unsigned long long)ctx->refl.grid.cap);
 	mix((unsigned long long)(uintptr_t)ctx->stream); mix((unsigned long long)(uintptr_t)ctx->d_rgb);
 	return k;
 }
@@ -615,15 +681,16 @@ static int run_frame_once(ug_context *ctx, const ug_frame_params *p)
 }
 
 /* after a synchronise: did any pair arena overflow?  If so grow it (the caller re-runs the frame). */
-static int check_overflow(ug_context *ctx, int num_lights, bool *grew)
+static int check_overflow(ug_context *ctx, int num_lights, bool *grew, bool reflect = false)
 {
 	*grew = false;
-	GridBuffers *gs[1 + UG_MAX_LIGHTS];
+	GridBuffers *gs[2 + UG_MAX_LIGHTS];
 	int n = 0;
 	gs[n++] = &ctx->cam_grid;
 	for (int l = 0; l < num_lights; l++) gs[n++] = &ctx->light_grid[l];
+	if (reflect) gs[n++] = &ctx->refl.grid;
 	for (int i = 0; i < n; i++) {
-		const u32 *c = ctx->h_counters + 4 * i; /* copied by the frame itself; the caller has synchronised */
+		const u32 *c = ctx->h_counters + 4 * ((reflect && i == n - 1) ? 1 + UG_MAX_LIGHTS : i); /* copied by the frame itself; the caller has synchronised */
 		if (c[1]) {
 			const size_t want = (size_t)c[2] + (size_t)c[2] / 4 + 1024;
 			int rc = alloc_grid(ctx, *gs[i], gs[i]->T, gs[i]->C, want);
@@ -662,7 +729,7 @@ extern "C" int ug_render_frame_host(ug_context *ctx, const ug_frame_params *p, u
 		UG_CUDA(ctx, cudaMemcpyAsync(dst, ctx->d_rgb, 3 * (size_t)ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
 		UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 		bool grew = false;
-		rc = check_overflow(ctx, p->num_lights, &grew);
+		rc = check_overflow(ctx, p->num_lights, &grew, p->bounces > 0 && ctx->d_reflect);
 		if (rc) return rc;
 		if (!grew) {
 			if (!direct) memcpy(host_rgb, ctx->h_rgb_pinned, 3 * (size_t)ctx->N);

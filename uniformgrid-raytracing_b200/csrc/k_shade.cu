@@ -8,7 +8,7 @@
  *                 written once.  The normal is recomputed from the triangle id with the reference's
  *                 arithmetic instead of being stored per pixel; the direction comes from d_primary_ray_direction.
  */
-#include "k_common.cuh"
+#include "k_shade_dev.cuh"
 
 /* one vertex, transformation_kernel.cu:10-16; cos/sin come from the host (same glibc values the
  * host-compiled reference gets; CUDA's cosf/sinf differ in the last ulp) */
@@ -51,42 +51,6 @@ void ugk_transform(cudaStream_t s, float *vertexlist, const float *orig, int siz
 	if (groups) k_transform_vec4<<<min((groups + 255) / 256, sms * 8), 256, 0, s>>>((float4 *)dst, (const float4 *)orig, groups, fc);
 	const int rest = size - 4 * groups;
 	if (rest) k_transform_scalar<<<min((rest + 255) / 256, sms * 8), 256, 0, s>>>(dst, orig, 4 * groups, rest, fc);
-}
-
-/* one pixel: shader_kernel.cu:165-221 + :46-86 (+ :347-359 when apply_shadow) */
-static __device__ __forceinline__ u32 shade_pixel(const float *R, float ex, float ey, float ez, float Lvx, float Lvy, float Lvz, float tv, float dx, float dy,
-                                                  float dz, int tri, int is_shadowed, const float4 *__restrict__ rec, const int *__restrict__ mat_idx,
-                                                  const float *__restrict__ mat_list, int mat_count, int apply_shadow, int &idx_out)
-{
-	float cr = 0.0f, cg = 0.0f, cb = 0.0f;
-	const int idx = (tri >= 0) ? mat_idx[tri] : -1; /* the reference reads mat_idx[-2] on a miss; ours: black */
-	idx_out = idx;
-	if (idx >= 0 && idx < mat_count && tv > 0.0f) {
-		const float Px = ex + tv * dx, Py = ey + tv * dy, Pz = ez + tv * dz;
-		/* normal as rckernel_alpha left it: abs(normalize(cross(normalize(e1), normalize(e2)))), trace_kernel.cu:234-243 */
-		const float4 r1 = rec[4 * (size_t)tri + 1], r2 = rec[4 * (size_t)tri + 2];
-		float ax = r1.x, ay = r1.y, az = r1.z, bx = r2.x, by = r2.y, bz = r2.z, nx, ny, nz;
-		ug_normalize(ax, ay, az);
-		ug_normalize(bx, by, bz);
-		ug_cross(nx, ny, nz, ax, ay, az, bx, by, bz);
-		ug_normalize(nx, ny, nz);
-		nx = (nx < 0) ? nx * -1.0f : nx; ny = (ny < 0) ? ny * -1.0f : ny; nz = (nz < 0) ? nz * -1.0f : nz;
-		/* lambert_color_pixel */
-		const float Pvx = R[0] * Px + R[4] * Py + R[8] * Pz, Pvy = R[1] * Px + R[5] * Py + R[9] * Pz, Pvz = R[2] * Px + R[6] * Py + R[10] * Pz;
-		float Nvx = R[0] * nx + R[4] * ny + R[8] * nz, Nvy = R[1] * nx + R[5] * ny + R[9] * nz, Nvz = R[2] * nx + R[6] * ny + R[10] * nz;
-		ug_normalize(Nvx, Nvy, Nvz);
-		float ldx = Pvx - Lvx, ldy = Pvy - Lvy, ldz = Pvz - Lvz;
-		ug_normalize(ldx, ldy, ldz);
-		const float kr = mat_list[idx * UG_MATERIAL_SIZE + 3], kg = mat_list[idx * UG_MATERIAL_SIZE + 4], kb = mat_list[idx * UG_MATERIAL_SIZE + 5];
-		cr += kr * 0.5f; cg += kg * 0.5f; cb += kb * 0.5f;  /* ambient term uses the DIFFUSE colour, :180-186 */
-		float dd = ug_dot(ldx, ldy, ldz, Nvx, Nvy, Nvz);
-		if (!(dd > 0)) dd *= -1.0f;
-		if (dd > 0) { cr += kr * 1.0f * dd; cg += kg * 1.0f * dd; cb += kb * 1.0f * dd; }
-		cr = cr > 1.0f ? 1.0f : cr; cg = cg > 1.0f ? 1.0f : cg; cb = cb > 1.0f ? 1.0f : cb;
-	}
-	unsigned char r8 = (unsigned char)(cr * 255.0f), g8 = (unsigned char)(cg * 255.0f), b8 = (unsigned char)(cb * 255.0f);
-	if (apply_shadow && is_shadowed == 1) { r8 /= 3; g8 /= 3; b8 /= 3; } /* shader_kernel.cu:351-356 */
-	return (u32)r8 | ((u32)g8 << 8) | ((u32)b8 << 16);
 }
 
 /* 4 consecutive pixels per thread: 16-byte loads of t/id/shadowed, 3 x 16-byte loads of dir, the 12 RGB bytes leave

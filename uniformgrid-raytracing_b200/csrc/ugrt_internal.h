@@ -76,6 +76,20 @@ struct LightRays {         /* DecisionData's regroup state (decision_data.h:72-8
 	size_t item_cap = 0;
 };
 
+struct UGridConst;
+struct ReflectState {      /* row R: world-space uniform grid + per-pixel reflection ray state (k_reflect.cu) */
+	GridBuffers grid;      /* count/scan/keys/vals/span/offset of the uniform grid; grid.C = cell arena */
+	u32 *box = nullptr;    /* [6] scene bounding box (order-preserving uint encoding) */
+	UGridConst *uc = nullptr;
+	float4 *geo = nullptr; /* [3T] v0, e1, e2 */
+	uint4 *rect = nullptr; /* [T] cell box of every triangle + pair count */
+	float *O = nullptr, *r = nullptr, *acc = nullptr, *w = nullptr;
+	u32 *live = nullptr, *live_scan = nullptr, *list = nullptr;
+	u64 *scan_state = nullptr;
+	size_t scan_tiles = 0;
+	int N = 0;
+};
+
 struct ug_context {
 	int device = 0;
 	cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -94,6 +108,8 @@ struct ug_context {
 	std::vector<float> h_vertexlist, h_materiallist;
 	std::vector<int> h_facelist, h_materiallist_index;
 	float *d_vertexlist = nullptr, *d_materiallist = nullptr, *d_vertex_orig_list = nullptr;
+	float *d_reflect = nullptr;  /* [M] reflectivity per material (MTL `r`), row R */
+	std::vector<float> h_reflect;
 	int *d_facelist = nullptr, *d_materiallist_index = nullptr;
 	int num_faces = 0, num_vertices = 0, num_materials = 0;
 	int size_orig_list = 0, offset_orig_list = 0;
@@ -114,6 +130,7 @@ struct ug_context {
 	GridBuffers cam_grid;
 	GridBuffers light_grid[UG_MAX_LIGHTS];
 	LightRays rays[UG_MAX_LIGHTS];
+	ReflectState refl;
 	int lights_allocated = 0;
 
 	/* DecisionData (decision_data.h:66-82) */
@@ -185,6 +202,9 @@ void ugk_shade(cudaStream_t s, const FrameConst *fc, const float *t, const float
                const float *mat_list, int mat_count, unsigned char *rgb, int *mat_out, int N, int apply_shadow, int sms);
 void ugk_add_shadows(cudaStream_t s, const int *shadowed, unsigned char *rgb, int N, int sms);
 void ugk_fill_u32(cudaStream_t s, u32 *p, u32 v, size_t n, int sms);
+/* row R (k_reflect.cu) */
+size_t ugk_ugrid_const_bytes(void);
+void ugk_reflect(cudaStream_t s, ug_context *ctx, int bounces, int *launches);
 
 /* host helpers (camera_host.cpp, obj_loader.cpp) */
 void ugh_view_const(ViewConst *vc, const ug_camera *cam, int W, int H, int nbx, int nby, int gy_lo, int gy_cnt);
