@@ -99,8 +99,9 @@ def make_scene(name: str):
     return s
 
 
-def workload_name(scene, world):
-    return (f"config {scene.name}: {scene.num_tris} triangles, {scene.width}x{scene.height}, primary + shadow rays, "
+def workload_name(scene, world, bounces=0):
+    return (f"config {scene.name}: {scene.num_tris} triangles, {scene.width}x{scene.height}, primary + shadow"
+            + (f" + {bounces} reflection bounce(s)" if bounces else "") + " rays, "
             f"{len(scene.lights)} light(s), full grid rebuild every frame"
             + (", per-frame vertex transform" if scene.dyn_size else "") + (f", {world} image strips" if world > 1 else ""))
 
@@ -178,8 +179,12 @@ def run_ours(args):
     host_img = torch.empty(3 * scene.num_pixels, dtype=torch.uint8).pin_memory()
     rays_frame = scene.rays_per_frame()
 
+    bounces = scene.bounces if args.bounces < 0 else args.bounces
+    if not any(m.reflect > 0 for m in scene.materials):
+        bounces = 0
+
     def step(i, flags=0):
-        r.render(r.params(scene, frame=i, flags=flags, strip=(rank, world)))
+        r.render(r.params(scene, frame=i, flags=flags, strip=(rank, world), bounces=bounces))
         if world > 1:
             dist.gather(strip, gathered, dst=0)
 
@@ -189,7 +194,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- warm-up (also captures the CUDA graph and grows the pair arena if the scene needs it)
-    r.render_host(r.params(scene, frame=0, strip=(rank, world)), np.zeros(3 * n_local, np.uint8))
+    r.render_host(r.params(scene, frame=0, strip=(rank, world), bounces=bounces), np.zeros(3 * n_local, np.uint8))
     for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
@@ -216,7 +221,11 @@ def run_ours(args):
     per = per.cpu().numpy()
     total_ms = float(per.sum())
     st = r.stats()
-    launches_per_frame = st.kernel_launches + (0 if args.no_flush else 0)
+    launches_per_frame = st.kernel_launches
+    refl = torch.tensor([float(st.reflect_rays)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(refl)                        # every rank traces the reflection rays of its own strip
+    rays_frame = scene.rays_per_frame() + int(refl.item())
 
     # ---- e2e: host buffers in, host image out, wall clock
     e2e_steps = max(3, min(args.steps, 50))
@@ -225,7 +234,7 @@ def run_ours(args):
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         if world == 1:
-            r.render_host(r.params(scene, frame=i), out_np)          # H2D consts + kernels + D2H image + sync
+            r.render_host(r.params(scene, frame=i, bounces=bounces), out_np)   # H2D consts + kernels + D2H image + sync
         else:
             step(i)
             if rank == 0:
@@ -246,7 +255,7 @@ def run_ours(args):
     stage = {}
     reps = 5
     for i in range(reps):
-        r.render(r.params(scene, frame=i, flags=ug.FLAG_STAGE_EVENTS, strip=(rank, world)))
+        r.render(r.params(scene, frame=i, flags=ug.FLAG_STAGE_EVENTS, strip=(rank, world), bounces=bounces))
         for k, v in r.stage_times().items():
             stage[k] = stage.get(k, 0.0) + v / reps
     st2 = r.stats()
@@ -294,7 +303,8 @@ def run_ours(args):
             "metric": METRIC, "value": rays_frame * args.steps / (total_ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(scene, world), "rays_per_frame": rays_frame,
+            "config": {"workload": workload_name(scene, world, bounces), "rays_per_frame": rays_frame,
+                       "rays": {"primary": scene.num_pixels, "shadow": scene.num_pixels * len(scene.lights), "reflection": int(refl.item())},
                        "l2": "flushed between timed frames (256 MiB write)" if not args.no_flush else "not flushed",
                        "timing": "CUDA events per frame on the launching stream, max over ranks, summed over the K frames",
                        "pairs_camera_grid": int(P), "pairs_light_grids": [int(st2.light_pairs[l]) for l in range(len(scene.lights))]},
@@ -324,6 +334,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="B", choices=["A", "B", "C", "D", "E"])
+    ap.add_argument("--bounces", type=int, default=-1, help="reflection bounces (-1: what the config names)")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

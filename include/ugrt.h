@@ -123,6 +123,8 @@ typedef struct ug_stats {
 	int kernel_launches;                  /* kernels launched by the last frame (graph nodes count) */
 	float ms_frame;                       /* CUDA-event time of the last frame (first kernel -> RGB8 done) */
 	float ms_transform, ms_cam_grid, ms_trace, ms_light_grid, ms_regroup, ms_shadow, ms_shade; /* STAGE_EVENTS only */
+	unsigned reflect_rays;                /* row R: live reflection rays of the last frame, summed over bounces */
+	unsigned reflect_pairs;               /* row R: (cell,triangle) pairs of the uniform grid */
 } ug_stats;
 
 /* ---- lifetime */

@@ -57,7 +57,7 @@ class Stats(C.Structure):
                 ("light_pairs", C.c_uint * UG_MAX_LIGHTS), ("pair_capacity", C.c_uint), ("overflowed", C.c_int),
                 ("kernel_launches", C.c_int), ("ms_frame", C.c_float), ("ms_transform", C.c_float), ("ms_cam_grid", C.c_float),
                 ("ms_trace", C.c_float), ("ms_light_grid", C.c_float), ("ms_regroup", C.c_float), ("ms_shadow", C.c_float),
-                ("ms_shade", C.c_float)]
+                ("ms_shade", C.c_float), ("reflect_rays", C.c_uint), ("reflect_pairs", C.c_uint)]
 
 
 def build(verbose: bool = False) -> str:
@@ -253,9 +253,10 @@ class Renderer:
         buf = (C.c_float * 40)()
         n = self.L.ug_stage_times(self.ctx, buf, 40)
         names = ["transform", "cam_grid", "trace"]
-        for l in range((max(n, 0) - 4) // 3):
+        for l in range((max(n, 0) - 4 - (1 if (max(n, 0) - 4) % 3 else 0)) // 3):
             names += [f"light{l}_grid", f"light{l}_regroup", f"light{l}_shadow"]
         names.append("shade")
+        names.append("reflect")
         return {names[k]: buf[k] for k in range(min(max(n, 0), len(names)))}
 
     def read(self, buffer: int, index: int = 0) -> np.ndarray:

@@ -67,14 +67,16 @@ extern "C" int ug_create(ug_context **out, int device)
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_init, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_init, cudaStreamNonBlocking));
+	UG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_refl, cudaStreamNonBlocking));
+	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_refl, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_trace, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaEventCreate(&ctx->ev_t0));
 	UG_CUDA(ctx, cudaEventCreate(&ctx->ev_t1));
 	for (auto &ev : ctx->ev_stage) UG_CUDA(ctx, cudaEventCreate(&ev));
 	UG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_fc, sizeof(FrameConst)));
 	memset(ctx->h_fc, 0, sizeof(FrameConst));
-	UG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_counters, sizeof(u32) * 4 * (2 + UG_MAX_LIGHTS)));
-	memset(ctx->h_counters, 0, sizeof(u32) * 4 * (2 + UG_MAX_LIGHTS));
+	UG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_counters, sizeof(u32) * (4 * (2 + UG_MAX_LIGHTS) + 8)));
+	memset(ctx->h_counters, 0, sizeof(u32) * (4 * (2 + UG_MAX_LIGHTS) + 8));
 	UG_CUDA(ctx, cudaMalloc((void **)&ctx->d_fc, sizeof(FrameConst)));
 	*out = ctx;
 	return UG_OK;
@@ -99,7 +101,7 @@ static void free_rays(LightRays &r)
 static void free_reflect(ReflectState &r)
 {
 	free_grid(r.grid);
-	dfree(r.box); dfree(r.geo); dfree(r.rect); dfree(r.O); dfree(r.r); dfree(r.acc); dfree(r.w); dfree(r.live); dfree(r.live_scan); dfree(r.list);
+	dfree(r.box); dfree(r.geo); dfree(r.rect); dfree(r.O); dfree(r.r); dfree(r.acc); dfree(r.w); dfree(r.live); dfree(r.live_scan); dfree(r.list); dfree(r.ray_counts);
 	dfree(r.scan_state);
 	if (r.uc) cudaFree(r.uc);
 	r.uc = nullptr;
@@ -123,7 +125,7 @@ extern "C" void ug_destroy(ug_context *ctx)
 	if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
 	dfree(ctx->d_fc);
 	for (int i = 0; i < UG_MAX_LIGHTS; i++) { cudaStreamDestroy(ctx->side[i]); cudaEventDestroy(ctx->ev_join[i]); }
-	cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_fork2); cudaEventDestroy(ctx->ev_init); cudaStreamDestroy(ctx->side_init); cudaEventDestroy(ctx->ev_trace); cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
+	cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_fork2); cudaEventDestroy(ctx->ev_init); cudaStreamDestroy(ctx->side_init); cudaStreamDestroy(ctx->side_refl); cudaEventDestroy(ctx->ev_refl); cudaEventDestroy(ctx->ev_trace); cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
 	for (auto &ev : ctx->ev_stage) cudaEventDestroy(ev);
 	cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
@@ -241,6 +243,8 @@ static int alloc_reflect(ug_context *ctx, int T, int N)
 	UG_CUDA(ctx, dmalloc(&r.live, (size_t)N));
 	UG_CUDA(ctx, dmalloc(&r.live_scan, (size_t)N + 1));
 	UG_CUDA(ctx, dmalloc(&r.list, (size_t)N));
+	UG_CUDA(ctx, dmalloc(&r.ray_counts, 8));
+	UG_CUDA(ctx, cudaMemset(r.ray_counts, 0, 8 * sizeof(u32)));
 	r.scan_tiles = ugk_scan_tiles((size_t)N + 2) + 1;
 	UG_CUDA(ctx, dmalloc(&r.scan_state, r.scan_tiles + 1));
 	r.N = N;
@@ -530,8 +534,14 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 			enqueue_light_grid(ctx, ctx->side[l], l, L);
 		}
 	}
+	const bool reflect = p->bounces > 0 && ctx->d_reflect;
 	if (parallel) { /* the per-pixel reset + ray directions do not depend on the grid: their own branch of the graph */
 		UG_CUDA(ctx, cudaEventRecord(ctx->ev_fork2, s));
+		if (reflect) { /* so does the world-space uniform grid of row R */
+			UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_refl, ctx->ev_fork2, 0));
+			ugk_reflect_grid(ctx->side_refl, ctx, &L.n);
+			UG_CUDA(ctx, cudaEventRecord(ctx->ev_refl, ctx->side_refl));
+		}
 		UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_init, ctx->ev_fork2, 0));
 		ugk_init_pixels(ctx->side_init, ctx->d_fc, ctx->d_t, ctx->d_id, ctx->d_shadowed, ctx->d_best, full ? ctx->d_normal : nullptr, ctx->d_dir, ctx->N, sms);
 		UG_CUDA(ctx, cudaEventRecord(ctx->ev_init, ctx->side_init));
@@ -568,10 +578,16 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 	          ctx->d_rgb, ctx->d_matid, ctx->N, 1, sms);
 	L.n += 1;
 	stage_mark(ctx, k, stage_events); /* shade */
-	if (p->bounces > 0 && ctx->d_reflect) { /* row R: reflection bounces on top of the shaded frame */
-		ugk_reflect(s, ctx, p->bounces, &L.n);
+	if (reflect) { /* row R: reflection bounces on top of the shaded frame */
+		if (parallel) UG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_refl, 0));
+		else ugk_reflect_grid(s, ctx, &L.n);
+		ugk_reflect_rays(s, ctx, p->bounces, &L.n);
 		stage_mark(ctx, k, stage_events);
 		UG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 4 * (1 + UG_MAX_LIGHTS), ctx->refl.grid.counters, 4 * sizeof(u32), cudaMemcpyDeviceToHost, s));
+		UG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 4 * (2 + UG_MAX_LIGHTS), ctx->refl.ray_counts, 8 * sizeof(u32), cudaMemcpyDeviceToHost, s));
+		ctx->last_bounces = p->bounces;
+	} else {
+		ctx->last_bounces = 0;
 	}
 	/* pair counts + overflow flags of every grid ride back with the frame (no extra synchronisation later) */
 	UG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->cam_grid.counters, 4 * sizeof(u32), cudaMemcpyDeviceToHost, s));
@@ -930,6 +946,10 @@ extern "C" int ug_get_stats(ug_context *ctx, ug_stats *out)
 			if (c[1]) s.overflowed = 1;
 		}
 	}
+	s.reflect_rays = 0;
+	s.reflect_pairs = 0;
+	for (int b = 0; b < ctx->last_bounces && b < 8; b++) s.reflect_rays += ctx->h_counters[4 * (2 + UG_MAX_LIGHTS) + b];
+	if (ctx->last_bounces) s.reflect_pairs = ctx->h_counters[4 * (1 + UG_MAX_LIGHTS)];
 	if (ctx->frame_valid) {
 		float ms = 0;
 		if (cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1) == cudaSuccess) s.ms_frame = ms;

@@ -16,6 +16,13 @@
 #include "k_shade_dev.cuh"
 #include "k_grid_dev.cuh"
 
+#ifndef UG_REFL_LOOK
+#define UG_REFL_LOOK 2            /* DDA look-ahead (cells whose spans are fetched together) */
+#endif
+#ifndef UG_REFL_CELLS_PER_TRI
+#define UG_REFL_CELLS_PER_TRI 4.0f /* uniform-grid resolution: cells per triangle */
+#endif
+
 struct UGridConst {
 	float lo[3], h[3], inv_h[3];
 	int n[3];
@@ -53,8 +60,8 @@ __global__ void k_ugrid_setup(const u32 *box, int T, int max_cells, UGridConst *
 		lo[k] -= pad;
 		ext[k] = (hi + pad) - lo[k];
 	}
-	/* roughly cubic cells, about 4 triangles' worth of cells, capped by the arena */
-	float target = fminf(4.0f * (float)T, (float)max_cells);
+	/* roughly cubic cells, about one cell per triangle (coarser cells = fewer empty DDA steps), capped by the arena */
+	float target = fminf(UG_REFL_CELLS_PER_TRI * (float)T, (float)max_cells);
 	target = fmaxf(target, 8.0f);
 	float hcell = cbrtf(ext[0] * ext[1] * ext[2] / target);
 	int n[3];
@@ -251,21 +258,46 @@ __global__ void __launch_bounds__(128) k_refl_trace(const ReflectArgs a, int bou
 				} else { tmax[k] = 3.0e38f; tdelta[k] = 3.0e38f; }
 			}
 			const float hmin = fminf(u.h[0], fminf(u.h[1], u.h[2]));
-			for (int guard = 0; guard < 4096; guard++) {
-				const u32 cell = ((u32)ci[0] * (u32)u.n[1] + (u32)ci[1]) * (u32)u.n[2] + (u32)ci[2];
-				const u32 n = a.span[cell], off = a.offset[cell];
-				for (u32 q = 0; q < n; q++) {
-					const int tri = (int)a.vals[off + q];
-					float tt;
-					if (!intersect_full(a.geo[3 * (size_t)tri], a.geo[3 * (size_t)tri + 1], a.geo[3 * (size_t)tri + 2], O[0], O[1], O[2], r[0], r[1], r[2], tt)) continue;
-					if (tt > 0.0f && (tt < best || (tt == best && tri < hit))) { best = tt; hit = tri; }
+			/* Most cells on a ray's way are empty, so a step would be one dependent load of span[cell] after another:
+			 * walk LOOK cells ahead with the (cheap) DDA arithmetic, fetch their spans together, then visit them in order. */
+			constexpr int LOOK = UG_REFL_LOOK;
+			bool finished = false;
+			for (int guard = 0; guard < 1100 && !finished; guard++) {
+				u32 cells[LOOK], sp[LOOK];
+				float texit[LOOK];
+				int nstep = 0;
+				bool left = false;
+#pragma unroll
+				for (int j = 0; j < LOOK; j++) {
+					cells[j] = 0; texit[j] = 0.0f;
+					if (!left) {
+						cells[j] = ((u32)ci[0] * (u32)u.n[1] + (u32)ci[1]) * (u32)u.n[2] + (u32)ci[2];
+						const int ax = (tmax[0] <= tmax[1]) ? ((tmax[0] <= tmax[2]) ? 0 : 2) : ((tmax[1] <= tmax[2]) ? 1 : 2);
+						texit[j] = tmax[ax];
+						nstep = j + 1;
+						ci[ax] += step[ax];
+						if (step[ax] == 0 || ci[ax] < 0 || ci[ax] >= u.n[ax]) left = true;
+						tmax[ax] += tdelta[ax];
+					}
 				}
-				const int ax = (tmax[0] <= tmax[1]) ? ((tmax[0] <= tmax[2]) ? 0 : 2) : ((tmax[1] <= tmax[2]) ? 1 : 2);
-				const float t_exit = tmax[ax];
-				if (hit >= 0 && best < t_exit * 0.999f - 1e-4f * hmin) break; /* clearly before the cell's exit: nothing later can win */
-				ci[ax] += step[ax];
-				if (step[ax] == 0 || ci[ax] < 0 || ci[ax] >= u.n[ax]) break;
-				tmax[ax] += tdelta[ax];
+#pragma unroll
+				for (int j = 0; j < LOOK; j++) sp[j] = (j < nstep) ? a.span[cells[j]] : 0u;
+#pragma unroll
+				for (int j = 0; j < LOOK; j++) {
+					if (j >= nstep || finished) continue;
+					if (sp[j]) {
+						const u32 off = a.offset[cells[j]];
+						for (u32 q = 0; q < sp[j]; q++) {
+							const int tri = (int)a.vals[off + q];
+							float tt;
+							if (!intersect_full(a.geo[3 * (size_t)tri], a.geo[3 * (size_t)tri + 1], a.geo[3 * (size_t)tri + 2], O[0], O[1], O[2], r[0], r[1], r[2], tt)) continue;
+							if (tt > 0.0f && (tt < best || (tt == best && tri < hit))) { best = tt; hit = tri; }
+						}
+					}
+					/* clearly before this cell's exit: nothing in a later cell can win */
+					if (hit >= 0 && best < texit[j] * 0.999f - 1e-4f * hmin) finished = true;
+				}
+				if (left) finished = true;
 			}
 		}
 		/* spec: accumulate, then finish the pixel or spawn the next ray */
@@ -303,12 +335,13 @@ __global__ void __launch_bounds__(128) k_refl_trace(const ReflectArgs a, int bou
 /* host side ------------------------------------------------------------------------------------------ */
 size_t ugk_ugrid_const_bytes(void) { return sizeof(UGridConst); }
 
-void ugk_reflect(cudaStream_t s, ug_context *ctx, int bounces, int *launches)
+/* the world-space uniform grid of the current vertices: independent of camera and lights, so the frame builds it on
+ * its own branch of the graph */
+void ugk_reflect_grid(cudaStream_t s, ug_context *ctx, int *launches)
 {
 	ReflectState &rf = ctx->refl;
-	const int sms = ctx->num_sms, T = ctx->num_faces, N = ctx->N, V = ctx->num_vertices;
+	const int sms = ctx->num_sms, T = ctx->num_faces, V = ctx->num_vertices;
 	GridBuffers &g = rf.grid;
-	/* uniform grid of the current vertices */
 	k_aabb_reset<<<1, 32, 0, s>>>(rf.box);
 	k_aabb<<<min((V + 255) / 256, sms * 4), 256, 0, s>>>(ctx->d_vertexlist, V, rf.box);
 	k_ugrid_setup<<<1, 32, 0, s>>>(rf.box, T, g.C, rf.uc);
@@ -324,7 +357,16 @@ void ugk_reflect(cudaStream_t s, ug_context *ctx, int bounces, int *launches)
 	g.final_buf = ugk_radix_sort_pairs(s, g.keys, g.vals, g.counters, g.cap, g.key_bits, g.sort, sms, &n);
 	ugk_exclusive_scan(s, g.span, g.offset, (size_t)g.C, g.sort.scan_state, g.sort.scan_tiles, sms);
 	n += 1;
-	/* rays */
+	if (launches) *launches += n;
+}
+
+/* the bounces themselves, on top of the shaded frame */
+void ugk_reflect_rays(cudaStream_t s, ug_context *ctx, int bounces, int *launches)
+{
+	ReflectState &rf = ctx->refl;
+	const int sms = ctx->num_sms, N = ctx->N;
+	const GridBuffers &g = rf.grid;
+	int n = 0;
 	ReflectArgs a;
 	a.fc = ctx->d_fc; a.uc = rf.uc; a.geo = rf.geo; a.span = g.span; a.offset = g.offset; a.vals = g.vals[g.final_buf];
 	a.mat_idx = ctx->d_materiallist_index; a.mat_list = ctx->d_materiallist; a.mat_reflect = ctx->d_reflect; a.mat_count = ctx->num_materials;
@@ -335,6 +377,7 @@ void ugk_reflect(cudaStream_t s, ug_context *ctx, int bounces, int *launches)
 	n += 1;
 	for (int b = 1; b <= bounces; b++) {
 		ugk_exclusive_scan(s, rf.live, rf.live_scan, (size_t)N, rf.scan_state, rf.scan_tiles, sms);  /* compaction by scan */
+		cudaMemcpyAsync(rf.ray_counts + (b - 1 < 7 ? b - 1 : 7), rf.live_scan + N, sizeof(u32), cudaMemcpyDeviceToDevice, s); /* live rays of bounce b */
 		k_refl_compact<<<pb, 256, 0, s>>>(rf.live, rf.live_scan, rf.list, N);
 		k_refl_trace<<<min((N + 127) / 128, sms * 16), 128, 0, s>>>(a, b);
 		n += 3;

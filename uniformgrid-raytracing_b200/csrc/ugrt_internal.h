@@ -85,6 +85,7 @@ struct ReflectState {      /* row R: world-space uniform grid + per-pixel reflec
 	uint4 *rect = nullptr; /* [T] cell box of every triangle + pair count */
 	float *O = nullptr, *r = nullptr, *acc = nullptr, *w = nullptr;
 	u32 *live = nullptr, *live_scan = nullptr, *list = nullptr;
+	u32 *ray_counts = nullptr; /* [8] live reflection rays per bounce */
 	u64 *scan_state = nullptr;
 	size_t scan_tiles = 0;
 	int N = 0;
@@ -94,8 +95,8 @@ struct ug_context {
 	int device = 0;
 	cudaStream_t own_stream = nullptr, stream = nullptr;
 	cudaStream_t side[UG_MAX_LIGHTS] = {};
-	cudaStream_t side_init = nullptr;
-	cudaEvent_t ev_fork2 = nullptr, ev_init = nullptr;
+	cudaStream_t side_init = nullptr, side_refl = nullptr;
+	cudaEvent_t ev_fork2 = nullptr, ev_init = nullptr, ev_refl = nullptr;
 	cudaEvent_t ev_fork = nullptr, ev_trace = nullptr, ev_join[UG_MAX_LIGHTS] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
 	cudaEvent_t ev_stage[40] = {};
 	int stage_marks = 0;
@@ -125,6 +126,7 @@ struct ug_context {
 	FrameConst *d_fc = nullptr;
 	u32 *h_counters = nullptr;  /* pinned [1+UG_MAX_LIGHTS][4]: counters of every grid, copied back by the frame */
 	int num_lights = 0;
+	int last_bounces = 0;
 
 	/* grids */
 	GridBuffers cam_grid;
@@ -204,7 +206,8 @@ void ugk_add_shadows(cudaStream_t s, const int *shadowed, unsigned char *rgb, in
 void ugk_fill_u32(cudaStream_t s, u32 *p, u32 v, size_t n, int sms);
 /* row R (k_reflect.cu) */
 size_t ugk_ugrid_const_bytes(void);
-void ugk_reflect(cudaStream_t s, ug_context *ctx, int bounces, int *launches);
+void ugk_reflect_grid(cudaStream_t s, ug_context *ctx, int *launches);
+void ugk_reflect_rays(cudaStream_t s, ug_context *ctx, int bounces, int *launches);
 
 /* host helpers (camera_host.cpp, obj_loader.cpp) */
 void ugh_view_const(ViewConst *vc, const ug_camera *cam, int W, int H, int nbx, int nby, int gy_lo, int gy_cnt);
