@@ -157,6 +157,10 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the product has no CPU path (use --impl reference for the CPU arm)")
+    # stdout carries exactly one JSON line: everything libraries print (NCCL banner ...) goes to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -171,10 +175,10 @@ def run_ours(args):
     lo, hi = nby * rank // world, nby * (rank + 1) // world
     rows = [(nby * (k + 1) // world - nby * k // world) * 8 for k in range(world)]
     n_local = scene.width * (hi - lo) * 8
-    strip_bytes_max = 3 * scene.width * max(rows)
-    strip = torch.zeros(strip_bytes_max, dtype=torch.uint8, device=dev)      # NCCL send buffer the shade kernel writes into
-    r.set_rgb_buffer(strip.data_ptr(), strip.numel())
-    gathered = [torch.zeros(strip_bytes_max, dtype=torch.uint8, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    if world > 1:   # the library gathers the strips itself (NCCL send/recv inside the frame's CUDA graph)
+        uid = [ug.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        r.comm_init(rank, world, uid[0])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)            # > 126 MB L2
     host_img = torch.empty(3 * scene.num_pixels, dtype=torch.uint8).pin_memory()
     rays_frame = scene.rays_per_frame()
@@ -185,8 +189,6 @@ def run_ours(args):
 
     def step(i, flags=0):
         r.render(r.params(scene, frame=i, flags=flags, strip=(rank, world), bounces=bounces))
-        if world > 1:
-            dist.gather(strip, gathered, dst=0)
 
     def barrier():
         if world > 1:
@@ -194,7 +196,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- warm-up (also captures the CUDA graph and grows the pair arena if the scene needs it)
-    r.render_host(r.params(scene, frame=0, strip=(rank, world), bounces=bounces), np.zeros(3 * n_local, np.uint8))
+    r.render_host(r.params(scene, frame=0, strip=(rank, world), bounces=bounces), host_img.numpy())
     for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
@@ -233,17 +235,8 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        if world == 1:
-            r.render_host(r.params(scene, frame=i, bounces=bounces), out_np)   # H2D consts + kernels + D2H image + sync
-        else:
-            step(i)
-            if rank == 0:
-                off = 0
-                for k in range(world):
-                    nb = 3 * scene.width * rows[k]
-                    host_img[off:off + nb].copy_(gathered[k][:nb], non_blocking=True)
-                    off += nb
-            torch.cuda.synchronize()
+        # H2D constants + kernels [+ NCCL strip gather] + D2H of the (full) image on rank 0 + sync
+        r.render_host(r.params(scene, frame=i, strip=(rank, world), bounces=bounces), out_np if world == 1 else host_img.numpy())
     barrier()
     e2e_dt = time.perf_counter() - t0
     e2e_t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
@@ -319,7 +312,8 @@ def run_ours(args):
             "frame_hbm_frac": frame_bytes / (total_ms / args.steps * 1e-3) / 1e9 / hbm_peak,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         }
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

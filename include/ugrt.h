@@ -109,6 +109,7 @@ enum ug_buffer {
 	UG_BUF_LIGHT_OFFSET,     /* u32[C] */
 	UG_BUF_LIGHT_CELL,       /* u32[N]   d_map[N..2N): light cell of every pixel's shadow ray, C = outside */
 	UG_BUF_SIZELIST,         /* u32[T]   frustum_grid.h:32 d_sizeList of the camera grid */
+	UG_BUF_RGB_FULL,         /* u8[3*W*H] rank 0 of a communicator: the gathered frame */
 	UG_BUF_CAM_COUNTERS,     /* u32[32]  debug: pair counters and phase time stamps of the camera-grid build */
 	UG_BUF_COUNT_
 };
@@ -185,6 +186,13 @@ int ug_write_ppm(ug_context *ctx, const char *filename);                        
  * then per light (light grid, ray->cell map + regroup, shadow rays), then shade; returns the number of intervals
  * written (these are the cutCreateTimer printf's of the reference) */
 int ug_stage_times(ug_context *ctx, float *out_ms, int max_entries);
+
+/* ---- multi-GPU: one context per GPU/process, image strips (ug_frame_params.strip_*), scene replicated.  With a communicator
+ * every ug_render_frame* ends with the gather of the RGB8 strips to rank 0 over NCCL (part of the frame's CUDA graph);
+ * ug_render_frame_host then delivers the FULL frame on rank 0 (other ranks get nothing).  The 128-byte id comes from
+ * ug_comm_unique_id on one rank and is handed to the others by the host program (MPI, torch.distributed, a file ...). */
+int ug_comm_unique_id(void *out128);
+int ug_comm_init(ug_context *ctx, int rank, int world, const void *unique_id128);
 
 /* ---- the reference's own entry points on a process-wide default context */
 void init_model(int argc, char **argv);                  /* per_app_funcs.h:8 */

@@ -1,0 +1,58 @@
+"""N > 1 on real GPUs (skipped on boxes with fewer than 2): one process per GPU, image strips, the library's own NCCL
+gather inside the frame; rank 0's gathered frame must equal the oracle's frame byte for byte."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import parity  # noqa: F401
+from oracle import harness
+from uniformgrid_raytracing_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_path):
+    import torch
+    import torch.distributed as dist
+    import ugrt  # noqa: F401
+    import uniformgrid_raytracing_b200 as ug
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)   # only carries the 128-byte NCCL id
+    scene = scenes.scene_a(256, 264)                                # 33 cell rows: uneven strips
+    r = ug.Renderer(rank)
+    r.set_scene(scene)
+    uid = [ug.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    r.comm_init(rank, world, uid[0])
+    host = torch.empty(3 * scene.num_pixels, dtype=torch.uint8).pin_memory()
+    for frame in range(3):                                          # graph capture, then replays
+        r.render_host(r.params(scene, frame=frame, strip=(rank, world)), host.numpy())
+    if rank == 0:
+        np.save(out_path, host.numpy().copy())
+    dist.barrier()
+    r.close()
+    dist.destroy_process_group()
+
+
+def test_strip_gather_over_nccl(oracle, tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    scene = scenes.scene_a(256, 264)
+    want = harness.run_frame(oracle, scene, threads=0)["rgb"]
+    out = str(tmp_path / "full.npy")
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert np.array_equal(np.load(out), want)

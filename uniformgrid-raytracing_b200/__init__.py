@@ -24,12 +24,12 @@ UG_TILE = 8
 FLAG_FULL_BUFFERS, FLAG_NO_GRAPH, FLAG_STAGE_EVENTS = 1, 2, 4
 
 (BUF_VERTEXLIST, BUF_CAM_VALUES, BUF_CAM_SPAN, BUF_CAM_OFFSET, BUF_T, BUF_ID, BUF_NORMAL, BUF_DIR, BUF_SHADOWED, BUF_RGB,
- BUF_LIGHT_VALUES, BUF_LIGHT_SPAN, BUF_LIGHT_OFFSET, BUF_LIGHT_CELL, BUF_SIZELIST, BUF_CAM_COUNTERS) = range(16)
+ BUF_LIGHT_VALUES, BUF_LIGHT_SPAN, BUF_LIGHT_OFFSET, BUF_LIGHT_CELL, BUF_SIZELIST, BUF_RGB_FULL, BUF_CAM_COUNTERS) = range(17)
 
 _BUF_DTYPE = {BUF_VERTEXLIST: np.float32, BUF_CAM_VALUES: np.uint32, BUF_CAM_SPAN: np.uint32, BUF_CAM_OFFSET: np.uint32,
               BUF_T: np.float32, BUF_ID: np.int32, BUF_NORMAL: np.float32, BUF_DIR: np.float32, BUF_SHADOWED: np.int32,
               BUF_RGB: np.uint8, BUF_LIGHT_VALUES: np.uint32, BUF_LIGHT_SPAN: np.uint32, BUF_LIGHT_OFFSET: np.uint32,
-              BUF_LIGHT_CELL: np.uint32, BUF_SIZELIST: np.uint32, BUF_CAM_COUNTERS: np.uint32}
+              BUF_LIGHT_CELL: np.uint32, BUF_SIZELIST: np.uint32, BUF_RGB_FULL: np.uint8, BUF_CAM_COUNTERS: np.uint32}
 
 
 class Camera(C.Structure):  # ug_camera == camera.h:7-47
@@ -83,7 +83,7 @@ def lib() -> C.CDLL:
         vp, f, i = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)
         sig = {
             "ug_create": (C.c_int, [C.POINTER(vp), C.c_int]), "ug_destroy": (None, [vp]), "ug_last_error": (C.c_char_p, [vp]),
-            "ug_version": (C.c_char_p, []), "ug_frame_const_bytes": (C.c_size_t, []), "ug_set_stream": (C.c_int, [vp, vp]), "ug_set_rgb_buffer": (C.c_int, [vp, vp, C.c_size_t]), "ug_synchronize": (C.c_int, [vp]),
+            "ug_version": (C.c_char_p, []), "ug_frame_const_bytes": (C.c_size_t, []), "ug_set_stream": (C.c_int, [vp, vp]), "ug_comm_unique_id": (C.c_int, [vp]), "ug_comm_init": (C.c_int, [vp, C.c_int, C.c_int, vp]), "ug_set_rgb_buffer": (C.c_int, [vp, vp, C.c_size_t]), "ug_synchronize": (C.c_int, [vp]),
             "ug_model_load": (C.c_int, [vp, C.c_char_p, C.c_char_p]),
             "ug_model_set": (C.c_int, [vp, f, C.c_int, i, C.c_int, i, f, C.c_int]),
             "ug_obj_parse": (C.c_int, [C.c_char_p, i, i, f, i, i]), "ug_material_parse": (C.c_int, [C.c_char_p, i, f]),
@@ -106,6 +106,13 @@ def lib() -> C.CDLL:
             fn.restype, fn.argtypes = res, args
         _lib = L
     return _lib
+
+
+def unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    if lib().ug_comm_unique_id(C.cast(buf, C.c_void_p)) != UG_OK:
+        raise RuntimeError("ug_comm_unique_id failed (libnccl not available?)")
+    return bytes(buf.raw)
 
 
 def make_camera(eye, look, up, near, far, fovy, aspect) -> Camera:
@@ -239,6 +246,11 @@ class Renderer:
 
     def set_rgb_buffer(self, device_ptr: int, nbytes: int):
         self._ck(self.L.ug_set_rgb_buffer(self.ctx, C.c_void_p(device_ptr), nbytes), "ug_set_rgb_buffer")
+
+    def comm_init(self, rank: int, world: int, unique_id: bytes):
+        """Join the NCCL communicator of the strip gather (unique_id: 128 bytes from unique_id() on one rank)."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._ck(self.L.ug_comm_init(self.ctx, rank, world, C.cast(buf, C.c_void_p)), "ug_comm_init")
 
     def synchronize(self):
         self._ck(self.L.ug_synchronize(self.ctx), "ug_synchronize")

@@ -114,6 +114,8 @@ extern "C" void ug_destroy(ug_context *ctx)
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
 	if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+	ugc_destroy(ctx);
+	dfree(ctx->d_rgb_full);
 	free_reflect(ctx->refl);
 	dfree(ctx->d_reflect);
 	free_grid(ctx->cam_grid);
@@ -307,6 +309,11 @@ static int ensure_buffers(ug_context *ctx, int num_lights, bool full, bool refle
 	if (reflect && (ctx->refl.grid.T != T || ctx->refl.N != ctx->N || !ctx->refl.geo)) {
 		int rc = alloc_reflect(ctx, T, ctx->N);
 		if (rc) return rc;
+		changed = true;
+	}
+	if (ctx->comm && ctx->comm_world > 1 && ctx->comm_rank == 0 && ctx->rgb_full_bytes != 3 * (size_t)ctx->W * ctx->H) {
+		ctx->rgb_full_bytes = 3 * (size_t)ctx->W * ctx->H;
+		UG_CUDA(ctx, dmalloc(&ctx->d_rgb_full, ctx->rgb_full_bytes));
 		changed = true;
 	}
 	if (full && !ctx->full_alloc) {
@@ -589,6 +596,19 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 	} else {
 		ctx->last_bounces = 0;
 	}
+	if (ctx->comm && ctx->comm_world > 1 && ctx->strip_count == ctx->comm_world && ctx->strip_index == ctx->comm_rank) {
+		/* the one exchange step: RGB8 strips -> rank 0 over NVLink, inside the frame */
+		size_t bytes[64], offs[64], acc = 0;
+		for (int r = 0; r < ctx->comm_world && r < 64; r++) {
+			const long long lo = (long long)ctx->nby * r / ctx->comm_world, hi = (long long)ctx->nby * (r + 1) / ctx->comm_world;
+			bytes[r] = 3 * (size_t)ctx->W * (size_t)(hi - lo) * UG_TILE;
+			offs[r] = acc;
+			acc += bytes[r];
+		}
+		int rc = ugc_gather_strips(ctx, s, ctx->d_rgb, ctx->d_rgb_full, bytes, offs);
+		if (rc) return rc;
+		L.n += 1;
+	}
 	/* pair counts + overflow flags of every grid ride back with the frame (no extra synchronisation later) */
 	UG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->cam_grid.counters, 4 * sizeof(u32), cudaMemcpyDeviceToHost, s));
 	for (int l = 0; l < nl; l++)
@@ -655,6 +675,7 @@ static unsigned long long frame_key(const ug_context *ctx, const ug_frame_params
 	mix((unsigned long long)(p->transform && ctx->d_vertex_orig_list ? 1 : 0)); mix((unsigned long long)ctx->cam_grid.cap);
 	for (int l = 0; l < p->num_lights; l++) mix((unsigned long long)ctx->light_grid[l].cap);
 	mix((unsigned long long)(p->bounces > 0 && ctx->d_reflect ? p->bounces : 0)); mix((unsigned long long)ctx->refl.grid.cap);
+	mix((unsigned long long)(uintptr_t)ctx->comm); mix((unsigned long long)(uintptr_t)ctx->d_rgb_full);
 	mix((unsigned long long)(uintptr_t)ctx->stream); mix((unsigned long long)(uintptr_t)ctx->d_rgb);
 	return k;
 }
@@ -738,17 +759,21 @@ extern "C" int ug_render_frame_host(ug_context *ctx, const ug_frame_params *p, u
 	cudaPointerAttributes attr;
 	bool direct = cudaPointerGetAttributes(&attr, host_rgb) == cudaSuccess && attr.type == cudaMemoryTypeHost;
 	cudaGetLastError();
+	const bool gathered = ctx->comm && ctx->comm_world > 1 && ctx->strip_count == ctx->comm_world;
+	const size_t out_bytes = gathered ? 3 * (size_t)ctx->W * ctx->H : 3 * (size_t)ctx->N;
+	if (gathered && !direct && ctx->comm_rank == 0) return ug_fail(ctx, UG_ERR_ARG, "gathered frames need a pinned (cudaHostAlloc/registered) destination");
 	unsigned char *dst = direct ? host_rgb : ctx->h_rgb_pinned;
 	for (int attempt = 0; attempt < 3; attempt++) {
 		rc = run_frame_once(ctx, p);
 		if (rc) return rc;
-		UG_CUDA(ctx, cudaMemcpyAsync(dst, ctx->d_rgb, 3 * (size_t)ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
+		if (gathered) { if (ctx->comm_rank == 0) UG_CUDA(ctx, cudaMemcpyAsync(dst, ctx->d_rgb_full, out_bytes, cudaMemcpyDeviceToHost, ctx->stream)); }
+		else UG_CUDA(ctx, cudaMemcpyAsync(dst, ctx->d_rgb, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
 		UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 		bool grew = false;
 		rc = check_overflow(ctx, p->num_lights, &grew, p->bounces > 0 && ctx->d_reflect);
 		if (rc) return rc;
 		if (!grew) {
-			if (!direct) memcpy(host_rgb, ctx->h_rgb_pinned, 3 * (size_t)ctx->N);
+			if (!direct && !gathered) memcpy(host_rgb, ctx->h_rgb_pinned, out_bytes);
 			return UG_OK;
 		}
 		ctx->stats.overflowed = 1;
@@ -886,6 +911,7 @@ static int buffer_info(ug_context *ctx, int buffer, int index, void **ptr, size_
 	case UG_BUF_CAM_OFFSET:
 	case UG_BUF_LIGHT_OFFSET: *ptr = g->offset; *bytes = sizeof(u32) * (size_t)g->C; break;
 	case UG_BUF_SIZELIST: *ptr = g->count; *bytes = sizeof(u32) * (size_t)g->T; break;
+	case UG_BUF_RGB_FULL: *ptr = ctx->d_rgb_full; *bytes = ctx->rgb_full_bytes; break;
 	case UG_BUF_CAM_COUNTERS: *ptr = ctx->cam_grid.counters; *bytes = sizeof(u32) * 32; break;
 	case UG_BUF_T: *ptr = ctx->d_t; *bytes = sizeof(float) * N; break;
 	case UG_BUF_ID: *ptr = ctx->d_id; *bytes = sizeof(int) * N; break;

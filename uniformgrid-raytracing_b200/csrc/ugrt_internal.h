@@ -149,6 +149,12 @@ struct ug_context {
 	size_t pix_alloc = 0;
 	bool full_alloc = false;
 
+	/* multi-GPU strips (comm.cpp) */
+	void *comm = nullptr;            /* ncclComm_t */
+	int comm_rank = 0, comm_world = 1;
+	unsigned char *d_rgb_full = nullptr; /* rank 0: the gathered frame, 3*W*H */
+	size_t rgb_full_bytes = 0;
+
 	/* CUDA graph of the frame */
 	cudaGraphExec_t graph_exec = nullptr;
 	unsigned long long graph_key = 0;
@@ -208,6 +214,10 @@ void ugk_fill_u32(cudaStream_t s, u32 *p, u32 v, size_t n, int sms);
 size_t ugk_ugrid_const_bytes(void);
 void ugk_reflect_grid(cudaStream_t s, ug_context *ctx, int *launches);
 void ugk_reflect_rays(cudaStream_t s, ug_context *ctx, int bounces, int *launches);
+
+/* comm.cpp */
+void ugc_destroy(ug_context *ctx);
+int ugc_gather_strips(ug_context *ctx, cudaStream_t s, const unsigned char *strip, unsigned char *full, const size_t *bytes, const size_t *offs);
 
 /* host helpers (camera_host.cpp, obj_loader.cpp) */
 void ugh_view_const(ViewConst *vc, const ug_camera *cam, int W, int H, int nbx, int nby, int gy_lo, int gy_cnt);

@@ -299,12 +299,12 @@ def scene_d(width: int = 4096, height: int = 4096, target_tris: int = 282000) ->
     L, Wd, Hh = 36.0, 24.0, 9.0
     for i in range(30):
         tx, ty = 4.0 + (i % 6) * 5.5, -9.0 + (i // 6) * 4.5
-        b.add(box((tx - 1.6, ty - 0.9, 1.45), (tx + 1.6, ty + 0.9, 1.6), 14), 1)                   # table top
+        b.add(box((tx - 1.6, ty - 0.9, 1.45), (tx + 1.6, ty + 0.9, 1.6), 10), 1)                   # table top
         b.add(cylinder(tx, ty, 0.0, 1.45, 0.25, 24, 16), 2)                                          # pedestal
         for c in range(6):
             cx, cy = tx - 1.2 + (c % 3) * 1.2, ty + (1.5 if c < 3 else -1.5)
-            b.add(box((cx - 0.35, cy - 0.35, 0.75), (cx + 0.35, cy + 0.35, 0.85), 8), 3)            # seat
-            b.add(box((cx - 0.35, cy + (0.3 if c < 3 else -0.35), 0.85), (cx + 0.35, cy + (0.35 if c < 3 else -0.3), 1.7), 8), 3)
+            b.add(box((cx - 0.35, cy - 0.35, 0.75), (cx + 0.35, cy + 0.35, 0.85), 3), 3)            # seat
+            b.add(box((cx - 0.35, cy + (0.3 if c < 3 else -0.35), 0.85), (cx + 0.35, cy + (0.35 if c < 3 else -0.3), 1.7), 3), 3)
             b.add(cylinder(cx, cy, 0.0, 0.75, 0.06, 8, 4), 2)
     n = 64
     b.add(quad_patch((0, -Wd / 2, 0), (L, 0, 0), (0, 0, Hh), 2 * n, n), 4)
