@@ -170,7 +170,11 @@ def run_ours(args):
     scene = make_scene(args.config)
     r = ug.Renderer(local)
     r.set_scene(scene)
-    r.set_stream(torch.cuda.current_stream().cuda_stream)
+    # the library launches on the stream it is given (NULL would mean its own stream): a dedicated torch stream, made
+    # current, so torch.cuda.Event.record() brackets exactly the library's work
+    work_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(work_stream)
+    r.set_stream(work_stream.cuda_stream)
     nby = scene.height // 8
     lo, hi = nby * rank // world, nby * (rank + 1) // world
     rows = [(nby * (k + 1) // world - nby * k // world) * 8 for k in range(world)]
@@ -211,6 +215,9 @@ def run_ours(args):
     for i in range(args.steps):
         if not args.no_flush:
             flush.zero_()
+        if world > 1:   # start every frame together: the in-frame gather must not be charged for host-side launch skew
+            torch.cuda.synchronize()
+            dist.barrier()
         ev[i][0].record()
         step(i)
         ev[i][1].record()
