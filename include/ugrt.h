@@ -149,10 +149,18 @@ int ug_model_set(ug_context *ctx, const float *vertexlist, int num_vertices, con
                  const int *materiallist_index, const float *materiallist, int num_materials);
 /* host-side parse only (no device): two-call protocol, pass NULL arrays to get the counts */
 int ug_obj_parse(const char *obj_path, int *num_vertices, int *num_faces, float *vertexlist, int *facelist, int *matidx);
+int ug_obj_parse_vertices(const char *obj_path, int *num_vertices, float *vertexlist, int capacity);
 int ug_material_parse(const char *file, int *num_materials, float *materiallist);
 /* reflectivity per material: the MTL `r` value (obj_parser/obj_parser.cpp:262-266 keeps it in obj_material.reflect; the
  * 6-float material file of scene.h:370-439 has no slot for it).  Row R is an authored spec - see DESIGN.md. */
 int ug_model_set_reflect(ug_context *ctx, const float *reflect, int num_materials);
+/* keyframed scenes - Model::tmp_model(path, i) (scene.h:70-120): reload the vertices of <path>/f_<i>.obj into the loaded
+ * model (same topology, at most the model's vertex count) and stage them to the device asynchronously on the frame's
+ * stream through pinned memory; ug_model_update_vertices is the same from a host array; ug_model_bounds returns the
+ * xMin..zMax the loader tracks (scene.h:92-111) */
+int ug_model_tmp_model(ug_context *ctx, const char *path, int i);
+int ug_model_update_vertices(ug_context *ctx, const float *vertexlist, int num_vertices);
+int ug_model_bounds(ug_context *ctx, float *min_max6);
 int ug_model_init_orig_list(ug_context *ctx, int vertices_size, int vertices_offset); /* scene.h:336-368 */
 int ug_model_rotate_bunny(ug_context *ctx, float rot_factor);                         /* scene.h:122-139 */
 
@@ -181,6 +189,8 @@ int ug_render_frame_host(ug_context *ctx, const ug_frame_params *p, uint8_t *hos
 int ug_get_stats(ug_context *ctx, ug_stats *out);                                        /* synchronises */
 int ug_read(ug_context *ctx, int buffer, int index, void *dst, size_t bytes);            /* synchronises; D2H */
 int ug_device_ptr(ug_context *ctx, int buffer, int index, void **ptr, size_t *bytes);    /* no copy */
+int ug_timeline(ug_context *ctx, double *ns64); /* development aid, needs env UG_TIMELINE=1 at ug_create: marker times of the last frame */
+int ug_write_ppm_binary(ug_context *ctx, const char *filename); /* same image as binary P6, top row first */
 int ug_write_ppm(ug_context *ctx, const char *filename);                                 /* per_app_funcs.h:39-66, ASCII P3 */
 /* ms between the stage marks of the last UG_FLAG_STAGE_EVENTS frame, in order: transform, camera grid, primary rays,
  * then per light (light grid, ray->cell map + regroup, shadow rays), then shade; returns the number of intervals

@@ -49,6 +49,15 @@ def test_random_soups(renderer, ug, oracle, seed, ntris, w, h, nl):
     assert_frame(parity.gpu_frame(renderer, s), cpu_frame(oracle, s), s.name)
 
 
+@pytest.mark.parametrize("seed", [77, 78, 79])
+def test_hostile_geometry(renderer, ug, oracle, seed):
+    """No clipping, no culling: triangles through the eye / light plane, behind the camera, degenerate,
+    duplicated - garbage boxes included, every stage must still match the oracle bit for bit."""
+    s = scenes.scene_hostile(seed)
+    renderer.set_scene(s)
+    assert_frame(parity.gpu_frame(renderer, s), cpu_frame(oracle, s), s.name)
+
+
 def test_config_a(renderer, ug, oracle):
     """BASELINE config A: 16 370-triangle icosphere on a plane, 512x512, primary + shadow, 1 light - every stage."""
     s = scenes.scene_a()
@@ -144,6 +153,43 @@ def test_model_load_through_obj(renderer, ug, oracle, tmp_path):
     assert_frame(parity.gpu_frame(renderer, s), cpu_frame(oracle, s), "config A via OBJ loader")
 
 
+def test_keyframed_loader_tmp_model(renderer, ug, oracle, tmp_path):
+    """Model::tmp_model (scene.h:70-120): f_<i>.obj keyframes reloaded into the same topology every frame; each frame
+    must equal the oracle run on that keyframe's vertices (as parsed: the OBJ text is %.6f)."""
+    s = scenes.scene_random(21, 300, 128, 96, 2)
+    obj, mat = scenes.write_obj(s, str(tmp_path / "f_0.obj"))
+    rng = np.random.default_rng(5)
+    for i in (1, 2, 3):
+        k = scenes.Scene(**{**s.__dict__, "verts": (s.verts + rng.normal(scale=0.15, size=s.verts.shape)).astype(np.float32)})
+        scenes.write_obj(k, str(tmp_path / f"f_{i}.obj"))
+    renderer.load(obj, mat)
+    renderer.scene = s
+    for i in (0, 1, 2, 3, 1):
+        renderer.tmp_model(str(tmp_path), i)
+        V, F, M = ug.parse_obj(str(tmp_path / f"f_{i}.obj"))
+        k = scenes.Scene(**{**s.__dict__, "verts": V})
+        b = renderer.bounds()
+        assert np.array_equal(b[:3], V.min(0)) and np.array_equal(b[3:], V.max(0))
+        assert_frame(parity.gpu_frame(renderer, s), cpu_frame(oracle, k), f"keyframe {i}")
+    with pytest.raises(RuntimeError):
+        renderer.tmp_model(str(tmp_path), 9)          # no such keyframe: loud
+    with pytest.raises(RuntimeError):
+        renderer.update_vertices(np.zeros((len(s.verts) + 1, 3), np.float32))   # more vertices than the model holds
+
+
+def test_binary_ppm(renderer, ug, tmp_path):
+    s = scenes.scene_random(22, 200, 128, 96, 1)
+    renderer.set_scene(s)
+    renderer.render(renderer.params(s))
+    rgb = renderer.read(ug.BUF_RGB).reshape(s.height, s.width, 3)
+    path = tmp_path / "o.ppm"
+    renderer.write_ppm_binary(str(path))
+    raw = path.read_bytes()
+    head = b"P6\n%d %d\n255\n" % (s.width, s.height)
+    assert raw.startswith(head) and len(raw) == len(head) + rgb.size
+    assert np.array_equal(np.frombuffer(raw[len(head):], np.uint8).reshape(s.height, s.width, 3), rgb[::-1])   # top row first
+
+
 def test_pair_arena_overflow_regrows(ug, oracle):
     """P is data dependent: a scene whose pair count exceeds the initial arena must be re-run with a larger one."""
     # 24 huge triangles at 1024x1024: each covers most of the 16 384 cells -> P far above 16*T + C + 2^20
@@ -195,6 +241,28 @@ def test_reflection_row_r(renderer, ug, oracle, make, bounces):
     assert np.array_equal(again["rgb"], gpu["rgb"])
     plain = parity.gpu_frame(renderer, s, flags=0, bounces=0)                         # bounces off -> the reference frame
     assert np.array_equal(plain["rgb"], cpu["rgb"])
+
+
+@pytest.mark.parametrize("env", [{"UG_NO_FUSED": "1"}, {"UG_FUSED_GRID": "1", "UG_FUSED_REGROUP": "1", "UG_FUSED_UGRID": "1"}])
+def test_build_variants(ug, oracle, env, monkeypatch):
+    """Every grid / regroup / uniform-grid build exists as a kernel chain and as a one-launch cooperative kernel; which one
+    a frame uses is a per-frame policy (context.cu), so both are forced here: two lights + two reflection bounces."""
+    for k in ("UG_NO_FUSED", "UG_FUSED_GRID", "UG_FUSED_REGROUP", "UG_FUSED_UGRID"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    r = ug.Renderer()      # the switches are read by ug_create
+    try:
+        s = reflective(scenes.scene_random(31, 900, 192, 128, 2), (0.5, 0.3), 2)
+        r.set_scene(s)
+        cpu = harness.run_frame(oracle, s, threads=0, reflect=True)
+        gpu = parity.gpu_frame(r, s, bounces=2)
+        for k in ("cam_values", "cam_span", "cam_offset", "t", "id", "shadowed", "light0_values", "light1_values", "light0_cell", "light1_cell"):
+            assert np.array_equal(gpu[k], cpu[k]), k
+        assert np.array_equal(gpu["rgb"], cpu["rgb_reflect"])
+        assert np.array_equal(parity.gpu_frame(r, s, bounces=0)["rgb"], cpu["rgb"])
+    finally:
+        r.close()
 
 
 def test_full_size_properties(renderer, ug):

@@ -44,6 +44,14 @@ def test_random_soups(ref, oracle, seed, ntris, w, h, nl):
     check_frame(ref, oracle, scenes.scene_random(seed, ntris, w, h, nlights=nl))
 
 
+@pytest.mark.parametrize("seed", [77, 78])
+def test_hostile_geometry(ref, oracle, seed):
+    """Triangles through the eye plane / behind the camera / degenerate / duplicated: whatever the reference computes
+    (garbage boxes included) the oracle must compute too."""
+    out = check_frame(ref, oracle, scenes.scene_hostile(seed))
+    assert out["cam_P"] > 5000 and (out["id"] == 5).sum() == 0     # the duplicate (id 5) never beats id 4
+
+
 def test_config_a_reduced(ref, oracle):
     out = check_frame(ref, oracle, scenes.scene_a(256, 256))
     assert out["cam_P"] > 16370 and out["shadowed"].sum() > 1000

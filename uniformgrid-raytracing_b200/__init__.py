@@ -97,7 +97,9 @@ def lib() -> C.CDLL:
             "ug_render_frame_host": (C.c_int, [vp, C.POINTER(FrameParams), C.c_void_p]),
             "ug_get_stats": (C.c_int, [vp, C.POINTER(Stats)]), "ug_read": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_size_t]),
             "ug_device_ptr": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]),
-            "ug_write_ppm": (C.c_int, [vp, C.c_char_p]), "ug_stage_times": (C.c_int, [vp, f, C.c_int]),
+            "ug_write_ppm": (C.c_int, [vp, C.c_char_p]), "ug_write_ppm_binary": (C.c_int, [vp, C.c_char_p]),
+            "ug_model_tmp_model": (C.c_int, [vp, C.c_char_p, C.c_int]), "ug_model_update_vertices": (C.c_int, [vp, f, C.c_int]),
+            "ug_model_bounds": (C.c_int, [vp, f]), "ug_obj_parse_vertices": (C.c_int, [C.c_char_p, i, f, C.c_int]), "ug_stage_times": (C.c_int, [vp, f, C.c_int]),
             "ug_camera_adjustCameraAndPosition": (None, [C.POINTER(Camera)]), "ug_camera_pack": (None, [C.POINTER(Camera), f]),
             "ug_direction_lattice": (None, [f, f]),
         }
@@ -218,6 +220,19 @@ class Renderer:
             self._ck(self.L.ug_model_set_reflect(self.ctx, refl.ctypes.data_as(C.POINTER(C.c_float)), refl.size), "ug_model_set_reflect")
         self.scene = scene
 
+    # ---- keyframed scenes (Model::tmp_model, scene.h:70-120)
+    def tmp_model(self, path: str, i: int):
+        self._ck(self.L.ug_model_tmp_model(self.ctx, path.encode(), int(i)), "ug_model_tmp_model")
+
+    def update_vertices(self, verts):
+        verts = np.ascontiguousarray(verts, np.float32).reshape(-1)
+        self._ck(self.L.ug_model_update_vertices(self.ctx, verts.ctypes.data_as(C.POINTER(C.c_float)), verts.size // 3), "ug_model_update_vertices")
+
+    def bounds(self) -> np.ndarray:
+        out = np.zeros(6, np.float32)
+        self._ck(self.L.ug_model_bounds(self.ctx, out.ctypes.data_as(C.POINTER(C.c_float))), "ug_model_bounds")
+        return out
+
     # ---- frames
     def params(self, scene=None, frame: int = 0, flags: int = 0, strip=(0, 1), bounces: int = 0) -> FrameParams:
         s = scene or self.scene
@@ -284,6 +299,9 @@ class Renderer:
         ptr, nbytes = C.c_void_p(), C.c_size_t()
         self._ck(self.L.ug_device_ptr(self.ctx, buffer, index, C.byref(ptr), C.byref(nbytes)), f"ug_device_ptr({buffer})")
         return ptr.value, nbytes.value
+
+    def write_ppm_binary(self, path: str):
+        self._ck(self.L.ug_write_ppm_binary(self.ctx, path.encode()), "ug_write_ppm_binary")
 
     def write_ppm(self, path: str):
         self._ck(self.L.ug_write_ppm(self.ctx, path.encode()), "ug_write_ppm")

@@ -55,12 +55,29 @@ extern "C" int ug_create(ug_context **out, int device)
 	cudaDeviceProp prop;
 	UG_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
 	ctx->num_sms = prop.multiProcessorCount;
-	ctx->use_fused = ugk_grid_fused_supported(device) && !getenv("UG_NO_FUSED");
-	ctx->use_fused_regroup = ugk_regroup_fused_supported(device) && !getenv("UG_NO_FUSED");
+	/* One-launch cooperative builds win where the build is alone on the critical path (small scenes, one light); with
+	 * more branches in flight (two lights, reflection) they cannot all be resident and the kernel chains, whose short
+	 * kernels interleave with the other branches, come out ahead - measured per config in DESIGN.md section 7.  So the
+	 * grid build is chosen per frame (fused_grid_now), the other two are opt-in.  UG_NO_FUSED / UG_FUSED_* override. */
+	ctx->use_fused = ugk_grid_fused_supported(device) && !getenv("UG_NO_FUSED") && !getenv("UG_NO_FUSED_GRID");
+	ctx->use_fused_regroup = ugk_regroup_fused_supported(device) && !getenv("UG_NO_FUSED") && getenv("UG_FUSED_REGROUP");
+	ctx->use_fused_ugrid = ugk_ugrid_fused_supported(device) && !getenv("UG_NO_FUSED") && getenv("UG_FUSED_UGRID");
+	ctx->force_fused_grid = getenv("UG_FUSED_GRID") != nullptr;
+	if (getenv("UG_TIMELINE")) {
+		UG_CUDA(ctx, cudaMalloc((void **)&ctx->d_stamps, 64 * sizeof(unsigned long long)));
+		UG_CUDA(ctx, cudaMemset(ctx->d_stamps, 0, 64 * sizeof(unsigned long long)));
+	}
+	if (const char *e = getenv("UG_REFL_CELLS_PER_TRI")) {
+		const float v = (float)atof(e);
+		if (v >= 0.25f && v <= 256.0f) ctx->refl_cells_per_tri = v;
+	}
 	UG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
 	ctx->stream = ctx->own_stream;
+	int prio_least = 0, prio_greatest = 0;
+	cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
 	for (int i = 0; i < UG_MAX_LIGHTS; i++) {
-		UG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking));
+		/* the shadow branch is on the frame's critical path; the reflection branch (default priority) fills in around it */
+		UG_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side[i], cudaStreamNonBlocking, getenv("UG_NO_PRIO") ? prio_least : prio_greatest));
 		UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
 	}
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
@@ -68,6 +85,10 @@ extern "C" int ug_create(ug_context **out, int device)
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_init, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_init, cudaStreamNonBlocking));
 	UG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_refl, cudaStreamNonBlocking));
+	/* the uniform-grid build is a chain of short kernels that must be done when the primary rays are: high priority, or
+	 * its blocks queue behind the big kernels of the other branches (measured: 290 us instead of ~120) */
+	UG_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_ugrid, cudaStreamNonBlocking, getenv("UG_NO_PRIO") ? prio_least : prio_greatest));
+	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ugrid, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_refl, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_trace, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaEventCreate(&ctx->ev_t0));
@@ -75,8 +96,8 @@ extern "C" int ug_create(ug_context **out, int device)
 	for (auto &ev : ctx->ev_stage) UG_CUDA(ctx, cudaEventCreate(&ev));
 	UG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_fc, sizeof(FrameConst)));
 	memset(ctx->h_fc, 0, sizeof(FrameConst));
-	UG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_counters, sizeof(u32) * (4 * (2 + UG_MAX_LIGHTS) + 8)));
-	memset(ctx->h_counters, 0, sizeof(u32) * (4 * (2 + UG_MAX_LIGHTS) + 8));
+	UG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_counters, sizeof(u32) * (4 * (2 + UG_MAX_LIGHTS) + UG_MAX_BOUNCES + 1)));
+	memset(ctx->h_counters, 0, sizeof(u32) * (4 * (2 + UG_MAX_LIGHTS) + UG_MAX_BOUNCES + 1));
 	UG_CUDA(ctx, cudaMalloc((void **)&ctx->d_fc, sizeof(FrameConst)));
 	*out = ctx;
 	return UG_OK;
@@ -101,8 +122,10 @@ static void free_rays(LightRays &r)
 static void free_reflect(ReflectState &r)
 {
 	free_grid(r.grid);
-	dfree(r.box); dfree(r.geo); dfree(r.rect); dfree(r.O); dfree(r.r); dfree(r.acc); dfree(r.w); dfree(r.live); dfree(r.live_scan); dfree(r.list); dfree(r.ray_counts);
-	dfree(r.scan_state);
+	dfree(r.box); dfree(r.geo); dfree(r.tbox); dfree(r.prec); dfree(r.cellrec);
+	r.prec_cap = 0; dfree(r.rect); dfree(r.O); dfree(r.r); dfree(r.term); dfree(r.w); dfree(r.k0); dfree(r.list[0]); dfree(r.list[1]); dfree(r.list0); dfree(r.depth);
+	dfree(r.ray_counts);
+	r.term_bounces = 0;
 	if (r.uc) cudaFree(r.uc);
 	r.uc = nullptr;
 	r.N = 0;
@@ -125,9 +148,13 @@ extern "C" void ug_destroy(ug_context *ctx)
 	if (ctx->h_rgb_pinned) cudaFreeHost(ctx->h_rgb_pinned);
 	if (ctx->h_fc) cudaFreeHost(ctx->h_fc);
 	if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+	for (int i = 0; i < 2; i++) {
+		if (ctx->h_vstage[i]) cudaFreeHost(ctx->h_vstage[i]);
+		if (ctx->ev_vstage[i]) cudaEventDestroy(ctx->ev_vstage[i]);
+	}
 	dfree(ctx->d_fc);
 	for (int i = 0; i < UG_MAX_LIGHTS; i++) { cudaStreamDestroy(ctx->side[i]); cudaEventDestroy(ctx->ev_join[i]); }
-	cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_fork2); cudaEventDestroy(ctx->ev_init); cudaStreamDestroy(ctx->side_init); cudaStreamDestroy(ctx->side_refl); cudaEventDestroy(ctx->ev_refl); cudaEventDestroy(ctx->ev_trace); cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
+	cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_fork2); cudaEventDestroy(ctx->ev_init); cudaStreamDestroy(ctx->side_init); cudaStreamDestroy(ctx->side_refl); cudaStreamDestroy(ctx->side_ugrid); cudaEventDestroy(ctx->ev_ugrid); cudaEventDestroy(ctx->ev_refl); cudaEventDestroy(ctx->ev_trace); cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
 	for (auto &ev : ctx->ev_stage) cudaEventDestroy(ev);
 	cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
@@ -222,33 +249,62 @@ static int alloc_rays(ug_context *ctx, LightRays &r, int N, int C)
 	return UG_OK;
 }
 
-static int alloc_reflect(ug_context *ctx, int T, int N)
+/* the per-pair records follow the pair arena of the uniform grid (also when it regrows after an overflow) */
+static int alloc_reflect_records(ug_context *ctx)
 {
 	ReflectState &r = ctx->refl;
-	if (r.grid.T == T && r.N == N && r.geo) return UG_OK;
+	if (r.prec && r.prec_cap >= r.grid.cap) return UG_OK;
+	dfree(r.prec);
+	r.prec_cap = 0;
+	UG_CUDA(ctx, dmalloc(&r.prec, r.grid.cap));
+	r.prec_cap = r.grid.cap;
+	return UG_OK;
+}
+
+static int alloc_reflect(ug_context *ctx, int T, int N, int bounces)
+{
+	ReflectState &r = ctx->refl;
+	if (r.grid.T == T && r.N == N && r.geo) {
+		if (bounces > r.term_bounces) { /* deeper recursion than before: one more [3N] term plane per bounce */
+			dfree(r.term);
+			r.term_bounces = 0;
+			UG_CUDA(ctx, dmalloc(&r.term, 3 * (size_t)N * (size_t)bounces));
+			r.term_bounces = bounces;
+		}
+		return UG_OK;
+	}
 	const size_t keep = r.grid.cap;
 	free_reflect(r);
-	long long cells = 4ll * T;
+	long long cells = (long long)(ctx->refl_cells_per_tri * (float)T) + 1;
 	if (cells < 4096) cells = 4096;
-	if (cells > (1ll << 21)) cells = 1ll << 21;
+	if (cells > (1ll << 23)) cells = 1ll << 23;
 	const size_t cap = (size_t)24 * (size_t)T + (size_t)cells + (1u << 20);
 	int rc = alloc_grid(ctx, r.grid, T, (int)cells, keep > cap ? keep : cap);
 	if (rc) return rc;
 	UG_CUDA(ctx, dmalloc(&r.box, 8));
+	{ /* empty box in the order-preserving encoding; the fused build leaves it like this after every launch */
+		const u32 empty[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
+		UG_CUDA(ctx, cudaMemcpy(r.box, empty, sizeof(empty), cudaMemcpyHostToDevice));
+	}
 	UG_CUDA(ctx, cudaMalloc((void **)&r.uc, ugk_ugrid_const_bytes()));
 	UG_CUDA(ctx, dmalloc(&r.geo, 3 * (size_t)T));
+	UG_CUDA(ctx, dmalloc(&r.tbox, 2 * (size_t)T));
+	UG_CUDA(ctx, dmalloc(&r.cellrec, (size_t)cells));
+	rc = alloc_reflect_records(ctx);
+	if (rc) return rc;
 	UG_CUDA(ctx, dmalloc(&r.rect, (size_t)T));
 	UG_CUDA(ctx, dmalloc(&r.O, 3 * (size_t)N));
 	UG_CUDA(ctx, dmalloc(&r.r, 3 * (size_t)N));
-	UG_CUDA(ctx, dmalloc(&r.acc, 3 * (size_t)N));
+	UG_CUDA(ctx, dmalloc(&r.term, 3 * (size_t)N * (size_t)bounces));
+	r.term_bounces = bounces;
 	UG_CUDA(ctx, dmalloc(&r.w, (size_t)N));
-	UG_CUDA(ctx, dmalloc(&r.live, (size_t)N));
-	UG_CUDA(ctx, dmalloc(&r.live_scan, (size_t)N + 1));
-	UG_CUDA(ctx, dmalloc(&r.list, (size_t)N));
-	UG_CUDA(ctx, dmalloc(&r.ray_counts, 8));
-	UG_CUDA(ctx, cudaMemset(r.ray_counts, 0, 8 * sizeof(u32)));
-	r.scan_tiles = ugk_scan_tiles((size_t)N + 2) + 1;
-	UG_CUDA(ctx, dmalloc(&r.scan_state, r.scan_tiles + 1));
+	UG_CUDA(ctx, dmalloc(&r.k0, (size_t)N));
+	UG_CUDA(ctx, dmalloc(&r.list0, (size_t)N));
+	UG_CUDA(ctx, dmalloc(&r.depth, (size_t)N));
+	UG_CUDA(ctx, dmalloc(&r.list[0], (size_t)N));
+	UG_CUDA(ctx, dmalloc(&r.list[1], (size_t)N));
+	UG_CUDA(ctx, dmalloc(&r.ray_counts, UG_MAX_BOUNCES + 1));
+	UG_CUDA(ctx, cudaMemset(r.ray_counts, 0, (UG_MAX_BOUNCES + 1) * sizeof(u32)));
 	r.N = N;
 	return UG_OK;
 }
@@ -256,7 +312,7 @@ static int alloc_reflect(ug_context *ctx, int T, int N)
 static size_t default_cap(int T, int C) { return (size_t)16 * (size_t)T + (size_t)C + (1u << 20); }
 
 /* make every buffer the current (model, screen, strip, lights, flags) needs exist */
-static int ensure_buffers(ug_context *ctx, int num_lights, bool full, bool reflect = false)
+static int ensure_buffers(ug_context *ctx, int num_lights, bool full, int bounces = 0)
 {
 	if (ctx->num_faces <= 0) return ug_fail(ctx, UG_ERR_ARG, "no model loaded");
 	if (ctx->W <= 0) return ug_fail(ctx, UG_ERR_ARG, "screen size not set");
@@ -306,8 +362,8 @@ static int ensure_buffers(ug_context *ctx, int num_lights, bool full, bool refle
 		if (ctx->d_rgb_ext && want != ctx->d_rgb_ext) return ug_fail(ctx, UG_ERR_ARG, "external RGB buffer holds %zu bytes, need %zu", ctx->rgb_ext_bytes, 3 * (size_t)ctx->N);
 		if (want != ctx->d_rgb) { ctx->d_rgb = want; changed = true; }
 	}
-	if (reflect && (ctx->refl.grid.T != T || ctx->refl.N != ctx->N || !ctx->refl.geo)) {
-		int rc = alloc_reflect(ctx, T, ctx->N);
+	if (bounces > 0 && (ctx->refl.grid.T != T || ctx->refl.N != ctx->N || !ctx->refl.geo || ctx->refl.term_bounces < bounces)) {
+		int rc = alloc_reflect(ctx, T, ctx->N, bounces);
 		if (rc) return rc;
 		changed = true;
 	}
@@ -341,6 +397,12 @@ extern "C" int ug_model_set(ug_context *ctx, const float *vertexlist, int num_ve
 	if (materiallist && num_materials > 0) ctx->h_materiallist.assign(materiallist, materiallist + (size_t)UG_MATERIAL_SIZE * num_materials);
 	else { ctx->h_materiallist.clear(); num_materials = 0; }
 	ctx->num_vertices = num_vertices; ctx->num_faces = num_faces; ctx->num_materials = num_materials;
+	for (int k = 0; k < 3; k++) { ctx->bounds[k] = 9999.9f; ctx->bounds[3 + k] = -9999.9f; } /* scene.h:224-229 */
+	for (size_t i = 0; i < 3 * (size_t)num_vertices; i++) {
+		const int k = (int)(i % 3);
+		if (vertexlist[i] < ctx->bounds[k]) ctx->bounds[k] = vertexlist[i];
+		if (vertexlist[i] > ctx->bounds[3 + k]) ctx->bounds[3 + k] = vertexlist[i];
+	}
 	UG_CUDA(ctx, dmalloc(&ctx->d_vertexlist, 3 * (size_t)num_vertices + 4));
 	UG_CUDA(ctx, dmalloc(&ctx->d_facelist, 3 * (size_t)num_faces));
 	UG_CUDA(ctx, dmalloc(&ctx->d_materiallist_index, (size_t)num_faces));
@@ -376,6 +438,68 @@ extern "C" int ug_model_load(ug_context *ctx, const char *obj_path, const char *
 	std::vector<int> F(3 * (size_t)nf), M(nf);
 	ug_obj_parse(obj_path, &nv, &nf, V.data(), F.data(), M.data());
 	return ug_model_set(ctx, V.data(), nv, F.data(), nf, M.data(), nm ? mats.data() : nullptr, nm);
+}
+
+/* Keyframed scenes: Model::tmp_model (scene.h:70-120) re-reads f_<i>.obj every frame, overwrites h_vertexlist and does a
+ * blocking cudaMemcpy of faces + vertices.  Here only the vertices move (the topology is fixed by contract - the
+ * reference copies an unchanged h_facelist), through one of two pinned staging blocks, asynchronously on the frame's
+ * stream: the caller may parse keyframe i+1 while frame i renders.  Pointers do not change, so the captured graph stays. */
+extern "C" int ug_model_update_vertices(ug_context *ctx, const float *vertexlist, int num_vertices)
+{
+	if (!ctx || !vertexlist || ctx->num_vertices <= 0) return ug_fail(ctx, UG_ERR_ARG, "update_vertices: no model");
+	if (num_vertices <= 0 || num_vertices > ctx->num_vertices)
+		return ug_fail(ctx, UG_ERR_ARG, "update_vertices: %d vertices, the model holds %d", num_vertices, ctx->num_vertices);
+	UG_CUDA(ctx, cudaSetDevice(ctx->device));
+	const size_t n = 3 * (size_t)num_vertices;
+	if (ctx->vstage_floats < 3 * (size_t)ctx->num_vertices) {
+		for (int i = 0; i < 2; i++) {
+			if (ctx->ev_vstage[i]) UG_CUDA(ctx, cudaEventSynchronize(ctx->ev_vstage[i]));
+			if (ctx->h_vstage[i]) cudaFreeHost(ctx->h_vstage[i]);
+			ctx->h_vstage[i] = nullptr;
+			UG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_vstage[i], sizeof(float) * 3 * (size_t)ctx->num_vertices));
+			if (!ctx->ev_vstage[i]) UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_vstage[i], cudaEventDisableTiming));
+		}
+		ctx->vstage_floats = 3 * (size_t)ctx->num_vertices;
+	}
+	const int b = ctx->vstage_next;
+	ctx->vstage_next ^= 1;
+	UG_CUDA(ctx, cudaEventSynchronize(ctx->ev_vstage[b])); /* the copy that last used this block (two updates ago) */
+	float lo[3] = {9999.9f, 9999.9f, 9999.9f}, hi[3] = {-9999.9f, -9999.9f, -9999.9f}; /* scene.h:92-97 */
+	float *st = ctx->h_vstage[b];
+	for (size_t i = 0; i < n; i++) {
+		const float v = vertexlist[i];
+		st[i] = v;
+		const int k = (int)(i % 3);
+		if (v < lo[k]) lo[k] = v;
+		if (v > hi[k]) hi[k] = v;
+	}
+	for (int k = 0; k < 3; k++) { ctx->bounds[k] = lo[k]; ctx->bounds[3 + k] = hi[k]; }
+	std::copy(vertexlist, vertexlist + n, ctx->h_vertexlist.begin());
+	UG_CUDA(ctx, cudaMemcpyAsync(ctx->d_vertexlist, st, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+	UG_CUDA(ctx, cudaEventRecord(ctx->ev_vstage[b], ctx->stream));
+	ctx->frame_valid = false;
+	return UG_OK;
+}
+
+extern "C" int ug_model_tmp_model(ug_context *ctx, const char *path, int i)
+{
+	if (!ctx || !path) return ug_fail(ctx, UG_ERR_ARG, "tmp_model: bad arguments");
+	if (ctx->num_vertices <= 0) return ug_fail(ctx, UG_ERR_ARG, "tmp_model: no model (load the first keyframe with ug_model_load)");
+	char file[4096];
+	if (snprintf(file, sizeof(file), "%s/f_%d.obj", path, i) >= (int)sizeof(file)) return ug_fail(ctx, UG_ERR_ARG, "tmp_model: path too long"); /* scene.h:78-83 */
+	int nv = 0;
+	if (ug_obj_parse_vertices(file, &nv, nullptr, 0) != UG_OK) return ug_fail(ctx, UG_ERR_IO, "cannot read %s", file);
+	if (nv <= 0 || nv > ctx->num_vertices) return ug_fail(ctx, UG_ERR_IO, "%s: %d vertices, the model holds %d", file, nv, ctx->num_vertices);
+	std::vector<float> V(3 * (size_t)nv);
+	ug_obj_parse_vertices(file, &nv, V.data(), nv);
+	return ug_model_update_vertices(ctx, V.data(), nv);
+}
+
+extern "C" int ug_model_bounds(ug_context *ctx, float *min_max6)
+{
+	if (!ctx || !min_max6) return ug_fail(ctx, UG_ERR_ARG, "ug_model_bounds: bad arguments");
+	memcpy(min_max6, ctx->bounds, sizeof(ctx->bounds));
+	return UG_OK;
 }
 
 extern "C" int ug_model_set_reflect(ug_context *ctx, const float *reflect, int num_materials)
@@ -472,7 +596,7 @@ struct Launches { int n = 0; };
 static void enqueue_grid(ug_context *ctx, cudaStream_t s, const ViewConst *vc, GridBuffers &g, Launches &L)
 {
 	const int sms = ctx->num_sms;
-	if (ctx->use_fused && g.key_bits <= 32) {
+	if (ctx->use_fused && ctx->fused_grid_now && g.key_bits <= 32) {
 		const int fb = ugk_grid_fused(s, vc, ctx->d_facelist, ctx->d_vertexlist, g, sms);
 		if (fb >= 0) { g.final_buf = fb; L.n += 1; return; }
 		cudaGetLastError();   /* cooperative launch refused: fall back to the multi-kernel chain for good */
@@ -525,8 +649,12 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 	cudaStream_t s = ctx->stream;
 	const int sms = ctx->num_sms, nl = p->num_lights;
 	const bool full = (p->flags & UG_FLAG_FULL_BUFFERS) != 0;
+	const bool reflect = p->bounces > 0 && ctx->d_reflect;
+	ctx->fused_grid_now = ctx->force_fused_grid || (!reflect && nl <= 1 && ctx->num_faces <= 150000);
 	int k = 0;
 	UG_CUDA(ctx, cudaMemcpyAsync(ctx->d_fc, ctx->h_fc, sizeof(FrameConst), cudaMemcpyHostToDevice, s));
+	unsigned long long *const tl = ctx->d_stamps;
+	ugk_stamp(s, tl, 0);
 	stage_mark(ctx, k, stage_events); /* 0 */
 	if (p->transform && ctx->d_vertex_orig_list) {
 		ugk_transform(s, ctx->d_vertexlist, ctx->d_vertex_orig_list, ctx->size_orig_list, ctx->offset_orig_list, ctx->d_fc, sms);
@@ -537,17 +665,20 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 		UG_CUDA(ctx, cudaEventRecord(ctx->ev_fork, s));
 		for (int l = 0; l < nl; l++) {
 			UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side[l], ctx->ev_fork, 0));
+			if (l == 0) ugk_stamp(ctx->side[l], tl, 10);
 			enqueue_light_zero(ctx, ctx->side[l], l);
 			enqueue_light_grid(ctx, ctx->side[l], l, L);
+			if (l == 0) ugk_stamp(ctx->side[l], tl, 11);
 		}
 	}
-	const bool reflect = p->bounces > 0 && ctx->d_reflect;
 	if (parallel) { /* the per-pixel reset + ray directions do not depend on the grid: their own branch of the graph */
 		UG_CUDA(ctx, cudaEventRecord(ctx->ev_fork2, s));
 		if (reflect) { /* so does the world-space uniform grid of row R */
-			UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_refl, ctx->ev_fork2, 0));
-			ugk_reflect_grid(ctx->side_refl, ctx, &L.n);
-			UG_CUDA(ctx, cudaEventRecord(ctx->ev_refl, ctx->side_refl));
+			UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_ugrid, ctx->ev_fork2, 0));
+			ugk_stamp(ctx->side_ugrid, tl, 20);
+			ugk_reflect_grid(ctx->side_ugrid, ctx, &L.n);
+			ugk_stamp(ctx->side_ugrid, tl, 21);
+			UG_CUDA(ctx, cudaEventRecord(ctx->ev_ugrid, ctx->side_ugrid));
 		}
 		UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_init, ctx->ev_fork2, 0));
 		ugk_init_pixels(ctx->side_init, ctx->d_fc, ctx->d_t, ctx->d_id, ctx->d_shadowed, ctx->d_best, full ? ctx->d_normal : nullptr, ctx->d_dir, ctx->N, sms);
@@ -557,16 +688,32 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 	}
 	L.n += 1;
 	enqueue_grid(ctx, s, &ctx->d_fc->cam, ctx->cam_grid, L);
+	ugk_stamp(s, tl, 1);
 	if (parallel) UG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_init, 0));
 	stage_mark(ctx, k, stage_events); /* 2: camera grid done */
 	ugk_trace(s, ctx->d_fc, ctx->cam_grid, ctx->d_best, ctx->d_cell_done, ctx->d_dir, ctx->d_t, ctx->d_id, full ? ctx->d_normal : nullptr, sms);
 	L.n += 1;
+	ugk_stamp(s, tl, 2);
 	stage_mark(ctx, k, stage_events); /* 3: primary rays done */
+	if (parallel && (nl > 0 || reflect)) UG_CUDA(ctx, cudaEventRecord(ctx->ev_trace, s));
+	if (parallel && reflect) {
+		/* row R needs the primary hits only: the bounces run beside the shadow rays (on the branch that built the
+		 * uniform grid, so that is finished), and a short combine pass joins them with the shaded frame */
+		UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_refl, ctx->ev_trace, 0));
+		UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_refl, ctx->ev_ugrid, 0));
+		ugk_stamp(ctx->side_refl, tl, 22);
+		ugk_reflect_rays(ctx->side_refl, ctx, p->bounces, &L.n);
+		ugk_stamp(ctx->side_refl, tl, 23);
+		UG_CUDA(ctx, cudaEventRecord(ctx->ev_refl, ctx->side_refl));
+	}
 	if (parallel && nl > 0) {
-		UG_CUDA(ctx, cudaEventRecord(ctx->ev_trace, s));
 		for (int l = 0; l < nl; l++) {
 			UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side[l], ctx->ev_trace, 0));
-			enqueue_light_rays(ctx, ctx->side[l], l, L);
+			if (l == 0) ugk_stamp(ctx->side[l], tl, 12);
+			enqueue_light_regroup(ctx, ctx->side[l], l, L);
+			if (l == 0) ugk_stamp(ctx->side[l], tl, 13);
+			enqueue_light_shadow(ctx, ctx->side[l], l, L);
+			if (l == 0) ugk_stamp(ctx->side[l], tl, 14);
 			UG_CUDA(ctx, cudaEventRecord(ctx->ev_join[l], ctx->side[l]));
 			UG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join[l], 0));
 		}
@@ -584,14 +731,19 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 	ugk_shade(s, ctx->d_fc, ctx->d_t, ctx->d_dir, ctx->d_id, ctx->d_shadowed, ctx->cam_grid.tri_rec, ctx->d_materiallist_index, ctx->d_materiallist, ctx->num_materials,
 	          ctx->d_rgb, ctx->d_matid, ctx->N, 1, sms);
 	L.n += 1;
+	ugk_stamp(s, tl, 3);
 	stage_mark(ctx, k, stage_events); /* shade */
 	if (reflect) { /* row R: reflection bounces on top of the shaded frame */
 		if (parallel) UG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_refl, 0));
-		else ugk_reflect_grid(s, ctx, &L.n);
-		ugk_reflect_rays(s, ctx, p->bounces, &L.n);
+		else {
+			ugk_reflect_grid(s, ctx, &L.n);
+			ugk_reflect_rays(s, ctx, p->bounces, &L.n);
+		}
+		ugk_reflect_combine(s, ctx, &L.n);
+		ugk_stamp(s, tl, 4);
 		stage_mark(ctx, k, stage_events);
 		UG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 4 * (1 + UG_MAX_LIGHTS), ctx->refl.grid.counters, 4 * sizeof(u32), cudaMemcpyDeviceToHost, s));
-		UG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 4 * (2 + UG_MAX_LIGHTS), ctx->refl.ray_counts, 8 * sizeof(u32), cudaMemcpyDeviceToHost, s));
+		UG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 4 * (2 + UG_MAX_LIGHTS), ctx->refl.ray_counts, (UG_MAX_BOUNCES + 1) * sizeof(u32), cudaMemcpyDeviceToHost, s));
 		ctx->last_bounces = p->bounces;
 	} else {
 		ctx->last_bounces = 0;
@@ -623,11 +775,12 @@ static int prepare_frame(ug_context *ctx, const ug_frame_params *p)
 {
 	if (!p) return ug_fail(ctx, UG_ERR_ARG, "null frame params");
 	if (p->num_lights < 0 || p->num_lights > UG_MAX_LIGHTS) return ug_fail(ctx, UG_ERR_ARG, "num_lights %d not in [0,%d]", p->num_lights, UG_MAX_LIGHTS);
+	if (p->bounces < 0 || p->bounces > UG_MAX_BOUNCES) return ug_fail(ctx, UG_ERR_ARG, "bounces %d not in [0,%d]", p->bounces, UG_MAX_BOUNCES);
 	int rc = ug_set_screen(ctx, p->width, p->height, p->fovy);
 	if (rc) return rc;
 	rc = ug_set_strip(ctx, p->strip_count > 0 ? p->strip_index : 0, p->strip_count > 0 ? p->strip_count : 1);
 	if (rc) return rc;
-	rc = ensure_buffers(ctx, p->num_lights, (p->flags & UG_FLAG_FULL_BUFFERS) != 0, p->bounces > 0 && ctx->d_reflect);
+	rc = ensure_buffers(ctx, p->num_lights, (p->flags & UG_FLAG_FULL_BUFFERS) != 0, ctx->d_reflect ? p->bounces : 0);
 	if (rc) return rc;
 	/* the previous frame may still be reading the pinned block through its H2D copy */
 	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -732,6 +885,7 @@ static int check_overflow(ug_context *ctx, int num_lights, bool *grew, bool refl
 			const size_t want = (size_t)c[2] + (size_t)c[2] / 4 + 1024;
 			int rc = alloc_grid(ctx, *gs[i], gs[i]->T, gs[i]->C, want);
 			if (rc) return rc;
+			if (gs[i] == &ctx->refl.grid && (rc = alloc_reflect_records(ctx)) != UG_OK) return rc;
 			*grew = true;
 		}
 	}
@@ -974,7 +1128,7 @@ extern "C" int ug_get_stats(ug_context *ctx, ug_stats *out)
 	}
 	s.reflect_rays = 0;
 	s.reflect_pairs = 0;
-	for (int b = 0; b < ctx->last_bounces && b < 8; b++) s.reflect_rays += ctx->h_counters[4 * (2 + UG_MAX_LIGHTS) + b];
+	for (int b = 0; b < ctx->last_bounces && b < UG_MAX_BOUNCES; b++) s.reflect_rays += ctx->h_counters[4 * (2 + UG_MAX_LIGHTS) + b];
 	if (ctx->last_bounces) s.reflect_pairs = ctx->h_counters[4 * (1 + UG_MAX_LIGHTS)];
 	if (ctx->frame_valid) {
 		float ms = 0;
@@ -997,6 +1151,36 @@ extern "C" int ug_stage_times(ug_context *ctx, float *out, int max)
 		out[n++] = ms;
 	}
 	return n;
+}
+
+/* the same image as a binary P6, top row first (what image viewers expect) - ~12x smaller than the P3 text
+ * and written with one fwrite per row */
+/* UG_TIMELINE=1: ns since the frame's first marker for each of the 64 marker slots (0 = not reached) */
+extern "C" int ug_timeline(ug_context *ctx, double *ns64)
+{
+	if (!ctx || !ns64 || !ctx->d_stamps) return ug_fail(ctx, UG_ERR_ARG, "ug_timeline: set UG_TIMELINE=1 before ug_create");
+	unsigned long long h[64];
+	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	UG_CUDA(ctx, cudaMemcpy(h, ctx->d_stamps, sizeof(h), cudaMemcpyDeviceToHost));
+	for (int i = 0; i < 64; i++) ns64[i] = h[i] ? (double)((long long)(h[i] - h[0])) : 0.0;
+	return UG_OK;
+}
+
+extern "C" int ug_write_ppm_binary(ug_context *ctx, const char *filename)
+{
+	if (!ctx || !filename || !ctx->d_rgb) return ug_fail(ctx, UG_ERR_ARG, "write_ppm_binary: nothing rendered");
+	const size_t bytes = 3 * (size_t)ctx->N, row = 3 * (size_t)ctx->W;
+	const int rows = ctx->gy_cnt * UG_TILE;
+	std::vector<unsigned char> img(bytes);
+	int rc = ug_read(ctx, UG_BUF_RGB, 0, img.data(), bytes);
+	if (rc) return rc;
+	FILE *fp = fopen(filename, "wb");
+	if (!fp) return ug_fail(ctx, UG_ERR_IO, "cannot open %s", filename);
+	fprintf(fp, "P6\n%d %d\n255\n", ctx->W, rows);
+	bool ok = true;
+	for (int y = rows - 1; y >= 0 && ok; y--) ok = fwrite(img.data() + row * (size_t)y, 1, row, fp) == row;
+	ok = (fclose(fp) == 0) && ok;
+	return ok ? UG_OK : ug_fail(ctx, UG_ERR_IO, "short write to %s", filename);
 }
 
 extern "C" int ug_write_ppm(ug_context *ctx, const char *filename)

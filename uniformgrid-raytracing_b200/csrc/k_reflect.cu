@@ -14,25 +14,13 @@
  * with a 3-D key (k_sort.cu primitives); the resolution is chosen on the device from the scene's bounding box.
  */
 #include "k_shade_dev.cuh"
-#include "k_grid_dev.cuh"
+#include "k_ugrid_dev.cuh"
 
 #ifndef UG_REFL_LOOK
 #define UG_REFL_LOOK 2            /* DDA look-ahead (cells whose spans are fetched together) */
 #endif
-#ifndef UG_REFL_CELLS_PER_TRI
-#define UG_REFL_CELLS_PER_TRI 4.0f /* uniform-grid resolution: cells per triangle */
-#endif
 
-struct UGridConst {
-	float lo[3], h[3], inv_h[3];
-	int n[3];
-	int cells;
-};
-
-/* ---------------------------------------------------------------- bounding box + resolution */
-static __device__ __forceinline__ u32 f2ord(float f) { const u32 u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
-static __device__ __forceinline__ float ord2f(u32 u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
-
+/* ---------------------------------------------------------------- bounding box + resolution (kernel-chain build) */
 __global__ void k_aabb_reset(u32 *box) { if (threadIdx.x < 3) box[threadIdx.x] = 0xffffffffu; else if (threadIdx.x < 6) box[threadIdx.x] = 0u; }
 
 __global__ void __launch_bounds__(256) k_aabb(const float *__restrict__ verts, int V, u32 *box)
@@ -49,62 +37,18 @@ __global__ void __launch_bounds__(256) k_aabb(const float *__restrict__ verts, i
 	}
 }
 
-__global__ void k_ugrid_setup(const u32 *box, int T, int max_cells, UGridConst *uc)
+__global__ void k_ugrid_setup(const u32 *box, int T, int max_cells, float cells_per_tri, UGridConst *uc)
 {
 	if (threadIdx.x || blockIdx.x) return;
-	float lo[3], ext[3];
-	for (int k = 0; k < 3; k++) {
-		lo[k] = ord2f(box[k]);
-		const float hi = ord2f(box[3 + k]);
-		const float pad = 1e-3f * fmaxf(hi - lo[k], 1e-3f);
-		lo[k] -= pad;
-		ext[k] = (hi + pad) - lo[k];
-	}
-	/* roughly cubic cells, about one cell per triangle (coarser cells = fewer empty DDA steps), capped by the arena */
-	float target = fminf(UG_REFL_CELLS_PER_TRI * (float)T, (float)max_cells);
-	target = fmaxf(target, 8.0f);
-	float hcell = cbrtf(ext[0] * ext[1] * ext[2] / target);
-	int n[3];
-	for (int iter = 0; iter < 64; iter++) {
-		long long prod = 1;
-		for (int k = 0; k < 3; k++) { n[k] = (int)ceilf(ext[k] / hcell); n[k] = max(1, min(n[k], 1024)); prod *= n[k]; }
-		if (prod <= max_cells) break;
-		hcell *= 1.1f;
-	}
-	for (int k = 0; k < 3; k++) {
-		uc->lo[k] = lo[k];
-		uc->n[k] = n[k];
-		uc->h[k] = ext[k] / (float)n[k];
-		uc->inv_h[k] = (float)n[k] / ext[k];
-	}
-	uc->cells = n[0] * n[1] * n[2];
+	ugrid_resolution(box, T, max_cells, cells_per_tri, uc);
 }
 
-/* ---------------------------------------------------------------- grid build */
-static __device__ __forceinline__ int ucell(const UGridConst &u, int k, float x) { return ug_clampi((int)floorf((x - u.lo[k]) * u.inv_h[k]), 0, u.n[k] - 1); }
-
+/* ---------------------------------------------------------------- grid build (kernel chain; k_ugridfused.cu is the one-launch version) */
 __global__ void __launch_bounds__(256) k_ugrid_count(const UGridConst *__restrict__ ucp, const int *__restrict__ faces, const float *__restrict__ verts, int T,
-                                                    float4 *__restrict__ geo, uint4 *__restrict__ rect, u32 *__restrict__ count)
+                                                    float4 *__restrict__ geo, float4 *__restrict__ tbox, uint4 *__restrict__ rect, u32 *__restrict__ count)
 {
 	const UGridConst u = *ucp;
-	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
-		const float *p0 = verts + 3 * (size_t)faces[3 * t], *p1 = verts + 3 * (size_t)faces[3 * t + 1], *p2 = verts + 3 * (size_t)faces[3 * t + 2];
-		const float ax = p0[0], ay = p0[1], az = p0[2];
-		/* (v0, e1, e2) with the staging arithmetic of light_kernel.cu:133-144 */
-		geo[3 * (size_t)t + 0] = make_float4(ax, ay, az, 0.0f);
-		geo[3 * (size_t)t + 1] = make_float4(p1[0] - ax, p1[1] - ay, p1[2] - az, 0.0f);
-		geo[3 * (size_t)t + 2] = make_float4(p2[0] - ax, p2[1] - ay, p2[2] - az, 0.0f);
-		u32 r[3], c = 1;
-		for (int k = 0; k < 3; k++) {
-			const float mn = fminf(p0[k], fminf(p1[k], p2[k])), mx = fmaxf(p0[k], fmaxf(p1[k], p2[k]));
-			const float eps = 1e-4f * u.h[k] + 1e-6f * fmaxf(fabsf(mn), fabsf(mx)); /* conservative margin */
-			const int i0 = ucell(u, k, mn - eps), i1 = ucell(u, k, mx + eps);
-			r[k] = (u32)i0 | ((u32)i1 << 16);
-			c *= (u32)(i1 - i0 + 1);
-		}
-		rect[t] = make_uint4(r[0], r[1], r[2], c);
-		count[t] = c;
-	}
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) count[t] = ugrid_tri_setup(u, faces, verts, t, geo, tbox, rect);
 }
 
 __global__ void __launch_bounds__(256) k_ugrid_emit(const UGridConst *__restrict__ ucp, const u32 *__restrict__ scan, const uint4 *__restrict__ rect, int T,
@@ -123,17 +67,27 @@ __global__ void __launch_bounds__(256) k_ugrid_emit(const UGridConst *__restrict
 		const int tlo = s_range[0], thi = s_range[1];
 		for (u32 p = blk + threadIdx.x; p < blk_end; p += blockDim.x) {
 			const int t = ug_upper_bound(scan, tlo, thi + 1, p) - 1;
-			const uint4 r = rect[t];
-			u32 local = p - scan[t];
-			const u32 sy = (r.y >> 16) - (r.y & 0xffffu) + 1, sz = (r.z >> 16) - (r.z & 0xffffu) + 1;
-			const u32 iz = local % sz; local /= sz;
-			const u32 iy = local % sy, ix = local / sy;
-			const u32 key = (((r.x & 0xffffu) + ix) * (u32)ny + ((r.y & 0xffffu) + iy)) * (u32)nz + ((r.z & 0xffffu) + iz);
+			const u32 key = ugrid_pair_key(rect[t], p - scan[t], ny, nz);
 			keys[p] = key;
 			vals[p] = (u32)t;
 			atomicAdd(&span[key], 1u);
 		}
 	}
+}
+
+__global__ void __launch_bounds__(256) k_ugrid_records(const UGridConst *__restrict__ ucp, const u32 *__restrict__ counters, const u32 *__restrict__ keys,
+                                                      const u32 *__restrict__ vals, const float4 *__restrict__ tbox, uint4 *__restrict__ prec)
+{
+	const UGridConst u = *ucp;
+	const u32 P = counters[0];
+	for (u32 p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) prec[p] = ugrid_pair_record(u, keys[p], vals[p], tbox);
+}
+
+__global__ void __launch_bounds__(256) k_ugrid_cells(const UGridConst *__restrict__ ucp, const u32 *__restrict__ span, const u32 *__restrict__ offset,
+                                                    const uint4 *__restrict__ prec, uint4 *__restrict__ cellrec)
+{
+	const u32 C = (u32)ucp->cells;
+	for (u32 c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) cellrec[c] = ugrid_cell_record(offset[c], span[c], prec);
 }
 
 /* ---------------------------------------------------------------- rays */
@@ -171,6 +125,8 @@ struct ReflectArgs {
 	const FrameConst *fc;
 	const UGridConst *uc;
 	const float4 *geo;           /* [3T] v0, e1, e2 */
+	const uint4 *prec;           /* [P] per-pair record: triangle id + its box clipped to the cell in 16-bit cell units */
+	const uint4 *cellrec;        /* [C] (offset, span, union box lo, hi) of every cell */
 	const u32 *span, *offset, *vals;
 	const int *mat_idx;
 	const float *mat_list, *mat_reflect;
@@ -178,132 +134,183 @@ struct ReflectArgs {
 	const float *t, *dir;
 	const int *id;
 	unsigned char *rgb;
-	float *O, *r, *acc, *w;      /* per-pixel ray state [3N],[3N],[3N],[N] */
-	u32 *live;                   /* [N] flags */
-	const u32 *live_scan;        /* [N+1] */
-	u32 *list;                   /* compacted pixel ids */
+	float *O, *r, *w, *k0;       /* per-pixel ray state [3N],[3N], running weight [N], first-hit reflectivity [N] */
+	float *term;                 /* [bounces][3N]: what bounce b adds to the pixel (w * local colour) */
+	u32 *depth;                  /* [N] number of valid terms */
+	const u32 *list;             /* compacted pixel ids of this bounce's rays */
+	u32 *next;                   /* ... and of the rays it spawns (compaction, see ug_append) */
+	u32 *counts;                 /* [UG_MAX_BOUNCES + 1] rays per bounce: counts[b-1] = rays of bounce b */
 };
+
+/* Ray compaction: the survivors of a warp take consecutive slots - an exclusive scan of the warp's live flags (ballot +
+ * popc) places each one, a single atomicAdd per warp reserves the run.  List order is not deterministic and does not
+ * matter: every ray writes only its own pixel.  All 32 lanes must call. */
+static __device__ __forceinline__ void ug_append(bool live, u32 value, u32 *__restrict__ list, u32 *counter)
+{
+	const u32 m = __ballot_sync(UG_FULL_MASK, live);
+	if (m == 0) return;
+	const int leader = __ffs(m) - 1;
+	u32 base = 0;
+	if ((int)ug_lane() == leader) base = atomicAdd(counter, (u32)__popc(m));
+	base = __shfl_sync(UG_FULL_MASK, base, leader);
+	if (live) list[base + (u32)__popc(m & ((1u << ug_lane()) - 1u))] = value;
+}
 
 /* bounce 0: which pixels spawn a reflection ray */
 __global__ void __launch_bounds__(256) k_refl_init(const ReflectArgs a)
 {
 	const float ex = a.fc->cam.cc[0], ey = a.fc->cam.cc[1], ez = a.fc->cam.cc[2];
-	for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < a.N; pix += gridDim.x * blockDim.x) {
-		u32 live = 0;
-		const int tri = a.id[pix];
-		const float tv = a.t[pix];
-		if (tri >= 0 && tv > 0.0f) {
-			const int m = a.mat_idx[tri];
-			const float k = (m >= 0 && m < a.mat_count) ? a.mat_reflect[m] : 0.0f;
-			if (k > 0) {
-				const float dx = a.dir[3 * (size_t)pix], dy = a.dir[3 * (size_t)pix + 1], dz = a.dir[3 * (size_t)pix + 2];
-				const float Px = ex + tv * dx, Py = ey + tv * dy, Pz = ez + tv * dz;
-				float O[3], r[3];
-				reflect_ray(a.geo[3 * (size_t)tri + 1], a.geo[3 * (size_t)tri + 2], Px, Py, Pz, dx, dy, dz, O, r);
-				for (int c = 0; c < 3; c++) {
-					a.O[3 * (size_t)pix + c] = O[c];
-					a.r[3 * (size_t)pix + c] = r[c];
-					a.acc[3 * (size_t)pix + c] = (1.0f - k) * (float)a.rgb[3 * (size_t)pix + c];
+	for (int w0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); w0 < a.N; w0 += gridDim.x * blockDim.x) { /* warp-uniform trip count */
+		const int pix = w0 + (int)ug_lane();
+		bool live = false;
+		if (pix < a.N) {
+			const int tri = a.id[pix];
+			const float tv = a.t[pix];
+			if (tri >= 0 && tv > 0.0f) {
+				const int m = a.mat_idx[tri];
+				const float k = (m >= 0 && m < a.mat_count) ? a.mat_reflect[m] : 0.0f;
+				if (k > 0) {
+					const float dx = a.dir[3 * (size_t)pix], dy = a.dir[3 * (size_t)pix + 1], dz = a.dir[3 * (size_t)pix + 2];
+					const float Px = ex + tv * dx, Py = ey + tv * dy, Pz = ez + tv * dz;
+					float O[3], r[3];
+					reflect_ray(a.geo[3 * (size_t)tri + 1], a.geo[3 * (size_t)tri + 2], Px, Py, Pz, dx, dy, dz, O, r);
+					for (int c = 0; c < 3; c++) {
+						a.O[3 * (size_t)pix + c] = O[c];
+						a.r[3 * (size_t)pix + c] = r[c];
+					}
+					a.w[pix] = k;
+					a.k0[pix] = k;
+					a.depth[pix] = 0;
+					live = true;
 				}
-				a.w[pix] = k;
-				live = 1;
 			}
 		}
-		a.live[pix] = live;
+		ug_append(live, (u32)pix, a.next, a.counts);
 	}
 }
 
-__global__ void __launch_bounds__(256) k_refl_compact(const u32 *__restrict__ live, const u32 *__restrict__ scan, u32 *__restrict__ list, int N)
-{
-	for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < N; pix += gridDim.x * blockDim.x)
-		if (live[pix]) list[scan[pix]] = (u32)pix;
-}
-
 /* one bounce for every live ray: 3-D DDA through the uniform grid, shade, spawn the next ray or finish the pixel */
-__global__ void __launch_bounds__(128) k_refl_trace(const ReflectArgs a, int bounce)
+#ifndef UG_REFL_MINB
+#define UG_REFL_MINB 8
+#endif
+__global__ void __launch_bounds__(128, UG_REFL_MINB) k_refl_trace(const ReflectArgs a, int bounce)
 {
 	const UGridConst u = *a.uc;
 	const float *R = a.fc->shade_mv;
 	const float l0 = a.fc->light_pos[0], l1 = a.fc->light_pos[1], l2 = a.fc->light_pos[2];
 	const float Lvx = R[0] * l0 + R[4] * l1 + R[8] * l2, Lvy = R[1] * l0 + R[5] * l1 + R[9] * l2, Lvz = R[2] * l0 + R[6] * l1 + R[10] * l2;
-	const u32 nlive = a.live_scan[a.N];
-	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < nlive; i += gridDim.x * blockDim.x) {
-		const int pix = (int)a.list[i];
-		float O[3], r[3];
-		for (int c = 0; c < 3; c++) { O[c] = a.O[3 * (size_t)pix + c]; r[c] = a.r[3 * (size_t)pix + c]; }
+	const u32 nlive = a.counts[bounce - 1];
+	const float hmin = fminf(u.h[0], fminf(u.h[1], u.h[2])), hmax = fmaxf(u.h[0], fmaxf(u.h[1], u.h[2]));
+	const int nz = u.n[2], nyz = u.n[1] * u.n[2];
+	for (u32 i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); i0 < nlive; i0 += gridDim.x * blockDim.x) { /* warp-uniform trip count */
+		const u32 i = i0 + ug_lane();
+		const bool active = i < nlive;
+		const int pix = (int)a.list[active ? i : nlive - 1];
+		const float Ox = a.O[3 * (size_t)pix], Oy = a.O[3 * (size_t)pix + 1], Oz = a.O[3 * (size_t)pix + 2];
+		const float rx = a.r[3 * (size_t)pix], ry = a.r[3 * (size_t)pix + 1], rz = a.r[3 * (size_t)pix + 2];
 		/* entry into the grid's box (the origin sits on a surface, normally inside) */
 		float t_in = 0.0f, t_out = 3.0e38f;
 		bool miss_box = false;
-		for (int k = 0; k < 3; k++) {
-			const float hi = u.lo[k] + u.h[k] * (float)u.n[k];
-			if (r[k] != 0.0f) {
-				float t0 = (u.lo[k] - O[k]) / r[k], t1 = (hi - O[k]) / r[k];
-				if (t0 > t1) { const float s = t0; t0 = t1; t1 = s; }
-				t_in = fmaxf(t_in, t0); t_out = fminf(t_out, t1);
-			} else if (O[k] < u.lo[k] || O[k] > hi) miss_box = true;
+		{
+			const float O[3] = {Ox, Oy, Oz}, r[3] = {rx, ry, rz};
+#pragma unroll
+			for (int k = 0; k < 3; k++) {
+				const float hi = u.lo[k] + u.h[k] * (float)u.n[k];
+				if (r[k] != 0.0f) {
+					float t0 = (u.lo[k] - O[k]) / r[k], t1 = (hi - O[k]) / r[k];
+					if (t0 > t1) { const float s = t0; t0 = t1; t1 = s; }
+					t_in = fmaxf(t_in, t0); t_out = fminf(t_out, t1);
+				} else if (O[k] < u.lo[k] || O[k] > hi) miss_box = true;
+			}
 		}
 		float best = 99999999.9f;
 		int hit = -1;
-		if (!miss_box && t_in <= t_out) {
-			int ci[3], step[3];
-			float tmax[3], tdelta[3];
-			for (int k = 0; k < 3; k++) {
-				const float s = O[k] + t_in * r[k];
-				ci[k] = ucell(u, k, s);
-				step[k] = (r[k] > 0.0f) ? 1 : ((r[k] < 0.0f) ? -1 : 0);
-				if (step[k] != 0) {
-					const float bound = u.lo[k] + u.h[k] * (float)(ci[k] + (step[k] > 0 ? 1 : 0));
-					tmax[k] = (bound - O[k]) / r[k];
-					tdelta[k] = u.h[k] / fabsf(r[k]);
-				} else { tmax[k] = 3.0e38f; tdelta[k] = 3.0e38f; }
-			}
-			const float hmin = fminf(u.h[0], fminf(u.h[1], u.h[2]));
-			/* Most cells on a ray's way are empty, so a step would be one dependent load of span[cell] after another:
-			 * walk LOOK cells ahead with the (cheap) DDA arithmetic, fetch their spans together, then visit them in order. */
+		if (active && !miss_box && t_in <= t_out) {
+			/* DDA state in scalars (arrays indexed by the stepping axis would live in local memory), stepped without branches */
+			int cx = ucell(u, 0, Ox + t_in * rx), cy = ucell(u, 1, Oy + t_in * ry), cz = ucell(u, 2, Oz + t_in * rz);
+			const int sx = (rx > 0.0f) ? 1 : ((rx < 0.0f) ? -1 : 0), sy = (ry > 0.0f) ? 1 : ((ry < 0.0f) ? -1 : 0), sz = (rz > 0.0f) ? 1 : ((rz < 0.0f) ? -1 : 0);
+			float tmx = 3.0e38f, tmy = 3.0e38f, tmz = 3.0e38f, tdx = 0.0f, tdy = 0.0f, tdz = 0.0f;
+			if (sx) { tmx = ((u.lo[0] + u.h[0] * (float)(cx + (sx > 0 ? 1 : 0))) - Ox) / rx; tdx = u.h[0] / fabsf(rx); }
+			if (sy) { tmy = ((u.lo[1] + u.h[1] * (float)(cy + (sy > 0 ? 1 : 0))) - Oy) / ry; tdy = u.h[1] / fabsf(ry); }
+			if (sz) { tmz = ((u.lo[2] + u.h[2] * (float)(cz + (sz > 0 ? 1 : 0))) - Oz) / rz; tdz = u.h[2] / fabsf(rz); }
+			int cell = cx * nyz + cy * nz + cz;
+			const int dcx = sx * nyz, dcy = sy * nz;
+			/* A triangle can only be hit inside this cell where its box meets the piece of the ray inside the cell (a hit
+			 * elsewhere is found in that other cell - the pieces tile the ray), so most of a crowded cell's list is
+			 * rejected on six compares.  pad: rounding of O + t r, same form as the margin the boxes were grown by. */
+			const float pad = 1e-4f * hmax + 1e-6f * fmaxf(fabsf(Ox) + t_out * fabsf(rx), fmaxf(fabsf(Oy) + t_out * fabsf(ry), fabsf(Oz) + t_out * fabsf(rz)));
+			const float qsx = 65535.0f * u.inv_h[0], qsy = 65535.0f * u.inv_h[1], qsz = 65535.0f * u.inv_h[2];
+			float t_prev = t_in;
+			/* Most cells on a ray's way are empty, so a step would be one dependent load after another: walk LOOK cells
+			 * ahead with the (cheap) DDA arithmetic, fetch their records together, then visit them in order. */
 			constexpr int LOOK = UG_REFL_LOOK;
 			bool finished = false;
-			for (int guard = 0; guard < 1100 && !finished; guard++) {
-				u32 cells[LOOK], sp[LOOK];
+			for (int guard = 0; guard < 3200 && !finished; guard++) {
+				u32 cpk[LOOK];
+				int cells[LOOK];
+				uint4 cr[LOOK];
 				float texit[LOOK];
 				int nstep = 0;
 				bool left = false;
 #pragma unroll
 				for (int j = 0; j < LOOK; j++) {
-					cells[j] = 0; texit[j] = 0.0f;
+					cpk[j] = 0; texit[j] = 0.0f; cells[j] = 0;
 					if (!left) {
-						cells[j] = ((u32)ci[0] * (u32)u.n[1] + (u32)ci[1]) * (u32)u.n[2] + (u32)ci[2];
-						const int ax = (tmax[0] <= tmax[1]) ? ((tmax[0] <= tmax[2]) ? 0 : 2) : ((tmax[1] <= tmax[2]) ? 1 : 2);
-						texit[j] = tmax[ax];
+						cpk[j] = (u32)cx | ((u32)cy << 10) | ((u32)cz << 20);
+						cells[j] = cell;
 						nstep = j + 1;
-						ci[ax] += step[ax];
-						if (step[ax] == 0 || ci[ax] < 0 || ci[ax] >= u.n[ax]) left = true;
-						tmax[ax] += tdelta[ax];
+						const bool ax0 = (tmx <= tmy) && (tmx <= tmz), ax1 = !ax0 && (tmy <= tmz), ax2 = !ax0 && !ax1;
+						texit[j] = ax0 ? tmx : (ax1 ? tmy : tmz);
+						tmx += ax0 ? tdx : 0.0f; tmy += ax1 ? tdy : 0.0f; tmz += ax2 ? tdz : 0.0f;
+						cx += ax0 ? sx : 0; cy += ax1 ? sy : 0; cz += ax2 ? sz : 0;
+						cell += ax0 ? dcx : (ax1 ? dcy : sz);
+						const int moved = ax0 ? sx : (ax1 ? sy : sz);
+						left = (moved == 0) | ((u32)cx >= (u32)u.n[0]) | ((u32)cy >= (u32)u.n[1]) | ((u32)cz >= (u32)nz);
 					}
 				}
 #pragma unroll
-				for (int j = 0; j < LOOK; j++) sp[j] = (j < nstep) ? a.span[cells[j]] : 0u;
+				for (int j = 0; j < LOOK; j++) cr[j] = (j < nstep) ? a.cellrec[cells[j]] : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
 				for (int j = 0; j < LOOK; j++) {
 					if (j >= nstep || finished) continue;
-					if (sp[j]) {
-						const u32 off = a.offset[cells[j]];
-						for (u32 q = 0; q < sp[j]; q++) {
-							const int tri = (int)a.vals[off + q];
-							float tt;
-							if (!intersect_full(a.geo[3 * (size_t)tri], a.geo[3 * (size_t)tri + 1], a.geo[3 * (size_t)tri + 2], O[0], O[1], O[2], r[0], r[1], r[2], tt)) continue;
-							if (tt > 0.0f && (tt < best || (tt == best && tri < hit))) { best = tt; hit = tri; }
+					if (cr[j].y) {
+						const int jx = (int)(cpk[j] & 1023u), jy = (int)((cpk[j] >> 10) & 1023u), jz = (int)(cpk[j] >> 20);
+						const float clx = u.lo[0] + u.h[0] * (float)jx, cly = u.lo[1] + u.h[1] * (float)jy, clz = u.lo[2] + u.h[2] * (float)jz;
+						const float ax_ = Ox + t_prev * rx, bx_ = Ox + texit[j] * rx, ay_ = Oy + t_prev * ry, by_ = Oy + texit[j] * ry, az_ = Oz + t_prev * rz, bz_ = Oz + texit[j] * rz;
+						/* the ray piece in cell units, rounded outwards */
+						const u32 sxl = (u32)floorf(q16(fminf(ax_, bx_) - pad, clx, qsx)), sxh = (u32)ceilf(q16(fmaxf(ax_, bx_) + pad, clx, qsx));
+						const u32 syl = (u32)floorf(q16(fminf(ay_, by_) - pad, cly, qsy)), syh = (u32)ceilf(q16(fmaxf(ay_, by_) + pad, cly, qsy));
+						const u32 szl = (u32)floorf(q16(fminf(az_, bz_) - pad, clz, qsz)), szh = (u32)ceilf(q16(fmaxf(az_, bz_) + pad, clz, qsz));
+						/* the whole cell first (10-bit union box) */
+						const u32 ulo = cr[j].z, uhi = cr[j].w;
+						const bool cell_out = ((ulo & 1023u) > ((sxh + 63u) >> 6)) | ((uhi & 1023u) < (sxl >> 6)) | (((ulo >> 10) & 1023u) > ((syh + 63u) >> 6)) |
+						                      (((uhi >> 10) & 1023u) < (syl >> 6)) | ((ulo >> 20) > ((szh + 63u) >> 6)) | ((uhi >> 20) < (szl >> 6));
+						if (!cell_out) {
+							const uint4 *rec = a.prec + cr[j].x;
+							const u32 n = cr[j].y;
+							uint4 cur = rec[0];
+							for (u32 q = 0; q < n; q++) {
+								const uint4 c = cur;
+								if (q + 1 < n) cur = rec[q + 1]; /* next record in flight during this one's test */
+								const bool out = ((c.y & 0xffffu) > sxh) | ((c.y >> 16) < sxl) | ((c.z & 0xffffu) > syh) | ((c.z >> 16) < syl) | ((c.w & 0xffffu) > szh) | ((c.w >> 16) < szl);
+								if (out) continue;
+								const int tri = (int)c.x;
+								float tt;
+								if (!intersect_full(a.geo[3 * (size_t)tri], a.geo[3 * (size_t)tri + 1], a.geo[3 * (size_t)tri + 2], Ox, Oy, Oz, rx, ry, rz, tt)) continue;
+								if (tt > 0.0f && (tt < best || (tt == best && tri < hit))) { best = tt; hit = tri; }
+							}
 						}
 					}
+					t_prev = texit[j];
 					/* clearly before this cell's exit: nothing in a later cell can win */
 					if (hit >= 0 && best < texit[j] * 0.999f - 1e-4f * hmin) finished = true;
 				}
 				if (left) finished = true;
 			}
 		}
-		/* spec: accumulate, then finish the pixel or spawn the next ray */
-		float acc[3] = {a.acc[3 * (size_t)pix], a.acc[3 * (size_t)pix + 1], a.acc[3 * (size_t)pix + 2]};
-		const float w = a.w[pix];
-		u32 live = 0;
+		const float O[3] = {Ox, Oy, Oz}, r[3] = {rx, ry, rz};
+		/* spec: this bounce's term of the pixel sum (added in bounce order by k_refl_combine), then spawn the next ray */
+		bool live = false;
 		if (hit >= 0) {
 			const float Px = O[0] + best * r[0], Py = O[1] + best * r[1], Pz = O[2] + best * r[2];
 			const float4 e1 = a.geo[3 * (size_t)hit + 1], e2 = a.geo[3 * (size_t)hit + 2];
@@ -314,21 +321,39 @@ __global__ void __launch_bounds__(128) k_refl_trace(const ReflectArgs a, int bou
 			                                 a.mat_list[m * UG_MATERIAL_SIZE + 5]);
 			const float local[3] = {(float)(c8 & 255u), (float)((c8 >> 8) & 255u), (float)((c8 >> 16) & 255u)};
 			const float k = (bounce < a.bounces && mat_ok) ? a.mat_reflect[m] : 0.0f;
+			const float w = a.w[pix];
+			float *term = a.term + 3 * ((size_t)(bounce - 1) * (size_t)a.N + (size_t)pix);
+			a.depth[pix] = (u32)bounce;
 			if (!(k > 0)) {
-				for (int c = 0; c < 3; c++) acc[c] = acc[c] + w * local[c];
+				for (int c = 0; c < 3; c++) term[c] = w * local[c];
 			} else {
 				const float wk = w * (1.0f - k);
-				for (int c = 0; c < 3; c++) acc[c] = acc[c] + wk * local[c];
+				for (int c = 0; c < 3; c++) term[c] = wk * local[c];
 				a.w[pix] = w * k;
 				float O2[3], r2[3];
 				reflect_ray(e1, e2, Px, Py, Pz, r[0], r[1], r[2], O2, r2);
-				for (int c = 0; c < 3; c++) { a.O[3 * (size_t)pix + c] = O2[c]; a.r[3 * (size_t)pix + c] = r2[c]; a.acc[3 * (size_t)pix + c] = acc[c]; }
-				live = 1;
+				for (int c = 0; c < 3; c++) { a.O[3 * (size_t)pix + c] = O2[c]; a.r[3 * (size_t)pix + c] = r2[c]; }
+				live = true;
 			}
 		}
-		a.live[pix] = live;
-		if (!live)
-			for (int c = 0; c < 3; c++) a.rgb[3 * (size_t)pix + c] = (unsigned char)acc[c];
+		ug_append(live, (u32)pix, a.next, a.counts + bounce);
+	}
+}
+
+/* spec: pixel = (uchar)(((1-k0)*local0 + term_1) + term_2 ...) for every pixel that spawned a reflection ray; local0 is
+ * the shaded (shadowed) colour, which is why this pass comes after k_shade while the bounces themselves do not */
+__global__ void __launch_bounds__(256) k_refl_combine(const ReflectArgs a, const u32 *__restrict__ list0)
+{
+	const u32 n = a.counts[0];
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const size_t pix = list0[i];
+		const float k = a.k0[pix];
+		const u32 depth = a.depth[pix];
+		float acc[3];
+		for (int c = 0; c < 3; c++) acc[c] = (1.0f - k) * (float)a.rgb[3 * pix + c];
+		for (u32 b = 0; b < depth; b++)
+			for (int c = 0; c < 3; c++) acc[c] = acc[c] + a.term[3 * ((size_t)b * (size_t)a.N + pix) + c];
+		for (int c = 0; c < 3; c++) a.rgb[3 * pix + c] = (unsigned char)acc[c];
 	}
 }
 
@@ -342,10 +367,18 @@ void ugk_reflect_grid(cudaStream_t s, ug_context *ctx, int *launches)
 	ReflectState &rf = ctx->refl;
 	const int sms = ctx->num_sms, T = ctx->num_faces, V = ctx->num_vertices;
 	GridBuffers &g = rf.grid;
+	if (ctx->use_fused_ugrid) { /* one cooperative launch (k_ugridfused.cu); the chain below is the fallback */
+		if (ugk_ugrid_fused(s, ctx)) {
+			if (launches) *launches += 1;
+			return;
+		}
+		cudaGetLastError();
+		ctx->use_fused_ugrid = false;
+	}
 	k_aabb_reset<<<1, 32, 0, s>>>(rf.box);
 	k_aabb<<<min((V + 255) / 256, sms * 4), 256, 0, s>>>(ctx->d_vertexlist, V, rf.box);
-	k_ugrid_setup<<<1, 32, 0, s>>>(rf.box, T, g.C, rf.uc);
-	k_ugrid_count<<<min((T + 255) / 256, sms * 8), 256, 0, s>>>(rf.uc, ctx->d_facelist, ctx->d_vertexlist, T, rf.geo, rf.rect, g.count);
+	k_ugrid_setup<<<1, 32, 0, s>>>(rf.box, T, g.C, ctx->refl_cells_per_tri, rf.uc);
+	k_ugrid_count<<<min((T + 255) / 256, sms * 8), 256, 0, s>>>(rf.uc, ctx->d_facelist, ctx->d_vertexlist, T, rf.geo, rf.tbox, rf.rect, g.count);
 	ugk_exclusive_scan(s, g.count, g.scan, (size_t)T, g.sort.scan_state, g.sort.scan_tiles, sms);
 	cudaMemsetAsync(g.span, 0, sizeof(u32) * (size_t)g.C, s);
 	{
@@ -356,31 +389,49 @@ void ugk_reflect_grid(cudaStream_t s, ug_context *ctx, int *launches)
 	int n = 6;
 	g.final_buf = ugk_radix_sort_pairs(s, g.keys, g.vals, g.counters, g.cap, g.key_bits, g.sort, sms, &n);
 	ugk_exclusive_scan(s, g.span, g.offset, (size_t)g.C, g.sort.scan_state, g.sort.scan_tiles, sms);
-	n += 1;
+	k_ugrid_records<<<sms * 8, 256, 0, s>>>(rf.uc, g.counters, g.keys[g.final_buf], g.vals[g.final_buf], rf.tbox, rf.prec);
+	k_ugrid_cells<<<sms * 8, 256, 0, s>>>(rf.uc, g.span, g.offset, rf.prec, rf.cellrec);
+	n += 3;
 	if (launches) *launches += n;
 }
 
-/* the bounces themselves, on top of the shaded frame */
+static ReflectArgs reflect_args(ug_context *ctx, int bounces)
+{
+	ReflectState &rf = ctx->refl;
+	const GridBuffers &g = rf.grid;
+	ReflectArgs a;
+	a.fc = ctx->d_fc; a.uc = rf.uc; a.geo = rf.geo; a.prec = rf.prec; a.cellrec = rf.cellrec; a.span = g.span; a.offset = g.offset; a.vals = g.vals[g.final_buf];
+	a.mat_idx = ctx->d_materiallist_index; a.mat_list = ctx->d_materiallist; a.mat_reflect = ctx->d_reflect; a.mat_count = ctx->num_materials;
+	a.N = ctx->N; a.bounces = bounces; a.t = ctx->d_t; a.dir = ctx->d_dir; a.id = ctx->d_id; a.rgb = ctx->d_rgb;
+	a.O = rf.O; a.r = rf.r; a.w = rf.w; a.k0 = rf.k0; a.term = rf.term; a.depth = rf.depth; a.list = rf.list0; a.next = rf.list0;
+	a.counts = rf.ray_counts;
+	return a;
+}
+
+/* the bounces themselves: they need the primary hits only (not the shadow bits or the shaded colour) */
 void ugk_reflect_rays(cudaStream_t s, ug_context *ctx, int bounces, int *launches)
 {
 	ReflectState &rf = ctx->refl;
 	const int sms = ctx->num_sms, N = ctx->N;
-	const GridBuffers &g = rf.grid;
 	int n = 0;
-	ReflectArgs a;
-	a.fc = ctx->d_fc; a.uc = rf.uc; a.geo = rf.geo; a.span = g.span; a.offset = g.offset; a.vals = g.vals[g.final_buf];
-	a.mat_idx = ctx->d_materiallist_index; a.mat_list = ctx->d_materiallist; a.mat_reflect = ctx->d_reflect; a.mat_count = ctx->num_materials;
-	a.N = N; a.bounces = bounces; a.t = ctx->d_t; a.dir = ctx->d_dir; a.id = ctx->d_id; a.rgb = ctx->d_rgb;
-	a.O = rf.O; a.r = rf.r; a.acc = rf.acc; a.w = rf.w; a.live = rf.live; a.live_scan = rf.live_scan; a.list = rf.list;
+	ReflectArgs a = reflect_args(ctx, bounces);
 	const int pb = min((N + 255) / 256, sms * 8);
+	cudaMemsetAsync(rf.ray_counts, 0, sizeof(u32) * (UG_MAX_BOUNCES + 1), s);
+	a.next = rf.list0; /* the rays of bounce 1 are the pixels the combine pass rewrites: their list is kept */
 	k_refl_init<<<pb, 256, 0, s>>>(a);
 	n += 1;
 	for (int b = 1; b <= bounces; b++) {
-		ugk_exclusive_scan(s, rf.live, rf.live_scan, (size_t)N, rf.scan_state, rf.scan_tiles, sms);  /* compaction by scan */
-		cudaMemcpyAsync(rf.ray_counts + (b - 1 < 7 ? b - 1 : 7), rf.live_scan + N, sizeof(u32), cudaMemcpyDeviceToDevice, s); /* live rays of bounce b */
-		k_refl_compact<<<pb, 256, 0, s>>>(rf.live, rf.live_scan, rf.list, N);
+		a.list = (b == 1) ? rf.list0 : rf.list[b & 1];
+		a.next = rf.list[(b + 1) & 1];
 		k_refl_trace<<<min((N + 127) / 128, sms * 16), 128, 0, s>>>(a, b);
-		n += 3;
+		n += 1;
 	}
 	if (launches) *launches += n;
+}
+
+void ugk_reflect_combine(cudaStream_t s, ug_context *ctx, int *launches)
+{
+	const ReflectArgs a = reflect_args(ctx, 0);
+	k_refl_combine<<<min((ctx->N + 255) / 256, ctx->num_sms * 8), 256, 0, s>>>(a, ctx->refl.list0);
+	if (launches) *launches += 1;
 }

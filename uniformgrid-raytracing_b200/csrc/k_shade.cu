@@ -106,3 +106,13 @@ void ugk_add_shadows(cudaStream_t s, const int *shadowed, unsigned char *rgb, in
 	if (N <= 0) return;
 	k_add_shadows<<<min((N + 255) / 256, sms * 8), 256, 0, s>>>(shadowed, rgb, N);
 }
+
+/* development aid (env UG_TIMELINE=1): one-thread marker kernels between the stages of every branch of the frame graph,
+ * each writing %globaltimer - the only way to see how the branches really interleave without a tracing tool */
+__global__ void k_stamp(unsigned long long *slot)
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	*slot = t;
+}
+void ugk_stamp(cudaStream_t s, unsigned long long *slots, int slot) { if (slots) k_stamp<<<1, 1, 0, s>>>(slots + slot); }

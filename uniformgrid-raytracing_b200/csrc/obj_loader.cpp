@@ -53,6 +53,29 @@ int lookup(const MaterialNames &m, const char *want)
 
 } // namespace
 
+/* vertices only: the per-frame keyframe read of Model::tmp_model (scene.h:86-111 uses nothing else of the file) */
+extern "C" int ug_obj_parse_vertices(const char *obj_path, int *num_vertices, float *vertexlist, int capacity)
+{
+	if (!obj_path || !num_vertices) return UG_ERR_ARG;
+	FILE *fp = fopen(obj_path, "r");
+	if (!fp) return UG_ERR_IO;
+	char line[500];
+	int nv = 0;
+	while (fgets(line, sizeof(line), fp)) {
+		char *tok = strtok(line, kSpace);
+		if (!tok || strcmp(tok, "v") != 0) continue;
+		for (int k = 0; k < 3; k++) {
+			const char *s = strtok(NULL, kSpace);
+			const double e = s ? atof(s) : 0.0;
+			if (vertexlist && nv < capacity) vertexlist[(size_t)3 * nv + k] = (float)e;
+		}
+		nv++;
+	}
+	fclose(fp);
+	*num_vertices = nv;
+	return UG_OK;
+}
+
 extern "C" int ug_obj_parse(const char *obj_path, int *num_vertices, int *num_faces, float *vertexlist, int *facelist, int *matidx)
 {
 	if (!obj_path || !num_vertices || !num_faces) return UG_ERR_ARG;

@@ -77,17 +77,22 @@ struct LightRays {         /* DecisionData's regroup state (decision_data.h:72-8
 };
 
 struct UGridConst;
+#define UG_MAX_BOUNCES 31
 struct ReflectState {      /* row R: world-space uniform grid + per-pixel reflection ray state (k_reflect.cu) */
 	GridBuffers grid;      /* count/scan/keys/vals/span/offset of the uniform grid; grid.C = cell arena */
 	u32 *box = nullptr;    /* [6] scene bounding box (order-preserving uint encoding) */
 	UGridConst *uc = nullptr;
 	float4 *geo = nullptr; /* [3T] v0, e1, e2 */
+	float4 *tbox = nullptr; /* [2T] grown bounding boxes */
+	uint4 *prec = nullptr;  /* [grid.cap] per-pair records (k_ugrid_records) */
+	uint4 *cellrec = nullptr; /* [grid.C] (offset, span, union box) */
+	size_t prec_cap = 0;
 	uint4 *rect = nullptr; /* [T] cell box of every triangle + pair count */
-	float *O = nullptr, *r = nullptr, *acc = nullptr, *w = nullptr;
-	u32 *live = nullptr, *live_scan = nullptr, *list = nullptr;
-	u32 *ray_counts = nullptr; /* [8] live reflection rays per bounce */
-	u64 *scan_state = nullptr;
-	size_t scan_tiles = 0;
+	float *O = nullptr, *r = nullptr, *w = nullptr, *k0 = nullptr; /* per-pixel ray, running weight, first-hit reflectivity */
+	float *term = nullptr; /* [term_bounces][3N] what bounce b adds to the pixel; summed in order by the combine pass */
+	int term_bounces = 0;
+	u32 *list[2] = {nullptr, nullptr}, *list0 = nullptr, *depth = nullptr; /* compacted rays: list0 = bounce 1 (kept for the combine), then ping-pong */
+	u32 *ray_counts = nullptr; /* [UG_MAX_BOUNCES + 1] live reflection rays per bounce */
 	int N = 0;
 };
 
@@ -95,7 +100,11 @@ struct ug_context {
 	int device = 0;
 	cudaStream_t own_stream = nullptr, stream = nullptr;
 	cudaStream_t side[UG_MAX_LIGHTS] = {};
-	cudaStream_t side_init = nullptr, side_refl = nullptr;
+	cudaStream_t side_init = nullptr, side_refl = nullptr, side_ugrid = nullptr;
+	cudaEvent_t ev_ugrid = nullptr;
+	unsigned long long *d_stamps = nullptr; /* [64] UG_TIMELINE markers, null when off */
+	bool use_fused_ugrid = false, force_fused_grid = false, fused_grid_now = true;
+	float refl_cells_per_tri = 2.0f; /* row R uniform-grid resolution (env UG_REFL_CELLS_PER_TRI overrides) */
 	cudaEvent_t ev_fork2 = nullptr, ev_init = nullptr, ev_refl = nullptr;
 	cudaEvent_t ev_fork = nullptr, ev_trace = nullptr, ev_join[UG_MAX_LIGHTS] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
 	cudaEvent_t ev_stage[40] = {};
@@ -124,6 +133,11 @@ struct ug_context {
 	/* frame constants */
 	FrameConst *h_fc = nullptr; /* pinned */
 	FrameConst *d_fc = nullptr;
+	float *h_vstage[2] = {nullptr, nullptr}; /* pinned staging of the keyframe loader (ug_model_update_vertices), alternating */
+	cudaEvent_t ev_vstage[2] = {nullptr, nullptr};
+	size_t vstage_floats = 0;
+	int vstage_next = 0;
+	float bounds[6] = {0, 0, 0, 0, 0, 0}; /* xMin,yMin,zMin,xMax,yMax,zMax of the last keyframe (scene.h:92-111) */
 	u32 *h_counters = nullptr;  /* pinned [1+UG_MAX_LIGHTS][4]: counters of every grid, copied back by the frame */
 	int num_lights = 0;
 	int last_bounces = 0;
@@ -174,6 +188,7 @@ int ug_fail(ug_context *ctx, int code, const char *fmt, ...);
 
 /* ---------------------------------------------------------------- kernel launchers (k_*.cu) */
 /* K1 transform */
+void ugk_stamp(cudaStream_t s, unsigned long long *slots, int slot);
 void ugk_transform(cudaStream_t s, float *vertexlist, const float *orig, int size, int offset, const FrameConst *fc, int sms);
 /* K2 setup+bin, scan, emit */
 void ugk_setup_bin(cudaStream_t s, const ViewConst *vc, const int *faces, const float *verts, int T, GridBuffers &g, int sms);
@@ -213,7 +228,10 @@ void ugk_fill_u32(cudaStream_t s, u32 *p, u32 v, size_t n, int sms);
 /* row R (k_reflect.cu) */
 size_t ugk_ugrid_const_bytes(void);
 void ugk_reflect_grid(cudaStream_t s, ug_context *ctx, int *launches);
+bool ugk_ugrid_fused_supported(int device);
+bool ugk_ugrid_fused(cudaStream_t s, ug_context *ctx);
 void ugk_reflect_rays(cudaStream_t s, ug_context *ctx, int bounces, int *launches);
+void ugk_reflect_combine(cudaStream_t s, ug_context *ctx, int *launches);
 
 /* comm.cpp */
 void ugc_destroy(ug_context *ctx);

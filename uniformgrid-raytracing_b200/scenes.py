@@ -406,6 +406,27 @@ def scene_random(seed: int, ntris: int, width: int, height: int, nlights: int = 
                  up=(0.0, 0.0, 1.0), lights=lights)
 
 
+def scene_hostile(seed: int = 77, ntris: int = 600, width: int = 128, height: int = 128) -> Scene:
+    """Parity stress: geometry the reference has no protection against - triangles straddling the eye
+    plane and the light's plane (no near clipping: w <= 0 vertices give flipped / huge NDC boxes), triangles behind the
+    camera (mirrored into the image by |t|), zero-area and needle triangles, exact duplicates (tie rule), triangles far
+    outside the frustum (border clamp)."""
+    rng = _rng(seed)
+    cen = np.stack([rng.uniform(-8, 8, ntris), rng.uniform(-14, 25, ntris), rng.uniform(-8, 8, ntris)], axis=1)
+    size = np.exp(rng.uniform(np.log(0.05), np.log(9.0), ntris))[:, None, None]
+    V = cen[:, None, :] + size * rng.normal(size=(ntris, 3, 3)) * 0.5
+    V[5] = V[4]                                   # exact duplicate of triangle 4
+    V[10, 2] = V[10, 1]                           # zero-area (two equal vertices)
+    V[11, 2] = 0.5 * (V[11, 0] + V[11, 1])        # zero-area (collinear)
+    V[12] = np.array([[0.0, -8.0, 1.0]] * 3) + np.array([[0, 0, 0], [1e-3, 30, 0], [0, 30, 1e-3]])   # needle through the eye
+    V = V.reshape(-1, 3).astype(np.float32)
+    F = np.arange(3 * ntris, dtype=np.int32).reshape(-1, 3)
+    M = (np.arange(ntris) % 2).astype(np.int32)
+    mats = [Material("m0", (0.2, 0.2, 0.2), (0.8, 0.6, 0.4)), Material("m1", (0.2, 0.2, 0.2), (0.3, 0.6, 0.9))]
+    return Scene(f"hostile-{seed}", V, F, M, mats, width, height, eye=(0.0, -8.0, 1.0), look=(0.0, 10.0, 0.0), up=(0.0, 0.0, 1.0),
+                 lights=[Light((6.0, 2.0, 9.0), (0.0, 8.0, 0.0), (0.0, 0.0, 1.0)), Light((-3.0, 14.0, 3.0), (1.0, 0.0, 0.0), (0.0, 0.0, 1.0))])
+
+
 SCENES = {"A": scene_a, "B": scene_b, "C": scene_c, "D": scene_d, "E": scene_e}
 
 
