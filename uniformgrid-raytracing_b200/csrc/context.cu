@@ -596,7 +596,8 @@ struct Launches { int n = 0; };
 static void enqueue_grid(ug_context *ctx, cudaStream_t s, const ViewConst *vc, GridBuffers &g, Launches &L)
 {
 	const int sms = ctx->num_sms;
-	if (ctx->use_fused && ctx->fused_grid_now && g.key_bits <= 32) {
+	const bool want_fused = (&g == &ctx->cam_grid) ? ctx->fused_cam_now : ctx->fused_grid_now;
+	if (ctx->use_fused && want_fused && g.key_bits <= 32) {
 		const int fb = ugk_grid_fused(s, vc, ctx->d_facelist, ctx->d_vertexlist, g, sms);
 		if (fb >= 0) { g.final_buf = fb; L.n += 1; return; }
 		cudaGetLastError();   /* cooperative launch refused: fall back to the multi-kernel chain for good */
@@ -650,6 +651,9 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 	const int sms = ctx->num_sms, nl = p->num_lights;
 	const bool full = (p->flags & UG_FLAG_FULL_BUFFERS) != 0;
 	const bool reflect = p->bounces > 0 && ctx->d_reflect;
+	/* measured policy: the camera grid is alone on the critical path in front of the primary rays, so
+	 * it is built by the one-launch kernel; a light grid only when nothing else (second light, uniform grid) runs beside it */
+	ctx->fused_cam_now = ctx->force_fused_grid || ctx->num_faces <= 150000;
 	ctx->fused_grid_now = ctx->force_fused_grid || (!reflect && nl <= 1 && ctx->num_faces <= 150000);
 	int k = 0;
 	UG_CUDA(ctx, cudaMemcpyAsync(ctx->d_fc, ctx->h_fc, sizeof(FrameConst), cudaMemcpyHostToDevice, s));

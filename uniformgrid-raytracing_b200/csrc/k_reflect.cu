@@ -75,12 +75,18 @@ __global__ void __launch_bounds__(256) k_ugrid_emit(const UGridConst *__restrict
 	}
 }
 
-__global__ void __launch_bounds__(256) k_ugrid_records(const UGridConst *__restrict__ ucp, const u32 *__restrict__ counters, const u32 *__restrict__ keys,
-                                                      const u32 *__restrict__ vals, const float4 *__restrict__ tbox, uint4 *__restrict__ prec)
+/* counting fill instead of a sort: the order of a cell's list does not matter to the DDA (nearest hit with ties to the
+ * lower id is order independent), so every pair takes the next free slot of its cell */
+__global__ void __launch_bounds__(256) k_ugrid_fill(const UGridConst *__restrict__ ucp, const u32 *__restrict__ counters, const u32 *__restrict__ keys,
+                                                   const u32 *__restrict__ vals, const float4 *__restrict__ tbox, const u32 *__restrict__ offset,
+                                                   u32 *__restrict__ cursor, uint4 *__restrict__ prec)
 {
 	const UGridConst u = *ucp;
 	const u32 P = counters[0];
-	for (u32 p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) prec[p] = ugrid_pair_record(u, keys[p], vals[p], tbox);
+	for (u32 p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+		const u32 key = keys[p];
+		prec[offset[key] + atomicAdd(&cursor[key], 1u)] = ugrid_pair_record(u, key, vals[p], tbox);
+	}
 }
 
 __global__ void __launch_bounds__(256) k_ugrid_cells(const UGridConst *__restrict__ ucp, const u32 *__restrict__ span, const u32 *__restrict__ offset,
@@ -160,8 +166,13 @@ static __device__ __forceinline__ void ug_append(bool live, u32 value, u32 *__re
 __global__ void __launch_bounds__(256) k_refl_init(const ReflectArgs a)
 {
 	const float ex = a.fc->cam.cc[0], ey = a.fc->cam.cc[1], ez = a.fc->cam.cc[2];
+	/* a warp takes an 8x4 pixel block, not 32 pixels of one row: neighbouring lanes then spawn rays with neighbouring
+	 * origins in both directions, which walk the same cells for longer (W is a multiple of 8, the strip height of 8 rows) */
+	const int W = a.fc->cam.W, bw = W >> 3;
 	for (int w0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); w0 < a.N; w0 += gridDim.x * blockDim.x) { /* warp-uniform trip count */
-		const int pix = w0 + (int)ug_lane();
+		const int blk = w0 >> 5, lane = (int)ug_lane();
+		const int by = blk / bw, bx = blk - by * bw;
+		const int pix = (by * 4 + (lane >> 3)) * W + bx * 8 + (lane & 7);
 		bool live = false;
 		if (pix < a.N) {
 			const int tri = a.id[pix];
@@ -381,15 +392,16 @@ void ugk_reflect_grid(cudaStream_t s, ug_context *ctx, int *launches)
 	k_ugrid_count<<<min((T + 255) / 256, sms * 8), 256, 0, s>>>(rf.uc, ctx->d_facelist, ctx->d_vertexlist, T, rf.geo, rf.tbox, rf.rect, g.count);
 	ugk_exclusive_scan(s, g.count, g.scan, (size_t)T, g.sort.scan_state, g.sort.scan_tiles, sms);
 	cudaMemsetAsync(g.span, 0, sizeof(u32) * (size_t)g.C, s);
+	cudaMemsetAsync(g.keys[1], 0, sizeof(u32) * (size_t)g.C, s); /* fill cursors (the second key buffer is free: nothing is sorted) */
 	{
 		const size_t want = (g.cap + 511) / 512;
 		k_ugrid_emit<<<(unsigned)(want < (size_t)sms * 16 ? (want ? want : 1) : (size_t)sms * 16), 256, 0, s>>>(rf.uc, g.scan, rf.rect, T, (u32)g.cap, g.keys[0],
 		                                                                                                    g.vals[0], g.span, g.counters);
 	}
 	int n = 6;
-	g.final_buf = ugk_radix_sort_pairs(s, g.keys, g.vals, g.counters, g.cap, g.key_bits, g.sort, sms, &n);
+	g.final_buf = 0;
 	ugk_exclusive_scan(s, g.span, g.offset, (size_t)g.C, g.sort.scan_state, g.sort.scan_tiles, sms);
-	k_ugrid_records<<<sms * 8, 256, 0, s>>>(rf.uc, g.counters, g.keys[g.final_buf], g.vals[g.final_buf], rf.tbox, rf.prec);
+	k_ugrid_fill<<<sms * 8, 256, 0, s>>>(rf.uc, g.counters, g.keys[0], g.vals[0], rf.tbox, g.offset, g.keys[1], rf.prec);
 	k_ugrid_cells<<<sms * 8, 256, 0, s>>>(rf.uc, g.span, g.offset, rf.prec, rf.cellrec);
 	n += 3;
 	if (launches) *launches += n;

@@ -103,7 +103,7 @@ struct ug_context {
 	cudaStream_t side_init = nullptr, side_refl = nullptr, side_ugrid = nullptr;
 	cudaEvent_t ev_ugrid = nullptr;
 	unsigned long long *d_stamps = nullptr; /* [64] UG_TIMELINE markers, null when off */
-	bool use_fused_ugrid = false, force_fused_grid = false, fused_grid_now = true;
+	bool use_fused_ugrid = false, force_fused_grid = false, fused_grid_now = true, fused_cam_now = true;
 	float refl_cells_per_tri = 2.0f; /* row R uniform-grid resolution (env UG_REFL_CELLS_PER_TRI overrides) */
 	cudaEvent_t ev_fork2 = nullptr, ev_init = nullptr, ev_refl = nullptr;
 	cudaEvent_t ev_fork = nullptr, ev_trace = nullptr, ev_join[UG_MAX_LIGHTS] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
