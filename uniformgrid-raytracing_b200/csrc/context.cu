@@ -656,7 +656,9 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 	ctx->fused_cam_now = ctx->force_fused_grid || ctx->num_faces <= 150000;
 	ctx->fused_grid_now = ctx->force_fused_grid || (!reflect && nl <= 1 && ctx->num_faces <= 150000);
 	int k = 0;
-	UG_CUDA(ctx, cudaMemcpyAsync(ctx->d_fc, ctx->h_fc, sizeof(FrameConst), cudaMemcpyHostToDevice, s));
+	static_assert(sizeof(FrameConst) % 16 == 0, "FrameConst is fetched in 16-byte words");
+	if (getenv("UG_CONST_MEMCPY")) UG_CUDA(ctx, cudaMemcpyAsync(ctx->d_fc, ctx->h_fc, sizeof(FrameConst), cudaMemcpyHostToDevice, s));
+	else { ugk_fetch_consts(s, ctx->h_fc, ctx->d_fc, sizeof(FrameConst)); L.n += 1; }
 	unsigned long long *const tl = ctx->d_stamps;
 	ugk_stamp(s, tl, 0);
 	stage_mark(ctx, k, stage_events); /* 0 */
@@ -746,8 +748,6 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 		ugk_reflect_combine(s, ctx, &L.n);
 		ugk_stamp(s, tl, 4);
 		stage_mark(ctx, k, stage_events);
-		UG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 4 * (1 + UG_MAX_LIGHTS), ctx->refl.grid.counters, 4 * sizeof(u32), cudaMemcpyDeviceToHost, s));
-		UG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 4 * (2 + UG_MAX_LIGHTS), ctx->refl.ray_counts, (UG_MAX_BOUNCES + 1) * sizeof(u32), cudaMemcpyDeviceToHost, s));
 		ctx->last_bounces = p->bounces;
 	} else {
 		ctx->last_bounces = 0;
@@ -766,9 +766,18 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 		L.n += 1;
 	}
 	/* pair counts + overflow flags of every grid ride back with the frame (no extra synchronisation later) */
-	UG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->cam_grid.counters, 4 * sizeof(u32), cudaMemcpyDeviceToHost, s));
-	for (int l = 0; l < nl; l++)
-		UG_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters + 4 * (1 + l), ctx->light_grid[l].counters, 4 * sizeof(u32), cudaMemcpyDeviceToHost, s));
+	{
+		const u32 *src[UG_MAX_LIGHTS + 3];
+		int words[UG_MAX_LIGHTS + 3], off[UG_MAX_LIGHTS + 3], n = 0;
+		src[n] = ctx->cam_grid.counters; words[n] = 4; off[n++] = 0;
+		for (int l = 0; l < nl; l++) { src[n] = ctx->light_grid[l].counters; words[n] = 4; off[n++] = 4 * (1 + l); }
+		if (reflect) {
+			src[n] = ctx->refl.grid.counters; words[n] = 4; off[n++] = 4 * (1 + UG_MAX_LIGHTS);
+			src[n] = ctx->refl.ray_counts; words[n] = UG_MAX_BOUNCES + 1; off[n++] = 4 * (2 + UG_MAX_LIGHTS);
+		}
+		ugk_publish(s, src, words, off, n, ctx->h_counters);
+		L.n += 1;
+	}
 	if (stage_events) ctx->stage_marks = k;
 	UG_CUDA(ctx, cudaGetLastError());
 	return UG_OK;

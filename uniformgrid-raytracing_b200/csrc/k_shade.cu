@@ -116,3 +116,36 @@ __global__ void k_stamp(unsigned long long *slot)
 	*slot = t;
 }
 void ugk_stamp(cudaStream_t s, unsigned long long *slots, int slot) { if (slots) k_stamp<<<1, 1, 0, s>>>(slots + slot); }
+
+/* The pair counts / overflow flags of every grid and the reflection ray counts ride back with the frame: one tiny kernel
+ * writes them straight into the context's pinned (device-visible) block, instead of one copy-engine node per grid at the
+ * tail of the frame graph (~5 us each in series). */
+struct PublishArgs {
+	const u32 *src[UG_MAX_LIGHTS + 3];
+	int words[UG_MAX_LIGHTS + 3], dst_off[UG_MAX_LIGHTS + 3];
+	int n;
+};
+__global__ void k_publish(const PublishArgs a, u32 *__restrict__ host_block)
+{
+	for (int i = 0; i < a.n; i++)
+		for (int w = threadIdx.x; w < a.words[i]; w += blockDim.x) host_block[a.dst_off[i] + w] = a.src[i][w];
+}
+void ugk_publish(cudaStream_t s, const u32 *const *src, const int *words, const int *dst_off, int n, u32 *host_block)
+{
+	PublishArgs a;
+	a.n = n;
+	for (int i = 0; i < n; i++) { a.src[i] = src[i]; a.words[i] = words[i]; a.dst_off[i] = dst_off[i]; }
+	k_publish<<<1, 64, 0, s>>>(a, host_block);
+}
+
+/* the frame's constant block comes from the context's pinned (device-visible) host copy: a one-block kernel pulls its
+ * ~6 KB over PCIe and stores them in device memory - a kernel node starts sooner than a copy-engine node at the head
+ * of the frame graph */
+__global__ void k_fetch_consts(const uint4 *__restrict__ host_block, uint4 *__restrict__ dev_block, int n16)
+{
+	for (int i = threadIdx.x; i < n16; i += blockDim.x) dev_block[i] = host_block[i];
+}
+void ugk_fetch_consts(cudaStream_t s, const void *host_block, void *dev_block, size_t bytes)
+{
+	k_fetch_consts<<<1, 512, 0, s>>>((const uint4 *)host_block, (uint4 *)dev_block, (int)(bytes / 16));
+}

@@ -188,6 +188,8 @@ int ug_fail(ug_context *ctx, int code, const char *fmt, ...);
 
 /* ---------------------------------------------------------------- kernel launchers (k_*.cu) */
 /* K1 transform */
+void ugk_fetch_consts(cudaStream_t s, const void *host_block, void *dev_block, size_t bytes);
+void ugk_publish(cudaStream_t s, const u32 *const *src, const int *words, const int *dst_off, int n, u32 *host_block);
 void ugk_stamp(cudaStream_t s, unsigned long long *slots, int slot);
 void ugk_transform(cudaStream_t s, float *vertexlist, const float *orig, int size, int offset, const FrameConst *fc, int sms);
 /* K2 setup+bin, scan, emit */
