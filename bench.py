@@ -99,11 +99,12 @@ def make_scene(name: str):
     return s
 
 
-def workload_name(scene, world, bounces=0):
+def workload_name(scene, world, bounces=0, mode="single"):
     return (f"config {scene.name}: {scene.num_tris} triangles, {scene.width}x{scene.height}, primary + shadow"
             + (f" + {bounces} reflection bounce(s)" if bounces else "") + " rays, "
             f"{len(scene.lights)} light(s), full grid rebuild every frame"
-            + (", per-frame vertex transform" if scene.dyn_size else "") + (f", {world} image strips" if world > 1 else ""))
+            + (", per-frame vertex transform" if scene.dyn_size else "")
+            + (f", {world} image strips" if mode == "strips" else "") + (f", {world} frames per step (one per GPU)" if mode == "frames" else ""))
 
 
 # --------------------------------------------------------------------------------------------- reference arm
@@ -175,14 +176,26 @@ def run_ours(args):
     work_stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(work_stream)
     r.set_stream(work_stream.cuda_stream)
+    # N > 1, two ways to shard:
+    #   frames (default): one whole frame per GPU per step, the frames gathered to rank 0 over NCCL - per-GPU work is fixed,
+    #                     so this is the weak-scaling (throughput) series; N = 1 is the same workload
+    #   strips          : ONE frame cut into image strips of cell rows, gathered inside the frame graph - strong scaling
+    #                     (latency) of a single frame; measured after the main loop too and reported under "strips"
+    mode = "single" if world == 1 else ("strips" if args.shard == "strips" else "frames")
     nby = scene.height // 8
-    lo, hi = nby * rank // world, nby * (rank + 1) // world
-    rows = [(nby * (k + 1) // world - nby * k // world) * 8 for k in range(world)]
-    n_local = scene.width * (hi - lo) * 8
-    if world > 1:   # the library gathers the strips itself (NCCL send/recv inside the frame's CUDA graph)
+
+    def strip_of(m):
+        return (rank, world) if m == "strips" else (0, 1)
+
+    def join_comm():   # the library gathers the strips itself (NCCL send/recv inside the frame's CUDA graph)
         uid = [ug.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         r.comm_init(rank, world, uid[0])
+
+    lo, hi = (nby * rank // world, nby * (rank + 1) // world) if mode == "strips" else (0, nby)
+    n_local = scene.width * (hi - lo) * 8
+    if world > 1:
+        join_comm()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)            # > 126 MB L2
     host_img = torch.empty(3 * scene.num_pixels, dtype=torch.uint8).pin_memory()
     rays_frame = scene.rays_per_frame()
@@ -191,8 +204,12 @@ def run_ours(args):
     if not any(m.reflect > 0 for m in scene.materials):
         bounces = 0
 
-    def step(i, flags=0):
-        r.render(r.params(scene, frame=i, flags=flags, strip=(rank, world), bounces=bounces))
+    def step(i, flags=0, m=None):
+        m = m or mode
+        if m == "frames":   # whole frames, collected on rank 0 by the library's own NCCL send/recv inside the frame graph
+            r.render(r.params(scene, frame=i * world + rank, flags=flags | ug.FLAG_GATHER_FRAMES, bounces=bounces))
+        else:
+            r.render(r.params(scene, frame=i, flags=flags, strip=strip_of(m), bounces=bounces))
 
     def barrier():
         if world > 1:
@@ -200,7 +217,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- warm-up (also captures the CUDA graph and grows the pair arena if the scene needs it)
-    r.render_host(r.params(scene, frame=0, strip=(rank, world), bounces=bounces), host_img.numpy())
+    r.render_host(r.params(scene, frame=0, strip=strip_of(mode), bounces=bounces), host_img.numpy())
     for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
@@ -248,7 +265,8 @@ def run_ours(args):
     refl = torch.tensor([float(st.reflect_rays)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(refl)                        # every rank traces the reflection rays of its own strip
-    rays_frame = scene.rays_per_frame() + int(refl.item())
+    frames_per_step = world if mode == "frames" else 1
+    rays_frame = scene.rays_per_frame() * frames_per_step + int(refl.item())   # rays of one step
 
     # ---- e2e: host buffers in, host image out, wall clock
     e2e_steps = max(3, min(args.steps, 50))
@@ -256,8 +274,10 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        # H2D constants + kernels [+ NCCL strip gather] + D2H of the (full) image on rank 0 + sync
-        r.render_host(r.params(scene, frame=i, strip=(rank, world), bounces=bounces), out_np if world == 1 else host_img.numpy())
+        # H2D constants + kernels [+ NCCL strip gather] + D2H of the image (strips: the gathered frame on rank 0;
+        # frames: every rank reads its own frame back over its own PCIe link) + sync
+        r.render_host(r.params(scene, frame=i * frames_per_step + (rank if mode == "frames" else 0), strip=strip_of(mode), bounces=bounces),
+                      out_np if mode != "strips" else host_img.numpy())
     barrier()
     e2e_dt = time.perf_counter() - t0
     e2e_t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
@@ -269,10 +289,32 @@ def run_ours(args):
     stage = {}
     reps = 5
     for i in range(reps):
-        r.render(r.params(scene, frame=i, flags=ug.FLAG_STAGE_EVENTS, strip=(rank, world), bounces=bounces))
+        r.render(r.params(scene, frame=i, flags=ug.FLAG_STAGE_EVENTS, strip=strip_of(mode), bounces=bounces))
         for k, v in r.stage_times().items():
             stage[k] = stage.get(k, 0.0) + v / reps
     st2 = r.stats()
+
+    # ---- N > 1 in frames mode: the same K steps once more as ONE frame in strips (strong scaling of the frame latency)
+    strips = None
+    if mode == "frames":
+        for i in range(5):
+            step(i, m="strips")
+        barrier()
+        k2 = min(args.steps, 50)
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k2)]
+        for i in range(k2):
+            if not args.no_flush:
+                flush.zero_()
+            torch.cuda.synchronize()
+            dist.barrier()
+            ev2[i][0].record()
+            step(i, m="strips")
+            ev2[i][1].record()
+        barrier()
+        t2 = torch.tensor([a.elapsed_time(b) for a, b in ev2], dtype=torch.float64, device=dev)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        strips = {"ms_per_frame": float(t2.mean().item()), "steps": k2, "scaling": "strong",
+                  "note": "one frame cut into %d image strips of cell rows, gathered to rank 0 inside the frame graph (NCCL send/recv)" % world}
 
     if rank == 0:
         P, N, Cc = st2.cam_pairs, st2.num_pixels, st2.num_cells
@@ -316,16 +358,19 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": rays_frame * args.steps / (total_ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(scene, world, bounces), "rays_per_frame": rays_frame,
-                       "rays": {"primary": scene.num_pixels, "shadow": scene.num_pixels * len(scene.lights), "reflection": int(refl.item())},
+            "scaling": "weak" if mode == "frames" else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(scene, world, bounces, mode), "rays_per_step": rays_frame, "frames_per_step": frames_per_step,
+                       "parallelism": {"single": "one GPU", "frames": f"{world} GPUs, one frame each per step, frames gathered to rank 0 (NCCL)",
+                                       "strips": f"{world} GPUs, one frame in {world} image strips, gathered to rank 0 (NCCL, inside the frame graph)"}[mode],
+                       "rays": {"primary": scene.num_pixels * frames_per_step, "shadow": scene.num_pixels * len(scene.lights) * frames_per_step,
+                                "reflection": int(refl.item())},
                        "l2": "flushed between timed frames (256 MiB write)" if not args.no_flush else "not flushed",
                        "timing": "CUDA events per frame on the launching stream, max over ranks, summed over the K frames",
                        "pairs_camera_grid": int(P), "pairs_light_grids": [int(st2.light_pairs[l]) for l in range(len(scene.lights))]},
             "ms_per_frame_warm_l2": warm_ms, "ms_per_frame_p50": float(np.median(per)), "ms_per_frame_p10": float(np.percentile(per, 10)),
             "ms_per_frame_p90": float(np.percentile(per, 90)), "wall_s_timed_region": wall,
             "e2e": {"value": rays_frame * e2e_steps / e2e_dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(ug.lib().ug_frame_const_bytes()) * world,
-                    "d2h_bytes_per_step": 3 * scene.num_pixels, "steps": e2e_steps, "ms_per_step": e2e_dt / e2e_steps * 1e3},
+                    "d2h_bytes_per_step": 3 * scene.num_pixels * frames_per_step, "steps": e2e_steps, "ms_per_step": e2e_dt / e2e_steps * 1e3},
             "gpu_launches": int(launches_per_frame) * args.steps * world,
             "kernels_per_frame": int(launches_per_frame),
             "stage_ms": {k: round(v, 4) for k, v in stage.items()},
@@ -333,6 +378,10 @@ def run_ours(args):
             "frame_hbm_frac": frame_bytes / (total_ms / args.steps * 1e-3) / 1e9 / hbm_peak,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         }
+        if strips:
+            strips["value"] = (scene.rays_per_frame() + int(refl.item()) / frames_per_step) / (strips["ms_per_frame"] * 1e-3) / 1e6
+            strips["unit"] = "Mrays/s"
+            line["strips"] = strips
         json_out.write(json.dumps(line) + "\n")
         json_out.flush()
     if world > 1:
@@ -350,6 +399,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="B", choices=["A", "B", "C", "D", "E"])
     ap.add_argument("--bounces", type=int, default=-1, help="reflection bounces (-1: what the config names)")
+    ap.add_argument("--shard", default="auto", choices=["auto", "frames", "strips"], help="N > 1: frames = one frame per GPU (weak, default), strips = one frame in strips (strong)")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

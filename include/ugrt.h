@@ -90,6 +90,7 @@ typedef struct ug_frame_params {
 
 #define UG_FLAG_FULL_BUFFERS 1 /* also fill the reference's normal/dir/shadowed buffers (decision_data.h:66-82) */
 #define UG_FLAG_NO_GRAPH 2     /* launch kernels directly instead of replaying the captured CUDA graph */
+#define UG_FLAG_GATHER_FRAMES 8 /* with ug_comm_init and no strips: every rank renders its own frame, rank 0 collects them (slot r = rank r) */
 #define UG_FLAG_STAGE_EVENTS 4 /* record one CUDA event per stage (implies NO_GRAPH); see ug_stats.ms_* */
 
 /* buffers that can be read back for parity checks / interop (ug_read, ug_device_ptr) */

@@ -41,6 +41,15 @@ def _worker(rank, world, port, out_path):
     if rank == 0:
         np.save(out_path, host.numpy().copy())
     dist.barrier()
+    # frame-parallel mode: rank k renders frame k of a dynamic scene on its own, rank 0 collects the frames (slot k = rank k)
+    dyn = scenes.scene_c(240, 136)
+    r.set_scene(dyn)
+    for _ in range(2):                                              # capture, replay
+        r.render(r.params(dyn, frame=rank, flags=ug.FLAG_GATHER_FRAMES))
+    r.synchronize()
+    if rank == 0:
+        np.save(out_path + ".frames.npy", r.read(ug.BUF_RGB_FULL)[:3 * dyn.num_pixels * world].copy())
+    dist.barrier()
     r.close()
     dist.destroy_process_group()
 
@@ -56,3 +65,7 @@ def test_strip_gather_over_nccl(oracle, tmp_path):
     out = str(tmp_path / "full.npy")
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert np.array_equal(np.load(out), want)
+    dyn = scenes.scene_c(240, 136)
+    got = np.load(out + ".frames.npy").reshape(world, -1)
+    for k in range(world):
+        assert np.array_equal(got[k], harness.run_frame(oracle, dyn, frame=k, threads=0)["rgb"]), f"frame of rank {k}"

@@ -12,6 +12,7 @@ NAMES = {0: "frame start", 1: "cam grid done", 2: "primary rays done", 3: "shade
          12: "regroup start", 13: "regroup done", 14: "shadow done", 20: "ugrid start", 21: "ugrid done", 22: "refl rays start", 23: "refl rays done"}
 name = sys.argv[1] if len(sys.argv) > 1 else "B"
 bounces = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+strip = (int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else (0, 1)
 s = scenes.SCENES[name]()
 r = ug.Renderer()
 r.set_scene(s)
@@ -19,7 +20,7 @@ L = ug.lib()
 L.ug_timeline.restype = C.c_int
 L.ug_timeline.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-p = r.params(s, bounces=bounces)
+p = r.params(s, bounces=bounces, strip=strip)
 acc = []
 for it in range(8):
     flush.fill_(it)

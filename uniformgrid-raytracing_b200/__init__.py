@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libugrt.so")
 UG_OK = 0
 UG_MAX_LIGHTS = 8
 UG_TILE = 8
-FLAG_FULL_BUFFERS, FLAG_NO_GRAPH, FLAG_STAGE_EVENTS = 1, 2, 4
+FLAG_FULL_BUFFERS, FLAG_NO_GRAPH, FLAG_STAGE_EVENTS, FLAG_GATHER_FRAMES = 1, 2, 4, 8
 
 (BUF_VERTEXLIST, BUF_CAM_VALUES, BUF_CAM_SPAN, BUF_CAM_OFFSET, BUF_T, BUF_ID, BUF_NORMAL, BUF_DIR, BUF_SHADOWED, BUF_RGB,
  BUF_LIGHT_VALUES, BUF_LIGHT_SPAN, BUF_LIGHT_OFFSET, BUF_LIGHT_CELL, BUF_SIZELIST, BUF_RGB_FULL, BUF_CAM_COUNTERS) = range(17)

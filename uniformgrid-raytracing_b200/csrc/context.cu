@@ -367,8 +367,8 @@ static int ensure_buffers(ug_context *ctx, int num_lights, bool full, int bounce
 		if (rc) return rc;
 		changed = true;
 	}
-	if (ctx->comm && ctx->comm_world > 1 && ctx->comm_rank == 0 && ctx->rgb_full_bytes != 3 * (size_t)ctx->W * ctx->H) {
-		ctx->rgb_full_bytes = 3 * (size_t)ctx->W * ctx->H;
+	if (ctx->comm && ctx->comm_world > 1 && ctx->comm_rank == 0 && ctx->rgb_full_bytes != 3 * (size_t)ctx->W * ctx->H * (size_t)ctx->comm_world) {
+		ctx->rgb_full_bytes = 3 * (size_t)ctx->W * ctx->H * (size_t)ctx->comm_world; /* one gathered frame (strips) or one frame per rank (UG_FLAG_GATHER_FRAMES) */
 		UG_CUDA(ctx, dmalloc(&ctx->d_rgb_full, ctx->rgb_full_bytes));
 		changed = true;
 	}
@@ -764,6 +764,13 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 		int rc = ugc_gather_strips(ctx, s, ctx->d_rgb, ctx->d_rgb_full, bytes, offs);
 		if (rc) return rc;
 		L.n += 1;
+	} else if (ctx->comm && ctx->comm_world > 1 && (p->flags & UG_FLAG_GATHER_FRAMES) && ctx->strip_count == 1) {
+		/* frame-parallel rendering: every rank has rendered a whole frame of its own; frame r lands in slot r on rank 0 */
+		size_t bytes[64], offs[64];
+		for (int r = 0; r < ctx->comm_world && r < 64; r++) { bytes[r] = 3 * (size_t)ctx->N; offs[r] = (size_t)r * bytes[r]; }
+		int rc = ugc_gather_strips(ctx, s, ctx->d_rgb, ctx->d_rgb_full, bytes, offs);
+		if (rc) return rc;
+		L.n += 1;
 	}
 	/* pair counts + overflow flags of every grid ride back with the frame (no extra synchronisation later) */
 	{
@@ -837,7 +844,7 @@ static unsigned long long frame_key(const ug_context *ctx, const ug_frame_params
 	unsigned long long k = 1469598103934665603ull;
 	auto mix = [&](unsigned long long v) { k = (k ^ v) * 1099511628211ull; };
 	mix((unsigned long long)ctx->W); mix((unsigned long long)ctx->H); mix((unsigned long long)ctx->gy_lo); mix((unsigned long long)ctx->gy_cnt);
-	mix((unsigned long long)ctx->num_faces); mix((unsigned long long)p->num_lights); mix((unsigned long long)(p->flags & UG_FLAG_FULL_BUFFERS));
+	mix((unsigned long long)ctx->num_faces); mix((unsigned long long)p->num_lights); mix((unsigned long long)(p->flags & (UG_FLAG_FULL_BUFFERS | UG_FLAG_GATHER_FRAMES)));
 	mix((unsigned long long)(p->transform && ctx->d_vertex_orig_list ? 1 : 0)); mix((unsigned long long)ctx->cam_grid.cap);
 	for (int l = 0; l < p->num_lights; l++) mix((unsigned long long)ctx->light_grid[l].cap);
 	mix((unsigned long long)(p->bounces > 0 && ctx->d_reflect ? p->bounces : 0)); mix((unsigned long long)ctx->refl.grid.cap);

@@ -15,7 +15,9 @@
  */
 #include "k_grid_dev.cuh"
 
+#ifndef RS_BLOCKS_PER_SM
 #define RS_BLOCKS_PER_SM 2
+#endif
 
 __global__ void __launch_bounds__(RS_THREADS) rs_hist(const u32 *__restrict__ keys, const u32 *__restrict__ n_dev, u32 n_max, int shift,
                                                       u32 *__restrict__ hist)
