@@ -108,8 +108,9 @@ def workload_name(scene, world, bounces=0, mode="single"):
 
 
 # --------------------------------------------------------------------------------------------- reference arm
-def cpu_reference(scene, frames: int, warmup: int):
-    """Time the reference's own CPU code (host-compiled kernels, oracle/_ref) - falls back to the C port."""
+def cpu_reference(scene, frames: int, warmup: int, budget_s: float = 0.0):
+    """Time the reference's own CPU code (host-compiled kernels, oracle/_ref) - falls back to the C port.
+    budget_s > 0: run whole frames until about that much CPU time is spent (at least `frames`)."""
     from oracle import harness
     kind = "ref" if harness.available("ref") else "oracle"
     if kind == "oracle" and not harness.available("oracle"):
@@ -119,8 +120,11 @@ def cpu_reference(scene, frames: int, warmup: int):
     for _ in range(max(warmup, 0)):
         harness.run_frame(lib, scene, threads=cores)
     t0 = time.perf_counter()
-    for _ in range(frames):
+    done = 0
+    while done < frames or (budget_s > 0 and time.perf_counter() - t0 < budget_s and done < 1000):
         harness.run_frame(lib, scene, threads=cores)
+        done += 1
+    frames = done
     dt = time.perf_counter() - t0
     rays = scene.rays_per_frame() * frames
     return {"value": rays / dt / 1e6, "unit": "Mrays/s", "cores": lib.get_threads(), "kind": "reference" if kind == "ref" else "port",
@@ -133,13 +137,24 @@ def run_reference(args):
     if rank != 0:
         return 0
     scene = make_scene(args.config)
-    frames = max(1, min(args.steps, 5))
+    # each step = one full frame of the workload; K is honoured unless that would take more than ~2 minutes (the first
+    # frame is timed to find out), in which case fewer steps are run and the line says how many
+    from oracle import harness
+    kind = "ref" if harness.available("ref") else "oracle"
+    if kind == "oracle" and not harness.available("oracle"):
+        harness.build("oracle")
+    t0 = time.perf_counter()
+    harness.run_frame(harness.load(kind), scene, threads=os.cpu_count() or 1)
+    one = time.perf_counter() - t0
+    frames = max(1, min(args.steps, int(120.0 / max(one, 1e-3))))
     base = cpu_reference(scene, frames, min(args.warmup, 1))
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": frames,
             "warmup": min(args.warmup, 1), "ms_per_step": base["ms_per_frame"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(scene, 1), "note": "reference kernel sources compiled as host C++ (oracle/_ref), OpenMP over "
-                       "cells/pixels; each step = one full frame; steps capped at 5 to bound the run"},
+                       "cells/pixels on all host cores; each step = one full frame; the reference has no reflection code "
+                       "(SURVEY.md 0.3), so its frames hold the primary and shadow rays only",
+                       "steps_requested": args.steps},
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -319,31 +334,44 @@ def run_ours(args):
     if rank == 0:
         P, N, Cc = st2.cam_pairs, st2.num_pixels, st2.num_cells
         T = scene.num_tris
-        # single-kernel stages only (grid builds / regroup are several kernels)
-        kern = {"trace": ("k_trace", 8 * Cc + 52 * P + 8 * N, 64 * P)}
+        # single-kernel stages only (grid builds / regroup are several kernels); algorithmic bytes per launch from SURVEY.md 8(d)
+        R1 = int(refl.item()) // max(frames_per_step, 1)      # reflection rays of one frame (all bounces)
+        Pu, Cu = int(st2.reflect_pairs), int(2.0 * T)         # uniform grid: pairs, cells (cells_per_tri = 2)
+        kern = {"trace": ("k_trace", 8 * Cc + 52 * P + 8 * N, 64 * P, "FP32-issue bound (ray-triangle tests), not HBM bound: see fp32_issue"),
+                "shade": ("k_shade", (8 + 4 * 1) * N + 3 * N, None, "HBM streaming"),
+                "reflect_rays": ("k_refl_trace", 44 * R1 + 48 * T + 16 * Pu + 16 * Cu, None,
+                                 "3-D DDA: latency / issue bound (dependent cell and record fetches, divergent rays), not HBM bound; the stage "
+                                 "also holds the ray-spawn kernel (~10 us)")}
         for l in range(len(scene.lights)):
-            kern[f"light{l}_shadow"] = ("k_shadow", None, None)
-        kern["shade"] = ("k_shade", (8 + 4 * 1) * N + 3 * N, None)
-        dom = max((k for k in kern if k in stage), key=lambda k: stage[k])
-        name, alg_bytes, tests = kern[dom]
-        if alg_bytes is None:   # shadow traversal: report the primary-traversal kernel instead (same inner loop, exact counts)
-            dom, (name, alg_bytes, tests) = "trace", kern["trace"]
-        t_s = stage[dom] * 1e-3
-        achieved = alg_bytes / t_s / 1e9
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(name)
-        except Exception:
-            pass
-        roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": traffic, "peak_source": peak_kind, "algorithmic_bytes_per_launch": alg_bytes,
-                    "kernel_ms": stage[dom], "note": "ray traversal is FP32-issue bound, not HBM bound: see fp32_issue"}
-        if tests:
-            issue_peak = 148 * 128 * sm_max * 1e6 / 1e12   # T lane-ops/s at the max SM clock
-            ach = tests * FP32_ISSUE_PER_TEST / t_s / 1e12
-            roofline["fp32_issue"] = {"achieved": ach, "peak": issue_peak, "unit": "T lane-ops/s", "frac": ach / issue_peak,
-                                      "ray_triangle_tests_per_launch": tests, "fp32_instr_per_test": FP32_ISSUE_PER_TEST}
+            kern[f"light{l}_shadow"] = ("k_shadow", None, None, "")
+
+        def roof(stage_name):
+            name, alg_bytes, tests, note = kern[stage_name]
+            t_s = stage[stage_name] * 1e-3
+            achieved = alg_bytes / t_s / 1e9
+            traffic, issue = None, None
+            try:
+                with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                    prof = json.load(f)
+                traffic, issue = prof.get(name), prof.get("issue_active_pct", {}).get(name)
+            except Exception:
+                pass
+            out = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                   "traffic": traffic, "peak_source": peak_kind, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": stage[stage_name], "note": note}
+            if issue is not None:   # from the committed ncu capture of the same command (profiles/), not measured live
+                out["sm_issue_active_pct_ncu"] = issue
+            if tests:
+                issue_peak = 148 * 128 * sm_max * 1e6 / 1e12   # T lane-ops/s at the max SM clock
+                ach = tests * FP32_ISSUE_PER_TEST / t_s / 1e12
+                out["fp32_issue"] = {"achieved": ach, "peak": issue_peak, "unit": "T lane-ops/s", "frac": ach / issue_peak,
+                                     "ray_triangle_tests_per_launch": tests, "fp32_instr_per_test": FP32_ISSUE_PER_TEST}
+            return out
+
+        dom = max((k for k in kern if k in stage and stage[k] > 0), key=lambda k: stage[k])
+        if kern[dom][1] is None:   # shadow traversal: report the primary-traversal kernel instead (same inner loop, exact counts)
+            dom = "trace"
+        roofline = roof(dom)
+        roofline_all = {kern[k][0]: roof(k) for k in kern if k in stage and stage[k] > 0 and kern[k][1] is not None}
         frame_bytes = 0
         for nm, Pg, Cg in [("cam", P, Cc)] + [(f"l{l}", st2.light_pairs[l], (scene.width // 8) * (scene.height // 8)) for l in range(len(scene.lights))]:
             frame_bytes += 48 * T + 4 * Pg + 8 * Cg
@@ -351,7 +379,7 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
-                cpu = cpu_reference(scene, 3, 1)
+                cpu = cpu_reference(scene, 3, 1, budget_s=10.0)
                 cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
             except Exception as e:  # the checker is optional for the bench line
                 cpu = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
@@ -376,7 +404,7 @@ def run_ours(args):
             "stage_ms": {k: round(v, 4) for k, v in stage.items()},
             "frame_algorithmic_bytes": frame_bytes,
             "frame_hbm_frac": frame_bytes / (total_ms / args.steps * 1e-3) / 1e9 / hbm_peak,
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": roofline, "roofline_kernels": roofline_all, "cpu_baseline": cpu, "clocks": clocks,
         }
         if strips:
             strips["value"] = (scene.rays_per_frame() + int(refl.item()) / frames_per_step) / (strips["ms_per_frame"] * 1e-3) / 1e6

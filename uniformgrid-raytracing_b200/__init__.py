@@ -250,6 +250,7 @@ class Renderer:
         return p
 
     def render(self, p: FrameParams):
+        self._last_lights = int(p.num_lights)
         self._ck(self.L.ug_render_frame(self.ctx, C.byref(p)), "ug_render_frame")
 
     def render_host(self, p: FrameParams, out: np.ndarray):
@@ -280,10 +281,9 @@ class Renderer:
         buf = (C.c_float * 40)()
         n = self.L.ug_stage_times(self.ctx, buf, 40)
         names = ["transform", "cam_grid", "trace"]
-        for l in range((max(n, 0) - 4 - (1 if (max(n, 0) - 4) % 3 else 0)) // 3):
+        for l in range(getattr(self, "_last_lights", 0)):
             names += [f"light{l}_grid", f"light{l}_regroup", f"light{l}_shadow"]
-        names.append("shade")
-        names.append("reflect")
+        names += ["shade", "reflect_grid", "reflect_rays", "reflect_combine"]
         return {names[k]: buf[k] for k in range(min(max(n, 0), len(names)))}
 
     def read(self, buffer: int, index: int = 0) -> np.ndarray:

@@ -743,11 +743,13 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 		if (parallel) UG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_refl, 0));
 		else {
 			ugk_reflect_grid(s, ctx, &L.n);
+			stage_mark(ctx, k, stage_events); /* uniform grid */
 			ugk_reflect_rays(s, ctx, p->bounces, &L.n);
+			stage_mark(ctx, k, stage_events); /* reflection rays: spawn + one DDA kernel per bounce */
 		}
 		ugk_reflect_combine(s, ctx, &L.n);
 		ugk_stamp(s, tl, 4);
-		stage_mark(ctx, k, stage_events);
+		stage_mark(ctx, k, stage_events); /* combine */
 		ctx->last_bounces = p->bounces;
 	} else {
 		ctx->last_bounces = 0;
