@@ -21,12 +21,14 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_path):
+def _worker(rank, world, port, out_path, no_push):
     import torch
     import torch.distributed as dist
     import ugrt  # noqa: F401
     import uniformgrid_raytracing_b200 as ug
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    if no_push:
+        os.environ["UG_NO_PUSH"] = "1"          # the ncclSend/ncclRecv fallback instead of the IPC push over NVLink
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", rank=rank, world_size=world)   # only carries the 128-byte NCCL id
     scene = scenes.scene_a(256, 264)                                # 33 cell rows: uneven strips
@@ -54,7 +56,8 @@ def _worker(rank, world, port, out_path):
     dist.destroy_process_group()
 
 
-def test_strip_gather_over_nccl(oracle, tmp_path):
+@pytest.mark.parametrize("no_push", [False, True])
+def test_strip_gather_over_nccl(oracle, tmp_path, no_push):
     import torch
     import torch.multiprocessing as mp
     world = min(torch.cuda.device_count(), 4)
@@ -63,7 +66,7 @@ def test_strip_gather_over_nccl(oracle, tmp_path):
     scene = scenes.scene_a(256, 264)
     want = harness.run_frame(oracle, scene, threads=0)["rgb"]
     out = str(tmp_path / "full.npy")
-    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), out, no_push), nprocs=world, join=True)
     assert np.array_equal(np.load(out), want)
     dyn = scenes.scene_c(240, 136)
     got = np.load(out + ".frames.npy").reshape(world, -1)

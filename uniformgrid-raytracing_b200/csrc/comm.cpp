@@ -1,17 +1,28 @@
-/* comm.cpp -- NCCL plumbing for the image-strip sharding: one communicator per context, the strips
- * are gathered to rank 0 INSIDE the frame (captured in the frame's CUDA graph), straight from the buffer the shade
- * kernel wrote.  NCCL has no gather primitive: rank 0 posts one ncclRecv per peer, every other rank one ncclSend,
- * inside a group.  libnccl is opened lazily with dlopen, so the library loads (and the single-GPU path runs) on
- * machines without NCCL; in a torch process this resolves to the NCCL torch already loaded.
+/* comm.cpp -- the one exchange step of the multi-GPU path: strips (or whole frames) are gathered to
+ * rank 0 INSIDE the frame (captured in the frame's CUDA graph), straight from the buffer the shade kernel wrote.
+ *
+ * Two transports, chosen collectively when the destination buffer is (re)allocated:
+ *   push   rank 0 exports its gather buffer with a CUDA IPC handle (broadcast over NCCL); every other rank maps it and
+ *          its copy engine writes the strip into place over NVLink (one peer memcpy node in the graph).  Two 4-byte
+ *          ncclAllReduce's bracket the copies: "ready" (rank 0's stream has finished reading the previous frame out of
+ *          the buffer) and "done" (every rank's copy precedes its contribution, so when rank 0's completes the image
+ *          is whole).  Measured 8 x 3 MB into rank 0: see DESIGN.md section 6.
+ *   nccl   fallback when IPC mapping is refused: rank 0 posts one ncclRecv per peer, every other rank one ncclSend,
+ *          inside a group (NCCL has no gather primitive); ~160 GB/s into rank 0, which is what made the push path
+ *          worth writing.
+ * libnccl is opened lazily with dlopen, so the library loads (and the single-GPU path runs) on machines without
+ * NCCL; in a torch process this resolves to the NCCL torch already loaded.
  */
 #include "ugrt_internal.h"
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
 
 typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclInt8 = 0, ncclUint8 = 1 };
+enum { ncclInt8 = 0, ncclUint8 = 1, ncclInt32 = 2, ncclUint32 = 3 };
+enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 };
 
 static struct {
 	void *handle;
@@ -21,6 +32,8 @@ static struct {
 	ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t);
 	ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t);
 	ncclResult_t (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t);
+	ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
+	ncclResult_t (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
 	ncclResult_t (*GroupStart)(void);
 	ncclResult_t (*GroupEnd)(void);
 	const char *(*GetErrorString)(ncclResult_t);
@@ -35,7 +48,7 @@ static bool load_nccl(ug_context *ctx)
 #define SYM(field, name) *(void **)(&N.field) = dlsym(h, name); if (!N.field) { ug_fail(ctx, UG_ERR_CUDA, "libnccl lacks %s", name); return false; }
 	SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy") SYM(Send, "ncclSend")
 	SYM(Recv, "ncclRecv") SYM(AllGather, "ncclAllGather") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd")
-	SYM(GetErrorString, "ncclGetErrorString")
+	SYM(GetErrorString, "ncclGetErrorString") SYM(AllReduce, "ncclAllReduce") SYM(Broadcast, "ncclBroadcast")
 #undef SYM
 	N.handle = h;
 	return true;
@@ -46,6 +59,12 @@ static bool load_nccl(ug_context *ctx)
 		ncclResult_t r_ = (call);                                                                            \
 		if (r_ != 0) return ug_fail(ctx, UG_ERR_CUDA, "%s: %s", #call, N.GetErrorString(r_));                \
 	} while (0)
+
+static void unmap_peer(ug_context *ctx)
+{
+	if (ctx->peer_full) cudaIpcCloseMemHandle(ctx->peer_full);
+	ctx->peer_full = nullptr;
+}
 
 extern "C" int ug_comm_unique_id(void *out128)
 {
@@ -70,21 +89,95 @@ extern "C" int ug_comm_init(ug_context *ctx, int rank, int world, const void *un
 	ctx->comm = comm;
 	ctx->comm_rank = rank;
 	ctx->comm_world = world;
+	unmap_peer(ctx);
+	ctx->use_push = false;
+	ctx->rgb_full_bytes = 0; /* the gather buffer is shared again (collectively) by the next frame */
 	if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
 	return UG_OK;
 }
 
 void ugc_destroy(ug_context *ctx)
 {
+	unmap_peer(ctx);
+	if (ctx->d_comm_scratch) cudaFree(ctx->d_comm_scratch);
+	ctx->d_comm_scratch = nullptr;
 	if (ctx->comm && N.handle) N.CommDestroy((ncclComm_t)ctx->comm);
 	ctx->comm = nullptr;
 }
 
-/* strips -> rank 0's full image.  bytes[r] / offs[r] describe every rank's strip inside the full image. */
+/* Collective: (re)allocate rank 0's gather buffer and decide the transport.  Every rank of the communicator calls this
+ * from the same frame call (the size depends on screen and world size only). */
+int ugc_share_full(ug_context *ctx, size_t bytes)
+{
+	ncclComm_t comm = (ncclComm_t)ctx->comm;
+	cudaStream_t s = ctx->stream;
+	const int rank = ctx->comm_rank;
+	if (!ctx->d_comm_scratch) {
+		UG_CUDA(ctx, cudaMalloc((void **)&ctx->d_comm_scratch, 256));
+		UG_CUDA(ctx, cudaMemset(ctx->d_comm_scratch, 0, 256));
+	}
+	unsigned char *scr = (unsigned char *)ctx->d_comm_scratch; /* [0,64) IPC handle, [64,68) ok flags, [128,132) barrier word */
+	/* 1. nobody keeps the old buffer mapped when rank 0 frees it */
+	UG_CUDA(ctx, cudaStreamSynchronize(s));
+	unmap_peer(ctx);
+	ctx->use_push = false;
+	UG_NCCL(ctx, N.AllReduce(scr + 128, scr + 128, 1, ncclUint32, ncclSum, comm, s));
+	UG_CUDA(ctx, cudaStreamSynchronize(s));
+	/* 2. rank 0 allocates and exports */
+	cudaIpcMemHandle_t h;
+	memset(&h, 0, sizeof(h));
+	unsigned int ok = 1;
+	if (rank == 0) {
+		if (ctx->d_rgb_full) cudaFree(ctx->d_rgb_full);
+		ctx->d_rgb_full = nullptr;
+		UG_CUDA(ctx, cudaMalloc((void **)&ctx->d_rgb_full, bytes));
+		if (getenv("UG_NO_PUSH") || cudaIpcGetMemHandle(&h, ctx->d_rgb_full) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+		UG_CUDA(ctx, cudaMemcpyAsync(scr, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+	}
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle travels in 64 bytes");
+	UG_NCCL(ctx, N.Broadcast(scr, scr, 64, ncclUint8, 0, comm, s));
+	/* 3. the others map it */
+	if (rank != 0) {
+		UG_CUDA(ctx, cudaMemcpyAsync(&h, scr, sizeof(h), cudaMemcpyDeviceToHost, s));
+		UG_CUDA(ctx, cudaStreamSynchronize(s));
+		void *p = nullptr;
+		if (getenv("UG_NO_PUSH") || cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); p = nullptr; }
+		ctx->peer_full = (unsigned char *)p;
+	}
+	/* 4. push only if it works everywhere */
+	UG_CUDA(ctx, cudaMemcpyAsync(scr + 64, &ok, 4, cudaMemcpyHostToDevice, s));
+	UG_NCCL(ctx, N.AllReduce(scr + 64, scr + 64, 1, ncclUint32, ncclMin, comm, s));
+	UG_CUDA(ctx, cudaMemcpyAsync(&ok, scr + 64, 4, cudaMemcpyDeviceToHost, s));
+	UG_CUDA(ctx, cudaStreamSynchronize(s));
+	ctx->use_push = ok != 0;
+	if (!ctx->use_push) unmap_peer(ctx);
+	ctx->rgb_full_bytes = bytes;
+	return UG_OK;
+}
+
+/* push transport: "rank 0 is past its read-out of the previous frame".  Issued at the head of the frame on a side
+ * branch, so its latency hides behind the frame's own kernels. */
+int ugc_ready(ug_context *ctx, cudaStream_t s)
+{
+	if (!ctx->use_push) return UG_OK;
+	unsigned char *scr = (unsigned char *)ctx->d_comm_scratch;
+	UG_NCCL(ctx, N.AllReduce(scr + 128, scr + 128, 1, ncclUint32, ncclSum, (ncclComm_t)ctx->comm, s));
+	return UG_OK;
+}
+
+/* strips -> rank 0's full image.  bytes[r] / offs[r] describe every rank's strip inside the full image.  The caller has
+ * ordered ugc_ready() before this on the same stream (directly or through an event). */
 int ugc_gather_strips(ug_context *ctx, cudaStream_t s, const unsigned char *strip, unsigned char *full, const size_t *bytes, const size_t *offs)
 {
 	ncclComm_t comm = (ncclComm_t)ctx->comm;
 	const int rank = ctx->comm_rank, world = ctx->comm_world;
+	if (ctx->use_push) {
+		unsigned char *scr = (unsigned char *)ctx->d_comm_scratch;
+		if (rank == 0) UG_CUDA(ctx, cudaMemcpyAsync(full + offs[0], strip, bytes[0], cudaMemcpyDeviceToDevice, s));
+		else UG_CUDA(ctx, cudaMemcpyAsync(ctx->peer_full + offs[rank], strip, bytes[rank], cudaMemcpyDefault, s)); /* copy engine, over NVLink */
+		UG_NCCL(ctx, N.AllReduce(scr + 132, scr + 132, 1, ncclUint32, ncclSum, comm, s)); /* done: every copy precedes its rank's contribution */
+		return UG_OK;
+	}
 	if (rank == 0) UG_CUDA(ctx, cudaMemcpyAsync(full + offs[0], strip, bytes[0], cudaMemcpyDeviceToDevice, s));
 	UG_NCCL(ctx, N.GroupStart());
 	if (rank == 0) {

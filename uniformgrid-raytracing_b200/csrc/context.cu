@@ -89,6 +89,8 @@ extern "C" int ug_create(ug_context **out, int device)
 	 * its blocks queue behind the big kernels of the other branches (measured: 290 us instead of ~120) */
 	UG_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_ugrid, cudaStreamNonBlocking, getenv("UG_NO_PRIO") ? prio_least : prio_greatest));
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ugrid, cudaEventDisableTiming));
+	UG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_comm, cudaStreamNonBlocking));
+	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_refl, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_trace, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaEventCreate(&ctx->ev_t0));
@@ -154,7 +156,7 @@ extern "C" void ug_destroy(ug_context *ctx)
 	}
 	dfree(ctx->d_fc);
 	for (int i = 0; i < UG_MAX_LIGHTS; i++) { cudaStreamDestroy(ctx->side[i]); cudaEventDestroy(ctx->ev_join[i]); }
-	cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_fork2); cudaEventDestroy(ctx->ev_init); cudaStreamDestroy(ctx->side_init); cudaStreamDestroy(ctx->side_refl); cudaStreamDestroy(ctx->side_ugrid); cudaEventDestroy(ctx->ev_ugrid); cudaEventDestroy(ctx->ev_refl); cudaEventDestroy(ctx->ev_trace); cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
+	cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_fork2); cudaEventDestroy(ctx->ev_init); cudaStreamDestroy(ctx->side_init); cudaStreamDestroy(ctx->side_refl); cudaStreamDestroy(ctx->side_ugrid); cudaEventDestroy(ctx->ev_ugrid); cudaStreamDestroy(ctx->side_comm); cudaEventDestroy(ctx->ev_ready); cudaEventDestroy(ctx->ev_refl); cudaEventDestroy(ctx->ev_trace); cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
 	for (auto &ev : ctx->ev_stage) cudaEventDestroy(ev);
 	cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
@@ -367,9 +369,10 @@ static int ensure_buffers(ug_context *ctx, int num_lights, bool full, int bounce
 		if (rc) return rc;
 		changed = true;
 	}
-	if (ctx->comm && ctx->comm_world > 1 && ctx->comm_rank == 0 && ctx->rgb_full_bytes != 3 * (size_t)ctx->W * ctx->H * (size_t)ctx->comm_world) {
-		ctx->rgb_full_bytes = 3 * (size_t)ctx->W * ctx->H * (size_t)ctx->comm_world; /* one gathered frame (strips) or one frame per rank (UG_FLAG_GATHER_FRAMES) */
-		UG_CUDA(ctx, dmalloc(&ctx->d_rgb_full, ctx->rgb_full_bytes));
+	if (ctx->comm && ctx->comm_world > 1 && ctx->rgb_full_bytes != 3 * (size_t)ctx->W * ctx->H * (size_t)ctx->comm_world) {
+		/* one gathered frame (strips) or one frame per rank (UG_FLAG_GATHER_FRAMES); collective: every rank gets here in the same call */
+		int rc = ugc_share_full(ctx, 3 * (size_t)ctx->W * ctx->H * (size_t)ctx->comm_world);
+		if (rc) return rc;
 		changed = true;
 	}
 	if (full && !ctx->full_alloc) {
@@ -677,8 +680,16 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 			if (l == 0) ugk_stamp(ctx->side[l], tl, 11);
 		}
 	}
+	const bool gather_strips = ctx->comm && ctx->comm_world > 1 && ctx->strip_count == ctx->comm_world && ctx->strip_index == ctx->comm_rank;
+	const bool gather_frames = !gather_strips && ctx->comm && ctx->comm_world > 1 && (p->flags & UG_FLAG_GATHER_FRAMES) && ctx->strip_count == 1;
 	if (parallel) { /* the per-pixel reset + ray directions do not depend on the grid: their own branch of the graph */
 		UG_CUDA(ctx, cudaEventRecord(ctx->ev_fork2, s));
+		if ((gather_strips || gather_frames) && ctx->use_push) { /* the gather's "ready" handshake hides behind the whole frame */
+			UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_comm, ctx->ev_fork2, 0));
+			int rc = ugc_ready(ctx, ctx->side_comm);
+			if (rc) return rc;
+			UG_CUDA(ctx, cudaEventRecord(ctx->ev_ready, ctx->side_comm));
+		}
 		if (reflect) { /* so does the world-space uniform grid of row R */
 			UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_ugrid, ctx->ev_fork2, 0));
 			ugk_stamp(ctx->side_ugrid, tl, 20);
@@ -754,7 +765,11 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 	} else {
 		ctx->last_bounces = 0;
 	}
-	if (ctx->comm && ctx->comm_world > 1 && ctx->strip_count == ctx->comm_world && ctx->strip_index == ctx->comm_rank) {
+	if ((gather_strips || gather_frames) && ctx->use_push) {
+		if (parallel) UG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_ready, 0));
+		else { int rc = ugc_ready(ctx, s); if (rc) return rc; }
+	}
+	if (gather_strips) {
 		/* the one exchange step: RGB8 strips -> rank 0 over NVLink, inside the frame */
 		size_t bytes[64], offs[64], acc = 0;
 		for (int r = 0; r < ctx->comm_world && r < 64; r++) {
@@ -766,7 +781,7 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 		int rc = ugc_gather_strips(ctx, s, ctx->d_rgb, ctx->d_rgb_full, bytes, offs);
 		if (rc) return rc;
 		L.n += 1;
-	} else if (ctx->comm && ctx->comm_world > 1 && (p->flags & UG_FLAG_GATHER_FRAMES) && ctx->strip_count == 1) {
+	} else if (gather_frames) {
 		/* frame-parallel rendering: every rank has rendered a whole frame of its own; frame r lands in slot r on rank 0 */
 		size_t bytes[64], offs[64];
 		for (int r = 0; r < ctx->comm_world && r < 64; r++) { bytes[r] = 3 * (size_t)ctx->N; offs[r] = (size_t)r * bytes[r]; }
@@ -851,6 +866,7 @@ static unsigned long long frame_key(const ug_context *ctx, const ug_frame_params
 	for (int l = 0; l < p->num_lights; l++) mix((unsigned long long)ctx->light_grid[l].cap);
 	mix((unsigned long long)(p->bounces > 0 && ctx->d_reflect ? p->bounces : 0)); mix((unsigned long long)ctx->refl.grid.cap);
 	mix((unsigned long long)(uintptr_t)ctx->comm); mix((unsigned long long)(uintptr_t)ctx->d_rgb_full);
+	mix((unsigned long long)(uintptr_t)ctx->peer_full); mix((unsigned long long)ctx->use_push);
 	mix((unsigned long long)(uintptr_t)ctx->stream); mix((unsigned long long)(uintptr_t)ctx->d_rgb);
 	return k;
 }

@@ -100,7 +100,8 @@ struct ug_context {
 	int device = 0;
 	cudaStream_t own_stream = nullptr, stream = nullptr;
 	cudaStream_t side[UG_MAX_LIGHTS] = {};
-	cudaStream_t side_init = nullptr, side_refl = nullptr, side_ugrid = nullptr;
+	cudaStream_t side_init = nullptr, side_refl = nullptr, side_ugrid = nullptr, side_comm = nullptr;
+	cudaEvent_t ev_ready = nullptr;
 	cudaEvent_t ev_ugrid = nullptr;
 	unsigned long long *d_stamps = nullptr; /* [64] UG_TIMELINE markers, null when off */
 	bool use_fused_ugrid = false, force_fused_grid = false, fused_grid_now = true, fused_cam_now = true;
@@ -168,6 +169,9 @@ struct ug_context {
 	int comm_rank = 0, comm_world = 1;
 	unsigned char *d_rgb_full = nullptr; /* rank 0: the gathered frame, 3*W*H */
 	size_t rgb_full_bytes = 0;
+	unsigned char *peer_full = nullptr;  /* ranks > 0: rank 0's gather buffer mapped through CUDA IPC */
+	void *d_comm_scratch = nullptr;      /* 256 B: IPC handle, flags, barrier words */
+	bool use_push = false;
 
 	/* CUDA graph of the frame */
 	cudaGraphExec_t graph_exec = nullptr;
@@ -237,6 +241,8 @@ void ugk_reflect_combine(cudaStream_t s, ug_context *ctx, int *launches);
 
 /* comm.cpp */
 void ugc_destroy(ug_context *ctx);
+int ugc_share_full(ug_context *ctx, size_t bytes);
+int ugc_ready(ug_context *ctx, cudaStream_t s);
 int ugc_gather_strips(ug_context *ctx, cudaStream_t s, const unsigned char *strip, unsigned char *full, const size_t *bytes, const size_t *offs);
 
 /* host helpers (camera_host.cpp, obj_loader.cpp) */
