@@ -92,6 +92,13 @@ typedef struct ug_frame_params {
 #define UG_FLAG_NO_GRAPH 2     /* launch kernels directly instead of replaying the captured CUDA graph */
 #define UG_FLAG_GATHER_FRAMES 8 /* with ug_comm_init and no strips: every rank renders its own frame, rank 0 collects them (slot r = rank r) */
 #define UG_FLAG_STAGE_EVENTS 4 /* record one CUDA event per stage (implies NO_GRAPH); see ug_stats.ms_* */
+#define UG_FLAG_SPHERICAL_LIGHTS 16 /* light grids and shadow-ray binning by the spherical map the committed display() uses
+                                       (main.cu:189-192 getEffectiveRayGridMapping + buildSphericalGrid with x_max = y_max = M_PI)
+                                       instead of the perspective one north-star names (misc_kernel.cu:63-129) */
+
+/* how a light's grid is parameterised (ug_set_light_grid_mode, UG_FLAG_SPHERICAL_LIGHTS) */
+#define UG_LIGHT_GRID_PERSPECTIVE 0 /* mapSortkernel misc_kernel.cu:63-129 + DSKernel/DSFillkernel grid_kernel.cu:164-332 */
+#define UG_LIGHT_GRID_SPHERICAL 1   /* mapSort_Effective_kernel misc_kernel.cu:255-296 + DS_spherical_Kernel/Fillkernel grid_kernel.cu:481-854 */
 
 /* buffers that can be read back for parity checks / interop (ug_read, ug_device_ptr) */
 enum ug_buffer {
@@ -134,6 +141,9 @@ int ug_create(ug_context **out, int device);
 void ug_destroy(ug_context *ctx);
 const char *ug_last_error(const ug_context *ctx);
 const char *ug_version(void);
+/* host evaluation of the acosf the kernels use for the spherical light grid (a restatement of glibc 2.39's, which is what
+ * the host-compiled reference calls): lets a CPU test pin it against libm without a GPU */
+void ug_acosf_host(const float *x, float *y, size_t n);
 size_t ug_frame_const_bytes(void); /* bytes of per-frame constants ug_render_frame* uploads (pinned H2D) */
 int ug_set_stream(ug_context *ctx, void *cuda_stream); /* NULL: the context's own non-blocking stream */
 int ug_synchronize(ug_context *ctx);
@@ -176,6 +186,9 @@ int ug_shadow_pass(ug_context *ctx, int light_id, const ug_camera *light_cam);  
                                                                                      + getRayGridMapping (:72, perspective variant
                                                                                      misc_kernel.cu:63-129) + build_secondary_frustum_grid
                                                                                      (:57) + processData (:116) + check_for_shadows (:139) */
+/* which binning ug_shadow_pass uses from now on: per_frame_funcs.h:97-114 getEffectiveRayGridMapping(xM, yM) and :57-70
+ * build_secondary_frustum_grid(xM, yM) -> FrustumGrid::buildSphericalGrid (frustum_grid.h:368-532) when spherical */
+int ug_set_light_grid_mode(ug_context *ctx, int mode, float xM, float yM);
 int ug_simple_shade(ug_context *ctx);                                             /* shader.h:70-86 */
 int ug_add_shadows(ug_context *ctx);                                              /* shader.h:58-68 */
 

@@ -53,6 +53,9 @@ class CpuLib:
             "transform": (None, [_f, _f, C.c_int, C.c_int, C.c_float]),
             "grid_count": (None, [_i, _f, C.c_int, _u, _f]),
             "build_grid": (C.c_long, [_i, _f, C.c_int, _u, _u, _u, _u, C.c_long]),
+            "grid_count_spherical": (None, [_i, _f, C.c_int, _u, _f, C.c_float, C.c_float]),
+            "build_grid_spherical": (C.c_long, [_i, _f, C.c_int, _u, _u, _u, _u, C.c_long, C.c_float, C.c_float]),
+            "map_rays_spherical": (None, [_f, _f, _u, _f, C.c_float, C.c_float]),
             "trace": (None, [_u, _u, _u, _f, _f, _f, _i, _i, _f, _i]),
             "map_rays": (None, [_f, _f, _u, _f, C.c_float]),
             "shadow": (None, [_u, _f, _i, _u, _u, _f, _f, _i, _u, _f]),
@@ -106,25 +109,31 @@ class CpuLib:
     def transform(self, verts: np.ndarray, orig: np.ndarray, size: int, offset: int, rot: float):
         self._transform(self._p(verts, _f), self._p(orig, _f), size, offset, rot)
 
-    def grid_count(self, faces, verts):
+    def grid_count(self, faces, verts, spherical=None):
         T = faces.shape[0]
         size = np.zeros(T, dtype=np.uint32)
         z = np.zeros(T, dtype=np.float32)
-        self._grid_count(self._p(faces, _i), self._p(verts, _f), T, self._p(size, _u), self._p(z, _f))
+        if spherical is None:
+            self._grid_count(self._p(faces, _i), self._p(verts, _f), T, self._p(size, _u), self._p(z, _f))
+        else:
+            self._grid_count_spherical(self._p(faces, _i), self._p(verts, _f), T, self._p(size, _u), self._p(z, _f),
+                                       float(spherical[0]), float(spherical[1]))
         return size, z
 
-    def build_grid(self, faces, verts) -> Dict[str, np.ndarray]:
+    def build_grid(self, faces, verts, spherical=None) -> Dict[str, np.ndarray]:
+        """`spherical` = (xM, yM) selects buildSphericalGrid (frustum_grid.h:368-532) instead of buildGrid (:210-366)."""
         T = faces.shape[0]
         Cn = self.nbx * self.nby
         span = np.zeros(Cn, dtype=np.uint32)
         offset = np.zeros(Cn, dtype=np.uint32)
         dummy = np.zeros(1, dtype=np.uint32)
-        P = self._build_grid(self._p(faces, _i), self._p(verts, _f), T, self._p(span, _u), self._p(offset, _u),
-                             self._p(dummy, _u), self._p(dummy, _u), 0)
+        fn, extra = (self._build_grid, ()) if spherical is None else (self._build_grid_spherical, tuple(float(x) for x in spherical))
+        P = fn(self._p(faces, _i), self._p(verts, _f), T, self._p(span, _u), self._p(offset, _u),
+               self._p(dummy, _u), self._p(dummy, _u), 0, *extra)
         keys = np.zeros(max(P, 1), dtype=np.uint32)
         vals = np.zeros(max(P, 1), dtype=np.uint32)
-        P2 = self._build_grid(self._p(faces, _i), self._p(verts, _f), T, self._p(span, _u), self._p(offset, _u),
-                              self._p(keys, _u), self._p(vals, _u), P)
+        P2 = fn(self._p(faces, _i), self._p(verts, _f), T, self._p(span, _u), self._p(offset, _u),
+                self._p(keys, _u), self._p(vals, _u), P, *extra)
         assert P2 == P
         return {"P": int(P), "keys": keys[:P], "values": vals[:P], "span": span, "offset": offset}
 
@@ -138,11 +147,15 @@ class CpuLib:
                     self._p(verts, _f), self._p(faces, _i))
         return out
 
-    def map_rays(self, t, d, cam_pos, near) -> np.ndarray:
+    def map_rays(self, t, d, cam_pos, near, spherical=None) -> np.ndarray:
+        """`spherical` = (xM, yM) selects mapSort_Effective_kernel (misc_kernel.cu:255-296) instead of mapSortkernel (:63-129)."""
         N = self.W * self.H
         m = np.zeros(2 * N, dtype=np.uint32)
         cam_pos = np.ascontiguousarray(cam_pos, dtype=np.float32)
-        self._map_rays(self._p(t, _f), self._p(d, _f), self._p(m, _u), self._p(cam_pos, _f), near)
+        if spherical is None:
+            self._map_rays(self._p(t, _f), self._p(d, _f), self._p(m, _u), self._p(cam_pos, _f), near)
+        else:
+            self._map_rays_spherical(self._p(t, _f), self._p(d, _f), self._p(m, _u), self._p(cam_pos, _f), float(spherical[0]), float(spherical[1]))
         return m
 
     def shadow(self, grid, faces, verts, t, d, shadowed, m, cam_pos):
@@ -221,10 +234,13 @@ def reflect_table(scene) -> np.ndarray:
 
 
 def run_frame(lib: CpuLib, scene, frame: int = 0, threads: int = 0, stages: str = "all",
-              timings: Optional[dict] = None, reflect: bool = False) -> Dict[str, np.ndarray]:
+              timings: Optional[dict] = None, reflect: bool = False, spherical: bool = False) -> Dict[str, np.ndarray]:
     """One display() (main.cu:59-302) on the CPU: [transform ->] camera grid -> primary rays -> per
     light (light camera, ray->cell map, light grid, shadow rays) -> shade -> shadow modulation.
-    Returns every stage's output for bit-exact comparison."""
+    Returns every stage's output for bit-exact comparison.  `spherical` runs the per-light steps the way the committed
+    display() does (main.cu:186-192: spherical ray map + spherical grid with x_max = y_max = M_PI) instead of the
+    perspective variant north-star names."""
+    sph = (np.float32(np.pi), np.float32(np.pi)) if spherical else None
     lib.configure(scene.width, scene.height, scene.fovy, 0)
     lib.set_threads(threads)
     faces = np.ascontiguousarray(scene.faces, dtype=np.int32)
@@ -269,10 +285,10 @@ def run_frame(lib: CpuLib, scene, frame: int = 0, threads: int = 0, stages: str 
         cc = lib.camera_setup(light.pos, light.look, light.up, scene.near, scene.far, square=True)
         out[f"light{li}_camcoords"] = cc
         t0 = time.perf_counter()
-        m = lib.map_rays(prim["t"], prim["dir"], cam_pos, scene.near)
+        m = lib.map_rays(prim["t"], prim["dir"], cam_pos, scene.near, spherical=sph)
         tick("map", t0)
         t0 = time.perf_counter()
-        lgrid = lib.build_grid(faces, verts)
+        lgrid = lib.build_grid(faces, verts, spherical=sph)
         tick("grid", t0)
         t0 = time.perf_counter()
         lib.shadow(lgrid, faces, verts, prim["t"], prim["dir"], shadowed, m, cam_pos)

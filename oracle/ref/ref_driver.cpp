@@ -264,6 +264,56 @@ long ref_build_grid(int *faces, float *verts, int T, unsigned *span, unsigned *o
 	return P;
 }
 
+/* frustum_grid.h:377: DS_spherical_Kernel */
+void ref_grid_count_spherical(int *faces, float *verts, int T, unsigned *sizeList, float *projZ, float xM, float yM)
+{
+	int mp[1] = {T};
+	launch(T / NUMTHREADSDS + 1, 1, NUMTHREADSDS, 1, [&] { DS_spherical_Kernel(sizeList, projZ, faces, verts, mp, xM, yM); });
+}
+
+/* frustum_grid.h:368-532 buildSphericalGrid: the sequence of buildGrid around the spherical kernels */
+long ref_build_grid_spherical(int *faces, float *verts, int T, unsigned *span, unsigned *offset, unsigned *key_list, unsigned *value_list, long cap,
+                              float xM, float yM)
+{
+	const int C = NUM_BLOCKS_X * NUM_BLOCKS_Y * NUM_SLABS;
+	int mp[1] = {T};
+	std::vector<unsigned> sizeList(T), scanned(T), zSlabs(T, 0);
+	std::vector<float> projZ(T);
+	const int nb = T / NUMTHREADSDS + 1;
+	launch(nb, 1, NUMTHREADSDS, 1, [&] { DS_spherical_Kernel(sizeList.data(), projZ.data(), faces, verts, mp, xM, yM); });
+	float zMin = 9999.9f, zMax = -9999.9f; /* :385-398 */
+	for (int i = 0; i < T; i++) {
+		if (zMin > projZ[i] && projZ[i] >= 0.0f) zMin = projZ[i];
+		if (zMax < projZ[i]) zMax = projZ[i];
+	}
+	unsigned run = 0; /* :414 cudppScan inclusive */
+	for (int i = 0; i < T; i++) { run += sizeList[i]; scanned[i] = run; }
+	const long P = T ? (long)scanned[T - 1] : 0;
+	if (P > cap) return P;
+	std::vector<unsigned> keys(P), vals(P);
+	launch(nb, 1, NUMTHREADSDS, 1, [&] { SlabKernel(zSlabs.data(), projZ.data(), mp, zMin, zMax); });
+	launch(nb, 1, NUMTHREADSDS, 1, [&] { DS_spherical_Fillkernel(keys.data(), vals.data(), scanned.data(), zSlabs.data(), faces, verts, mp, xM, yM); });
+	std::vector<unsigned> perm(P); /* :464 cudppSort (stable LSD radix) */
+	std::iota(perm.begin(), perm.end(), 0u);
+	std::stable_sort(perm.begin(), perm.end(), [&](unsigned a, unsigned b) { return keys[a] < keys[b]; });
+	for (long i = 0; i < P; i++) { key_list[i] = keys[perm[i]]; value_list[i] = vals[perm[i]]; }
+	std::vector<unsigned> pos(P), head(P), compacted; /* :470-503 do_scan_dump + cudppCompact */
+	launch((int)(P / 256) + 1, 1, 256, 1, [&] { do_scan_dump(key_list, pos.data(), head.data(), (int)P); });
+	for (long i = 0; i < P; i++) if (head[i]) compacted.push_back(pos[i]);
+	const int ncells = (int)compacted.size();
+	launch(C / 256 + 1, 1, 256, 1, [&] { set_as_zero(span); }); /* :506-523 */
+	launch(ncells / 256 + 1, 1, 256, 1, [&] { create_histogram(compacted.data(), ncells, (int)P, key_list, span); });
+	unsigned acc = 0; /* :527 cudppScan exclusive over ALL cells */
+	for (int c = 0; c < C; c++) { offset[c] = acc; acc += span[c]; }
+	return P;
+}
+
+/* misc_kernel.cu:255-296 mapSort_Effective_kernel, verbatim (dd_camcoords must hold the LIGHT camera) */
+void ref_map_rays_spherical(float *t_list, float *dir_list, unsigned *map, float *cmPt, float xM, float yM)
+{
+	launch(NUM_BLOCKS_X, NUM_BLOCKS_Y, NUM_THREADS_X, NUM_THREADS_Y, [&] { mapSort_Effective_kernel(t_list, dir_list, map, cmPt, xM, yM); });
+}
+
 /* trace_kernel.cu:84-270 rckernel_alpha, per pixel.  Buffers as decision_data.h:66-82. */
 void ref_trace(unsigned *value_list, unsigned *span, unsigned *offset, float *dd_normal, float *dd_t, float *dd_dir,
                int *dd_shadowed, int *dd_id, float *verts, int *tris)

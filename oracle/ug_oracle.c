@@ -216,22 +216,93 @@ static void tri_cells(const int *faces, const float *verts, int t, int *gx0, int
 	*gy1 = clampi(f2i(floorf(((ymax + 1.0f) / 2.0f) * g_nby)), 0, g_nby - 1);
 }
 
-void orc_grid_count(int *faces, float *verts, int T, unsigned *sizeList, float *projZ)
+/* ------------------------------------------------------------------ a14/a15: spherical ("effective") light grid
+ * grid_kernel.cu:395-421 getEffective_x: angle between the forward axis and the direction with its up component
+ * removed, binned as NBX/2 +- (int)((angle/max)*(NBX/2)); the unsigned result is read back as int by the callers.
+ * g_cc[16..] = modelview of the light camera: rows right (16,20,24), up (17,21,25), -forward (18,22,26).
+ * acosf / sqrtf are libm's here, as in the host-compiled reference. */
+static int effective_x(const float *vec, float maxa)
+{
+	const float *cc = g_cc;
+	float upDot = vec[0] * cc[16 + 1] + vec[1] * cc[16 + 5] + vec[2] * cc[16 + 9];
+	float tmp[3] = {vec[0] - upDot * cc[16 + 1], vec[1] - upDot * cc[16 + 5], vec[2] - upDot * cc[16 + 9]};
+	float val = sqrtf(tmp[0] * tmp[0] + tmp[1] * tmp[1] + tmp[2] * tmp[2]); /* getMagnitude :355-363 */
+	tmp[0] /= val; tmp[1] /= val; tmp[2] /= val;
+	float fwd = tmp[0] * cc[16 + 2] + tmp[1] * cc[16 + 6] + tmp[2] * cc[16 + 10];
+	float angle = acosf(fwd);
+	float rightDot = tmp[0] * cc[16 + 0] + tmp[1] * cc[16 + 4] + tmp[2] * cc[16 + 8];
+	unsigned half = (unsigned)(g_nbx / 2), k = (unsigned)f2i((angle / maxa) * (g_nbx / 2)); /* wraps like the int sum does on x86 */
+	return (int)(rightDot > 0 ? half + k : half - k);
+}
+/* grid_kernel.cu:452-479 getEffective_y: same with right removed - but the forward dot product is written
+ * `a + b*c*d` (:468) and the bin is computed in float and converted float -> unsigned (:475-478). */
+static int effective_y(const float *vec, float maxa)
+{
+	const float *cc = g_cc;
+	float rightDot = vec[0] * cc[16 + 0] + vec[1] * cc[16 + 4] + vec[2] * cc[16 + 8];
+	float tmp[3] = {vec[0] - rightDot * cc[16 + 0], vec[1] - rightDot * cc[16 + 4], vec[2] - rightDot * cc[16 + 8]};
+	float val = sqrtf(tmp[0] * tmp[0] + tmp[1] * tmp[1] + tmp[2] * tmp[2]);
+	tmp[0] /= val; tmp[1] /= val; tmp[2] /= val;
+	float upDot = tmp[0] * cc[16 + 1] + tmp[1] * cc[16 + 5] + tmp[2] * cc[16 + 9];
+	float fwd = tmp[0] * cc[16 + 2] + tmp[1] * cc[16 + 6] * tmp[2] * cc[16 + 10];
+	float angle = acosf(fwd);
+	unsigned bly;
+	if (upDot > 0) bly = (unsigned)(long long)(g_nby / 2 + (angle / maxa) * (g_nby / 2)); /* cvttss2si r64, low half (NaN -> 0) */
+	else bly = (unsigned)(long long)(g_nby / 2 - (angle / maxa) * (g_nby / 2));
+	return (int)bly;
+}
+static inline int imin3(int a, int b, int c) { return (a < b) ? ((a < c) ? a : c) : ((b < c) ? b : c); }
+static inline int imax3(int a, int b, int c) { return (a > b) ? ((a > c) ? a : c) : ((b > c) ? b : c); }
+
+/* grid_kernel.cu:481-659 DS_spherical_Kernel (count) and :661-854 DS_spherical_Fillkernel share this */
+static void tri_cells_sph(const int *faces, const float *verts, int t, float xM, float yM, int *gx0, int *gx1, int *gy0, int *gy1, float *zmin)
+{
+	int bx[3], by[3];
+	float radius[3];
+	for (int k = 0; k < 3; k++) {
+		const float *v = verts + 3 * (size_t)faces[3 * t + k];
+		float p[3] = {v[0] - g_cc[0], v[1] - g_cc[1], v[2] - g_cc[2]};
+		radius[k] = sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+		p[0] /= radius[k]; p[1] /= radius[k]; p[2] /= radius[k];
+		bx[k] = effective_x(p, xM);
+		by[k] = effective_y(p, yM);
+	}
+	*zmin = min3(radius[0], radius[1], radius[2]); /* :613 */
+	*gx0 = clampi(imin3(bx[0], bx[1], bx[2]), 0, g_nbx - 1);
+	*gy0 = clampi(imin3(by[0], by[1], by[2]), 0, g_nby - 1);
+	*gx1 = clampi(imax3(bx[0], bx[1], bx[2]), 0, g_nbx - 1);
+	*gy1 = clampi(imax3(by[0], by[1], by[2]), 0, g_nby - 1);
+	/* :627-639: the "wrap" branch of size_x / size_y equals gmax - gmin + 1 */
+}
+
+/* mode 0: perspective rectangle, 1: spherical */
+static void tri_rect(int mode, float xM, float yM, const int *faces, const float *verts, int t, int *r, float *z)
+{
+	if (mode) tri_cells_sph(faces, verts, t, xM, yM, &r[0], &r[1], &r[2], &r[3], z);
+	else tri_cells(faces, verts, t, &r[0], &r[1], &r[2], &r[3], z);
+}
+
+static void grid_count(int mode, float xM, float yM, int *faces, float *verts, int T, unsigned *sizeList, float *projZ)
 {
 #pragma omp parallel for num_threads(g_threads)
 	for (int t = 0; t < T; t++) {
-		int a, b, c, d;
-		tri_cells(faces, verts, t, &a, &b, &c, &d, &projZ[t]);
-		sizeList[t] = (unsigned)((b - a + 1) * (d - c + 1)); /* grid_kernel.cu:231 */
+		int r[4];
+		tri_rect(mode, xM, yM, faces, verts, t, r, &projZ[t]);
+		sizeList[t] = (unsigned)((r[1] - r[0] + 1) * (r[3] - r[2] + 1)); /* grid_kernel.cu:231 / :641 */
 	}
+}
+void orc_grid_count(int *faces, float *verts, int T, unsigned *sizeList, float *projZ) { grid_count(0, 0, 0, faces, verts, T, sizeList, projZ); }
+void orc_grid_count_spherical(int *faces, float *verts, int T, unsigned *sizeList, float *projZ, float xM, float yM)
+{
+	grid_count(1, xM, yM, faces, verts, T, sizeList, projZ);
 }
 
 /* frustum_grid.h:210-366: count -> inclusive scan -> emit (x-major rectangle order, key =
  * gx*NBY+gy, grid_kernel.cu:318-325) -> stable sort by key (cudppSort = LSD radix) -> per-cell span
  * -> exclusive scan over ALL cells. Implemented as a counting sort, which is what a stable sort by
  * a small integer key is. */
-long orc_build_grid(int *faces, float *verts, int T, unsigned *span, unsigned *offset, unsigned *key_list,
-                    unsigned *value_list, long cap)
+static long build_grid(int mode, float xM, float yM, int *faces, float *verts, int T, unsigned *span, unsigned *offset, unsigned *key_list,
+                       unsigned *value_list, long cap)
 {
 	const int C = g_nbx * g_nby;
 	int *rect = (int *)malloc(sizeof(int) * 4 * (size_t)(T > 0 ? T : 1));
@@ -239,7 +310,7 @@ long orc_build_grid(int *faces, float *verts, int T, unsigned *span, unsigned *o
 #pragma omp parallel for num_threads(g_threads) reduction(+ : P)
 	for (int t = 0; t < T; t++) {
 		float z;
-		tri_cells(faces, verts, t, &rect[4 * t], &rect[4 * t + 1], &rect[4 * t + 2], &rect[4 * t + 3], &z);
+		tri_rect(mode, xM, yM, faces, verts, t, &rect[4 * t], &z);
 		P += (unsigned)((rect[4 * t + 1] - rect[4 * t] + 1) * (rect[4 * t + 3] - rect[4 * t + 2] + 1));
 	}
 	if (P > cap) { free(rect); return P; }
@@ -261,6 +332,16 @@ long orc_build_grid(int *faces, float *verts, int T, unsigned *span, unsigned *o
 	free(cursor);
 	free(rect);
 	return P;
+}
+long orc_build_grid(int *faces, float *verts, int T, unsigned *span, unsigned *offset, unsigned *key_list, unsigned *value_list, long cap)
+{
+	return build_grid(0, 0, 0, faces, verts, T, span, offset, key_list, value_list, cap);
+}
+/* frustum_grid.h:368-532 buildSphericalGrid: the same sequence around the spherical count / fill kernels */
+long orc_build_grid_spherical(int *faces, float *verts, int T, unsigned *span, unsigned *offset, unsigned *key_list, unsigned *value_list, long cap,
+                              float xM, float yM)
+{
+	return build_grid(1, xM, yM, faces, verts, T, span, offset, key_list, value_list, cap);
 }
 
 /* ------------------------------------------------------------------ a9: primary ray through a pixel
@@ -386,6 +467,29 @@ void orc_map_rays(float *t_list, float *dir_list, unsigned *map, float *cmPt, fl
 		int bly = (int)floor(((upd + nearPlane * tanHalf) / (2.0 * nearPlane * tanHalf)) * g_nby);
 		unsigned cell = (unsigned)(g_nbx * g_nby);
 		if (blx >= 0 && blx <= g_nbx - 1 && bly >= 0 && bly <= g_nby - 1) cell = (unsigned)(blx * g_nby + bly);
+		map[pix] = (unsigned)pix;
+		map[N + pix] = cell;
+	}
+}
+
+/* libm's acosf over an array: what the host-compiled reference gets from glibc; tests pin the product's restatement on it */
+void orc_acosf_array(const float *x, float *y, long n)
+{
+	for (long i = 0; i < n; i++) y[i] = acosf(x[i]);
+}
+
+/* a14: misc_kernel.cu:255-296 mapSort_Effective_kernel - the map display() really calls (main.cu:189) */
+void orc_map_rays_spherical(float *t_list, float *dir_list, unsigned *map, float *cmPt, float xM, float yM)
+{
+	const int N = g_W * g_H;
+#pragma omp parallel for num_threads(g_threads)
+	for (int pix = 0; pix < N; pix++) {
+		float tv = t_list[pix], P[3], L[3];
+		for (int k = 0; k < 3; k++) { P[k] = cmPt[k] + tv * dir_list[3 * (size_t)pix + k]; L[k] = P[k] - g_cc[k]; }
+		normalize3(L);
+		int blx = effective_x(L, xM), bly = effective_y(L, yM);
+		unsigned cell = (unsigned)(g_nbx * g_nby);
+		if (blx >= 0 && blx < g_nbx && bly >= 0 && bly < g_nby) cell = (unsigned)(blx * g_nby + bly);
 		map[pix] = (unsigned)pix;
 		map[N + pix] = cell;
 	}

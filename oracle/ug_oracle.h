@@ -30,6 +30,12 @@ void orc_transform(float *vertexlist, float *orig_list, int size, int offset, fl
 void orc_grid_count(int *faces, float *verts, int T, unsigned *sizeList, float *projZ);
 long orc_build_grid(int *faces, float *verts, int T, unsigned *span, unsigned *offset, unsigned *key_list,
                     unsigned *value_list, long cap);
+/* a14/a15: the spherical light grid display() uses (grid_kernel.cu:395-479,481-854; misc_kernel.cu:255-296) */
+void orc_grid_count_spherical(int *faces, float *verts, int T, unsigned *sizeList, float *projZ, float xM, float yM);
+long orc_build_grid_spherical(int *faces, float *verts, int T, unsigned *span, unsigned *offset, unsigned *key_list,
+                              unsigned *value_list, long cap, float xM, float yM);
+void orc_map_rays_spherical(float *t_list, float *dir_list, unsigned *map, float *cmPt, float xM, float yM);
+void orc_acosf_array(const float *x, float *y, long n); /* libm acosf, the reference's */
 void orc_trace(unsigned *value_list, unsigned *span, unsigned *offset, float *normal, float *t, float *dir,
                int *shadowed, int *id, float *verts, int *tris);
 void orc_map_rays(float *t_list, float *dir_list, unsigned *map, float *cmPt, float nearPlane);

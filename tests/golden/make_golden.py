@@ -28,6 +28,10 @@ def golden_scenes():
     out = {f"tiny_{k}": scenes.scene_tiny(k) for k in ("one", "tie", "behind", "near", "outside", "ka")}
     out["rand_11"] = scenes.scene_random(11, 800, 96, 64, nlights=1)
     out["a_256"] = scenes.scene_a(256, 256)
+    # "sph_" = the light path of the committed display() (spherical ray map + spherical light grid, main.cu:186-192)
+    out["sph_tiny_ka"] = scenes.scene_tiny("ka")
+    out["sph_rand_11"] = scenes.scene_random(11, 800, 96, 64, nlights=1)
+    out["sph_a_256"] = scenes.scene_a(256, 256)
     return out
 
 
@@ -39,7 +43,7 @@ def main():
     harness.build("ref")
     ref = harness.load("ref")
     for name, scene in golden_scenes().items():
-        res = harness.run_frame(ref, scene, threads=0)
+        res = harness.run_frame(ref, scene, threads=0, spherical=name.startswith("sph_"))
         data = {"stages": np.array([s for s in STAGES if s in res]), "sha256": np.array([digest(res[s]) for s in STAGES if s in res]),
                 "P": np.array([res["cam_P"], res.get("light0_P", 0)], dtype=np.int64)}
         small = scene.num_pixels <= 96 * 64

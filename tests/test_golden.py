@@ -16,6 +16,8 @@ FILES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
 
 
 def scene_for(name):
+    if name.startswith("sph_"):
+        return scene_for(name[4:])
     if name.startswith("tiny_"):
         return scenes.scene_tiny(name[5:])
     if name == "rand_11":
@@ -47,7 +49,7 @@ def check(result, gold, stages=None):
 
 
 def test_golden_files_present():
-    assert len(FILES) >= 8
+    assert len(FILES) >= 11
 
 
 @pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-4] for f in FILES])
@@ -55,7 +57,7 @@ def test_oracle_reproduces_golden(oracle, path):
     name = os.path.basename(path)[:-4]
     gold = np.load(path)
     scene = scene_for(name)
-    res = harness.run_frame(oracle, scene, threads=0)
+    res = harness.run_frame(oracle, scene, threads=0, spherical=name.startswith("sph_"))
     assert [res["cam_P"], res.get("light0_P", 0)] == gold["P"].tolist()
     check(res, gold)
 
@@ -71,6 +73,6 @@ def test_cuda_reproduces_golden(renderer, ug, path):
     gold = np.load(path)
     scene = scene_for(name)
     renderer.set_scene(scene)
-    res = parity.gpu_frame(renderer, scene, flags=ug.FLAG_FULL_BUFFERS)
+    res = parity.gpu_frame(renderer, scene, flags=ug.FLAG_FULL_BUFFERS | (ug.FLAG_SPHERICAL_LIGHTS if name.startswith("sph_") else 0))
     assert int(renderer.stats().cam_pairs) == int(gold["P"][0])
     check(res, gold, stages=GPU_STAGES)

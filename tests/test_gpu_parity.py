@@ -26,8 +26,8 @@ def assert_frame(gpu, cpu, what):
     assert not bad, f"{what}: stages not bit-exact: {bad}"
 
 
-def cpu_frame(oracle, scene, frame=0):
-    out = harness.run_frame(oracle, scene, frame=frame, threads=0)
+def cpu_frame(oracle, scene, frame=0, spherical=False):
+    out = harness.run_frame(oracle, scene, frame=frame, threads=0, spherical=spherical)
     oracle.configure(scene.width, scene.height, scene.fovy, 0)
     oracle.camera_setup(scene.eye, scene.look, scene.up, scene.near, scene.far)
     out["sizelist"] = oracle.grid_count(np.ascontiguousarray(scene.faces, np.int32), np.ascontiguousarray(out["verts"], np.float32))[0]
@@ -66,6 +66,42 @@ def test_config_a(renderer, ug, oracle):
     assert_frame(parity.gpu_frame(renderer, s), cpu, "config A (graph)")
     assert_frame(parity.gpu_frame(renderer, s, flags=ug.FLAG_FULL_BUFFERS | ug.FLAG_NO_GRAPH), cpu, "config A (direct launches)")
     assert_frame(parity.gpu_frame(renderer, s, stepwise=True), cpu, "config A (per_frame_funcs call sequence)")
+
+
+@pytest.mark.parametrize("case", ["ka", "soup2l", "soup", "hostile", "a", "c"])
+def test_spherical_light_grid(renderer, ug, oracle, case):
+    """a14/a15: the light path of the committed display() (main.cu:186-192) - spherical shadow-ray map
+    (misc_kernel.cu:255-296) and spherical light grid (grid_kernel.cu:395-479, 481-854; frustum_grid.h:368-532).  Needs
+    acosf to agree with the host's libm bit for bit: light cells, light-grid lists and shadow bits are all compared."""
+    s = {"ka": lambda: scenes.scene_tiny("ka"), "soup2l": lambda: scenes.scene_random(1, 2000, 128, 64, nlights=2),
+         "soup": lambda: scenes.scene_random(5, 20000, 320, 200, nlights=3), "hostile": lambda: scenes.scene_hostile(77),
+         "a": lambda: scenes.scene_a(), "c": lambda: scenes.scene_c(480, 272)}[case]()
+    renderer.set_scene(s)
+    fl = ug.FLAG_FULL_BUFFERS | ug.FLAG_SPHERICAL_LIGHTS
+    cpu = cpu_frame(oracle, s, spherical=True)
+    assert_frame(parity.gpu_frame(renderer, s, flags=fl), cpu, f"{s.name} spherical (graph)")
+    if case in ("ka", "a"):
+        assert_frame(parity.gpu_frame(renderer, s, flags=fl | ug.FLAG_NO_GRAPH), cpu, f"{s.name} spherical (direct launches)")
+        assert_frame(parity.gpu_frame(renderer, s, flags=fl, stepwise=True), cpu, f"{s.name} spherical (per_frame_funcs call sequence)")
+        # and back: the same context renders the perspective variant again
+        assert_frame(parity.gpu_frame(renderer, s), cpu_frame(oracle, s), f"{s.name} perspective after spherical")
+
+
+def test_spherical_build_variants(renderer, ug, oracle, monkeypatch):
+    """Both build variants (one cooperative kernel / kernel chain) of the spherical light grid give the same lists."""
+    s = scenes.scene_a(256, 256)
+    cpu = cpu_frame(oracle, s, spherical=True)
+    for env in ({"UG_NO_FUSED": "1"}, {"UG_FUSED_GRID": "1", "UG_FUSED_REGROUP": "1"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        r = ug.Renderer(0)
+        try:
+            r.set_scene(s)
+            assert_frame(parity.gpu_frame(r, s, flags=ug.FLAG_FULL_BUFFERS | ug.FLAG_SPHERICAL_LIGHTS), cpu, f"spherical {env}")
+        finally:
+            r.close()
+        for k in env:
+            monkeypatch.delenv(k)
 
 
 def test_config_b(renderer, ug, oracle):

@@ -17,9 +17,9 @@ def same(a, b):
     return a.shape == b.shape and np.array_equal(parity.bits(a.reshape(-1)), parity.bits(b.reshape(-1)))
 
 
-def check_frame(ref, oracle, scene, frame=0):
-    want = harness.run_frame(ref, scene, frame=frame, threads=0)
-    got = harness.run_frame(oracle, scene, frame=frame, threads=0)
+def check_frame(ref, oracle, scene, frame=0, spherical=False):
+    want = harness.run_frame(ref, scene, frame=frame, threads=0, spherical=spherical)
+    got = harness.run_frame(oracle, scene, frame=frame, threads=0, spherical=spherical)
     assert set(want) == set(got)
     bad = [k for k in want if not same(want[k], got[k])]
     assert not bad, f"{scene.name}: oracle differs from the reference build in {bad}"
@@ -50,6 +50,30 @@ def test_hostile_geometry(ref, oracle, seed):
     (garbage boxes included) the oracle must compute too."""
     out = check_frame(ref, oracle, scenes.scene_hostile(seed))
     assert out["cam_P"] > 5000 and (out["id"] == 5).sum() == 0     # the duplicate (id 5) never beats id 4
+
+
+@pytest.mark.parametrize("case", ["ka", "a", "soup1", "soup2", "hostile"])
+def test_spherical_light_grid(ref, oracle, case):
+    """a14/a15 - the light path the committed display() runs (main.cu:186-192): mapSort_Effective_kernel
+    (misc_kernel.cu:255-296) + DS_spherical_Kernel/Fillkernel (grid_kernel.cu:481-854) with getEffective_x/y
+    (:395-479, including the `a + b*c*d` dot product of :468) executed VERBATIM by the reference build vs the restatement."""
+    s = {"ka": lambda: scenes.scene_tiny("ka"), "a": lambda: scenes.scene_a(256, 256),
+         "soup1": lambda: scenes.scene_random(1, 2000, 128, 64, nlights=2), "soup2": lambda: scenes.scene_random(3, 6000, 256, 256, nlights=1),
+         "hostile": lambda: scenes.scene_hostile(77)}[case]()
+    out = check_frame(ref, oracle, s, spherical=True)
+    per = harness.run_frame(oracle, s, threads=0)
+    assert not same(out["light0_cell"], per["light0_cell"])          # it really is a different binning ...
+    assert same(out["id"], per["id"]) and same(out["t"], per["t"])   # ... of the same primary hits
+    if case == "a":
+        assert out["shadowed"].sum() > 1000
+        # the sizeList of the spherical count kernel alone (DS_spherical_Kernel), light camera resident
+        for lib in (ref, oracle):
+            lib.configure(s.width, s.height, s.fovy, 0)
+            lib.camera_setup(s.lights[0].pos, s.lights[0].look, s.lights[0].up, s.near, s.far, square=True)
+        pi = np.float32(np.pi)
+        a = ref.grid_count(np.ascontiguousarray(s.faces), np.ascontiguousarray(s.verts), spherical=(pi, pi))
+        b = oracle.grid_count(np.ascontiguousarray(s.faces), np.ascontiguousarray(s.verts), spherical=(pi, pi))
+        assert same(a[0], b[0]) and same(a[1], b[1]) and int(a[0].sum()) == out["light0_P"]
 
 
 def test_config_a_reduced(ref, oracle):

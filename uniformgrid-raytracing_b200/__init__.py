@@ -21,7 +21,8 @@ LIB_PATH = os.path.join(PKG_DIR, "libugrt.so")
 UG_OK = 0
 UG_MAX_LIGHTS = 8
 UG_TILE = 8
-FLAG_FULL_BUFFERS, FLAG_NO_GRAPH, FLAG_STAGE_EVENTS, FLAG_GATHER_FRAMES = 1, 2, 4, 8
+FLAG_FULL_BUFFERS, FLAG_NO_GRAPH, FLAG_STAGE_EVENTS, FLAG_GATHER_FRAMES, FLAG_SPHERICAL_LIGHTS = 1, 2, 4, 8, 16
+LIGHT_GRID_PERSPECTIVE, LIGHT_GRID_SPHERICAL = 0, 1
 
 (BUF_VERTEXLIST, BUF_CAM_VALUES, BUF_CAM_SPAN, BUF_CAM_OFFSET, BUF_T, BUF_ID, BUF_NORMAL, BUF_DIR, BUF_SHADOWED, BUF_RGB,
  BUF_LIGHT_VALUES, BUF_LIGHT_SPAN, BUF_LIGHT_OFFSET, BUF_LIGHT_CELL, BUF_SIZELIST, BUF_RGB_FULL, BUF_CAM_COUNTERS) = range(17)
@@ -93,6 +94,7 @@ def lib() -> C.CDLL:
             "ug_fill_coordinates_data": (C.c_int, [vp, C.POINTER(Camera)]), "ug_build_frustum_grid": (C.c_int, [vp]),
             "ug_trace": (C.c_int, [vp]), "ug_shadow_pass": (C.c_int, [vp, C.c_int, C.POINTER(Camera)]),
             "ug_simple_shade": (C.c_int, [vp]), "ug_add_shadows": (C.c_int, [vp]),
+            "ug_set_light_grid_mode": (C.c_int, [vp, C.c_int, C.c_float, C.c_float]), "ug_acosf_host": (None, [f, f, C.c_size_t]),
             "ug_render_frame": (C.c_int, [vp, C.POINTER(FrameParams)]),
             "ug_render_frame_host": (C.c_int, [vp, C.POINTER(FrameParams), C.c_void_p]),
             "ug_get_stats": (C.c_int, [vp, C.POINTER(Stats)]), "ug_read": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_size_t]),
@@ -307,9 +309,13 @@ class Renderer:
         self._ck(self.L.ug_write_ppm(self.ctx, path.encode()), "ug_write_ppm")
 
     # ---- the reference's call-by-call sequence (display(), main.cu:59-302)
-    def render_stepwise(self, scene=None):
+    def render_stepwise(self, scene=None, spherical: bool = False):
+        """The per_frame_funcs.h call sequence of display(), one C-ABI call per reference function; `spherical` selects the
+        getEffectiveRayGridMapping / buildSphericalGrid variant with x_max = y_max = M_PI (main.cu:186-192)."""
         s = scene or self.scene
         L = self.L
+        pi = float(np.float32(np.pi))
+        self._ck(L.ug_set_light_grid_mode(self.ctx, LIGHT_GRID_SPHERICAL if spherical else LIGHT_GRID_PERSPECTIVE, pi, pi), "ug_set_light_grid_mode")
         self._ck(L.ug_set_screen(self.ctx, s.width, s.height, float(s.fovy)), "ug_set_screen")
         self._ck(L.ug_set_strip(self.ctx, 0, 1), "ug_set_strip")
         lights = np.asarray([l.pos for l in s.lights], np.float32).reshape(-1)

@@ -4,7 +4,7 @@
  * shader.h call for call, minus every cudaThreadSynchronize(), D2H scalar read-back, per-frame
  * cudaMalloc/cudaFree and cudppPlan of the reference (frustum_grid.h:221-272,285-290,317-337).
  */
-#include "ugrt_internal.h"
+#include "k_common.cuh"
 #include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
@@ -38,6 +38,10 @@ static int bits_for(unsigned max_key_exclusive) /* number of key bits needed for
 
 /* ------------------------------------------------------------------ lifetime */
 extern "C" const char *ug_version(void) { return "ugrt 0.1 (sm_100a)"; }
+extern "C" void ug_acosf_host(const float *x, float *y, size_t n)
+{
+	for (size_t i = 0; i < n; i++) y[i] = ug_acosf(x[i]);
+}
 extern "C" size_t ug_frame_const_bytes(void) { return sizeof(FrameConst); }
 
 extern "C" int ug_create(ug_context **out, int device)
@@ -239,7 +243,7 @@ static int alloc_rays(ug_context *ctx, LightRays &r, int N, int C)
 	UG_CUDA(ctx, dmalloc(&r.offset, (size_t)C + 2));
 	UG_CUDA(ctx, dmalloc(&r.cursor, (size_t)C + 1));
 	UG_CUDA(ctx, dmalloc(&r.item_off, (size_t)C + 2));
-	r.item_cap = (size_t)N + (size_t)C; /* worst case: one item per ray (every list longer than 1024) */
+	r.item_cap = ugk_shadow_item_cap(N, C); /* worst case: one item per ray (every list longer than 1024) + the segment budget of every cell */
 	UG_CUDA(ctx, dmalloc(&r.items, r.item_cap));
 	UG_CUDA(ctx, dmalloc(&r.counters, 4));
 	UG_CUDA(ctx, cudaMemset(r.counters, 0, 4 * sizeof(u32)));
@@ -843,7 +847,9 @@ static int prepare_frame(ug_context *ctx, const ug_frame_params *p)
 		lc.fovy = p->fovy;
 		lc.aspect = 1.0f;
 		ug_camera_adjustCameraAndPosition(&lc);
-		ugh_view_const(&fc->light[l], &lc, ctx->W, ctx->H, ctx->nbx, ctx->nby, 0, ctx->nby);
+		/* main.cu:186-187: x_max = y_max = M_PI, narrowed to the float parameters of the two calls that follow */
+		ugh_view_const(&fc->light[l], &lc, ctx->W, ctx->H, ctx->nbx, ctx->nby, 0, ctx->nby,
+		               (p->flags & UG_FLAG_SPHERICAL_LIGHTS) ? UG_LIGHT_GRID_SPHERICAL : UG_LIGHT_GRID_PERSPECTIVE, (float)M_PI, (float)M_PI);
 		for (int k = 0; k < 3; k++) fc->light_pos[3 * l + k] = p->lights[l].pos[k];
 		/* shading runs with the LAST light camera's modelview resident in dd_camcoords (main.cu:205-211) */
 		memcpy(fc->shade_mv, lc.modelview_matrix, sizeof(fc->shade_mv));
@@ -1033,7 +1039,7 @@ extern "C" int ug_shadow_pass(ug_context *ctx, int light_id, const ug_camera *li
 	int rc = ensure_buffers(ctx, ctx->num_lights, ctx->full_alloc);
 	if (rc) return rc;
 	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	ugh_view_const(&ctx->h_fc->light[light_id], light_cam, ctx->W, ctx->H, ctx->nbx, ctx->nby, 0, ctx->nby);
+	ugh_view_const(&ctx->h_fc->light[light_id], light_cam, ctx->W, ctx->H, ctx->nbx, ctx->nby, 0, ctx->nby, ctx->light_grid_mode, ctx->light_xM, ctx->light_yM);
 	memcpy(ctx->h_fc->shade_mv, light_cam->modelview_matrix, sizeof(ctx->h_fc->shade_mv)); /* fillCoordinatesData with the light camera */
 	rc = upload_consts(ctx);
 	if (rc) return rc;
@@ -1059,6 +1065,15 @@ extern "C" int ug_shadow_pass(ug_context *ctx, int light_id, const ug_camera *li
 		}
 	}
 	return ug_fail(ctx, UG_ERR_OVERFLOW, "pair arena still too small after growing");
+}
+
+extern "C" int ug_set_light_grid_mode(ug_context *ctx, int mode, float xM, float yM)
+{
+	if (!ctx) return UG_ERR_ARG;
+	if (mode != UG_LIGHT_GRID_PERSPECTIVE && mode != UG_LIGHT_GRID_SPHERICAL) return ug_fail(ctx, UG_ERR_ARG, "light grid mode %d unknown", mode);
+	ctx->light_grid_mode = mode;
+	ctx->light_xM = xM; ctx->light_yM = yM;
+	return UG_OK;
 }
 
 extern "C" int ug_simple_shade(ug_context *ctx)

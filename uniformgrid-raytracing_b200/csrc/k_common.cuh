@@ -40,6 +40,63 @@ __device__ __forceinline__ int ug_d2i(double f)
 	return (f >= 2147483648.0 || f < -2147483648.0 || f != f) ? (int)0x80000000 : (int)f;
 }
 
+/* float -> unsigned the way gcc does it on x86-64 (grid_kernel.cu:475-478 assigns a float expression to an
+ * `unsigned int`): cvttss2si into a 64-bit register, low 32 bits kept; NaN / out of range give 0x8000000000000000 -> 0 */
+__device__ __forceinline__ u32 ug_f2u(float f)
+{
+	return (f >= 9223372036854775808.0f || f < -9223372036854775808.0f || f != f) ? 0u : (u32)(unsigned long long)__float2ll_rz(f);
+}
+
+/* acosf exactly as the reference's host build gets it from glibc 2.39 (sysdeps/ieee754/flt-32/e_acosf.c, the
+ * fdlibm float algorithm: only float + - * / and sqrtf, so -fmad=false / IEEE div+sqrt reproduce it bit for bit;
+ * tests/test_abi.py checks this restatement against libm through ug_acosf_host).  CUDA's own acosf differs in the
+ * last ulp, which would move vertices and rays across cell borders of the spherical light grid (a14/a15). */
+__host__ __device__ __forceinline__ float ug_acosf(float x)
+{
+	const float one = 1.0f, pi = 3.1415925026e+00f, pio2_hi = 1.5707962513e+00f, pio2_lo = 7.5497894159e-08f,
+	            pS0 = 1.6666667163e-01f, pS1 = -3.2556581497e-01f, pS2 = 2.0121252537e-01f, pS3 = -4.0055535734e-02f,
+	            pS4 = 7.9153501429e-04f, pS5 = 3.4793309169e-05f, qS1 = -2.4033949375e+00f, qS2 = 2.0209457874e+00f,
+	            qS3 = -6.8828397989e-01f, qS4 = 7.7038154006e-02f;
+#ifdef __CUDA_ARCH__
+	const int hx = __float_as_int(x);
+#else
+	int hx; memcpy(&hx, &x, 4);
+#endif
+	const int ix = hx & 0x7fffffff;
+	if (ix == 0x3f800000) return hx > 0 ? 0.0f : pi + 2.0f * pio2_lo; /* |x| == 1 */
+	if (ix > 0x3f800000) return (x - x) / (x - x);                    /* |x| > 1 or NaN: NaN */
+	if (ix < 0x3f000000) {                                            /* |x| < 0.5 */
+		if (ix <= 0x23000000) return pio2_hi + pio2_lo;
+		const float z = x * x;
+		const float p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+		const float q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+		const float r = p / q;
+		return pio2_hi - (x - (pio2_lo - x * r));
+	}
+	if (hx < 0) {                                                     /* x < -0.5 */
+		const float z = (one + x) * 0.5f;
+		const float p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+		const float q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+		const float s = sqrtf(z);
+		const float r = p / q;
+		const float w = r * s - pio2_lo;
+		return pi - 2.0f * (s + w);
+	}
+	const float z = (one - x) * 0.5f;                                 /* x > 0.5 */
+	const float s = sqrtf(z);
+#ifdef __CUDA_ARCH__
+	const float df = __int_as_float(__float_as_int(s) & 0xfffff000);
+#else
+	int is_; memcpy(&is_, &s, 4); is_ &= 0xfffff000; float df; memcpy(&df, &is_, 4);
+#endif
+	const float c = (z - df * df) / (s + df);
+	const float p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+	const float q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+	const float r = p / q;
+	const float w = r * s + c;
+	return 2.0f * (df + w);
+}
+
 /* grid_kernel.cu:4-11: one row of a column-major 4x4 times (x,y,z,w), summed left to right */
 __device__ __forceinline__ float ug_row(const float *m, int r, float x, float y, float z, float w)
 {

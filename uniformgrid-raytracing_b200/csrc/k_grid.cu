@@ -21,11 +21,9 @@ __global__ void __launch_bounds__(256) k_setup_bin(const ViewConst *__restrict__
                                                   int T, float4 *__restrict__ rec, uint2 *__restrict__ rect, u32 *__restrict__ count)
 {
 	__shared__ float s_cc[64];
-	__shared__ int s_geo[4];
 	if (threadIdx.x < 64) s_cc[threadIdx.x] = vcp->cc[threadIdx.x];
-	if (threadIdx.x == 64) { s_geo[0] = vcp->nbx; s_geo[1] = vcp->nby; s_geo[2] = vcp->gy_lo; s_geo[3] = vcp->gy_cnt; }
 	__syncthreads();
-	const GridGeo g = {s_geo[0], s_geo[1], s_geo[2], s_geo[2] + s_geo[3] - 1, s_cc[0], s_cc[1], s_cc[2]};
+	const GridGeo g = ug_grid_geo(vcp, s_cc);
 	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x)
 		count[t] = ug_tri_setup(s_cc, g, faces, verts, t, rec, rect);
 }

@@ -20,7 +20,67 @@ static __device__ __forceinline__ void ug_project(const float *cc, float x, floa
 	nx = qx / qw; ny = qy / qw; nz = qz / qw;
 }
 
-struct GridGeo { int nbx, nby, gy_lo, gy_hi; float ox, oy, oz; };
+struct GridGeo { int nbx, nby, gy_lo, gy_hi; float ox, oy, oz; int mode; float xM, yM; };
+static __device__ __forceinline__ GridGeo ug_grid_geo(const ViewConst *vc, const float *s_cc)
+{
+	const int gy_lo = vc->gy_lo;
+	const GridGeo g = {vc->nbx, vc->nby, gy_lo, gy_lo + vc->gy_cnt - 1, s_cc[0], s_cc[1], s_cc[2], vc->grid_mode, vc->xM, vc->yM};
+	return g;
+}
+
+/* ---- a14/a15: the spherical ("effective") light grid, grid_kernel.cu:395-421 getEffective_x and :452-479 getEffective_y.
+ * `v` = normalised direction from the light to the point; cc[16..] = the light camera's modelview, whose rows are
+ * right (16,20,24), up (17,21,25) and -forward (18,22,26). */
+static __device__ __forceinline__ int ug_effective_x(const float *cc, float vx, float vy, float vz, float maxa, int nbx)
+{
+	const float upd = vx * cc[17] + vy * cc[21] + vz * cc[25];
+	float tx = vx - upd * cc[17], ty = vy - upd * cc[21], tz = vz - upd * cc[25];
+	const float val = sqrtf(tx * tx + ty * ty + tz * tz); /* getMagnitude: ((0+x*x)+y*y)+z*z, sqrt -> sqrtf */
+	tx /= val; ty /= val; tz /= val;
+	const float fwd = tx * cc[18] + ty * cc[22] + tz * cc[26];
+	const float angle = ug_acosf(fwd);
+	const float rightd = tx * cc[16] + ty * cc[20] + tz * cc[24];
+	const u32 half = (u32)(nbx / 2), k = (u32)ug_f2i((angle / maxa) * (float)(nbx / 2)); /* int + (int)float, stored unsigned, read back as int */
+	return (int)(rightd > 0.0f ? half + k : half - k);
+}
+static __device__ __forceinline__ int ug_effective_y(const float *cc, float vx, float vy, float vz, float maxa, int nby)
+{
+	const float rd = vx * cc[16] + vy * cc[20] + vz * cc[24];
+	float tx = vx - rd * cc[16], ty = vy - rd * cc[20], tz = vz - rd * cc[24];
+	const float val = sqrtf(tx * tx + ty * ty + tz * tz);
+	tx /= val; ty /= val; tz /= val;
+	const float upd = tx * cc[17] + ty * cc[21] + tz * cc[25];
+	const float fwd = tx * cc[18] + ty * cc[22] * tz * cc[26]; /* grid_kernel.cu:468: `a + b*c*d` as written */
+	const float angle = ug_acosf(fwd);
+	const float half = (float)(nby / 2), part = (angle / maxa) * half; /* :475-478: int + float -> float -> unsigned int */
+	return (int)ug_f2u(upd > 0.0f ? half + part : half - part);
+}
+/* cell of one vertex, grid_kernel.cu:500-527: direction from the light, divided (not multiplied) by its length */
+static __device__ __forceinline__ void ug_sph_vertex(const float *cc, const GridGeo &g, float x, float y, float z, int &bx, int &by)
+{
+	float px = x - cc[0], py = y - cc[1], pz = z - cc[2];
+	const float radius = sqrtf(px * px + py * py + pz * pz);
+	px /= radius; py /= radius; pz /= radius;
+	bx = ug_effective_x(cc, px, py, pz, g.xM, g.nbx);
+	by = ug_effective_y(cc, px, py, pz, g.yM, g.nby);
+}
+static __device__ __forceinline__ int ug_imin3(int a, int b, int c) { return (a < b) ? ((a < c) ? a : c) : ((b < c) ? b : c); }
+static __device__ __forceinline__ int ug_imax3(int a, int b, int c) { return (a > b) ? ((a > c) ? a : c) : ((b > c) ? b : c); }
+/* grid_kernel.cu:481-659 DS_spherical_Kernel: integer min/max of the three vertex cells, clamped (:615-625); the
+ * wrap branch of size_x/size_y (:627-639) is algebraically gmax-gmin+1.  Kept out of line: the perspective path's
+ * register budget (the fused cooperative build) must not pay for it. */
+static __device__ __noinline__ void ug_sph_rect(const float *cc, const GridGeo &g, const float *p0, const float *p1, const float *p2, int &gx0, int &gx1, int &gy0,
+                                               int &gy1)
+{
+	int x0, y0, x1, y1, x2, y2;
+	ug_sph_vertex(cc, g, p0[0], p0[1], p0[2], x0, y0);
+	ug_sph_vertex(cc, g, p1[0], p1[1], p1[2], x1, y1);
+	ug_sph_vertex(cc, g, p2[0], p2[1], p2[2], x2, y2);
+	gx0 = ug_clampi(ug_imin3(x0, x1, x2), 0, g.nbx - 1);
+	gy0 = ug_clampi(ug_imin3(y0, y1, y2), 0, g.nby - 1);
+	gx1 = ug_clampi(ug_imax3(x0, x1, x2), 0, g.nbx - 1);
+	gy1 = ug_clampi(ug_imax3(y0, y1, y2), 0, g.nby - 1);
+}
 
 /* One triangle of one view: the ray-independent Moeller-Trumbore record (trace_kernel.cu:158-174 /
  * light_kernel.cu:133-148 staging arithmetic + the hoisted qvec and dot(e2,qvec)), its clamped cell
@@ -43,16 +103,21 @@ static __device__ __forceinline__ u32 ug_tri_setup(const float *s_cc, const Grid
 	rec[4 * (size_t)t + 1] = make_float4(e1x, e1y, e1z, 0.0f);
 	rec[4 * (size_t)t + 2] = make_float4(e2x, e2y, e2z, 0.0f);
 	rec[4 * (size_t)t + 3] = make_float4(qx, qy, qz, 0.0f);
-	float n0x, n0y, n0z, n1x, n1y, n1z, n2x, n2y, n2z;
-	ug_project(s_cc, ax, ay, az, n0x, n0y, n0z);
-	ug_project(s_cc, bx, by, bz, n1x, n1y, n1z);
-	ug_project(s_cc, cx, cy, cz, n2x, n2y, n2z);
-	const float xmin = ug_min3(n0x, n1x, n2x), ymin = ug_min3(n0y, n1y, n2y);
-	const float xmax = ug_max3(n0x, n1x, n2x), ymax = ug_max3(n0y, n1y, n2y);
-	const int gx0 = ug_clampi(ug_f2i(floorf(((xmin + 1.0f) / 2.0f) * (float)g.nbx)), 0, g.nbx - 1);
-	const int gy0 = ug_clampi(ug_f2i(floorf(((ymin + 1.0f) / 2.0f) * (float)g.nby)), 0, g.nby - 1);
-	const int gx1 = ug_clampi(ug_f2i(floorf(((xmax + 1.0f) / 2.0f) * (float)g.nbx)), 0, g.nbx - 1);
-	const int gy1 = ug_clampi(ug_f2i(floorf(((ymax + 1.0f) / 2.0f) * (float)g.nby)), 0, g.nby - 1);
+	int gx0, gy0, gx1, gy1;
+	if (g.mode == UG_LIGHT_GRID_SPHERICAL) {
+		ug_sph_rect(s_cc, g, p0, p1, p2, gx0, gx1, gy0, gy1);
+	} else {
+		float n0x, n0y, n0z, n1x, n1y, n1z, n2x, n2y, n2z;
+		ug_project(s_cc, ax, ay, az, n0x, n0y, n0z);
+		ug_project(s_cc, bx, by, bz, n1x, n1y, n1z);
+		ug_project(s_cc, cx, cy, cz, n2x, n2y, n2z);
+		const float xmin = ug_min3(n0x, n1x, n2x), ymin = ug_min3(n0y, n1y, n2y);
+		const float xmax = ug_max3(n0x, n1x, n2x), ymax = ug_max3(n0y, n1y, n2y);
+		gx0 = ug_clampi(ug_f2i(floorf(((xmin + 1.0f) / 2.0f) * (float)g.nbx)), 0, g.nbx - 1);
+		gy0 = ug_clampi(ug_f2i(floorf(((ymin + 1.0f) / 2.0f) * (float)g.nby)), 0, g.nby - 1);
+		gx1 = ug_clampi(ug_f2i(floorf(((xmax + 1.0f) / 2.0f) * (float)g.nbx)), 0, g.nbx - 1);
+		gy1 = ug_clampi(ug_f2i(floorf(((ymax + 1.0f) / 2.0f) * (float)g.nby)), 0, g.nby - 1);
+	}
 	/* image-strip sharding: keep only the owned cell rows; the rectangle itself is the global one */
 	const int ry0 = max(gy0, g.gy_lo), ry1 = min(gy1, g.gy_hi);
 	const int sx = gx1 - gx0 + 1, sy = ry1 - ry0 + 1;

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(GF_THREADS, 2) k_grid_fused(const GridFusedArg
 	if (tid < 64) s_cc[tid] = a.vc->cc[tid];
 	const int gy_lo = a.vc->gy_lo, gy_cnt = a.vc->gy_cnt;
 	__syncthreads();
-	const GridGeo geo = {a.vc->nbx, a.vc->nby, gy_lo, gy_lo + gy_cnt - 1, s_cc[0], s_cc[1], s_cc[2]};
+	const GridGeo geo = ug_grid_geo(a.vc, s_cc);
 
 	gf_stamp(a.counters, 0);
 	/* ---------------- phase 0: triangles -> record, rectangle, count; scan of the counts */

@@ -26,7 +26,9 @@ namespace cg = cooperative_groups;
 
 #define RG_THREADS 512
 #define SH_WARPS 4
-#define SH_SEGMAX 2048 /* lists longer than this are also cut along the triangle axis */
+#define SH_SEGMAX 2048 /* lists longer than this are also cut along the triangle axis ... */
+#define SH_SEGBUDGET 16 /* ... but only while the cell has few rays: at most 1 + SH_SEGBUDGET/rays segments, so a cell never needs more than
+                           rays + SH_SEGBUDGET items and the table is bounded by N + (SH_SEGBUDGET + 1)*C (ugk_shadow_item_cap) */
 
 /* rays per item for a list of `ntri` triangles */
 static __device__ __forceinline__ u32 sh_rays_per_item(u32 ntri)
@@ -38,11 +40,17 @@ static __device__ __forceinline__ u32 sh_rays_per_item(u32 ntri)
 	if (ntri <= 1024) return 2;
 	return 1;
 }
+/* segments of a list: many rays already give the cell enough items; few rays on a long list are what needs cutting */
+static __device__ __forceinline__ u32 sh_segments(u32 rays, u32 ntri)
+{
+	if (ntri <= SH_SEGMAX) return 1;
+	return min((ntri + SH_SEGMAX - 1) / SH_SEGMAX, 1u + SH_SEGBUDGET / rays);
+}
 static __device__ __forceinline__ u32 sh_items_of_cell(u32 rays, u32 ntri)
 {
 	if (!rays || !ntri) return 0;
 	const u32 rpi = sh_rays_per_item(ntri);
-	return ((rays + rpi - 1) / rpi) * ((ntri + SH_SEGMAX - 1) / SH_SEGMAX);
+	return ((rays + rpi - 1) / rpi) * sh_segments(rays, ntri);
 }
 
 struct RegroupArgs {
@@ -102,6 +110,21 @@ static __device__ __forceinline__ u32 light_cell_of(const LightMap &m, float ex,
 	return cell;
 }
 
+/* a14: misc_kernel.cu:255-296 mapSort_Effective_kernel - the spherical variant of the same map (the one display()
+ * actually calls, main.cu:189): angular bins of the normalised light->point direction */
+static __device__ __noinline__ u32 light_cell_sph(const ViewConst &lv, float ex, float ey, float ez, float tv, float dx, float dy, float dz)
+{
+	const float *cc = lv.cc;
+	const float Px = ex + tv * dx, Py = ey + tv * dy, Pz = ez + tv * dz;
+	float Lx = Px - cc[0], Ly = Py - cc[1], Lz = Pz - cc[2];
+	ug_normalize(Lx, Ly, Lz);
+	const int blx = ug_effective_x(cc, Lx, Ly, Lz, lv.xM, lv.nbx);
+	const int bly = ug_effective_y(cc, Lx, Ly, Lz, lv.yM, lv.nby);
+	u32 cell = (u32)(lv.nbx * lv.nby);
+	if (blx >= 0 && blx < lv.nbx && bly >= 0 && bly < lv.nby) cell = (u32)(blx * lv.nby + bly);
+	return cell;
+}
+
 /* phase < 0: all phases with grid barriers (cooperative launch); otherwise just that phase */
 __global__ void __launch_bounds__(RG_THREADS, 2) k_regroup(const RegroupArgs a, int phase)
 {
@@ -113,7 +136,9 @@ __global__ void __launch_bounds__(RG_THREADS, 2) k_regroup(const RegroupArgs a, 
 
 	if (all || phase == 0) { /* ---- phase A: ray -> light cell, rays per cell */
 		const ViewConst &cam = a.fc->cam;
-		const LightMap m = make_light_map(a.fc->light[a.light]);
+		const ViewConst &lv = a.fc->light[a.light];
+		const LightMap m = make_light_map(lv);
+		const bool spherical = lv.grid_mode == UG_LIGHT_GRID_SPHERICAL;
 		const float ex = cam.cc[0], ey = cam.cc[1], ez = cam.cc[2];
 		if (b == 0 && tid == 0) a.counters[1] = 0;
 		for (int base = b * RG_THREADS; base < N; base += G * RG_THREADS) {
@@ -121,7 +146,8 @@ __global__ void __launch_bounds__(RG_THREADS, 2) k_regroup(const RegroupArgs a, 
 			const bool valid = pix < N;
 			u32 cell = 0xffffffffu;
 			if (valid) {
-				cell = light_cell_of(m, ex, ey, ez, a.t[pix], a.dir[3 * (size_t)pix], a.dir[3 * (size_t)pix + 1], a.dir[3 * (size_t)pix + 2]);
+				const float tv = a.t[pix], dx = a.dir[3 * (size_t)pix], dy = a.dir[3 * (size_t)pix + 1], dz = a.dir[3 * (size_t)pix + 2];
+				cell = spherical ? light_cell_sph(lv, ex, ey, ez, tv, dx, dy, dz) : light_cell_of(m, ex, ey, ez, tv, dx, dy, dz);
 				a.light_cell[pix] = cell;
 			}
 			/* rays of one warp mostly share a light cell: one atomic per distinct cell */
@@ -182,9 +208,10 @@ __global__ void __launch_bounds__(RG_THREADS, 2) k_regroup(const RegroupArgs a, 
 		}
 		const u32 total = a.item_off[C];
 		if (b == 0 && tid == 0) a.counters[0] = min(total, a.item_cap);
-		for (u32 c = b * RG_THREADS + tid; c < (u32)C; c += G * RG_THREADS) {
+		/* a warp per cell: a crowded cell (spherical light grids put tens of thousands of rays into one) has as many items as rays */
+		for (u32 c = (b * RG_THREADS + tid) >> 5; c < (u32)C; c += (G * RG_THREADS) >> 5) {
 			const u32 o = a.item_off[c], n = a.item_off[c + 1] - o;
-			for (u32 q = 0; q < n; q++)
+			for (u32 q = ug_lane(); q < n; q += 32)
 				if (o + q < a.item_cap) a.items[o + q] = make_uint2(c, q);
 		}
 	}
@@ -226,10 +253,11 @@ __global__ void __launch_bounds__(32 * SH_WARPS) k_shadow(const FrameConst *__re
 		if (i >= nitems) break;
 		const uint2 it = items[i]; /* (cell, local item index) */
 		const u32 cell = it.x, ntri = span[cell], toff = offset[cell], nrays = ray_span[cell], roff = ray_offset[cell];
-		const u32 rpi = sh_rays_per_item(ntri), nseg = (ntri + SH_SEGMAX - 1) / SH_SEGMAX;
+		const u32 rpi = sh_rays_per_item(ntri), nseg = sh_segments(nrays, ntri);
+		const u32 seglen = (((ntri + nseg - 1) / nseg) + 31u) & ~31u; /* whole staging batches */
 		const u32 chunk = it.y / nseg, seg = it.y - chunk * nseg;
 		const u32 a = chunk * rpi, m = min(rpi, nrays - a);         /* this item's rays: [roff+a, roff+a+m) */
-		const u32 t0 = toff + seg * SH_SEGMAX, t1 = toff + min(ntri, (seg + 1) * SH_SEGMAX);
+		const u32 t0 = toff + min(ntri, seg * seglen), t1 = toff + min(ntri, (seg + 1) * seglen);
 		/* lane = (ray slot, triangle group) */
 		const u32 g = 32u / m, slot = lane % m, grp = lane / m;
 		const bool usable = grp < g;
@@ -280,6 +308,7 @@ bool ugk_regroup_fused_supported(int device)
 	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_regroup, RG_THREADS, 0) != cudaSuccess) return false;
 	return n >= 2;
 }
+size_t ugk_shadow_item_cap(int N, int C) { return (size_t)N + (size_t)(SH_SEGBUDGET + 1) * (size_t)C; }
 size_t ugk_regroup_state_entries(int C) { return ((size_t)C + 2 + RG_THREADS * 4 - 1) / (RG_THREADS * 4) + 2; }
 
 /* getRayGridMapping + processData (per_frame_funcs.h:72-137) for one light; returns false if the launch failed */

@@ -81,8 +81,16 @@ void build_frustum_grid(void) { die(ug_build_frustum_grid(ug_default_context()),
  * fillCoordinatesData made resident.  Here the five calls are one fused pass; it runs when
  * check_for_shadows() is reached, the other four record their arguments. */
 void getRayGridMapping(float *, float *, float *, float *, float *, float *) {}             /* result discarded in the reference, main.cu:186-187 */
-void getEffectiveRayGridMapping(float *, float *, unsigned int *, float *, float, float) {}
-void build_secondary_frustum_grid(float, float) {}
+/* these two are the SPHERICAL variants (per_frame_funcs.h:97-114 -> mapSort_Effective_kernel, :57-70 -> buildSphericalGrid):
+ * a display() that calls them gets the spherical light grid with its extents, as in the reference */
+void getEffectiveRayGridMapping(float *, float *, unsigned int *, float *, float xM, float yM)
+{
+	die(ug_set_light_grid_mode(ug_default_context(), UG_LIGHT_GRID_SPHERICAL, xM, yM), "getEffectiveRayGridMapping");
+}
+void build_secondary_frustum_grid(float xM, float yM)
+{
+	die(ug_set_light_grid_mode(ug_default_context(), UG_LIGHT_GRID_SPHERICAL, xM, yM), "build_secondary_frustum_grid");
+}
 void processData(void) {}
 void check_for_shadows(int light_id)
 {

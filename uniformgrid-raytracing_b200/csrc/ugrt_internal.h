@@ -24,6 +24,9 @@ struct ViewConst {
 	int nbx, nby;       /* cells of the full grid */
 	int gy_lo, gy_cnt;  /* owned cell rows (image strip); lights own everything */
 	int W, H;           /* full screen */
+	int grid_mode;      /* UG_LIGHT_GRID_*: how triangles and shadow rays are binned into this view's grid (the eye: always perspective) */
+	float xM, yM;       /* spherical mode: angular extents (main.cu:186-187 passes pi, pi) */
+	int pad_;
 };
 
 struct FrameConst {
@@ -142,6 +145,8 @@ struct ug_context {
 	u32 *h_counters = nullptr;  /* pinned [1+UG_MAX_LIGHTS][4]: counters of every grid, copied back by the frame */
 	int num_lights = 0;
 	int last_bounces = 0;
+	int light_grid_mode = UG_LIGHT_GRID_PERSPECTIVE; /* ug_set_light_grid_mode: used by ug_shadow_pass */
+	float light_xM = 3.14159274f, light_yM = 3.14159274f;
 
 	/* grids */
 	GridBuffers cam_grid;
@@ -222,6 +227,7 @@ void ugk_trace(cudaStream_t s, const FrameConst *fc, const GridBuffers &g, u64 *
 /* K7/K8 shadow (k_shadow.cu) */
 bool ugk_regroup_fused_supported(int device);
 size_t ugk_regroup_state_entries(int C);
+size_t ugk_shadow_item_cap(int N, int C);
 bool ugk_regroup(cudaStream_t s, const FrameConst *fc, int light, const GridBuffers &g, const LightRays &r, const float *t, const float *dir, int N, int C,
                  int sms, bool fused, int *launches);
 void ugk_shadow(cudaStream_t s, const FrameConst *fc, int light, const GridBuffers &g, const LightRays &r, const float *t, const float *dir, int *shadowed,
@@ -246,6 +252,7 @@ int ugc_ready(ug_context *ctx, cudaStream_t s);
 int ugc_gather_strips(ug_context *ctx, cudaStream_t s, const unsigned char *strip, unsigned char *full, const size_t *bytes, const size_t *offs);
 
 /* host helpers (camera_host.cpp, obj_loader.cpp) */
-void ugh_view_const(ViewConst *vc, const ug_camera *cam, int W, int H, int nbx, int nby, int gy_lo, int gy_cnt);
+void ugh_view_const(ViewConst *vc, const ug_camera *cam, int W, int H, int nbx, int nby, int gy_lo, int gy_cnt, int grid_mode = UG_LIGHT_GRID_PERSPECTIVE,
+                    float xM = 0.0f, float yM = 0.0f);
 
 #endif
