@@ -96,6 +96,9 @@ typedef struct ug_frame_params {
                                        (main.cu:189-192 getEffectiveRayGridMapping + buildSphericalGrid with x_max = y_max = M_PI)
                                        instead of the perspective one north-star names (misc_kernel.cu:63-129) */
 
+#define UG_FLAG_SPOT_SHADE 32 /* shade with Shader::spotlight_shade (shader.h:88-113 -> spot_shade, shader_kernel.cu:275-345) instead of
+                                simpleShade: what display() does from its third frame on (main.cu:205-219) */
+
 /* how a light's grid is parameterised (ug_set_light_grid_mode, UG_FLAG_SPHERICAL_LIGHTS) */
 #define UG_LIGHT_GRID_PERSPECTIVE 0 /* mapSortkernel misc_kernel.cu:63-129 + DSKernel/DSFillkernel grid_kernel.cu:164-332 */
 #define UG_LIGHT_GRID_SPHERICAL 1   /* mapSort_Effective_kernel misc_kernel.cu:255-296 + DS_spherical_Kernel/Fillkernel grid_kernel.cu:481-854 */
@@ -190,6 +193,7 @@ int ug_shadow_pass(ug_context *ctx, int light_id, const ug_camera *light_cam);  
  * build_secondary_frustum_grid(xM, yM) -> FrustumGrid::buildSphericalGrid (frustum_grid.h:368-532) when spherical */
 int ug_set_light_grid_mode(ug_context *ctx, int mode, float xM, float yM);
 int ug_simple_shade(ug_context *ctx);                                             /* shader.h:70-86 */
+int ug_spotlight_shade(ug_context *ctx);                                          /* shader.h:88-113 (without its printf dump) */
 int ug_add_shadows(ug_context *ctx);                                              /* shader.h:58-68 */
 
 /* ---- the whole frame: every step of display() between "frame_cnt++" and the image being complete,

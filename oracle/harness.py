@@ -60,6 +60,7 @@ class CpuLib:
             "map_rays": (None, [_f, _f, _u, _f, C.c_float]),
             "shadow": (None, [_u, _f, _i, _u, _u, _f, _f, _i, _u, _f]),
             "shade": (None, [_b, _f, _f, _f, _i, _f, _i, _f, C.c_int]),
+            "spot_shade": (None, [_b, _f, _f, _f, _i, _f, _i, _f, C.c_int, _f]),
             "add_shadows": (None, [_b, _i]),
             "load_obj": (C.c_int, [C.c_char_p, _i, _i, _f, _i, _i]),
             "load_materials": (C.c_int, [C.c_char_p, _i, _f]),
@@ -165,14 +166,21 @@ class CpuLib:
                      self._p(grid["offset"], _u), self._p(t, _f), self._p(d, _f), self._p(shadowed, _i), self._p(m, _u),
                      self._p(cam_pos, _f))
 
-    def shade(self, normal, t, d, ids, cam_pos, mat_idx, mat_list) -> np.ndarray:
-        """`ids` (triangle ids, -2 on miss) is overwritten with material indices like the reference does."""
+    def shade(self, normal, t, d, ids, cam_pos, mat_idx, mat_list, spot: bool = False) -> np.ndarray:
+        """`ids` (triangle ids, -2 on miss) is overwritten with material indices like the reference does.
+        `spot`: Shader::spotlight_shade (shader.h:88-113) instead of simpleShade (:70-86)."""
         N = self.W * self.H
         img = np.zeros(3 * N, dtype=np.uint8)
         cam_pos = np.ascontiguousarray(cam_pos, dtype=np.float32)
         padded = np.concatenate([np.full(2, -1, np.int32), np.ascontiguousarray(mat_idx, np.int32)])  # mat_idx[-2] readable
         base = padded.ctypes.data + 8
         mat_list = np.ascontiguousarray(mat_list, dtype=np.float32)
+        if spot:
+            dump = np.zeros(2 * N, dtype=np.float32)
+            self._spot_shade(self._p(img, _b), self._p(normal, _f), self._p(t, _f), self._p(d, _f), self._p(ids, _i),
+                             self._p(cam_pos, _f), C.cast(base, _i), self._p(mat_list, _f), mat_list.size // 6, self._p(dump, _f))
+            self.last_spot_angles = dump
+            return img
         self._shade(self._p(img, _b), self._p(normal, _f), self._p(t, _f), self._p(d, _f), self._p(ids, _i),
                     self._p(cam_pos, _f), C.cast(base, _i), self._p(mat_list, _f), mat_list.size // 6)
         return img
@@ -234,12 +242,14 @@ def reflect_table(scene) -> np.ndarray:
 
 
 def run_frame(lib: CpuLib, scene, frame: int = 0, threads: int = 0, stages: str = "all",
-              timings: Optional[dict] = None, reflect: bool = False, spherical: bool = False) -> Dict[str, np.ndarray]:
+              timings: Optional[dict] = None, reflect: bool = False, spherical: bool = False,
+              spot: bool = False) -> Dict[str, np.ndarray]:
     """One display() (main.cu:59-302) on the CPU: [transform ->] camera grid -> primary rays -> per
     light (light camera, ray->cell map, light grid, shadow rays) -> shade -> shadow modulation.
     Returns every stage's output for bit-exact comparison.  `spherical` runs the per-light steps the way the committed
     display() does (main.cu:186-192: spherical ray map + spherical grid with x_max = y_max = M_PI) instead of the
-    perspective variant north-star names."""
+    perspective variant north-star names; `spot` shades with spotlight_shade, as display() does from its third frame on
+    (main.cu:205-219)."""
     sph = (np.float32(np.pi), np.float32(np.pi)) if spherical else None
     lib.configure(scene.width, scene.height, scene.fovy, 0)
     lib.set_threads(threads)
@@ -301,7 +311,7 @@ def run_frame(lib: CpuLib, scene, frame: int = 0, threads: int = 0, stages: str 
     t0 = time.perf_counter()
     mat_list = material_table(scene)
     ids = prim["id"].copy()
-    img = lib.shade(prim["normal"], prim["t"], prim["dir"], ids, cam_pos, scene.face_mat, mat_list)
+    img = lib.shade(prim["normal"], prim["t"], prim["dir"], ids, cam_pos, scene.face_mat, mat_list, spot=spot)
     out["rgb_unshadowed"] = img.copy()
     lib.add_shadows(img, shadowed)
     tick("shade", t0)

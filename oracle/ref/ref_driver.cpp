@@ -438,6 +438,11 @@ void ref_shade(unsigned char *img, float *normal, float *t, float *dir, int *id,
 {
 	launch(NUM_BLOCKS_X, NUM_BLOCKS_Y, NUM_THREADS_X, NUM_THREADS_Y, [&] { lambertian_shade(img, normal, t, dir, id, cam_pos, mat_idx, mat_list, mat_count); });
 }
+/* shader.h:88-113 spotlight_shade -> shader_kernel.cu:275-345 spot_shade, verbatim; `dump` = its 2N-float debug buffer */
+void ref_spot_shade(unsigned char *img, float *normal, float *t, float *dir, int *id, float *cam_pos, int *mat_idx, float *mat_list, int mat_count, float *dump)
+{
+	launch(NUM_BLOCKS_X, NUM_BLOCKS_Y, NUM_THREADS_X, NUM_THREADS_Y, [&] { spot_shade(img, normal, t, dir, id, cam_pos, mat_idx, mat_list, mat_count, dump); });
+}
 /* shader.h:58-68 add_shadows -> shader_kernel.cu:347-359 */
 void ref_add_shadows(unsigned char *img, int *is_shadowed)
 {

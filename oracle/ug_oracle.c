@@ -528,8 +528,50 @@ void orc_shadow(unsigned *value_list, float *verts, int *tris, unsigned *span, u
  * shader_kernel.cu:165-221 lambertian_shade + :46-86 lambert_color_pixel.  Miss pixels (id < 0) are
  * black (the reference reads mat_idx[-2] there - SURVEY A.3); `id` is overwritten with the material
  * index as the reference does (:176). */
+/* shader_kernel.cu:223-273 get_along_x / get_along_y: the signed versions of getEffective_x/y's angles */
+static float along_x(const float *vec)
+{
+	const float *cc = g_cc;
+	float upDot = vec[0] * cc[16 + 1] + vec[1] * cc[16 + 5] + vec[2] * cc[16 + 9];
+	float tmp[3] = {vec[0] - upDot * cc[16 + 1], vec[1] - upDot * cc[16 + 5], vec[2] - upDot * cc[16 + 9]};
+	float val = sqrtf(tmp[0] * tmp[0] + tmp[1] * tmp[1] + tmp[2] * tmp[2]);
+	tmp[0] /= val; tmp[1] /= val; tmp[2] /= val;
+	float fwd = tmp[0] * cc[16 + 2] + tmp[1] * cc[16 + 6] + tmp[2] * cc[16 + 10];
+	float angle = acosf(fwd);
+	float rightDot = tmp[0] * cc[16 + 0] + tmp[1] * cc[16 + 4] + tmp[2] * cc[16 + 8];
+	return rightDot > 0 ? angle : (float)(-1.0 * angle);
+}
+static float along_y(const float *vec)
+{
+	const float *cc = g_cc;
+	float rightDot = vec[0] * cc[16 + 0] + vec[1] * cc[16 + 4] + vec[2] * cc[16 + 8];
+	float tmp[3] = {vec[0] - rightDot * cc[16 + 0], vec[1] - rightDot * cc[16 + 4], vec[2] - rightDot * cc[16 + 8]};
+	float val = sqrtf(tmp[0] * tmp[0] + tmp[1] * tmp[1] + tmp[2] * tmp[2]);
+	tmp[0] /= val; tmp[1] /= val; tmp[2] /= val;
+	float upDot = tmp[0] * cc[16 + 1] + tmp[1] * cc[16 + 5] + tmp[2] * cc[16 + 9];
+	float fwd = tmp[0] * cc[16 + 2] + tmp[1] * cc[16 + 6] * tmp[2] * cc[16 + 10]; /* :262, as written */
+	float angle = acosf(fwd);
+	return upDot > 0 ? angle : (float)(-1.0 * angle);
+}
+
+static void shade(int spot, unsigned char *img, float *normal, float *t, float *dir, int *id, float *cam_pos, int *mat_idx, float *mat_list, int mat_count,
+                  float *dump);
 void orc_shade(unsigned char *img, float *normal, float *t, float *dir, int *id, float *cam_pos, int *mat_idx,
                float *mat_list, int mat_count)
+{
+	shade(0, img, normal, t, dir, id, cam_pos, mat_idx, mat_list, mat_count, NULL);
+}
+/* shader_kernel.cu:275-345 spot_shade + :88-128 lambert_color_drop_off_pixel (Shader::spotlight_shade, shader.h:88-113 - what
+ * display() shades with from its third frame on, main.cu:205-219).  g_cc holds the resident (last light's) camera: the
+ * cone is about ITS axes, from ITS eye.  `dump` (2N floats, may be NULL) receives the two angles like the reference's
+ * debug buffer; miss pixels get NaN-free zeros here because the reference computes them from t = -1 garbage. */
+void orc_spot_shade(unsigned char *img, float *normal, float *t, float *dir, int *id, float *cam_pos, int *mat_idx,
+                    float *mat_list, int mat_count, float *dump)
+{
+	shade(1, img, normal, t, dir, id, cam_pos, mat_idx, mat_list, mat_count, dump);
+}
+static void shade(int spot, unsigned char *img, float *normal, float *t, float *dir, int *id, float *cam_pos, int *mat_idx, float *mat_list, int mat_count,
+                  float *dump)
 {
 	const int N = g_W * g_H;
 	const float *R = g_cc + 16;
@@ -543,6 +585,14 @@ void orc_shade(unsigned char *img, float *normal, float *t, float *dir, int *id,
 			float P[3], Lv[3], Pv[3], Nv[3], ld[3];
 			const float *n = normal + 3 * (size_t)pix;
 			for (int k = 0; k < 3; k++) P[k] = cam_pos[k] + t[pix] * dir[3 * (size_t)pix + k];
+			float drop = 1.0f;
+			if (spot) { /* :283-301 */
+				float L[3] = {P[0] - g_cc[0], P[1] - g_cc[1], P[2] - g_cc[2]};
+				normalize3(L);
+				const float x = along_x(L), y = along_y(L);
+				if (dump) { dump[2 * (size_t)pix] = x; dump[2 * (size_t)pix + 1] = y; }
+				drop = (x < M_PI / 4 && x > -M_PI / 4 && y < M_PI / 4 && y > -M_PI / 4) ? 1.0f : 0.25f;
+			}
 			for (int k = 0; k < 3; k++) { /* rotation part of the resident modelview, :54-67 */
 				Lv[k] = R[k] * g_light[0] + R[4 + k] * g_light[1] + R[8 + k] * g_light[2];
 				Pv[k] = R[k] * P[0] + R[4 + k] * P[1] + R[8 + k] * P[2];
@@ -551,11 +601,11 @@ void orc_shade(unsigned char *img, float *normal, float *t, float *dir, int *id,
 			normalize3(Nv);
 			for (int k = 0; k < 3; k++) ld[k] = Pv[k] - Lv[k];
 			normalize3(ld);
-			for (int k = 0; k < 3; k++) color[k] += kd[k] * 0.5f;
+			for (int k = 0; k < 3; k++) color[k] += spot ? kd[k] * 0.5f * drop : kd[k] * 0.5f;
 			float dd = dot3(ld, Nv);
 			if (!(dd > 0)) dd *= -1;
 			if (dd > 0)
-				for (int k = 0; k < 3; k++) color[k] += kd[k] * 1.0f * dd;
+				for (int k = 0; k < 3; k++) color[k] += spot ? kd[k] * 1.0f * dd * drop : kd[k] * 1.0f * dd;
 			for (int k = 0; k < 3; k++) if (color[k] > 1.0f) color[k] = 1.0f;
 		}
 		for (int k = 0; k < 3; k++) img[3 * (size_t)pix + k] = (unsigned char)(color[k] * 255);

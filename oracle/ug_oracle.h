@@ -43,6 +43,8 @@ void orc_shadow(unsigned *value_list, float *verts, int *tris, unsigned *span, u
                 float *dir_list, int *is_shadowed, unsigned *map, float *cmPt);
 void orc_shade(unsigned char *img, float *normal, float *t, float *dir, int *id, float *cam_pos, int *mat_idx,
                float *mat_list, int mat_count);
+void orc_spot_shade(unsigned char *img, float *normal, float *t, float *dir, int *id, float *cam_pos, int *mat_idx,
+                    float *mat_list, int mat_count, float *dump);
 void orc_add_shadows(unsigned char *img, int *is_shadowed);
 /* row R (reflection): authored spec, parity unpinned - see ug_oracle.c.  `rgb` holds the shaded + shadowed frame on
  * entry and the final frame on return; g_cc / g_light must be what was resident when orc_shade ran. */

@@ -27,7 +27,7 @@ def bits(a: np.ndarray) -> np.ndarray:
 def gpu_frame(r: "ug.Renderer", scene, frame=0, flags=ug.FLAG_FULL_BUFFERS, strip=(0, 1), stepwise=False, bounces=0):
     """Render through the C-ABI and read every stage buffer back."""
     if stepwise:
-        r.render_stepwise(scene, spherical=bool(flags & ug.FLAG_SPHERICAL_LIGHTS))
+        r.render_stepwise(scene, spherical=bool(flags & ug.FLAG_SPHERICAL_LIGHTS), spot=bool(flags & ug.FLAG_SPOT_SHADE))
     else:
         r.render(r.params(scene, frame=frame, flags=flags, strip=strip, bounces=bounces))
     out = {"verts": r.read(ug.BUF_VERTEXLIST).reshape(-1, 3), "cam_values": r.read(ug.BUF_CAM_VALUES), "cam_span": r.read(ug.BUF_CAM_SPAN),

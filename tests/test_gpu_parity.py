@@ -26,8 +26,8 @@ def assert_frame(gpu, cpu, what):
     assert not bad, f"{what}: stages not bit-exact: {bad}"
 
 
-def cpu_frame(oracle, scene, frame=0, spherical=False):
-    out = harness.run_frame(oracle, scene, frame=frame, threads=0, spherical=spherical)
+def cpu_frame(oracle, scene, frame=0, spherical=False, spot=False):
+    out = harness.run_frame(oracle, scene, frame=frame, threads=0, spherical=spherical, spot=spot)
     oracle.configure(scene.width, scene.height, scene.fovy, 0)
     oracle.camera_setup(scene.eye, scene.look, scene.up, scene.near, scene.far)
     out["sizelist"] = oracle.grid_count(np.ascontiguousarray(scene.faces, np.int32), np.ascontiguousarray(out["verts"], np.float32))[0]
@@ -85,6 +85,24 @@ def test_spherical_light_grid(renderer, ug, oracle, case):
         assert_frame(parity.gpu_frame(renderer, s, flags=fl, stepwise=True), cpu, f"{s.name} spherical (per_frame_funcs call sequence)")
         # and back: the same context renders the perspective variant again
         assert_frame(parity.gpu_frame(renderer, s), cpu_frame(oracle, s), f"{s.name} perspective after spherical")
+
+
+@pytest.mark.parametrize("case", ["ka", "soup2l", "hostile", "a", "c"])
+def test_spot_shade(renderer, ug, oracle, case):
+    """Shader::spotlight_shade -> spot_shade (shader_kernel.cu:275-345; display() from its third frame on, main.cu:205-219),
+    behind the spherical light path and behind the perspective one: RGB bit-exact, cone border pixels included."""
+    s = {"ka": lambda: scenes.scene_tiny("ka"), "soup2l": lambda: scenes.scene_random(1, 2000, 128, 64, nlights=2),
+         "hostile": lambda: scenes.scene_hostile(77), "a": lambda: scenes.scene_a(), "c": lambda: scenes.scene_c(480, 272)}[case]()
+    renderer.set_scene(s)
+    for sph in (True, False):
+        fl = ug.FLAG_FULL_BUFFERS | ug.FLAG_SPOT_SHADE | (ug.FLAG_SPHERICAL_LIGHTS if sph else 0)
+        cpu = cpu_frame(oracle, s, spherical=sph, spot=True)
+        assert_frame(parity.gpu_frame(renderer, s, flags=fl), cpu, f"{s.name} spot shade, spherical={sph}")
+        if case in ("ka", "a"):
+            assert_frame(parity.gpu_frame(renderer, s, flags=fl, stepwise=True), cpu, f"{s.name} spot shade, call sequence, spherical={sph}")
+    if case == "a":
+        plain = parity.gpu_frame(renderer, s)
+        assert not np.array_equal(plain["rgb"], cpu["rgb"])     # the flag is part of the graph key: the plain shader is back
 
 
 def test_spherical_build_variants(renderer, ug, oracle, monkeypatch):

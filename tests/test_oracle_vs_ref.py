@@ -17,9 +17,9 @@ def same(a, b):
     return a.shape == b.shape and np.array_equal(parity.bits(a.reshape(-1)), parity.bits(b.reshape(-1)))
 
 
-def check_frame(ref, oracle, scene, frame=0, spherical=False):
-    want = harness.run_frame(ref, scene, frame=frame, threads=0, spherical=spherical)
-    got = harness.run_frame(oracle, scene, frame=frame, threads=0, spherical=spherical)
+def check_frame(ref, oracle, scene, frame=0, spherical=False, spot=False):
+    want = harness.run_frame(ref, scene, frame=frame, threads=0, spherical=spherical, spot=spot)
+    got = harness.run_frame(oracle, scene, frame=frame, threads=0, spherical=spherical, spot=spot)
     assert set(want) == set(got)
     bad = [k for k in want if not same(want[k], got[k])]
     assert not bad, f"{scene.name}: oracle differs from the reference build in {bad}"
@@ -74,6 +74,22 @@ def test_spherical_light_grid(ref, oracle, case):
         a = ref.grid_count(np.ascontiguousarray(s.faces), np.ascontiguousarray(s.verts), spherical=(pi, pi))
         b = oracle.grid_count(np.ascontiguousarray(s.faces), np.ascontiguousarray(s.verts), spherical=(pi, pi))
         assert same(a[0], b[0]) and same(a[1], b[1]) and int(a[0].sum()) == out["light0_P"]
+
+
+@pytest.mark.parametrize("case", ["ka", "a", "soup1", "hostile"])
+def test_spot_shade(ref, oracle, case):
+    """Shader::spotlight_shade -> spot_shade (shader_kernel.cu:275-345), the shader display() uses from its third frame on
+    (main.cu:205-219), run verbatim by the reference build vs the restatement - with the committed display()'s spherical
+    light path in front of it.  The two cone angles the reference dumps per pixel are compared on hit pixels as well."""
+    s = {"ka": lambda: scenes.scene_tiny("ka"), "a": lambda: scenes.scene_a(256, 256),
+         "soup1": lambda: scenes.scene_random(1, 2000, 128, 64, nlights=2), "hostile": lambda: scenes.scene_hostile(77)}[case]()
+    out = check_frame(ref, oracle, s, spherical=True, spot=True)
+    hit = np.repeat(out["id"] >= 0, 2)
+    assert same(ref.last_spot_angles[hit], oracle.last_spot_angles[hit])
+    plain = harness.run_frame(oracle, s, threads=0, spherical=True)
+    if case in ("ka", "a"):
+        assert not same(out["rgb"], plain["rgb"])       # part of the image lies outside the cone and is dimmed to a quarter
+    assert same(out["shadowed"], plain["shadowed"])
 
 
 def test_config_a_reduced(ref, oracle):

@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libugrt.so")
 UG_OK = 0
 UG_MAX_LIGHTS = 8
 UG_TILE = 8
-FLAG_FULL_BUFFERS, FLAG_NO_GRAPH, FLAG_STAGE_EVENTS, FLAG_GATHER_FRAMES, FLAG_SPHERICAL_LIGHTS = 1, 2, 4, 8, 16
+FLAG_FULL_BUFFERS, FLAG_NO_GRAPH, FLAG_STAGE_EVENTS, FLAG_GATHER_FRAMES, FLAG_SPHERICAL_LIGHTS, FLAG_SPOT_SHADE = 1, 2, 4, 8, 16, 32
 LIGHT_GRID_PERSPECTIVE, LIGHT_GRID_SPHERICAL = 0, 1
 
 (BUF_VERTEXLIST, BUF_CAM_VALUES, BUF_CAM_SPAN, BUF_CAM_OFFSET, BUF_T, BUF_ID, BUF_NORMAL, BUF_DIR, BUF_SHADOWED, BUF_RGB,
@@ -93,7 +93,7 @@ def lib() -> C.CDLL:
             "ug_update_light_position": (C.c_int, [vp, f, C.c_int]),
             "ug_fill_coordinates_data": (C.c_int, [vp, C.POINTER(Camera)]), "ug_build_frustum_grid": (C.c_int, [vp]),
             "ug_trace": (C.c_int, [vp]), "ug_shadow_pass": (C.c_int, [vp, C.c_int, C.POINTER(Camera)]),
-            "ug_simple_shade": (C.c_int, [vp]), "ug_add_shadows": (C.c_int, [vp]),
+            "ug_simple_shade": (C.c_int, [vp]), "ug_spotlight_shade": (C.c_int, [vp]), "ug_add_shadows": (C.c_int, [vp]),
             "ug_set_light_grid_mode": (C.c_int, [vp, C.c_int, C.c_float, C.c_float]), "ug_acosf_host": (None, [f, f, C.c_size_t]),
             "ug_render_frame": (C.c_int, [vp, C.POINTER(FrameParams)]),
             "ug_render_frame_host": (C.c_int, [vp, C.POINTER(FrameParams), C.c_void_p]),
@@ -309,7 +309,7 @@ class Renderer:
         self._ck(self.L.ug_write_ppm(self.ctx, path.encode()), "ug_write_ppm")
 
     # ---- the reference's call-by-call sequence (display(), main.cu:59-302)
-    def render_stepwise(self, scene=None, spherical: bool = False):
+    def render_stepwise(self, scene=None, spherical: bool = False, spot: bool = False):
         """The per_frame_funcs.h call sequence of display(), one C-ABI call per reference function; `spherical` selects the
         getEffectiveRayGridMapping / buildSphericalGrid variant with x_max = y_max = M_PI (main.cu:186-192)."""
         s = scene or self.scene
@@ -328,5 +328,8 @@ class Renderer:
         for k, l in enumerate(s.lights):
             lc = make_camera(l.pos, l.look, l.up, s.near, s.far, float(s.fovy), 1.0)
             self._ck(L.ug_shadow_pass(self.ctx, k, C.byref(lc)), "shadow pass")
-        self._ck(L.ug_simple_shade(self.ctx), "simpleShade")
+        if spot:
+            self._ck(L.ug_spotlight_shade(self.ctx), "spotlight_shade")
+        else:
+            self._ck(L.ug_simple_shade(self.ctx), "simpleShade")
         self._ck(L.ug_add_shadows(self.ctx), "add_shadows")

@@ -750,7 +750,7 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 		}
 	}
 	ugk_shade(s, ctx->d_fc, ctx->d_t, ctx->d_dir, ctx->d_id, ctx->d_shadowed, ctx->cam_grid.tri_rec, ctx->d_materiallist_index, ctx->d_materiallist, ctx->num_materials,
-	          ctx->d_rgb, ctx->d_matid, ctx->N, 1, sms);
+	          ctx->d_rgb, ctx->d_matid, ctx->N, 1, sms, (p->flags & UG_FLAG_SPOT_SHADE) != 0);
 	L.n += 1;
 	ugk_stamp(s, tl, 3);
 	stage_mark(ctx, k, stage_events); /* shade */
@@ -837,6 +837,7 @@ static int prepare_frame(ug_context *ctx, const ug_frame_params *p)
 	ug_camera_adjustCameraAndPosition(&cam);
 	ugh_view_const(&fc->cam, &cam, ctx->W, ctx->H, ctx->nbx, ctx->nby, ctx->gy_lo, ctx->gy_cnt);
 	memcpy(fc->shade_mv, cam.modelview_matrix, sizeof(fc->shade_mv));
+	memcpy(fc->shade_eye, cam.worldori, sizeof(fc->shade_eye));
 	for (int l = 0; l < p->num_lights; l++) {
 		ug_camera lc;
 		memset(&lc, 0, sizeof(lc));
@@ -853,6 +854,7 @@ static int prepare_frame(ug_context *ctx, const ug_frame_params *p)
 		for (int k = 0; k < 3; k++) fc->light_pos[3 * l + k] = p->lights[l].pos[k];
 		/* shading runs with the LAST light camera's modelview resident in dd_camcoords (main.cu:205-211) */
 		memcpy(fc->shade_mv, lc.modelview_matrix, sizeof(fc->shade_mv));
+		memcpy(fc->shade_eye, lc.worldori, sizeof(fc->shade_eye));
 	}
 	for (int l = p->num_lights; l < UG_MAX_LIGHTS; l++)
 		for (int k = 0; k < 3; k++) fc->light_pos[3 * l + k] = 0.0f;
@@ -867,7 +869,7 @@ static unsigned long long frame_key(const ug_context *ctx, const ug_frame_params
 	unsigned long long k = 1469598103934665603ull;
 	auto mix = [&](unsigned long long v) { k = (k ^ v) * 1099511628211ull; };
 	mix((unsigned long long)ctx->W); mix((unsigned long long)ctx->H); mix((unsigned long long)ctx->gy_lo); mix((unsigned long long)ctx->gy_cnt);
-	mix((unsigned long long)ctx->num_faces); mix((unsigned long long)p->num_lights); mix((unsigned long long)(p->flags & (UG_FLAG_FULL_BUFFERS | UG_FLAG_GATHER_FRAMES)));
+	mix((unsigned long long)ctx->num_faces); mix((unsigned long long)p->num_lights); mix((unsigned long long)(p->flags & (UG_FLAG_FULL_BUFFERS | UG_FLAG_GATHER_FRAMES | UG_FLAG_SPOT_SHADE)));
 	mix((unsigned long long)(p->transform && ctx->d_vertex_orig_list ? 1 : 0)); mix((unsigned long long)ctx->cam_grid.cap);
 	for (int l = 0; l < p->num_lights; l++) mix((unsigned long long)ctx->light_grid[l].cap);
 	mix((unsigned long long)(p->bounces > 0 && ctx->d_reflect ? p->bounces : 0)); mix((unsigned long long)ctx->refl.grid.cap);
@@ -998,6 +1000,7 @@ extern "C" int ug_fill_coordinates_data(ug_context *ctx, const ug_camera *cam)
 	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	ugh_view_const(&ctx->h_fc->cam, cam, ctx->W, ctx->H, ctx->nbx, ctx->nby, ctx->gy_lo, ctx->gy_cnt);
 	memcpy(ctx->h_fc->shade_mv, cam->modelview_matrix, sizeof(ctx->h_fc->shade_mv));
+	memcpy(ctx->h_fc->shade_eye, cam->worldori, sizeof(ctx->h_fc->shade_eye));
 	return upload_consts(ctx);
 }
 
@@ -1041,6 +1044,7 @@ extern "C" int ug_shadow_pass(ug_context *ctx, int light_id, const ug_camera *li
 	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	ugh_view_const(&ctx->h_fc->light[light_id], light_cam, ctx->W, ctx->H, ctx->nbx, ctx->nby, 0, ctx->nby, ctx->light_grid_mode, ctx->light_xM, ctx->light_yM);
 	memcpy(ctx->h_fc->shade_mv, light_cam->modelview_matrix, sizeof(ctx->h_fc->shade_mv)); /* fillCoordinatesData with the light camera */
+	memcpy(ctx->h_fc->shade_eye, light_cam->worldori, sizeof(ctx->h_fc->shade_eye));
 	rc = upload_consts(ctx);
 	if (rc) return rc;
 	for (int attempt = 0; attempt < 3; attempt++) {
@@ -1081,6 +1085,19 @@ extern "C" int ug_simple_shade(ug_context *ctx)
 	if (!ctx || !ctx->d_t) return ug_fail(ctx, UG_ERR_ARG, "simpleShade: trace first");
 	ugk_shade(ctx->stream, ctx->d_fc, ctx->d_t, ctx->d_dir, ctx->d_id, ctx->d_shadowed, ctx->cam_grid.tri_rec, ctx->d_materiallist_index, ctx->d_materiallist,
 	          ctx->num_materials, ctx->d_rgb, ctx->d_matid, ctx->N, 0, ctx->num_sms);
+	UG_CUDA(ctx, cudaGetLastError());
+	ctx->frame_valid = true;
+	return UG_OK;
+}
+
+/* shader.h:88-113 spotlight_shade -> spot_shade (shader_kernel.cu:275-345): what display() switches to from its third frame
+ * on (main.cu:205-219).  The reference's host wrapper also copies the two cone angles of every pixel back and printf's
+ * them (shader.h:106-111); that debug dump is not reproduced. */
+extern "C" int ug_spotlight_shade(ug_context *ctx)
+{
+	if (!ctx || !ctx->d_t) return ug_fail(ctx, UG_ERR_ARG, "spotlight_shade: trace first");
+	ugk_shade(ctx->stream, ctx->d_fc, ctx->d_t, ctx->d_dir, ctx->d_id, ctx->d_shadowed, ctx->cam_grid.tri_rec, ctx->d_materiallist_index, ctx->d_materiallist,
+	          ctx->num_materials, ctx->d_rgb, ctx->d_matid, ctx->N, 0, ctx->num_sms, true);
 	UG_CUDA(ctx, cudaGetLastError());
 	ctx->frame_valid = true;
 	return UG_OK;

@@ -55,13 +55,14 @@ void ugk_transform(cudaStream_t s, float *vertexlist, const float *orig, int siz
 
 /* 4 consecutive pixels per thread: 16-byte loads of t/id/shadowed, 3 x 16-byte loads of dir, the 12 RGB bytes leave
  * as three 32-bit stores (N is a multiple of 64, every buffer is 16-byte aligned) */
+template <bool SPOT>
 __global__ void __launch_bounds__(256) k_shade(const FrameConst *__restrict__ fc, const float *__restrict__ t, const float *__restrict__ dir,
                                               const int *__restrict__ id, const int *__restrict__ shadowed, const float4 *__restrict__ rec,
                                               const int *__restrict__ mat_idx, const float *__restrict__ mat_list, int mat_count,
                                               unsigned char *__restrict__ rgb, int *__restrict__ mat_out, int N, int apply_shadow)
 {
 	const ViewConst &cam = fc->cam;
-	const float *R = fc->shade_mv;
+	const float *R = fc->shade_mv, *leye = fc->shade_eye;
 	const float ex = cam.cc[0], ey = cam.cc[1], ez = cam.cc[2];
 	/* shader_kernel.cu:54-57: light 0 through the rotation part of the resident modelview */
 	const float l0 = fc->light_pos[0], l1 = fc->light_pos[1], l2 = fc->light_pos[2];
@@ -75,10 +76,10 @@ __global__ void __launch_bounds__(256) k_shade(const FrameConst *__restrict__ fc
 		const int4 sh = ((const int4 *)shadowed)[g];
 		const float4 d0 = ((const float4 *)dir)[3 * (size_t)g], d1 = ((const float4 *)dir)[3 * (size_t)g + 1], d2 = ((const float4 *)dir)[3 * (size_t)g + 2];
 		int m0, m1, m2, m3;
-		const u32 c0 = shade_pixel(R, ex, ey, ez, Lvx, Lvy, Lvz, tv.x, d0.x, d0.y, d0.z, tri.x, sh.x, rec, mat_idx, mat_list, mat_count, apply_shadow, m0);
-		const u32 c1 = shade_pixel(R, ex, ey, ez, Lvx, Lvy, Lvz, tv.y, d0.w, d1.x, d1.y, tri.y, sh.y, rec, mat_idx, mat_list, mat_count, apply_shadow, m1);
-		const u32 c2 = shade_pixel(R, ex, ey, ez, Lvx, Lvy, Lvz, tv.z, d1.z, d1.w, d2.x, tri.z, sh.z, rec, mat_idx, mat_list, mat_count, apply_shadow, m2);
-		const u32 c3 = shade_pixel(R, ex, ey, ez, Lvx, Lvy, Lvz, tv.w, d2.y, d2.z, d2.w, tri.w, sh.w, rec, mat_idx, mat_list, mat_count, apply_shadow, m3);
+		const u32 c0 = shade_pixel<SPOT>(R, leye, ex, ey, ez, Lvx, Lvy, Lvz, tv.x, d0.x, d0.y, d0.z, tri.x, sh.x, rec, mat_idx, mat_list, mat_count, apply_shadow, m0);
+		const u32 c1 = shade_pixel<SPOT>(R, leye, ex, ey, ez, Lvx, Lvy, Lvz, tv.y, d0.w, d1.x, d1.y, tri.y, sh.y, rec, mat_idx, mat_list, mat_count, apply_shadow, m1);
+		const u32 c2 = shade_pixel<SPOT>(R, leye, ex, ey, ez, Lvx, Lvy, Lvz, tv.z, d1.z, d1.w, d2.x, tri.z, sh.z, rec, mat_idx, mat_list, mat_count, apply_shadow, m2);
+		const u32 c3 = shade_pixel<SPOT>(R, leye, ex, ey, ez, Lvx, Lvy, Lvz, tv.w, d2.y, d2.z, d2.w, tri.w, sh.w, rec, mat_idx, mat_list, mat_count, apply_shadow, m3);
 		if (mat_out) ((int4 *)mat_out)[g] = make_int4(m0, m1, m2, m3); /* shader_kernel.cu:176 */
 		u32 *out = (u32 *)rgb + 3 * (size_t)g;
 		out[0] = c0 | (c1 << 24);
@@ -96,10 +97,12 @@ __global__ void __launch_bounds__(256) k_add_shadows(const int *__restrict__ sha
 }
 
 void ugk_shade(cudaStream_t s, const FrameConst *fc, const float *t, const float *dir, const int *id, const int *shadowed, const float4 *rec, const int *mat_idx,
-               const float *mat_list, int mat_count, unsigned char *rgb, int *mat_out, int N, int apply_shadow, int sms)
+               const float *mat_list, int mat_count, unsigned char *rgb, int *mat_out, int N, int apply_shadow, int sms, bool spot)
 {
 	if (N <= 0) return;
-	k_shade<<<min((N / 4 + 255) / 256, sms * 8), 256, 0, s>>>(fc, t, dir, id, shadowed, rec, mat_idx, mat_list, mat_count, rgb, mat_out, N, apply_shadow);
+	const int blocks = min((N / 4 + 255) / 256, sms * 8);
+	if (spot) k_shade<true><<<blocks, 256, 0, s>>>(fc, t, dir, id, shadowed, rec, mat_idx, mat_list, mat_count, rgb, mat_out, N, apply_shadow);
+	else k_shade<false><<<blocks, 256, 0, s>>>(fc, t, dir, id, shadowed, rec, mat_idx, mat_list, mat_count, rgb, mat_out, N, apply_shadow);
 }
 void ugk_add_shadows(cudaStream_t s, const int *shadowed, unsigned char *rgb, int N, int sms)
 {

@@ -34,6 +34,7 @@ struct FrameConst {
 	ViewConst light[UG_MAX_LIGHTS];
 	float light_pos[3 * UG_MAX_LIGHTS]; /* dd_light_position, main.cu.h:63 */
 	float shade_mv[16];                 /* the modelview resident in dd_camcoords when shading runs (last light's) */
+	float shade_eye[4];                 /* and that camera's eye, dd_camcoords[0..3] (spot_shade, shader_kernel.cu:289-291) */
 	float rot_cos, rot_sin;             /* cosf/sinf(rot_factor) from the host - transformation_kernel.cu:14-15 */
 	int num_lights;
 	int pad_;
@@ -234,7 +235,7 @@ void ugk_shadow(cudaStream_t s, const FrameConst *fc, int light, const GridBuffe
                 int N, int C, int sms);
 /* K10 shade */
 void ugk_shade(cudaStream_t s, const FrameConst *fc, const float *t, const float *dir, const int *id, const int *shadowed, const float4 *rec, const int *mat_idx,
-               const float *mat_list, int mat_count, unsigned char *rgb, int *mat_out, int N, int apply_shadow, int sms);
+               const float *mat_list, int mat_count, unsigned char *rgb, int *mat_out, int N, int apply_shadow, int sms, bool spot = false);
 void ugk_add_shadows(cudaStream_t s, const int *shadowed, unsigned char *rgb, int N, int sms);
 void ugk_fill_u32(cudaStream_t s, u32 *p, u32 v, size_t n, int sms);
 /* row R (k_reflect.cu) */
