@@ -35,6 +35,7 @@ extern "C" {
 #define UG_TILE 8          /* NUM_THREADS_X/Y, main.cu.h:24-25 */
 #define UG_MAX_LIGHTS 8    /* reference capacity is 2 (main.cu.h:61,63); only light 0 shades (shader_kernel.cu:52) */
 #define UG_MATERIAL_SIZE 6 /* main.cu.h:33 */
+#define UG_MAX_SLABS 64    /* NUM_SLABS (main.cu.h:18) is 1 in the committed build; the code for more is there and so is ours */
 
 typedef struct ug_context ug_context;
 
@@ -86,6 +87,8 @@ typedef struct ug_frame_params {
 	                                 [strip_index*NBY/strip_count, (strip_index+1)*NBY/strip_count); 0,1 = whole frame */
 	int flags;          /* UG_FLAG_* */
 	int bounces;        /* row R: reflection bounces after shading (0 = the reference's committed display()); needs ug_model_set_reflect */
+	int num_slabs;      /* NUM_SLABS, main.cu.h:18: depth slabs of every grid; 0 or 1 = the committed configuration.  With more, span/offset
+	                       buffers hold one entry per (cell, slab) and primary rays follow rckernel_alpha's slab loop (trace_kernel.cu:132-229) */
 } ug_frame_params;
 
 #define UG_FLAG_FULL_BUFFERS 1 /* also fill the reference's normal/dir/shadowed buffers (decision_data.h:66-82) */
@@ -181,6 +184,7 @@ int ug_model_rotate_bunny(ug_context *ctx, float rot_factor);                   
 /* ---- per_frame_funcs.h, one call per reference function (state lives in ctx) */
 int ug_set_screen(ug_context *ctx, int width, int height, float fovy);            /* main.cu.h:10-30 made runtime */
 int ug_set_strip(ug_context *ctx, int strip_index, int strip_count);
+int ug_set_slabs(ug_context *ctx, int num_slabs);                                 /* main.cu.h:18 NUM_SLABS made runtime */
 int ug_update_light_position(ug_context *ctx, const float *xyz, int num_lights);  /* per_frame_funcs.h:6-16 */
 int ug_fill_coordinates_data(ug_context *ctx, const ug_camera *cam);              /* :18-43 (+ setDirectionTexture) */
 int ug_build_frustum_grid(ug_context *ctx);                                       /* :45-55 -> frustum_grid.h:210-366 */

@@ -45,6 +45,7 @@ class CpuLib:
         sig = {
             "configure": (None, [C.c_int] * 4),
             "set_threads": (None, [C.c_int]),
+            "set_slabs": (None, [C.c_int]),
             "get_threads": (C.c_int, []),
             "camera_setup": (None, [_f, C.c_float, C.c_float, C.c_int, _f]),
             "set_camcoords": (None, [_f]),
@@ -85,6 +86,11 @@ class CpuLib:
     def set_threads(self, n: int):
         self._set_threads(n)
 
+    def set_slabs(self, n: int):
+        """NUM_SLABS (main.cu.h:18; the committed value is 1): depth slabs of every grid."""
+        self.slabs = max(int(n), 1)
+        self._set_slabs(self.slabs)
+
     def get_threads(self) -> int:
         return self._get_threads()
 
@@ -124,7 +130,7 @@ class CpuLib:
     def build_grid(self, faces, verts, spherical=None) -> Dict[str, np.ndarray]:
         """`spherical` = (xM, yM) selects buildSphericalGrid (frustum_grid.h:368-532) instead of buildGrid (:210-366)."""
         T = faces.shape[0]
-        Cn = self.nbx * self.nby
+        Cn = self.nbx * self.nby * getattr(self, "slabs", 1)
         span = np.zeros(Cn, dtype=np.uint32)
         offset = np.zeros(Cn, dtype=np.uint32)
         dummy = np.zeros(1, dtype=np.uint32)
@@ -243,16 +249,17 @@ def reflect_table(scene) -> np.ndarray:
 
 def run_frame(lib: CpuLib, scene, frame: int = 0, threads: int = 0, stages: str = "all",
               timings: Optional[dict] = None, reflect: bool = False, spherical: bool = False,
-              spot: bool = False) -> Dict[str, np.ndarray]:
+              spot: bool = False, slabs: int = 1) -> Dict[str, np.ndarray]:
     """One display() (main.cu:59-302) on the CPU: [transform ->] camera grid -> primary rays -> per
     light (light camera, ray->cell map, light grid, shadow rays) -> shade -> shadow modulation.
     Returns every stage's output for bit-exact comparison.  `spherical` runs the per-light steps the way the committed
     display() does (main.cu:186-192: spherical ray map + spherical grid with x_max = y_max = M_PI) instead of the
     perspective variant north-star names; `spot` shades with spotlight_shade, as display() does from its third frame on
-    (main.cu:205-219)."""
+    (main.cu:205-219); `slabs` = NUM_SLABS (main.cu.h:18), the depth slabs of every grid."""
     sph = (np.float32(np.pi), np.float32(np.pi)) if spherical else None
     lib.configure(scene.width, scene.height, scene.fovy, 0)
     lib.set_threads(threads)
+    lib.set_slabs(slabs)
     faces = np.ascontiguousarray(scene.faces, dtype=np.int32)
     verts = np.ascontiguousarray(scene.verts, dtype=np.float32).copy()
     out: Dict[str, np.ndarray] = {}

@@ -23,7 +23,7 @@
 
 thread_local uint3 threadIdx, blockIdx;
 thread_local dim3 blockDim, gridDim;
-int g_ref_W = 1024, g_ref_H = 1024, g_ref_NBX = 128, g_ref_NBY = 128, g_ref_FOVY = 45;
+int g_ref_W = 1024, g_ref_H = 1024, g_ref_NBX = 128, g_ref_NBY = 128, g_ref_FOVY = 45, g_ref_SLABS = 1;
 float dd_camcoords[16 * 4];
 float dd_light_position[6];
 ref_texture texdir;
@@ -136,6 +136,7 @@ void ref_configure(int W, int H, int fovy, int tex_q8)
 	g_ref_W = W; g_ref_H = H; g_ref_NBX = W / NUM_THREADS_X; g_ref_NBY = H / NUM_THREADS_Y;
 	g_ref_FOVY = fovy; g_ref_tex_q8 = tex_q8;
 }
+void ref_set_slabs(int n) { g_ref_SLABS = n > 0 ? n : 1; }
 void ref_set_threads(int n) { g_threads = n > 0 ? n : omp_get_max_threads(); }
 int ref_get_threads(void) { return g_threads; }
 
@@ -314,7 +315,9 @@ void ref_map_rays_spherical(float *t_list, float *dir_list, unsigned *map, float
 	launch(NUM_BLOCKS_X, NUM_BLOCKS_Y, NUM_THREADS_X, NUM_THREADS_Y, [&] { mapSort_Effective_kernel(t_list, dir_list, map, cmPt, xM, yM); });
 }
 
-/* trace_kernel.cu:84-270 rckernel_alpha, per pixel.  Buffers as decision_data.h:66-82. */
+/* trace_kernel.cu:84-270 rckernel_alpha, one emulated CTA (8x8 tile) at a time: the per-ray state of its 64 threads is
+ * kept across the slab loop (:132-229) because the "beam done" flag metadata[3] couples them; within a slab every ray
+ * walks the cell's list calling the reference's own intersectTriUV / isWithin.  Buffers as decision_data.h:66-82. */
 void ref_trace(unsigned *value_list, unsigned *span, unsigned *offset, float *dd_normal, float *dd_t, float *dd_dir,
                int *dd_shadowed, int *dd_id, float *verts, int *tris)
 {
@@ -322,61 +325,74 @@ void ref_trace(unsigned *value_list, unsigned *span, unsigned *offset, float *dd
 #pragma omp parallel for schedule(dynamic, 64) num_threads(g_threads)
 	for (int cellrow = 0; cellrow < (W / 8) * (H / 8); cellrow++) {
 		const int bx = cellrow / NBY, by = cellrow % NBY;
-		for (int ty = 0; ty < 8; ty++)
-			for (int tx = 0; tx < 8; tx++) {
-				const int px = bx * 8 + tx, py = by * 8 + ty;
-				const int pixelID = py * W + px; /* :91 */
-				/* :96-114 */
-				float ftx = (float)px / (float)(NUM_BLOCKS_X * NUM_THREADS_X);
-				float fty = (float)py / (float)(NUM_BLOCKS_Y * NUM_THREADS_Y);
-				ftx = 1 - ftx;
-				ftx = ftx * (0.9 - 0.1) + 0.1;
-				fty = fty * (0.9 - 0.1) + 0.1;
-				float4 rayDir = tex2D(texdir, ftx, fty);
-				rayDir.x -= dd_camcoords[0]; rayDir.y -= dd_camcoords[1]; rayDir.z -= dd_camcoords[2];
-				float ray_direction[3] = {rayDir.x, rayDir.y, rayDir.z};
-				NORMALIZE(ray_direction);
-				int rayDone = 0;
-				float oldt = 99999999.9f, value, e1[3], e2[3];
-				int tri_intersected = -1;
-				const unsigned cell = bx * NBY + by; /* :138 blockIdx.x*gridDim.y+blockIdx.y */
-				const unsigned n = span[cell], off = offset[cell];
-				for (unsigned k = 0; k < n; k++) {
-					/* staging :153-174 */
-					const int curface = value_list[off + k];
-					const int f1 = 3 * tris[curface * 3 + 0], f2 = 3 * tris[curface * 3 + 1], f3 = 3 * tris[curface * 3 + 2];
-					float vd[9];
-					vd[0] = verts[f1 + 0]; vd[1] = verts[f1 + 1]; vd[2] = verts[f1 + 2];
-					vd[3] = verts[f2 + 0] - vd[0]; vd[4] = verts[f2 + 1] - vd[1]; vd[5] = verts[f2 + 2] - vd[2];
-					vd[6] = verts[f3 + 0] - vd[0]; vd[7] = verts[f3 + 1] - vd[1]; vd[8] = verts[f3 + 2] - vd[2];
-					vd[0] = dd_camcoords[0] - vd[0]; vd[1] = dd_camcoords[1] - vd[1]; vd[2] = dd_camcoords[2] - vd[2];
-					/* :181-203 */
-					float tmp_u, tmp_v;
-					value = intersectTriUV(&vd[0], &vd[3], &vd[6], ray_direction, oldt, &tmp_u, &tmp_v);
-					if (value) {
-						oldt = value; rayDone = 1; tri_intersected = off + k;
-						e1[0] = vd[3]; e1[1] = vd[4]; e1[2] = vd[5];
-						e2[0] = vd[6]; e2[1] = vd[7]; e2[2] = vd[8];
+		float ray_direction[64][3], oldt[64], e1[64][3], e2[64][3];
+		int rayDone[64], tri_intersected[64];
+		for (int th = 0; th < 64; th++) {
+			const int tx = th % 8, ty = th / 8, px = bx * 8 + tx, py = by * 8 + ty;
+			/* :96-114 */
+			float ftx = (float)px / (float)(NUM_BLOCKS_X * NUM_THREADS_X);
+			float fty = (float)py / (float)(NUM_BLOCKS_Y * NUM_THREADS_Y);
+			ftx = 1 - ftx;
+			ftx = ftx * (0.9 - 0.1) + 0.1;
+			fty = fty * (0.9 - 0.1) + 0.1;
+			float4 rayDir = tex2D(texdir, ftx, fty);
+			rayDir.x -= dd_camcoords[0]; rayDir.y -= dd_camcoords[1]; rayDir.z -= dd_camcoords[2];
+			ray_direction[th][0] = rayDir.x; ray_direction[th][1] = rayDir.y; ray_direction[th][2] = rayDir.z;
+			NORMALIZE(ray_direction[th]);
+			rayDone[th] = 0; oldt[th] = 99999999.9f; tri_intersected[th] = -1;
+			for (int k = 0; k < 3; k++) e1[th][k] = e2[th][k] = 0.0f;
+		}
+		int beam_done = 0; /* metadata[3], :131 */
+		for (int slab = 0; slab < NUM_SLABS; slab++) {
+			if (beam_done) continue; /* :134 */
+			const unsigned cell = (bx * NBY + by) * NUM_SLABS + slab; /* :138 (blockIdx.x*gridDim.y+blockIdx.y)*NUM_SLABS+slab */
+			const unsigned n = span[cell], off = offset[cell];
+			int all_done = 1;
+			for (int th = 0; th < 64; th++) {
+				if (rayDone[th] != 2) /* :179 */
+					for (unsigned k = 0; k < n; k++) {
+						/* staging :153-174 */
+						const int curface = value_list[off + k];
+						const int f1 = 3 * tris[curface * 3 + 0], f2 = 3 * tris[curface * 3 + 1], f3 = 3 * tris[curface * 3 + 2];
+						float vd[9];
+						vd[0] = verts[f1 + 0]; vd[1] = verts[f1 + 1]; vd[2] = verts[f1 + 2];
+						vd[3] = verts[f2 + 0] - vd[0]; vd[4] = verts[f2 + 1] - vd[1]; vd[5] = verts[f2 + 2] - vd[2];
+						vd[6] = verts[f3 + 0] - vd[0]; vd[7] = verts[f3 + 1] - vd[1]; vd[8] = verts[f3 + 2] - vd[2];
+						vd[0] = dd_camcoords[0] - vd[0]; vd[1] = dd_camcoords[1] - vd[1]; vd[2] = dd_camcoords[2] - vd[2];
+						/* :181-203 */
+						float tmp_u, tmp_v;
+						float value = intersectTriUV(&vd[0], &vd[3], &vd[6], ray_direction[th], oldt[th], &tmp_u, &tmp_v);
+						if (value) {
+							oldt[th] = value; rayDone[th] = 1; tri_intersected[th] = off + k;
+							e1[th][0] = vd[3]; e1[th][1] = vd[4]; e1[th][2] = vd[5];
+							e2[th][0] = vd[6]; e2[th][1] = vd[7]; e2[th][2] = vd[8];
+						}
 					}
-				}
-				rayDone = isWithin(rayDone, oldt, ray_direction, 0); /* :217 */
-				float *d_normals = &dd_normal[pixelID * 3];
-				if (rayDone == 2) { /* :232-253 */
-					NORMALIZE(e1); NORMALIZE(e2);
-					float normal[3];
-					CROSS(normal, e1, e2);
-					NORMALIZE(normal);
-					(normal[0] < 0) ? normal[0] *= -1 : normal[0] = normal[0];
-					(normal[1] < 0) ? normal[1] *= -1 : normal[1] = normal[1];
-					(normal[2] < 0) ? normal[2] *= -1 : normal[2] = normal[2];
-					dd_t[pixelID] = oldt; dd_shadowed[pixelID] = 0; dd_id[pixelID] = value_list[tri_intersected];
-					d_normals[0] = normal[0]; d_normals[1] = normal[1]; d_normals[2] = normal[2];
-				} else { /* :255-263 */
-					dd_t[pixelID] = -1.0f; dd_shadowed[pixelID] = 0; dd_id[pixelID] = -2;
-					d_normals[0] = -1.0f; d_normals[1] = -1.0f; d_normals[2] = -1.0f;
-				}
-				dd_dir[pixelID * 3 + 0] = ray_direction[0]; dd_dir[pixelID * 3 + 1] = ray_direction[1]; dd_dir[pixelID * 3 + 2] = ray_direction[2];
+				rayDone[th] = isWithin(rayDone[th], oldt[th], ray_direction[th], slab); /* :217 */
+				if (rayDone[th] != 2) all_done = 0;                                       /* :219-228 */
 			}
+			beam_done = all_done;
+		}
+		for (int th = 0; th < 64; th++) {
+			const int tx = th % 8, ty = th / 8, px = bx * 8 + tx, py = by * 8 + ty;
+			const int pixelID = py * W + px; /* :91 */
+			float *d_normals = &dd_normal[pixelID * 3];
+			if (rayDone[th] == 2) { /* :232-253 */
+				NORMALIZE(e1[th]); NORMALIZE(e2[th]);
+				float normal[3];
+				CROSS(normal, e1[th], e2[th]);
+				NORMALIZE(normal);
+				(normal[0] < 0) ? normal[0] *= -1 : normal[0] = normal[0];
+				(normal[1] < 0) ? normal[1] *= -1 : normal[1] = normal[1];
+				(normal[2] < 0) ? normal[2] *= -1 : normal[2] = normal[2];
+				dd_t[pixelID] = oldt[th]; dd_shadowed[pixelID] = 0; dd_id[pixelID] = value_list[tri_intersected[th]];
+				d_normals[0] = normal[0]; d_normals[1] = normal[1]; d_normals[2] = normal[2];
+			} else { /* :255-263 */
+				dd_t[pixelID] = -1.0f; dd_shadowed[pixelID] = 0; dd_id[pixelID] = -2;
+				d_normals[0] = -1.0f; d_normals[1] = -1.0f; d_normals[2] = -1.0f;
+			}
+			dd_dir[pixelID * 3 + 0] = ray_direction[th][0]; dd_dir[pixelID * 3 + 1] = ray_direction[th][1]; dd_dir[pixelID * 3 + 2] = ray_direction[th][2];
+		}
 	}
 }
 
@@ -407,8 +423,9 @@ void ref_shadow(unsigned *curflist, float *verts, int *tris, unsigned *blockcnt,
 		ptIntersection[0] = rayDirection[0]; ptIntersection[1] = rayDirection[1]; ptIntersection[2] = rayDirection[2];
 		rayDirection[0] -= dd_camcoords[0]; rayDirection[1] -= dd_camcoords[1]; rayDirection[2] -= dd_camcoords[2];
 		NORMALIZE(rayDirection);
-		const unsigned n = blockcnt[cell], off = blockcntscan[cell];
 		int done = 0;
+		for (int slab = 0; slab < NUM_SLABS && !done; slab++) { /* :105-115: the cell's list of every depth slab in turn */
+		const unsigned n = blockcnt[cell * NUM_SLABS + slab], off = blockcntscan[cell * NUM_SLABS + slab];
 		for (unsigned k = 0; k < n && !done; k++) {
 			/* staging :128-148 */
 			const int curface = curflist[off + k];
@@ -427,6 +444,7 @@ void ref_shadow(unsigned *curflist, float *verts, int *tris, unsigned *blockcnt,
 				pt[2] = dd_camcoords[2] + value * rayDirection[2];
 				if (isSmaller(pt, ptIntersection, dd_camcoords)) { done = 1; is_shadowed[pseudoPixelId] = 1; }
 			}
+		}
 		}
 	}
 }

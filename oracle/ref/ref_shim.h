@@ -38,14 +38,14 @@ static inline void __syncthreads() {}
 struct float4 { float x, y, z, w; };
 
 /* main.cu.h:10-42 as runtime values */
-extern int g_ref_W, g_ref_H, g_ref_NBX, g_ref_NBY, g_ref_FOVY;
+extern int g_ref_W, g_ref_H, g_ref_NBX, g_ref_NBY, g_ref_FOVY, g_ref_SLABS;
 #define SCREEN_WIDTH    g_ref_W
 #define SCREEN_HEIGHT   g_ref_H
 #define IMAGE_SIZE      (SCREEN_WIDTH * SCREEN_HEIGHT)
 #define FOVY            g_ref_FOVY
 #define NUM_BLOCKS_X    g_ref_NBX
 #define NUM_BLOCKS_Y    g_ref_NBY
-#define NUM_SLABS       1
+#define NUM_SLABS       g_ref_SLABS /* main.cu.h:18 compiles 1; ref_set_slabs exercises the code paths for more */
 #define NUM_THREADS_X   8
 #define NUM_THREADS_Y   8
 #define MAX_TRIANGLES   (NUM_THREADS_X * NUM_THREADS_Y)

@@ -16,6 +16,7 @@
 #define TILE 8 /* NUM_THREADS_X/Y, main.cu.h:24-25 */
 
 static int g_W = 1024, g_H = 1024, g_nbx = 128, g_nby = 128, g_fovy = 45, g_q8 = 0, g_threads = 1;
+static int g_slabs = 1;    /* NUM_SLABS, main.cu.h:18 (the committed value is 1) */
 static float g_cc[64];     /* dd_camcoords, main.cu.h:62; layout per_frame_funcs.h:18-39 */
 static float g_light[6];   /* dd_light_position, main.cu.h:63 */
 static float g_lattice[25][4]; /* texdir, main.cu.h:58 */
@@ -24,6 +25,7 @@ void orc_configure(int W, int H, int fovy, int tex_q8)
 {
 	g_W = W; g_H = H; g_nbx = W / TILE; g_nby = H / TILE; g_fovy = fovy; g_q8 = tex_q8;
 }
+void orc_set_slabs(int n) { g_slabs = n > 0 ? n : 1; }
 void orc_set_threads(int n) { g_threads = n > 0 ? n : omp_get_max_threads(); }
 int orc_get_threads(void) { return g_threads; }
 
@@ -304,20 +306,39 @@ void orc_grid_count_spherical(int *faces, float *verts, int T, unsigned *sizeLis
 static long build_grid(int mode, float xM, float yM, int *faces, float *verts, int T, unsigned *span, unsigned *offset, unsigned *key_list,
                        unsigned *value_list, long cap)
 {
-	const int C = g_nbx * g_nby;
+	const int S = g_slabs, C = g_nbx * g_nby * S;
 	int *rect = (int *)malloc(sizeof(int) * 4 * (size_t)(T > 0 ? T : 1));
+	float *projZ = (float *)malloc(sizeof(float) * (size_t)(T > 0 ? T : 1));
+	unsigned *slab = (unsigned *)calloc((size_t)(T > 0 ? T : 1), sizeof(unsigned)); /* d_zSlabs; the reference never initialises it: 0 here */
 	long P = 0;
 #pragma omp parallel for num_threads(g_threads) reduction(+ : P)
 	for (int t = 0; t < T; t++) {
-		float z;
-		tri_rect(mode, xM, yM, faces, verts, t, &rect[4 * t], &z);
+		tri_rect(mode, xM, yM, faces, verts, t, &rect[4 * t], &projZ[t]);
 		P += (unsigned)((rect[4 * t + 1] - rect[4 * t] + 1) * (rect[4 * t + 3] - rect[4 * t + 2] + 1));
 	}
-	if (P > cap) { free(rect); return P; }
+	if (P > cap) { free(rect); free(projZ); free(slab); return P; }
+	{
+		/* frustum_grid.h:221-241 (buildGrid) / :385-398 (buildSphericalGrid): host min/max of projCoordZ, then
+		 * grid_kernel.cu:334-352 SlabKernel; DSFillkernel clamps the slab again (:300-311) */
+		float zMin = mode ? 9999.9f : +2.0f, zMax = mode ? -9999.9f : -2.0f;
+		for (int i = 0; i < T; i++) {
+			if (zMin > projZ[i] && projZ[i] >= 0.0f) zMin = projZ[i];
+			if (zMax < projZ[i]) zMax = projZ[i];
+		}
+		for (int t = 0; t < T; t++) {
+			float pCoord = projZ[t];
+			if (pCoord >= 0.0f) {
+				unsigned binID = (unsigned)(long long)(S * (float)((pCoord - zMin) / (zMax - zMin))); /* cvttss2si r64, low half */
+				if (binID >= (unsigned)S) binID = (unsigned)S - 1;
+				slab[t] = binID;
+			}
+			slab[t] = (unsigned)clampi((int)slab[t], 0, S - 1);
+		}
+	}
 	memset(span, 0, sizeof(unsigned) * C);
 	for (int t = 0; t < T; t++)
 		for (int gx = rect[4 * t]; gx <= rect[4 * t + 1]; gx++)
-			for (int gy = rect[4 * t + 2]; gy <= rect[4 * t + 3]; gy++) span[gx * g_nby + gy]++;
+			for (int gy = rect[4 * t + 2]; gy <= rect[4 * t + 3]; gy++) span[(gx * g_nby + gy) * S + (int)slab[t]]++;
 	unsigned acc = 0;
 	for (int c = 0; c < C; c++) { offset[c] = acc; acc += span[c]; }
 	unsigned *cursor = (unsigned *)malloc(sizeof(unsigned) * C);
@@ -325,12 +346,14 @@ static long build_grid(int mode, float xM, float yM, int *faces, float *verts, i
 	for (int t = 0; t < T; t++) /* ascending t == emission order; stability keeps it inside a cell */
 		for (int gx = rect[4 * t]; gx <= rect[4 * t + 1]; gx++)
 			for (int gy = rect[4 * t + 2]; gy <= rect[4 * t + 3]; gy++) {
-				unsigned key = (unsigned)(gx * g_nby + gy), at = cursor[key]++;
+				unsigned key = (unsigned)((gx * g_nby + gy) * S) + slab[t], at = cursor[key]++; /* grid_kernel.cu:322 */
 				key_list[at] = key;
 				value_list[at] = (unsigned)t;
 			}
 	free(cursor);
 	free(rect);
+	free(projZ);
+	free(slab);
 	return P;
 }
 long orc_build_grid(int *faces, float *verts, int T, unsigned *span, unsigned *offset, unsigned *key_list, unsigned *value_list, long cap)
@@ -402,46 +425,65 @@ static int moller_trumbore(const float *tv, const float *e1, const float *e2, co
 void orc_trace(unsigned *value_list, unsigned *span, unsigned *offset, float *normal, float *t_out, float *dir_out,
                int *shadowed, int *id, float *verts, int *tris)
 {
+	const int S = g_slabs;
 #pragma omp parallel for schedule(dynamic, 16) num_threads(g_threads)
 	for (int cell = 0; cell < g_nbx * g_nby; cell++) {
 		const int bx = cell / g_nby, by = cell % g_nby; /* cell = gx*NBY + gy, trace_kernel.cu:138 */
-		const unsigned n = span[cell], off = offset[cell];
+		/* per-ray state of the tile's 64 threads (trace_kernel.cu:86,124-130): rayDone 0 = nothing yet, 1 = a hit whose depth
+		 * slab is not the one being walked, 2 = done */
+		float d[TILE * TILE][3], best[TILE * TILE], be1[TILE * TILE][3], be2[TILE * TILE][3];
+		int hit[TILE * TILE], rayDone[TILE * TILE];
+		for (int sub = 0; sub < TILE * TILE; sub++) {
+			primary_dir(bx * TILE + sub % TILE, by * TILE + sub / TILE, d[sub]);
+			best[sub] = 99999999.9f; hit[sub] = -1; rayDone[sub] = 0;
+			memset(be1[sub], 0, sizeof(be1[sub])); memset(be2[sub], 0, sizeof(be2[sub]));
+		}
+		int beamDone = 0; /* metadata[3] */
+		for (int slab = 0; slab < S; slab++) { /* :132 */
+			if (beamDone) continue;            /* :134 */
+			const unsigned n = span[cell * S + slab], off = offset[cell * S + slab]; /* :138-139 */
+			int all2 = 1;
+			for (int sub = 0; sub < TILE * TILE; sub++) {
+				if (rayDone[sub] != 2) /* :179 */
+					for (unsigned k = 0; k < n; k++) {
+						float tv[3], e1[3], e2[3], t;
+						stage_triangle(verts, tris, (int)value_list[off + k], g_cc, tv, e1, e2);
+						if (!moller_trumbore(tv, e1, e2, d[sub], &t)) continue;
+						if (t < 0) t *= -1;                /* trace_kernel.cu:35: |t| */
+						if (t < best[sub] && t > 0) {      /* :38 strict: first in list order wins ties */
+							best[sub] = t; hit[sub] = (int)(off + k); rayDone[sub] = 1;
+							memcpy(be1[sub], e1, sizeof(e1)); memcpy(be2[sub], e2, sizeof(e2));
+						}
+					}
+				/* isWithin, trace_kernel.cu:56-82: a ray that was done (2) or has nothing (0) becomes 0; a ray with a hit is
+				 * done iff floor(ndc_z * NUM_SLABS) is the slab being walked */
+				if (rayDone[sub] == 0 || rayDone[sub] == 2) rayDone[sub] = 0;
+				else {
+					float p[4] = {g_cc[0] + best[sub] * d[sub][0], g_cc[1] + best[sub] * d[sub][1], g_cc[2] + best[sub] * d[sub][2], 1.0f}, q[4];
+					mat4_mul_vec4(q, g_cc + 48, p);
+					q[2] /= q[3];
+					rayDone[sub] = (f2i(floorf(q[2] * S)) == slab) ? 2 : 1;
+				}
+				if (rayDone[sub] != 2) all2 = 0;
+			}
+			beamDone = all2; /* :219-228: the tile stops walking slabs once all 64 rays are done */
+		}
 		for (int sub = 0; sub < TILE * TILE; sub++) {
 			const int px = bx * TILE + sub % TILE, py = by * TILE + sub / TILE, pix = py * g_W + px;
-			float d[3], best = 99999999.9f, be1[3] = {0, 0, 0}, be2[3] = {0, 0, 0};
-			int hit = -1;
-			primary_dir(px, py, d);
-			for (unsigned k = 0; k < n; k++) {
-				float tv[3], e1[3], e2[3], t;
-				stage_triangle(verts, tris, (int)value_list[off + k], g_cc, tv, e1, e2);
-				if (!moller_trumbore(tv, e1, e2, d, &t)) continue;
-				if (t < 0) t *= -1;           /* trace_kernel.cu:35: |t| */
-				if (t < best && t > 0) {      /* :38 strict: first in list order wins ties */
-					best = t; hit = (int)(off + k);
-					memcpy(be1, e1, sizeof(be1)); memcpy(be2, e2, sizeof(be2));
-				}
-			}
-			int keep = 0;
-			if (hit >= 0) { /* isWithin, trace_kernel.cu:56-82: floor(ndc_z * NUM_SLABS) == slab 0 */
-				float p[4] = {g_cc[0] + best * d[0], g_cc[1] + best * d[1], g_cc[2] + best * d[2], 1.0f}, q[4];
-				mat4_mul_vec4(q, g_cc + 48, p);
-				q[2] /= q[3];
-				keep = (f2i(floorf(q[2] * 1)) == 0);
-			}
 			float *nrm = normal + 3 * (size_t)pix;
-			if (keep) { /* :232-253 */
+			if (rayDone[sub] == 2) { /* :232-253 */
 				float nn[3];
-				normalize3(be1); normalize3(be2);
-				cross3(nn, be1, be2);
+				normalize3(be1[sub]); normalize3(be2[sub]);
+				cross3(nn, be1[sub], be2[sub]);
 				normalize3(nn);
 				for (int k = 0; k < 3; k++) nrm[k] = (nn[k] < 0) ? nn[k] * -1 : nn[k];
-				t_out[pix] = best; id[pix] = (int)value_list[hit];
+				t_out[pix] = best[sub]; id[pix] = (int)value_list[hit[sub]];
 			} else {    /* :255-263 */
 				nrm[0] = nrm[1] = nrm[2] = -1.0f;
 				t_out[pix] = -1.0f; id[pix] = -2;
 			}
 			shadowed[pix] = 0;
-			memcpy(dir_out + 3 * (size_t)pix, d, sizeof(d));
+			memcpy(dir_out + 3 * (size_t)pix, d[sub], sizeof(d[sub]));
 		}
 	}
 }
@@ -511,9 +553,12 @@ void orc_shadow(unsigned *value_list, float *verts, int *tris, unsigned *span, u
 		normalize3(L);
 		const float dx = P[0] - g_cc[0], dy = P[1] - g_cc[1], dz = P[2] - g_cc[2];
 		const float dist_b = sqrtf(dx * dx + dy * dy + dz * dz);
-		for (unsigned k = 0; k < span[cell]; k++) {
+		/* light_kernel.cu:105-115: the cell's lists of all depth slabs, one after the other (an OR: the order is immaterial);
+		 * sorted keys make them one contiguous range */
+		const unsigned l_off = offset[cell * g_slabs], l_end = offset[cell * g_slabs + g_slabs - 1] + span[cell * g_slabs + g_slabs - 1];
+		for (unsigned k = 0; k < l_end - l_off; k++) {
 			float o[3], e1[3], e2[3], t;
-			stage_triangle(verts, tris, (int)value_list[offset[cell] + k], g_cc, o, e1, e2);
+			stage_triangle(verts, tris, (int)value_list[l_off + k], g_cc, o, e1, e2);
 			if (!moller_trumbore(o, e1, e2, L, &t)) continue;
 			if (!(t < 999999.9f) || t == 0) continue; /* light_kernel.cu:45-47 + `if (value)` :191 */
 			float q[3] = {g_cc[0] + t * L[0], g_cc[1] + t * L[1], g_cc[2] + t * L[2]};

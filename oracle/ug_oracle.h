@@ -20,6 +20,7 @@ extern "C" {
 #endif
 
 void orc_configure(int W, int H, int fovy, int tex_q8);
+void orc_set_slabs(int n); /* NUM_SLABS (main.cu.h:18), default 1: depth slabs of every grid, SURVEY 8f-3 */
 void orc_set_threads(int n);
 int orc_get_threads(void);
 void orc_camera_setup(const float *pose9, float nearP, float farP, int square_aspect, float *out_camcoords);

@@ -24,12 +24,12 @@ def bits(a: np.ndarray) -> np.ndarray:
     return a.view(np.uint32) if a.dtype == np.float32 else a
 
 
-def gpu_frame(r: "ug.Renderer", scene, frame=0, flags=ug.FLAG_FULL_BUFFERS, strip=(0, 1), stepwise=False, bounces=0):
+def gpu_frame(r: "ug.Renderer", scene, frame=0, flags=ug.FLAG_FULL_BUFFERS, strip=(0, 1), stepwise=False, bounces=0, slabs=1):
     """Render through the C-ABI and read every stage buffer back."""
     if stepwise:
-        r.render_stepwise(scene, spherical=bool(flags & ug.FLAG_SPHERICAL_LIGHTS), spot=bool(flags & ug.FLAG_SPOT_SHADE))
+        r.render_stepwise(scene, spherical=bool(flags & ug.FLAG_SPHERICAL_LIGHTS), spot=bool(flags & ug.FLAG_SPOT_SHADE), slabs=slabs)
     else:
-        r.render(r.params(scene, frame=frame, flags=flags, strip=strip, bounces=bounces))
+        r.render(r.params(scene, frame=frame, flags=flags, strip=strip, bounces=bounces, slabs=slabs))
     out = {"verts": r.read(ug.BUF_VERTEXLIST).reshape(-1, 3), "cam_values": r.read(ug.BUF_CAM_VALUES), "cam_span": r.read(ug.BUF_CAM_SPAN),
            "cam_offset": r.read(ug.BUF_CAM_OFFSET), "t": r.read(ug.BUF_T), "id": r.read(ug.BUF_ID), "shadowed": r.read(ug.BUF_SHADOWED),
            "rgb": r.read(ug.BUF_RGB)}

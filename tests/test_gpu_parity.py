@@ -26,8 +26,11 @@ def assert_frame(gpu, cpu, what):
     assert not bad, f"{what}: stages not bit-exact: {bad}"
 
 
-def cpu_frame(oracle, scene, frame=0, spherical=False, spot=False):
-    out = harness.run_frame(oracle, scene, frame=frame, threads=0, spherical=spherical, spot=spot)
+def cpu_frame(oracle, scene, frame=0, spherical=False, spot=False, slabs=1):
+    try:
+        out = harness.run_frame(oracle, scene, frame=frame, threads=0, spherical=spherical, spot=spot, slabs=slabs)
+    finally:
+        oracle.set_slabs(1)
     oracle.configure(scene.width, scene.height, scene.fovy, 0)
     oracle.camera_setup(scene.eye, scene.look, scene.up, scene.near, scene.far)
     out["sizelist"] = oracle.grid_count(np.ascontiguousarray(scene.faces, np.int32), np.ascontiguousarray(out["verts"], np.float32))[0]
@@ -103,6 +106,29 @@ def test_spot_shade(renderer, ug, oracle, case):
     if case == "a":
         plain = parity.gpu_frame(renderer, s)
         assert not np.array_equal(plain["rgb"], cpu["rgb"])     # the flag is part of the graph key: the plain shader is back
+
+
+@pytest.mark.parametrize("case,slabs,sph", [("ka", 4, False), ("soup2l", 8, False), ("hostile", 4, False), ("a", 4, False), ("a", 3, True), ("c", 2, True),
+                                            ("b", 4, False)])
+def test_depth_slabs(renderer, ug, oracle, case, slabs, sph):
+    """NUM_SLABS > 1: slab-keyed cell lists of every grid (SlabKernel, grid_kernel.cu:334-352, :322), primary rays
+    through rckernel_alpha's per-tile slab loop (trace_kernel.cu:132-229, its reset-by-isWithin quirk included), shadow rays
+    over the union of a light cell's slabs (light_kernel.cu:105-115) - all stages bit-exact against the oracle."""
+    s = {"ka": lambda: scenes.scene_tiny("ka"), "soup2l": lambda: scenes.scene_random(1, 2000, 128, 64, nlights=2),
+         "hostile": lambda: scenes.scene_hostile(77), "a": lambda: scenes.scene_a(), "c": lambda: scenes.scene_c(480, 272),
+         "b": lambda: scenes.scene_b()}[case]()
+    renderer.set_scene(s)
+    fl = ug.FLAG_FULL_BUFFERS | (ug.FLAG_SPHERICAL_LIGHTS if sph else 0)
+    cpu = cpu_frame(oracle, s, spherical=sph, slabs=slabs)
+    cpu.pop("sizelist", None)
+    C = (s.width // 8) * (s.height // 8)
+    gpu = parity.gpu_frame(renderer, s, flags=fl, slabs=slabs)
+    assert gpu["cam_span"].size == C * slabs
+    assert_frame(gpu, cpu, f"{s.name} {slabs} slabs (graph)")
+    if case in ("ka", "a"):
+        assert_frame(parity.gpu_frame(renderer, s, flags=fl | ug.FLAG_NO_GRAPH, slabs=slabs), cpu, f"{s.name} {slabs} slabs (direct launches)")
+        assert_frame(parity.gpu_frame(renderer, s, flags=fl, stepwise=True, slabs=slabs), cpu, f"{s.name} {slabs} slabs (per_frame_funcs call sequence)")
+        assert_frame(parity.gpu_frame(renderer, s, flags=fl), cpu_frame(oracle, s, spherical=sph), f"{s.name} back to one slab")
 
 
 def test_spherical_build_variants(renderer, ug, oracle, monkeypatch):

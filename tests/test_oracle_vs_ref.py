@@ -17,9 +17,9 @@ def same(a, b):
     return a.shape == b.shape and np.array_equal(parity.bits(a.reshape(-1)), parity.bits(b.reshape(-1)))
 
 
-def check_frame(ref, oracle, scene, frame=0, spherical=False, spot=False):
-    want = harness.run_frame(ref, scene, frame=frame, threads=0, spherical=spherical, spot=spot)
-    got = harness.run_frame(oracle, scene, frame=frame, threads=0, spherical=spherical, spot=spot)
+def check_frame(ref, oracle, scene, frame=0, spherical=False, spot=False, slabs=1):
+    want = harness.run_frame(ref, scene, frame=frame, threads=0, spherical=spherical, spot=spot, slabs=slabs)
+    got = harness.run_frame(oracle, scene, frame=frame, threads=0, spherical=spherical, spot=spot, slabs=slabs)
     assert set(want) == set(got)
     bad = [k for k in want if not same(want[k], got[k])]
     assert not bad, f"{scene.name}: oracle differs from the reference build in {bad}"
@@ -90,6 +90,32 @@ def test_spot_shade(ref, oracle, case):
     if case in ("ka", "a"):
         assert not same(out["rgb"], plain["rgb"])       # part of the image lies outside the cone and is dimmed to a quarter
     assert same(out["shadowed"], plain["shadowed"])
+
+
+@pytest.mark.parametrize("case,slabs,sph", [("ka", 4, False), ("a", 4, False), ("a", 3, True), ("soup1", 8, False), ("soup2", 2, True), ("hostile", 4, False)])
+def test_depth_slabs(ref, oracle, case, slabs, sph):
+    """NUM_SLABS > 1 (main.cu.h:18 compiles 1, the code for more is all there): SlabKernel (grid_kernel.cu:334-352) and the
+    slab part of the DSFillkernel key (:322) run VERBATIM in the reference build, isWithin / intersectTriUV verbatim inside
+    the per-tile slab loop of rckernel_alpha (trace_kernel.cu:132-229), the light kernel's slab loop (light_kernel.cu:105).
+    What that code computes includes its quirk: a ray that finished in slab s is reset by isWithin in slab s+1 unless the
+    whole tile finished - so hits are lost relative to one slab; shadows are an OR over all slabs and keep their meaning."""
+    s = {"ka": lambda: scenes.scene_tiny("ka"), "a": lambda: scenes.scene_a(256, 256),
+         "soup1": lambda: scenes.scene_random(1, 2000, 128, 64, nlights=2), "soup2": lambda: scenes.scene_random(3, 6000, 256, 256, nlights=1),
+         "hostile": lambda: scenes.scene_hostile(77)}[case]()
+    try:
+        out = check_frame(ref, oracle, s, spherical=sph, slabs=slabs)
+        one = harness.run_frame(oracle, s, threads=0, spherical=sph)
+    finally:
+        ref.set_slabs(1)
+        oracle.set_slabs(1)
+    C = (s.width // 8) * (s.height // 8)
+    assert out["cam_span"].size == C * slabs and out["cam_P"] == one["cam_P"]
+    # the slabs partition every cell's list: the same triangles per cell, grouped by slab
+    assert np.array_equal(out["cam_span"].reshape(C, slabs).sum(axis=1), one["cam_span"])
+    assert np.array_equal(np.sort(out["cam_values"]), np.sort(one["cam_values"]))
+    if case == "a":
+        assert (out["cam_span"].reshape(C, slabs) > 0).sum(axis=0).min() > 0           # every slab is used
+        assert 0 < (out["id"] >= 0).sum() <= (one["id"] >= 0).sum()
 
 
 def test_config_a_reduced(ref, oracle):

@@ -49,7 +49,7 @@ class FrameParams(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("fovy", C.c_float), ("nearPlane", C.c_float), ("farPlane", C.c_float),
                 ("eye", C.c_float * 3), ("look", C.c_float * 3), ("up", C.c_float * 3), ("num_lights", C.c_int),
                 ("lights", LightS * UG_MAX_LIGHTS), ("transform", C.c_int), ("rot_factor", C.c_float),
-                ("strip_index", C.c_int), ("strip_count", C.c_int), ("flags", C.c_int), ("bounces", C.c_int)]
+                ("strip_index", C.c_int), ("strip_count", C.c_int), ("flags", C.c_int), ("bounces", C.c_int), ("num_slabs", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -89,7 +89,7 @@ def lib() -> C.CDLL:
             "ug_model_set": (C.c_int, [vp, f, C.c_int, i, C.c_int, i, f, C.c_int]),
             "ug_obj_parse": (C.c_int, [C.c_char_p, i, i, f, i, i]), "ug_material_parse": (C.c_int, [C.c_char_p, i, f]),
             "ug_model_init_orig_list": (C.c_int, [vp, C.c_int, C.c_int]), "ug_model_set_reflect": (C.c_int, [vp, f, C.c_int]), "ug_model_rotate_bunny": (C.c_int, [vp, C.c_float]),
-            "ug_set_screen": (C.c_int, [vp, C.c_int, C.c_int, C.c_float]), "ug_set_strip": (C.c_int, [vp, C.c_int, C.c_int]),
+            "ug_set_screen": (C.c_int, [vp, C.c_int, C.c_int, C.c_float]), "ug_set_strip": (C.c_int, [vp, C.c_int, C.c_int]), "ug_set_slabs": (C.c_int, [vp, C.c_int]),
             "ug_update_light_position": (C.c_int, [vp, f, C.c_int]),
             "ug_fill_coordinates_data": (C.c_int, [vp, C.POINTER(Camera)]), "ug_build_frustum_grid": (C.c_int, [vp]),
             "ug_trace": (C.c_int, [vp]), "ug_shadow_pass": (C.c_int, [vp, C.c_int, C.POINTER(Camera)]),
@@ -236,7 +236,7 @@ class Renderer:
         return out
 
     # ---- frames
-    def params(self, scene=None, frame: int = 0, flags: int = 0, strip=(0, 1), bounces: int = 0) -> FrameParams:
+    def params(self, scene=None, frame: int = 0, flags: int = 0, strip=(0, 1), bounces: int = 0, slabs: int = 1) -> FrameParams:
         s = scene or self.scene
         p = FrameParams()
         p.width, p.height, p.fovy, p.nearPlane, p.farPlane = s.width, s.height, float(s.fovy), s.near, s.far
@@ -249,6 +249,7 @@ class Renderer:
         p.strip_index, p.strip_count = strip
         p.flags = flags
         p.bounces = bounces
+        p.num_slabs = slabs
         return p
 
     def render(self, p: FrameParams):
@@ -309,7 +310,7 @@ class Renderer:
         self._ck(self.L.ug_write_ppm(self.ctx, path.encode()), "ug_write_ppm")
 
     # ---- the reference's call-by-call sequence (display(), main.cu:59-302)
-    def render_stepwise(self, scene=None, spherical: bool = False, spot: bool = False):
+    def render_stepwise(self, scene=None, spherical: bool = False, spot: bool = False, slabs: int = 1):
         """The per_frame_funcs.h call sequence of display(), one C-ABI call per reference function; `spherical` selects the
         getEffectiveRayGridMapping / buildSphericalGrid variant with x_max = y_max = M_PI (main.cu:186-192)."""
         s = scene or self.scene
@@ -317,6 +318,7 @@ class Renderer:
         pi = float(np.float32(np.pi))
         self._ck(L.ug_set_light_grid_mode(self.ctx, LIGHT_GRID_SPHERICAL if spherical else LIGHT_GRID_PERSPECTIVE, pi, pi), "ug_set_light_grid_mode")
         self._ck(L.ug_set_screen(self.ctx, s.width, s.height, float(s.fovy)), "ug_set_screen")
+        self._ck(L.ug_set_slabs(self.ctx, slabs), "ug_set_slabs")
         self._ck(L.ug_set_strip(self.ctx, 0, 1), "ug_set_strip")
         lights = np.asarray([l.pos for l in s.lights], np.float32).reshape(-1)
         if len(s.lights):

@@ -164,9 +164,9 @@ void ug_direction_lattice(const float cc[64], float lattice[100])
 
 } // extern "C"
 
-void ugh_view_const(ViewConst *vc, const ug_camera *cam, int W, int H, int nbx, int nby, int gy_lo, int gy_cnt, int grid_mode, float xM, float yM)
+void ugh_view_const(ViewConst *vc, const ug_camera *cam, int W, int H, int nbx, int nby, int gy_lo, int gy_cnt, int grid_mode, float xM, float yM, int num_slabs)
 {
-	vc->grid_mode = grid_mode; vc->xM = xM; vc->yM = yM; vc->pad_ = 0;
+	vc->grid_mode = grid_mode; vc->xM = xM; vc->yM = yM; vc->num_slabs = num_slabs > 0 ? num_slabs : 1;
 	ug_camera_pack(cam, vc->cc);
 	ug_direction_lattice(vc->cc, vc->lattice);
 	/* misc_kernel.cu:115: tanf(FOVY*M_PI/360.0f) - int*double/float -> double, narrowed to tanf's float argument */

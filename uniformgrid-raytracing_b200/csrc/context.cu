@@ -116,6 +116,7 @@ static void free_grid(GridBuffers &g)
 	dfree(g.span); dfree(g.offset); dfree(g.counters);
 	dfree(g.sort.tile_hist); dfree(g.sort.tile_base); dfree(g.sort.scan_state);
 	dfree(g.fused_hist); dfree(g.fused_tot); dfree(g.fused_state_a); dfree(g.fused_state_b);
+	dfree(g.projz); dfree(g.zrange); dfree(g.cspan); dfree(g.coffset);
 	g = GridBuffers();
 }
 static void free_rays(LightRays &r)
@@ -196,12 +197,19 @@ extern "C" int ug_synchronize(ug_context *ctx)
 }
 
 /* ------------------------------------------------------------------ arenas */
-static int alloc_grid(ug_context *ctx, GridBuffers &g, int T, int C, size_t cap)
+static int alloc_grid(ug_context *ctx, GridBuffers &g, int T, int C, size_t cap, int S = 0)
 {
-	if (g.T == T && g.C == C && g.cap >= cap && g.tri_rec) return UG_OK;
+	if (S <= 0) S = g.S > 0 ? g.S : 1; /* regrowing keeps the slab count; C counts (cell, slab) entries */
+	if (g.T == T && g.C == C && g.S == S && g.cap >= cap && g.tri_rec) return UG_OK;
 	const size_t keep_cap = g.cap > cap ? g.cap : cap;
 	free_grid(g);
-	g.T = T; g.C = C; g.cap = keep_cap;
+	g.T = T; g.C = C; g.cap = keep_cap; g.S = S; g.cells = C / S;
+	if (S > 1) {
+		UG_CUDA(ctx, dmalloc(&g.projz, (size_t)T));
+		UG_CUDA(ctx, dmalloc(&g.zrange, 4));
+		UG_CUDA(ctx, dmalloc(&g.cspan, (size_t)g.cells + 1));
+		UG_CUDA(ctx, dmalloc(&g.coffset, (size_t)g.cells + 1));
+	}
 	g.key_bits = bits_for((unsigned)C);
 	UG_CUDA(ctx, dmalloc(&g.tri_rec, 4 * (size_t)T));
 	UG_CUDA(ctx, dmalloc(&g.rect, (size_t)T));
@@ -343,16 +351,17 @@ static int ensure_buffers(ug_context *ctx, int num_lights, bool full, int bounce
 		for (int l = 0; l < UG_MAX_LIGHTS; l++) free_rays(ctx->rays[l]); /* sized by N */
 		changed = true;
 	}
-	if (ctx->cam_grid.T != T || ctx->cam_grid.C != ctx->C_cam || !ctx->cam_grid.tri_rec) {
-		int rc = alloc_grid(ctx, ctx->cam_grid, T, ctx->C_cam, default_cap(T, ctx->C_cam));
+	const int S = ctx->num_slabs;
+	if (ctx->cam_grid.T != T || ctx->cam_grid.C != ctx->C_cam * S || ctx->cam_grid.S != S || !ctx->cam_grid.tri_rec) {
+		int rc = alloc_grid(ctx, ctx->cam_grid, T, ctx->C_cam * S, default_cap(T, ctx->C_cam * S), S);
 		if (rc) return rc;
 		UG_CUDA(ctx, dmalloc(&ctx->d_cell_done, (size_t)ctx->C_cam));
 		UG_CUDA(ctx, cudaMemset(ctx->d_cell_done, 0, sizeof(u32) * (size_t)ctx->C_cam));
 		changed = true;
 	}
 	for (int l = 0; l < num_lights; l++) {
-		if (ctx->light_grid[l].T != T || ctx->light_grid[l].C != ctx->C_light || !ctx->light_grid[l].tri_rec) {
-			int rc = alloc_grid(ctx, ctx->light_grid[l], T, ctx->C_light, default_cap(T, ctx->C_light));
+		if (ctx->light_grid[l].T != T || ctx->light_grid[l].C != ctx->C_light * S || ctx->light_grid[l].S != S || !ctx->light_grid[l].tri_rec) {
+			int rc = alloc_grid(ctx, ctx->light_grid[l], T, ctx->C_light * S, default_cap(T, ctx->C_light * S), S);
 			if (rc) return rc;
 			free_rays(ctx->rays[l]);
 			changed = true;
@@ -586,6 +595,14 @@ extern "C" int ug_set_screen(ug_context *ctx, int width, int height, float fovy)
 	return UG_OK;
 }
 
+/* NUM_SLABS (main.cu.h:18) made runtime: every grid is built with that many depth slabs from now on */
+extern "C" int ug_set_slabs(ug_context *ctx, int num_slabs)
+{
+	if (!ctx || num_slabs < 1 || num_slabs > UG_MAX_SLABS) return ug_fail(ctx, UG_ERR_ARG, "num_slabs %d not in [1,%d]", num_slabs, UG_MAX_SLABS);
+	if (ctx->num_slabs != num_slabs) { ctx->num_slabs = num_slabs; ctx->frame_valid = false; }
+	return UG_OK;
+}
+
 extern "C" int ug_set_strip(ug_context *ctx, int strip_index, int strip_count)
 {
 	if (!ctx || strip_count <= 0 || strip_index < 0 || strip_index >= strip_count) return ug_fail(ctx, UG_ERR_ARG, "bad strip %d/%d", strip_index, strip_count);
@@ -604,7 +621,9 @@ static void enqueue_grid(ug_context *ctx, cudaStream_t s, const ViewConst *vc, G
 {
 	const int sms = ctx->num_sms;
 	const bool want_fused = (&g == &ctx->cam_grid) ? ctx->fused_cam_now : ctx->fused_grid_now;
-	if (ctx->use_fused && want_fused && g.key_bits <= 32) {
+	if (g.S > 1) { /* depth slabs: kernel chain only - the slab of a triangle needs the z range of ALL triangles before any pair is emitted */
+		ugk_slab_reset(s, vc, g);                                                                       L.n += 1;
+	} else if (ctx->use_fused && want_fused && g.key_bits <= 32) {
 		const int fb = ugk_grid_fused(s, vc, ctx->d_facelist, ctx->d_vertexlist, g, sms);
 		if (fb >= 0) { g.final_buf = fb; L.n += 1; return; }
 		cudaGetLastError();   /* cooperative launch refused: fall back to the multi-kernel chain for good */
@@ -615,6 +634,7 @@ static void enqueue_grid(ug_context *ctx, cudaStream_t s, const ViewConst *vc, G
 	ugk_emit_pairs(s, vc, g, sms);                                                                      L.n += 1;
 	g.final_buf = ugk_radix_sort_pairs(s, g.keys, g.vals, g.counters, g.cap, g.key_bits, g.sort, sms, &L.n);
 	ugk_cell_offsets(s, g, sms);                                                                        L.n += 1;
+	if (g.S > 1 && &g != &ctx->cam_grid) { ugk_slab_union(s, g, sms);                                   L.n += 1; }
 }
 
 /* main.cu:148-203 for one light, after its ViewConst is resident: ray->cell map, light grid, regroup, shadow rays */
@@ -712,7 +732,8 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 	ugk_stamp(s, tl, 1);
 	if (parallel) UG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_init, 0));
 	stage_mark(ctx, k, stage_events); /* 2: camera grid done */
-	ugk_trace(s, ctx->d_fc, ctx->cam_grid, ctx->d_best, ctx->d_cell_done, ctx->d_dir, ctx->d_t, ctx->d_id, full ? ctx->d_normal : nullptr, sms);
+	if (ctx->cam_grid.S > 1) ugk_trace_slabs(s, ctx->d_fc, ctx->cam_grid, ctx->d_dir, ctx->d_t, ctx->d_id, full ? ctx->d_normal : nullptr, ctx->C_cam, sms);
+	else ugk_trace(s, ctx->d_fc, ctx->cam_grid, ctx->d_best, ctx->d_cell_done, ctx->d_dir, ctx->d_t, ctx->d_id, full ? ctx->d_normal : nullptr, sms);
 	L.n += 1;
 	ugk_stamp(s, tl, 2);
 	stage_mark(ctx, k, stage_events); /* 3: primary rays done */
@@ -819,6 +840,8 @@ static int prepare_frame(ug_context *ctx, const ug_frame_params *p)
 	if (p->bounces < 0 || p->bounces > UG_MAX_BOUNCES) return ug_fail(ctx, UG_ERR_ARG, "bounces %d not in [0,%d]", p->bounces, UG_MAX_BOUNCES);
 	int rc = ug_set_screen(ctx, p->width, p->height, p->fovy);
 	if (rc) return rc;
+	rc = ug_set_slabs(ctx, p->num_slabs > 0 ? p->num_slabs : 1);
+	if (rc) return rc;
 	rc = ug_set_strip(ctx, p->strip_count > 0 ? p->strip_index : 0, p->strip_count > 0 ? p->strip_count : 1);
 	if (rc) return rc;
 	rc = ensure_buffers(ctx, p->num_lights, (p->flags & UG_FLAG_FULL_BUFFERS) != 0, ctx->d_reflect ? p->bounces : 0);
@@ -835,7 +858,7 @@ static int prepare_frame(ug_context *ctx, const ug_frame_params *p)
 	cam.fovy = p->fovy;
 	cam.aspect = (float)p->width / (float)p->height; /* camera.h:137 */
 	ug_camera_adjustCameraAndPosition(&cam);
-	ugh_view_const(&fc->cam, &cam, ctx->W, ctx->H, ctx->nbx, ctx->nby, ctx->gy_lo, ctx->gy_cnt);
+	ugh_view_const(&fc->cam, &cam, ctx->W, ctx->H, ctx->nbx, ctx->nby, ctx->gy_lo, ctx->gy_cnt, UG_LIGHT_GRID_PERSPECTIVE, 0.0f, 0.0f, ctx->num_slabs);
 	memcpy(fc->shade_mv, cam.modelview_matrix, sizeof(fc->shade_mv));
 	memcpy(fc->shade_eye, cam.worldori, sizeof(fc->shade_eye));
 	for (int l = 0; l < p->num_lights; l++) {
@@ -850,7 +873,7 @@ static int prepare_frame(ug_context *ctx, const ug_frame_params *p)
 		ug_camera_adjustCameraAndPosition(&lc);
 		/* main.cu:186-187: x_max = y_max = M_PI, narrowed to the float parameters of the two calls that follow */
 		ugh_view_const(&fc->light[l], &lc, ctx->W, ctx->H, ctx->nbx, ctx->nby, 0, ctx->nby,
-		               (p->flags & UG_FLAG_SPHERICAL_LIGHTS) ? UG_LIGHT_GRID_SPHERICAL : UG_LIGHT_GRID_PERSPECTIVE, (float)M_PI, (float)M_PI);
+		               (p->flags & UG_FLAG_SPHERICAL_LIGHTS) ? UG_LIGHT_GRID_SPHERICAL : UG_LIGHT_GRID_PERSPECTIVE, (float)M_PI, (float)M_PI, ctx->num_slabs);
 		for (int k = 0; k < 3; k++) fc->light_pos[3 * l + k] = p->lights[l].pos[k];
 		/* shading runs with the LAST light camera's modelview resident in dd_camcoords (main.cu:205-211) */
 		memcpy(fc->shade_mv, lc.modelview_matrix, sizeof(fc->shade_mv));
@@ -873,6 +896,7 @@ static unsigned long long frame_key(const ug_context *ctx, const ug_frame_params
 	mix((unsigned long long)(p->transform && ctx->d_vertex_orig_list ? 1 : 0)); mix((unsigned long long)ctx->cam_grid.cap);
 	for (int l = 0; l < p->num_lights; l++) mix((unsigned long long)ctx->light_grid[l].cap);
 	mix((unsigned long long)(p->bounces > 0 && ctx->d_reflect ? p->bounces : 0)); mix((unsigned long long)ctx->refl.grid.cap);
+	mix((unsigned long long)ctx->num_slabs);
 	mix((unsigned long long)(uintptr_t)ctx->comm); mix((unsigned long long)(uintptr_t)ctx->d_rgb_full);
 	mix((unsigned long long)(uintptr_t)ctx->peer_full); mix((unsigned long long)ctx->use_push);
 	mix((unsigned long long)(uintptr_t)ctx->stream); mix((unsigned long long)(uintptr_t)ctx->d_rgb);
@@ -998,7 +1022,7 @@ extern "C" int ug_fill_coordinates_data(ug_context *ctx, const ug_camera *cam)
 	if (ctx->W <= 0) return ug_fail(ctx, UG_ERR_ARG, "fillCoordinatesData: ug_set_screen first");
 	UG_CUDA(ctx, cudaSetDevice(ctx->device));
 	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	ugh_view_const(&ctx->h_fc->cam, cam, ctx->W, ctx->H, ctx->nbx, ctx->nby, ctx->gy_lo, ctx->gy_cnt);
+	ugh_view_const(&ctx->h_fc->cam, cam, ctx->W, ctx->H, ctx->nbx, ctx->nby, ctx->gy_lo, ctx->gy_cnt, UG_LIGHT_GRID_PERSPECTIVE, 0.0f, 0.0f, ctx->num_slabs);
 	memcpy(ctx->h_fc->shade_mv, cam->modelview_matrix, sizeof(ctx->h_fc->shade_mv));
 	memcpy(ctx->h_fc->shade_eye, cam->worldori, sizeof(ctx->h_fc->shade_eye));
 	return upload_consts(ctx);
@@ -1029,7 +1053,8 @@ extern "C" int ug_trace(ug_context *ctx)
 	int rc = ensure_buffers(ctx, ctx->num_lights, true);
 	if (rc) return rc;
 	ugk_init_pixels(ctx->stream, ctx->d_fc, ctx->d_t, ctx->d_id, ctx->d_shadowed, ctx->d_best, ctx->d_normal, ctx->d_dir, ctx->N, ctx->num_sms);
-	ugk_trace(ctx->stream, ctx->d_fc, ctx->cam_grid, ctx->d_best, ctx->d_cell_done, ctx->d_dir, ctx->d_t, ctx->d_id, ctx->d_normal, ctx->num_sms);
+	if (ctx->cam_grid.S > 1) ugk_trace_slabs(ctx->stream, ctx->d_fc, ctx->cam_grid, ctx->d_dir, ctx->d_t, ctx->d_id, ctx->d_normal, ctx->C_cam, ctx->num_sms);
+	else ugk_trace(ctx->stream, ctx->d_fc, ctx->cam_grid, ctx->d_best, ctx->d_cell_done, ctx->d_dir, ctx->d_t, ctx->d_id, ctx->d_normal, ctx->num_sms);
 	UG_CUDA(ctx, cudaGetLastError());
 	return UG_OK;
 }
@@ -1042,7 +1067,7 @@ extern "C" int ug_shadow_pass(ug_context *ctx, int light_id, const ug_camera *li
 	int rc = ensure_buffers(ctx, ctx->num_lights, ctx->full_alloc);
 	if (rc) return rc;
 	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	ugh_view_const(&ctx->h_fc->light[light_id], light_cam, ctx->W, ctx->H, ctx->nbx, ctx->nby, 0, ctx->nby, ctx->light_grid_mode, ctx->light_xM, ctx->light_yM);
+	ugh_view_const(&ctx->h_fc->light[light_id], light_cam, ctx->W, ctx->H, ctx->nbx, ctx->nby, 0, ctx->nby, ctx->light_grid_mode, ctx->light_xM, ctx->light_yM, ctx->num_slabs);
 	memcpy(ctx->h_fc->shade_mv, light_cam->modelview_matrix, sizeof(ctx->h_fc->shade_mv)); /* fillCoordinatesData with the light camera */
 	memcpy(ctx->h_fc->shade_eye, light_cam->worldori, sizeof(ctx->h_fc->shade_eye));
 	rc = upload_consts(ctx);

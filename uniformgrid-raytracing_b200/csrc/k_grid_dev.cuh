@@ -56,13 +56,14 @@ static __device__ __forceinline__ int ug_effective_y(const float *cc, float vx, 
 	return (int)ug_f2u(upd > 0.0f ? half + part : half - part);
 }
 /* cell of one vertex, grid_kernel.cu:500-527: direction from the light, divided (not multiplied) by its length */
-static __device__ __forceinline__ void ug_sph_vertex(const float *cc, const GridGeo &g, float x, float y, float z, int &bx, int &by)
+static __device__ __forceinline__ float ug_sph_vertex(const float *cc, const GridGeo &g, float x, float y, float z, int &bx, int &by)
 {
 	float px = x - cc[0], py = y - cc[1], pz = z - cc[2];
 	const float radius = sqrtf(px * px + py * py + pz * pz);
 	px /= radius; py /= radius; pz /= radius;
 	bx = ug_effective_x(cc, px, py, pz, g.xM, g.nbx);
 	by = ug_effective_y(cc, px, py, pz, g.yM, g.nby);
+	return radius;
 }
 static __device__ __forceinline__ int ug_imin3(int a, int b, int c) { return (a < b) ? ((a < c) ? a : c) : ((b < c) ? b : c); }
 static __device__ __forceinline__ int ug_imax3(int a, int b, int c) { return (a > b) ? ((a > c) ? a : c) : ((b > c) ? b : c); }
@@ -70,12 +71,13 @@ static __device__ __forceinline__ int ug_imax3(int a, int b, int c) { return (a 
  * wrap branch of size_x/size_y (:627-639) is algebraically gmax-gmin+1.  Kept out of line: the perspective path's
  * register budget (the fused cooperative build) must not pay for it. */
 static __device__ __noinline__ void ug_sph_rect(const float *cc, const GridGeo &g, const float *p0, const float *p1, const float *p2, int &gx0, int &gx1, int &gy0,
-                                               int &gy1)
+                                               int &gy1, float &zmin)
 {
 	int x0, y0, x1, y1, x2, y2;
-	ug_sph_vertex(cc, g, p0[0], p0[1], p0[2], x0, y0);
-	ug_sph_vertex(cc, g, p1[0], p1[1], p1[2], x1, y1);
-	ug_sph_vertex(cc, g, p2[0], p2[1], p2[2], x2, y2);
+	const float r0 = ug_sph_vertex(cc, g, p0[0], p0[1], p0[2], x0, y0);
+	const float r1 = ug_sph_vertex(cc, g, p1[0], p1[1], p1[2], x1, y1);
+	const float r2 = ug_sph_vertex(cc, g, p2[0], p2[1], p2[2], x2, y2);
+	zmin = ug_min3(r0, r1, r2); /* grid_kernel.cu:613: projCoordZ = the nearest vertex's distance */
 	gx0 = ug_clampi(ug_imin3(x0, x1, x2), 0, g.nbx - 1);
 	gy0 = ug_clampi(ug_imin3(y0, y1, y2), 0, g.nby - 1);
 	gx1 = ug_clampi(ug_imax3(x0, x1, x2), 0, g.nbx - 1);
@@ -86,7 +88,7 @@ static __device__ __noinline__ void ug_sph_rect(const float *cc, const GridGeo &
  * light_kernel.cu:133-148 staging arithmetic + the hoisted qvec and dot(e2,qvec)), its clamped cell
  * rectangle (grid_kernel.cu:180-229) clipped to the owned cell rows, and its pair count (:231). */
 static __device__ __forceinline__ u32 ug_tri_setup(const float *s_cc, const GridGeo &g, const int *__restrict__ faces, const float *__restrict__ verts, int t,
-                                                   float4 *__restrict__ rec, uint2 *__restrict__ rect)
+                                                   float4 *__restrict__ rec, uint2 *__restrict__ rect, float *zmin_out = nullptr)
 {
 	const int i0 = faces[3 * t], i1 = faces[3 * t + 1], i2 = faces[3 * t + 2];
 	const float *p0 = verts + 3 * (size_t)i0, *p1 = verts + 3 * (size_t)i1, *p2 = verts + 3 * (size_t)i2;
@@ -104,8 +106,9 @@ static __device__ __forceinline__ u32 ug_tri_setup(const float *s_cc, const Grid
 	rec[4 * (size_t)t + 2] = make_float4(e2x, e2y, e2z, 0.0f);
 	rec[4 * (size_t)t + 3] = make_float4(qx, qy, qz, 0.0f);
 	int gx0, gy0, gx1, gy1;
+	float zmin;
 	if (g.mode == UG_LIGHT_GRID_SPHERICAL) {
-		ug_sph_rect(s_cc, g, p0, p1, p2, gx0, gx1, gy0, gy1);
+		ug_sph_rect(s_cc, g, p0, p1, p2, gx0, gx1, gy0, gy1, zmin);
 	} else {
 		float n0x, n0y, n0z, n1x, n1y, n1z, n2x, n2y, n2z;
 		ug_project(s_cc, ax, ay, az, n0x, n0y, n0z);
@@ -117,13 +120,43 @@ static __device__ __forceinline__ u32 ug_tri_setup(const float *s_cc, const Grid
 		gy0 = ug_clampi(ug_f2i(floorf(((ymin + 1.0f) / 2.0f) * (float)g.nby)), 0, g.nby - 1);
 		gx1 = ug_clampi(ug_f2i(floorf(((xmax + 1.0f) / 2.0f) * (float)g.nbx)), 0, g.nbx - 1);
 		gy1 = ug_clampi(ug_f2i(floorf(((ymax + 1.0f) / 2.0f) * (float)g.nby)), 0, g.nby - 1);
+		zmin = ug_min3(n0z, n1z, n2z); /* grid_kernel.cu:203,211 projCoordZ */
 	}
+	if (zmin_out) *zmin_out = zmin;
 	/* image-strip sharding: keep only the owned cell rows; the rectangle itself is the global one */
 	const int ry0 = max(gy0, g.gy_lo), ry1 = min(gy1, g.gy_hi);
 	const int sx = gx1 - gx0 + 1, sy = ry1 - ry0 + 1;
 	const u32 c = (sx > 0 && sy > 0) ? (u32)(sx * sy) : 0u; /* NaN vertices can invert the rectangle: no cells */
 	rect[t] = make_uint2((u32)gx0 | ((u32)gx1 << 16), (u32)ry0 | ((u32)(c ? ry1 : ry0) << 16));
 	return c;
+}
+
+/* ---- depth slabs (NUM_SLABS > 1).  frustum_grid.h:227-235 reduces projCoordZ on the host:
+ *   zMin = min(init, min{z : z >= 0}),  zMax = max(init, max z)   (NaN never wins a comparison)
+ * here as atomics on zrange[0] (bits of a non-negative float order like the float) and zrange[1] (order-preserving code). */
+static __device__ __forceinline__ u32 ug_fenc(float f) { const u32 b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+static __device__ __forceinline__ float ug_fdec(u32 e) { return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e); }
+static __device__ __forceinline__ void ug_zrange_add(u32 *zrange, float z)
+{
+	u32 lo = 0xffffffffu, hi = 0u;
+	if (z >= 0.0f) lo = __float_as_uint(z + 0.0f); /* -0 -> +0 */
+	if (z == z) hi = ug_fenc(z + 0.0f);
+	lo = __reduce_min_sync(UG_FULL_MASK, lo);
+	hi = __reduce_max_sync(UG_FULL_MASK, hi);
+	if (ug_lane() == 0) {
+		if (lo != 0xffffffffu) atomicMin(&zrange[0], lo);
+		if (hi != 0u) atomicMax(&zrange[1], hi);
+	}
+}
+/* grid_kernel.cu:334-352 SlabKernel + the clamp of DSFillkernel (:300-311); a triangle SlabKernel skips (z < 0 or NaN) keeps
+ * whatever d_zSlabs held - never initialised in the reference, 0 here */
+static __device__ __forceinline__ u32 ug_slab_of(float p, const u32 *__restrict__ zrange, int S)
+{
+	if (!(p >= 0.0f)) return 0u;
+	const float zMin = __uint_as_float(zrange[0]), zMax = ug_fdec(zrange[1]);
+	u32 bin = ug_f2u((float)S * ((p - zMin) / (zMax - zMin)));
+	if (bin >= (u32)S) bin = (u32)S - 1u;
+	return (u32)ug_clampi((int)bin, 0, S - 1);
 }
 
 /* first index in [lo,hi) with a[idx] > x */

@@ -316,7 +316,7 @@ bool ugk_regroup(cudaStream_t s, const FrameConst *fc, int light, const GridBuff
                  int sms, bool fused, int *launches)
 {
 	RegroupArgs a;
-	a.fc = fc; a.light = light; a.N = N; a.C = C; a.t = t; a.dir = dir; a.grid_span = g.span;
+	a.fc = fc; a.light = light; a.N = N; a.C = C; a.t = t; a.dir = dir; a.grid_span = g.cell_span();
 	a.light_cell = r.cell; a.ray_span = r.span; a.ray_offset = r.offset; a.cursor = r.cursor; a.ray_pix = r.pix;
 	a.item_off = r.item_off; a.items = r.items; a.counters = r.counters; a.state_a = r.state_a; a.state_b = r.state_b;
 	a.item_cap = (u32)r.item_cap;
@@ -342,6 +342,6 @@ void ugk_shadow(cudaStream_t s, const FrameConst *fc, int light, const GridBuffe
 	if (C <= 0 || N <= 0) return;
 	const size_t want = (r.item_cap + SH_WARPS - 1) / SH_WARPS;
 	const unsigned blocks = (unsigned)(want < (size_t)sms * 16 ? want : (size_t)sms * 16);
-	k_shadow<<<blocks, 32 * SH_WARPS, 0, s>>>(fc, light, g.span, g.offset, g.vals[g.final_buf], g.tri_rec, r.pix, r.span, r.offset, r.items, r.counters, t,
+	k_shadow<<<blocks, 32 * SH_WARPS, 0, s>>>(fc, light, g.cell_span(), g.cell_offset(), g.vals[g.final_buf], g.tri_rec, r.pix, r.span, r.offset, r.items, r.counters, t,
 	                                          dir, shadowed);
 }

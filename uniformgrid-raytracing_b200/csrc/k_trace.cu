@@ -52,15 +52,31 @@ __global__ void __launch_bounds__(256) k_init_pixels(const FrameConst *__restric
 	}
 }
 
-/* isWithin (trace_kernel.cu:56-82, NUM_SLABS 1) + write-out (:232-253) of one pixel's final hit */
-static __device__ __forceinline__ void finalize_pixel(const float *cc, float dx, float dy, float dz, float best, u32 tri, int pix,
-                                                      const float4 *__restrict__ rec, float *__restrict__ out_t, int *__restrict__ out_id,
-                                                      float *__restrict__ out_normal)
+/* the depth slab isWithin (trace_kernel.cu:56-82) assigns to the point at distance `best` along the ray: floor(ndc_z * NUM_SLABS) */
+static __device__ __forceinline__ int hit_slab(const float *cc, float dx, float dy, float dz, float best, int S)
 {
 	const float X = cc[0] + best * dx, Y = cc[1] + best * dy, Z = cc[2] + best * dz;
 	const float *M = cc + 48;
 	const float z = ug_row(M, 2, X, Y, Z, 1.0f) / ug_row(M, 3, X, Y, Z, 1.0f);
-	if (ug_f2i(floorf(z * 1.0f)) != 0) return; /* outside NDC z [0,1): stays a miss, even if a farther hit existed */
+	return ug_f2i(floorf(z * (float)S));
+}
+
+/* write-out (trace_kernel.cu:232-253) of one pixel's final hit */
+static __device__ __forceinline__ void write_hit(float best, u32 tri, int pix, const float4 *__restrict__ rec, float *__restrict__ out_t, int *__restrict__ out_id,
+                                                 float *__restrict__ out_normal);
+
+/* isWithin (NUM_SLABS 1) + write-out of one pixel's final hit */
+static __device__ __forceinline__ void finalize_pixel(const float *cc, float dx, float dy, float dz, float best, u32 tri, int pix,
+                                                      const float4 *__restrict__ rec, float *__restrict__ out_t, int *__restrict__ out_id,
+                                                      float *__restrict__ out_normal)
+{
+	if (hit_slab(cc, dx, dy, dz, best, 1) != 0) return; /* outside NDC z [0,1): stays a miss, even if a farther hit existed */
+	write_hit(best, tri, pix, rec, out_t, out_id, out_normal);
+}
+
+static __device__ __forceinline__ void write_hit(float best, u32 tri, int pix, const float4 *__restrict__ rec, float *__restrict__ out_t, int *__restrict__ out_id,
+                                                 float *__restrict__ out_normal)
+{
 	out_t[pix] = best;
 	out_id[pix] = (int)tri;
 	if (out_normal) {
@@ -199,6 +215,63 @@ __global__ void __launch_bounds__(64) k_trace(const FrameConst *__restrict__ fc,
 			}
 		}
 	}
+}
+
+/* NUM_SLABS > 1: rckernel_alpha's slab loop, trace_kernel.cu:132-229, as the reference runs it - one CTA per
+ * 8x8 tile walks the tile's cell slab by slab.  A ray is 0 (nothing yet), 1 (has a hit whose depth slab is not the one
+ * just walked) or 2 (done); isWithin turns a done ray back into 0 in the next slab the tile walks, and the tile stops as
+ * soon as all 64 rays are done after the same slab (metadata[3]).  That coupling is why this cannot use k_trace's
+ * range decomposition; it is a fidelity mode, not a fast path. */
+__global__ void __launch_bounds__(64) k_trace_slabs(const FrameConst *__restrict__ fc, const u32 *__restrict__ vals, const u32 *__restrict__ span,
+                                                    const u32 *__restrict__ offset, const float4 *__restrict__ rec, const float *__restrict__ dir,
+                                                    float *__restrict__ out_t, int *__restrict__ out_id, float *__restrict__ out_normal, int cells, int S)
+{
+	__shared__ float4 s_rec[TR_BATCH * 4];
+	__shared__ float s_cc[64];
+	const ViewConst &vc = fc->cam;
+	const int tid = threadIdx.x;
+	s_cc[tid] = vc.cc[tid];
+	const int gy_cnt = vc.gy_cnt, W = vc.W;
+	const u32 rec_base = (u32)__cvta_generic_to_shared(s_rec);
+	__syncthreads();
+	for (int cell = blockIdx.x; cell < cells; cell += gridDim.x) {
+		const int gx = cell / gy_cnt, gyl = cell - gx * gy_cnt;
+		const int pix = (gyl * UG_TILE + (tid >> 3)) * W + gx * UG_TILE + (tid & 7);
+		const float dx = dir[3 * (size_t)pix], dy = dir[3 * (size_t)pix + 1], dz = dir[3 * (size_t)pix + 2];
+		int rayDone = 0;
+		float best = 99999999.9f;
+		u32 hit = 0xffffffffu;
+		for (int slab = 0; slab < S; slab++) {
+			const u32 n = span[(size_t)cell * S + slab], off = offset[(size_t)cell * S + slab];
+			for (u32 base = 0; base < n; base += TR_BATCH) {
+				const u32 cnt = min((u32)TR_BATCH, n - base);
+				__syncthreads();
+				if ((u32)tid < cnt) {
+					const float4 *src = rec + 4 * (size_t)vals[off + base + tid];
+					s_rec[4 * tid + 0] = src[0]; s_rec[4 * tid + 1] = src[1]; s_rec[4 * tid + 2] = src[2]; s_rec[4 * tid + 3] = src[3];
+				}
+				__syncthreads();
+				if (rayDone != 2)
+					for (u32 k = 0; k < cnt; k++) {
+						float t;
+						if (ug_intersect_lds(rec_base + k * 64u, dx, dy, dz, t)) {
+							t = fabsf(t);
+							if (t < best && t > 0.0f) { best = t; hit = off + base + k; rayDone = 1; }
+						}
+					}
+			}
+			if (rayDone == 1) rayDone = (hit_slab(s_cc, dx, dy, dz, best, S) == slab) ? 2 : 1;
+			else rayDone = 0;
+			if (__syncthreads_and(rayDone == 2)) break;
+		}
+		if (rayDone == 2) write_hit(best, vals[hit], pix, rec, out_t, out_id, out_normal);
+	}
+}
+
+void ugk_trace_slabs(cudaStream_t s, const FrameConst *fc, const GridBuffers &g, const float *dir, float *t, int *id, float *normal, int cells, int sms)
+{
+	if (cells <= 0) return;
+	k_trace_slabs<<<min(cells, sms * 32), 64, 0, s>>>(fc, g.vals[g.final_buf], g.span, g.offset, g.tri_rec, dir, t, id, normal, cells, g.S);
 }
 
 void ugk_init_pixels(cudaStream_t s, const FrameConst *fc, float *t, int *id, int *shadowed, u64 *best, float *normal, float *dir, int N, int sms)

@@ -26,7 +26,7 @@ struct ViewConst {
 	int W, H;           /* full screen */
 	int grid_mode;      /* UG_LIGHT_GRID_*: how triangles and shadow rays are binned into this view's grid (the eye: always perspective) */
 	float xM, yM;       /* spherical mode: angular extents (main.cu:186-187 passes pi, pi) */
-	int pad_;
+	int num_slabs;      /* NUM_SLABS, main.cu.h:18 (1 in the committed build): depth slabs of the grid */
 };
 
 struct FrameConst {
@@ -64,7 +64,14 @@ struct GridBuffers {       /* FrustumGrid, frustum_grid.h:15-68 */
 	size_t cap = 0;            /* pair capacity */
 	int final_buf = 0;         /* which of vals[] holds the sorted list */
 	int key_bits = 0;
-	int C = 0, T = 0;
+	int C = 0, T = 0;          /* C = cells * S: span/offset have one entry per (cell, slab), key = cell*S + slab (grid_kernel.cu:322) */
+	/* depth slabs (NUM_SLABS > 1) */
+	int S = 1, cells = 0;
+	float *projz = nullptr;    /* [T] d_projCoordZ (frustum_grid.h:33): min NDC z (perspective) / min distance (spherical) */
+	u32 *zrange = nullptr;     /* [2] zMin bits, order-preserving zMax: the host loop of frustum_grid.h:227-235 as atomics */
+	u32 *cspan = nullptr, *coffset = nullptr; /* [cells] a cell's slabs as ONE range of the sorted list (what an any-hit over all slabs walks) */
+	const u32 *cell_span() const { return S > 1 ? cspan : span; }
+	const u32 *cell_offset() const { return S > 1 ? coffset : offset; }
 };
 
 struct LightRays {         /* DecisionData's regroup state (decision_data.h:72-80), one per light */
@@ -146,6 +153,7 @@ struct ug_context {
 	u32 *h_counters = nullptr;  /* pinned [1+UG_MAX_LIGHTS][4]: counters of every grid, copied back by the frame */
 	int num_lights = 0;
 	int last_bounces = 0;
+	int num_slabs = 1;           /* NUM_SLABS of every grid (ug_set_slabs / ug_frame_params.num_slabs) */
 	int light_grid_mode = UG_LIGHT_GRID_PERSPECTIVE; /* ug_set_light_grid_mode: used by ug_shadow_pass */
 	float light_xM = 3.14159274f, light_yM = 3.14159274f;
 
@@ -206,6 +214,9 @@ void ugk_transform(cudaStream_t s, float *vertexlist, const float *orig, int siz
 void ugk_setup_bin(cudaStream_t s, const ViewConst *vc, const int *faces, const float *verts, int T, GridBuffers &g, int sms);
 void ugk_scan_counts(cudaStream_t s, GridBuffers &g, int sms);
 void ugk_emit_pairs(cudaStream_t s, const ViewConst *vc, GridBuffers &g, int sms);
+void ugk_slab_reset(cudaStream_t s, const ViewConst *vc, GridBuffers &g);
+void ugk_slab_union(cudaStream_t s, GridBuffers &g, int sms);
+void ugk_trace_slabs(cudaStream_t s, const FrameConst *fc, const GridBuffers &g, const float *dir, float *t, int *id, float *normal, int cells, int sms);
 void ugk_cell_offsets(cudaStream_t s, GridBuffers &g, int sms);
 /* fused single-kernel build (k_gridfused.cu) */
 bool ugk_grid_fused_supported(int device);
@@ -254,6 +265,6 @@ int ugc_gather_strips(ug_context *ctx, cudaStream_t s, const unsigned char *stri
 
 /* host helpers (camera_host.cpp, obj_loader.cpp) */
 void ugh_view_const(ViewConst *vc, const ug_camera *cam, int W, int H, int nbx, int nby, int gy_lo, int gy_cnt, int grid_mode = UG_LIGHT_GRID_PERSPECTIVE,
-                    float xM = 0.0f, float yM = 0.0f);
+                    float xM = 0.0f, float yM = 0.0f, int num_slabs = 1);
 
 #endif
