@@ -94,6 +94,9 @@ typedef struct ug_frame_params {
 #define UG_FLAG_FULL_BUFFERS 1 /* also fill the reference's normal/dir/shadowed buffers (decision_data.h:66-82) */
 #define UG_FLAG_NO_GRAPH 2     /* launch kernels directly instead of replaying the captured CUDA graph */
 #define UG_FLAG_GATHER_FRAMES 8 /* with ug_comm_init and no strips: every rank renders its own frame, rank 0 collects them (slot r = rank r) */
+#define UG_FLAG_GATHER_DEFERRED 64 /* with a communicator: do not wait for the gather at the end of the frame.  Rank 0's buffer holds two
+                                      slots; gathered frame k lands in slot k & 1 and is whole once frame k+1 has run on rank 0's stream, or
+                                      after ug_comm_flush.  The per-frame "done" handshake leaves the critical path (throughput mode). */
 #define UG_FLAG_STAGE_EVENTS 4 /* record one CUDA event per stage (implies NO_GRAPH); see ug_stats.ms_* */
 #define UG_FLAG_SPHERICAL_LIGHTS 16 /* light grids and shadow-ray binning by the spherical map the committed display() uses
                                        (main.cu:189-192 getEffectiveRayGridMapping + buildSphericalGrid with x_max = y_max = M_PI)
@@ -225,6 +228,7 @@ int ug_stage_times(ug_context *ctx, float *out_ms, int max_entries);
  * ug_comm_unique_id on one rank and is handed to the others by the host program (MPI, torch.distributed, a file ...). */
 int ug_comm_unique_id(void *out128);
 int ug_comm_init(ug_context *ctx, int rank, int world, const void *unique_id128);
+int ug_comm_flush(ug_context *ctx); /* collective: completes the last UG_FLAG_GATHER_DEFERRED frame on rank 0 and synchronises */
 
 /* ---- the reference's own entry points on a process-wide default context */
 void init_model(int argc, char **argv);                  /* per_app_funcs.h:8 */

@@ -21,14 +21,17 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_path, no_push):
+def _worker(rank, world, port, out_path, transport):
     import torch
     import torch.distributed as dist
     import ugrt  # noqa: F401
     import uniformgrid_raytracing_b200 as ug
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    no_push = transport == "nccl"
     if no_push:
         os.environ["UG_NO_PUSH"] = "1"          # the ncclSend/ncclRecv fallback instead of the IPC push over NVLink
+    if transport == "copy":
+        os.environ["UG_NO_FUSED_GATHER"] = "1"  # push by a copy-engine node after the frame instead of P2P stores from the shader
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", rank=rank, world_size=world)   # only carries the 128-byte NCCL id
     scene = scenes.scene_a(256, 264)                                # 33 cell rows: uneven strips
@@ -52,12 +55,24 @@ def _worker(rank, world, port, out_path, no_push):
     if rank == 0:
         np.save(out_path + ".frames.npy", r.read(ug.BUF_RGB_FULL)[:3 * dyn.num_pixels * world].copy())
     dist.barrier()
+    # the same with deferred completion (throughput mode): frame k of every rank lands in slot k & 1 of rank 0's buffer and
+    # is whole after the next frame / after comm_flush; 5 steps -> slot 0 holds step 4, slot 1 holds step 3
+    fl = ug.FLAG_GATHER_FRAMES | ug.FLAG_GATHER_DEFERRED
+    for step in range(5):
+        r.render(r.params(dyn, frame=step * world + rank, flags=fl))
+    r.comm_flush()
+    if rank == 0:
+        np.save(out_path + ".deferred.npy", r.read(ug.BUF_RGB_FULL).copy())
+    dist.barrier()
     r.close()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("no_push", [False, True])
-def test_strip_gather_over_nccl(oracle, tmp_path, no_push):
+@pytest.mark.parametrize("transport", ["fused", "copy", "nccl"])
+def test_strip_gather_over_nccl(oracle, tmp_path, transport):
+    """fused: the shading kernels store into rank 0's IPC-mapped frame over NVLink themselves; copy: one peer memcpy node
+    after the frame; nccl: grouped ncclSend/ncclRecv.  Strips, whole frames, and whole frames with deferred completion."""
+    no_push = transport == "nccl"
     import torch
     import torch.multiprocessing as mp
     world = min(torch.cuda.device_count(), 4)
@@ -66,9 +81,16 @@ def test_strip_gather_over_nccl(oracle, tmp_path, no_push):
     scene = scenes.scene_a(256, 264)
     want = harness.run_frame(oracle, scene, threads=0)["rgb"]
     out = str(tmp_path / "full.npy")
-    mp.spawn(_worker, args=(world, _free_port(), out, no_push), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), out, transport), nprocs=world, join=True)
     assert np.array_equal(np.load(out), want)
     dyn = scenes.scene_c(240, 136)
     got = np.load(out + ".frames.npy").reshape(world, -1)
     for k in range(world):
         assert np.array_equal(got[k], harness.run_frame(oracle, dyn, frame=k, threads=0)["rgb"]), f"frame of rank {k}"
+    both = np.load(out + ".deferred.npy").reshape(2, -1)
+    # the ncclSend/ncclRecv fallback has nothing to defer (a receive completes with its data): every frame lands in slot 0
+    for slot, step in (((0, 4),) if no_push else ((0, 4), (1, 3))):
+        frames = both[slot][:3 * dyn.num_pixels * world].reshape(world, -1)
+        for k in range(world):
+            want_k = harness.run_frame(oracle, dyn, frame=step * world + k, threads=0)["rgb"]
+            assert np.array_equal(frames[k], want_k), f"deferred gather: step {step}, rank {k}"

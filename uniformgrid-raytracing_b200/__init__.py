@@ -21,7 +21,8 @@ LIB_PATH = os.path.join(PKG_DIR, "libugrt.so")
 UG_OK = 0
 UG_MAX_LIGHTS = 8
 UG_TILE = 8
-FLAG_FULL_BUFFERS, FLAG_NO_GRAPH, FLAG_STAGE_EVENTS, FLAG_GATHER_FRAMES, FLAG_SPHERICAL_LIGHTS, FLAG_SPOT_SHADE = 1, 2, 4, 8, 16, 32
+(FLAG_FULL_BUFFERS, FLAG_NO_GRAPH, FLAG_STAGE_EVENTS, FLAG_GATHER_FRAMES, FLAG_SPHERICAL_LIGHTS, FLAG_SPOT_SHADE,
+ FLAG_GATHER_DEFERRED) = 1, 2, 4, 8, 16, 32, 64
 LIGHT_GRID_PERSPECTIVE, LIGHT_GRID_SPHERICAL = 0, 1
 
 (BUF_VERTEXLIST, BUF_CAM_VALUES, BUF_CAM_SPAN, BUF_CAM_OFFSET, BUF_T, BUF_ID, BUF_NORMAL, BUF_DIR, BUF_SHADOWED, BUF_RGB,
@@ -84,7 +85,7 @@ def lib() -> C.CDLL:
         vp, f, i = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)
         sig = {
             "ug_create": (C.c_int, [C.POINTER(vp), C.c_int]), "ug_destroy": (None, [vp]), "ug_last_error": (C.c_char_p, [vp]),
-            "ug_version": (C.c_char_p, []), "ug_frame_const_bytes": (C.c_size_t, []), "ug_set_stream": (C.c_int, [vp, vp]), "ug_comm_unique_id": (C.c_int, [vp]), "ug_comm_init": (C.c_int, [vp, C.c_int, C.c_int, vp]), "ug_set_rgb_buffer": (C.c_int, [vp, vp, C.c_size_t]), "ug_synchronize": (C.c_int, [vp]),
+            "ug_version": (C.c_char_p, []), "ug_frame_const_bytes": (C.c_size_t, []), "ug_set_stream": (C.c_int, [vp, vp]), "ug_comm_unique_id": (C.c_int, [vp]), "ug_comm_init": (C.c_int, [vp, C.c_int, C.c_int, vp]), "ug_comm_flush": (C.c_int, [vp]), "ug_set_rgb_buffer": (C.c_int, [vp, vp, C.c_size_t]), "ug_synchronize": (C.c_int, [vp]),
             "ug_model_load": (C.c_int, [vp, C.c_char_p, C.c_char_p]),
             "ug_model_set": (C.c_int, [vp, f, C.c_int, i, C.c_int, i, f, C.c_int]),
             "ug_obj_parse": (C.c_int, [C.c_char_p, i, i, f, i, i]), "ug_material_parse": (C.c_int, [C.c_char_p, i, f]),
@@ -270,6 +271,10 @@ class Renderer:
         """Join the NCCL communicator of the strip gather (unique_id: 128 bytes from unique_id() on one rank)."""
         buf = C.create_string_buffer(bytes(unique_id), 128)
         self._ck(self.L.ug_comm_init(self.ctx, rank, world, C.cast(buf, C.c_void_p)), "ug_comm_init")
+
+    def comm_flush(self):
+        """Collective: completes the last FLAG_GATHER_DEFERRED frame on rank 0 and synchronises."""
+        self._ck(self.L.ug_comm_flush(self.ctx), "ug_comm_flush")
 
     def synchronize(self):
         self._ck(self.L.ug_synchronize(self.ctx), "ug_synchronize")

@@ -92,7 +92,7 @@ extern "C" int ug_comm_init(ug_context *ctx, int rank, int world, const void *un
 	unmap_peer(ctx);
 	ctx->use_push = false;
 	ctx->rgb_full_bytes = 0; /* the gather buffer is shared again (collectively) by the next frame */
-	if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+	ug_drop_graphs(ctx);
 	return UG_OK;
 }
 
@@ -165,17 +165,31 @@ int ugc_ready(ug_context *ctx, cudaStream_t s)
 	return UG_OK;
 }
 
+/* deferred gather: the handshake that makes the last frame whole (what the next frame's "ready" would have been) */
+int ugc_flush(ug_context *ctx, cudaStream_t s)
+{
+	if (!ctx->use_push) return UG_OK; /* ncclRecv completes with the data: nothing is ever pending */
+	unsigned char *scr = (unsigned char *)ctx->d_comm_scratch;
+	UG_NCCL(ctx, N.AllReduce(scr + 132, scr + 132, 1, ncclUint32, ncclSum, (ncclComm_t)ctx->comm, s));
+	return UG_OK;
+}
+
 /* strips -> rank 0's full image.  bytes[r] / offs[r] describe every rank's strip inside the full image.  The caller has
  * ordered ugc_ready() before this on the same stream (directly or through an event). */
-int ugc_gather_strips(ug_context *ctx, cudaStream_t s, const unsigned char *strip, unsigned char *full, const size_t *bytes, const size_t *offs)
+int ugc_gather_strips(ug_context *ctx, cudaStream_t s, const unsigned char *strip, size_t slot_offset, const size_t *bytes, const size_t *offs, bool deferred,
+                      bool already_stored)
 {
 	ncclComm_t comm = (ncclComm_t)ctx->comm;
 	const int rank = ctx->comm_rank, world = ctx->comm_world;
+	unsigned char *full = ctx->d_rgb_full ? ctx->d_rgb_full + slot_offset : nullptr;
 	if (ctx->use_push) {
 		unsigned char *scr = (unsigned char *)ctx->d_comm_scratch;
-		if (rank == 0) UG_CUDA(ctx, cudaMemcpyAsync(full + offs[0], strip, bytes[0], cudaMemcpyDeviceToDevice, s));
-		else UG_CUDA(ctx, cudaMemcpyAsync(ctx->peer_full + offs[rank], strip, bytes[rank], cudaMemcpyDefault, s)); /* copy engine, over NVLink */
-		UG_NCCL(ctx, N.AllReduce(scr + 132, scr + 132, 1, ncclUint32, ncclSum, comm, s)); /* done: every copy precedes its rank's contribution */
+		if (already_stored) { /* fused gather: the shading kernels wrote the pixels into rank 0's frame themselves */ }
+		else if (rank == 0) UG_CUDA(ctx, cudaMemcpyAsync(full + offs[0], strip, bytes[0], cudaMemcpyDeviceToDevice, s));
+		else UG_CUDA(ctx, cudaMemcpyAsync(ctx->peer_full + slot_offset + offs[rank], strip, bytes[rank], cudaMemcpyDefault, s)); /* copy engine, over NVLink */
+		/* done: every copy precedes its rank's contribution.  Deferred: the NEXT frame's "ready" handshake is issued after
+		 * this copy in stream order on every rank, so it doubles as this frame's "done" and nothing waits here */
+		if (!deferred) UG_NCCL(ctx, N.AllReduce(scr + 132, scr + 132, 1, ncclUint32, ncclSum, comm, s));
 		return UG_OK;
 	}
 	if (rank == 0) UG_CUDA(ctx, cudaMemcpyAsync(full + offs[0], strip, bytes[0], cudaMemcpyDeviceToDevice, s));

@@ -64,6 +64,7 @@ extern "C" int ug_create(ug_context **out, int device)
 	 * kernels interleave with the other branches, come out ahead - measured per config in DESIGN.md section 7.  So the
 	 * grid build is chosen per frame (fused_grid_now), the other two are opt-in.  UG_NO_FUSED / UG_FUSED_* override. */
 	ctx->use_fused = ugk_grid_fused_supported(device) && !getenv("UG_NO_FUSED") && !getenv("UG_NO_FUSED_GRID");
+	ctx->fused_gather = !getenv("UG_NO_FUSED_GATHER");
 	ctx->use_fused_regroup = ugk_regroup_fused_supported(device) && !getenv("UG_NO_FUSED") && getenv("UG_FUSED_REGROUP");
 	ctx->use_fused_ugrid = ugk_ugrid_fused_supported(device) && !getenv("UG_NO_FUSED") && getenv("UG_FUSED_UGRID");
 	ctx->force_fused_grid = getenv("UG_FUSED_GRID") != nullptr;
@@ -95,6 +96,7 @@ extern "C" int ug_create(ug_context **out, int device)
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ugrid, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_comm, cudaStreamNonBlocking));
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
+	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_cam, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_refl, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_trace, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaEventCreate(&ctx->ev_t0));
@@ -143,7 +145,7 @@ extern "C" void ug_destroy(ug_context *ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
-	if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+	ug_drop_graphs(ctx);
 	ugc_destroy(ctx);
 	dfree(ctx->d_rgb_full);
 	free_reflect(ctx->refl);
@@ -161,10 +163,16 @@ extern "C" void ug_destroy(ug_context *ctx)
 	}
 	dfree(ctx->d_fc);
 	for (int i = 0; i < UG_MAX_LIGHTS; i++) { cudaStreamDestroy(ctx->side[i]); cudaEventDestroy(ctx->ev_join[i]); }
-	cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_fork2); cudaEventDestroy(ctx->ev_init); cudaStreamDestroy(ctx->side_init); cudaStreamDestroy(ctx->side_refl); cudaStreamDestroy(ctx->side_ugrid); cudaEventDestroy(ctx->ev_ugrid); cudaStreamDestroy(ctx->side_comm); cudaEventDestroy(ctx->ev_ready); cudaEventDestroy(ctx->ev_refl); cudaEventDestroy(ctx->ev_trace); cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
+	cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_fork2); cudaEventDestroy(ctx->ev_init); cudaStreamDestroy(ctx->side_init); cudaStreamDestroy(ctx->side_refl); cudaStreamDestroy(ctx->side_ugrid); cudaEventDestroy(ctx->ev_ugrid); cudaStreamDestroy(ctx->side_comm); cudaEventDestroy(ctx->ev_ready); cudaEventDestroy(ctx->ev_cam); cudaEventDestroy(ctx->ev_refl); cudaEventDestroy(ctx->ev_trace); cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
 	for (auto &ev : ctx->ev_stage) cudaEventDestroy(ev);
 	cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
+}
+
+void ug_drop_graphs(ug_context *ctx)
+{
+	for (int k = 0; k < 2; k++)
+		if (ctx->graph_exec[k]) { cudaGraphExecDestroy(ctx->graph_exec[k]); ctx->graph_exec[k] = nullptr; }
 }
 
 extern "C" const char *ug_last_error(const ug_context *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -173,7 +181,7 @@ extern "C" int ug_set_stream(ug_context *ctx, void *cuda_stream)
 {
 	if (!ctx) return UG_ERR_ARG;
 	ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
-	if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+	ug_drop_graphs(ctx);
 	return UG_OK;
 }
 
@@ -184,7 +192,7 @@ extern "C" int ug_set_rgb_buffer(ug_context *ctx, void *device_ptr, size_t bytes
 	ctx->d_rgb_ext = (unsigned char *)device_ptr;
 	ctx->rgb_ext_bytes = device_ptr ? bytes : 0;
 	if (!device_ptr) ctx->d_rgb = ctx->d_rgb_own;
-	if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+	ug_drop_graphs(ctx);
 	return UG_OK;
 }
 
@@ -382,9 +390,10 @@ static int ensure_buffers(ug_context *ctx, int num_lights, bool full, int bounce
 		if (rc) return rc;
 		changed = true;
 	}
-	if (ctx->comm && ctx->comm_world > 1 && ctx->rgb_full_bytes != 3 * (size_t)ctx->W * ctx->H * (size_t)ctx->comm_world) {
-		/* one gathered frame (strips) or one frame per rank (UG_FLAG_GATHER_FRAMES); collective: every rank gets here in the same call */
-		int rc = ugc_share_full(ctx, 3 * (size_t)ctx->W * ctx->H * (size_t)ctx->comm_world);
+	if (ctx->comm && ctx->comm_world > 1 && ctx->rgb_full_bytes != 2 * 3 * (size_t)ctx->W * ctx->H * (size_t)ctx->comm_world) {
+		/* one gathered frame (strips) or one frame per rank (UG_FLAG_GATHER_FRAMES), times the two slots of a deferred gather;
+		 * collective: every rank gets here in the same call */
+		int rc = ugc_share_full(ctx, 2 * 3 * (size_t)ctx->W * ctx->H * (size_t)ctx->comm_world);
 		if (rc) return rc;
 		changed = true;
 	}
@@ -393,7 +402,7 @@ static int ensure_buffers(ug_context *ctx, int num_lights, bool full, int bounce
 		ctx->full_alloc = true;
 		changed = true;
 	}
-	if (changed && ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+	if (changed) ug_drop_graphs(ctx);
 	return UG_OK;
 }
 
@@ -432,7 +441,7 @@ extern "C" int ug_model_set(ug_context *ctx, const float *vertexlist, int num_ve
 	dfree(ctx->d_reflect);
 	ctx->h_reflect.clear();
 	ctx->size_orig_list = ctx->offset_orig_list = 0;
-	if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+	ug_drop_graphs(ctx);
 	ctx->frame_valid = false;
 	return UG_OK;
 }
@@ -526,7 +535,7 @@ extern "C" int ug_model_set_reflect(ug_context *ctx, const float *reflect, int n
 	ctx->h_reflect.assign(reflect, reflect + num_materials);
 	UG_CUDA(ctx, dmalloc(&ctx->d_reflect, (size_t)num_materials));
 	UG_CUDA(ctx, cudaMemcpy(ctx->d_reflect, reflect, sizeof(float) * (size_t)num_materials, cudaMemcpyHostToDevice));
-	if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+	ug_drop_graphs(ctx);
 	return UG_OK;
 }
 
@@ -541,7 +550,7 @@ extern "C" int ug_model_init_orig_list(ug_context *ctx, int vertices_size, int v
 	                        cudaMemcpyHostToDevice));
 	ctx->size_orig_list = vertices_size;
 	ctx->offset_orig_list = vertices_offset;
-	if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+	ug_drop_graphs(ctx);
 	return UG_OK;
 }
 
@@ -615,6 +624,8 @@ extern "C" int ug_set_strip(ug_context *ctx, int strip_index, int strip_count)
 
 /* ------------------------------------------------------------------ stage sequencing */
 struct Launches { int n = 0; };
+static bool gather_deferred(const ug_context *ctx, const ug_frame_params *p);
+static int gather_slot(const ug_context *ctx, const ug_frame_params *p);
 
 /* FrustumGrid::buildGrid, frustum_grid.h:210-366, on stream s */
 static void enqueue_grid(ug_context *ctx, cudaStream_t s, const ViewConst *vc, GridBuffers &g, Launches &L)
@@ -708,12 +719,6 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 	const bool gather_frames = !gather_strips && ctx->comm && ctx->comm_world > 1 && (p->flags & UG_FLAG_GATHER_FRAMES) && ctx->strip_count == 1;
 	if (parallel) { /* the per-pixel reset + ray directions do not depend on the grid: their own branch of the graph */
 		UG_CUDA(ctx, cudaEventRecord(ctx->ev_fork2, s));
-		if ((gather_strips || gather_frames) && ctx->use_push) { /* the gather's "ready" handshake hides behind the whole frame */
-			UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_comm, ctx->ev_fork2, 0));
-			int rc = ugc_ready(ctx, ctx->side_comm);
-			if (rc) return rc;
-			UG_CUDA(ctx, cudaEventRecord(ctx->ev_ready, ctx->side_comm));
-		}
 		if (reflect) { /* so does the world-space uniform grid of row R */
 			UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_ugrid, ctx->ev_fork2, 0));
 			ugk_stamp(ctx->side_ugrid, tl, 20);
@@ -730,6 +735,16 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 	L.n += 1;
 	enqueue_grid(ctx, s, &ctx->d_fc->cam, ctx->cam_grid, L);
 	ugk_stamp(s, tl, 1);
+	if (parallel && (gather_strips || gather_frames) && ctx->use_push) {
+		/* the gather's "ready" handshake hides behind the rest of the frame.  It starts only now: an NCCL kernel spins on an SM
+		 * until the slowest rank arrives, and while it does the cooperative camera-grid build (all blocks co-resident or none)
+		 * cannot start - issued at the head of the frame it put every rank's skew on the critical path */
+		UG_CUDA(ctx, cudaEventRecord(ctx->ev_cam, s));
+		UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_comm, ctx->ev_cam, 0));
+		int rc = ugc_ready(ctx, ctx->side_comm);
+		if (rc) return rc;
+		UG_CUDA(ctx, cudaEventRecord(ctx->ev_ready, ctx->side_comm));
+	}
 	if (parallel) UG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_init, 0));
 	stage_mark(ctx, k, stage_events); /* 2: camera grid done */
 	if (ctx->cam_grid.S > 1) ugk_trace_slabs(s, ctx->d_fc, ctx->cam_grid, ctx->d_dir, ctx->d_t, ctx->d_id, full ? ctx->d_normal : nullptr, ctx->C_cam, sms);
@@ -770,8 +785,33 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 			stage_mark(ctx, k, stage_events); /* 6+3l: shadow rays */
 		}
 	}
+	/* UG_FLAG_GATHER_DEFERRED: the frame lands in slot (sequence & 1) of rank 0's buffer and nobody waits for "done" here -
+	 * the next frame's "ready" handshake (or ug_comm_flush) is what tells rank 0 that this one is whole */
+	const bool deferred = gather_deferred(ctx, p);
+	const size_t slot_off = deferred ? (size_t)gather_slot(ctx, p) * (ctx->rgb_full_bytes / 2) : 0;
+	size_t g_bytes[64], g_offs[64];
+	if (gather_strips) {
+		size_t acc = 0;
+		for (int r = 0; r < ctx->comm_world && r < 64; r++) {
+			const long long lo = (long long)ctx->nby * r / ctx->comm_world, hi = (long long)ctx->nby * (r + 1) / ctx->comm_world;
+			g_bytes[r] = 3 * (size_t)ctx->W * (size_t)(hi - lo) * UG_TILE;
+			g_offs[r] = acc;
+			acc += g_bytes[r];
+		}
+	} else if (gather_frames) { /* frame-parallel rendering: frame r lands in slot r of the gathered buffer */
+		for (int r = 0; r < ctx->comm_world && r < 64; r++) { g_bytes[r] = 3 * (size_t)ctx->N; g_offs[r] = (size_t)r * g_bytes[r]; }
+	}
+	/* fused compute + collective: with the push transport the shading kernels store every pixel a second time, straight into
+	 * rank 0's frame over NVLink (P2P stores), so the exchange overlaps the shading instead of following it as a copy */
+	const bool fused_gather = (gather_strips || gather_frames) && ctx->use_push && ctx->fused_gather && parallel;
+	ctx->rgb_remote = nullptr;
+	if (fused_gather) {
+		unsigned char *base = ctx->comm_rank == 0 ? ctx->d_rgb_full : ctx->peer_full;
+		ctx->rgb_remote = base + slot_off + g_offs[ctx->comm_rank];
+		UG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_ready, 0)); /* rank 0 is past its read-out of what these stores overwrite */
+	}
 	ugk_shade(s, ctx->d_fc, ctx->d_t, ctx->d_dir, ctx->d_id, ctx->d_shadowed, ctx->cam_grid.tri_rec, ctx->d_materiallist_index, ctx->d_materiallist, ctx->num_materials,
-	          ctx->d_rgb, ctx->d_matid, ctx->N, 1, sms, (p->flags & UG_FLAG_SPOT_SHADE) != 0);
+	          ctx->d_rgb, ctx->d_matid, ctx->N, 1, sms, (p->flags & UG_FLAG_SPOT_SHADE) != 0, ctx->rgb_remote);
 	L.n += 1;
 	ugk_stamp(s, tl, 3);
 	stage_mark(ctx, k, stage_events); /* shade */
@@ -790,29 +830,15 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 	} else {
 		ctx->last_bounces = 0;
 	}
-	if ((gather_strips || gather_frames) && ctx->use_push) {
+	if ((gather_strips || gather_frames) && ctx->use_push && !fused_gather) {
 		if (parallel) UG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_ready, 0));
 		else { int rc = ugc_ready(ctx, s); if (rc) return rc; }
 	}
-	if (gather_strips) {
-		/* the one exchange step: RGB8 strips -> rank 0 over NVLink, inside the frame */
-		size_t bytes[64], offs[64], acc = 0;
-		for (int r = 0; r < ctx->comm_world && r < 64; r++) {
-			const long long lo = (long long)ctx->nby * r / ctx->comm_world, hi = (long long)ctx->nby * (r + 1) / ctx->comm_world;
-			bytes[r] = 3 * (size_t)ctx->W * (size_t)(hi - lo) * UG_TILE;
-			offs[r] = acc;
-			acc += bytes[r];
-		}
-		int rc = ugc_gather_strips(ctx, s, ctx->d_rgb, ctx->d_rgb_full, bytes, offs);
+	if (gather_strips || gather_frames) {
+		/* the one exchange step: RGB8 strips (or whole frames) -> rank 0 over NVLink, inside the frame */
+		int rc = ugc_gather_strips(ctx, s, ctx->d_rgb, slot_off, g_bytes, g_offs, deferred, fused_gather);
 		if (rc) return rc;
-		L.n += 1;
-	} else if (gather_frames) {
-		/* frame-parallel rendering: every rank has rendered a whole frame of its own; frame r lands in slot r on rank 0 */
-		size_t bytes[64], offs[64];
-		for (int r = 0; r < ctx->comm_world && r < 64; r++) { bytes[r] = 3 * (size_t)ctx->N; offs[r] = (size_t)r * bytes[r]; }
-		int rc = ugc_gather_strips(ctx, s, ctx->d_rgb, ctx->d_rgb_full, bytes, offs);
-		if (rc) return rc;
-		L.n += 1;
+		if (!(fused_gather && deferred)) L.n += 1;
 	}
 	/* pair counts + overflow flags of every grid ride back with the frame (no extra synchronisation later) */
 	{
@@ -887,16 +913,26 @@ static int prepare_frame(ug_context *ctx, const ug_frame_params *p)
 	return UG_OK;
 }
 
+/* does this frame end in a gather to rank 0, and is its completion deferred (UG_FLAG_GATHER_DEFERRED)? */
+static bool gathers(const ug_context *ctx, const ug_frame_params *p)
+{
+	if (!ctx->comm || ctx->comm_world <= 1) return false;
+	if (ctx->strip_count == ctx->comm_world && ctx->strip_index == ctx->comm_rank) return true;
+	return (p->flags & UG_FLAG_GATHER_FRAMES) && ctx->strip_count == 1;
+}
+static bool gather_deferred(const ug_context *ctx, const ug_frame_params *p) { return gathers(ctx, p) && ctx->use_push && (p->flags & UG_FLAG_GATHER_DEFERRED); }
+static int gather_slot(const ug_context *ctx, const ug_frame_params *p) { return gather_deferred(ctx, p) ? (int)(ctx->gather_seq & 1) : 0; }
+
 static unsigned long long frame_key(const ug_context *ctx, const ug_frame_params *p)
 {
 	unsigned long long k = 1469598103934665603ull;
 	auto mix = [&](unsigned long long v) { k = (k ^ v) * 1099511628211ull; };
 	mix((unsigned long long)ctx->W); mix((unsigned long long)ctx->H); mix((unsigned long long)ctx->gy_lo); mix((unsigned long long)ctx->gy_cnt);
-	mix((unsigned long long)ctx->num_faces); mix((unsigned long long)p->num_lights); mix((unsigned long long)(p->flags & (UG_FLAG_FULL_BUFFERS | UG_FLAG_GATHER_FRAMES | UG_FLAG_SPOT_SHADE)));
+	mix((unsigned long long)ctx->num_faces); mix((unsigned long long)p->num_lights); mix((unsigned long long)(p->flags & (UG_FLAG_FULL_BUFFERS | UG_FLAG_GATHER_FRAMES | UG_FLAG_SPOT_SHADE | UG_FLAG_GATHER_DEFERRED)));
 	mix((unsigned long long)(p->transform && ctx->d_vertex_orig_list ? 1 : 0)); mix((unsigned long long)ctx->cam_grid.cap);
 	for (int l = 0; l < p->num_lights; l++) mix((unsigned long long)ctx->light_grid[l].cap);
 	mix((unsigned long long)(p->bounces > 0 && ctx->d_reflect ? p->bounces : 0)); mix((unsigned long long)ctx->refl.grid.cap);
-	mix((unsigned long long)ctx->num_slabs);
+	mix((unsigned long long)ctx->num_slabs); mix((unsigned long long)gather_slot(ctx, p));
 	mix((unsigned long long)(uintptr_t)ctx->comm); mix((unsigned long long)(uintptr_t)ctx->d_rgb_full);
 	mix((unsigned long long)(uintptr_t)ctx->peer_full); mix((unsigned long long)ctx->use_push);
 	mix((unsigned long long)(uintptr_t)ctx->stream); mix((unsigned long long)(uintptr_t)ctx->d_rgb);
@@ -907,10 +943,11 @@ static int run_frame_once(ug_context *ctx, const ug_frame_params *p)
 {
 	const bool stage_events = (p->flags & UG_FLAG_STAGE_EVENTS) != 0;
 	const bool use_graph = !(p->flags & UG_FLAG_NO_GRAPH) && !stage_events;
+	const int gs = gather_slot(ctx, p); /* a deferred gather alternates between two destination slots: one captured graph per slot */
 	if (use_graph) {
 		const unsigned long long key = frame_key(ctx, p);
-		if (!ctx->graph_exec || ctx->graph_key != key) {
-			if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+		if (!ctx->graph_exec[gs] || ctx->graph_key[gs] != key) {
+			if (ctx->graph_exec[gs]) { cudaGraphExecDestroy(ctx->graph_exec[gs]); ctx->graph_exec[gs] = nullptr; }
 			cudaGraph_t graph = nullptr;
 			Launches L;
 			UG_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
@@ -918,16 +955,16 @@ static int run_frame_once(ug_context *ctx, const ug_frame_params *p)
 			cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
 			if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
 			if (e != cudaSuccess) return ug_fail(ctx, UG_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
-			e = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+			e = cudaGraphInstantiate(&ctx->graph_exec[gs], graph, 0);
 			cudaGraphDestroy(graph);
 			if (e != cudaSuccess) return ug_fail(ctx, UG_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
-			ctx->graph_key = key;
-			ctx->graph_launches = L.n;
+			ctx->graph_key[gs] = key;
+			ctx->graph_launches[gs] = L.n;
 		}
 		UG_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
-		UG_CUDA(ctx, cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+		UG_CUDA(ctx, cudaGraphLaunch(ctx->graph_exec[gs], ctx->stream));
 		UG_CUDA(ctx, cudaEventRecord(ctx->ev_t1, ctx->stream));
-		ctx->stats.kernel_launches = ctx->graph_launches;
+		ctx->stats.kernel_launches = ctx->graph_launches[gs];
 	} else {
 		Launches L;
 		UG_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
@@ -936,6 +973,7 @@ static int run_frame_once(ug_context *ctx, const ug_frame_params *p)
 		UG_CUDA(ctx, cudaEventRecord(ctx->ev_t1, ctx->stream));
 		ctx->stats.kernel_launches = L.n;
 	}
+	if (gather_deferred(ctx, p)) ctx->gather_seq++;
 	ctx->frame_valid = true;
 	return UG_OK;
 }
@@ -959,7 +997,7 @@ static int check_overflow(ug_context *ctx, int num_lights, bool *grew, bool refl
 			*grew = true;
 		}
 	}
-	if (*grew && ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+	if (*grew) ug_drop_graphs(ctx);
 	return UG_OK;
 }
 
@@ -1094,6 +1132,18 @@ extern "C" int ug_shadow_pass(ug_context *ctx, int light_id, const ug_camera *li
 		}
 	}
 	return ug_fail(ctx, UG_ERR_OVERFLOW, "pair arena still too small after growing");
+}
+
+/* UG_FLAG_GATHER_DEFERRED: make the last gathered frame whole on rank 0 (one handshake + a synchronise); collective */
+extern "C" int ug_comm_flush(ug_context *ctx)
+{
+	if (!ctx) return UG_ERR_ARG;
+	if (!ctx->comm || ctx->comm_world <= 1) return UG_OK;
+	UG_CUDA(ctx, cudaSetDevice(ctx->device));
+	int rc = ugc_flush(ctx, ctx->stream);
+	if (rc) return rc;
+	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return UG_OK;
 }
 
 extern "C" int ug_set_light_grid_mode(ug_context *ctx, int mode, float xM, float yM)

@@ -140,6 +140,7 @@ struct ReflectArgs {
 	const float *t, *dir;
 	const int *id;
 	unsigned char *rgb;
+	unsigned char *rgb_remote; /* fused multi-GPU gather: rank 0's copy of these pixels (P2P stores), or null */
 	float *O, *r, *w, *k0;       /* per-pixel ray state [3N],[3N], running weight [N], first-hit reflectivity [N] */
 	float *term;                 /* [bounces][3N]: what bounce b adds to the pixel (w * local colour) */
 	u32 *depth;                  /* [N] number of valid terms */
@@ -364,7 +365,11 @@ __global__ void __launch_bounds__(256) k_refl_combine(const ReflectArgs a, const
 		for (int c = 0; c < 3; c++) acc[c] = (1.0f - k) * (float)a.rgb[3 * pix + c];
 		for (u32 b = 0; b < depth; b++)
 			for (int c = 0; c < 3; c++) acc[c] = acc[c] + a.term[3 * ((size_t)b * (size_t)a.N + pix) + c];
-		for (int c = 0; c < 3; c++) a.rgb[3 * pix + c] = (unsigned char)acc[c];
+		for (int c = 0; c < 3; c++) {
+			const unsigned char v = (unsigned char)acc[c];
+			a.rgb[3 * pix + c] = v;
+			if (a.rgb_remote) a.rgb_remote[3 * pix + c] = v;
+		}
 	}
 }
 
@@ -414,7 +419,7 @@ static ReflectArgs reflect_args(ug_context *ctx, int bounces)
 	ReflectArgs a;
 	a.fc = ctx->d_fc; a.uc = rf.uc; a.geo = rf.geo; a.prec = rf.prec; a.cellrec = rf.cellrec; a.span = g.span; a.offset = g.offset; a.vals = g.vals[g.final_buf];
 	a.mat_idx = ctx->d_materiallist_index; a.mat_list = ctx->d_materiallist; a.mat_reflect = ctx->d_reflect; a.mat_count = ctx->num_materials;
-	a.N = ctx->N; a.bounces = bounces; a.t = ctx->d_t; a.dir = ctx->d_dir; a.id = ctx->d_id; a.rgb = ctx->d_rgb;
+	a.N = ctx->N; a.bounces = bounces; a.t = ctx->d_t; a.dir = ctx->d_dir; a.id = ctx->d_id; a.rgb = ctx->d_rgb; a.rgb_remote = ctx->rgb_remote;
 	a.O = rf.O; a.r = rf.r; a.w = rf.w; a.k0 = rf.k0; a.term = rf.term; a.depth = rf.depth; a.list = rf.list0; a.next = rf.list0;
 	a.counts = rf.ray_counts;
 	return a;

@@ -59,7 +59,8 @@ template <bool SPOT>
 __global__ void __launch_bounds__(256) k_shade(const FrameConst *__restrict__ fc, const float *__restrict__ t, const float *__restrict__ dir,
                                               const int *__restrict__ id, const int *__restrict__ shadowed, const float4 *__restrict__ rec,
                                               const int *__restrict__ mat_idx, const float *__restrict__ mat_list, int mat_count,
-                                              unsigned char *__restrict__ rgb, int *__restrict__ mat_out, int N, int apply_shadow)
+                                              unsigned char *__restrict__ rgb, int *__restrict__ mat_out, int N, int apply_shadow,
+                                              unsigned char *__restrict__ rgb_remote)
 {
 	const ViewConst &cam = fc->cam;
 	const float *R = fc->shade_mv, *leye = fc->shade_eye;
@@ -82,9 +83,12 @@ __global__ void __launch_bounds__(256) k_shade(const FrameConst *__restrict__ fc
 		const u32 c3 = shade_pixel<SPOT>(R, leye, ex, ey, ez, Lvx, Lvy, Lvz, tv.w, d2.y, d2.z, d2.w, tri.w, sh.w, rec, mat_idx, mat_list, mat_count, apply_shadow, m3);
 		if (mat_out) ((int4 *)mat_out)[g] = make_int4(m0, m1, m2, m3); /* shader_kernel.cu:176 */
 		u32 *out = (u32 *)rgb + 3 * (size_t)g;
-		out[0] = c0 | (c1 << 24);
-		out[1] = (c1 >> 8) | (c2 << 16);
-		out[2] = (c2 >> 16) | (c3 << 8);
+		const u32 w0 = c0 | (c1 << 24), w1 = (c1 >> 8) | (c2 << 16), w2 = (c2 >> 16) | (c3 << 8);
+		out[0] = w0; out[1] = w1; out[2] = w2;
+		if (rgb_remote) { /* multi-GPU gather fused into the shader: the same words go straight into rank 0's frame over NVLink (P2P stores) */
+			u32 *far = (u32 *)rgb_remote + 3 * (size_t)g;
+			far[0] = w0; far[1] = w1; far[2] = w2;
+		}
 	}
 }
 
@@ -97,12 +101,12 @@ __global__ void __launch_bounds__(256) k_add_shadows(const int *__restrict__ sha
 }
 
 void ugk_shade(cudaStream_t s, const FrameConst *fc, const float *t, const float *dir, const int *id, const int *shadowed, const float4 *rec, const int *mat_idx,
-               const float *mat_list, int mat_count, unsigned char *rgb, int *mat_out, int N, int apply_shadow, int sms, bool spot)
+               const float *mat_list, int mat_count, unsigned char *rgb, int *mat_out, int N, int apply_shadow, int sms, bool spot, unsigned char *rgb_remote)
 {
 	if (N <= 0) return;
 	const int blocks = min((N / 4 + 255) / 256, sms * 8);
-	if (spot) k_shade<true><<<blocks, 256, 0, s>>>(fc, t, dir, id, shadowed, rec, mat_idx, mat_list, mat_count, rgb, mat_out, N, apply_shadow);
-	else k_shade<false><<<blocks, 256, 0, s>>>(fc, t, dir, id, shadowed, rec, mat_idx, mat_list, mat_count, rgb, mat_out, N, apply_shadow);
+	if (spot) k_shade<true><<<blocks, 256, 0, s>>>(fc, t, dir, id, shadowed, rec, mat_idx, mat_list, mat_count, rgb, mat_out, N, apply_shadow, rgb_remote);
+	else k_shade<false><<<blocks, 256, 0, s>>>(fc, t, dir, id, shadowed, rec, mat_idx, mat_list, mat_count, rgb, mat_out, N, apply_shadow, rgb_remote);
 }
 void ugk_add_shadows(cudaStream_t s, const int *shadowed, unsigned char *rgb, int N, int sms)
 {

@@ -112,7 +112,7 @@ struct ug_context {
 	cudaStream_t own_stream = nullptr, stream = nullptr;
 	cudaStream_t side[UG_MAX_LIGHTS] = {};
 	cudaStream_t side_init = nullptr, side_refl = nullptr, side_ugrid = nullptr, side_comm = nullptr;
-	cudaEvent_t ev_ready = nullptr;
+	cudaEvent_t ev_ready = nullptr, ev_cam = nullptr;
 	cudaEvent_t ev_ugrid = nullptr;
 	unsigned long long *d_stamps = nullptr; /* [64] UG_TIMELINE markers, null when off */
 	bool use_fused_ugrid = false, force_fused_grid = false, fused_grid_now = true, fused_cam_now = true;
@@ -186,11 +186,15 @@ struct ug_context {
 	unsigned char *peer_full = nullptr;  /* ranks > 0: rank 0's gather buffer mapped through CUDA IPC */
 	void *d_comm_scratch = nullptr;      /* 256 B: IPC handle, flags, barrier words */
 	bool use_push = false;
+	bool fused_gather = true;            /* push transport: the shader (and the reflection combine) store into rank 0's frame themselves;
+	                                        UG_NO_FUSED_GATHER=1 keeps the copy-engine node instead */
+	unsigned char *rgb_remote = nullptr; /* where this frame's pixels go on rank 0 (its own buffer or the IPC-mapped one), null without a fused gather */
 
 	/* CUDA graph of the frame */
-	cudaGraphExec_t graph_exec = nullptr;
-	unsigned long long graph_key = 0;
-	int graph_launches = 0;
+	cudaGraphExec_t graph_exec[2] = {nullptr, nullptr}; /* [1]: the odd frames of a deferred gather (they write the other slot) */
+	unsigned long long graph_key[2] = {0, 0};
+	int graph_launches[2] = {0, 0};
+	unsigned long long gather_seq = 0; /* frames gathered with UG_FLAG_GATHER_DEFERRED so far: frame k lands in slot k & 1 */
 
 	ug_stats stats = {};
 	bool frame_valid = false;
@@ -198,6 +202,7 @@ struct ug_context {
 
 /* ---------------------------------------------------------------- error helpers */
 int ug_fail(ug_context *ctx, int code, const char *fmt, ...);
+void ug_drop_graphs(ug_context *ctx);
 #define UG_CUDA(ctx, call)                                                                              \
 	do {                                                                                                \
 		cudaError_t e_ = (call);                                                                        \
@@ -246,7 +251,8 @@ void ugk_shadow(cudaStream_t s, const FrameConst *fc, int light, const GridBuffe
                 int N, int C, int sms);
 /* K10 shade */
 void ugk_shade(cudaStream_t s, const FrameConst *fc, const float *t, const float *dir, const int *id, const int *shadowed, const float4 *rec, const int *mat_idx,
-               const float *mat_list, int mat_count, unsigned char *rgb, int *mat_out, int N, int apply_shadow, int sms, bool spot = false);
+               const float *mat_list, int mat_count, unsigned char *rgb, int *mat_out, int N, int apply_shadow, int sms, bool spot = false,
+               unsigned char *rgb_remote = nullptr);
 void ugk_add_shadows(cudaStream_t s, const int *shadowed, unsigned char *rgb, int N, int sms);
 void ugk_fill_u32(cudaStream_t s, u32 *p, u32 v, size_t n, int sms);
 /* row R (k_reflect.cu) */
@@ -261,7 +267,9 @@ void ugk_reflect_combine(cudaStream_t s, ug_context *ctx, int *launches);
 void ugc_destroy(ug_context *ctx);
 int ugc_share_full(ug_context *ctx, size_t bytes);
 int ugc_ready(ug_context *ctx, cudaStream_t s);
-int ugc_gather_strips(ug_context *ctx, cudaStream_t s, const unsigned char *strip, unsigned char *full, const size_t *bytes, const size_t *offs);
+int ugc_gather_strips(ug_context *ctx, cudaStream_t s, const unsigned char *strip, size_t slot_offset, const size_t *bytes, const size_t *offs, bool deferred,
+                      bool already_stored);
+int ugc_flush(ug_context *ctx, cudaStream_t s);
 
 /* host helpers (camera_host.cpp, obj_loader.cpp) */
 void ugh_view_const(ViewConst *vc, const ug_camera *cam, int W, int H, int nbx, int nby, int gy_lo, int gy_cnt, int grid_mode = UG_LIGHT_GRID_PERSPECTIVE,
