@@ -16,7 +16,7 @@ import numpy as np
 from . import scenes  # noqa: F401  (scene generators for the BASELINE configs)
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libugrt.so")
+LIB_PATH = os.environ.get("UGRT_LIB") or os.path.join(PKG_DIR, "libugrt.so")   # UGRT_LIB: development aid (A/B builds)
 
 UG_OK = 0
 UG_MAX_LIGHTS = 8

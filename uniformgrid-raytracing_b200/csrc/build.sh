@@ -3,7 +3,7 @@
 # reference's arithmetic forbids FMA contraction.
 set -e
 cd "$(dirname "$0")"
-OUT=../libugrt.so
+OUT=${UG_OUT:-../libugrt.so}
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -prec-div=true -prec-sqrt=true -ftz=false \
   -Xcompiler -fPIC,-ffp-contract=off,-fno-fast-math,-Wall -I../../include -I. ${UG_EXTRA_FLAGS}"
