@@ -205,7 +205,8 @@ int ug_add_shadows(ug_context *ctx);                                            
 
 /* ---- the whole frame: every step of display() between "frame_cnt++" and the image being complete,
  * replayed as one CUDA graph, no host synchronisation inside */
-int ug_render_frame(ug_context *ctx, const ug_frame_params *p);
+int ug_render_frame(ug_context *ctx, const ug_frame_params *p); /* asynchronous: a pair arena that proved too small shows as
+                                                                   ug_stats.overflowed; ug_get_stats then grows it - render again */
 /* same, end to end with host buffers: uploads the frame constants, renders, copies the RGB8 strip into
  * host_rgb (3*W*H_strip bytes, pinned or pageable) and synchronises - main.cu:245 included */
 int ug_render_frame_host(ug_context *ctx, const ug_frame_params *p, uint8_t *host_rgb);

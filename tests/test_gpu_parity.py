@@ -295,6 +295,55 @@ def test_pair_arena_overflow_regrows(ug, oracle):
         r.close()
 
 
+def test_async_frame_overflow_is_reported_and_repaired(ug, oracle):
+    """ug_render_frame cannot re-run itself: the overflow shows in the stats, ug_get_stats grows the arena, the second
+    attempt is complete."""
+    T = 96
+    V = np.zeros((T, 3, 3), np.float32)
+    for k in range(T):
+        y = 20.0 + 0.25 * k
+        V[k] = [[-60, y, -60], [60, y, -60], [0, y, 70]]
+    s = scenes.scene_random(1, 10, 1024, 1024, nlights=1)
+    s.verts, s.faces, s.face_mat = V.reshape(-1, 3), np.arange(3 * T, dtype=np.int32).reshape(-1, 3), np.zeros(T, np.int32)
+    r = ug.Renderer(0)
+    try:
+        r.set_scene(s)
+        r.render(r.params(s))
+        assert r.stats().overflowed == 1
+        r.render(r.params(s))
+        st = r.stats()
+        cpu = cpu_frame(oracle, s)
+        assert st.overflowed == 0 and st.cam_pairs == cpu["cam_P"]
+        assert np.array_equal(r.read(ug.BUF_RGB), cpu["rgb"]) and np.array_equal(r.read(ug.BUF_ID), cpu["id"])
+    finally:
+        r.close()
+
+
+@pytest.mark.parametrize("case", ["8x8", "8lights", "nan", "allmiss", "1tri_wide"])
+def test_edge_sizes(renderer, ug, oracle, case):
+    """Smallest screen (one cell), the maximum number of lights, a NaN vertex (NaN-propagating min/max, x86 float->int rule),
+    a frame without a single hit, one triangle on a very wide strip-shaped screen."""
+    if case == "8x8":
+        s = scenes.scene_tiny("ka", 8, 8)
+    elif case == "8lights":
+        s = scenes.scene_random(21, 800, 96, 64, nlights=8)
+    elif case == "nan":
+        s = scenes.scene_random(22, 600, 96, 96, nlights=1)
+        s.verts = s.verts.copy()
+        s.verts[7, 1] = np.nan
+        s.verts[100] = np.inf
+    elif case == "allmiss":
+        s = scenes.scene_tiny("one", 64, 64)
+        s.verts = (s.verts + np.array([500.0, 0.0, 0.0], np.float32)).astype(np.float32)
+    else:
+        s = scenes.scene_tiny("one", 2048, 8)
+    renderer.set_scene(s)
+    cpu = cpu_frame(oracle, s)
+    assert_frame(parity.gpu_frame(renderer, s), cpu, s.name + " " + case)
+    if case == "allmiss":
+        assert (cpu["id"] >= 0).sum() == 0 and cpu["rgb"].max() == 0
+
+
 def reflective(scene, ks, bounces):
     for m, k in zip(scene.materials, ks):
         m.reflect = k

@@ -118,6 +118,29 @@ def test_depth_slabs(ref, oracle, case, slabs, sph):
         assert 0 < (out["id"] >= 0).sum() <= (one["id"] >= 0).sum()
 
 
+@pytest.mark.parametrize("case", ["8x8", "8lights", "nan", "allmiss", "wide"])
+def test_edge_sizes(ref, oracle, case):
+    """One-cell screen, the maximum number of lights, NaN / inf vertices, a frame without a hit, a 256x1-cell screen."""
+    if case == "8x8":
+        s = scenes.scene_tiny("ka", 8, 8)
+    elif case == "8lights":
+        s = scenes.scene_random(21, 800, 96, 64, nlights=8)
+    elif case == "nan":
+        s = scenes.scene_random(22, 600, 96, 96, nlights=1)
+        s.verts = s.verts.copy()
+        s.verts[7, 1] = np.nan
+        s.verts[100] = np.inf
+    elif case == "allmiss":
+        s = scenes.scene_tiny("one", 64, 64)
+        s.verts = (s.verts + np.array([500.0, 0.0, 0.0], np.float32)).astype(np.float32)
+    else:
+        s = scenes.scene_tiny("one", 2048, 8)
+    out = check_frame(ref, oracle, s)
+    if case == "allmiss":
+        assert (out["id"] >= 0).sum() == 0 and out["rgb"].max() == 0
+    check_frame(ref, oracle, s, spherical=True, spot=True)
+
+
 def test_config_a_reduced(ref, oracle):
     out = check_frame(ref, oracle, scenes.scene_a(256, 256))
     assert out["cam_P"] > 16370 and out["shadowed"].sum() > 1000

@@ -1281,6 +1281,14 @@ extern "C" int ug_get_stats(ug_context *ctx, ug_stats *out)
 		else cudaGetLastError();
 	}
 	*out = s;
+	if (s.overflowed && ctx->frame_valid) {
+		/* ug_render_frame is asynchronous and cannot re-run itself: the frame that overflowed is incomplete, but the arenas are
+		 * grown here so that rendering it again succeeds (ug_render_frame_host does both on its own) */
+		bool grew = false;
+		int rc = check_overflow(ctx, ctx->num_lights, &grew, ctx->last_bounces > 0);
+		if (rc) return rc;
+		if (grew) ctx->frame_valid = false;
+	}
 	return UG_OK;
 }
 
