@@ -219,14 +219,17 @@ def run_ours(args):
     if not any(m.reflect > 0 for m in scene.materials):
         bounces = 0
 
+    base_flags = (ug.FLAG_SPHERICAL_LIGHTS if args.light_grid == "spherical" else 0) | (ug.FLAG_SPOT_SHADE if args.shader == "spot" else 0)
+
     def step(i, flags=0, m=None):
         m = m or mode
+        flags |= base_flags
         if m == "frames":   # whole frames, collected on rank 0 by the library's own NCCL send/recv inside the frame graph
             # deferred completion: frame i is whole on rank 0 once frame i+1 has passed its "ready" handshake, or after
             # comm_flush() - the per-frame "done" handshake is off the critical path, the timed region ends with the flush
-            r.render(r.params(scene, frame=i * world + rank, flags=flags | ug.FLAG_GATHER_FRAMES | ug.FLAG_GATHER_DEFERRED, bounces=bounces))
+            r.render(r.params(scene, frame=i * world + rank, flags=flags | ug.FLAG_GATHER_FRAMES | ug.FLAG_GATHER_DEFERRED, bounces=bounces, slabs=args.slabs))
         else:
-            r.render(r.params(scene, frame=i, flags=flags, strip=strip_of(m), bounces=bounces))
+            r.render(r.params(scene, frame=i, flags=flags, strip=strip_of(m), bounces=bounces, slabs=args.slabs))
 
     def barrier():
         if world > 1:
@@ -234,7 +237,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- warm-up (also captures the CUDA graph and grows the pair arena if the scene needs it)
-    r.render_host(r.params(scene, frame=0, strip=strip_of(mode), bounces=bounces), host_img.numpy())
+    r.render_host(r.params(scene, frame=0, flags=base_flags, strip=strip_of(mode), bounces=bounces, slabs=args.slabs), host_img.numpy())
     for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
@@ -297,7 +300,8 @@ def run_ours(args):
     for i in range(e2e_steps):
         # H2D constants + kernels [+ NCCL strip gather] + D2H of the image (strips: the gathered frame on rank 0;
         # frames: every rank reads its own frame back over its own PCIe link) + sync
-        r.render_host(r.params(scene, frame=i * frames_per_step + (rank if mode == "frames" else 0), strip=strip_of(mode), bounces=bounces),
+        r.render_host(r.params(scene, frame=i * frames_per_step + (rank if mode == "frames" else 0), flags=base_flags, strip=strip_of(mode),
+                               bounces=bounces, slabs=args.slabs),
                       out_np if mode != "strips" else host_img.numpy())
     barrier()
     e2e_dt = time.perf_counter() - t0
@@ -310,7 +314,7 @@ def run_ours(args):
     stage = {}
     reps = 5
     for i in range(reps):
-        r.render(r.params(scene, frame=i, flags=ug.FLAG_STAGE_EVENTS, strip=strip_of(mode), bounces=bounces))
+        r.render(r.params(scene, frame=i, flags=ug.FLAG_STAGE_EVENTS | base_flags, strip=strip_of(mode), bounces=bounces, slabs=args.slabs))
         for k, v in r.stage_times().items():
             stage[k] = stage.get(k, 0.0) + v / reps
     st2 = r.stats()
@@ -398,7 +402,8 @@ def run_ours(args):
                                 "reflection": int(refl.item())},
                        "l2": "flushed between timed frames (256 MiB write)" if not args.no_flush else "not flushed",
                        "timing": "CUDA events per frame on the launching stream, max over ranks, summed over the K frames",
-                       "pairs_camera_grid": int(P), "pairs_light_grids": [int(st2.light_pairs[l]) for l in range(len(scene.lights))]},
+                       "pairs_camera_grid": int(P), "pairs_light_grids": [int(st2.light_pairs[l]) for l in range(len(scene.lights))],
+                       "light_grid": args.light_grid, "shader": args.shader, "num_slabs": args.slabs},
             "ms_per_frame_warm_l2": warm_ms, "ms_per_frame_p50": float(np.median(per)), "ms_per_frame_p10": float(np.percentile(per, 10)),
             "ms_per_frame_p90": float(np.percentile(per, 90)), "wall_s_timed_region": wall,
             "e2e": {"value": rays_frame * e2e_steps / e2e_dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(ug.lib().ug_frame_const_bytes()) * world,
@@ -432,6 +437,10 @@ def main():
     ap.add_argument("--config", default="B", choices=["A", "B", "C", "D", "E"])
     ap.add_argument("--bounces", type=int, default=-1, help="reflection bounces (-1: what the config names)")
     ap.add_argument("--shard", default="auto", choices=["auto", "frames", "strips"], help="N > 1: frames = one frame per GPU (weak, default), strips = one frame in strips (strong)")
+    ap.add_argument("--light-grid", default="perspective", choices=["perspective", "spherical"],
+                    help="perspective: the light path north-star names (default); spherical: the one the committed display() runs")
+    ap.add_argument("--shader", default="lambert", choices=["lambert", "spot"], help="spot: Shader::spotlight_shade (display() from its third frame on)")
+    ap.add_argument("--slabs", type=int, default=1, help="NUM_SLABS (main.cu.h:18 compiles 1)")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

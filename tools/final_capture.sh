@@ -11,8 +11,8 @@ python bench.py --bounces 0 --no-cpu-baseline > $O/${R}_bench_B_nobounce.json 2>
 python bench.py --config A --no-cpu-baseline > $O/${R}_bench_A.json 2>/dev/null
 python bench.py --config C --no-cpu-baseline --steps 50 > $O/${R}_bench_C.json 2>/dev/null
 python bench.py --config D --no-cpu-baseline --steps 30 --warmup 5 > $O/${R}_bench_D.json 2>/dev/null
-python bench.py --config E --no-cpu-baseline --steps 5 --warmup 3 > $O/${R}_bench_E.json 2> $O/${R}_bench_E.err
-for f in B B_reference B_nobounce A C D E; do python - $O/${R}_bench_$f.json <<'PY'
+python bench.py --light-grid spherical --shader spot --bounces 0 --no-cpu-baseline --steps 50 > $O/${R}_bench_B_display_faithful.json 2>/dev/null
+for f in B B_reference B_nobounce B_display_faithful A C D; do python - $O/${R}_bench_$f.json <<'PY'
 import json,sys
 try:
     d=json.load(open(sys.argv[1])); print(sys.argv[1], d.get("ms_per_step"), d.get("value"), (d.get("e2e") or {}).get("value"))

@@ -46,11 +46,37 @@ static __device__ __forceinline__ u32 sh_segments(u32 rays, u32 ntri)
 	if (ntri <= SH_SEGMAX) return 1;
 	return min((ntri + SH_SEGMAX - 1) / SH_SEGMAX, 1u + SH_SEGBUDGET / rays);
 }
+/* The shape of a cell's items.  Few rays on a long list: few rays per item, the lanes split every staged batch (above).
+ * A warp's worth of rays or more on a long list (crowded cells - the spherical light grid puts tens of thousands of rays
+ * and thousands of triangles into one): 32 rays per item, one per lane, and the LIST is cut into segments of about
+ * SH_SEG triangles, so every staged batch is tested by 32 rays instead of being fetched again for every ray or two.
+ * Either way a cell needs at most rays + SH_SEGBUDGET items. */
+#ifndef SH_SEG
+#define SH_SEG 128
+#endif
+#ifndef SH_CROWD_NTRI
+#define SH_CROWD_NTRI 256 /* lists longer than this count as long (measured: 64 costs config B 5 us, 512+ costs the crowded cases) */
+#endif
+struct ItemShape { u32 rpi, nseg, seglen; };
+static __device__ __forceinline__ ItemShape sh_shape(u32 rays, u32 ntri)
+{
+	ItemShape s;
+	if (rays >= 32 && ntri > SH_CROWD_NTRI) {
+		const u32 chunks = (rays + 31) / 32;
+		s.rpi = 32;
+		s.nseg = min((ntri + SH_SEG - 1) / SH_SEG, max(1u, (rays + SH_SEGBUDGET) / chunks));
+	} else {
+		s.rpi = sh_rays_per_item(ntri);
+		s.nseg = sh_segments(max(rays, 1u), ntri);
+	}
+	s.seglen = (((ntri + s.nseg - 1) / s.nseg) + 31u) & ~31u; /* whole staging batches */
+	return s;
+}
 static __device__ __forceinline__ u32 sh_items_of_cell(u32 rays, u32 ntri)
 {
 	if (!rays || !ntri) return 0;
-	const u32 rpi = sh_rays_per_item(ntri);
-	return ((rays + rpi - 1) / rpi) * sh_segments(rays, ntri);
+	const ItemShape s = sh_shape(rays, ntri);
+	return ((rays + s.rpi - 1) / s.rpi) * s.nseg;
 }
 
 struct RegroupArgs {
@@ -253,8 +279,8 @@ __global__ void __launch_bounds__(32 * SH_WARPS) k_shadow(const FrameConst *__re
 		if (i >= nitems) break;
 		const uint2 it = items[i]; /* (cell, local item index) */
 		const u32 cell = it.x, ntri = span[cell], toff = offset[cell], nrays = ray_span[cell], roff = ray_offset[cell];
-		const u32 rpi = sh_rays_per_item(ntri), nseg = sh_segments(nrays, ntri);
-		const u32 seglen = (((ntri + nseg - 1) / nseg) + 31u) & ~31u; /* whole staging batches */
+		const ItemShape shp = sh_shape(nrays, ntri);
+		const u32 rpi = shp.rpi, nseg = shp.nseg, seglen = shp.seglen;
 		const u32 chunk = it.y / nseg, seg = it.y - chunk * nseg;
 		const u32 a = chunk * rpi, m = min(rpi, nrays - a);         /* this item's rays: [roff+a, roff+a+m) */
 		const u32 t0 = toff + min(ntri, seg * seglen), t1 = toff + min(ntri, (seg + 1) * seglen);

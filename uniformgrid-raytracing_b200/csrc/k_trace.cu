@@ -91,7 +91,10 @@ static __device__ __forceinline__ void write_hit(float best, u32 tri, int pix, c
 	}
 }
 
-__global__ void __launch_bounds__(64) k_trace(const FrameConst *__restrict__ fc, const u32 *__restrict__ counters, const u32 *__restrict__ keys,
+#ifndef TR_MINB
+#define TR_MINB 16 /* 64 registers: no spills (the compiler's own choice was 48 with spills); measured -5 us on config B */
+#endif
+__global__ void __launch_bounds__(64, TR_MINB) k_trace(const FrameConst *__restrict__ fc, const u32 *__restrict__ counters, const u32 *__restrict__ keys,
                                               const u32 *__restrict__ vals, const u32 *__restrict__ span, const u32 *__restrict__ offset,
                                               const float4 *__restrict__ rec, u64 *__restrict__ best_buf, u32 *__restrict__ cell_done,
                                               const float *__restrict__ dir, float *__restrict__ out_t, int *__restrict__ out_id,
