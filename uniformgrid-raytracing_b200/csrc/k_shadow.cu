@@ -167,18 +167,33 @@ __global__ void __launch_bounds__(RG_THREADS, 2) k_regroup(const RegroupArgs a, 
 		const bool spherical = lv.grid_mode == UG_LIGHT_GRID_SPHERICAL;
 		const float ex = cam.cc[0], ey = cam.cc[1], ez = cam.cc[2];
 		if (b == 0 && tid == 0) a.counters[1] = 0;
-		for (int base = b * RG_THREADS; base < N; base += G * RG_THREADS) {
-			const int pix = base + tid;
-			const bool valid = pix < N;
-			u32 cell = 0xffffffffu;
-			if (valid) {
-				const float tv = a.t[pix], dx = a.dir[3 * (size_t)pix], dy = a.dir[3 * (size_t)pix + 1], dz = a.dir[3 * (size_t)pix + 2];
-				cell = spherical ? light_cell_sph(lv, ex, ey, ez, tv, dx, dy, dz) : light_cell_of(m, ex, ey, ez, tv, dx, dy, dz);
-				a.light_cell[pix] = cell;
+		/* two pixels per thread and trip: both pixels' loads are in flight before either one's arithmetic starts (the loop is a
+		 * dependent chain load -> divide -> match -> atomic, and only 32 warps per SM are resident) */
+		const int stride = (int)(G * RG_THREADS);
+		for (int base = b * RG_THREADS; base < N; base += 2 * stride) {
+			const int pix[2] = {base + (int)tid, base + stride + (int)tid};
+			float tv[2], dx[2], dy[2], dz[2];
+#pragma unroll
+			for (int k = 0; k < 2; k++) {
+				const bool valid = pix[k] < N;
+				tv[k] = valid ? a.t[pix[k]] : 0.0f;
+				dx[k] = valid ? a.dir[3 * (size_t)pix[k]] : 0.0f;
+				dy[k] = valid ? a.dir[3 * (size_t)pix[k] + 1] : 0.0f;
+				dz[k] = valid ? a.dir[3 * (size_t)pix[k] + 2] : 1.0f;
 			}
-			/* rays of one warp mostly share a light cell: one atomic per distinct cell */
-			const u32 peers = __match_any_sync(UG_FULL_MASK, cell);
-			if (valid && (peers & ((1u << ug_lane()) - 1u)) == 0) atomicAdd(&a.ray_span[cell], (u32)__popc(peers));
+#pragma unroll
+			for (int k = 0; k < 2; k++) {
+				if (base + k * stride >= N) break; /* warp-uniform: the second half-trip lies past the end */
+				const bool valid = pix[k] < N;
+				u32 cell = 0xffffffffu;
+				if (valid) {
+					cell = spherical ? light_cell_sph(lv, ex, ey, ez, tv[k], dx[k], dy[k], dz[k]) : light_cell_of(m, ex, ey, ez, tv[k], dx[k], dy[k], dz[k]);
+					a.light_cell[pix[k]] = cell;
+				}
+				/* rays of one warp mostly share a light cell: one atomic per distinct cell */
+				const u32 peers = __match_any_sync(UG_FULL_MASK, cell);
+				if (valid && (peers & ((1u << ug_lane()) - 1u)) == 0) atomicAdd(&a.ray_span[cell], (u32)__popc(peers));
+			}
 		}
 	}
 	if (all) cg::this_grid().sync();
@@ -220,17 +235,26 @@ __global__ void __launch_bounds__(RG_THREADS, 2) k_regroup(const RegroupArgs a, 
 	if (all || phase == 2) { /* ---- phase C: scatter the rays, write the item table, reset the scratch */
 		const u32 per = RG_THREADS * 4, tiles = ((u32)C + 2 + per - 1) / per;
 		for (u32 i = b * RG_THREADS + tid; i < tiles + 1; i += G * RG_THREADS) { a.state_a[i] = 0; a.state_b[i] = 0; }
-		for (int base = b * RG_THREADS; base < N; base += G * RG_THREADS) {
-			const int pix = base + tid;
-			const bool valid = pix < N;
-			const u32 cell = valid ? a.light_cell[pix] : 0xffffffffu;
-			const u32 peers = __match_any_sync(UG_FULL_MASK, cell);
-			const u32 lower = __popc(peers & ((1u << ug_lane()) - 1u));
-			u32 start = 0;
-			const int leader = __ffs(peers) - 1;
-			if (valid && lower == 0) start = atomicAdd(&a.cursor[cell], (u32)__popc(peers));
-			start = __shfl_sync(UG_FULL_MASK, start, leader);
-			if (valid) a.ray_pix[a.ray_offset[cell] + start + lower] = (u32)pix;
+		const int stride = (int)(G * RG_THREADS);
+		for (int base = b * RG_THREADS; base < N; base += 2 * stride) { /* two pixels per trip, as in phase A */
+			const int pix[2] = {base + (int)tid, base + stride + (int)tid};
+			u32 cell[2], roff[2];
+#pragma unroll
+			for (int k = 0; k < 2; k++) cell[k] = (pix[k] < N) ? a.light_cell[pix[k]] : 0xffffffffu;
+#pragma unroll
+			for (int k = 0; k < 2; k++) roff[k] = (pix[k] < N) ? a.ray_offset[cell[k]] : 0u;
+#pragma unroll
+			for (int k = 0; k < 2; k++) {
+				if (base + k * stride >= N) break; /* warp-uniform */
+				const bool valid = pix[k] < N;
+				const u32 peers = __match_any_sync(UG_FULL_MASK, cell[k]);
+				const u32 lower = __popc(peers & ((1u << ug_lane()) - 1u));
+				u32 start = 0;
+				const int leader = __ffs(peers) - 1;
+				if (valid && lower == 0) start = atomicAdd(&a.cursor[cell[k]], (u32)__popc(peers));
+				start = __shfl_sync(UG_FULL_MASK, start, leader);
+				if (valid) a.ray_pix[roff[k] + start + lower] = (u32)pix[k];
+			}
 		}
 		const u32 total = a.item_off[C];
 		if (b == 0 && tid == 0) a.counters[0] = min(total, a.item_cap);
