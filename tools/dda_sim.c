@@ -6,6 +6,9 @@
 #include <string.h>
 
 int g_cull = 0;
+/* empty-space skipping study: for coarse blocks of 2^k cells per axis (k = 1,2,3), per ray the fine steps taken inside blocks that
+ * hold no triangle at all (skippable) and the number of such blocks entered (what a two-level walk would pay instead) */
+long g_skip_steps[4], g_skip_blocks[4];
 typedef struct { float lo[3], h[3], inv_h[3]; int n[3]; } G;
 static int clampi(int v, int a, int b) { return v < a ? a : (v > b ? b : v); }
 static int ucell(const G *u, int k, float x) { return clampi((int)floorf((x - u->lo[k]) * u->inv_h[k]), 0, u->n[k] - 1); }
@@ -66,6 +69,17 @@ long dda_sim(const float *verts, int V, const int *tris, int T, const float *O, 
 			}
 		}
 	}
+	unsigned char *occ[4] = {0, 0, 0, 0};
+	int cn[4][3];
+	for (int k = 1; k <= 3; k++) {
+		for (int a = 0; a < 3; a++) cn[k][a] = (n[a] + (1 << k) - 1) >> k;
+		occ[k] = calloc((size_t)cn[k][0] * cn[k][1] * cn[k][2], 1);
+		for (long c = 0; c < C; c++) if (span[c]) {
+			long cz = c % n[2], cy = (c / n[2]) % n[1], cx = c / ((long)n[1] * n[2]);
+			occ[k][((cx >> k) * cn[k][1] + (cy >> k)) * cn[k][2] + (cz >> k)] = 1;
+		}
+		g_skip_steps[k] = g_skip_blocks[k] = 0;
+	}
 	float hmin = fminf(u.h[0], fminf(u.h[1], u.h[2]));
 	for (int i = 0; i < R; i++) {
 		const float *o = O + 3 * i, *d = r + 3 * i;
@@ -87,8 +101,14 @@ long dda_sim(const float *verts, int V, const int *tris, int T, const float *O, 
 			}
 			float best = 99999999.9f; int hit = -1;
 			float t_prev = t_in;
+			long last_block[4] = {-1, -1, -1, -1};
 			for (;;) {
 				long c = ((long)ci[0] * n[1] + ci[1]) * n[2] + ci[2];
+				for (int k = 1; k <= 3; k++) {
+					long b = (((long)(ci[0] >> k)) * cn[k][1] + (ci[1] >> k)) * cn[k][2] + (ci[2] >> k);
+					if (!occ[k][b]) { g_skip_steps[k]++; if (b != last_block[k]) g_skip_blocks[k]++; }
+					last_block[k] = b;
+				}
 				int ax = (tmax[0] <= tmax[1]) ? ((tmax[0] <= tmax[2]) ? 0 : 2) : ((tmax[1] <= tmax[2]) ? 1 : 2);
 				float texit = tmax[ax];
 				ns++;
@@ -137,6 +157,7 @@ long dda_sim(const float *verts, int V, const int *tris, int T, const float *O, 
 		}
 		steps[i] = ns | (nc << 16); tests[i] = nt; nonempty[i] = ne;
 	}
+	for (int k = 1; k <= 3; k++) free(occ[k]);
 	free(ubox); free(span); free(rect); free(off); free(vals); free(fill);
 	return P;
 }

@@ -40,6 +40,9 @@ def sim(scene, O, r, n):
     nn = np.asarray(n, np.int32)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     P = L.dda_sim(p(V), len(V), p(F), len(F), p(np.ascontiguousarray(O)), p(np.ascontiguousarray(r)), R, p(nn), p(steps), p(tests), p(ne))
+    sk = (C.c_long * 4).in_dll(L, "g_skip_steps"); bl = (C.c_long * 4).in_dll(L, "g_skip_blocks")
+    global SKIP
+    SKIP = {1 << k: (sk[k] / max(R, 1), bl[k] / max(R, 1)) for k in (1, 2, 3)}
     return P, steps & 0xffff, tests, ne, steps >> 16
 
 def res_for(scene, lam):
@@ -61,4 +64,6 @@ if __name__ == "__main__":
         # warp cost: max over each group of 32 consecutive rays
         R = len(O) // 32 * 32
         wc = cost[:R].reshape(-1, 32).max(1).sum() * 32
+        print("   empty-space skipping, coarse block edge -> (fine steps inside empty blocks, empty blocks entered) per ray -> steps of a two-level walk:",
+              {b: (round(v[0], 1), round(v[1], 1), round(st.mean() - v[0] + v[1], 1)) for b, v in SKIP.items()})
         print(f"lam={lam:5.1f} n={n} pairs={P} steps/ray={st.mean():7.1f} nonemptycells={nc.mean():5.1f} boxtests={ne.mean():6.1f} tests/ray={te.mean():7.1f} p99tests={np.percentile(te,99):.0f} cost/ray={cost.mean():8.0f} warpcost/ray={wc/R:8.0f}")
