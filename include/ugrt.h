@@ -153,6 +153,9 @@ const char *ug_version(void);
 /* host evaluation of the acosf the kernels use for the spherical light grid (a restatement of glibc 2.39's, which is what
  * the host-compiled reference calls): lets a CPU test pin it against libm without a GPU */
 void ug_acosf_host(const float *x, float *y, size_t n);
+/* host view of how the shadow pass cuts a light cell with `rays` rays and `ntri` triangles into work items:
+ * out = {rays per item, list segments, segment length, items}; items <= rays + 16 is what bounds the item table */
+void ug_shadow_item_shape(unsigned rays, unsigned ntri, unsigned out[4]);
 size_t ug_frame_const_bytes(void); /* bytes of per-frame constants ug_render_frame* uploads (pinned H2D) */
 int ug_set_stream(ug_context *ctx, void *cuda_stream); /* NULL: the context's own non-blocking stream */
 int ug_synchronize(ug_context *ctx);

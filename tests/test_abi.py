@@ -111,3 +111,28 @@ def test_acosf_restatement_matches_libm(ug, oracle):
     assert np.array_equal(nan, np.isnan(got))
     assert np.array_equal(got[~nan].view(np.uint32), want[~nan].view(np.uint32))
     assert nan.sum() > 1000 and (~nan).sum() > 8_000_000
+
+
+def test_shadow_item_table_bound(ug):
+    """The shadow pass sizes its work-item table as N + 17 C entries; that holds only if no light cell ever asks for more than
+    rays + 16 items (a spherical light grid with long lists once overflowed an N + C table silently).  Check the policy the
+    kernels use (host view of the same function) over the whole range of cell shapes, and that every item's rays and triangles
+    tile the cell exactly."""
+    import ctypes as C
+    import numpy as np
+    fn = ug.lib().ug_shadow_item_shape
+    out = (C.c_uint * 4)()
+    rng = np.random.default_rng(5)
+    rays = np.unique(np.concatenate([np.arange(0, 70), 2 ** np.arange(6, 27), 2 ** np.arange(6, 27) - 1, rng.integers(1, 1 << 26, 400)]))
+    tris = np.unique(np.concatenate([np.arange(0, 70), [127, 128, 129, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 2047, 2048, 2049, 4095, 4096, 4097],
+                                     2 ** np.arange(12, 21), rng.integers(1, 1 << 20, 300)]))
+    for r in rays:
+        for t in tris:
+            fn(int(r), int(t), out)
+            rpi, nseg, seglen, items = out[0], out[1], out[2], out[3]
+            if r == 0 or t == 0:
+                assert items == 0
+                continue
+            assert items == -(-int(r) // rpi) * nseg
+            assert items <= int(r) + 16, (r, t, rpi, nseg)
+            assert 1 <= rpi <= 32 and nseg >= 1 and seglen % 32 == 0 and nseg * seglen >= t and (nseg - 1) * seglen < t + 32 * nseg

@@ -95,7 +95,7 @@ def lib() -> C.CDLL:
             "ug_fill_coordinates_data": (C.c_int, [vp, C.POINTER(Camera)]), "ug_build_frustum_grid": (C.c_int, [vp]),
             "ug_trace": (C.c_int, [vp]), "ug_shadow_pass": (C.c_int, [vp, C.c_int, C.POINTER(Camera)]),
             "ug_simple_shade": (C.c_int, [vp]), "ug_spotlight_shade": (C.c_int, [vp]), "ug_add_shadows": (C.c_int, [vp]),
-            "ug_set_light_grid_mode": (C.c_int, [vp, C.c_int, C.c_float, C.c_float]), "ug_acosf_host": (None, [f, f, C.c_size_t]),
+            "ug_set_light_grid_mode": (C.c_int, [vp, C.c_int, C.c_float, C.c_float]), "ug_acosf_host": (None, [f, f, C.c_size_t]), "ug_shadow_item_shape": (None, [C.c_uint, C.c_uint, C.POINTER(C.c_uint)]),
             "ug_render_frame": (C.c_int, [vp, C.POINTER(FrameParams)]),
             "ug_render_frame_host": (C.c_int, [vp, C.POINTER(FrameParams), C.c_void_p]),
             "ug_get_stats": (C.c_int, [vp, C.POINTER(Stats)]), "ug_read": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_size_t]),

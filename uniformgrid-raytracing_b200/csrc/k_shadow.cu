@@ -31,7 +31,7 @@ namespace cg = cooperative_groups;
                            rays + SH_SEGBUDGET items and the table is bounded by N + (SH_SEGBUDGET + 1)*C (ugk_shadow_item_cap) */
 
 /* rays per item for a list of `ntri` triangles */
-static __device__ __forceinline__ u32 sh_rays_per_item(u32 ntri)
+static __host__ __device__ __forceinline__ u32 sh_rays_per_item(u32 ntri)
 {
 	if (ntri <= 64) return 32;
 	if (ntri <= 128) return 16;
@@ -41,7 +41,7 @@ static __device__ __forceinline__ u32 sh_rays_per_item(u32 ntri)
 	return 1;
 }
 /* segments of a list: many rays already give the cell enough items; few rays on a long list are what needs cutting */
-static __device__ __forceinline__ u32 sh_segments(u32 rays, u32 ntri)
+static __host__ __device__ __forceinline__ u32 sh_segments(u32 rays, u32 ntri)
 {
 	if (ntri <= SH_SEGMAX) return 1;
 	return min((ntri + SH_SEGMAX - 1) / SH_SEGMAX, 1u + SH_SEGBUDGET / rays);
@@ -58,7 +58,7 @@ static __device__ __forceinline__ u32 sh_segments(u32 rays, u32 ntri)
 #define SH_CROWD_NTRI 256 /* lists longer than this count as long (measured: 64 costs config B 5 us, 512+ costs the crowded cases) */
 #endif
 struct ItemShape { u32 rpi, nseg, seglen; };
-static __device__ __forceinline__ ItemShape sh_shape(u32 rays, u32 ntri)
+static __host__ __device__ __forceinline__ ItemShape sh_shape(u32 rays, u32 ntri)
 {
 	ItemShape s;
 	if (rays >= 32 && ntri > SH_CROWD_NTRI) {
@@ -72,7 +72,7 @@ static __device__ __forceinline__ ItemShape sh_shape(u32 rays, u32 ntri)
 	s.seglen = (((ntri + s.nseg - 1) / s.nseg) + 31u) & ~31u; /* whole staging batches */
 	return s;
 }
-static __device__ __forceinline__ u32 sh_items_of_cell(u32 rays, u32 ntri)
+static __host__ __device__ __forceinline__ u32 sh_items_of_cell(u32 rays, u32 ntri)
 {
 	if (!rays || !ntri) return 0;
 	const ItemShape s = sh_shape(rays, ntri);
@@ -359,6 +359,12 @@ bool ugk_regroup_fused_supported(int device)
 	return n >= 2;
 }
 size_t ugk_shadow_item_cap(int N, int C) { return (size_t)N + (size_t)(SH_SEGBUDGET + 1) * (size_t)C; }
+/* host view of the item policy, so a CPU test can check the bound the table's size rests on: items <= rays + SH_SEGBUDGET */
+extern "C" void ug_shadow_item_shape(unsigned rays, unsigned ntri, unsigned out[4])
+{
+	const ItemShape sh = sh_shape(rays ? rays : 1u, ntri);
+	out[0] = sh.rpi; out[1] = sh.nseg; out[2] = sh.seglen; out[3] = sh_items_of_cell(rays, ntri);
+}
 size_t ugk_regroup_state_entries(int C) { return ((size_t)C + 2 + RG_THREADS * 4 - 1) / (RG_THREADS * 4) + 2; }
 
 /* getRayGridMapping + processData (per_frame_funcs.h:72-137) for one light; returns false if the launch failed */
