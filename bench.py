@@ -11,9 +11,13 @@ One "step" = one frame of the hot path: [vertex transform ->] camera-grid rebuil
             stream the library launches on; L2 is flushed (256 MiB write) between timed frames.
   e2e       the same frames through the host-buffer C-ABI call (ug_render_frame_host): pinned H2D of the frame
             constants and D2H of the RGB8 image inside the timed region, wall clock.
-  N > 1     one process per GPU (torchrun); the frame is cut into N strips of cell rows, the scene is replicated,
-            every rank renders its strip straight into an NCCL buffer and the strips are gathered to rank 0
-            (NCCL over NVLink) inside the timed step.  Strong scaling: the frame is fixed.
+  N > 1     one process per GPU (torchrun), scene replicated.  Default ("frames", weak scaling): every rank renders a whole
+            frame of its own per step and the library gathers the N frames to rank 0 inside the frame's CUDA graph (the
+            shading kernels store into rank 0's IPC-mapped buffer over NVLink, NCCL handshakes, deferred completion; the
+            timed region ends with ug_comm_flush).  The same steps are then measured once more as ONE frame cut into N strips
+            of cell rows (strong scaling of the frame latency) and reported under "strips"; --shard strips makes that the headline.
+  --light-grid spherical --shader spot
+            the variant the committed display() runs (main.cu:186-219) instead of the one north-star names.
   roofline  the dominant kernel (timed live with one CUDA event per stage): algorithmic bytes/launch vs the
             measured HBM peak, plus the FP32-issue roofline that actually bounds ray traversal.
   cpu_baseline / --impl reference
@@ -149,7 +153,7 @@ def run_reference(args):
     frames = max(1, min(args.steps, int(120.0 / max(one, 1e-3))))
     base = cpu_reference(scene, frames, min(args.warmup, 1))
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": frames,
-            "warmup": min(args.warmup, 1), "ms_per_step": base["ms_per_frame"], "higher_is_better": True, "scaling": "strong",
+            "warmup": min(args.warmup, 1), "ms_per_step": base["ms_per_frame"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(scene, 1), "note": "reference kernel sources compiled as host C++ (oracle/_ref), OpenMP over "
                        "cells/pixels on all host cores; each step = one full frame; the reference has no reflection code "
