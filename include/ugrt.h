@@ -91,19 +91,18 @@ typedef struct ug_frame_params {
 	                       buffers hold one entry per (cell, slab) and primary rays follow rckernel_alpha's slab loop (trace_kernel.cu:132-229) */
 } ug_frame_params;
 
-#define UG_FLAG_FULL_BUFFERS 1 /* also fill the reference's normal/dir/shadowed buffers (decision_data.h:66-82) */
-#define UG_FLAG_NO_GRAPH 2     /* launch kernels directly instead of replaying the captured CUDA graph */
-#define UG_FLAG_GATHER_FRAMES 8 /* with ug_comm_init and no strips: every rank renders its own frame, rank 0 collects them (slot r = rank r) */
-#define UG_FLAG_GATHER_DEFERRED 64 /* with a communicator: do not wait for the gather at the end of the frame.  Rank 0's buffer holds two
-                                      slots; gathered frame k lands in slot k & 1 and is whole once frame k+1 has run on rank 0's stream, or
-                                      after ug_comm_flush.  The per-frame "done" handshake leaves the critical path (throughput mode). */
-#define UG_FLAG_STAGE_EVENTS 4 /* record one CUDA event per stage (implies NO_GRAPH); see ug_stats.ms_* */
+#define UG_FLAG_FULL_BUFFERS 1      /* also fill the reference's normal/dir/shadowed buffers (decision_data.h:66-82) */
+#define UG_FLAG_NO_GRAPH 2          /* launch kernels directly instead of replaying the captured CUDA graph */
+#define UG_FLAG_STAGE_EVENTS 4      /* record one CUDA event per stage (implies NO_GRAPH); see ug_stats.ms_* */
+#define UG_FLAG_GATHER_FRAMES 8     /* with ug_comm_init and no strips: every rank renders its own frame, rank 0 collects them (slot r = rank r) */
 #define UG_FLAG_SPHERICAL_LIGHTS 16 /* light grids and shadow-ray binning by the spherical map the committed display() uses
                                        (main.cu:189-192 getEffectiveRayGridMapping + buildSphericalGrid with x_max = y_max = M_PI)
                                        instead of the perspective one north-star names (misc_kernel.cu:63-129) */
-
-#define UG_FLAG_SPOT_SHADE 32 /* shade with Shader::spotlight_shade (shader.h:88-113 -> spot_shade, shader_kernel.cu:275-345) instead of
-                                simpleShade: what display() does from its third frame on (main.cu:205-219) */
+#define UG_FLAG_SPOT_SHADE 32       /* shade with Shader::spotlight_shade (shader.h:88-113 -> spot_shade, shader_kernel.cu:275-345) instead of
+                                       simpleShade: what display() does from its third frame on (main.cu:205-219) */
+#define UG_FLAG_GATHER_DEFERRED 64  /* with a communicator: do not wait for the gather at the end of the frame.  Rank 0's buffer holds two
+                                       slots; gathered frame k lands in slot k & 1 and is whole once frame k+1 has run on rank 0's stream, or
+                                       after ug_comm_flush.  The per-frame "done" handshake leaves the critical path (throughput mode). */
 
 /* how a light's grid is parameterised (ug_set_light_grid_mode, UG_FLAG_SPHERICAL_LIGHTS) */
 #define UG_LIGHT_GRID_PERSPECTIVE 0 /* mapSortkernel misc_kernel.cu:63-129 + DSKernel/DSFillkernel grid_kernel.cu:164-332 */
@@ -113,7 +112,7 @@ typedef struct ug_frame_params {
 enum ug_buffer {
 	UG_BUF_VERTEXLIST = 0,   /* f32[3V]  scene.h:20 */
 	UG_BUF_CAM_VALUES,       /* u32[P]   frustum_grid.h:28 d_triangle_value_list (camera grid) */
-	UG_BUF_CAM_SPAN,         /* u32[C]   frustum_grid.h:26 */
+	UG_BUF_CAM_SPAN,         /* u32[C]   frustum_grid.h:26 (C = cells x num_slabs, entry = cell*num_slabs + slab) */
 	UG_BUF_CAM_OFFSET,       /* u32[C]   frustum_grid.h:25 */
 	UG_BUF_T,                /* f32[N]   decision_data.h:13 d_primary_ray_t_value (-1 on miss) */
 	UG_BUF_ID,               /* i32[N]   decision_data.h:17 d_intersect_id (-2 on miss) */
@@ -126,7 +125,8 @@ enum ug_buffer {
 	UG_BUF_LIGHT_OFFSET,     /* u32[C] */
 	UG_BUF_LIGHT_CELL,       /* u32[N]   d_map[N..2N): light cell of every pixel's shadow ray, C = outside */
 	UG_BUF_SIZELIST,         /* u32[T]   frustum_grid.h:32 d_sizeList of the camera grid */
-	UG_BUF_RGB_FULL,         /* u8[3*W*H] rank 0 of a communicator: the gathered frame */
+	UG_BUF_RGB_FULL,         /* rank 0 of a communicator: the gathered frame(s) - two slots of 3*W*H*world bytes (the second one is only
+	                            used by UG_FLAG_GATHER_DEFERRED); strips fill the first 3*W*H bytes of a slot, frames mode all of it */
 	UG_BUF_CAM_COUNTERS,     /* u32[32]  debug: pair counters and phase time stamps of the camera-grid build */
 	UG_BUF_COUNT_
 };
