@@ -32,7 +32,20 @@ def golden_scenes():
     out["sph_tiny_ka"] = scenes.scene_tiny("ka")
     out["sph_rand_11"] = scenes.scene_random(11, 800, 96, 64, nlights=1)
     out["sph_a_256"] = scenes.scene_a(256, 256)
+    # "mode+mode+scene": spot = Shader::spotlight_shade (display() from its third frame on), slabN = NUM_SLABS N, sph as above
+    out["sph+spot+a_256"] = scenes.scene_a(256, 256)          # the committed display(), frame 3 onwards
+    out["spot+rand_11"] = scenes.scene_random(11, 800, 96, 64, nlights=1)
+    out["slab4+tiny_ka"] = scenes.scene_tiny("ka")
+    out["slab4+a_256"] = scenes.scene_a(256, 256)
+    out["sph+slab3+rand_11"] = scenes.scene_random(11, 800, 96, 64, nlights=1)
     return out
+
+
+def modes_of(name):
+    """{'spherical': bool, 'spot': bool, 'slabs': int} encoded in a fixture name (see golden_scenes)."""
+    toks = name.split("+")[:-1] if "+" in name else (["sph"] if name.startswith("sph_") else [])
+    slabs = [int(t[4:]) for t in toks if t.startswith("slab")]
+    return {"spherical": "sph" in toks, "spot": "spot" in toks, "slabs": slabs[0] if slabs else 1}
 
 
 def digest(a) -> str:
@@ -43,7 +56,8 @@ def main():
     harness.build("ref")
     ref = harness.load("ref")
     for name, scene in golden_scenes().items():
-        res = harness.run_frame(ref, scene, threads=0, spherical=name.startswith("sph_"))
+        res = harness.run_frame(ref, scene, threads=0, **modes_of(name))
+        ref.set_slabs(1)
         data = {"stages": np.array([s for s in STAGES if s in res]), "sha256": np.array([digest(res[s]) for s in STAGES if s in res]),
                 "P": np.array([res["cam_P"], res.get("light0_P", 0)], dtype=np.int64)}
         small = scene.num_pixels <= 96 * 64

@@ -15,7 +15,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 FILES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
 
 
+def modes_of(name):
+    """Modes encoded in a fixture name: "sph_x" or "mode+mode+x" with sph (spherical light grid), spot (spotlight_shade), slabN."""
+    toks = name.split("+")[:-1] if "+" in name else (["sph"] if name.startswith("sph_") else [])
+    slabs = [int(t[4:]) for t in toks if t.startswith("slab")]
+    return {"spherical": "sph" in toks, "spot": "spot" in toks, "slabs": slabs[0] if slabs else 1}
+
+
 def scene_for(name):
+    if "+" in name:
+        return scene_for(name.split("+")[-1])
     if name.startswith("sph_"):
         return scene_for(name[4:])
     if name.startswith("tiny_"):
@@ -49,7 +58,7 @@ def check(result, gold, stages=None):
 
 
 def test_golden_files_present():
-    assert len(FILES) >= 11
+    assert len(FILES) >= 16
 
 
 @pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-4] for f in FILES])
@@ -57,7 +66,10 @@ def test_oracle_reproduces_golden(oracle, path):
     name = os.path.basename(path)[:-4]
     gold = np.load(path)
     scene = scene_for(name)
-    res = harness.run_frame(oracle, scene, threads=0, spherical=name.startswith("sph_"))
+    try:
+        res = harness.run_frame(oracle, scene, threads=0, **modes_of(name))
+    finally:
+        oracle.set_slabs(1)
     assert [res["cam_P"], res.get("light0_P", 0)] == gold["P"].tolist()
     check(res, gold)
 
@@ -73,6 +85,8 @@ def test_cuda_reproduces_golden(renderer, ug, path):
     gold = np.load(path)
     scene = scene_for(name)
     renderer.set_scene(scene)
-    res = parity.gpu_frame(renderer, scene, flags=ug.FLAG_FULL_BUFFERS | (ug.FLAG_SPHERICAL_LIGHTS if name.startswith("sph_") else 0))
+    m = modes_of(name)
+    flags = ug.FLAG_FULL_BUFFERS | (ug.FLAG_SPHERICAL_LIGHTS if m["spherical"] else 0) | (ug.FLAG_SPOT_SHADE if m["spot"] else 0)
+    res = parity.gpu_frame(renderer, scene, flags=flags, slabs=m["slabs"])
     assert int(renderer.stats().cam_pairs) == int(gold["P"][0])
     check(res, gold, stages=GPU_STAGES)
