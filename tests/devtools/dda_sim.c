@@ -1,6 +1,6 @@
 /* dda_sim.c -- development tool (not product, not oracle): counts the work the reflection DDA does per ray on the
  * CPU for a given grid resolution, so the grid parameters can be chosen without GPU time.
- * gcc -O2 -shared -fPIC -o build/libddasim.so tools/dda_sim.c -lm */
+ * gcc -O2 -shared -fPIC -o build/libddasim.so tests/devtools/dda_sim.c -lm */
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>

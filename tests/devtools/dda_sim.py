@@ -1,8 +1,8 @@
-"""Development tool: reflection-ray work statistics (cells stepped / triangles tested per ray) on the CPU for
+"""Development tool (lives under tests/ because it drives the oracle, which only tests, smoke() and the bench's CPU leg may do): reflection-ray work statistics (cells stepped / triangles tested per ray) on the CPU for
 different uniform-grid resolutions.  Uses the oracle only to obtain the primary hits of the scene."""
 import ctypes as C, sys, os
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import ugrt  # noqa
 from oracle import harness
 from uniformgrid_raytracing_b200 import scenes

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """First-contact GPU check: per-stage parity against the CPU oracle with diagnostics (not a pytest)."""
 import os, sys, time, json
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import parity
