@@ -2,10 +2,10 @@
 """Print the phase time stamps the fused grid-build kernel leaves in counters[8..] (block 0's view)."""
 import os, sys, ctypes as C
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 import numpy as np, torch
-import parity
-from parity import ug
+import ugrt  # noqa: F401
+import uniformgrid_raytracing_b200 as ug
 from uniformgrid_raytracing_b200 import scenes
 s = scenes.SCENES[sys.argv[1] if len(sys.argv) > 1 else "B"]()
 r = ug.Renderer(0); r.set_scene(s)

@@ -2,10 +2,10 @@
 """Small end-to-end case for compute-sanitizer: micro scene + soup with 2 lights, strips, reflection, overflow regrow."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 import numpy as np
-import parity
-from parity import ug
+import ugrt  # noqa: F401
+import uniformgrid_raytracing_b200 as ug
 from uniformgrid_raytracing_b200 import scenes
 r = ug.Renderer(0)
 for s in (scenes.scene_tiny("ka"), scenes.scene_random(5, 3000, 128, 96, nlights=2)):
