@@ -35,6 +35,7 @@ extern "C" {
 #define UG_TILE 8          /* NUM_THREADS_X/Y, main.cu.h:24-25 */
 #define UG_MAX_LIGHTS 8    /* reference capacity is 2 (main.cu.h:61,63); only light 0 shades (shader_kernel.cu:52) */
 #define UG_MATERIAL_SIZE 6 /* main.cu.h:33 */
+#define UG_MAX_RANKS 64    /* largest communicator ug_comm_init accepts */
 #define UG_MAX_SLABS 64    /* NUM_SLABS (main.cu.h:18) is 1 in the committed build; the code for more is there and so is ours */
 
 typedef struct ug_context ug_context;

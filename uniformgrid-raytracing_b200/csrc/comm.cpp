@@ -79,6 +79,7 @@ extern "C" int ug_comm_unique_id(void *out128)
 extern "C" int ug_comm_init(ug_context *ctx, int rank, int world, const void *unique_id128)
 {
 	if (!ctx || !unique_id128 || world < 1 || rank < 0 || rank >= world) return ug_fail(ctx, UG_ERR_ARG, "ug_comm_init: bad arguments");
+	if (world > UG_MAX_RANKS) return ug_fail(ctx, UG_ERR_ARG, "ug_comm_init: %d ranks, at most %d are supported", world, UG_MAX_RANKS);
 	if (!load_nccl(ctx)) return UG_ERR_CUDA;
 	UG_CUDA(ctx, cudaSetDevice(ctx->device));
 	if (ctx->comm) { N.CommDestroy((ncclComm_t)ctx->comm); ctx->comm = nullptr; }
@@ -162,6 +163,22 @@ int ugc_ready(ug_context *ctx, cudaStream_t s)
 	if (!ctx->use_push) return UG_OK;
 	unsigned char *scr = (unsigned char *)ctx->d_comm_scratch;
 	UG_NCCL(ctx, N.AllReduce(scr + 128, scr + 128, 1, ncclUint32, ncclSum, (ncclComm_t)ctx->comm, s));
+	return UG_OK;
+}
+
+/* host-side collective decision (e.g. "did any rank overflow its pair arena?"): max over the ranks of *value */
+int ugc_allreduce_max(ug_context *ctx, cudaStream_t s, unsigned *value)
+{
+	if (!ctx->comm || ctx->comm_world <= 1) return UG_OK;
+	if (!ctx->d_comm_scratch) {
+		UG_CUDA(ctx, cudaMalloc((void **)&ctx->d_comm_scratch, 256));
+		UG_CUDA(ctx, cudaMemset(ctx->d_comm_scratch, 0, 256));
+	}
+	unsigned char *scr = (unsigned char *)ctx->d_comm_scratch;
+	UG_CUDA(ctx, cudaMemcpyAsync(scr + 192, value, 4, cudaMemcpyHostToDevice, s));
+	UG_NCCL(ctx, N.AllReduce(scr + 192, scr + 192, 1, ncclUint32, ncclMax, (ncclComm_t)ctx->comm, s));
+	UG_CUDA(ctx, cudaMemcpyAsync(value, scr + 192, 4, cudaMemcpyDeviceToHost, s));
+	UG_CUDA(ctx, cudaStreamSynchronize(s));
 	return UG_OK;
 }
 

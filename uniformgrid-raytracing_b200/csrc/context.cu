@@ -102,8 +102,13 @@ extern "C" int ug_create(ug_context **out, int device)
 	UG_CUDA(ctx, cudaEventCreate(&ctx->ev_t0));
 	UG_CUDA(ctx, cudaEventCreate(&ctx->ev_t1));
 	for (auto &ev : ctx->ev_stage) UG_CUDA(ctx, cudaEventCreate(&ev));
-	UG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_fc, sizeof(FrameConst)));
-	memset(ctx->h_fc, 0, sizeof(FrameConst));
+	ctx->h_fc = (FrameConst *)calloc(1, sizeof(FrameConst));
+	if (!ctx->h_fc) return ug_fail(ctx, UG_ERR_CUDA, "out of host memory");
+	UG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_ring, sizeof(FrameConst) * UG_FC_SLOTS));
+	memset(ctx->h_ring, 0, sizeof(FrameConst) * UG_FC_SLOTS);
+	for (int i = 0; i < UG_FC_SLOTS; i++) UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ring[i], cudaEventDisableTiming));
+	UG_CUDA(ctx, cudaMalloc((void **)&ctx->d_fc_seq, sizeof(u32)));
+	UG_CUDA(ctx, cudaMemset(ctx->d_fc_seq, 0, sizeof(u32)));
 	UG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_counters, sizeof(u32) * (4 * (2 + UG_MAX_LIGHTS) + UG_MAX_BOUNCES + 1)));
 	memset(ctx->h_counters, 0, sizeof(u32) * (4 * (2 + UG_MAX_LIGHTS) + UG_MAX_BOUNCES + 1));
 	UG_CUDA(ctx, cudaMalloc((void **)&ctx->d_fc, sizeof(FrameConst)));
@@ -155,7 +160,11 @@ extern "C" void ug_destroy(ug_context *ctx)
 	dfree(ctx->d_vertexlist); dfree(ctx->d_materiallist); dfree(ctx->d_vertex_orig_list); dfree(ctx->d_facelist); dfree(ctx->d_materiallist_index);
 	dfree(ctx->d_t); dfree(ctx->d_id); dfree(ctx->d_shadowed); dfree(ctx->d_matid); dfree(ctx->d_best); dfree(ctx->d_cell_done); dfree(ctx->d_normal); dfree(ctx->d_dir); dfree(ctx->d_rgb_own);
 	if (ctx->h_rgb_pinned) cudaFreeHost(ctx->h_rgb_pinned);
-	if (ctx->h_fc) cudaFreeHost(ctx->h_fc);
+	if (ctx->h_full_pinned) cudaFreeHost(ctx->h_full_pinned);
+	free(ctx->h_fc);
+	if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
+	for (int i = 0; i < UG_FC_SLOTS; i++) if (ctx->ev_ring[i]) cudaEventDestroy(ctx->ev_ring[i]);
+	dfree(ctx->d_fc_seq);
 	if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
 	for (int i = 0; i < 2; i++) {
 		if (ctx->h_vstage[i]) cudaFreeHost(ctx->h_vstage[i]);
@@ -560,17 +569,39 @@ static void set_rotation(ug_context *ctx, float rot)
 	ctx->h_fc->rot_sin = sinf(rot);
 }
 
+/* The constant block travels through a ring of pinned slots (ugrt_internal.h): copy the master block into the slot the
+ * next k_fetch_consts launch will read.  The slot was last read UG_FC_SLOTS uploads ago; its event has long fired unless the
+ * caller runs that many frames ahead of the GPU, so this never blocks in a normal frame loop. */
+static int stage_consts(ug_context *ctx, int *slot_out)
+{
+	const int slot = (int)(ctx->fc_seq % UG_FC_SLOTS);
+	if (ctx->ring_used[slot]) UG_CUDA(ctx, cudaEventSynchronize(ctx->ev_ring[slot]));
+	memcpy(&ctx->h_ring[slot], ctx->h_fc, sizeof(FrameConst));
+	*slot_out = slot;
+	return UG_OK;
+}
+/* after the launch (graph or direct) that contains exactly one k_fetch_consts */
+static int consts_launched(ug_context *ctx, int slot)
+{
+	ctx->fc_seq++;
+	ctx->ring_used[slot] = true;
+	UG_CUDA(ctx, cudaEventRecord(ctx->ev_ring[slot], ctx->stream));
+	return UG_OK;
+}
 static int upload_consts(ug_context *ctx)
 {
-	UG_CUDA(ctx, cudaMemcpyAsync(ctx->d_fc, ctx->h_fc, sizeof(FrameConst), cudaMemcpyHostToDevice, ctx->stream));
-	return UG_OK;
+	int slot = 0;
+	int rc = stage_consts(ctx, &slot);
+	if (rc) return rc;
+	ugk_fetch_consts(ctx->stream, ctx->h_ring, ctx->d_fc, sizeof(FrameConst), ctx->d_fc_seq, UG_FC_SLOTS);
+	UG_CUDA(ctx, cudaGetLastError());
+	return consts_launched(ctx, slot);
 }
 
 extern "C" int ug_model_rotate_bunny(ug_context *ctx, float rot_factor)
 {
 	if (!ctx || !ctx->d_vertex_orig_list) return ug_fail(ctx, UG_ERR_ARG, "rotate_bunny: init_orig_list not called");
 	UG_CUDA(ctx, cudaSetDevice(ctx->device));
-	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); /* the pinned constant block is about to be rewritten */
 	set_rotation(ctx, rot_factor);
 	int rc = upload_consts(ctx);
 	if (rc) return rc;
@@ -695,8 +726,8 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 	ctx->fused_grid_now = ctx->force_fused_grid || (!reflect && nl <= 1 && ctx->num_faces <= 150000);
 	int k = 0;
 	static_assert(sizeof(FrameConst) % 16 == 0, "FrameConst is fetched in 16-byte words");
-	if (getenv("UG_CONST_MEMCPY")) UG_CUDA(ctx, cudaMemcpyAsync(ctx->d_fc, ctx->h_fc, sizeof(FrameConst), cudaMemcpyHostToDevice, s));
-	else { ugk_fetch_consts(s, ctx->h_fc, ctx->d_fc, sizeof(FrameConst)); L.n += 1; }
+	ugk_fetch_consts(s, ctx->h_ring, ctx->d_fc, sizeof(FrameConst), ctx->d_fc_seq, UG_FC_SLOTS);
+	L.n += 1;
 	unsigned long long *const tl = ctx->d_stamps;
 	ugk_stamp(s, tl, 0);
 	stage_mark(ctx, k, stage_events); /* 0 */
@@ -789,17 +820,17 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 	 * the next frame's "ready" handshake (or ug_comm_flush) is what tells rank 0 that this one is whole */
 	const bool deferred = gather_deferred(ctx, p);
 	const size_t slot_off = deferred ? (size_t)gather_slot(ctx, p) * (ctx->rgb_full_bytes / 2) : 0;
-	size_t g_bytes[64], g_offs[64];
+	size_t g_bytes[UG_MAX_RANKS], g_offs[UG_MAX_RANKS];
 	if (gather_strips) {
 		size_t acc = 0;
-		for (int r = 0; r < ctx->comm_world && r < 64; r++) {
+		for (int r = 0; r < ctx->comm_world && r < UG_MAX_RANKS; r++) {
 			const long long lo = (long long)ctx->nby * r / ctx->comm_world, hi = (long long)ctx->nby * (r + 1) / ctx->comm_world;
 			g_bytes[r] = 3 * (size_t)ctx->W * (size_t)(hi - lo) * UG_TILE;
 			g_offs[r] = acc;
 			acc += g_bytes[r];
 		}
 	} else if (gather_frames) { /* frame-parallel rendering: frame r lands in slot r of the gathered buffer */
-		for (int r = 0; r < ctx->comm_world && r < 64; r++) { g_bytes[r] = 3 * (size_t)ctx->N; g_offs[r] = (size_t)r * g_bytes[r]; }
+		for (int r = 0; r < ctx->comm_world && r < UG_MAX_RANKS; r++) { g_bytes[r] = 3 * (size_t)ctx->N; g_offs[r] = (size_t)r * g_bytes[r]; }
 	}
 	/* fused compute + collective: with the push transport the shading kernels store every pixel a second time, straight into
 	 * rank 0's frame over NVLink (P2P stores), so the exchange overlaps the shading instead of following it as a copy */
@@ -872,9 +903,7 @@ static int prepare_frame(ug_context *ctx, const ug_frame_params *p)
 	if (rc) return rc;
 	rc = ensure_buffers(ctx, p->num_lights, (p->flags & UG_FLAG_FULL_BUFFERS) != 0, ctx->d_reflect ? p->bounces : 0);
 	if (rc) return rc;
-	/* the previous frame may still be reading the pinned block through its H2D copy */
-	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	FrameConst *fc = ctx->h_fc;
+	FrameConst *fc = ctx->h_fc; /* the master copy: no frame in flight reads it (stage_consts copies it into a ring slot) */
 	ug_camera cam;
 	memset(&cam, 0, sizeof(cam));
 	ug_camera_setCameraCenter(&cam, p->eye[0], p->eye[1], p->eye[2]);
@@ -944,6 +973,9 @@ static int run_frame_once(ug_context *ctx, const ug_frame_params *p)
 	const bool stage_events = (p->flags & UG_FLAG_STAGE_EVENTS) != 0;
 	const bool use_graph = !(p->flags & UG_FLAG_NO_GRAPH) && !stage_events;
 	const int gs = gather_slot(ctx, p); /* a deferred gather alternates between two destination slots: one captured graph per slot */
+	int fc_slot = 0;
+	int rc0 = stage_consts(ctx, &fc_slot);
+	if (rc0) return rc0;
 	if (use_graph) {
 		const unsigned long long key = frame_key(ctx, p);
 		if (!ctx->graph_exec[gs] || ctx->graph_key[gs] != key) {
@@ -973,6 +1005,8 @@ static int run_frame_once(ug_context *ctx, const ug_frame_params *p)
 		UG_CUDA(ctx, cudaEventRecord(ctx->ev_t1, ctx->stream));
 		ctx->stats.kernel_launches = L.n;
 	}
+	rc0 = consts_launched(ctx, fc_slot);
+	if (rc0) return rc0;
 	if (gather_deferred(ctx, p)) ctx->gather_seq++;
 	ctx->frame_valid = true;
 	return UG_OK;
@@ -1013,6 +1047,9 @@ extern "C" int ug_render_frame(ug_context *ctx, const ug_frame_params *p)
 extern "C" int ug_render_frame_host(ug_context *ctx, const ug_frame_params *p, uint8_t *host_rgb)
 {
 	if (!ctx || !host_rgb) return ug_fail(ctx, UG_ERR_ARG, "ug_render_frame_host: null argument");
+	/* a deferred gather is whole only after the NEXT frame's handshake (or ug_comm_flush): there is nothing this call could
+	 * hand back.  Checked before any collective, and the flag is the same on every rank, so all ranks return together. */
+	if (p && (p->flags & UG_FLAG_GATHER_DEFERRED)) return ug_fail(ctx, UG_ERR_ARG, "ug_render_frame_host: UG_FLAG_GATHER_DEFERRED frames are read with ug_comm_flush + ug_read");
 	int rc = prepare_frame(ctx, p);
 	if (rc) return rc;
 	ctx->stats.overflowed = 0;
@@ -1022,9 +1059,18 @@ extern "C" int ug_render_frame_host(ug_context *ctx, const ug_frame_params *p, u
 	bool direct = cudaPointerGetAttributes(&attr, host_rgb) == cudaSuccess && attr.type == cudaMemoryTypeHost;
 	cudaGetLastError();
 	const bool gathered = ctx->comm && ctx->comm_world > 1 && ctx->strip_count == ctx->comm_world;
+	const bool collective = gathers(ctx, p);
 	const size_t out_bytes = gathered ? 3 * (size_t)ctx->W * ctx->H : 3 * (size_t)ctx->N;
-	if (gathered && !direct && ctx->comm_rank == 0) return ug_fail(ctx, UG_ERR_ARG, "gathered frames need a pinned (cudaHostAlloc/registered) destination");
 	unsigned char *dst = direct ? host_rgb : ctx->h_rgb_pinned;
+	if (gathered && !direct && ctx->comm_rank == 0) { /* pageable destination of a gathered frame: through a pinned staging block of the full size */
+		if (ctx->h_full_bytes < out_bytes) {
+			if (ctx->h_full_pinned) cudaFreeHost(ctx->h_full_pinned);
+			ctx->h_full_pinned = nullptr; ctx->h_full_bytes = 0;
+			UG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_full_pinned, out_bytes));
+			ctx->h_full_bytes = out_bytes;
+		}
+		dst = ctx->h_full_pinned;
+	}
 	for (int attempt = 0; attempt < 3; attempt++) {
 		rc = run_frame_once(ctx, p);
 		if (rc) return rc;
@@ -1034,8 +1080,16 @@ extern "C" int ug_render_frame_host(ug_context *ctx, const ug_frame_params *p, u
 		bool grew = false;
 		rc = check_overflow(ctx, p->num_lights, &grew, p->bounces > 0 && ctx->d_reflect);
 		if (rc) return rc;
+		if (collective) {
+			/* every attempt issues the frame's collectives (handshakes, gather): the decision to run it again must be the same
+			 * on every rank, or the ranks fall out of step and hang.  One 4-byte max-allreduce after the frame. */
+			unsigned any = grew ? 1u : 0u;
+			rc = ugc_allreduce_max(ctx, ctx->stream, &any);
+			if (rc) return rc;
+			grew = any != 0;
+		}
 		if (!grew) {
-			if (!direct && !gathered) memcpy(host_rgb, ctx->h_rgb_pinned, out_bytes);
+			if (!direct && (!gathered || ctx->comm_rank == 0)) memcpy(host_rgb, dst, out_bytes);
 			return UG_OK;
 		}
 		ctx->stats.overflowed = 1;
@@ -1048,7 +1102,6 @@ extern "C" int ug_update_light_position(ug_context *ctx, const float *xyz, int n
 {
 	if (!ctx || !xyz || num_lights < 0 || num_lights > UG_MAX_LIGHTS) return ug_fail(ctx, UG_ERR_ARG, "updateLightPosition: bad arguments");
 	UG_CUDA(ctx, cudaSetDevice(ctx->device));
-	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	for (int i = 0; i < 3 * UG_MAX_LIGHTS; i++) ctx->h_fc->light_pos[i] = i < 3 * num_lights ? xyz[i] : 0.0f;
 	ctx->h_fc->num_lights = num_lights;
 	return upload_consts(ctx);
@@ -1059,7 +1112,6 @@ extern "C" int ug_fill_coordinates_data(ug_context *ctx, const ug_camera *cam)
 	if (!ctx || !cam) return ug_fail(ctx, UG_ERR_ARG, "fillCoordinatesData: bad arguments");
 	if (ctx->W <= 0) return ug_fail(ctx, UG_ERR_ARG, "fillCoordinatesData: ug_set_screen first");
 	UG_CUDA(ctx, cudaSetDevice(ctx->device));
-	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	ugh_view_const(&ctx->h_fc->cam, cam, ctx->W, ctx->H, ctx->nbx, ctx->nby, ctx->gy_lo, ctx->gy_cnt, UG_LIGHT_GRID_PERSPECTIVE, 0.0f, 0.0f, ctx->num_slabs);
 	memcpy(ctx->h_fc->shade_mv, cam->modelview_matrix, sizeof(ctx->h_fc->shade_mv));
 	memcpy(ctx->h_fc->shade_eye, cam->worldori, sizeof(ctx->h_fc->shade_eye));
@@ -1104,7 +1156,6 @@ extern "C" int ug_shadow_pass(ug_context *ctx, int light_id, const ug_camera *li
 	if (ctx->num_lights <= light_id) ctx->num_lights = light_id + 1;
 	int rc = ensure_buffers(ctx, ctx->num_lights, ctx->full_alloc);
 	if (rc) return rc;
-	UG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	ugh_view_const(&ctx->h_fc->light[light_id], light_cam, ctx->W, ctx->H, ctx->nbx, ctx->nby, 0, ctx->nby, ctx->light_grid_mode, ctx->light_xM, ctx->light_yM, ctx->num_slabs);
 	memcpy(ctx->h_fc->shade_mv, light_cam->modelview_matrix, sizeof(ctx->h_fc->shade_mv)); /* fillCoordinatesData with the light camera */
 	memcpy(ctx->h_fc->shade_eye, light_cam->worldori, sizeof(ctx->h_fc->shade_eye));

@@ -145,14 +145,20 @@ void ugk_publish(cudaStream_t s, const u32 *const *src, const int *words, const 
 	k_publish<<<1, 64, 0, s>>>(a, host_block);
 }
 
-/* the frame's constant block comes from the context's pinned (device-visible) host copy: a one-block kernel pulls its
- * ~6 KB over PCIe and stores them in device memory - a kernel node starts sooner than a copy-engine node at the head
- * of the frame graph */
-__global__ void k_fetch_consts(const uint4 *__restrict__ host_block, uint4 *__restrict__ dev_block, int n16)
+/* the frame's constant block comes from a ring of pinned (device-visible) host slots: a one-block kernel pulls the ~6 KB
+ * of slot (seq % slots) over PCIe, stores them in device memory and advances the device-side sequence counter.  A kernel
+ * node starts sooner than a copy-engine node at the head of the frame graph, and because the slot is chosen on the device
+ * the captured graph is launched unchanged while the host fills the next slot (no host synchronisation per frame). */
+__global__ void k_fetch_consts(const uint4 *__restrict__ host_ring, uint4 *__restrict__ dev_block, int n16, u32 *seq, int slots)
 {
-	for (int i = threadIdx.x; i < n16; i += blockDim.x) dev_block[i] = host_block[i];
+	__shared__ u32 s_seq;
+	if (threadIdx.x == 0) s_seq = *seq;
+	__syncthreads();
+	const uint4 *src = host_ring + (size_t)(s_seq % (u32)slots) * (size_t)n16;
+	for (int i = threadIdx.x; i < n16; i += blockDim.x) dev_block[i] = src[i];
+	if (threadIdx.x == 0) *seq = s_seq + 1u;
 }
-void ugk_fetch_consts(cudaStream_t s, const void *host_block, void *dev_block, size_t bytes)
+void ugk_fetch_consts(cudaStream_t s, const void *host_ring, void *dev_block, size_t bytes, u32 *seq, int slots)
 {
-	k_fetch_consts<<<1, 512, 0, s>>>((const uint4 *)host_block, (uint4 *)dev_block, (int)(bytes / 16));
+	k_fetch_consts<<<1, 512, 0, s>>>((const uint4 *)host_ring, (uint4 *)dev_block, (int)(bytes / 16), seq, slots);
 }

@@ -89,6 +89,7 @@ struct LightRays {         /* DecisionData's regroup state (decision_data.h:72-8
 
 struct UGridConst;
 #define UG_MAX_BOUNCES 31
+#define UG_FC_SLOTS 4
 struct ReflectState {      /* row R: world-space uniform grid + per-pixel reflection ray state (k_reflect.cu) */
 	GridBuffers grid;      /* count/scan/keys/vals/span/offset of the uniform grid; grid.C = cell arena */
 	u32 *box = nullptr;    /* [6] scene bounding box (order-preserving uint encoding) */
@@ -143,7 +144,15 @@ struct ug_context {
 	int N = 0, C_cam = 0, C_light = 0; /* pixels / cells of this strip; cells of a (full) light grid */
 
 	/* frame constants */
-	FrameConst *h_fc = nullptr; /* pinned */
+	/* h_fc is the host master copy every entry point edits.  Each upload copies it into the next slot of a small pinned
+	 * ring; the frame's first kernel (k_fetch_consts) picks its slot from a device-side sequence counter that the host
+	 * mirrors, so a captured graph never needs patching and ug_render_frame never waits for the previous frame. */
+	FrameConst *h_fc = nullptr;
+	FrameConst *h_ring = nullptr;              /* pinned [UG_FC_SLOTS] */
+	cudaEvent_t ev_ring[UG_FC_SLOTS] = {};     /* recorded after the launch that reads the slot */
+	bool ring_used[UG_FC_SLOTS] = {};
+	u32 *d_fc_seq = nullptr;                   /* device mirror of fc_seq (advanced by k_fetch_consts) */
+	unsigned long long fc_seq = 0;
 	FrameConst *d_fc = nullptr;
 	float *h_vstage[2] = {nullptr, nullptr}; /* pinned staging of the keyframe loader (ug_model_update_vertices), alternating */
 	cudaEvent_t ev_vstage[2] = {nullptr, nullptr};
@@ -175,6 +184,8 @@ struct ug_context {
 	unsigned char *d_rgb_own = nullptr, *d_rgb_ext = nullptr;
 	size_t rgb_ext_bytes = 0;
 	unsigned char *h_rgb_pinned = nullptr;
+	unsigned char *h_full_pinned = nullptr; /* rank 0: staging of a gathered frame whose destination is pageable */
+	size_t h_full_bytes = 0;
 	size_t pix_alloc = 0;
 	bool full_alloc = false;
 
@@ -211,7 +222,7 @@ void ug_drop_graphs(ug_context *ctx);
 
 /* ---------------------------------------------------------------- kernel launchers (k_*.cu) */
 /* K1 transform */
-void ugk_fetch_consts(cudaStream_t s, const void *host_block, void *dev_block, size_t bytes);
+void ugk_fetch_consts(cudaStream_t s, const void *host_ring, void *dev_block, size_t bytes, u32 *seq, int slots);
 void ugk_publish(cudaStream_t s, const u32 *const *src, const int *words, const int *dst_off, int n, u32 *host_block);
 void ugk_stamp(cudaStream_t s, unsigned long long *slots, int slot);
 void ugk_transform(cudaStream_t s, float *vertexlist, const float *orig, int size, int offset, const FrameConst *fc, int sms);
@@ -270,6 +281,7 @@ int ugc_ready(ug_context *ctx, cudaStream_t s);
 int ugc_gather_strips(ug_context *ctx, cudaStream_t s, const unsigned char *strip, size_t slot_offset, const size_t *bytes, const size_t *offs, bool deferred,
                       bool already_stored);
 int ugc_flush(ug_context *ctx, cudaStream_t s);
+int ugc_allreduce_max(ug_context *ctx, cudaStream_t s, unsigned *value); /* host value in/out; synchronises s */
 
 /* host helpers (camera_host.cpp, obj_loader.cpp) */
 void ugh_view_const(ViewConst *vc, const ug_camera *cam, int W, int H, int nbx, int nby, int gy_lo, int gy_cnt, int grid_mode = UG_LIGHT_GRID_PERSPECTIVE,
