@@ -21,7 +21,8 @@ from oracle import harness  # noqa: E402
 from uniformgrid_raytracing_b200 import scenes  # noqa: E402
 
 STAGES = ["camcoords", "dirtex", "cam_values", "cam_span", "cam_offset", "t", "id", "normal", "dir", "light0_camcoords", "light0_cell",
-          "light0_values", "light0_span", "light0_offset", "shadowed", "rgb_unshadowed", "material_id", "rgb"]
+          "light0_values", "light0_span", "light0_offset", "light1_cell", "light1_values", "light1_span", "light1_offset", "shadowed",
+          "rgb_unshadowed", "material_id", "rgb"]
 
 
 def golden_scenes():
@@ -38,6 +39,10 @@ def golden_scenes():
     out["slab4+tiny_ka"] = scenes.scene_tiny("ka")
     out["slab4+a_256"] = scenes.scene_a(256, 256)
     out["sph+slab3+rand_11"] = scenes.scene_random(11, 800, 96, 64, nlights=1)
+    # the BASELINE configs at their stated sizes (primary + shadow rays: the part of the frame the reference defines)
+    out["b_full"] = scenes.scene_b()          # 80 000 triangles, 1024x1024, 1 light
+    out["c_full"] = scenes.scene_c()          # 174 000 triangles, 1920x1080, 2 lights, frame 0 of the dynamic scene
+    out["d_full"] = scenes.scene_d()          # 282 000 triangles, 4096x4096, 1 light
     return out
 
 
@@ -55,18 +60,22 @@ def digest(a) -> str:
 def main():
     harness.build("ref")
     ref = harness.load("ref")
+    only = set(sys.argv[1:])
     for name, scene in golden_scenes().items():
+        if only and name not in only:
+            continue
         res = harness.run_frame(ref, scene, threads=0, **modes_of(name))
         ref.set_slabs(1)
         data = {"stages": np.array([s for s in STAGES if s in res]), "sha256": np.array([digest(res[s]) for s in STAGES if s in res]),
                 "P": np.array([res["cam_P"], res.get("light0_P", 0)], dtype=np.int64)}
         small = scene.num_pixels <= 96 * 64
-        keep = STAGES if small else ["camcoords", "dirtex", "cam_span", "light0_span"]
+        big = scene.num_pixels > 512 * 512
+        keep = STAGES if small else (["camcoords", "dirtex"] if big else ["camcoords", "dirtex", "cam_span", "light0_span"])
         for s in keep:
             if s in res:
                 data["full_" + s] = np.asarray(res[s])
         if not small:  # a strided sample of the per-pixel buffers
-            idx = np.arange(0, scene.num_pixels, 97)
+            idx = np.arange(0, scene.num_pixels, 4999 if big else 97)
             data["sample_idx"] = idx
             for s in ("t", "id", "shadowed", "light0_cell"):
                 data["sample_" + s] = np.asarray(res[s])[idx]

@@ -33,6 +33,8 @@ def scene_for(name):
         return scenes.scene_random(11, 800, 96, 64, nlights=1)
     if name == "a_256":
         return scenes.scene_a(256, 256)
+    if name.endswith("_full"):          # the BASELINE configs at their stated sizes
+        return {"b": scenes.scene_b, "c": scenes.scene_c, "d": scenes.scene_d}[name[0]]()
     raise KeyError(name)
 
 
@@ -58,7 +60,7 @@ def check(result, gold, stages=None):
 
 
 def test_golden_files_present():
-    assert len(FILES) >= 16
+    assert len(FILES) >= 19
 
 
 @pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-4] for f in FILES])
@@ -75,7 +77,7 @@ def test_oracle_reproduces_golden(oracle, path):
 
 
 GPU_STAGES = ["cam_values", "cam_span", "cam_offset", "t", "id", "normal", "dir", "light0_cell", "light0_values", "light0_span", "light0_offset",
-              "shadowed", "rgb"]
+              "light1_cell", "light1_values", "light1_span", "light1_offset", "shadowed", "rgb"]
 
 
 @pytest.mark.gpu
