@@ -250,6 +250,8 @@ void check_for_shadows(int light_id);                    /* per_frame_funcs.h:13
 ug_context *ug_default_context(void);
 ug_camera *ug_default_camera(void);                      /* the global `camera` (main.cu:28) */
 void ug_default_set_light(int light_id, const ug_light *l);
+void ug_default_tmp_model(int i);                        /* model->tmp_model(argv[1], i), scene.h:70-120: keyframe i of the directory init_model was given */
+int ug_default_num_frames(void);                         /* Model::num_frames (scene.h:33): argv[3] of a directory scene, else 1 */
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,8 @@
 #include "ugrt_internal.h"
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
+#include <sys/types.h>
 
 static ug_context *g_ctx = nullptr;
 static ug_camera g_camera;
@@ -14,6 +16,8 @@ static ug_light g_lights[UG_MAX_LIGHTS];
 static float g_light_xyz[3 * UG_MAX_LIGHTS] = {10.0f, 12.0f, 6.0f}; /* per_frame_funcs.h:8-10 */
 static int g_num_lights = 1;                                        /* main.cu.h:40 h_numLights */
 static int g_current_light = 0;
+static int g_frames = 1;             /* Model::num_frames (scene.h:33, 59-67): > 1 = keyframed scene */
+static std::string g_model_path;     /* argv[1]: the OBJ, or the directory holding f_<i>.obj */
 
 static void die(int rc, const char *what)
 {
@@ -57,9 +61,34 @@ void init_model(int argc, char **argv)
 		fprintf(stderr, "USAGE: ./exec {file/dir_name}.obj [number_frames]\n");
 		exit(-1);
 	}
+	/* per_app_funcs.h:14-30: a directory means a keyframed scene, f_0.obj ... f_<frames-1>.obj, and needs the frame count */
+	int frames = 1;
+	struct stat sb;
+	const bool is_dir = stat(argv[1], &sb) == 0 && S_ISDIR(sb.st_mode);
+	if (is_dir) {
+		if (argc < 4) {
+			fprintf(stderr, "USAGE: ./exec {dir_name}.ply [desc_file] [number_frames]\n");
+			exit(-1);
+		}
+		frames = atoi(argv[3]);
+	}
 	ug_context *ctx = ug_default_context();
-	die(ug_model_load(ctx, argv[1], argc > 2 ? argv[2] : NULL), "init_model");
+	g_frames = frames;
+	g_model_path = argv[1];
+	/* Model::Model(frames): dynamic iff frames > 1 (scene.h:59-67); Model::load_model then reads <dir>/f_0.obj once and
+	 * keeps its topology (scene.h:142-222), later frames come through Model::tmp_model == ug_default_tmp_model.  Unlike the
+	 * reference's dynamic branch, which never fills h_materiallist_index, the first keyframe's usemtl indices are kept. */
+	std::string first = g_model_path;
+	if (is_dir && frames > 1) first += "/f_0.obj";
+	die(ug_model_load(ctx, first.c_str(), argc > 2 ? argv[2] : NULL), "init_model");
 }
+
+/* Model::tmp_model(path, i) on the default context's model, path = what init_model was given (scene.h:70-120) */
+void ug_default_tmp_model(int i)
+{
+	die(ug_model_tmp_model(ug_default_context(), g_model_path.c_str(), i), "tmp_model");
+}
+int ug_default_num_frames(void) { return g_frames; }
 
 /* per_app_funcs.h:39-66 */
 void writePPM(char *filename) { die(ug_write_ppm(ug_default_context(), filename), "writePPM"); }
