@@ -135,7 +135,7 @@ def test_spherical_build_variants(renderer, ug, oracle, monkeypatch):
     """Both build variants (one cooperative kernel / kernel chain) of the spherical light grid give the same lists."""
     s = scenes.scene_a(256, 256)
     cpu = cpu_frame(oracle, s, spherical=True)
-    for env in ({"UG_NO_FUSED": "1"}, {"UG_FUSED_GRID": "1", "UG_FUSED_REGROUP": "1"}):
+    for env in ({"UG_NO_FUSED": "1"}, {"UG_FUSED_GRID": "1", "UG_FUSED_REGROUP": "1"}, {"UG_NO_SWEEP": "1"}):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         r = ug.Renderer(0)
@@ -372,11 +372,12 @@ def test_reflection_row_r(renderer, ug, oracle, make, bounces):
     assert np.array_equal(plain["rgb"], cpu["rgb"])
 
 
-@pytest.mark.parametrize("env", [{"UG_NO_FUSED": "1"}, {"UG_FUSED_GRID": "1", "UG_FUSED_REGROUP": "1", "UG_FUSED_UGRID": "1"}])
+@pytest.mark.parametrize("env", [{"UG_NO_FUSED": "1"}, {"UG_FUSED_GRID": "1", "UG_FUSED_REGROUP": "1", "UG_FUSED_UGRID": "1"}, {"UG_NO_SWEEP": "1"}, {}])
 def test_build_variants(ug, oracle, env, monkeypatch):
-    """Every grid / regroup / uniform-grid build exists as a kernel chain and as a one-launch cooperative kernel; which one
-    a frame uses is a per-frame policy (context.cu), so both are forced here: two lights + two reflection bounces."""
-    for k in ("UG_NO_FUSED", "UG_FUSED_GRID", "UG_FUSED_REGROUP", "UG_FUSED_UGRID"):
+    """Every view grid can be built three ways - the three one-sweep launches of k_gridsweep.cu (default), the 8-bit LSD
+    kernel chain, the one-launch cooperative kernel - and regroup / uniform grid two ways; which one a frame uses is a
+    policy (context.cu), so each is forced here: two lights + two reflection bounces."""
+    for k in ("UG_NO_FUSED", "UG_FUSED_GRID", "UG_FUSED_REGROUP", "UG_FUSED_UGRID", "UG_NO_SWEEP"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)

@@ -64,6 +64,9 @@ extern "C" int ug_create(ug_context **out, int device)
 	 * kernels interleave with the other branches, come out ahead - measured per config in DESIGN.md section 7.  So the
 	 * grid build is chosen per frame (fused_grid_now), the other two are opt-in.  UG_NO_FUSED / UG_FUSED_* override. */
 	ctx->use_fused = ugk_grid_fused_supported(device) && !getenv("UG_NO_FUSED") && !getenv("UG_NO_FUSED_GRID");
+	/* the default build of every perspective / spherical grid: three one-sweep launches (k_gridsweep.cu).  UG_NO_SWEEP, or any
+	 * switch that forces one of the other two variants, turns it off. */
+	ctx->use_sweep = !getenv("UG_NO_SWEEP") && !getenv("UG_NO_FUSED") && !getenv("UG_FUSED_GRID");
 	ctx->fused_gather = !getenv("UG_NO_FUSED_GATHER");
 	ctx->use_fused_regroup = ugk_regroup_fused_supported(device) && !getenv("UG_NO_FUSED") && getenv("UG_FUSED_REGROUP");
 	ctx->use_fused_ugrid = ugk_ugrid_fused_supported(device) && !getenv("UG_NO_FUSED") && getenv("UG_FUSED_UGRID");
@@ -123,6 +126,7 @@ static void free_grid(GridBuffers &g)
 	dfree(g.span); dfree(g.offset); dfree(g.counters);
 	dfree(g.sort.tile_hist); dfree(g.sort.tile_base); dfree(g.sort.scan_state);
 	dfree(g.fused_hist); dfree(g.fused_tot); dfree(g.fused_state_a); dfree(g.fused_state_b);
+	dfree(g.sweep_hist); dfree(g.sweep_base); dfree(g.sweep_ctl); dfree(g.sweep_tile_first); dfree(g.sweep_desc_a); dfree(g.sweep_desc_b); dfree(g.sweep_desc);
 	dfree(g.projz); dfree(g.zrange); dfree(g.cspan); dfree(g.coffset);
 	g = GridBuffers();
 }
@@ -214,7 +218,7 @@ extern "C" int ug_synchronize(ug_context *ctx)
 }
 
 /* ------------------------------------------------------------------ arenas */
-static int alloc_grid(ug_context *ctx, GridBuffers &g, int T, int C, size_t cap, int S = 0)
+static int alloc_grid(ug_context *ctx, GridBuffers &g, int T, int C, size_t cap, int S = 0, bool view_grid = true)
 {
 	if (S <= 0) S = g.S > 0 ? g.S : 1; /* regrowing keeps the slab count; C counts (cell, slab) entries */
 	if (g.T == T && g.C == C && g.S == S && g.cap >= cap && g.tri_rec) return UG_OK;
@@ -255,6 +259,24 @@ static int alloc_grid(ug_context *ctx, GridBuffers &g, int T, int C, size_t cap,
 		UG_CUDA(ctx, dmalloc(&g.fused_state_b, nb));
 		UG_CUDA(ctx, cudaMemset(g.fused_state_a, 0, sizeof(u64) * na));
 		UG_CUDA(ctx, cudaMemset(g.fused_state_b, 0, sizeof(u64) * nb));
+	}
+	/* three-launch build: sorts on (cell column, cell row), one digit each.  Descriptors are tagged with the build's sequence
+	 * number, so they are cleared once, here. */
+	if (view_grid && S == 1 && ctx->nbx > 0 && ctx->nbx <= UG_SWEEP_MAXB && ctx->nby <= UG_SWEEP_MAXB && g.cap < (1ull << 30) && C <= ctx->nbx * ctx->nby) {
+		const size_t na = ugk_sweep_desc_a(T), nb = ugk_sweep_desc_b(C), nd = ugk_sweep_desc(g.cap, ctx->nbx > ctx->nby ? ctx->nbx : ctx->nby);
+		UG_CUDA(ctx, dmalloc(&g.sweep_hist, ugk_sweep_hist_words()));
+		UG_CUDA(ctx, dmalloc(&g.sweep_base, 2 * UG_SWEEP_MAXB));
+		UG_CUDA(ctx, dmalloc(&g.sweep_ctl, 8));
+		UG_CUDA(ctx, dmalloc(&g.sweep_tile_first, ugk_sweep_tiles(g.cap)));
+		UG_CUDA(ctx, cudaMemset(g.sweep_tile_first, 0, sizeof(u32) * ugk_sweep_tiles(g.cap)));
+		UG_CUDA(ctx, dmalloc(&g.sweep_desc_a, na));
+		UG_CUDA(ctx, dmalloc(&g.sweep_desc_b, nb));
+		UG_CUDA(ctx, dmalloc(&g.sweep_desc, nd));
+		UG_CUDA(ctx, cudaMemset(g.sweep_hist, 0, sizeof(u32) * ugk_sweep_hist_words()));
+		UG_CUDA(ctx, cudaMemset(g.sweep_ctl, 0, sizeof(u32) * 8));
+		UG_CUDA(ctx, cudaMemset(g.sweep_desc_a, 0, sizeof(u64) * na));
+		UG_CUDA(ctx, cudaMemset(g.sweep_desc_b, 0, sizeof(u64) * nb));
+		UG_CUDA(ctx, cudaMemset(g.sweep_desc, 0, sizeof(u64) * nd));
 	}
 	return UG_OK;
 }
@@ -310,7 +332,7 @@ static int alloc_reflect(ug_context *ctx, int T, int N, int bounces)
 	if (cells < 4096) cells = 4096;
 	if (cells > (1ll << 23)) cells = 1ll << 23;
 	const size_t cap = (size_t)24 * (size_t)T + (size_t)cells + (1u << 20);
-	int rc = alloc_grid(ctx, r.grid, T, (int)cells, keep > cap ? keep : cap);
+	int rc = alloc_grid(ctx, r.grid, T, (int)cells, keep > cap ? keep : cap, 0, false);
 	if (rc) return rc;
 	UG_CUDA(ctx, dmalloc(&r.box, 8));
 	{ /* empty box in the order-preserving encoding; the fused build leaves it like this after every launch */
@@ -665,6 +687,9 @@ static void enqueue_grid(ug_context *ctx, cudaStream_t s, const ViewConst *vc, G
 	const bool want_fused = (&g == &ctx->cam_grid) ? ctx->fused_cam_now : ctx->fused_grid_now;
 	if (g.S > 1) { /* depth slabs: kernel chain only - the slab of a triangle needs the z range of ALL triangles before any pair is emitted */
 		ugk_slab_reset(s, vc, g);                                                                       L.n += 1;
+	} else if (ctx->use_sweep && g.sweep_desc) {
+		g.final_buf = ugk_grid_sweep(s, vc, ctx->d_facelist, ctx->d_vertexlist, g, sms, &L.n);
+		return;
 	} else if (ctx->use_fused && want_fused && g.key_bits <= 32) {
 		const int fb = ugk_grid_fused(s, vc, ctx->d_facelist, ctx->d_vertexlist, g, sms);
 		if (fb >= 0) { g.final_buf = fb; L.n += 1; return; }
@@ -1025,7 +1050,7 @@ static int check_overflow(ug_context *ctx, int num_lights, bool *grew, bool refl
 		const u32 *c = ctx->h_counters + 4 * ((reflect && i == n - 1) ? 1 + UG_MAX_LIGHTS : i); /* copied by the frame itself; the caller has synchronised */
 		if (c[1]) {
 			const size_t want = (size_t)c[2] + (size_t)c[2] / 4 + 1024;
-			int rc = alloc_grid(ctx, *gs[i], gs[i]->T, gs[i]->C, want);
+			int rc = alloc_grid(ctx, *gs[i], gs[i]->T, gs[i]->C, want, 0, gs[i] != &ctx->refl.grid);
 			if (rc) return rc;
 			if (gs[i] == &ctx->refl.grid && (rc = alloc_reflect_records(ctx)) != UG_OK) return rc;
 			*grew = true;

@@ -61,6 +61,9 @@ struct GridBuffers {       /* FrustumGrid, frustum_grid.h:15-68 */
 	SortScratch sort;
 	u32 *fused_hist = nullptr, *fused_tot = nullptr; /* scratch of the fused build (k_gridfused.cu) */
 	u64 *fused_state_a = nullptr, *fused_state_b = nullptr;
+	/* scratch of the three-launch build (k_gridsweep.cu); null when the grid is not eligible (more than UG_SWEEP_MAXB cell rows or columns) */
+	u32 *sweep_hist = nullptr, *sweep_base = nullptr, *sweep_ctl = nullptr, *sweep_tile_first = nullptr;
+	u64 *sweep_desc_a = nullptr, *sweep_desc_b = nullptr, *sweep_desc = nullptr;
 	size_t cap = 0;            /* pair capacity */
 	int final_buf = 0;         /* which of vals[] holds the sorted list */
 	int key_bits = 0;
@@ -90,6 +93,7 @@ struct LightRays {         /* DecisionData's regroup state (decision_data.h:72-8
 struct UGridConst;
 #define UG_MAX_BOUNCES 31
 #define UG_FC_SLOTS 4
+#define UG_SWEEP_MAXB 1024 /* k_gridsweep.cu sorts on (cell column, cell row): at most this many of each */
 struct ReflectState {      /* row R: world-space uniform grid + per-pixel reflection ray state (k_reflect.cu) */
 	GridBuffers grid;      /* count/scan/keys/vals/span/offset of the uniform grid; grid.C = cell arena */
 	u32 *box = nullptr;    /* [6] scene bounding box (order-preserving uint encoding) */
@@ -126,6 +130,7 @@ struct ug_context {
 	int num_sms = 148;
 	bool use_fused_regroup = true;
 	bool use_fused = true;      /* fused cooperative grid build when the device supports it (UG_NO_FUSED=1 disables) */
+	bool use_sweep = true;      /* three-launch one-sweep grid build (k_gridsweep.cu) where eligible (UG_NO_SWEEP=1 disables) */
 
 	/* Model (scene.h:13-57) */
 	std::vector<float> h_vertexlist, h_materiallist;
@@ -240,6 +245,12 @@ size_t ugk_grid_fused_state_a(int T);
 size_t ugk_grid_fused_state_b(int C);
 size_t ugk_grid_fused_hist(int sms);
 int ugk_grid_fused(cudaStream_t s, const ViewConst *vc, const int *faces, const float *verts, GridBuffers &g, int sms);
+size_t ugk_sweep_desc_a(int T);
+size_t ugk_sweep_desc_b(int C);
+size_t ugk_sweep_desc(size_t cap, int bins);
+size_t ugk_sweep_hist_words();
+size_t ugk_sweep_tiles(size_t cap);
+int ugk_grid_sweep(cudaStream_t s, const ViewConst *vc, const int *faces, const float *verts, GridBuffers &g, int sms, int *launches);
 /* radix sort / scan primitives (k_sort.cu) */
 size_t ugk_scan_tiles(size_t n);
 /* stable LSD radix sort of (key,val) pairs on `bits` key bits; n read from *n_dev (<= n_max).
