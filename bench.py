@@ -11,11 +11,16 @@ One "step" = one frame of the hot path: [vertex transform ->] camera-grid rebuil
             stream the library launches on; L2 is flushed (256 MiB write) between timed frames.
   e2e       the same frames through the host-buffer C-ABI call (ug_render_frame_host): pinned H2D of the frame
             constants and D2H of the RGB8 image inside the timed region, wall clock.
-  N > 1     one process per GPU (torchrun), scene replicated.  Default ("frames", weak scaling): every rank renders a whole
-            frame of its own per step and the library gathers the N frames to rank 0 inside the frame's CUDA graph (the
-            shading kernels store into rank 0's IPC-mapped buffer over NVLink, NCCL handshakes, deferred completion; the
-            timed region ends with ug_comm_flush).  The same steps are then measured once more as ONE frame cut into N strips
-            of cell rows (strong scaling of the frame latency) and reported under "strips"; --shard strips makes that the headline.
+  N = 1     config B (the configuration BASELINE.json quotes the metric on); the line also carries config D's one-GPU frame
+            time under "config_D_single_gpu", the denominator of the N > 1 series.
+  N > 1     one process per GPU (torchrun), scene replicated.  Default: config D (282 000 triangles, 4096x4096) as ONE frame
+            cut into N image strips of cell rows - the tile sharding north-star names, strong scaling of the frame latency.
+            Every rank builds the camera grid of its own sub-frustum, traces and shades its strip, and the shading kernel
+            stores the RGB8 pixels straight into rank 0's IPC-mapped frame over NVLink (P2P stores; NCCL carries the two
+            4-byte handshakes), all inside the frame's CUDA graph.  After the timed region rank 0 renders the same frame alone
+            and the gathered frame must hash to the same bytes ("gathered_frame_check"); that one-GPU time is reported as
+            "single_gpu_same_frame".  The frame-parallel mode (one whole frame per GPU per step, weak scaling, deferred
+            gather) is measured beside it and reported under "frames"; --shard frames makes it the headline.
   --light-grid spherical --shader spot
             the variant the committed display() runs (main.cu:186-219) instead of the one north-star names.
   roofline  the dominant kernel (timed live with one CUDA event per stage): algorithmic bytes/launch vs the
@@ -140,7 +145,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    scene = make_scene(args.config)
+    scene = make_scene(args.config or ("B" if args.gpus <= 1 else "D"))   # the product arm's workload at this N
     # each step = one full frame of the workload; K is honoured unless that would take more than ~2 minutes (the first
     # frame is timed to find out), in which case fewer steps are run and the line says how many
     from oracle import harness
@@ -187,7 +192,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     hbm_peak, peak_kind, sm_max = load_peaks()
 
-    scene = make_scene(args.config)
+    config = args.config or ("B" if world == 1 else "D")
+    scene = make_scene(config)
     r = ug.Renderer(local)
     r.set_scene(scene)
     # the library launches on the stream it is given (NULL would mean its own stream): a dedicated torch stream, made
@@ -200,13 +206,13 @@ def run_ours(args):
     #                     so this is the weak-scaling (throughput) series; N = 1 is the same workload
     #   strips          : ONE frame cut into image strips of cell rows, gathered inside the frame graph - strong scaling
     #                     (latency) of a single frame; measured after the main loop too and reported under "strips"
-    mode = "single" if world == 1 else ("strips" if args.shard == "strips" else "frames")
+    mode = "single" if world == 1 else ("frames" if args.shard == "frames" else "strips")
     nby = scene.height // 8
 
     def strip_of(m):
         return (rank, world) if m == "strips" else (0, 1)
 
-    def join_comm():   # the library gathers the strips itself (NCCL send/recv inside the frame's CUDA graph)
+    def join_comm():   # the library gathers the strips itself (P2P stores over NVLink + NCCL handshakes, inside the frame's CUDA graph)
         uid = [ug.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         r.comm_init(rank, world, uid[0])
@@ -228,7 +234,7 @@ def run_ours(args):
     def step(i, flags=0, m=None):
         m = m or mode
         flags |= base_flags
-        if m == "frames":   # whole frames, collected on rank 0 by the library's own NCCL send/recv inside the frame graph
+        if m == "frames":   # whole frames, collected on rank 0 by the library itself inside the frame graph
             # deferred completion: frame i is whole on rank 0 once frame i+1 has passed its "ready" handshake, or after
             # comm_flush() - the per-frame "done" handshake is off the critical path, the timed region ends with the flush
             r.render(r.params(scene, frame=i * world + rank, flags=flags | ug.FLAG_GATHER_FRAMES | ug.FLAG_GATHER_DEFERRED, bounces=bounces, slabs=args.slabs))
@@ -323,25 +329,88 @@ def run_ours(args):
             stage[k] = stage.get(k, 0.0) + v / reps
     st2 = r.stats()
 
-    # ---- N > 1 in frames mode: the same K steps once more as ONE frame in strips (strong scaling of the frame latency)
-    strips = None
-    if mode == "frames":
+    # ---- N > 1: the same workload once more in the OTHER sharding mode (strips <-> frames), reported beside the headline
+    other = None
+    if world > 1:
+        om = "frames" if mode == "strips" else "strips"
         for i in range(5):
-            step(i, m="strips")
+            step(i, m=om)
+        if om == "frames":
+            r.comm_flush()
         barrier()
-        k2 = min(args.steps, 50)
+        k2 = min(args.steps, 30)
         ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k2)]
         for i in range(k2):
             if not args.no_flush:
                 flush.zero_()
             ev2[i][0].record()
-            step(i, m="strips")
+            step(i, m=om)
             ev2[i][1].record()
+        tail2 = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        tail2[0].record()
+        if om == "frames":
+            r.comm_flush()
+        tail2[1].record()
         barrier()
-        t2 = torch.tensor([a.elapsed_time(b) for a, b in ev2], dtype=torch.float64, device=dev)
+        t2 = torch.tensor([a.elapsed_time(b) for a, b in ev2] + [tail2[0].elapsed_time(tail2[1])], dtype=torch.float64, device=dev)
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        strips = {"ms_per_frame": float(t2.mean().item()), "steps": k2, "scaling": "strong",
-                  "note": "one frame cut into %d image strips of cell rows, gathered to rank 0 inside the frame graph (NCCL send/recv)" % world}
+        ms2 = float(t2.sum().item()) / k2
+        fps2 = world if om == "frames" else 1
+        other = {"mode": om, "ms_per_step": ms2, "steps": k2, "scaling": "weak" if om == "frames" else "strong", "frames_per_step": fps2,
+                 "note": ("one whole frame per GPU per step, gathered to rank 0 with deferred completion" if om == "frames" else
+                          "one frame cut into %d image strips of cell rows" % world) + "; shading kernels store into rank 0's frame over NVLink (P2P), NCCL handshakes"}
+
+    # ---- N > 1, strips: rank 0's gathered frame must be the frame one GPU renders alone; that render is also the 1-GPU time of this workload
+    check, single = None, None
+    if world > 1:
+        import hashlib
+        r.render_host(r.params(scene, frame=0, flags=base_flags, strip=(rank, world), bounces=bounces, slabs=args.slabs), host_img.numpy())
+        barrier()
+        if rank == 0:
+            h_gather = hashlib.sha256(host_img.numpy().tobytes()).hexdigest()
+            p1 = r.params(scene, frame=0, flags=base_flags, strip=(0, 1), bounces=bounces, slabs=args.slabs)
+            for _ in range(3):
+                r.render(p1)
+            r.synchronize()
+            h_single = hashlib.sha256(r.read(ug.BUF_RGB).tobytes()).hexdigest()
+            evs = []
+            for i in range(min(args.steps, 20)):
+                if not args.no_flush:
+                    flush.zero_()
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record(); r.render(p1); b_.record()
+                evs.append((a_, b_))
+            torch.cuda.synchronize()
+            ms1 = float(np.mean([a_.elapsed_time(b_) for a_, b_ in evs]))
+            check = {"sha256_gathered": h_gather, "sha256_single_gpu": h_single, "equal": h_gather == h_single}
+            single = {"ms_per_frame": ms1, "value": scene.rays_per_frame() / (ms1 * 1e-3) / 1e6, "unit": "Mrays/s", "steps": len(evs),
+                      "note": "rank 0 renders the same frame alone (strip 0 of 1, no gather) in the same process, same timing rules"}
+        barrier()
+        r.render(r.params(scene, frame=0, flags=base_flags, strip=strip_of(mode), bounces=bounces, slabs=args.slabs))   # back to the run's geometry
+        r.synchronize()
+
+    # ---- N = 1: config D's one-GPU frame time (the workload of the N > 1 series), so the scaling series has its own denominator
+    config_d = None
+    if world == 1 and config == "B" and not args.no_config_d:
+        sd = make_scene("D")
+        rd = ug.Renderer(local)
+        rd.set_scene(sd)
+        rd.set_stream(work_stream.cuda_stream)
+        pd_ = rd.params(sd, frame=0, flags=base_flags)
+        for _ in range(4):
+            rd.render(pd_)
+        torch.cuda.synchronize()
+        evs = []
+        for i in range(20):
+            if not args.no_flush:
+                flush.zero_()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record(); rd.render(pd_); b_.record()
+            evs.append((a_, b_))
+        torch.cuda.synchronize()
+        msd = float(np.mean([a_.elapsed_time(b_) for a_, b_ in evs]))
+        config_d = {"workload": workload_name(sd, 1), "ms_per_frame": msd, "value": sd.rays_per_frame() / (msd * 1e-3) / 1e6, "unit": "Mrays/s", "steps": 20}
+        rd.close()
 
     if rank == 0:
         P, N, Cc = st2.cam_pairs, st2.num_pixels, st2.num_cells
@@ -361,7 +430,7 @@ def run_ours(args):
             name, alg_bytes, tests, note = kern[stage_name]
             t_s = stage[stage_name] * 1e-3
             achieved = alg_bytes / t_s / 1e9
-            traffic, issue = None, None
+            traffic, issue = None, None   # from the committed ncu capture (profiles/traffic.json), not measured in this run
             try:
                 with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                     prof = json.load(f)
@@ -369,7 +438,8 @@ def run_ours(args):
             except Exception:
                 pass
             out = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                   "traffic": traffic, "peak_source": peak_kind, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": stage[stage_name], "note": note}
+                   "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full capture of the same command, committed)" if traffic is not None else None,
+                   "peak_source": peak_kind, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": stage[stage_name], "note": note}
             if issue is not None:   # from the committed ncu capture of the same command (profiles/), not measured live
                 out["sm_issue_active_pct_ncu"] = issue
             if tests:
@@ -400,8 +470,8 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if mode == "strips" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(scene, world, bounces, mode), "rays_per_step": rays_frame, "frames_per_step": frames_per_step,
-                       "parallelism": {"single": "one GPU", "frames": f"{world} GPUs, one frame each per step, frames gathered to rank 0 (NCCL)",
-                                       "strips": f"{world} GPUs, one frame in {world} image strips, gathered to rank 0 (NCCL, inside the frame graph)"}[mode],
+                       "parallelism": {"single": "one GPU", "frames": f"{world} GPUs, one frame each per step, frames stored into rank 0's buffer over NVLink by the shading kernels (P2P, NCCL handshakes, deferred completion)",
+                                       "strips": f"{world} GPUs, one frame in {world} image strips of cell rows, stored into rank 0's frame over NVLink by the shading kernels (P2P, NCCL handshakes, inside the frame graph)"}[mode],
                        "rays": {"primary": scene.num_pixels * frames_per_step, "shadow": scene.num_pixels * len(scene.lights) * frames_per_step,
                                 "reflection": int(refl.item())},
                        "l2": "flushed between timed frames (256 MiB write)" if not args.no_flush else "not flushed",
@@ -419,10 +489,15 @@ def run_ours(args):
             "frame_hbm_frac": frame_bytes / (total_ms / args.steps * 1e-3) / 1e9 / hbm_peak,
             "roofline": roofline, "roofline_kernels": roofline_all, "cpu_baseline": cpu, "clocks": clocks,
         }
-        if strips:
-            strips["value"] = (scene.rays_per_frame() + int(refl.item()) / frames_per_step) / (strips["ms_per_frame"] * 1e-3) / 1e6
-            strips["unit"] = "Mrays/s"
-            line["strips"] = strips
+        if other:
+            other["value"] = (scene.rays_per_frame() * other["frames_per_step"] + int(refl.item()) / frames_per_step * other["frames_per_step"]) / (other["ms_per_step"] * 1e-3) / 1e6
+            other["unit"] = "Mrays/s"
+            line[other["mode"]] = other
+        if check:
+            line["gathered_frame_check"] = check
+            line["single_gpu_same_frame"] = single
+        if config_d:
+            line["config_D_single_gpu"] = config_d
         json_out.write(json.dumps(line) + "\n")
         json_out.flush()
     if world > 1:
@@ -438,9 +513,10 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="B", choices=["A", "B", "C", "D", "E"])
+    ap.add_argument("--config", default=None, choices=["A", "B", "C", "D", "E"], help="default: B on one GPU, D on several")
+    ap.add_argument("--no-config-d", action="store_true", help="N = 1: skip the side measurement of config D")
     ap.add_argument("--bounces", type=int, default=-1, help="reflection bounces (-1: what the config names)")
-    ap.add_argument("--shard", default="auto", choices=["auto", "frames", "strips"], help="N > 1: frames = one frame per GPU (weak, default), strips = one frame in strips (strong)")
+    ap.add_argument("--shard", default="auto", choices=["auto", "frames", "strips"], help="N > 1: strips = one frame in image strips (strong scaling, default), frames = one frame per GPU (weak)")
     ap.add_argument("--light-grid", default="perspective", choices=["perspective", "spherical"],
                     help="perspective: the light path north-star names (default); spherical: the one the committed display() runs")
     ap.add_argument("--shader", default="lambert", choices=["lambert", "spot"], help="spot: Shader::spotlight_shade (display() from its third frame on)")

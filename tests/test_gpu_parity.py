@@ -550,3 +550,36 @@ def test_config_e_subsample(ug, oracle):
         assert np.array_equal(r.read(ug.BUF_RGB), a)
     finally:
         r.close()
+
+
+def _flat_far_scene():
+    """Every vertex on the axis-aligned plane y = 48: the scene's bounding box has no extent along y, and the pad that
+    would give it one is lost to rounding that far from the origin."""
+    s = scenes.scene_random(41, 1200, 128, 96, nlights=1)
+    V = s.verts.copy()
+    V[:, 1] = 48.0
+    V[:, 0] *= 3.0
+    V[:, 2] *= 3.0
+    s.verts = V
+    return reflective(s, (0.5, 0.5), 2)
+
+
+@pytest.mark.parametrize("make", [_flat_far_scene])
+def test_reflection_degenerate_bounding_box(ug, oracle, make):
+    """The uniform grid of row R must stay inside its cell arena when the scene's bounding box is flat:
+    the resolution is clamped, the frame still equals the oracle's brute force, and the context renders an ordinary
+    scene correctly afterwards."""
+    s = make()
+    r = ug.Renderer(0)
+    try:
+        r.set_scene(s)
+        cpu = harness.run_frame(oracle, s, threads=0, reflect=True)
+        gpu = parity.gpu_frame(r, s, flags=0, bounces=2)
+        assert not parity.compare(gpu, cpu, keys=["t", "id", "shadowed"], verbose=False)
+        assert np.array_equal(gpu["rgb"], cpu["rgb_reflect"])
+        s2 = reflective(scenes.scene_random(31, 1500, 160, 96, nlights=1), (0.5, 0.25), 2)
+        r.set_scene(s2)
+        cpu2 = harness.run_frame(oracle, s2, threads=0, reflect=True)
+        assert np.array_equal(parity.gpu_frame(r, s2, flags=0, bounces=2)["rgb"], cpu2["rgb_reflect"])
+    finally:
+        r.close()

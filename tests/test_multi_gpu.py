@@ -94,3 +94,59 @@ def test_strip_gather_over_nccl(oracle, tmp_path, transport):
         for k in range(world):
             want_k = harness.run_frame(oracle, dyn, frame=step * world + k, threads=0)["rgb"]
             assert np.array_equal(frames[k], want_k), f"deferred gather: step {step}, rank {k}"
+
+
+def _overflow_scene():
+    """192 huge triangles below eye level at 1024x1024: the bottom strip's pair count exceeds its initial arena, the top strip's
+    does not - only one rank wants to run the frame again."""
+    T = 192
+    V = np.zeros((T, 3, 3), np.float32)
+    for k in range(T):
+        y = 20.0 + 0.25 * k
+        V[k] = [[-60, y, -60], [60, y, -60], [0, y, 0.5]]
+    s = scenes.scene_random(1, 10, 1024, 1024, nlights=0)     # no light: a light grid is built in full by every rank and would overflow on both
+    s.verts, s.faces, s.face_mat = V.reshape(-1, 3), np.arange(3 * T, dtype=np.int32).reshape(-1, 3), np.zeros(T, np.int32)
+    return s
+
+
+def _worker_overflow(rank, world, port, out_path):
+    import torch
+    import torch.distributed as dist
+    import ugrt  # noqa: F401
+    import uniformgrid_raytracing_b200 as ug
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    scene = _overflow_scene()
+    r = ug.Renderer(rank)
+    r.set_scene(scene)
+    uid = [ug.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    r.comm_init(rank, world, uid[0])
+    host = np.zeros(3 * scene.num_pixels, np.uint8)            # pageable on purpose: rank 0 stages the gathered frame itself
+    r.render_host(r.params(scene, strip=(rank, world)), host)  # one rank overflows: every rank must run the frame again
+    over = [None] * world
+    dist.all_gather_object(over, int(r.stats().overflowed))
+    r.render_host(r.params(scene, strip=(rank, world)), host)  # and the ranks are still in step afterwards
+    if rank == 0:
+        np.save(out_path, host)
+        np.save(out_path + ".over.npy", np.asarray(over))
+    dist.barrier()
+    r.close()
+    dist.destroy_process_group()
+
+
+def test_one_rank_overflow_is_a_collective_decision(oracle, tmp_path):
+    """the pair-arena overflow retry used to be decided per rank, so a frame in which only one strip overflowed
+    left the ranks with different numbers of collectives (hang).  The decision is now a max-allreduce."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    scene = _overflow_scene()
+    want = harness.run_frame(oracle, scene, threads=0)["rgb"]
+    out = str(tmp_path / "full.npy")
+    mp.spawn(_worker_overflow, args=(2, _free_port(), out), nprocs=2, join=True)
+    over = np.load(out + ".over.npy")
+    assert over.tolist().count(1) == 1, f"exactly one strip was meant to overflow, got {over.tolist()}"
+    assert np.array_equal(np.load(out), want)

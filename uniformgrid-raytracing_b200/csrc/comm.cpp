@@ -166,6 +166,11 @@ int ugc_ready(ug_context *ctx, cudaStream_t s)
 	return UG_OK;
 }
 
+u32 *ugc_overflow_word(ug_context *ctx)
+{
+	return (ctx->comm && ctx->use_push && ctx->d_comm_scratch) ? (u32 *)((unsigned char *)ctx->d_comm_scratch + 136) : nullptr;
+}
+
 /* host-side collective decision (e.g. "did any rank overflow its pair arena?"): max over the ranks of *value */
 int ugc_allreduce_max(ug_context *ctx, cudaStream_t s, unsigned *value)
 {
@@ -206,7 +211,7 @@ int ugc_gather_strips(ug_context *ctx, cudaStream_t s, const unsigned char *stri
 		else UG_CUDA(ctx, cudaMemcpyAsync(ctx->peer_full + slot_offset + offs[rank], strip, bytes[rank], cudaMemcpyDefault, s)); /* copy engine, over NVLink */
 		/* done: every copy precedes its rank's contribution.  Deferred: the NEXT frame's "ready" handshake is issued after
 		 * this copy in stream order on every rank, so it doubles as this frame's "done" and nothing waits here */
-		if (!deferred) UG_NCCL(ctx, N.AllReduce(scr + 132, scr + 132, 1, ncclUint32, ncclSum, comm, s));
+		if (!deferred) UG_NCCL(ctx, N.AllReduce(scr + 132, scr + 132, 2, ncclUint32, ncclSum, comm, s)); /* [1] = ranks whose pair arena overflowed */
 		return UG_OK;
 	}
 	if (rank == 0) UG_CUDA(ctx, cudaMemcpyAsync(full + offs[0], strip, bytes[0], cudaMemcpyDeviceToDevice, s));

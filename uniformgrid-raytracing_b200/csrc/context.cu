@@ -112,8 +112,8 @@ extern "C" int ug_create(ug_context **out, int device)
 	for (int i = 0; i < UG_FC_SLOTS; i++) UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ring[i], cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaMalloc((void **)&ctx->d_fc_seq, sizeof(u32)));
 	UG_CUDA(ctx, cudaMemset(ctx->d_fc_seq, 0, sizeof(u32)));
-	UG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_counters, sizeof(u32) * (4 * (2 + UG_MAX_LIGHTS) + UG_MAX_BOUNCES + 1)));
-	memset(ctx->h_counters, 0, sizeof(u32) * (4 * (2 + UG_MAX_LIGHTS) + UG_MAX_BOUNCES + 1));
+	UG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_counters, sizeof(u32) * UG_HC_WORDS));
+	memset(ctx->h_counters, 0, sizeof(u32) * UG_HC_WORDS);
 	UG_CUDA(ctx, cudaMalloc((void **)&ctx->d_fc, sizeof(FrameConst)));
 	*out = ctx;
 	return UG_OK;
@@ -890,22 +890,35 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 		if (parallel) UG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_ready, 0));
 		else { int rc = ugc_ready(ctx, s); if (rc) return rc; }
 	}
+	ctx->overflow_in_frame = false;
 	if (gather_strips || gather_frames) {
 		/* the one exchange step: RGB8 strips (or whole frames) -> rank 0 over NVLink, inside the frame */
+		u32 *ow = ugc_overflow_word(ctx);
+		if (ow && !deferred) { /* the "done" handshake also tells every rank whether any pair arena overflowed */
+			const u32 *src[UG_MAX_LIGHTS + 3];
+			int n = 0;
+			src[n++] = ctx->cam_grid.counters;
+			for (int l = 0; l < nl; l++) src[n++] = ctx->light_grid[l].counters;
+			if (reflect) src[n++] = ctx->refl.grid.counters;
+			ugk_overflow_any(s, src, n, ow);
+			L.n += 1;
+			ctx->overflow_in_frame = true;
+		}
 		int rc = ugc_gather_strips(ctx, s, ctx->d_rgb, slot_off, g_bytes, g_offs, deferred, fused_gather);
 		if (rc) return rc;
 		if (!(fused_gather && deferred)) L.n += 1;
 	}
 	/* pair counts + overflow flags of every grid ride back with the frame (no extra synchronisation later) */
 	{
-		const u32 *src[UG_MAX_LIGHTS + 3];
-		int words[UG_MAX_LIGHTS + 3], off[UG_MAX_LIGHTS + 3], n = 0;
+		const u32 *src[UG_MAX_LIGHTS + 4];
+		int words[UG_MAX_LIGHTS + 4], off[UG_MAX_LIGHTS + 4], n = 0;
 		src[n] = ctx->cam_grid.counters; words[n] = 4; off[n++] = 0;
 		for (int l = 0; l < nl; l++) { src[n] = ctx->light_grid[l].counters; words[n] = 4; off[n++] = 4 * (1 + l); }
 		if (reflect) {
 			src[n] = ctx->refl.grid.counters; words[n] = 4; off[n++] = 4 * (1 + UG_MAX_LIGHTS);
 			src[n] = ctx->refl.ray_counts; words[n] = UG_MAX_BOUNCES + 1; off[n++] = 4 * (2 + UG_MAX_LIGHTS);
 		}
+		if (ctx->overflow_in_frame) { src[n] = ugc_overflow_word(ctx); words[n] = 1; off[n++] = UG_HC_WORDS - 1; }
 		ugk_publish(s, src, words, off, n, ctx->h_counters);
 		L.n += 1;
 	}
@@ -1017,7 +1030,9 @@ static int run_frame_once(ug_context *ctx, const ug_frame_params *p)
 			if (e != cudaSuccess) return ug_fail(ctx, UG_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
 			ctx->graph_key[gs] = key;
 			ctx->graph_launches[gs] = L.n;
+			ctx->graph_overflow[gs] = ctx->overflow_in_frame;
 		}
+		ctx->overflow_in_frame = ctx->graph_overflow[gs]; /* a property of the captured frame, not of the last capture */
 		UG_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
 		UG_CUDA(ctx, cudaGraphLaunch(ctx->graph_exec[gs], ctx->stream));
 		UG_CUDA(ctx, cudaEventRecord(ctx->ev_t1, ctx->stream));
@@ -1105,19 +1120,20 @@ extern "C" int ug_render_frame_host(ug_context *ctx, const ug_frame_params *p, u
 		bool grew = false;
 		rc = check_overflow(ctx, p->num_lights, &grew, p->bounces > 0 && ctx->d_reflect);
 		if (rc) return rc;
+		const bool grew_here = grew;
 		if (collective) {
 			/* every attempt issues the frame's collectives (handshakes, gather): the decision to run it again must be the same
 			 * on every rank, or the ranks fall out of step and hang.  One 4-byte max-allreduce after the frame. */
 			unsigned any = grew ? 1u : 0u;
-			rc = ugc_allreduce_max(ctx, ctx->stream, &any);
-			if (rc) return rc;
+			if (ctx->overflow_in_frame) any = ctx->h_counters[UG_HC_WORDS - 1]; /* summed over the ranks by the frame's own "done" handshake */
+			else if ((rc = ugc_allreduce_max(ctx, ctx->stream, &any)) != UG_OK) return rc;
 			grew = any != 0;
 		}
 		if (!grew) {
 			if (!direct && (!gathered || ctx->comm_rank == 0)) memcpy(host_rgb, dst, out_bytes);
 			return UG_OK;
 		}
-		ctx->stats.overflowed = 1;
+		if (grew_here) ctx->stats.overflowed = 1; /* the other ranks run the frame again too, but their arenas were large enough */
 	}
 	return ug_fail(ctx, UG_ERR_OVERFLOW, "pair arena still too small after growing");
 }

@@ -128,14 +128,29 @@ void ugk_stamp(cudaStream_t s, unsigned long long *slots, int slot) { if (slots)
  * writes them straight into the context's pinned (device-visible) block, instead of one copy-engine node per grid at the
  * tail of the frame graph (~5 us each in series). */
 struct PublishArgs {
-	const u32 *src[UG_MAX_LIGHTS + 3];
-	int words[UG_MAX_LIGHTS + 3], dst_off[UG_MAX_LIGHTS + 3];
+	const u32 *src[UG_MAX_LIGHTS + 4];
+	int words[UG_MAX_LIGHTS + 4], dst_off[UG_MAX_LIGHTS + 4];
 	int n;
 };
 __global__ void k_publish(const PublishArgs a, u32 *__restrict__ host_block)
 {
 	for (int i = 0; i < a.n; i++)
 		for (int w = threadIdx.x; w < a.words[i]; w += blockDim.x) host_block[a.dst_off[i] + w] = a.src[i][w];
+}
+/* word [1] of each listed counter block is that grid's overflow flag: their OR becomes this rank's contribution to the
+ * frame's "done" handshake, so that all ranks learn in the same collective whether anyone has to run the frame again */
+__global__ void k_overflow_any(const PublishArgs a, u32 *__restrict__ out)
+{
+	u32 any = 0;
+	for (int i = 0; i < a.n; i++) any |= a.src[i][1];
+	*out = any ? 1u : 0u;
+}
+void ugk_overflow_any(cudaStream_t s, const u32 *const *src, int n, u32 *out)
+{
+	PublishArgs a;
+	a.n = n;
+	for (int i = 0; i < n; i++) { a.src[i] = src[i]; a.words[i] = 0; a.dst_off[i] = 0; }
+	k_overflow_any<<<1, 1, 0, s>>>(a, out);
 }
 void ugk_publish(cudaStream_t s, const u32 *const *src, const int *words, const int *dst_off, int n, u32 *host_block)
 {

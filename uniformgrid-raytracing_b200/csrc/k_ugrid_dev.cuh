@@ -23,6 +23,17 @@ static __device__ void ugrid_resolution(const u32 *box, int T, int max_cells, fl
 		lo[k] -= pad;
 		ext[k] = (hi + pad) - lo[k];
 	}
+	/* a flat scene far from the origin loses the pad to rounding (extent 0), NaN / inf vertices give a useless box: every axis
+	 * gets a positive, finite extent - the grid only has to be conservative, any resolution gives the same hits */
+	{
+		float m = 0.0f;
+		for (int k = 0; k < 3; k++) if (ext[k] == ext[k] && ext[k] < 3.0e38f && ext[k] > m) m = ext[k];
+		if (!(m > 0.0f)) m = 1.0f;
+		for (int k = 0; k < 3; k++) {
+			if (!(lo[k] == lo[k]) || fabsf(lo[k]) > 3.0e38f) lo[k] = 0.0f;
+			if (!(ext[k] >= 1e-3f * m) || !(ext[k] < 3.0e38f)) ext[k] = fmaxf(1e-3f * m, 1e-30f);
+		}
+	}
 	float target = fminf(cells_per_tri * (float)T, (float)max_cells);
 	target = fmaxf(target, 8.0f);
 	float hcell = cbrtf(ext[0] * ext[1] * ext[2] / target);
@@ -32,6 +43,11 @@ static __device__ void ugrid_resolution(const u32 *box, int T, int max_cells, fl
 		for (int k = 0; k < 3; k++) { n[k] = (int)ceilf(ext[k] / hcell); n[k] = max(1, min(n[k], 1024)); prod *= n[k]; }
 		if (prod <= max_cells) break;
 		hcell *= 1.1f;
+	}
+	while ((long long)n[0] * n[1] * n[2] > (long long)max_cells) { /* whatever the loop left: the cell arena is a hard bound */
+		const int k = (n[0] >= n[1] && n[0] >= n[2]) ? 0 : (n[1] >= n[2] ? 1 : 2);
+		if (n[k] <= 1) break;
+		n[k] = (n[k] + 1) / 2;
 	}
 	for (int k = 0; k < 3; k++) {
 		uc->lo[k] = lo[k];

@@ -130,6 +130,7 @@ struct ug_context {
 	int num_sms = 148;
 	bool use_fused_regroup = true;
 	bool use_fused = true;      /* fused cooperative grid build when the device supports it (UG_NO_FUSED=1 disables) */
+	bool overflow_in_frame = false; /* the last enqueued frame's "done" handshake carried the overflow flags (h_counters[UG_HC_WORDS-1]) */
 	bool use_sweep = true;      /* three-launch one-sweep grid build (k_gridsweep.cu) where eligible (UG_NO_SWEEP=1 disables) */
 
 	/* Model (scene.h:13-57) */
@@ -210,6 +211,7 @@ struct ug_context {
 	cudaGraphExec_t graph_exec[2] = {nullptr, nullptr}; /* [1]: the odd frames of a deferred gather (they write the other slot) */
 	unsigned long long graph_key[2] = {0, 0};
 	int graph_launches[2] = {0, 0};
+	bool graph_overflow[2] = {false, false}; /* that graph's "done" handshake carries the overflow flags */
 	unsigned long long gather_seq = 0; /* frames gathered with UG_FLAG_GATHER_DEFERRED so far: frame k lands in slot k & 1 */
 
 	ug_stats stats = {};
@@ -229,6 +231,8 @@ void ug_drop_graphs(ug_context *ctx);
 /* K1 transform */
 void ugk_fetch_consts(cudaStream_t s, const void *host_ring, void *dev_block, size_t bytes, u32 *seq, int slots);
 void ugk_publish(cudaStream_t s, const u32 *const *src, const int *words, const int *dst_off, int n, u32 *host_block);
+void ugk_overflow_any(cudaStream_t s, const u32 *const *src, int n, u32 *out);
+#define UG_HC_WORDS (4 * (2 + UG_MAX_LIGHTS) + UG_MAX_BOUNCES + 1 + 1) /* h_counters: grids, reflection ray counts, [last] = ranks that overflowed */
 void ugk_stamp(cudaStream_t s, unsigned long long *slots, int slot);
 void ugk_transform(cudaStream_t s, float *vertexlist, const float *orig, int size, int offset, const FrameConst *fc, int sms);
 /* K2 setup+bin, scan, emit */
@@ -293,6 +297,7 @@ int ugc_gather_strips(ug_context *ctx, cudaStream_t s, const unsigned char *stri
                       bool already_stored);
 int ugc_flush(ug_context *ctx, cudaStream_t s);
 int ugc_allreduce_max(ug_context *ctx, cudaStream_t s, unsigned *value); /* host value in/out; synchronises s */
+u32 *ugc_overflow_word(ug_context *ctx);   /* device word the "done" handshake sums over the ranks (push transport), or null */
 
 /* host helpers (camera_host.cpp, obj_loader.cpp) */
 void ugh_view_const(ViewConst *vc, const ug_camera *cam, int W, int H, int nbx, int nby, int gy_lo, int gy_cnt, int grid_mode = UG_LIGHT_GRID_PERSPECTIVE,
