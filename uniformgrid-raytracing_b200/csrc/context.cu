@@ -67,6 +67,7 @@ extern "C" int ug_create(ug_context **out, int device)
 	/* the default build of every perspective / spherical grid: three one-sweep launches (k_gridsweep.cu).  UG_NO_SWEEP, or any
 	 * switch that forces one of the other two variants, turns it off. */
 	ctx->use_sweep = !getenv("UG_NO_SWEEP") && !getenv("UG_NO_FUSED") && !getenv("UG_FUSED_GRID");
+	ctx->direct_shadow = getenv("UG_SHADOW_DIRECT") != nullptr; /* measured slower than the regrouped path on every config: opt-in */
 	ctx->fused_gather = !getenv("UG_NO_FUSED_GATHER");
 	ctx->use_fused_regroup = ugk_regroup_fused_supported(device) && !getenv("UG_NO_FUSED") && getenv("UG_FUSED_REGROUP");
 	ctx->use_fused_ugrid = ugk_ugrid_fused_supported(device) && !getenv("UG_NO_FUSED") && getenv("UG_FUSED_UGRID");
@@ -133,7 +134,7 @@ static void free_grid(GridBuffers &g)
 static void free_rays(LightRays &r)
 {
 	dfree(r.cell); dfree(r.pix); dfree(r.span); dfree(r.offset); dfree(r.cursor);
-	dfree(r.item_off); dfree(r.items); dfree(r.counters); dfree(r.state_a); dfree(r.state_b);
+	dfree(r.item_off); dfree(r.items); dfree(r.counters); dfree(r.state_a); dfree(r.state_b); dfree(r.heavy);
 	r = LightRays();
 }
 
@@ -285,6 +286,13 @@ static int alloc_rays(ug_context *ctx, LightRays &r, int N, int C)
 {
 	free_rays(r);
 	UG_CUDA(ctx, dmalloc(&r.cell, (size_t)N));
+	UG_CUDA(ctx, dmalloc(&r.counters, 4));
+	UG_CUDA(ctx, cudaMemset(r.counters, 0, 4 * sizeof(u32)));
+	if (ctx->direct_shadow) { /* rays stay in screen order: only the queue of long (ray group, list segment) products */
+		r.heavy_cap = ugk_shadow_heavy_cap(N);
+		UG_CUDA(ctx, dmalloc(&r.heavy, r.heavy_cap));
+		return UG_OK;
+	}
 	UG_CUDA(ctx, dmalloc(&r.pix, (size_t)N));
 	UG_CUDA(ctx, dmalloc(&r.span, (size_t)C + 1));
 	UG_CUDA(ctx, dmalloc(&r.offset, (size_t)C + 2));
@@ -292,8 +300,6 @@ static int alloc_rays(ug_context *ctx, LightRays &r, int N, int C)
 	UG_CUDA(ctx, dmalloc(&r.item_off, (size_t)C + 2));
 	r.item_cap = ugk_shadow_item_cap(N, C); /* worst case: one item per ray (every list longer than 1024) + the segment budget of every cell */
 	UG_CUDA(ctx, dmalloc(&r.items, r.item_cap));
-	UG_CUDA(ctx, dmalloc(&r.counters, 4));
-	UG_CUDA(ctx, cudaMemset(r.counters, 0, 4 * sizeof(u32)));
 	const size_t ns = ugk_regroup_state_entries(C);
 	UG_CUDA(ctx, dmalloc(&r.state_a, ns));
 	UG_CUDA(ctx, dmalloc(&r.state_b, ns));
@@ -711,12 +717,14 @@ static void enqueue_light_grid(ug_context *ctx, cudaStream_t s, int l, Launches 
 }
 static void enqueue_light_zero(ug_context *ctx, cudaStream_t s, int l)
 { /* independent of the primary rays: issued early on the light's branch */
+	if (ctx->direct_shadow) return;
 	LightRays &r = ctx->rays[l];
 	cudaMemsetAsync(r.span, 0, sizeof(u32) * ((size_t)ctx->C_light + 1), s);
 	cudaMemsetAsync(r.cursor, 0, sizeof(u32) * ((size_t)ctx->C_light + 1), s);
 }
 static void enqueue_light_regroup(ug_context *ctx, cudaStream_t s, int l, Launches &L)
 {
+	if (ctx->direct_shadow) return; /* the rays are not regrouped: ray -> light cell is part of the shadow pass */
 	LightRays &r = ctx->rays[l];
 	if (!ugk_regroup(s, ctx->d_fc, l, ctx->light_grid[l], r, ctx->d_t, ctx->d_dir, ctx->N, ctx->C_light, ctx->num_sms, ctx->use_fused_regroup, &L.n)) {
 		ctx->use_fused_regroup = false; /* cooperative launch refused: phase-by-phase launches from now on */
@@ -725,6 +733,10 @@ static void enqueue_light_regroup(ug_context *ctx, cudaStream_t s, int l, Launch
 }
 static void enqueue_light_shadow(ug_context *ctx, cudaStream_t s, int l, Launches &L)
 {
+	if (ctx->direct_shadow) {
+		ugk_shadow_direct(s, ctx->d_fc, l, ctx->light_grid[l], ctx->rays[l], ctx->d_t, ctx->d_dir, ctx->d_shadowed, ctx->N, ctx->C_light, ctx->num_sms, &L.n);
+		return;
+	}
 	ugk_shadow(s, ctx->d_fc, l, ctx->light_grid[l], ctx->rays[l], ctx->d_t, ctx->d_dir, ctx->d_shadowed, ctx->N, ctx->C_light, ctx->num_sms); L.n += 1;
 }
 static void enqueue_light_rays(ug_context *ctx, cudaStream_t s, int l, Launches &L)

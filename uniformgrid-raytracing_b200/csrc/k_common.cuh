@@ -181,6 +181,29 @@ __device__ __forceinline__ bool ug_intersect_lds(u32 addr, float dx, float dy, f
 	return true;
 }
 
+/* The same test cut in two, so that a caller can keep TWO triangles in flight per ray: the first half (pvec, det, 1/det, u)
+ * is evaluated for both without a branch in between - two independent dependency chains instead of one, which is what the
+ * issue slots of a warp were waiting for - and only a ray that passes a u test goes on to v and t.  Operations and their
+ * order are those of ug_intersect, so the results are bit-identical; a |det| <= EPSILON triangle gets inf/NaN here and is
+ * masked by the returned flag instead of leaving early. */
+struct TriU { float inv, u; };
+__device__ __forceinline__ bool ug_isect_u(const float4 &r0, const float4 &r1, const float4 &r2, float dx, float dy, float dz, TriU &o)
+{
+	float px, py, pz;
+	ug_cross(px, py, pz, dx, dy, dz, r2.x, r2.y, r2.z);
+	const float det = ug_dot(r1.x, r1.y, r1.z, px, py, pz);
+	o.inv = 1.0f / det;
+	o.u = ug_dot(r0.x, r0.y, r0.z, px, py, pz) * o.inv;
+	return !(fabsf(det) <= 1e-21f) && !(o.u < 0.0f || o.u > 1.0f);
+}
+__device__ __forceinline__ bool ug_isect_vt(const float4 &r0, const float4 &r3, float dx, float dy, float dz, const TriU &o, float &t)
+{
+	const float v = ug_dot(dx, dy, dz, r3.x, r3.y, r3.z) * o.inv;
+	if (v < 0.0f || o.u + v > 1.0f) return false;
+	t = r0.w * o.inv;
+	return true;
+}
+
 __device__ __forceinline__ u32 ug_lane() { return threadIdx.x & 31u; }
 
 #endif

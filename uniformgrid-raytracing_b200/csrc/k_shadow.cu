@@ -20,7 +20,7 @@
  * ray and the hits are OR-ed with a ballot.  No lane ever owns more than ~64 sequential tests, short
  * cells with few rays still fill the warp, and a ray still stops at its first occluder.
  */
-#include "k_grid_dev.cuh"
+#include "k_shadow_dev.cuh"
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -95,61 +95,6 @@ struct RegroupArgs {
 	u64 *state_a, *state_b;     /* look-back descriptors of the two scans; self-resetting */
 	u32 item_cap;
 };
-
-/* phase A body: misc_kernel.cu:63-129 for one pixel */
-struct LightMap {
-	float lx, ly, lz, p0, p1, p2, num, half, r0, r1, r2, u0, u1, u2;
-	double den;
-	int nbx, nby;
-};
-static __device__ __forceinline__ LightMap make_light_map(const ViewConst &lv)
-{
-	LightMap m;
-	const float *cc = lv.cc;
-	m.lx = cc[0]; m.ly = cc[1]; m.lz = cc[2];
-	/* misc_kernel.cu:97-101: un-normalised near plane = MVP row 3 + row 2 */
-	m.p0 = cc[48 + 3] + cc[48 + 2]; m.p1 = cc[48 + 7] + cc[48 + 6]; m.p2 = cc[48 + 11] + cc[48 + 10];
-	const float p3 = cc[48 + 15] + cc[48 + 14];
-	m.num = ug_dot(m.p0, m.p1, m.p2, m.lx, m.ly, m.lz) + p3;
-	m.half = lv.near_plane * lv.tan_half;                                                   /* float */
-	m.den = __dmul_rn(__dmul_rn(2.0, (double)lv.near_plane), (double)lv.tan_half);          /* 2.0 * near * tan: double */
-	m.r0 = cc[16 + 0]; m.r1 = cc[16 + 4]; m.r2 = cc[16 + 8];
-	m.u0 = cc[16 + 1]; m.u1 = cc[16 + 5]; m.u2 = cc[16 + 9];
-	m.nbx = lv.nbx; m.nby = lv.nby;
-	return m;
-}
-static __device__ __forceinline__ u32 light_cell_of(const LightMap &m, float ex, float ey, float ez, float tv, float dx, float dy, float dz)
-{
-	/* misc_kernel.cu:74-88: P = eye + t*dir (misses have t = -1 and still shoot), L = normalize(P - light) */
-	const float Px = ex + tv * dx, Py = ey + tv * dy, Pz = ez + tv * dz;
-	float Lx = Px - m.lx, Ly = Py - m.ly, Lz = Pz - m.lz;
-	ug_normalize(Lx, Ly, Lz);
-	const float s = -1.0f * m.num / ug_dot(m.p0, m.p1, m.p2, Lx, Ly, Lz);
-	const float X = s * Lx, Y = s * Ly, Z = s * Lz;
-	const float right = X * m.r0 + Y * m.r1 + Z * m.r2;
-	const float up = X * m.u0 + Y * m.u1 + Z * m.u2;
-	/* misc_kernel.cu:115-116: (float)/(double) -> double, * int, floor, -> int */
-	const int blx = ug_d2i(floor(__dmul_rn(__ddiv_rn((double)(right + m.half), m.den), (double)m.nbx)));
-	const int bly = ug_d2i(floor(__dmul_rn(__ddiv_rn((double)(up + m.half), m.den), (double)m.nby)));
-	u32 cell = (u32)(m.nbx * m.nby);
-	if (blx >= 0 && blx <= m.nbx - 1 && bly >= 0 && bly <= m.nby - 1) cell = (u32)(blx * m.nby + bly);
-	return cell;
-}
-
-/* a14: misc_kernel.cu:255-296 mapSort_Effective_kernel - the spherical variant of the same map (the one display()
- * actually calls, main.cu:189): angular bins of the normalised light->point direction */
-static __device__ __noinline__ u32 light_cell_sph(const ViewConst &lv, float ex, float ey, float ez, float tv, float dx, float dy, float dz)
-{
-	const float *cc = lv.cc;
-	const float Px = ex + tv * dx, Py = ey + tv * dy, Pz = ez + tv * dz;
-	float Lx = Px - cc[0], Ly = Py - cc[1], Lz = Pz - cc[2];
-	ug_normalize(Lx, Ly, Lz);
-	const int blx = ug_effective_x(cc, Lx, Ly, Lz, lv.xM, lv.nbx);
-	const int bly = ug_effective_y(cc, Lx, Ly, Lz, lv.yM, lv.nby);
-	u32 cell = (u32)(lv.nbx * lv.nby);
-	if (blx >= 0 && blx < lv.nbx && bly >= 0 && bly < lv.nby) cell = (u32)(blx * lv.nby + bly);
-	return cell;
-}
 
 /* phase < 0: all phases with grid barriers (cooperative launch); otherwise just that phase */
 __global__ void __launch_bounds__(RG_THREADS, 2) k_regroup(const RegroupArgs a, int phase)
@@ -267,23 +212,6 @@ __global__ void __launch_bounds__(RG_THREADS, 2) k_regroup(const RegroupArgs a, 
 	}
 }
 
-struct ShadowRay { float Lx, Ly, Lz, dist_b; int pix; };
-
-/* light_kernel.cu:164-184: rebuild the shadow ray of one pixel from (t, dir) */
-static __device__ __forceinline__ ShadowRay make_shadow_ray(const float *__restrict__ dir, const float *__restrict__ t, int pix, float ex, float ey, float ez,
-                                                            float lx, float ly, float lz)
-{
-	ShadowRay r;
-	const float tv = t[pix], dx = dir[3 * (size_t)pix], dy = dir[3 * (size_t)pix + 1], dz = dir[3 * (size_t)pix + 2];
-	const float Px = ex + tv * dx, Py = ey + tv * dy, Pz = ez + tv * dz;
-	r.Lx = Px - lx; r.Ly = Py - ly; r.Lz = Pz - lz;
-	const float bx = r.Lx, by = r.Ly, bz = r.Lz;
-	ug_normalize(r.Lx, r.Ly, r.Lz);
-	r.dist_b = sqrtf(bx * bx + by * by + bz * bz); /* isSmaller's distance_b, light_kernel.cu:5 */
-	r.pix = pix;
-	return r;
-}
-
 __global__ void __launch_bounds__(32 * SH_WARPS) k_shadow(const FrameConst *__restrict__ fc, int light, const u32 *__restrict__ span,
                                                         const u32 *__restrict__ offset, const u32 *__restrict__ value_list, const float4 *__restrict__ rec,
                                                         const u32 *__restrict__ ray_pix, const u32 *__restrict__ ray_span, const u32 *__restrict__ ray_offset,
@@ -331,7 +259,7 @@ __global__ void __launch_bounds__(32 * SH_WARPS) k_shadow(const FrameConst *__re
 				p0 = src4[0]; p1 = src4[1]; p2 = src4[2]; p3 = src4[3];
 			}
 			if (usable && !done) {
-				for (u32 k = grp; k < cnt; k += g) {
+				for (u32 k = grp; k < cnt; k += g) { /* (two tests in flight per ray, as in k_trace, was measured here: 0-9 % slower - an any-hit walk ends early) */
 					float tt;
 					if (!ug_intersect(w_rec[4 * k], w_rec[4 * k + 1], w_rec[4 * k + 2], w_rec[4 * k + 3], ray.Lx, ray.Ly, ray.Lz, tt)) continue;
 					if (!(tt < 999999.9f) || tt == 0.0f) continue; /* intersectTri returns t only if t < oldt; `if (value)` */

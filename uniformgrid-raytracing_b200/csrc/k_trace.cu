@@ -24,6 +24,29 @@
  */
 #include "k_common.cuh"
 
+/* ---- TMA bulk copy + mbarrier (cp.async.bulk / mbarrier PTX; SASS: UBLKCP, SYNCS) */
+static __device__ __forceinline__ void tr_mbar_init(u32 bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+static __device__ __forceinline__ void tr_mbar_expect(u32 bar, u32 bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+static __device__ __forceinline__ void tr_mbar_wait(u32 bar, u32 parity)
+{
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "TR_WAIT:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	    "@p bra TR_DONE;\n"
+	    "bra TR_WAIT;\n"
+	    "TR_DONE:\n"
+	    "}\n" ::"r"(bar),
+	    "r"(parity)
+	    : "memory");
+}
+static __device__ __forceinline__ void tr_bulk_g2s(u32 dst_smem, const void *src, u32 bytes, u32 bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar)
+	             : "memory");
+}
+
 #define TR_ITEM 128   /* pairs per work item */
 #define TR_BATCH 64   /* triangles staged per round = threads per packet */
 
@@ -100,7 +123,12 @@ __global__ void __launch_bounds__(64, TR_MINB) k_trace(const FrameConst *__restr
                                               const float *__restrict__ dir, float *__restrict__ out_t, int *__restrict__ out_id,
                                               float *__restrict__ out_normal)
 {
+#ifndef TR_NO_TMA
+	__shared__ __align__(128) float4 s_rec[2 * TR_BATCH * 4]; /* two staging windows, filled by TMA */
+	__shared__ __align__(8) unsigned long long s_bar[2];     /* one mbarrier per window: completes when its records have landed */
+#else
 	__shared__ float4 s_rec[TR_BATCH * 4];
+#endif
 	__shared__ u32 s_key[TR_ITEM + 2]; /* keys[lo-1 .. hi], so both ends can tell whole cells from partial ones */
 	__shared__ u32 s_val[TR_ITEM];
 	__shared__ u32 s_head[TR_ITEM / 32]; /* bit p = pair lo+p starts a run (its key differs from the previous pair's) */
@@ -110,9 +138,15 @@ __global__ void __launch_bounds__(64, TR_MINB) k_trace(const FrameConst *__restr
 	const int tid = threadIdx.x;
 	s_cc[tid] = vc.cc[tid];
 	const int gy_cnt = vc.gy_cnt, W = vc.W;
-	const u32 rec_base = (u32)__cvta_generic_to_shared(s_rec);
+	const u32 rec_base0 = (u32)__cvta_generic_to_shared(s_rec);
 	const u32 P = counters[0];
 	const u32 nitems = (P + TR_ITEM - 1) / TR_ITEM;
+#ifndef TR_NO_TMA
+	const u32 bar0 = (u32)__cvta_generic_to_shared(&s_bar[0]);
+	if (tid == 0) { tr_mbar_init(bar0, 1); tr_mbar_init(bar0 + 8u, 1); }
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	u32 wc = 0, phase0 = 0, phase1 = 0; /* windows staged so far (window w uses buffer w & 1), parity of each barrier's next completion */
+#endif
 	__syncthreads();
 	for (u32 item = blockIdx.x; item < nitems; item += gridDim.x) {
 		const u32 lo = item * TR_ITEM, hi = min(lo + TR_ITEM, P);
@@ -130,13 +164,22 @@ __global__ void __launch_bounds__(64, TR_MINB) k_trace(const FrameConst *__restr
 			const u32 bits = __ballot_sync(UG_FULL_MASK, head);
 			if ((tid & 31) == 0) s_head[p >> 5] = bits;
 		}
-		/* Staging is decoupled from the runs: windows of 64 consecutive pairs, the next window's records in
-		 * flight in registers while the current one is tested. */
+		/* Staging is decoupled from the runs: windows of 64 consecutive pairs.  Every thread issues ONE 64-byte TMA bulk copy
+		 * (cp.async.bulk global -> shared) for the record its pair names; an mbarrier counts the bytes.  The next window is
+		 * issued into the other buffer before the current one is tested, so its latency hides behind 64 x 64 tests. */
+#ifndef TR_NO_TMA
+		{
+			const u32 cnt = min((u32)TR_BATCH, hi - lo), b = wc & 1u;
+			if (tid == 0) tr_mbar_expect(bar0 + 8u * b, cnt * 64u);
+			if ((u32)tid < cnt) tr_bulk_g2s(rec_base0 + b * (TR_BATCH * 64u) + tid * 64u, rec + 4 * (size_t)s_val[tid], 64u, bar0 + 8u * b);
+		}
+#else
 		float4 p0 = make_float4(0, 0, 0, 0), p1 = p0, p2 = p0, p3 = p0;
 		if (lo + tid < hi) {
 			const float4 *src = rec + 4 * (size_t)s_val[tid];
 			p0 = src[0]; p1 = src[1]; p2 = src[2]; p3 = src[3];
 		}
+#endif
 
 		/* state of the run being walked (a run = the part of one cell's list inside this item) */
 		bool have = false;
@@ -146,6 +189,20 @@ __global__ void __launch_bounds__(64, TR_MINB) k_trace(const FrameConst *__restr
 
 		for (u32 wlo = lo; wlo < hi; wlo += TR_BATCH) { /* the last window (whi == hi) also closes the last run */
 			const u32 whi = min(wlo + TR_BATCH, hi);
+#ifndef TR_NO_TMA
+			const u32 b = wc & 1u;
+			const u32 rec_base = rec_base0 + b * (TR_BATCH * 64u);
+			__syncthreads(); /* everybody is done with the other buffer (the window before this one) */
+			if (whi < hi) {
+				const u32 cnt2 = min((u32)TR_BATCH, hi - whi), bar2 = bar0 + 8u * (b ^ 1u);
+				if (tid == 0) tr_mbar_expect(bar2, cnt2 * 64u);
+				if ((u32)tid < cnt2) tr_bulk_g2s(rec_base0 + (b ^ 1u) * (TR_BATCH * 64u) + tid * 64u, rec + 4 * (size_t)s_val[whi - lo + tid], 64u, bar2);
+			}
+			tr_mbar_wait(bar0 + 8u * b, b ? phase1 : phase0);
+			if (b) phase1 ^= 1u; else phase0 ^= 1u;
+			wc++;
+#else
+			const u32 rec_base = rec_base0;
 			__syncthreads();
 			if (wlo + tid < whi) { s_rec[4 * tid + 0] = p0; s_rec[4 * tid + 1] = p1; s_rec[4 * tid + 2] = p2; s_rec[4 * tid + 3] = p3; }
 			__syncthreads();
@@ -153,6 +210,7 @@ __global__ void __launch_bounds__(64, TR_MINB) k_trace(const FrameConst *__restr
 				const float4 *src = rec + 4 * (size_t)s_val[whi - lo + tid];
 				p0 = src[0]; p1 = src[1]; p2 = src[2]; p3 = src[3];
 			}
+#endif
 			u32 p = wlo;
 			while (true) {
 				const bool at_end = p >= hi;
@@ -204,7 +262,26 @@ __global__ void __launch_bounds__(64, TR_MINB) k_trace(const FrameConst *__restr
 						}
 					}
 				}
-				for (u32 k = p; k < e; k++) {
+				u32 k = p;
+#ifndef TR_NO_ILP2
+				for (; k + 1 < e; k += 2) { /* two triangles in flight per ray (ug_isect_u); hits are taken in list order */
+					const u32 ad = rec_base + (k - wlo) * 64u;
+					const float4 a2 = ug_lds128(ad + 32), a1 = ug_lds128(ad + 16), b2 = ug_lds128(ad + 96), b1 = ug_lds128(ad + 80);
+					const float4 a0 = ug_lds128(ad), b0 = ug_lds128(ad + 64);
+					TriU A, B;
+					const bool ha = ug_isect_u(a0, a1, a2, dx, dy, dz, A), hb = ug_isect_u(b0, b1, b2, dx, dy, dz, B);
+					float t;
+					if (ha && ug_isect_vt(a0, ug_lds128(ad + 48), dx, dy, dz, A, t)) {
+						t = fabsf(t);                    /* trace_kernel.cu:35 */
+						if (t < best && t > 0.0f) { best = t; hit = k; } /* :38 */
+					}
+					if (hb && ug_isect_vt(b0, ug_lds128(ad + 112), dx, dy, dz, B, t)) {
+						t = fabsf(t);
+						if (t < best && t > 0.0f) { best = t; hit = k + 1; }
+					}
+				}
+#endif
+				for (; k < e; k++) {
 					float t;
 					if (ug_intersect_lds(rec_base + (k - wlo) * 64u, dx, dy, dz, t)) {
 						t = fabsf(t);                    /* trace_kernel.cu:35 */

@@ -88,6 +88,8 @@ struct LightRays {         /* DecisionData's regroup state (decision_data.h:72-8
 	u32 *counters = nullptr; /* [0] number of items, [1] ticket */
 	u64 *state_a = nullptr, *state_b = nullptr; /* look-back descriptors (self-resetting) */
 	size_t item_cap = 0;
+	uint4 *heavy = nullptr;  /* k_shadowdirect.cu: queue of (cell, pixel block, lane mask, list segment) */
+	size_t heavy_cap = 0;
 };
 
 struct UGridConst;
@@ -131,6 +133,7 @@ struct ug_context {
 	bool use_fused_regroup = true;
 	bool use_fused = true;      /* fused cooperative grid build when the device supports it (UG_NO_FUSED=1 disables) */
 	bool overflow_in_frame = false; /* the last enqueued frame's "done" handshake carried the overflow flags (h_counters[UG_HC_WORDS-1]) */
+	bool direct_shadow = false; /* UG_SHADOW_DIRECT=1: shadow rays in screen order, no regroup (k_shadowdirect.cu); default is the regrouped path (k_shadow.cu) */
 	bool use_sweep = true;      /* three-launch one-sweep grid build (k_gridsweep.cu) where eligible (UG_NO_SWEEP=1 disables) */
 
 	/* Model (scene.h:13-57) */
@@ -273,6 +276,9 @@ size_t ugk_regroup_state_entries(int C);
 size_t ugk_shadow_item_cap(int N, int C);
 bool ugk_regroup(cudaStream_t s, const FrameConst *fc, int light, const GridBuffers &g, const LightRays &r, const float *t, const float *dir, int N, int C,
                  int sms, bool fused, int *launches);
+size_t ugk_shadow_heavy_cap(int N);
+void ugk_shadow_direct(cudaStream_t s, const FrameConst *fc, int light, const GridBuffers &g, const LightRays &r, const float *t, const float *dir, int *shadowed,
+                       int N, int C, int sms, int *launches);
 void ugk_shadow(cudaStream_t s, const FrameConst *fc, int light, const GridBuffers &g, const LightRays &r, const float *t, const float *dir, int *shadowed,
                 int N, int C, int sms);
 /* K10 shade */
