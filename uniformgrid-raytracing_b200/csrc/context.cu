@@ -133,7 +133,7 @@ static void free_grid(GridBuffers &g)
 }
 static void free_rays(LightRays &r)
 {
-	dfree(r.cell); dfree(r.pix); dfree(r.span); dfree(r.offset); dfree(r.cursor);
+	dfree(r.cell); dfree(r.pix); dfree(r.span); dfree(r.offset); dfree(r.rank);
 	dfree(r.item_off); dfree(r.items); dfree(r.counters); dfree(r.state_a); dfree(r.state_b); dfree(r.heavy);
 	r = LightRays();
 }
@@ -296,7 +296,7 @@ static int alloc_rays(ug_context *ctx, LightRays &r, int N, int C)
 	UG_CUDA(ctx, dmalloc(&r.pix, (size_t)N));
 	UG_CUDA(ctx, dmalloc(&r.span, (size_t)C + 1));
 	UG_CUDA(ctx, dmalloc(&r.offset, (size_t)C + 2));
-	UG_CUDA(ctx, dmalloc(&r.cursor, (size_t)C + 1));
+	UG_CUDA(ctx, dmalloc(&r.rank, (size_t)N));
 	UG_CUDA(ctx, dmalloc(&r.item_off, (size_t)C + 2));
 	r.item_cap = ugk_shadow_item_cap(N, C); /* worst case: one item per ray (every list longer than 1024) + the segment budget of every cell */
 	UG_CUDA(ctx, dmalloc(&r.items, r.item_cap));
@@ -720,7 +720,6 @@ static void enqueue_light_zero(ug_context *ctx, cudaStream_t s, int l)
 	if (ctx->direct_shadow) return;
 	LightRays &r = ctx->rays[l];
 	cudaMemsetAsync(r.span, 0, sizeof(u32) * ((size_t)ctx->C_light + 1), s);
-	cudaMemsetAsync(r.cursor, 0, sizeof(u32) * ((size_t)ctx->C_light + 1), s);
 }
 static void enqueue_light_regroup(ug_context *ctx, cudaStream_t s, int l, Launches &L)
 {

@@ -7,8 +7,8 @@
  *     phase B  ray ranges per light cell (exclusive scan) and the WORK-ITEM table sizes (second scan)
  *     phase C  DecisionData::sort_by_block_indices ... stream_compact (decision_data.h:171-271): regroup
  *              the rays by light cell.  The shadow bit is an OR over the cell's triangles, so the order
- *              of rays inside a cell cannot change any output and a counting sort with warp-aggregated
- *              cursors replaces the reference's 15-bit radix sort + segmented scan + compaction.
+ *              of rays inside a cell cannot change any output and a counting sort (the histogram's own atomics
+ *              hand out the ranks) replaces the reference's 15-bit radix sort + segmented scan + compaction.
  *              Also writes the item table.
  *   k_shadow   light_kernel.cu:52-270 mod_light_rckernel: any-hit traversal, one warp per work item.
  *
@@ -25,6 +25,12 @@
 namespace cg = cooperative_groups;
 
 #define RG_THREADS 512
+#ifndef RG_KA
+#define RG_KA 2 /* pixels per thread and trip, ray -> cell map */
+#endif
+#ifndef RG_KC
+#define RG_KC 4 /* pixels per thread and trip, scatter */
+#endif
 #define SH_WARPS 4
 #define SH_SEGMAX 2048 /* lists longer than this are also cut along the triangle axis ... */
 #define SH_SEGBUDGET 16 /* ... but only while the cell has few rays: at most 1 + SH_SEGBUDGET/rays segments, so a cell never needs more than
@@ -87,7 +93,7 @@ struct RegroupArgs {
 	u32 *light_cell;            /* [N]   d_map[N..2N) */
 	u32 *ray_span;              /* [C+1] rays per cell, zeroed before the launch */
 	u32 *ray_offset;            /* [C+2] */
-	u32 *cursor;                /* [C+1] zeroed before the launch */
+	u32 *ray_rank;              /* [N]   position of every ray among the rays of its cell */
 	u32 *ray_pix;               /* [N]   d_map[0..N) after the regroup */
 	u32 *item_off;              /* [C+1] */
 	uint2 *items;               /* (cell, local item index) */
@@ -112,32 +118,43 @@ __global__ void __launch_bounds__(RG_THREADS, 2) k_regroup(const RegroupArgs a, 
 		const bool spherical = lv.grid_mode == UG_LIGHT_GRID_SPHERICAL;
 		const float ex = cam.cc[0], ey = cam.cc[1], ez = cam.cc[2];
 		if (b == 0 && tid == 0) a.counters[1] = 0;
-		/* two pixels per thread and trip: both pixels' loads are in flight before either one's arithmetic starts (the loop is a
-		 * dependent chain load -> divide -> match -> atomic, and only 32 warps per SM are resident) */
+		/* RG_KA pixels per thread and trip: all their loads are in flight before any arithmetic starts (the loop is a dependent
+		 * chain load -> divide -> match -> atomic, and only 32 warps per SM are resident) */
 		const int stride = (int)(G * RG_THREADS);
-		for (int base = b * RG_THREADS; base < N; base += 2 * stride) {
-			const int pix[2] = {base + (int)tid, base + stride + (int)tid};
-			float tv[2], dx[2], dy[2], dz[2];
+		for (int base = b * RG_THREADS; base < N; base += RG_KA * stride) {
+			int pix[RG_KA];
+			float tv[RG_KA], dx[RG_KA], dy[RG_KA], dz[RG_KA];
 #pragma unroll
-			for (int k = 0; k < 2; k++) {
+			for (int k = 0; k < RG_KA; k++) {
+				pix[k] = base + k * stride + (int)tid;
 				const bool valid = pix[k] < N;
 				tv[k] = valid ? a.t[pix[k]] : 0.0f;
 				dx[k] = valid ? a.dir[3 * (size_t)pix[k]] : 0.0f;
 				dy[k] = valid ? a.dir[3 * (size_t)pix[k] + 1] : 0.0f;
 				dz[k] = valid ? a.dir[3 * (size_t)pix[k] + 2] : 1.0f;
 			}
+			u32 cell[RG_KA], old[RG_KA], lower[RG_KA];
 #pragma unroll
-			for (int k = 0; k < 2; k++) {
-				if (base + k * stride >= N) break; /* warp-uniform: the second half-trip lies past the end */
+			for (int k = 0; k < RG_KA; k++) {
+				cell[k] = 0xffffffffu; old[k] = 0; lower[k] = 0;
+				if (base + k * stride >= N) continue; /* warp-uniform: the rest of the trip lies past the end */
 				const bool valid = pix[k] < N;
-				u32 cell = 0xffffffffu;
 				if (valid) {
-					cell = spherical ? light_cell_sph(lv, ex, ey, ez, tv[k], dx[k], dy[k], dz[k]) : light_cell_of(m, ex, ey, ez, tv[k], dx[k], dy[k], dz[k]);
-					a.light_cell[pix[k]] = cell;
+					cell[k] = spherical ? light_cell_sph(lv, ex, ey, ez, tv[k], dx[k], dy[k], dz[k]) : light_cell_of(m, ex, ey, ez, tv[k], dx[k], dy[k], dz[k]);
+					a.light_cell[pix[k]] = cell[k];
 				}
-				/* rays of one warp mostly share a light cell: one atomic per distinct cell */
-				const u32 peers = __match_any_sync(UG_FULL_MASK, cell);
-				if (valid && (peers & ((1u << ug_lane()) - 1u)) == 0) atomicAdd(&a.ray_span[cell], (u32)__popc(peers));
+				/* rays of one warp mostly share a light cell: one atomic per distinct cell.  What it returns is where the group
+				 * starts among the cell's rays, so the scatter phase needs no cursors of its own (any order inside a cell will do) */
+				const u32 peers = __match_any_sync(UG_FULL_MASK, cell[k]);
+				lower[k] = __popc(peers & ((1u << ug_lane()) - 1u));
+				if (valid && lower[k] == 0) old[k] = atomicAdd(&a.ray_span[cell[k]], (u32)__popc(peers));
+				old[k] |= (u32)(__ffs(peers) - 1) << 27; /* the leader's lane rides in the top bits until the atomics have returned */
+			}
+#pragma unroll
+			for (int k = 0; k < RG_KA; k++) {
+				if (base + k * stride >= N) continue;
+				const u32 st = __shfl_sync(UG_FULL_MASK, old[k] & 0x7ffffffu, (int)(old[k] >> 27));
+				if (pix[k] < N) a.ray_rank[pix[k]] = st + lower[k];
 			}
 		}
 	}
@@ -181,25 +198,20 @@ __global__ void __launch_bounds__(RG_THREADS, 2) k_regroup(const RegroupArgs a, 
 		const u32 per = RG_THREADS * 4, tiles = ((u32)C + 2 + per - 1) / per;
 		for (u32 i = b * RG_THREADS + tid; i < tiles + 1; i += G * RG_THREADS) { a.state_a[i] = 0; a.state_b[i] = 0; }
 		const int stride = (int)(G * RG_THREADS);
-		for (int base = b * RG_THREADS; base < N; base += 2 * stride) { /* two pixels per trip, as in phase A */
-			const int pix[2] = {base + (int)tid, base + stride + (int)tid};
-			u32 cell[2], roff[2];
+		for (int base = b * RG_THREADS; base < N; base += RG_KC * stride) { /* RG_KC pixels per trip: a ray goes to (start of its cell) + (its rank, from phase A) */
+			int pix[RG_KC];
+			u32 cell[RG_KC], rank[RG_KC], roff[RG_KC];
 #pragma unroll
-			for (int k = 0; k < 2; k++) cell[k] = (pix[k] < N) ? a.light_cell[pix[k]] : 0xffffffffu;
-#pragma unroll
-			for (int k = 0; k < 2; k++) roff[k] = (pix[k] < N) ? a.ray_offset[cell[k]] : 0u;
-#pragma unroll
-			for (int k = 0; k < 2; k++) {
-				if (base + k * stride >= N) break; /* warp-uniform */
-				const bool valid = pix[k] < N;
-				const u32 peers = __match_any_sync(UG_FULL_MASK, cell[k]);
-				const u32 lower = __popc(peers & ((1u << ug_lane()) - 1u));
-				u32 start = 0;
-				const int leader = __ffs(peers) - 1;
-				if (valid && lower == 0) start = atomicAdd(&a.cursor[cell[k]], (u32)__popc(peers));
-				start = __shfl_sync(UG_FULL_MASK, start, leader);
-				if (valid) a.ray_pix[roff[k] + start + lower] = (u32)pix[k];
+			for (int k = 0; k < RG_KC; k++) {
+				pix[k] = base + k * stride + (int)tid;
+				cell[k] = (pix[k] < N) ? a.light_cell[pix[k]] : 0u;
+				rank[k] = (pix[k] < N) ? a.ray_rank[pix[k]] : 0u;
 			}
+#pragma unroll
+			for (int k = 0; k < RG_KC; k++) roff[k] = (pix[k] < N) ? a.ray_offset[cell[k]] : 0u;
+#pragma unroll
+			for (int k = 0; k < RG_KC; k++)
+				if (pix[k] < N) a.ray_pix[roff[k] + rank[k]] = (u32)pix[k];
 		}
 		const u32 total = a.item_off[C];
 		if (b == 0 && tid == 0) a.counters[0] = min(total, a.item_cap);
@@ -301,7 +313,7 @@ bool ugk_regroup(cudaStream_t s, const FrameConst *fc, int light, const GridBuff
 {
 	RegroupArgs a;
 	a.fc = fc; a.light = light; a.N = N; a.C = C; a.t = t; a.dir = dir; a.grid_span = g.cell_span();
-	a.light_cell = r.cell; a.ray_span = r.span; a.ray_offset = r.offset; a.cursor = r.cursor; a.ray_pix = r.pix;
+	a.light_cell = r.cell; a.ray_span = r.span; a.ray_offset = r.offset; a.ray_rank = r.rank; a.ray_pix = r.pix;
 	a.item_off = r.item_off; a.items = r.items; a.counters = r.counters; a.state_a = r.state_a; a.state_b = r.state_b;
 	a.item_cap = (u32)r.item_cap;
 	if (fused) {

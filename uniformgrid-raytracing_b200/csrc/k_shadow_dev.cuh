@@ -9,6 +9,7 @@
 struct LightMap {
 	float lx, ly, lz, p0, p1, p2, num, half, r0, r1, r2, u0, u1, u2;
 	double den;
+	float inv_den;  /* (float)(1/den): only used to decide whether the double expression can be skipped */
 	int nbx, nby;
 };
 static __device__ __forceinline__ LightMap make_light_map(const ViewConst &lv)
@@ -22,11 +23,25 @@ static __device__ __forceinline__ LightMap make_light_map(const ViewConst &lv)
 	m.num = ug_dot(m.p0, m.p1, m.p2, m.lx, m.ly, m.lz) + p3;
 	m.half = lv.near_plane * lv.tan_half;                                                   /* float */
 	m.den = __dmul_rn(__dmul_rn(2.0, (double)lv.near_plane), (double)lv.tan_half);          /* 2.0 * near * tan: double */
+	m.inv_den = (float)(1.0 / m.den);
 	m.r0 = cc[16 + 0]; m.r1 = cc[16 + 4]; m.r2 = cc[16 + 8];
 	m.u0 = cc[16 + 1]; m.u1 = cc[16 + 5]; m.u2 = cc[16 + 9];
 	m.nbx = lv.nbx; m.nby = lv.nby;
 	return m;
 }
+/* floor(((double)a / den) * nb) as an int, the reference's double expression.  A float estimate of the same value is within
+ * 2e-7 relative of it (three roundings); wherever the estimate is further than that from an integer, its floor IS the floor of
+ * the double expression, and the two double divides per ray (the most expensive instructions of the map on this part) are
+ * skipped.  Rays whose estimate is close to a cell border, out of range or not finite take the exact path. */
+static __device__ __forceinline__ int light_bin(float a, const LightMap &m, int nb)
+{
+	const float vf = (a * m.inv_den) * (float)nb;
+	const float fl = floorf(vf), fr = vf - fl;
+	const float tol = fabsf(vf) * 4e-7f + 1e-6f;
+	if (fr > tol && fr < 1.0f - tol && fabsf(vf) < 1.0e6f) return (int)fl;
+	return ug_d2i(floor(__dmul_rn(__ddiv_rn((double)a, m.den), (double)nb)));
+}
+
 static __device__ __forceinline__ u32 light_cell_of(const LightMap &m, float ex, float ey, float ez, float tv, float dx, float dy, float dz)
 {
 	/* misc_kernel.cu:74-88: P = eye + t*dir (misses have t = -1 and still shoot), L = normalize(P - light) */
@@ -38,8 +53,8 @@ static __device__ __forceinline__ u32 light_cell_of(const LightMap &m, float ex,
 	const float right = X * m.r0 + Y * m.r1 + Z * m.r2;
 	const float up = X * m.u0 + Y * m.u1 + Z * m.u2;
 	/* misc_kernel.cu:115-116: (float)/(double) -> double, * int, floor, -> int */
-	const int blx = ug_d2i(floor(__dmul_rn(__ddiv_rn((double)(right + m.half), m.den), (double)m.nbx)));
-	const int bly = ug_d2i(floor(__dmul_rn(__ddiv_rn((double)(up + m.half), m.den), (double)m.nby)));
+	const int blx = light_bin(right + m.half, m, m.nbx);
+	const int bly = light_bin(up + m.half, m, m.nby);
 	u32 cell = (u32)(m.nbx * m.nby);
 	if (blx >= 0 && blx <= m.nbx - 1 && bly >= 0 && bly <= m.nby - 1) cell = (u32)(blx * m.nby + bly);
 	return cell;

@@ -82,7 +82,7 @@ struct LightRays {         /* DecisionData's regroup state (decision_data.h:72-8
 	u32 *pix = nullptr;    /* [N]   d_map[0..N) after the regroup: pixel ids grouped by light cell */
 	u32 *span = nullptr;   /* [C+1] rays per light cell (last = outside) */
 	u32 *offset = nullptr; /* [C+2] */
-	u32 *cursor = nullptr; /* [C+1] */
+	u32 *rank = nullptr;   /* [N]   position of every ray among its cell's rays (handed out by the histogram's atomics) */
 	u32 *item_off = nullptr; /* [C+1] first work item of every cell */
 	uint2 *items = nullptr;  /* work items of the shadow pass: (cell, local index) */
 	u32 *counters = nullptr; /* [0] number of items, [1] ticket */
