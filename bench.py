@@ -217,7 +217,42 @@ def run_ours(args):
         dist.broadcast_object_list(uid, src=0)
         r.comm_init(rank, world, uid[0])
 
-    lo, hi = (nby * rank // world, nby * (rank + 1) // world) if mode == "strips" else (0, nby)
+    # ---- strips: move the strip boundaries until every rank's strip costs the same (measured, before the communicator exists)
+    bounds, balance = None, None
+    if world > 1 and not args.equal_strips:
+        bounds = [nby * k // world for k in range(world + 1)]
+        r.set_screen(scene.width, scene.height, scene.fovy)
+        history = []
+        for it in range(5):
+            r.set_strip_bounds(bounds, rank)
+            pcal = r.params(scene, frame=0, flags=0, strip=(rank, world), bounces=0, slabs=args.slabs)
+            for _ in range(3):
+                r.render(pcal)
+            ts = []
+            for _ in range(7):
+                r.render(pcal)
+                ts.append(r.stats().ms_frame)
+            mine = torch.tensor([float(np.median(ts))], dtype=torch.float64, device=dev)
+            allt = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allt, mine)
+            T = np.asarray([float(x.item()) for x in allt])
+            history.append({"bounds": list(bounds), "ms": [round(float(x), 4) for x in T]})
+            if T.max() / T.mean() < 1.03 or it == 4:
+                break
+            # cost density per cell row inside every strip -> cumulative cost over the rows -> equal-cost boundaries (damped)
+            dens = np.concatenate([np.full(bounds[k + 1] - bounds[k], T[k] / (bounds[k + 1] - bounds[k])) for k in range(world)])
+            cum = np.concatenate([[0.0], np.cumsum(dens)])
+            target = [int(np.searchsorted(cum, cum[-1] * k / world)) for k in range(1, world)]
+            new = [0] + [int(round(0.75 * t + 0.25 * b)) for t, b in zip(target, bounds[1:-1])] + [nby]
+            for k in range(1, world + 1):
+                new[k] = max(new[k], new[k - 1] + 1)
+            for k in range(world - 1, 0, -1):
+                new[k] = min(new[k], new[k + 1] - 1)
+            bounds = new
+        balance = {"row_bounds": list(bounds), "iterations": history,
+                   "note": "strip boundaries (cell rows) moved until the strips' measured frame times agree: image-space cost is not uniform"}
+        r.set_strip_bounds(bounds, rank)
+    lo, hi = ((bounds[rank], bounds[rank + 1]) if bounds else (nby * rank // world, nby * (rank + 1) // world)) if mode == "strips" else (0, nby)
     n_local = scene.width * (hi - lo) * 8
     if world > 1:
         join_comm()
@@ -364,6 +399,8 @@ def run_ours(args):
     check, single = None, None
     if world > 1:
         import hashlib
+        if bounds:
+            r.set_strip_bounds(bounds, rank)
         r.render_host(r.params(scene, frame=0, flags=base_flags, strip=(rank, world), bounces=bounces, slabs=args.slabs), host_img.numpy())
         barrier()
         if rank == 0:
@@ -493,6 +530,8 @@ def run_ours(args):
             other["value"] = (scene.rays_per_frame() * other["frames_per_step"] + int(refl.item()) / frames_per_step * other["frames_per_step"]) / (other["ms_per_step"] * 1e-3) / 1e6
             other["unit"] = "Mrays/s"
             line[other["mode"]] = other
+        if balance:
+            line["strip_balance"] = balance
         if check:
             line["gathered_frame_check"] = check
             line["single_gpu_same_frame"] = single
@@ -521,6 +560,7 @@ def main():
                     help="perspective: the light path north-star names (default); spherical: the one the committed display() runs")
     ap.add_argument("--shader", default="lambert", choices=["lambert", "spot"], help="spot: Shader::spotlight_shade (display() from its third frame on)")
     ap.add_argument("--slabs", type=int, default=1, help="NUM_SLABS (main.cu.h:18 compiles 1)")
+    ap.add_argument("--equal-strips", action="store_true", help="N > 1: keep the equal split instead of balancing the strip boundaries by measurement")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

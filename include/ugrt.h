@@ -191,6 +191,9 @@ int ug_model_rotate_bunny(ug_context *ctx, float rot_factor);                   
 /* ---- per_frame_funcs.h, one call per reference function (state lives in ctx) */
 int ug_set_screen(ug_context *ctx, int width, int height, float fovy);            /* main.cu.h:10-30 made runtime */
 int ug_set_strip(ug_context *ctx, int strip_index, int strip_count);
+/* the same with explicit boundaries (cell rows, row_bounds[0] = 0 ... row_bounds[strip_count] = height/8): strips of unequal height for
+ * load balance; ug_frame_params with the same (strip_index, strip_count) keep them, every rank of a communicator passes the same array */
+int ug_set_strip_bounds(ug_context *ctx, const int *row_bounds, int strip_count, int strip_index);
 int ug_set_slabs(ug_context *ctx, int num_slabs);                                 /* main.cu.h:18 NUM_SLABS made runtime */
 int ug_update_light_position(ug_context *ctx, const float *xyz, int num_lights);  /* per_frame_funcs.h:6-16 */
 int ug_fill_coordinates_data(ug_context *ctx, const ug_camera *cam);              /* :18-43 (+ setDirectionTexture) */

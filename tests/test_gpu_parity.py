@@ -584,3 +584,30 @@ def test_reflection_degenerate_bounding_box(ug, oracle, make):
         assert np.array_equal(parity.gpu_frame(r, s2, flags=0, bounces=2)["rgb"], cpu2["rgb_reflect"])
     finally:
         r.close()
+
+
+def test_unequal_strips(renderer, ug, oracle):
+    """ug_set_strip_bounds: strips of unequal height (what a host does to balance the ranks of an N-GPU frame) - every strip's
+    hits, shadow bits and pixels are the corresponding rows of the oracle's frame, and the equal split is back afterwards."""
+    s = scenes.scene_a(256, 264)        # 33 cell rows
+    renderer.set_scene(s)
+    cpu = cpu_frame(oracle, s)
+    bounds = [0, 1, 7, 8, 30, 33]
+    renderer.set_screen(s.width, s.height, s.fovy)
+    img = []
+    for rank in range(5):
+        renderer.set_strip_bounds(bounds, rank)
+        part = parity.gpu_frame(renderer, s, flags=0, strip=(rank, 5))
+        sl = slice(s.width * bounds[rank] * 8, s.width * bounds[rank + 1] * 8)
+        assert part["t"].size == sl.stop - sl.start
+        for k in ("t", "id", "shadowed"):
+            assert np.array_equal(parity.bits(part[k]), parity.bits(cpu[k][sl])), (rank, k)
+        img.append(part["rgb"])
+    assert np.array_equal(np.concatenate(img), cpu["rgb"])
+    with pytest.raises(RuntimeError):
+        renderer.set_strip_bounds([0, 5, 5, 33], 0)           # an empty strip
+    with pytest.raises(RuntimeError):
+        renderer.set_strip_bounds([0, 5, 32], 0)              # does not end at the last row
+    part = parity.gpu_frame(renderer, s, flags=0, strip=(1, 3))   # another split: equal strips again
+    assert np.array_equal(part["rgb"], cpu["rgb"][3 * s.width * 88:3 * s.width * 176])
+    renderer.render(renderer.params(s, strip=(0, 1)))

@@ -46,6 +46,16 @@ def _worker(rank, world, port, out_path, transport):
     if rank == 0:
         np.save(out_path, host.numpy().copy())
     dist.barrier()
+    # strips of unequal height (ug_set_strip_bounds): the gather's offsets follow the boundaries
+    nby = scene.height // 8
+    bounds = [0] + sorted({1 + (7 * k) % (nby - 2) for k in range(1, world)}) + [nby]
+    bounds = bounds if len(bounds) == world + 1 else [nby * k // world for k in range(world + 1)]
+    r.set_strip_bounds(bounds, rank)
+    for frame in range(2):
+        r.render_host(r.params(scene, frame=frame, strip=(rank, world)), host.numpy())
+    if rank == 0:
+        np.save(out_path + ".bounds.npy", host.numpy().copy())
+    dist.barrier()
     # frame-parallel mode: rank k renders frame k of a dynamic scene on its own, rank 0 collects the frames (slot k = rank k)
     dyn = scenes.scene_c(240, 136)
     r.set_scene(dyn)
@@ -83,6 +93,7 @@ def test_strip_gather_over_nccl(oracle, tmp_path, transport):
     out = str(tmp_path / "full.npy")
     mp.spawn(_worker, args=(world, _free_port(), out, transport), nprocs=world, join=True)
     assert np.array_equal(np.load(out), want)
+    assert np.array_equal(np.load(out + ".bounds.npy"), want), "strips of unequal height"
     dyn = scenes.scene_c(240, 136)
     got = np.load(out + ".frames.npy").reshape(world, -1)
     for k in range(world):

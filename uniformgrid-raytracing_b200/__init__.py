@@ -90,7 +90,7 @@ def lib() -> C.CDLL:
             "ug_model_set": (C.c_int, [vp, f, C.c_int, i, C.c_int, i, f, C.c_int]),
             "ug_obj_parse": (C.c_int, [C.c_char_p, i, i, f, i, i]), "ug_material_parse": (C.c_int, [C.c_char_p, i, f]),
             "ug_model_init_orig_list": (C.c_int, [vp, C.c_int, C.c_int]), "ug_model_set_reflect": (C.c_int, [vp, f, C.c_int]), "ug_model_rotate_bunny": (C.c_int, [vp, C.c_float]),
-            "ug_set_screen": (C.c_int, [vp, C.c_int, C.c_int, C.c_float]), "ug_set_strip": (C.c_int, [vp, C.c_int, C.c_int]), "ug_set_slabs": (C.c_int, [vp, C.c_int]),
+            "ug_set_screen": (C.c_int, [vp, C.c_int, C.c_int, C.c_float]), "ug_set_strip": (C.c_int, [vp, C.c_int, C.c_int]), "ug_set_strip_bounds": (C.c_int, [vp, i, C.c_int, C.c_int]), "ug_set_slabs": (C.c_int, [vp, C.c_int]),
             "ug_update_light_position": (C.c_int, [vp, f, C.c_int]),
             "ug_fill_coordinates_data": (C.c_int, [vp, C.POINTER(Camera)]), "ug_build_frustum_grid": (C.c_int, [vp]),
             "ug_trace": (C.c_int, [vp]), "ug_shadow_pass": (C.c_int, [vp, C.c_int, C.POINTER(Camera)]),
@@ -260,6 +260,14 @@ class Renderer:
     def render_host(self, p: FrameParams, out: np.ndarray):
         assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"]
         self._ck(self.L.ug_render_frame_host(self.ctx, C.byref(p), out.ctypes.data_as(C.c_void_p)), "ug_render_frame_host")
+
+    def set_strip_bounds(self, row_bounds, index: int):
+        """Strips of unequal height (cell-row boundaries 0 ... height/8); frames rendered with strip=(index, len(row_bounds)-1) keep them."""
+        b = np.ascontiguousarray(row_bounds, np.int32)
+        self._ck(self.L.ug_set_strip_bounds(self.ctx, b.ctypes.data_as(C.POINTER(C.c_int)), b.size - 1, int(index)), "ug_set_strip_bounds")
+
+    def set_screen(self, width: int, height: int, fovy: float):
+        self._ck(self.L.ug_set_screen(self.ctx, width, height, float(fovy)), "ug_set_screen")
 
     def set_stream(self, cuda_stream: int):
         self._ck(self.L.ug_set_stream(self.ctx, C.c_void_p(cuda_stream)), "ug_set_stream")

@@ -639,13 +639,25 @@ extern "C" int ug_model_rotate_bunny(ug_context *ctx, float rot_factor)
 }
 
 /* ------------------------------------------------------------------ screen / strip */
+/* cell rows [lo, hi) of strip r: an equal split of the nby rows, or the caller's boundaries (ug_set_strip_bounds) */
+void ug_strip_rows(const ug_context *ctx, int r, int *lo, int *hi)
+{
+	const int sc = ctx->strip_count > 0 ? ctx->strip_count : 1;
+	if ((int)ctx->strip_bounds.size() == sc + 1 && ctx->strip_bounds.back() == ctx->nby) {
+		*lo = ctx->strip_bounds[r];
+		*hi = ctx->strip_bounds[r + 1];
+		return;
+	}
+	*lo = (int)((long long)ctx->nby * r / sc);
+	*hi = (int)((long long)ctx->nby * (r + 1) / sc);
+}
+
 static void update_geometry(ug_context *ctx)
 {
 	ctx->nbx = ctx->W / UG_TILE;
 	ctx->nby = ctx->H / UG_TILE;
-	const int sc = ctx->strip_count > 0 ? ctx->strip_count : 1;
-	ctx->gy_lo = (int)((long long)ctx->nby * ctx->strip_index / sc);
-	const int hi = (int)((long long)ctx->nby * (ctx->strip_index + 1) / sc);
+	int hi = 0;
+	ug_strip_rows(ctx, ctx->strip_index, &ctx->gy_lo, &hi);
 	ctx->gy_cnt = hi - ctx->gy_lo;
 	ctx->C_cam = ctx->nbx * ctx->gy_cnt;
 	ctx->C_light = ctx->nbx * ctx->nby;
@@ -676,7 +688,25 @@ extern "C" int ug_set_strip(ug_context *ctx, int strip_index, int strip_count)
 	if (!ctx || strip_count <= 0 || strip_index < 0 || strip_index >= strip_count) return ug_fail(ctx, UG_ERR_ARG, "bad strip %d/%d", strip_index, strip_count);
 	if (ctx->strip_index == strip_index && ctx->strip_count == strip_count) return UG_OK;
 	ctx->strip_index = strip_index; ctx->strip_count = strip_count;
+	ctx->strip_bounds.clear(); /* a different split: equal strips again */
 	if (ctx->W > 0) update_geometry(ctx);
+	ctx->frame_valid = false;
+	return UG_OK;
+}
+
+/* Strips of unequal height: row_bounds[0] = 0 < ... < row_bounds[strip_count] = cell rows of the screen.  Image-space cost is
+ * not uniform (config D: the slowest of 8 equal strips takes 1.34x the mean), so a host that measures its ranks can move
+ * the boundaries; every rank of a communicator must be given the same array.  ug_set_strip with another split forgets them. */
+extern "C" int ug_set_strip_bounds(ug_context *ctx, const int *row_bounds, int strip_count, int strip_index)
+{
+	if (!ctx || !row_bounds || strip_count <= 0 || strip_index < 0 || strip_index >= strip_count) return ug_fail(ctx, UG_ERR_ARG, "bad strip %d/%d", strip_index, strip_count);
+	if (ctx->W <= 0) return ug_fail(ctx, UG_ERR_ARG, "ug_set_strip_bounds: ug_set_screen first");
+	if (row_bounds[0] != 0 || row_bounds[strip_count] != ctx->H / UG_TILE) return ug_fail(ctx, UG_ERR_ARG, "strip bounds must run from 0 to %d cell rows", ctx->H / UG_TILE);
+	for (int r = 0; r < strip_count; r++)
+		if (row_bounds[r + 1] <= row_bounds[r]) return ug_fail(ctx, UG_ERR_ARG, "strip %d is empty", r);
+	ctx->strip_index = strip_index; ctx->strip_count = strip_count;
+	ctx->strip_bounds.assign(row_bounds, row_bounds + strip_count + 1);
+	update_geometry(ctx);
 	ctx->frame_valid = false;
 	return UG_OK;
 }
@@ -860,7 +890,8 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 	if (gather_strips) {
 		size_t acc = 0;
 		for (int r = 0; r < ctx->comm_world && r < UG_MAX_RANKS; r++) {
-			const long long lo = (long long)ctx->nby * r / ctx->comm_world, hi = (long long)ctx->nby * (r + 1) / ctx->comm_world;
+			int lo = 0, hi = 0;
+			ug_strip_rows(ctx, r, &lo, &hi);
 			g_bytes[r] = 3 * (size_t)ctx->W * (size_t)(hi - lo) * UG_TILE;
 			g_offs[r] = acc;
 			acc += g_bytes[r];
@@ -1006,6 +1037,7 @@ static unsigned long long frame_key(const ug_context *ctx, const ug_frame_params
 	unsigned long long k = 1469598103934665603ull;
 	auto mix = [&](unsigned long long v) { k = (k ^ v) * 1099511628211ull; };
 	mix((unsigned long long)ctx->W); mix((unsigned long long)ctx->H); mix((unsigned long long)ctx->gy_lo); mix((unsigned long long)ctx->gy_cnt);
+	for (int b : ctx->strip_bounds) mix((unsigned long long)b); /* the gather's offsets depend on every rank's strip */
 	mix((unsigned long long)ctx->num_faces); mix((unsigned long long)p->num_lights); mix((unsigned long long)(p->flags & (UG_FLAG_FULL_BUFFERS | UG_FLAG_GATHER_FRAMES | UG_FLAG_SPOT_SHADE | UG_FLAG_GATHER_DEFERRED)));
 	mix((unsigned long long)(p->transform && ctx->d_vertex_orig_list ? 1 : 0)); mix((unsigned long long)ctx->cam_grid.cap);
 	for (int l = 0; l < p->num_lights; l++) mix((unsigned long long)ctx->light_grid[l].cap);

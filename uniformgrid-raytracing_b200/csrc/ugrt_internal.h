@@ -150,6 +150,7 @@ struct ug_context {
 	int W = 0, H = 0, nbx = 0, nby = 0;
 	float fovy = 45.0f;
 	int strip_index = 0, strip_count = 1, gy_lo = 0, gy_cnt = 0;
+	std::vector<int> strip_bounds; /* [strip_count + 1] cell-row boundaries when the strips are not an equal split (ug_set_strip_bounds) */
 	int N = 0, C_cam = 0, C_light = 0; /* pixels / cells of this strip; cells of a (full) light grid */
 
 	/* frame constants */
@@ -224,6 +225,7 @@ struct ug_context {
 /* ---------------------------------------------------------------- error helpers */
 int ug_fail(ug_context *ctx, int code, const char *fmt, ...);
 void ug_drop_graphs(ug_context *ctx);
+void ug_strip_rows(const ug_context *ctx, int r, int *lo, int *hi);
 #define UG_CUDA(ctx, call)                                                                              \
 	do {                                                                                                \
 		cudaError_t e_ = (call);                                                                        \
