@@ -217,54 +217,84 @@ def run_ours(args):
         dist.broadcast_object_list(uid, src=0)
         r.comm_init(rank, world, uid[0])
 
+    bounces = scene.bounces if args.bounces < 0 else args.bounces
+    if not any(m.reflect > 0 for m in scene.materials):
+        bounces = 0
+    base_flags = (ug.FLAG_SPHERICAL_LIGHTS if args.light_grid == "spherical" else 0) | (ug.FLAG_SPOT_SHADE if args.shader == "spot" else 0)
+
     # ---- strips: move the strip boundaries until every rank's strip costs the same (measured, before the communicator exists)
     bounds, balance = None, None
-    if world > 1 and not args.equal_strips:
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)            # > 126 MB L2
+    def rebalance(T, bounds):
+        """Equal-cost strip boundaries from the measured strip times T.  A strip costs F + (its rows' cost): F, the part that does
+        not shrink with the strip (launch chain, light grid, projecting every triangle), is taken as 0.3 x the fastest strip -
+        without it the correction undershoots and the loop converges slowly.  The last step of a loop is not kept blindly: the
+        best boundaries seen (smallest slowest strip) are."""
+        F = 0.3 * float(T.min())
+        dens = np.concatenate([np.full(bounds[k + 1] - bounds[k], max(T[k] - F, 1e-6) / (bounds[k + 1] - bounds[k])) for k in range(world)])
+        cum = np.concatenate([[0.0], np.cumsum(dens)])
+        target = [int(np.searchsorted(cum, cum[-1] * k / world)) for k in range(1, world)]
+        new = [0] + [int(round(0.75 * t + 0.25 * b)) for t, b in zip(target, bounds[1:-1])] + [nby]
+        for k in range(1, world + 1):
+            new[k] = max(new[k], new[k - 1] + 1)
+        for k in range(world - 1, 0, -1):
+            new[k] = min(new[k], new[k + 1] - 1)
+        return new
+
+    def measure_strips(own: bool):
+        """median time of this rank's strip over 9 flushed frames, gathered from every rank"""
+        pcal = r.params(scene, frame=0, flags=base_flags, strip=(rank, world), bounces=bounces, slabs=args.slabs)
+        for _ in range(3):
+            r.render(pcal)
+        ts = []
+        for _ in range(9):
+            if not args.no_flush:
+                flush.zero_()                      # the timed frames start from a flushed L2 as well
+            r.render(pcal)
+            st_ = r.stats()
+            ts.append(st_.ms_own if own else st_.ms_frame)
+        mine = torch.tensor([float(np.median(ts))], dtype=torch.float64, device=dev)
+        allt = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allt, mine)
+        return np.asarray([float(x.item()) for x in allt])
+
+    balancing = world > 1 and not args.equal_strips and mode == "strips"
+    history = []
+    if balancing:   # first without the communicator: every rank renders its strip on its own
         bounds = [nby * k // world for k in range(world + 1)]
         r.set_screen(scene.width, scene.height, scene.fovy)
-        history = []
-        for it in range(5):
+        for it in range(4):
             r.set_strip_bounds(bounds, rank)
-            pcal = r.params(scene, frame=0, flags=0, strip=(rank, world), bounces=0, slabs=args.slabs)
-            for _ in range(3):
-                r.render(pcal)
-            ts = []
-            for _ in range(7):
-                r.render(pcal)
-                ts.append(r.stats().ms_frame)
-            mine = torch.tensor([float(np.median(ts))], dtype=torch.float64, device=dev)
-            allt = [torch.zeros_like(mine) for _ in range(world)]
-            dist.all_gather(allt, mine)
-            T = np.asarray([float(x.item()) for x in allt])
-            history.append({"bounds": list(bounds), "ms": [round(float(x), 4) for x in T]})
-            if T.max() / T.mean() < 1.03 or it == 4:
+            T = measure_strips(own=False)
+            history.append({"bounds": list(bounds), "ms": [round(float(x), 4) for x in T], "gathered": False})
+            if T.max() / T.mean() < 1.015 or it == 3:
                 break
-            # cost density per cell row inside every strip -> cumulative cost over the rows -> equal-cost boundaries (damped)
-            dens = np.concatenate([np.full(bounds[k + 1] - bounds[k], T[k] / (bounds[k + 1] - bounds[k])) for k in range(world)])
-            cum = np.concatenate([[0.0], np.cumsum(dens)])
-            target = [int(np.searchsorted(cum, cum[-1] * k / world)) for k in range(1, world)]
-            new = [0] + [int(round(0.75 * t + 0.25 * b)) for t, b in zip(target, bounds[1:-1])] + [nby]
-            for k in range(1, world + 1):
-                new[k] = max(new[k], new[k - 1] + 1)
-            for k in range(world - 1, 0, -1):
-                new[k] = min(new[k], new[k + 1] - 1)
-            bounds = new
-        balance = {"row_bounds": list(bounds), "iterations": history,
-                   "note": "strip boundaries (cell rows) moved until the strips' measured frame times agree: image-space cost is not uniform"}
+            bounds = rebalance(T, bounds)
         r.set_strip_bounds(bounds, rank)
     lo, hi = ((bounds[rank], bounds[rank + 1]) if bounds else (nby * rank // world, nby * (rank + 1) // world)) if mode == "strips" else (0, nby)
     n_local = scene.width * (hi - lo) * 8
     if world > 1:
         join_comm()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)            # > 126 MB L2
+    if balancing:   # then inside the real gathered frames, on each rank's own time (ug_stats.ms_own: first kernel -> its last remote store)
+        best = None
+        for it in range(6):
+            T = measure_strips(own=True)
+            history.append({"bounds": list(bounds), "ms": [round(float(x), 4) for x in T], "gathered": True})
+            if best is None or T.max() < best[0]:
+                best = (float(T.max()), list(bounds))
+            if T.max() / T.mean() < 1.015 or it == 5:
+                break
+            bounds = rebalance(T, bounds)
+            r.set_strip_bounds(bounds, rank)
+        if bounds != best[1]:
+            bounds = best[1]
+            r.set_strip_bounds(bounds, rank)
+        balance = {"row_bounds": list(bounds), "iterations": history,
+                   "note": "strip boundaries (cell rows) moved until the strips' measured times agree: image-space cost is not uniform"}
+        lo, hi = bounds[rank], bounds[rank + 1]
+        n_local = scene.width * (hi - lo) * 8
     host_img = torch.empty(3 * scene.num_pixels, dtype=torch.uint8).pin_memory()
     rays_frame = scene.rays_per_frame()
-
-    bounces = scene.bounces if args.bounces < 0 else args.bounces
-    if not any(m.reflect > 0 for m in scene.materials):
-        bounces = 0
-
-    base_flags = (ug.FLAG_SPHERICAL_LIGHTS if args.light_grid == "spherical" else 0) | (ug.FLAG_SPOT_SHADE if args.shader == "spot" else 0)
 
     def step(i, flags=0, m=None):
         m = m or mode
@@ -293,6 +323,10 @@ def run_ours(args):
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    if world > 1:
+        # the ranks leave the host barrier up to a millisecond apart, and the first frame's handshake would charge that skew to
+        # frame 0: one more untimed frame lines the GPUs up (its "done" handshake ends on every rank at the same time)
+        step(max(args.warmup, 3))
     wall0 = time.perf_counter()
     for i in range(args.steps):
         if not args.no_flush:
@@ -449,6 +483,31 @@ def run_ours(args):
         config_d = {"workload": workload_name(sd, 1), "ms_per_frame": msd, "value": sd.rays_per_frame() / (msd * 1e-3) / 1e6, "unit": "Mrays/s", "steps": 20}
         rd.close()
 
+    # ---- UG_TIMELINE=1: marker times of every rank's frame (development aid; the markers are extra one-thread kernels, so the
+    #      env variable is never set for a bench line that is reported)
+    timeline = None
+    if os.environ.get("UG_TIMELINE"):
+        import ctypes as C
+        L_ = ug.lib()
+        L_.ug_timeline.restype = C.c_int
+        L_.ug_timeline.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        acc = []
+        for it in range(8):
+            flush.zero_()
+            step(it)
+            r.synchronize()
+            out = (C.c_double * 64)()
+            L_.ug_timeline(r.ctx, out)
+            acc.append(np.array(out[:]))
+        tmed = torch.tensor(np.median(np.stack(acc[2:]), axis=0) / 1000.0, dtype=torch.float64, device=dev)
+        allt = [torch.zeros_like(tmed) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(allt, tmed)
+        else:
+            allt = [tmed]
+        names = {1: "cam_grid", 11: "light_grid", 6: "ready", 2: "primary", 13: "regroup", 14: "shadow", 3: "shade", 5: "gather"}
+        timeline = {str(k): {n: round(float(allt[k][i].item()), 1) for i, n in names.items()} for k in range(world)}
+
     if rank == 0:
         P, N, Cc = st2.cam_pairs, st2.num_pixels, st2.num_cells
         T = scene.num_tris
@@ -516,7 +575,7 @@ def run_ours(args):
                        "pairs_camera_grid": int(P), "pairs_light_grids": [int(st2.light_pairs[l]) for l in range(len(scene.lights))],
                        "light_grid": args.light_grid, "shader": args.shader, "num_slabs": args.slabs},
             "ms_per_frame_warm_l2": warm_ms, "ms_per_frame_p50": float(np.median(per)), "ms_per_frame_p10": float(np.percentile(per, 10)),
-            "ms_per_frame_p90": float(np.percentile(per, 90)), "wall_s_timed_region": wall,
+            "ms_per_frame_p90": float(np.percentile(per, 90)), "ms_per_frame_all": [round(float(x), 4) for x in per], "wall_s_timed_region": wall,
             "e2e": {"value": rays_frame * e2e_steps / e2e_dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(ug.lib().ug_frame_const_bytes()) * world,
                     "d2h_bytes_per_step": 3 * scene.num_pixels * frames_per_step, "steps": e2e_steps, "ms_per_step": e2e_dt / e2e_steps * 1e3},
             "gpu_launches": int(launches_per_frame) * args.steps * world,
@@ -530,6 +589,8 @@ def run_ours(args):
             other["value"] = (scene.rays_per_frame() * other["frames_per_step"] + int(refl.item()) / frames_per_step * other["frames_per_step"]) / (other["ms_per_step"] * 1e-3) / 1e6
             other["unit"] = "Mrays/s"
             line[other["mode"]] = other
+        if timeline:
+            line["timeline_us"] = timeline
         if balance:
             line["strip_balance"] = balance
         if check:

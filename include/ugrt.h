@@ -144,6 +144,8 @@ typedef struct ug_stats {
 	float ms_transform, ms_cam_grid, ms_trace, ms_light_grid, ms_regroup, ms_shadow, ms_shade; /* STAGE_EVENTS only */
 	unsigned reflect_rays;                /* row R: live reflection rays of the last frame, summed over bounces */
 	unsigned reflect_pairs;               /* row R: (cell,triangle) pairs of the uniform grid */
+	float ms_own;                         /* gathered frames: first kernel -> this rank's own last store, i.e. ms_frame without the wait for the
+	                                         other ranks (what a host balances strip heights with); otherwise = ms_frame */
 } ug_stats;
 
 /* ---- lifetime */

@@ -8,7 +8,7 @@ import ugrt  # noqa
 import uniformgrid_raytracing_b200 as ug
 from uniformgrid_raytracing_b200 import scenes
 
-NAMES = {0: "frame start", 1: "cam grid done", 2: "primary rays done", 3: "shade done", 4: "combine done", 10: "light grid start", 11: "light grid done",
+NAMES = {0: "frame start", 1: "cam grid done", 2: "primary rays done", 3: "shade done", 4: "combine done", 5: "gather done", 6: "ready handshake done", 10: "light grid start", 11: "light grid done",
          12: "regroup start", 13: "regroup done", 14: "shadow done", 20: "ugrid start", 21: "ugrid done", 22: "refl rays start", 23: "refl rays done"}
 name = sys.argv[1] if len(sys.argv) > 1 else "B"
 bounces = int(sys.argv[2]) if len(sys.argv) > 2 else 1

@@ -59,7 +59,7 @@ class Stats(C.Structure):
                 ("light_pairs", C.c_uint * UG_MAX_LIGHTS), ("pair_capacity", C.c_uint), ("overflowed", C.c_int),
                 ("kernel_launches", C.c_int), ("ms_frame", C.c_float), ("ms_transform", C.c_float), ("ms_cam_grid", C.c_float),
                 ("ms_trace", C.c_float), ("ms_light_grid", C.c_float), ("ms_regroup", C.c_float), ("ms_shadow", C.c_float),
-                ("ms_shade", C.c_float), ("reflect_rays", C.c_uint), ("reflect_pairs", C.c_uint)]
+                ("ms_shade", C.c_float), ("reflect_rays", C.c_uint), ("reflect_pairs", C.c_uint), ("ms_own", C.c_float)]
 
 
 def build(verbose: bool = False) -> str:

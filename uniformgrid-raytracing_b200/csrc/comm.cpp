@@ -92,6 +92,7 @@ extern "C" int ug_comm_init(ug_context *ctx, int rank, int world, const void *un
 	ctx->comm_world = world;
 	unmap_peer(ctx);
 	ctx->use_push = false;
+	ctx->flag_handshake = getenv("UG_NCCL_HANDSHAKE") == nullptr;
 	ctx->rgb_full_bytes = 0; /* the gather buffer is shared again (collectively) by the next frame */
 	ug_drop_graphs(ctx);
 	return UG_OK;
@@ -131,7 +132,8 @@ int ugc_share_full(ug_context *ctx, size_t bytes)
 	if (rank == 0) {
 		if (ctx->d_rgb_full) cudaFree(ctx->d_rgb_full);
 		ctx->d_rgb_full = nullptr;
-		UG_CUDA(ctx, cudaMalloc((void **)&ctx->d_rgb_full, bytes));
+		UG_CUDA(ctx, cudaMalloc((void **)&ctx->d_rgb_full, bytes + UG_COMM_FLAGS_BYTES));
+		UG_CUDA(ctx, cudaMemsetAsync(ctx->d_rgb_full + bytes, 0, UG_COMM_FLAGS_BYTES, s)); /* handshake flags, all sequence numbers 0 */
 		if (getenv("UG_NO_PUSH") || cudaIpcGetMemHandle(&h, ctx->d_rgb_full) != cudaSuccess) { ok = 0; cudaGetLastError(); }
 		UG_CUDA(ctx, cudaMemcpyAsync(scr, &h, sizeof(h), cudaMemcpyHostToDevice, s));
 	}
@@ -153,19 +155,35 @@ int ugc_share_full(ug_context *ctx, size_t bytes)
 	ctx->use_push = ok != 0;
 	if (!ctx->use_push) unmap_peer(ctx);
 	ctx->rgb_full_bytes = bytes;
+	UG_CUDA(ctx, cudaMemsetAsync(scr + 200, 0, 4, s)); /* this rank's count of gathered frames (flag handshakes) */
+	UG_CUDA(ctx, cudaStreamSynchronize(s));
 	return UG_OK;
 }
 
 /* push transport: "rank 0 is past its read-out of the previous frame".  Issued at the head of the frame on a side
  * branch, so its latency hides behind the frame's own kernels. */
-int ugc_ready(ug_context *ctx, cudaStream_t s)
+static void *comm_flags(ug_context *ctx)
+{
+	unsigned char *base = ctx->comm_rank == 0 ? ctx->d_rgb_full : ctx->peer_full;
+	return base ? base + ctx->rgb_full_bytes : nullptr;
+}
+int ugc_ready(ug_context *ctx, cudaStream_t s, bool deferred)
 {
 	if (!ctx->use_push) return UG_OK;
 	unsigned char *scr = (unsigned char *)ctx->d_comm_scratch;
+	if (ctx->flag_handshake && !deferred) { /* flags in rank 0's mapped buffer instead of a collective (k_shade.cu) */
+		ugk_comm_ready(s, comm_flags(ctx), (u32 *)(scr + 200), ctx->comm_rank);
+		return UG_OK;
+	}
 	UG_NCCL(ctx, N.AllReduce(scr + 128, scr + 128, 1, ncclUint32, ncclSum, (ncclComm_t)ctx->comm, s));
 	return UG_OK;
 }
 
+/* ns of this rank's own work in the last gathered frame (first kernel -> in front of the "done" handshake); flag handshakes only */
+u32 *ugc_own_word(ug_context *ctx)
+{
+	return (ctx->comm && ctx->use_push && ctx->flag_handshake && ctx->d_comm_scratch) ? (u32 *)((unsigned char *)ctx->d_comm_scratch + 204) : nullptr;
+}
 u32 *ugc_overflow_word(ug_context *ctx)
 {
 	return (ctx->comm && ctx->use_push && ctx->d_comm_scratch) ? (u32 *)((unsigned char *)ctx->d_comm_scratch + 136) : nullptr;
@@ -211,7 +229,10 @@ int ugc_gather_strips(ug_context *ctx, cudaStream_t s, const unsigned char *stri
 		else UG_CUDA(ctx, cudaMemcpyAsync(ctx->peer_full + slot_offset + offs[rank], strip, bytes[rank], cudaMemcpyDefault, s)); /* copy engine, over NVLink */
 		/* done: every copy precedes its rank's contribution.  Deferred: the NEXT frame's "ready" handshake is issued after
 		 * this copy in stream order on every rank, so it doubles as this frame's "done" and nothing waits here */
-		if (!deferred) UG_NCCL(ctx, N.AllReduce(scr + 132, scr + 132, 2, ncclUint32, ncclSum, comm, s)); /* [1] = ranks whose pair arena overflowed */
+		if (!deferred) {
+			if (ctx->flag_handshake) ugk_comm_done(s, comm_flags(ctx), (const u32 *)(scr + 200), rank, world, (u32 *)(scr + 136), ctx->d_tstart, (u32 *)(scr + 204));
+			else UG_NCCL(ctx, N.AllReduce(scr + 132, scr + 132, 2, ncclUint32, ncclSum, comm, s)); /* [1] = ranks whose pair arena overflowed */
+		}
 		return UG_OK;
 	}
 	if (rank == 0) UG_CUDA(ctx, cudaMemcpyAsync(full + offs[0], strip, bytes[0], cudaMemcpyDeviceToDevice, s));

@@ -80,24 +80,35 @@ extern "C" int ug_create(ug_context **out, int device)
 		const float v = (float)atof(e);
 		if (v >= 0.25f && v <= 256.0f) ctx->refl_cells_per_tri = v;
 	}
-	UG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
-	ctx->stream = ctx->own_stream;
+	/* Priorities follow the slack of each branch of the frame graph (the graph is instantiated with per-node priorities): the
+	 * camera grid, the primary rays and the reflection rays are the critical path (greatest); a light grid or the uniform grid is
+	 * not needed before the primary rays are done (least).  Measured on the B200 this changes nothing (config D as 8 strips:
+	 * camera grid done at 178 us beside the light-grid build with or without priorities, ~105 us alone) - the build kernels
+	 * are persistent, all their blocks are resident at once and share the SMs' issue slots whatever the priority; what
+	 * does help is giving the non-critical build fewer blocks (UG_LIGHT_BLOCKS).  UG_NO_PRIO: all equal. */
 	int prio_least = 0, prio_greatest = 0;
 	cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+	const bool prio = !getenv("UG_NO_PRIO");
+	ctx->light_build_sms = -1; /* strip mode: two thirds of the SMs (set once the device is known); UG_LIGHT_BLOCKS=0: all of them */
+	if (const char *e = getenv("UG_LIGHT_BLOCKS")) ctx->light_build_sms = atoi(e);
+	UG_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->own_stream, cudaStreamNonBlocking, prio ? prio_greatest : prio_least));
+	ctx->stream = ctx->own_stream;
 	for (int i = 0; i < UG_MAX_LIGHTS; i++) {
-		/* the shadow branch is on the frame's critical path; the reflection branch (default priority) fills in around it */
-		UG_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side[i], cudaStreamNonBlocking, getenv("UG_NO_PRIO") ? prio_least : prio_greatest));
+		UG_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side[i], cudaStreamNonBlocking, prio_least));
 		UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
+		UG_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_map[i], cudaStreamNonBlocking, prio ? prio_greatest : prio_least));
+		UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_map[i], cudaEventDisableTiming));
 	}
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_init, cudaEventDisableTiming));
-	UG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_init, cudaStreamNonBlocking));
-	UG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_refl, cudaStreamNonBlocking));
-	/* the uniform-grid build is a chain of short kernels that must be done when the primary rays are: high priority, or
-	 * its blocks queue behind the big kernels of the other branches (measured: 290 us instead of ~120) */
-	UG_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_ugrid, cudaStreamNonBlocking, getenv("UG_NO_PRIO") ? prio_least : prio_greatest));
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ugrid, cudaEventDisableTiming));
+	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_camgrid, cudaEventDisableTiming));
+	ctx->light_after_cam = getenv("UG_LIGHT_AFTER_CAM") != nullptr;
+	if (const char *e = getenv("UG_TRACE_ITEM")) ctx->trace_item_forced = atoi(e) == 64 ? 64 : 128; /* tests force both item sizes of k_trace */
+	UG_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_init, cudaStreamNonBlocking, prio ? prio_greatest : prio_least));
+	UG_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_refl, cudaStreamNonBlocking, prio ? prio_greatest : prio_least));
+	UG_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_ugrid, cudaStreamNonBlocking, prio_least));
 	UG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_comm, cudaStreamNonBlocking));
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_cam, cudaEventDisableTiming));
@@ -113,6 +124,8 @@ extern "C" int ug_create(ug_context **out, int device)
 	for (int i = 0; i < UG_FC_SLOTS; i++) UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ring[i], cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaMalloc((void **)&ctx->d_fc_seq, sizeof(u32)));
 	UG_CUDA(ctx, cudaMemset(ctx->d_fc_seq, 0, sizeof(u32)));
+	UG_CUDA(ctx, cudaMalloc((void **)&ctx->d_tstart, 16));
+	UG_CUDA(ctx, cudaMemset(ctx->d_tstart, 0, 16));
 	UG_CUDA(ctx, cudaMallocHost((void **)&ctx->h_counters, sizeof(u32) * UG_HC_WORDS));
 	memset(ctx->h_counters, 0, sizeof(u32) * UG_HC_WORDS);
 	UG_CUDA(ctx, cudaMalloc((void **)&ctx->d_fc, sizeof(FrameConst)));
@@ -170,14 +183,15 @@ extern "C" void ug_destroy(ug_context *ctx)
 	if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
 	for (int i = 0; i < UG_FC_SLOTS; i++) if (ctx->ev_ring[i]) cudaEventDestroy(ctx->ev_ring[i]);
 	dfree(ctx->d_fc_seq);
+	dfree(ctx->d_tstart);
 	if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
 	for (int i = 0; i < 2; i++) {
 		if (ctx->h_vstage[i]) cudaFreeHost(ctx->h_vstage[i]);
 		if (ctx->ev_vstage[i]) cudaEventDestroy(ctx->ev_vstage[i]);
 	}
 	dfree(ctx->d_fc);
-	for (int i = 0; i < UG_MAX_LIGHTS; i++) { cudaStreamDestroy(ctx->side[i]); cudaEventDestroy(ctx->ev_join[i]); }
-	cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_fork2); cudaEventDestroy(ctx->ev_init); cudaStreamDestroy(ctx->side_init); cudaStreamDestroy(ctx->side_refl); cudaStreamDestroy(ctx->side_ugrid); cudaEventDestroy(ctx->ev_ugrid); cudaStreamDestroy(ctx->side_comm); cudaEventDestroy(ctx->ev_ready); cudaEventDestroy(ctx->ev_cam); cudaEventDestroy(ctx->ev_refl); cudaEventDestroy(ctx->ev_trace); cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
+	for (int i = 0; i < UG_MAX_LIGHTS; i++) { cudaStreamDestroy(ctx->side[i]); cudaEventDestroy(ctx->ev_join[i]); cudaStreamDestroy(ctx->side_map[i]); cudaEventDestroy(ctx->ev_map[i]); }
+	cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_fork2); cudaEventDestroy(ctx->ev_init); cudaStreamDestroy(ctx->side_init); cudaStreamDestroy(ctx->side_refl); cudaStreamDestroy(ctx->side_ugrid); cudaEventDestroy(ctx->ev_ugrid); cudaEventDestroy(ctx->ev_camgrid); cudaStreamDestroy(ctx->side_comm); cudaEventDestroy(ctx->ev_ready); cudaEventDestroy(ctx->ev_cam); cudaEventDestroy(ctx->ev_refl); cudaEventDestroy(ctx->ev_trace); cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
 	for (auto &ev : ctx->ev_stage) cudaEventDestroy(ev);
 	cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
@@ -621,7 +635,7 @@ static int upload_consts(ug_context *ctx)
 	int slot = 0;
 	int rc = stage_consts(ctx, &slot);
 	if (rc) return rc;
-	ugk_fetch_consts(ctx->stream, ctx->h_ring, ctx->d_fc, sizeof(FrameConst), ctx->d_fc_seq, UG_FC_SLOTS);
+	ugk_fetch_consts(ctx->stream, ctx->h_ring, ctx->d_fc, sizeof(FrameConst), ctx->d_fc_seq, UG_FC_SLOTS, ctx->d_tstart);
 	UG_CUDA(ctx, cudaGetLastError());
 	return consts_launched(ctx, slot);
 }
@@ -717,14 +731,19 @@ static bool gather_deferred(const ug_context *ctx, const ug_frame_params *p);
 static int gather_slot(const ug_context *ctx, const ug_frame_params *p);
 
 /* FrustumGrid::buildGrid, frustum_grid.h:210-366, on stream s */
-static void enqueue_grid(ug_context *ctx, cudaStream_t s, const ViewConst *vc, GridBuffers &g, Launches &L)
+static void enqueue_grid(ug_context *ctx, cudaStream_t s, const ViewConst *vc, GridBuffers &g, Launches &L, int part = 3)
 {
-	const int sms = ctx->num_sms;
+	/* A strip's light grid is as large as the whole frame's while its camera grid is small and alone on the critical path: the
+	 * light build gets the blocks of two thirds of the SMs, so that the camera grid's blocks meet less competition for issue
+	 * slots (config D, strip 5 of 8: camera grid done at 147 us instead of 178, frame 364 us instead of 402; with a third
+	 * of the SMs the light grid itself becomes the critical path).  UG_LIGHT_BLOCKS=<SMs>, 0 = all. */
+	const int lsms = ctx->light_build_sms < 0 ? (2 * ctx->num_sms + 2) / 3 : ctx->light_build_sms;
+	const int sms = (&g != &ctx->cam_grid && ctx->strip_count > 1 && lsms > 0) ? lsms : ctx->num_sms;
 	const bool want_fused = (&g == &ctx->cam_grid) ? ctx->fused_cam_now : ctx->fused_grid_now;
 	if (g.S > 1) { /* depth slabs: kernel chain only - the slab of a triangle needs the z range of ALL triangles before any pair is emitted */
 		ugk_slab_reset(s, vc, g);                                                                       L.n += 1;
 	} else if (ctx->use_sweep && g.sweep_desc) {
-		g.final_buf = ugk_grid_sweep(s, vc, ctx->d_facelist, ctx->d_vertexlist, g, sms, &L.n);
+		g.final_buf = ugk_grid_sweep(s, vc, ctx->d_facelist, ctx->d_vertexlist, g, sms, &L.n, part);
 		return;
 	} else if (ctx->use_fused && want_fused && g.key_bits <= 32) {
 		const int fb = ugk_grid_fused(s, vc, ctx->d_facelist, ctx->d_vertexlist, g, sms);
@@ -741,9 +760,15 @@ static void enqueue_grid(ug_context *ctx, cudaStream_t s, const ViewConst *vc, G
 }
 
 /* main.cu:148-203 for one light, after its ViewConst is resident: ray->cell map, light grid, regroup, shadow rays */
-static void enqueue_light_grid(ug_context *ctx, cudaStream_t s, int l, Launches &L)
+static void enqueue_light_grid(ug_context *ctx, cudaStream_t s, int l, Launches &L, int part = 3)
 {
-	enqueue_grid(ctx, s, &ctx->d_fc->light[l], ctx->light_grid[l], L);
+	enqueue_grid(ctx, s, &ctx->d_fc->light[l], ctx->light_grid[l], L, part);
+}
+/* a build that can be cut after its per-triangle launch */
+static bool light_grid_splits(const ug_context *ctx, int l)
+{
+	const GridBuffers &g = ctx->light_grid[l];
+	return ctx->light_after_cam && ctx->strip_count > 1 && g.S <= 1 && ctx->use_sweep && g.sweep_desc;
 }
 static void enqueue_light_zero(ug_context *ctx, cudaStream_t s, int l)
 { /* independent of the primary rays: issued early on the light's branch */
@@ -751,13 +776,13 @@ static void enqueue_light_zero(ug_context *ctx, cudaStream_t s, int l)
 	LightRays &r = ctx->rays[l];
 	cudaMemsetAsync(r.span, 0, sizeof(u32) * ((size_t)ctx->C_light + 1), s);
 }
-static void enqueue_light_regroup(ug_context *ctx, cudaStream_t s, int l, Launches &L)
+static void enqueue_light_regroup(ug_context *ctx, cudaStream_t s, int l, Launches &L, int phases = 7)
 {
 	if (ctx->direct_shadow) return; /* the rays are not regrouped: ray -> light cell is part of the shadow pass */
 	LightRays &r = ctx->rays[l];
-	if (!ugk_regroup(s, ctx->d_fc, l, ctx->light_grid[l], r, ctx->d_t, ctx->d_dir, ctx->N, ctx->C_light, ctx->num_sms, ctx->use_fused_regroup, &L.n)) {
+	if (!ugk_regroup(s, ctx->d_fc, l, ctx->light_grid[l], r, ctx->d_t, ctx->d_dir, ctx->N, ctx->C_light, ctx->num_sms, ctx->use_fused_regroup, &L.n, phases)) {
 		ctx->use_fused_regroup = false; /* cooperative launch refused: phase-by-phase launches from now on */
-		ugk_regroup(s, ctx->d_fc, l, ctx->light_grid[l], r, ctx->d_t, ctx->d_dir, ctx->N, ctx->C_light, ctx->num_sms, false, &L.n);
+		ugk_regroup(s, ctx->d_fc, l, ctx->light_grid[l], r, ctx->d_t, ctx->d_dir, ctx->N, ctx->C_light, ctx->num_sms, false, &L.n, phases);
 	}
 }
 static void enqueue_light_shadow(ug_context *ctx, cudaStream_t s, int l, Launches &L)
@@ -790,9 +815,10 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 	 * it is built by the one-launch kernel; a light grid only when nothing else (second light, uniform grid) runs beside it */
 	ctx->fused_cam_now = ctx->force_fused_grid || ctx->num_faces <= 150000;
 	ctx->fused_grid_now = ctx->force_fused_grid || (!reflect && nl <= 1 && ctx->num_faces <= 150000);
+	const bool split_map = parallel && !ctx->direct_shadow && !ctx->use_fused_regroup && !getenv("UG_NO_SPLIT_MAP");
 	int k = 0;
 	static_assert(sizeof(FrameConst) % 16 == 0, "FrameConst is fetched in 16-byte words");
-	ugk_fetch_consts(s, ctx->h_ring, ctx->d_fc, sizeof(FrameConst), ctx->d_fc_seq, UG_FC_SLOTS);
+	ugk_fetch_consts(s, ctx->h_ring, ctx->d_fc, sizeof(FrameConst), ctx->d_fc_seq, UG_FC_SLOTS, ctx->d_tstart);
 	L.n += 1;
 	unsigned long long *const tl = ctx->d_stamps;
 	ugk_stamp(s, tl, 0);
@@ -807,9 +833,12 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 		for (int l = 0; l < nl; l++) {
 			UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side[l], ctx->ev_fork, 0));
 			if (l == 0) ugk_stamp(ctx->side[l], tl, 10);
-			enqueue_light_zero(ctx, ctx->side[l], l);
-			enqueue_light_grid(ctx, ctx->side[l], l, L);
-			if (l == 0) ugk_stamp(ctx->side[l], tl, 11);
+			if (split_map) { /* the ray -> light cell map gets its own branch: it must not wait for the light grid */
+				UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_map[l], ctx->ev_fork, 0));
+				enqueue_light_zero(ctx, ctx->side_map[l], l);
+			} else enqueue_light_zero(ctx, ctx->side[l], l);
+			enqueue_light_grid(ctx, ctx->side[l], l, L, light_grid_splits(ctx, l) ? 1 : 3);
+			if (l == 0 && !light_grid_splits(ctx, l)) ugk_stamp(ctx->side[l], tl, 11);
 		}
 	}
 	const bool gather_strips = ctx->comm && ctx->comm_world > 1 && ctx->strip_count == ctx->comm_world && ctx->strip_index == ctx->comm_rank;
@@ -832,20 +861,34 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 	L.n += 1;
 	enqueue_grid(ctx, s, &ctx->d_fc->cam, ctx->cam_grid, L);
 	ugk_stamp(s, tl, 1);
+	if (parallel && nl > 0) { /* held-back sort passes of the light grids: beside the primary rays instead of beside the camera grid */
+		bool any = false;
+		for (int l = 0; l < nl; l++) any = any || light_grid_splits(ctx, l);
+		if (any) {
+			UG_CUDA(ctx, cudaEventRecord(ctx->ev_camgrid, s));
+			for (int l = 0; l < nl; l++) {
+				if (!light_grid_splits(ctx, l)) continue;
+				UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side[l], ctx->ev_camgrid, 0));
+				enqueue_light_grid(ctx, ctx->side[l], l, L, 2);
+				if (l == 0) ugk_stamp(ctx->side[l], tl, 11);
+			}
+		}
+	}
 	if (parallel && (gather_strips || gather_frames) && ctx->use_push) {
 		/* the gather's "ready" handshake hides behind the rest of the frame.  It starts only now: an NCCL kernel spins on an SM
 		 * until the slowest rank arrives, and while it does the cooperative camera-grid build (all blocks co-resident or none)
 		 * cannot start - issued at the head of the frame it put every rank's skew on the critical path */
 		UG_CUDA(ctx, cudaEventRecord(ctx->ev_cam, s));
 		UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_comm, ctx->ev_cam, 0));
-		int rc = ugc_ready(ctx, ctx->side_comm);
+		int rc = ugc_ready(ctx, ctx->side_comm, gather_deferred(ctx, p));
 		if (rc) return rc;
+		ugk_stamp(ctx->side_comm, tl, 6);
 		UG_CUDA(ctx, cudaEventRecord(ctx->ev_ready, ctx->side_comm));
 	}
 	if (parallel) UG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_init, 0));
 	stage_mark(ctx, k, stage_events); /* 2: camera grid done */
 	if (ctx->cam_grid.S > 1) ugk_trace_slabs(s, ctx->d_fc, ctx->cam_grid, ctx->d_dir, ctx->d_t, ctx->d_id, full ? ctx->d_normal : nullptr, ctx->C_cam, sms);
-	else ugk_trace(s, ctx->d_fc, ctx->cam_grid, ctx->d_best, ctx->d_cell_done, ctx->d_dir, ctx->d_t, ctx->d_id, full ? ctx->d_normal : nullptr, sms);
+	else ugk_trace(s, ctx->d_fc, ctx->cam_grid, ctx->d_best, ctx->d_cell_done, ctx->d_dir, ctx->d_t, ctx->d_id, full ? ctx->d_normal : nullptr, sms, ctx->trace_small);
 	L.n += 1;
 	ugk_stamp(s, tl, 2);
 	stage_mark(ctx, k, stage_events); /* 3: primary rays done */
@@ -862,9 +905,18 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 	}
 	if (parallel && nl > 0) {
 		for (int l = 0; l < nl; l++) {
-			UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side[l], ctx->ev_trace, 0));
-			if (l == 0) ugk_stamp(ctx->side[l], tl, 12);
-			enqueue_light_regroup(ctx, ctx->side[l], l, L);
+			if (split_map) {
+				UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_map[l], ctx->ev_trace, 0));
+				if (l == 0) ugk_stamp(ctx->side_map[l], tl, 12);
+				enqueue_light_regroup(ctx, ctx->side_map[l], l, L, 1);
+				UG_CUDA(ctx, cudaEventRecord(ctx->ev_map[l], ctx->side_map[l]));
+				UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side[l], ctx->ev_map[l], 0));
+				enqueue_light_regroup(ctx, ctx->side[l], l, L, 6);
+			} else {
+				UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side[l], ctx->ev_trace, 0));
+				if (l == 0) ugk_stamp(ctx->side[l], tl, 12);
+				enqueue_light_regroup(ctx, ctx->side[l], l, L);
+			}
 			if (l == 0) ugk_stamp(ctx->side[l], tl, 13);
 			enqueue_light_shadow(ctx, ctx->side[l], l, L);
 			if (l == 0) ugk_stamp(ctx->side[l], tl, 14);
@@ -930,7 +982,7 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 	}
 	if ((gather_strips || gather_frames) && ctx->use_push && !fused_gather) {
 		if (parallel) UG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_ready, 0));
-		else { int rc = ugc_ready(ctx, s); if (rc) return rc; }
+		else { int rc = ugc_ready(ctx, s, gather_deferred(ctx, p)); if (rc) return rc; }
 	}
 	ctx->overflow_in_frame = false;
 	if (gather_strips || gather_frames) {
@@ -948,12 +1000,13 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 		}
 		int rc = ugc_gather_strips(ctx, s, ctx->d_rgb, slot_off, g_bytes, g_offs, deferred, fused_gather);
 		if (rc) return rc;
+		ugk_stamp(s, tl, 5);
 		if (!(fused_gather && deferred)) L.n += 1;
 	}
 	/* pair counts + overflow flags of every grid ride back with the frame (no extra synchronisation later) */
 	{
-		const u32 *src[UG_MAX_LIGHTS + 4];
-		int words[UG_MAX_LIGHTS + 4], off[UG_MAX_LIGHTS + 4], n = 0;
+		const u32 *src[UG_MAX_LIGHTS + 5];
+		int words[UG_MAX_LIGHTS + 5], off[UG_MAX_LIGHTS + 5], n = 0;
 		src[n] = ctx->cam_grid.counters; words[n] = 4; off[n++] = 0;
 		for (int l = 0; l < nl; l++) { src[n] = ctx->light_grid[l].counters; words[n] = 4; off[n++] = 4 * (1 + l); }
 		if (reflect) {
@@ -961,6 +1014,8 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 			src[n] = ctx->refl.ray_counts; words[n] = UG_MAX_BOUNCES + 1; off[n++] = 4 * (2 + UG_MAX_LIGHTS);
 		}
 		if (ctx->overflow_in_frame) { src[n] = ugc_overflow_word(ctx); words[n] = 1; off[n++] = UG_HC_WORDS - 1; }
+		ctx->own_in_frame = (gather_strips || gather_frames) && ugc_own_word(ctx) && !deferred;
+		if (ctx->own_in_frame) { src[n] = ugc_own_word(ctx); words[n] = 1; off[n++] = UG_HC_OWN; }
 		ugk_publish(s, src, words, off, n, ctx->h_counters);
 		L.n += 1;
 	}
@@ -1042,7 +1097,7 @@ static unsigned long long frame_key(const ug_context *ctx, const ug_frame_params
 	mix((unsigned long long)(p->transform && ctx->d_vertex_orig_list ? 1 : 0)); mix((unsigned long long)ctx->cam_grid.cap);
 	for (int l = 0; l < p->num_lights; l++) mix((unsigned long long)ctx->light_grid[l].cap);
 	mix((unsigned long long)(p->bounces > 0 && ctx->d_reflect ? p->bounces : 0)); mix((unsigned long long)ctx->refl.grid.cap);
-	mix((unsigned long long)ctx->num_slabs); mix((unsigned long long)gather_slot(ctx, p));
+	mix((unsigned long long)ctx->num_slabs); mix((unsigned long long)gather_slot(ctx, p)); mix((unsigned long long)ctx->trace_small);
 	mix((unsigned long long)(uintptr_t)ctx->comm); mix((unsigned long long)(uintptr_t)ctx->d_rgb_full);
 	mix((unsigned long long)(uintptr_t)ctx->peer_full); mix((unsigned long long)ctx->use_push);
 	mix((unsigned long long)(uintptr_t)ctx->stream); mix((unsigned long long)(uintptr_t)ctx->d_rgb);
@@ -1057,6 +1112,15 @@ static int run_frame_once(ug_context *ctx, const ug_frame_params *p)
 	int fc_slot = 0;
 	int rc0 = stage_consts(ctx, &fc_slot);
 	if (rc0) return rc0;
+	if (ctx->trace_item_forced) ctx->trace_small = ctx->trace_item_forced == 64;
+	else if (ctx->frame_valid && ctx->h_counters[0]) {
+		/* primary rays: work items of 64 pairs instead of 128 when the camera grid is so small that the items would not fill
+		 * the GPU twice (ugk_trace); decided from the pair count the last finished frame published - a heuristic, both
+		 * kernels are exact - with some hysteresis so that the frame graph is not re-captured back and forth */
+		const double waves = (double)((ctx->h_counters[0] + 127u) / 128u) / ((double)ctx->num_sms * 16.0);
+		if (waves < 1.8) ctx->trace_small = true;
+		else if (waves > 2.2) ctx->trace_small = false;
+	}
 	if (use_graph) {
 		const unsigned long long key = frame_key(ctx, p);
 		if (!ctx->graph_exec[gs] || ctx->graph_key[gs] != key) {
@@ -1068,14 +1132,16 @@ static int run_frame_once(ug_context *ctx, const ug_frame_params *p)
 			cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
 			if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
 			if (e != cudaSuccess) return ug_fail(ctx, UG_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
-			e = cudaGraphInstantiate(&ctx->graph_exec[gs], graph, 0);
+			e = cudaGraphInstantiate(&ctx->graph_exec[gs], graph, cudaGraphInstantiateFlagUseNodePriority);
 			cudaGraphDestroy(graph);
 			if (e != cudaSuccess) return ug_fail(ctx, UG_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
 			ctx->graph_key[gs] = key;
 			ctx->graph_launches[gs] = L.n;
 			ctx->graph_overflow[gs] = ctx->overflow_in_frame;
+			ctx->graph_own[gs] = ctx->own_in_frame;
 		}
 		ctx->overflow_in_frame = ctx->graph_overflow[gs]; /* a property of the captured frame, not of the last capture */
+		ctx->own_in_frame = ctx->graph_own[gs];
 		UG_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
 		UG_CUDA(ctx, cudaGraphLaunch(ctx->graph_exec[gs], ctx->stream));
 		UG_CUDA(ctx, cudaEventRecord(ctx->ev_t1, ctx->stream));
@@ -1228,7 +1294,7 @@ extern "C" int ug_trace(ug_context *ctx)
 	if (rc) return rc;
 	ugk_init_pixels(ctx->stream, ctx->d_fc, ctx->d_t, ctx->d_id, ctx->d_shadowed, ctx->d_best, ctx->d_normal, ctx->d_dir, ctx->N, ctx->num_sms);
 	if (ctx->cam_grid.S > 1) ugk_trace_slabs(ctx->stream, ctx->d_fc, ctx->cam_grid, ctx->d_dir, ctx->d_t, ctx->d_id, ctx->d_normal, ctx->C_cam, ctx->num_sms);
-	else ugk_trace(ctx->stream, ctx->d_fc, ctx->cam_grid, ctx->d_best, ctx->d_cell_done, ctx->d_dir, ctx->d_t, ctx->d_id, ctx->d_normal, ctx->num_sms);
+	else ugk_trace(ctx->stream, ctx->d_fc, ctx->cam_grid, ctx->d_best, ctx->d_cell_done, ctx->d_dir, ctx->d_t, ctx->d_id, ctx->d_normal, ctx->num_sms, ctx->trace_small);
 	UG_CUDA(ctx, cudaGetLastError());
 	return UG_OK;
 }
@@ -1414,6 +1480,7 @@ extern "C" int ug_get_stats(ug_context *ctx, ug_stats *out)
 		float ms = 0;
 		if (cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1) == cudaSuccess) s.ms_frame = ms;
 		else cudaGetLastError();
+		s.ms_own = ctx->own_in_frame ? (float)ctx->h_counters[UG_HC_OWN] * 1e-6f : s.ms_frame;
 	}
 	*out = s;
 	if (s.overflowed && ctx->frame_valid) {

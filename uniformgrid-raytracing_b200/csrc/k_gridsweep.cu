@@ -381,8 +381,10 @@ size_t ugk_sweep_desc(size_t cap, int bins) { return ((cap + SW_TILE - 1) / SW_T
 size_t ugk_sweep_hist_words() { return (size_t)4 * SW_HSTRIDE; }
 size_t ugk_sweep_tiles(size_t cap) { return (cap + SW_TILE - 1) / SW_TILE + 2; }
 
-/* pass 0 writes buffer pair 0 from nothing, pass 1 sorts 0 -> 1: the ordered list ends in pair 1 */
-int ugk_grid_sweep(cudaStream_t s, const ViewConst *vc, const int *faces, const float *verts, GridBuffers &g, int sms, int *launches)
+/* pass 0 writes buffer pair 0 from nothing, pass 1 sorts 0 -> 1: the ordered list ends in pair 1.
+ * part: 1 = the per-triangle launch only, 2 = the two sort passes only, 3 = the whole build.  (A strip's light grid is not
+ * needed before its shadow rays: its sort passes can be held back until the camera grid is done.) */
+int ugk_grid_sweep(cudaStream_t s, const ViewConst *vc, const int *faces, const float *verts, GridBuffers &g, int sms, int *launches, int part)
 {
 	SweepArgs a;
 	a.vc = vc; a.faces = faces; a.verts = verts;
@@ -394,11 +396,16 @@ int ugk_grid_sweep(cudaStream_t s, const ViewConst *vc, const int *faces, const 
 	a.tile_first = g.sweep_tile_first;
 	const unsigned tiles_a = (unsigned)((g.T + SW_THREADS - 1) / SW_THREADS);
 	const unsigned max_blocks = (unsigned)sms * 2u;
-	k_sweep_setup<<<tiles_a < max_blocks ? (tiles_a ? tiles_a : 1u) : max_blocks, SW_THREADS, 0, s>>>(a);
-	const size_t tiles_p = (g.cap + SW_TILE - 1) / SW_TILE;
-	const size_t noff = ((size_t)g.C + 1 + SW_CELL_TILE - 1) / SW_CELL_TILE;
-	k_sweep_pass<0><<<(unsigned)(tiles_p < max_blocks ? (tiles_p ? tiles_p : 1) : max_blocks), SW_THREADS, 0, s>>>(a);
-	k_sweep_pass<1><<<(unsigned)(tiles_p + noff < max_blocks ? tiles_p + noff : max_blocks), SW_THREADS, 0, s>>>(a);
-	if (launches) *launches += 3;
+	if (part & 1) {
+		k_sweep_setup<<<tiles_a < max_blocks ? (tiles_a ? tiles_a : 1u) : max_blocks, SW_THREADS, 0, s>>>(a);
+		if (launches) *launches += 1;
+	}
+	if (part & 2) {
+		const size_t tiles_p = (g.cap + SW_TILE - 1) / SW_TILE;
+		const size_t noff = ((size_t)g.C + 1 + SW_CELL_TILE - 1) / SW_CELL_TILE;
+		k_sweep_pass<0><<<(unsigned)(tiles_p < max_blocks ? (tiles_p ? tiles_p : 1) : max_blocks), SW_THREADS, 0, s>>>(a);
+		k_sweep_pass<1><<<(unsigned)(tiles_p + noff < max_blocks ? tiles_p + noff : max_blocks), SW_THREADS, 0, s>>>(a);
+		if (launches) *launches += 2;
+	}
 	return 1;
 }

@@ -128,8 +128,8 @@ void ugk_stamp(cudaStream_t s, unsigned long long *slots, int slot) { if (slots)
  * writes them straight into the context's pinned (device-visible) block, instead of one copy-engine node per grid at the
  * tail of the frame graph (~5 us each in series). */
 struct PublishArgs {
-	const u32 *src[UG_MAX_LIGHTS + 4];
-	int words[UG_MAX_LIGHTS + 4], dst_off[UG_MAX_LIGHTS + 4];
+	const u32 *src[UG_MAX_LIGHTS + 5];
+	int words[UG_MAX_LIGHTS + 5], dst_off[UG_MAX_LIGHTS + 5];
 	int n;
 };
 __global__ void k_publish(const PublishArgs a, u32 *__restrict__ host_block)
@@ -164,16 +164,93 @@ void ugk_publish(cudaStream_t s, const u32 *const *src, const int *words, const 
  * of slot (seq % slots) over PCIe, stores them in device memory and advances the device-side sequence counter.  A kernel
  * node starts sooner than a copy-engine node at the head of the frame graph, and because the slot is chosen on the device
  * the captured graph is launched unchanged while the host fills the next slot (no host synchronisation per frame). */
-__global__ void k_fetch_consts(const uint4 *__restrict__ host_ring, uint4 *__restrict__ dev_block, int n16, u32 *seq, int slots)
+static __device__ __forceinline__ unsigned long long ug_globaltimer()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+__global__ void k_fetch_consts(const uint4 *__restrict__ host_ring, uint4 *__restrict__ dev_block, int n16, u32 *seq, int slots, unsigned long long *t_start)
 {
 	__shared__ u32 s_seq;
-	if (threadIdx.x == 0) s_seq = *seq;
+	if (threadIdx.x == 0) { s_seq = *seq; *t_start = ug_globaltimer(); /* the frame's first kernel: where ug_stats.ms_own starts */ }
 	__syncthreads();
 	const uint4 *src = host_ring + (size_t)(s_seq % (u32)slots) * (size_t)n16;
 	for (int i = threadIdx.x; i < n16; i += blockDim.x) dev_block[i] = src[i];
 	if (threadIdx.x == 0) *seq = s_seq + 1u;
 }
-void ugk_fetch_consts(cudaStream_t s, const void *host_ring, void *dev_block, size_t bytes, u32 *seq, int slots)
+void ugk_fetch_consts(cudaStream_t s, const void *host_ring, void *dev_block, size_t bytes, u32 *seq, int slots, unsigned long long *t_start)
 {
-	k_fetch_consts<<<1, 512, 0, s>>>((const uint4 *)host_ring, (uint4 *)dev_block, (int)(bytes / 16), seq, slots);
+	k_fetch_consts<<<1, 512, 0, s>>>((const uint4 *)host_ring, (uint4 *)dev_block, (int)(bytes / 16), seq, slots, t_start);
+}
+
+/* ---- the gather's handshakes as flags in rank 0's IPC-mapped buffer (the page behind the image slots) --------------------
+ * Every rank counts its gathered frames in a device word of its own (seq); all ranks render the same sequence of gathered
+ * frames, so the counts agree without being exchanged.
+ *   ready   rank 0: "my stream is past the read-out of the frame these stores will overwrite" = flags->ready := seq (release).
+ *           others: spin on rank 0's word over NVLink until it says seq (acquire) - issued on a side branch after the camera
+ *           grid, needed only in front of the first remote store.
+ *   done    others, after their last remote store: system fence, flags->done[rank] := seq | overflow << 31, then spin on
+ *           flags->result.  rank 0: one lane per rank spins on done[] (local memory, written by the peers), ORs the overflow
+ *           bits and publishes flags->result := seq | any << 31 - when that kernel retires the image is whole.
+ * Two stores and one round trip over NVLink per frame replace two 8-rank ncclAllReduce launches (~25 us each on the frame's
+ * tail, plus an SM per NCCL kernel while it waits for the slowest rank). */
+struct CommFlags { u32 ready, result, pad[14]; u32 done[UG_MAX_RANKS]; };
+static_assert(sizeof(CommFlags) <= 4096, "the flags live in one page behind rank 0's gather buffer");
+static __device__ __forceinline__ u32 ld_acquire_sys(const u32 *p)
+{
+	u32 v;
+	asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+static __device__ __forceinline__ void st_release_sys(u32 *p, u32 v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+static __device__ __forceinline__ bool seq_reached(u32 word, u32 seq) { return (int)((word & 0x7fffffffu) - seq) >= 0; }
+
+__global__ void k_comm_ready(CommFlags *flags, u32 *seq, int rank)
+{
+	const u32 s = (*seq + 1u) & 0x7fffffffu;
+	*seq = s;
+	if (rank == 0) { __threadfence_system(); st_release_sys(&flags->ready, s); }
+	else while (!seq_reached(ld_acquire_sys(&flags->ready), s)) __nanosleep(100);
+}
+__global__ void k_comm_done(CommFlags *flags, const u32 *seq, int rank, int world, u32 *over_word, const unsigned long long *t_start, u32 *own_ns)
+{
+	const u32 s = *seq, lane = threadIdx.x;
+	if (lane == 0 && own_ns) *own_ns = (u32)(ug_globaltimer() - *t_start); /* this rank's own work ends here: what follows is waiting for the others */
+	u32 over = over_word ? *over_word : 0u; /* in: this rank's pair arenas overflowed; out: anybody's did */
+	if (rank != 0) {
+		if (lane == 0) {
+			__threadfence_system(); /* this rank's remote pixel stores (earlier kernels of the stream) before its flag */
+			st_release_sys(&flags->done[rank], s | (over ? 0x80000000u : 0u));
+			u32 w;
+			while (!seq_reached(w = ld_acquire_sys(&flags->result), s)) __nanosleep(100);
+			if (over_word) *over_word = w >> 31;
+		}
+		return;
+	}
+	if ((int)lane > 0 && (int)lane < world) {
+		u32 w;
+		while (!seq_reached(w = ld_acquire_sys(&flags->done[lane]), s)) __nanosleep(20);
+		over |= w >> 31;
+	}
+	for (int o = 16; o > 0; o >>= 1) over |= __shfl_xor_sync(0xffffffffu, over, o);
+	if (world > 32) { /* lanes beyond the warp's width: the first lane walks the rest */
+		if (lane == 0)
+			for (int r = 32; r < world; r++) {
+				u32 w;
+				while (!seq_reached(w = ld_acquire_sys(&flags->done[r]), s)) __nanosleep(20);
+				over |= w >> 31;
+			}
+		over = __shfl_sync(0xffffffffu, over, 0) | over;
+	}
+	if (lane == 0) {
+		if (over_word) *over_word = over ? 1u : 0u;
+		__threadfence_system();
+		st_release_sys(&flags->result, s | (over ? 0x80000000u : 0u));
+	}
+}
+void ugk_comm_ready(cudaStream_t s, void *flags, u32 *seq, int rank) { k_comm_ready<<<1, 1, 0, s>>>((CommFlags *)flags, seq, rank); }
+void ugk_comm_done(cudaStream_t s, void *flags, const u32 *seq, int rank, int world, u32 *over_word, const unsigned long long *t_start, u32 *own_ns)
+{
+	k_comm_done<<<1, 32, 0, s>>>((CommFlags *)flags, seq, rank, world, over_word, t_start, own_ns);
 }

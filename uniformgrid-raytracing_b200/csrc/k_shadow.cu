@@ -215,11 +215,24 @@ __global__ void __launch_bounds__(RG_THREADS, 2) k_regroup(const RegroupArgs a, 
 		}
 		const u32 total = a.item_off[C];
 		if (b == 0 && tid == 0) a.counters[0] = min(total, a.item_cap);
-		/* a warp per cell: a crowded cell (spherical light grids put tens of thousands of rays into one) has as many items as rays */
-		for (u32 c = (b * RG_THREADS + tid) >> 5; c < (u32)C; c += (G * RG_THREADS) >> 5) {
-			const u32 o = a.item_off[c], n = a.item_off[c + 1] - o;
-			for (u32 q = ug_lane(); q < n; q += 32)
-				if (o + q < a.item_cap) a.items[o + q] = make_uint2(c, q);
+		/* the item table: a thread per cell writes a short run itself (most cells hold a few items, or none - an image strip's
+		 * rays reach only part of the light grid); a crowded cell (spherical light grids put tens of thousands of rays into
+		 * one, and it has as many items as rays) is taken over by its whole warp */
+		for (u32 c0 = (b * RG_THREADS + tid) & ~31u; c0 < (u32)C; c0 += G * RG_THREADS) {
+			const u32 c = c0 + ug_lane();
+			u32 o = 0, n = 0;
+			if (c < (u32)C) { o = a.item_off[c]; n = a.item_off[c + 1] - o; }
+			if (n <= 8)
+				for (u32 q = 0; q < n; q++)
+					if (o + q < a.item_cap) a.items[o + q] = make_uint2(c, q);
+			u32 big = __ballot_sync(UG_FULL_MASK, n > 8);
+			while (big) {
+				const int L = __ffs(big) - 1;
+				big &= big - 1;
+				const u32 oc = __shfl_sync(UG_FULL_MASK, o, L), nc = __shfl_sync(UG_FULL_MASK, n, L);
+				for (u32 q = ug_lane(); q < nc; q += 32)
+					if (oc + q < a.item_cap) a.items[oc + q] = make_uint2(c0 + (u32)L, q);
+			}
 		}
 	}
 }
@@ -307,16 +320,18 @@ extern "C" void ug_shadow_item_shape(unsigned rays, unsigned ntri, unsigned out[
 }
 size_t ugk_regroup_state_entries(int C) { return ((size_t)C + 2 + RG_THREADS * 4 - 1) / (RG_THREADS * 4) + 2; }
 
-/* getRayGridMapping + processData (per_frame_funcs.h:72-137) for one light; returns false if the launch failed */
+/* getRayGridMapping + processData (per_frame_funcs.h:72-137) for one light; returns false if the launch failed.
+ * phases: bit 0 = ray -> light cell + rays per cell (needs the primary hits only), bits 1, 2 = scans + scatter + item table
+ * (need the light grid's cell spans as well); 7 = everything */
 bool ugk_regroup(cudaStream_t s, const FrameConst *fc, int light, const GridBuffers &g, const LightRays &r, const float *t, const float *dir, int N, int C,
-                 int sms, bool fused, int *launches)
+                 int sms, bool fused, int *launches, int phases)
 {
 	RegroupArgs a;
 	a.fc = fc; a.light = light; a.N = N; a.C = C; a.t = t; a.dir = dir; a.grid_span = g.cell_span();
 	a.light_cell = r.cell; a.ray_span = r.span; a.ray_offset = r.offset; a.ray_rank = r.rank; a.ray_pix = r.pix;
 	a.item_off = r.item_off; a.items = r.items; a.counters = r.counters; a.state_a = r.state_a; a.state_b = r.state_b;
 	a.item_cap = (u32)r.item_cap;
-	if (fused) {
+	if (fused && phases == 7) {
 		int phase = -1;
 		void *args[] = {(void *)&a, (void *)&phase};
 		if (cudaLaunchCooperativeKernel((const void *)k_regroup, dim3((unsigned)sms * 2), dim3(RG_THREADS), args, 0, s) == cudaSuccess) {
@@ -327,8 +342,11 @@ bool ugk_regroup(cudaStream_t s, const FrameConst *fc, int light, const GridBuff
 		return false;
 	}
 	const unsigned blocks = (unsigned)sms * 2;
-	for (int phase = 0; phase < 3; phase++) k_regroup<<<blocks, RG_THREADS, 0, s>>>(a, phase);
-	if (launches) *launches += 3;
+	for (int phase = 0; phase < 3; phase++)
+		if (phases & (1 << phase)) {
+			k_regroup<<<blocks, RG_THREADS, 0, s>>>(a, phase);
+			if (launches) *launches += 1;
+		}
 	return true;
 }
 

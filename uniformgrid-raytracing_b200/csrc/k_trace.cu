@@ -47,7 +47,9 @@ static __device__ __forceinline__ void tr_bulk_g2s(u32 dst_smem, const void *src
 	             : "memory");
 }
 
+#ifndef TR_ITEM
 #define TR_ITEM 128   /* pairs per work item */
+#endif
 #define TR_BATCH 64   /* triangles staged per round = threads per packet */
 
 __global__ void __launch_bounds__(256) k_init_pixels(const FrameConst *__restrict__ fc, float *__restrict__ t, int *__restrict__ id,
@@ -117,6 +119,7 @@ static __device__ __forceinline__ void write_hit(float best, u32 tri, int pix, c
 #ifndef TR_MINB
 #define TR_MINB 16 /* 64 registers: no spills (the compiler's own choice was 48 with spills); measured -5 us on config B */
 #endif
+template <int ITEM>
 __global__ void __launch_bounds__(64, TR_MINB) k_trace(const FrameConst *__restrict__ fc, const u32 *__restrict__ counters, const u32 *__restrict__ keys,
                                               const u32 *__restrict__ vals, const u32 *__restrict__ span, const u32 *__restrict__ offset,
                                               const float4 *__restrict__ rec, u64 *__restrict__ best_buf, u32 *__restrict__ cell_done,
@@ -129,9 +132,9 @@ __global__ void __launch_bounds__(64, TR_MINB) k_trace(const FrameConst *__restr
 #else
 	__shared__ float4 s_rec[TR_BATCH * 4];
 #endif
-	__shared__ u32 s_key[TR_ITEM + 2]; /* keys[lo-1 .. hi], so both ends can tell whole cells from partial ones */
-	__shared__ u32 s_val[TR_ITEM];
-	__shared__ u32 s_head[TR_ITEM / 32]; /* bit p = pair lo+p starts a run (its key differs from the previous pair's) */
+	__shared__ u32 s_key[ITEM + 2]; /* keys[lo-1 .. hi], so both ends can tell whole cells from partial ones */
+	__shared__ u32 s_val[ITEM];
+	__shared__ u32 s_head[ITEM / 32]; /* bit p = pair lo+p starts a run (its key differs from the previous pair's) */
 	__shared__ float s_cc[64];
 	__shared__ u32 s_ticket;
 	const ViewConst &vc = fc->cam;
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(64, TR_MINB) k_trace(const FrameConst *__restr
 	const int gy_cnt = vc.gy_cnt, W = vc.W;
 	const u32 rec_base0 = (u32)__cvta_generic_to_shared(s_rec);
 	const u32 P = counters[0];
-	const u32 nitems = (P + TR_ITEM - 1) / TR_ITEM;
+	const u32 nitems = (P + ITEM - 1) / ITEM;
 #ifndef TR_NO_TMA
 	const u32 bar0 = (u32)__cvta_generic_to_shared(&s_bar[0]);
 	if (tid == 0) { tr_mbar_init(bar0, 1); tr_mbar_init(bar0 + 8u, 1); }
@@ -149,7 +152,7 @@ __global__ void __launch_bounds__(64, TR_MINB) k_trace(const FrameConst *__restr
 #endif
 	__syncthreads();
 	for (u32 item = blockIdx.x; item < nitems; item += gridDim.x) {
-		const u32 lo = item * TR_ITEM, hi = min(lo + TR_ITEM, P);
+		const u32 lo = item * ITEM, hi = min(lo + ITEM, P);
 		__syncthreads(); /* previous item's shared data is dead */
 		for (u32 i = tid; i < hi - lo + 2; i += 64) {
 			const u32 g = lo + i; /* s_key[i] = keys[lo - 1 + i] */
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(64, TR_MINB) k_trace(const FrameConst *__restr
 		for (u32 i = tid; i < hi - lo; i += 64) s_val[i] = vals[lo + i];
 		__syncthreads();
 #pragma unroll
-		for (u32 w = 0; w < TR_ITEM / 64; w++) { /* run heads, 32 pairs per ballot */
+		for (u32 w = 0; w < ITEM / 64; w++) { /* run heads, 32 pairs per ballot */
 			const u32 p = w * 64 + tid;
 			const bool head = (p < hi - lo) && (p == 0 || s_key[p + 1] != s_key[p]);
 			const u32 bits = __ballot_sync(UG_FULL_MASK, head);
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(64, TR_MINB) k_trace(const FrameConst *__restr
 					} else {
 						if (hit != 0xffffffffu) atomicMin((unsigned long long *)&best_buf[pix], ((u64)__float_as_uint(best) << 32) | (u64)hit);
 						const u32 c_lo = offset[cell], c_hi = c_lo + span[cell];
-						const u32 parts = (c_hi - 1) / TR_ITEM - c_lo / TR_ITEM + 1;
+						const u32 parts = (c_hi - 1) / ITEM - c_lo / ITEM + 1;
 						__threadfence();
 						__syncthreads();
 						if (tid == 0) s_ticket = atomicAdd(&cell_done[cell], 1u);
@@ -253,11 +256,11 @@ __global__ void __launch_bounds__(64, TR_MINB) k_trace(const FrameConst *__restr
 				{
 					const u32 q = p - lo + 1;
 					u32 w = q >> 5;
-					if (w < TR_ITEM / 32) {
+					if (w < ITEM / 32) {
 						u32 bits = s_head[w] & (0xffffffffu << (q & 31));
 						while (true) {
 							if (bits) { e = min(whi, lo + (w << 5) + (u32)__ffs(bits) - 1); break; }
-							if (++w >= TR_ITEM / 32) break;
+							if (++w >= ITEM / 32) break;
 							bits = s_head[w];
 						}
 					}
@@ -361,9 +364,17 @@ void ugk_init_pixels(cudaStream_t s, const FrameConst *fc, float *t, int *id, in
 }
 
 void ugk_trace(cudaStream_t s, const FrameConst *fc, const GridBuffers &g, u64 *best, u32 *cell_done, const float *dir, float *t, int *id, float *normal,
-               int sms)
+               int sms, bool small_items)
 {
-	const size_t want = (g.cap + TR_ITEM - 1) / TR_ITEM;
+	/* Items of 128 pairs; 64 when the grid holds so few pairs that the items would not fill the GPU twice (16 blocks are
+	 * resident per SM): the idle SMs of the last wave cost more than the per-item overhead (config B, 352 K pairs: 74.6 ->
+	 * 70.3 us; config D, 3.4 M pairs: 547 -> 574 us, so large grids keep 128).  The caller decides from the pair count of
+	 * the last finished frame. */
+	const size_t item = small_items ? TR_ITEM / 2 : TR_ITEM;
+	const size_t want = (g.cap + item - 1) / item;
 	const unsigned blocks = (unsigned)(want < (size_t)sms * 32 ? (want ? want : 1) : (size_t)sms * 32);
-	k_trace<<<blocks, 64, 0, s>>>(fc, g.counters, g.keys[g.final_buf], g.vals[g.final_buf], g.span, g.offset, g.tri_rec, best, cell_done, dir, t, id, normal);
+	if (small_items)
+		k_trace<TR_ITEM / 2><<<blocks, 64, 0, s>>>(fc, g.counters, g.keys[g.final_buf], g.vals[g.final_buf], g.span, g.offset, g.tri_rec, best, cell_done, dir, t, id, normal);
+	else
+		k_trace<TR_ITEM><<<blocks, 64, 0, s>>>(fc, g.counters, g.keys[g.final_buf], g.vals[g.final_buf], g.span, g.offset, g.tri_rec, best, cell_done, dir, t, id, normal);
 }

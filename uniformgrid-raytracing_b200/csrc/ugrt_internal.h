@@ -120,7 +120,9 @@ struct ug_context {
 	cudaStream_t side[UG_MAX_LIGHTS] = {};
 	cudaStream_t side_init = nullptr, side_refl = nullptr, side_ugrid = nullptr, side_comm = nullptr;
 	cudaEvent_t ev_ready = nullptr, ev_cam = nullptr;
-	cudaEvent_t ev_ugrid = nullptr;
+	cudaEvent_t ev_ugrid = nullptr, ev_camgrid = nullptr;
+	cudaStream_t side_map[UG_MAX_LIGHTS] = {}; /* ray -> light cell map of every light: needs the primary hits, not the light grid */
+	cudaEvent_t ev_map[UG_MAX_LIGHTS] = {};
 	unsigned long long *d_stamps = nullptr; /* [64] UG_TIMELINE markers, null when off */
 	bool use_fused_ugrid = false, force_fused_grid = false, fused_grid_now = true, fused_cam_now = true;
 	float refl_cells_per_tri = 2.0f; /* row R uniform-grid resolution (env UG_REFL_CELLS_PER_TRI overrides) */
@@ -132,7 +134,10 @@ struct ug_context {
 	int num_sms = 148;
 	bool use_fused_regroup = true;
 	bool use_fused = true;      /* fused cooperative grid build when the device supports it (UG_NO_FUSED=1 disables) */
+	bool own_in_frame = false;  /* the last enqueued frame published the ns of this rank's own work (h_counters[UG_HC_OWN]) */
 	bool overflow_in_frame = false; /* the last enqueued frame's "done" handshake carried the overflow flags (h_counters[UG_HC_WORDS-1]) */
+	bool light_after_cam = false; /* UG_LIGHT_AFTER_CAM=1: strip mode holds a light grid's sort passes back until the camera grid is done */
+	int light_build_sms = 0;    /* UG_LIGHT_BLOCKS: SMs' worth of blocks for a light-grid build in strip mode (0: all) */
 	bool direct_shadow = false; /* UG_SHADOW_DIRECT=1: shadow rays in screen order, no regroup (k_shadowdirect.cu); default is the regrouped path (k_shadow.cu) */
 	bool use_sweep = true;      /* three-launch one-sweep grid build (k_gridsweep.cu) where eligible (UG_NO_SWEEP=1 disables) */
 
@@ -161,6 +166,7 @@ struct ug_context {
 	FrameConst *h_ring = nullptr;              /* pinned [UG_FC_SLOTS] */
 	cudaEvent_t ev_ring[UG_FC_SLOTS] = {};     /* recorded after the launch that reads the slot */
 	bool ring_used[UG_FC_SLOTS] = {};
+	unsigned long long *d_tstart = nullptr;    /* %globaltimer of the last frame's first kernel */
 	u32 *d_fc_seq = nullptr;                   /* device mirror of fc_seq (advanced by k_fetch_consts) */
 	unsigned long long fc_seq = 0;
 	FrameConst *d_fc = nullptr;
@@ -207,6 +213,7 @@ struct ug_context {
 	unsigned char *peer_full = nullptr;  /* ranks > 0: rank 0's gather buffer mapped through CUDA IPC */
 	void *d_comm_scratch = nullptr;      /* 256 B: IPC handle, flags, barrier words */
 	bool use_push = false;
+	bool flag_handshake = true;          /* push transport, frames that are complete when the call's graph is: ready / done as flags in rank 0's buffer (UG_NCCL_HANDSHAKE=1: two ncclAllReduce) */
 	bool fused_gather = true;            /* push transport: the shader (and the reflection combine) store into rank 0's frame themselves;
 	                                        UG_NO_FUSED_GATHER=1 keeps the copy-engine node instead */
 	unsigned char *rgb_remote = nullptr; /* where this frame's pixels go on rank 0 (its own buffer or the IPC-mapped one), null without a fused gather */
@@ -215,7 +222,10 @@ struct ug_context {
 	cudaGraphExec_t graph_exec[2] = {nullptr, nullptr}; /* [1]: the odd frames of a deferred gather (they write the other slot) */
 	unsigned long long graph_key[2] = {0, 0};
 	int graph_launches[2] = {0, 0};
-	bool graph_overflow[2] = {false, false}; /* that graph's "done" handshake carries the overflow flags */
+	bool graph_overflow[2] = {false, false};
+	bool graph_own[2] = {false, false};
+	int trace_item_forced = 0;  /* UG_TRACE_ITEM=64|128 */
+	bool trace_small = false; /* primary rays in work items of 64 pairs (small camera grids), see run_frame_once */ /* that graph's "done" handshake carries the overflow flags */
 	unsigned long long gather_seq = 0; /* frames gathered with UG_FLAG_GATHER_DEFERRED so far: frame k lands in slot k & 1 */
 
 	ug_stats stats = {};
@@ -234,11 +244,15 @@ void ug_strip_rows(const ug_context *ctx, int r, int *lo, int *hi);
 
 /* ---------------------------------------------------------------- kernel launchers (k_*.cu) */
 /* K1 transform */
-void ugk_fetch_consts(cudaStream_t s, const void *host_ring, void *dev_block, size_t bytes, u32 *seq, int slots);
+void ugk_fetch_consts(cudaStream_t s, const void *host_ring, void *dev_block, size_t bytes, u32 *seq, int slots, unsigned long long *t_start);
 void ugk_publish(cudaStream_t s, const u32 *const *src, const int *words, const int *dst_off, int n, u32 *host_block);
 void ugk_overflow_any(cudaStream_t s, const u32 *const *src, int n, u32 *out);
-#define UG_HC_WORDS (4 * (2 + UG_MAX_LIGHTS) + UG_MAX_BOUNCES + 1 + 1) /* h_counters: grids, reflection ray counts, [last] = ranks that overflowed */
+#define UG_HC_WORDS (4 * (2 + UG_MAX_LIGHTS) + UG_MAX_BOUNCES + 1 + 2) /* h_counters: grids, reflection ray counts, [last - 1] = ns of this rank's own work, [last] = ranks that overflowed */
+#define UG_HC_OWN (UG_HC_WORDS - 2)
 void ugk_stamp(cudaStream_t s, unsigned long long *slots, int slot);
+void ugk_comm_ready(cudaStream_t s, void *flags, u32 *seq, int rank);
+void ugk_comm_done(cudaStream_t s, void *flags, const u32 *seq, int rank, int world, u32 *over_word, const unsigned long long *t_start, u32 *own_ns);
+#define UG_COMM_FLAGS_BYTES 4096 /* page of handshake flags behind rank 0's gather buffer */
 void ugk_transform(cudaStream_t s, float *vertexlist, const float *orig, int size, int offset, const FrameConst *fc, int sms);
 /* K2 setup+bin, scan, emit */
 void ugk_setup_bin(cudaStream_t s, const ViewConst *vc, const int *faces, const float *verts, int T, GridBuffers &g, int sms);
@@ -259,7 +273,7 @@ size_t ugk_sweep_desc_b(int C);
 size_t ugk_sweep_desc(size_t cap, int bins);
 size_t ugk_sweep_hist_words();
 size_t ugk_sweep_tiles(size_t cap);
-int ugk_grid_sweep(cudaStream_t s, const ViewConst *vc, const int *faces, const float *verts, GridBuffers &g, int sms, int *launches);
+int ugk_grid_sweep(cudaStream_t s, const ViewConst *vc, const int *faces, const float *verts, GridBuffers &g, int sms, int *launches, int part = 3);
 /* radix sort / scan primitives (k_sort.cu) */
 size_t ugk_scan_tiles(size_t n);
 /* stable LSD radix sort of (key,val) pairs on `bits` key bits; n read from *n_dev (<= n_max).
@@ -271,13 +285,13 @@ void ugk_exclusive_scan(cudaStream_t s, const u32 *in, u32 *out, size_t n, u64 *
 /* K6 primary */
 void ugk_init_pixels(cudaStream_t s, const FrameConst *fc, float *t, int *id, int *shadowed, u64 *best, float *normal, float *dir, int N, int sms);
 void ugk_trace(cudaStream_t s, const FrameConst *fc, const GridBuffers &g, u64 *best, u32 *cell_done, const float *dir, float *t, int *id, float *normal,
-               int sms);
+               int sms, bool small_items);
 /* K7/K8 shadow (k_shadow.cu) */
 bool ugk_regroup_fused_supported(int device);
 size_t ugk_regroup_state_entries(int C);
 size_t ugk_shadow_item_cap(int N, int C);
 bool ugk_regroup(cudaStream_t s, const FrameConst *fc, int light, const GridBuffers &g, const LightRays &r, const float *t, const float *dir, int N, int C,
-                 int sms, bool fused, int *launches);
+                 int sms, bool fused, int *launches, int phases = 7);
 size_t ugk_shadow_heavy_cap(int N);
 void ugk_shadow_direct(cudaStream_t s, const FrameConst *fc, int light, const GridBuffers &g, const LightRays &r, const float *t, const float *dir, int *shadowed,
                        int N, int C, int sms, int *launches);
@@ -300,12 +314,13 @@ void ugk_reflect_combine(cudaStream_t s, ug_context *ctx, int *launches);
 /* comm.cpp */
 void ugc_destroy(ug_context *ctx);
 int ugc_share_full(ug_context *ctx, size_t bytes);
-int ugc_ready(ug_context *ctx, cudaStream_t s);
+int ugc_ready(ug_context *ctx, cudaStream_t s, bool deferred);
 int ugc_gather_strips(ug_context *ctx, cudaStream_t s, const unsigned char *strip, size_t slot_offset, const size_t *bytes, const size_t *offs, bool deferred,
                       bool already_stored);
 int ugc_flush(ug_context *ctx, cudaStream_t s);
 int ugc_allreduce_max(ug_context *ctx, cudaStream_t s, unsigned *value); /* host value in/out; synchronises s */
-u32 *ugc_overflow_word(ug_context *ctx);   /* device word the "done" handshake sums over the ranks (push transport), or null */
+u32 *ugc_overflow_word(ug_context *ctx);
+u32 *ugc_own_word(ug_context *ctx);   /* device word the "done" handshake sums over the ranks (push transport), or null */
 
 /* host helpers (camera_host.cpp, obj_loader.cpp) */
 void ugh_view_const(ViewConst *vc, const ug_camera *cam, int W, int H, int nbx, int nby, int gy_lo, int gy_cnt, int grid_mode = UG_LIGHT_GRID_PERSPECTIVE,
