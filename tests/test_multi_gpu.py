@@ -32,6 +32,10 @@ def _worker(rank, world, port, out_path, transport):
         os.environ["UG_NO_PUSH"] = "1"          # the ncclSend/ncclRecv fallback instead of the IPC push over NVLink
     if transport == "copy":
         os.environ["UG_NO_FUSED_GATHER"] = "1"  # push by a copy-engine node after the frame instead of P2P stores from the shader
+    if transport == "fused-noshard":
+        os.environ["UG_NO_SHARD_LIGHTS"] = "1"  # every rank builds the light grid in full (the default shards it over the ranks)
+    if transport == "fused-nccl-handshake":
+        os.environ["UG_NCCL_HANDSHAKE"] = "1"   # ready / done as two ncclAllReduce instead of flags in rank 0's mapped buffer
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", rank=rank, world_size=world)   # only carries the 128-byte NCCL id
     scene = scenes.scene_a(256, 264)                                # 33 cell rows: uneven strips
@@ -78,10 +82,12 @@ def _worker(rank, world, port, out_path, transport):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("transport", ["fused", "copy", "nccl"])
+@pytest.mark.parametrize("transport", ["fused", "copy", "nccl", "fused-noshard", "fused-nccl-handshake"])
 def test_strip_gather_over_nccl(oracle, tmp_path, transport):
-    """fused: the shading kernels store into rank 0's IPC-mapped frame over NVLink themselves; copy: one peer memcpy node
-    after the frame; nccl: grouped ncclSend/ncclRecv.  Strips, whole frames, and whole frames with deferred completion."""
+    """fused: the shading kernels store into rank 0's IPC-mapped frame over NVLink themselves, handshakes are flags in that
+    buffer and every rank builds only its share of the light grid's cell rows, stored into every rank's copy (k_lightshare.cu);
+    copy: one peer memcpy node after the frame; nccl: grouped ncclSend/ncclRecv; fused-noshard: light grids built in full by
+    every rank; fused-nccl-handshake: two ncclAllReduce per frame.  Strips, whole frames, whole frames with deferred completion."""
     no_push = transport == "nccl"
     import torch
     import torch.multiprocessing as mp
@@ -107,7 +113,7 @@ def test_strip_gather_over_nccl(oracle, tmp_path, transport):
             assert np.array_equal(frames[k], want_k), f"deferred gather: step {step}, rank {k}"
 
 
-def _overflow_scene():
+def _overflow_scene(nlights=0):
     """192 huge triangles below eye level at 1024x1024: the bottom strip's pair count exceeds its initial arena, the top strip's
     does not - only one rank wants to run the frame again."""
     T = 192
@@ -115,12 +121,12 @@ def _overflow_scene():
     for k in range(T):
         y = 20.0 + 0.25 * k
         V[k] = [[-60, y, -60], [60, y, -60], [0, y, 0.5]]
-    s = scenes.scene_random(1, 10, 1024, 1024, nlights=0)     # no light: a light grid is built in full by every rank and would overflow on both
+    s = scenes.scene_random(1, 10, 1024, 1024, nlights=nlights)   # no light: a light grid would overflow on both ranks
     s.verts, s.faces, s.face_mat = V.reshape(-1, 3), np.arange(3 * T, dtype=np.int32).reshape(-1, 3), np.zeros(T, np.int32)
     return s
 
 
-def _worker_overflow(rank, world, port, out_path):
+def _worker_overflow(rank, world, port, out_path, nlights=0):
     import torch
     import torch.distributed as dist
     import ugrt  # noqa: F401
@@ -128,7 +134,7 @@ def _worker_overflow(rank, world, port, out_path):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    scene = _overflow_scene()
+    scene = _overflow_scene(nlights)
     r = ug.Renderer(rank)
     r.set_scene(scene)
     uid = [ug.unique_id() if rank == 0 else None]
@@ -160,4 +166,19 @@ def test_one_rank_overflow_is_a_collective_decision(oracle, tmp_path):
     mp.spawn(_worker_overflow, args=(2, _free_port(), out), nprocs=2, join=True)
     over = np.load(out + ".over.npy")
     assert over.tolist().count(1) == 1, f"exactly one strip was meant to overflow, got {over.tolist()}"
+    assert np.array_equal(np.load(out), want)
+
+
+def test_sharded_light_grid_overflow_falls_back(oracle, tmp_path):
+    """With a light, the two ranks build the light grid in row shards (k_lightshare.cu) and a shard of this scene does not fit
+    its slot of the shared value list: the frame's collective overflow flag ends the sharding on every rank, the frame is
+    rendered again with the light grid built in full (whose arena then has to grow as well) - and still equals the oracle."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    scene = _overflow_scene(1)
+    want = harness.run_frame(oracle, scene, threads=0)["rgb"]
+    out = str(tmp_path / "full.npy")
+    mp.spawn(_worker_overflow, args=(2, _free_port(), out, 1), nprocs=2, join=True)
     assert np.array_equal(np.load(out), want)

@@ -174,4 +174,6 @@ void ugh_view_const(ViewConst *vc, const ug_camera *cam, int W, int H, int nbx, 
 	vc->near_plane = cam->nearPlane;
 	vc->nbx = nbx; vc->nby = nby; vc->gy_lo = gy_lo; vc->gy_cnt = gy_cnt;
 	vc->W = W; vc->H = H;
+	vc->shards = 1;
+	vc->pad_[0] = vc->pad_[1] = vc->pad_[2] = 0;
 }

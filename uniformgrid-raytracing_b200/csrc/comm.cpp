@@ -17,6 +17,7 @@
 #include <dlfcn.h>
 #include <stdlib.h>
 #include <string.h>
+#include <vector>
 
 typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
@@ -93,13 +94,18 @@ extern "C" int ug_comm_init(ug_context *ctx, int rank, int world, const void *un
 	unmap_peer(ctx);
 	ctx->use_push = false;
 	ctx->flag_handshake = getenv("UG_NCCL_HANDSHAKE") == nullptr;
+	ugc_unshare_light(ctx);
 	ctx->rgb_full_bytes = 0; /* the gather buffer is shared again (collectively) by the next frame */
 	ug_drop_graphs(ctx);
 	return UG_OK;
 }
 
+void ugc_unshare_light(ug_context *ctx);
 void ugc_destroy(ug_context *ctx)
 {
+	ugc_unshare_light(ctx);
+	if (ctx->d_lg_handles) cudaFree(ctx->d_lg_handles);
+	ctx->d_lg_handles = nullptr;
 	unmap_peer(ctx);
 	if (ctx->d_comm_scratch) cudaFree(ctx->d_comm_scratch);
 	ctx->d_comm_scratch = nullptr;
@@ -243,5 +249,72 @@ int ugc_gather_strips(ug_context *ctx, cudaStream_t s, const unsigned char *stri
 		UG_NCCL(ctx, N.Send(strip, bytes[rank], ncclUint8, 0, comm, s));
 	}
 	UG_NCCL(ctx, N.GroupEnd());
+	return UG_OK;
+}
+
+/* ---- light grids built once per communicator instead of once per rank (strip mode) -------------------------------------
+ * Every rank builds the cell rows [nby*q/world, nby*(q+1)/world) of each light grid and stores its lists into the same
+ * place of EVERY rank's copy (P2P stores over NVLink, k_lightshare.cu).  For that every rank exports one buffer (flags page,
+ * then per light: span[C], offset[C], vals[world * slot]) and maps the buffers of all the others.  Collective. */
+static void unmap_light_peers(ug_context *ctx)
+{
+	for (int r = 0; r < UG_MAX_RANKS; r++) {
+		if (ctx->lg_peer[r] && r != ctx->comm_rank) cudaIpcCloseMemHandle(ctx->lg_peer[r]);
+		ctx->lg_peer[r] = nullptr;
+	}
+}
+void ugc_unshare_light(ug_context *ctx)
+{
+	unmap_light_peers(ctx);
+	if (ctx->lg_local) cudaFree(ctx->lg_local);
+	ctx->lg_local = nullptr;
+	ctx->lg_bytes = 0;
+	ctx->lg_ok = false;
+}
+int ugc_share_light(ug_context *ctx, size_t bytes)
+{
+	ncclComm_t comm = (ncclComm_t)ctx->comm;
+	cudaStream_t s = ctx->stream;
+	const int rank = ctx->comm_rank, world = ctx->comm_world;
+	/* nobody keeps an old buffer mapped when its owner frees it */
+	UG_CUDA(ctx, cudaStreamSynchronize(s));
+	unmap_light_peers(ctx);
+	unsigned char *scr = (unsigned char *)ctx->d_comm_scratch;
+	UG_NCCL(ctx, N.AllReduce(scr + 128, scr + 128, 1, ncclUint32, ncclSum, comm, s));
+	UG_CUDA(ctx, cudaStreamSynchronize(s));
+	if (ctx->lg_local) cudaFree(ctx->lg_local);
+	ctx->lg_local = nullptr;
+	unsigned int ok = 1;
+	cudaIpcMemHandle_t mine;
+	memset(&mine, 0, sizeof(mine));
+	if (cudaMalloc((void **)&ctx->lg_local, bytes) != cudaSuccess) { ok = 0; cudaGetLastError(); ctx->lg_local = nullptr; }
+	else {
+		UG_CUDA(ctx, cudaMemsetAsync(ctx->lg_local, 0, UG_COMM_FLAGS_BYTES, s)); /* arrival flags: sequence numbers start at 0 */
+		if (getenv("UG_NO_PUSH") || cudaIpcGetMemHandle(&mine, ctx->lg_local) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+	}
+	if (!ctx->d_lg_handles) UG_CUDA(ctx, cudaMalloc((void **)&ctx->d_lg_handles, 64 * (size_t)(UG_MAX_RANKS + 1)));
+	unsigned char *hd = (unsigned char *)ctx->d_lg_handles;
+	UG_CUDA(ctx, cudaMemcpyAsync(hd + 64 * (size_t)UG_MAX_RANKS, &mine, 64, cudaMemcpyHostToDevice, s));
+	UG_NCCL(ctx, N.AllGather(hd + 64 * (size_t)UG_MAX_RANKS, hd, 64, ncclUint8, comm, s));
+	std::vector<cudaIpcMemHandle_t> all((size_t)world);
+	UG_CUDA(ctx, cudaMemcpyAsync(all.data(), hd, 64 * (size_t)world, cudaMemcpyDeviceToHost, s));
+	UG_CUDA(ctx, cudaStreamSynchronize(s));
+	for (int r = 0; r < world && ok; r++) {
+		if (r == rank) { ctx->lg_peer[r] = ctx->lg_local; continue; }
+		void *p = nullptr;
+		if (cudaIpcOpenMemHandle(&p, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); p = nullptr; }
+		ctx->lg_peer[r] = (unsigned char *)p;
+	}
+	UG_CUDA(ctx, cudaMemcpyAsync(scr + 64, &ok, 4, cudaMemcpyHostToDevice, s));
+	UG_NCCL(ctx, N.AllReduce(scr + 64, scr + 64, 1, ncclUint32, ncclMin, comm, s));
+	UG_CUDA(ctx, cudaMemcpyAsync(&ok, scr + 64, 4, cudaMemcpyDeviceToHost, s));
+	UG_CUDA(ctx, cudaStreamSynchronize(s));
+	ctx->lg_ok = ok != 0;
+	ctx->lg_bytes = bytes; /* also when it failed: the attempt is not repeated for the same layout */
+	if (!ctx->lg_ok) {
+		unmap_light_peers(ctx);
+		if (ctx->lg_local) cudaFree(ctx->lg_local);
+		ctx->lg_local = nullptr;
+	}
 	return UG_OK;
 }

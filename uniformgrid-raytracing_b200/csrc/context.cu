@@ -184,6 +184,7 @@ extern "C" void ug_destroy(ug_context *ctx)
 	for (int i = 0; i < UG_FC_SLOTS; i++) if (ctx->ev_ring[i]) cudaEventDestroy(ctx->ev_ring[i]);
 	dfree(ctx->d_fc_seq);
 	dfree(ctx->d_tstart);
+	dfree(ctx->d_lg_seq);
 	if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
 	for (int i = 0; i < 2; i++) {
 		if (ctx->h_vstage[i]) cudaFreeHost(ctx->h_vstage[i]);
@@ -384,6 +385,29 @@ static int alloc_reflect(ug_context *ctx, int T, int N, int bounces)
 
 static size_t default_cap(int T, int C) { return (size_t)16 * (size_t)T + (size_t)C + (1u << 20); }
 
+/* ---- light grids sharded over the ranks of a strip gather (k_lightshare.cu): layout of every rank's buffer, in 32-bit words:
+ * flags page | per light: span[C] | offset[C] | vals[world * slot] */
+static size_t lg_align(size_t words) { return (words + 63) & ~(size_t)63; }
+static size_t lg_words_per_light(const ug_context *ctx) { return 2 * lg_align((size_t)ctx->lg_cells + 1) + (size_t)ctx->comm_world * ctx->lg_slot; }
+void ug_light_layout(const ug_context *ctx, int l, size_t *span_w, size_t *offset_w, size_t *vals_w)
+{
+	const size_t Cw = lg_align((size_t)ctx->lg_cells + 1), base = UG_COMM_FLAGS_BYTES / 4 + (size_t)l * lg_words_per_light(ctx);
+	*span_w = base; *offset_w = base + Cw; *vals_w = base + 2 * Cw;
+}
+/* rows [lo, hi) of a light grid that rank q of the communicator builds */
+static void lg_rows(const ug_context *ctx, int q, int *lo, int *hi) { *lo = ctx->nby * q / ctx->comm_world; *hi = ctx->nby * (q + 1) / ctx->comm_world; }
+/* the same answer on every rank: it only depends on what all ranks share */
+static bool lg_eligible(const ug_context *ctx, int num_lights)
+{
+	if (!ctx->comm || ctx->comm_world <= 1 || ctx->lg_disabled || num_lights <= 0) return false;
+	if (ctx->strip_count != ctx->comm_world || ctx->strip_index != ctx->comm_rank) return false; /* frames that end in the strip gather */
+	if (!ctx->use_push || !ctx->flag_handshake) return false; /* needs the mapped buffers and the frame-end handshake every rank waits in */
+	if (!ctx->use_sweep || ctx->num_slabs != 1 || ctx->direct_shadow || ctx->use_fused_regroup || ctx->nby < ctx->comm_world) return false;
+	for (int l = 0; l < num_lights; l++)
+		if (!ctx->light_grid[l].sweep_desc) return false;
+	return true;
+}
+
 /* make every buffer the current (model, screen, strip, lights, flags) needs exist */
 static int ensure_buffers(ug_context *ctx, int num_lights, bool full, int bounces = 0)
 {
@@ -447,6 +471,20 @@ static int ensure_buffers(ug_context *ctx, int num_lights, bool full, int bounce
 		int rc = ugc_share_full(ctx, 2 * 3 * (size_t)ctx->W * ctx->H * (size_t)ctx->comm_world);
 		if (rc) return rc;
 		changed = true;
+	}
+	if (lg_eligible(ctx, num_lights)) {
+		/* collective as well: one rank's slot of a light's value list has the capacity every rank's arena starts with (a shard
+		 * holds about 1/world of the grid's pairs; a shard that does not fit ends the sharding, check_overflow) */
+		const size_t slot = lg_align(default_cap(T, ctx->C_light));
+		if (ctx->lg_slot != slot || ctx->lg_lights != num_lights || ctx->lg_cells != ctx->C_light || !ctx->lg_bytes) {
+			ctx->lg_slot = slot; ctx->lg_lights = num_lights; ctx->lg_cells = ctx->C_light;
+			const size_t bytes = UG_COMM_FLAGS_BYTES + 4 * (size_t)num_lights * lg_words_per_light(ctx);
+			if (!ctx->d_lg_seq) UG_CUDA(ctx, cudaMalloc((void **)&ctx->d_lg_seq, sizeof(u32) * 2 * UG_MAX_LIGHTS));
+			UG_CUDA(ctx, cudaMemset(ctx->d_lg_seq, 0, sizeof(u32) * 2 * UG_MAX_LIGHTS));
+			int rc = ugc_share_light(ctx, bytes);
+			if (rc) return rc;
+			changed = true;
+		}
 	}
 	if (full && !ctx->full_alloc) {
 		UG_CUDA(ctx, dmalloc(&ctx->d_normal, 3 * (size_t)ctx->N));
@@ -743,6 +781,25 @@ static void enqueue_grid(ug_context *ctx, cudaStream_t s, const ViewConst *vc, G
 	if (g.S > 1) { /* depth slabs: kernel chain only - the slab of a triangle needs the z range of ALL triangles before any pair is emitted */
 		ugk_slab_reset(s, vc, g);                                                                       L.n += 1;
 	} else if (ctx->use_sweep && g.sweep_desc) {
+		if (&g != &ctx->cam_grid && ctx->lg_now) { /* this rank's cell rows only, then into every rank's copy (k_lightshare.cu) */
+			const int l = (int)(&g - ctx->light_grid);
+			int lo, hi;
+			lg_rows(ctx, ctx->comm_rank, &lo, &hi);
+			size_t span_w, offset_w, vals_w;
+			ug_light_layout(ctx, l, &span_w, &offset_w, &vals_w);
+			GridBuffers gl = g;
+			gl.C = ctx->nbx * (hi - lo);
+			gl.vals[1] = (u32 *)ctx->lg_local + vals_w + (size_t)ctx->comm_rank * ctx->lg_slot; /* pass 1 sorts straight into this rank's slot */
+			gl.cap = g.cap < ctx->lg_slot ? g.cap : ctx->lg_slot;
+			gl.offset_bias = (u32)((size_t)ctx->comm_rank * ctx->lg_slot);
+			gl.final_buf = g.final_buf = ugk_grid_sweep(s, vc, ctx->d_facelist, ctx->d_vertexlist, gl, ctx->num_sms, &L.n, part);
+			if (part & 2) {
+				ugk_light_push(s, ctx, l, gl, ctx->nbx * lo, gl.C, ctx->num_sms);
+				ugk_light_wait(s, ctx, l);
+				L.n += 2;
+			}
+			return;
+		}
 		g.final_buf = ugk_grid_sweep(s, vc, ctx->d_facelist, ctx->d_vertexlist, g, sms, &L.n, part);
 		return;
 	} else if (ctx->use_fused && want_fused && g.key_bits <= 32) {
@@ -770,6 +827,18 @@ static bool light_grid_splits(const ug_context *ctx, int l)
 	const GridBuffers &g = ctx->light_grid[l];
 	return ctx->light_after_cam && ctx->strip_count > 1 && g.S <= 1 && ctx->use_sweep && g.sweep_desc;
 }
+/* the light grid as its consumers see it: with sharded light grids, this rank's copy of the lists all ranks built together */
+static GridBuffers light_view(const ug_context *ctx, int l)
+{
+	GridBuffers g = ctx->light_grid[l];
+	if (ctx->lg_now) {
+		size_t span_w, offset_w, vals_w;
+		ug_light_layout(ctx, l, &span_w, &offset_w, &vals_w);
+		u32 *base = (u32 *)ctx->lg_local;
+		g.span = base + span_w; g.offset = base + offset_w; g.vals[g.final_buf] = base + vals_w;
+	}
+	return g;
+}
 static void enqueue_light_zero(ug_context *ctx, cudaStream_t s, int l)
 { /* independent of the primary rays: issued early on the light's branch */
 	if (ctx->direct_shadow) return;
@@ -780,9 +849,10 @@ static void enqueue_light_regroup(ug_context *ctx, cudaStream_t s, int l, Launch
 {
 	if (ctx->direct_shadow) return; /* the rays are not regrouped: ray -> light cell is part of the shadow pass */
 	LightRays &r = ctx->rays[l];
-	if (!ugk_regroup(s, ctx->d_fc, l, ctx->light_grid[l], r, ctx->d_t, ctx->d_dir, ctx->N, ctx->C_light, ctx->num_sms, ctx->use_fused_regroup, &L.n, phases)) {
+	const GridBuffers lg = light_view(ctx, l);
+	if (!ugk_regroup(s, ctx->d_fc, l, lg, r, ctx->d_t, ctx->d_dir, ctx->N, ctx->C_light, ctx->num_sms, ctx->use_fused_regroup, &L.n, phases)) {
 		ctx->use_fused_regroup = false; /* cooperative launch refused: phase-by-phase launches from now on */
-		ugk_regroup(s, ctx->d_fc, l, ctx->light_grid[l], r, ctx->d_t, ctx->d_dir, ctx->N, ctx->C_light, ctx->num_sms, false, &L.n, phases);
+		ugk_regroup(s, ctx->d_fc, l, lg, r, ctx->d_t, ctx->d_dir, ctx->N, ctx->C_light, ctx->num_sms, false, &L.n, phases);
 	}
 }
 static void enqueue_light_shadow(ug_context *ctx, cudaStream_t s, int l, Launches &L)
@@ -791,7 +861,7 @@ static void enqueue_light_shadow(ug_context *ctx, cudaStream_t s, int l, Launche
 		ugk_shadow_direct(s, ctx->d_fc, l, ctx->light_grid[l], ctx->rays[l], ctx->d_t, ctx->d_dir, ctx->d_shadowed, ctx->N, ctx->C_light, ctx->num_sms, &L.n);
 		return;
 	}
-	ugk_shadow(s, ctx->d_fc, l, ctx->light_grid[l], ctx->rays[l], ctx->d_t, ctx->d_dir, ctx->d_shadowed, ctx->N, ctx->C_light, ctx->num_sms); L.n += 1;
+	ugk_shadow(s, ctx->d_fc, l, light_view(ctx, l), ctx->rays[l], ctx->d_t, ctx->d_dir, ctx->d_shadowed, ctx->N, ctx->C_light, ctx->num_sms); L.n += 1;
 }
 static void enqueue_light_rays(ug_context *ctx, cudaStream_t s, int l, Launches &L)
 {
@@ -1039,6 +1109,7 @@ static int prepare_frame(ug_context *ctx, const ug_frame_params *p)
 	rc = ensure_buffers(ctx, p->num_lights, (p->flags & UG_FLAG_FULL_BUFFERS) != 0, ctx->d_reflect ? p->bounces : 0);
 	if (rc) return rc;
 	FrameConst *fc = ctx->h_fc; /* the master copy: no frame in flight reads it (stage_consts copies it into a ring slot) */
+	ctx->lg_now = lg_eligible(ctx, p->num_lights) && ctx->lg_ok && !(p->flags & (UG_FLAG_SPHERICAL_LIGHTS | UG_FLAG_GATHER_DEFERRED)) && !getenv("UG_NO_SHARD_LIGHTS");
 	ug_camera cam;
 	memset(&cam, 0, sizeof(cam));
 	ug_camera_setCameraCenter(&cam, p->eye[0], p->eye[1], p->eye[2]);
@@ -1062,8 +1133,11 @@ static int prepare_frame(ug_context *ctx, const ug_frame_params *p)
 		lc.aspect = 1.0f;
 		ug_camera_adjustCameraAndPosition(&lc);
 		/* main.cu:186-187: x_max = y_max = M_PI, narrowed to the float parameters of the two calls that follow */
-		ugh_view_const(&fc->light[l], &lc, ctx->W, ctx->H, ctx->nbx, ctx->nby, 0, ctx->nby,
+		int row_lo = 0, row_hi = ctx->nby;
+		if (ctx->lg_now) lg_rows(ctx, ctx->comm_rank, &row_lo, &row_hi); /* this rank's share of the light grid (k_lightshare.cu) */
+		ugh_view_const(&fc->light[l], &lc, ctx->W, ctx->H, ctx->nbx, ctx->nby, row_lo, row_hi - row_lo,
 		               (p->flags & UG_FLAG_SPHERICAL_LIGHTS) ? UG_LIGHT_GRID_SPHERICAL : UG_LIGHT_GRID_PERSPECTIVE, (float)M_PI, (float)M_PI, ctx->num_slabs);
+		fc->light[l].shards = ctx->lg_now ? ctx->comm_world : 1;
 		for (int k = 0; k < 3; k++) fc->light_pos[3 * l + k] = p->lights[l].pos[k];
 		/* shading runs with the LAST light camera's modelview resident in dd_camcoords (main.cu:205-211) */
 		memcpy(fc->shade_mv, lc.modelview_matrix, sizeof(fc->shade_mv));
@@ -1097,7 +1171,7 @@ static unsigned long long frame_key(const ug_context *ctx, const ug_frame_params
 	mix((unsigned long long)(p->transform && ctx->d_vertex_orig_list ? 1 : 0)); mix((unsigned long long)ctx->cam_grid.cap);
 	for (int l = 0; l < p->num_lights; l++) mix((unsigned long long)ctx->light_grid[l].cap);
 	mix((unsigned long long)(p->bounces > 0 && ctx->d_reflect ? p->bounces : 0)); mix((unsigned long long)ctx->refl.grid.cap);
-	mix((unsigned long long)ctx->num_slabs); mix((unsigned long long)gather_slot(ctx, p)); mix((unsigned long long)ctx->trace_small);
+	mix((unsigned long long)ctx->num_slabs); mix((unsigned long long)gather_slot(ctx, p)); mix((unsigned long long)ctx->trace_small); mix((unsigned long long)ctx->lg_now); mix((unsigned long long)(uintptr_t)ctx->lg_local);
 	mix((unsigned long long)(uintptr_t)ctx->comm); mix((unsigned long long)(uintptr_t)ctx->d_rgb_full);
 	mix((unsigned long long)(uintptr_t)ctx->peer_full); mix((unsigned long long)ctx->use_push);
 	mix((unsigned long long)(uintptr_t)ctx->stream); mix((unsigned long long)(uintptr_t)ctx->d_rgb);
@@ -1179,6 +1253,13 @@ static int check_overflow(ug_context *ctx, int num_lights, bool *grew, bool refl
 			if (gs[i] == &ctx->refl.grid && (rc = alloc_reflect_records(ctx)) != UG_OK) return rc;
 			*grew = true;
 		}
+	}
+	if (ctx->lg_now && ctx->overflow_in_frame && ctx->h_counters[UG_HC_WORDS - 1]) {
+		/* somebody's arena overflowed in a frame with sharded light grids (the flag is the same on every rank): the slots of the
+		 * shared lists cannot grow, so from now on every rank builds its light grids in full again */
+		ctx->lg_disabled = true;
+		ctx->lg_now = false;
+		ug_drop_graphs(ctx);
 	}
 	if (*grew) ug_drop_graphs(ctx);
 	return UG_OK;
@@ -1303,6 +1384,7 @@ extern "C" int ug_shadow_pass(ug_context *ctx, int light_id, const ug_camera *li
 {
 	if (!ctx || !light_cam || light_id < 0 || light_id >= UG_MAX_LIGHTS) return ug_fail(ctx, UG_ERR_ARG, "shadow pass: bad arguments");
 	if (!ctx->d_t) return ug_fail(ctx, UG_ERR_ARG, "shadow pass: trace first");
+	ctx->lg_now = false; /* the call-by-call path builds every light grid in full */
 	if (ctx->num_lights <= light_id) ctx->num_lights = light_id + 1;
 	int rc = ensure_buffers(ctx, ctx->num_lights, ctx->full_alloc);
 	if (rc) return rc;

@@ -115,6 +115,7 @@ struct SweepArgs {
 	u32 *count, *scan;
 	u32 *keys[2], *vals[2];
 	u32 *span, *offset, *counters;
+	u32 offset_bias; /* added to every offset written (a light-grid shard's slot base) */
 	u32 *hist;    /* [2 parities][2 passes][SW_HSTRIDE] difference arrays of the digit histograms */
 	u32 *base;    /* [2 passes][UG_SWEEP_MAXB] where the first key of every digit goes */
 	u64 *desc_a;  /* look-back descriptors of the count scan  (tiles of SW_THREADS triangles) */
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_pass(const SweepArgs a)
 			__syncthreads();
 			run += (u32)s_pref;
 #pragma unroll
-			for (int k = 0; k < 8; k++) { if (b0 + k <= (u32)C) a.offset[b0 + k] = run; run += v[k]; }
+			for (int k = 0; k < 8; k++) { if (b0 + k <= (u32)C) a.offset[b0 + k] = run + a.offset_bias; run += v[k]; }
 			continue;
 		}
 		tile -= noff;
@@ -391,7 +392,7 @@ int ugk_grid_sweep(cudaStream_t s, const ViewConst *vc, const int *faces, const 
 	a.T = g.T; a.C = g.C; a.cap = (u32)g.cap;
 	a.rec = g.tri_rec; a.rect = g.rect; a.count = g.count; a.scan = g.scan;
 	a.keys[0] = g.keys[0]; a.keys[1] = g.keys[1]; a.vals[0] = g.vals[0]; a.vals[1] = g.vals[1];
-	a.span = g.span; a.offset = g.offset; a.counters = g.counters;
+	a.span = g.span; a.offset = g.offset; a.counters = g.counters; a.offset_bias = g.offset_bias;
 	a.hist = g.sweep_hist; a.base = g.sweep_base; a.desc_a = g.sweep_desc_a; a.desc_b = g.sweep_desc_b; a.desc = g.sweep_desc; a.ctl = g.sweep_ctl;
 	a.tile_first = g.sweep_tile_first;
 	const unsigned tiles_a = (unsigned)((g.T + SW_THREADS - 1) / SW_THREADS);

@@ -10,7 +10,7 @@ struct LightMap {
 	float lx, ly, lz, p0, p1, p2, num, half, r0, r1, r2, u0, u1, u2;
 	double den;
 	float inv_den;  /* (float)(1/den): only used to decide whether the double expression can be skipped */
-	int nbx, nby;
+	int nbx, nby, shards;
 };
 static __device__ __forceinline__ LightMap make_light_map(const ViewConst &lv)
 {
@@ -26,7 +26,7 @@ static __device__ __forceinline__ LightMap make_light_map(const ViewConst &lv)
 	m.inv_den = (float)(1.0 / m.den);
 	m.r0 = cc[16 + 0]; m.r1 = cc[16 + 4]; m.r2 = cc[16 + 8];
 	m.u0 = cc[16 + 1]; m.u1 = cc[16 + 5]; m.u2 = cc[16 + 9];
-	m.nbx = lv.nbx; m.nby = lv.nby;
+	m.nbx = lv.nbx; m.nby = lv.nby; m.shards = lv.shards;
 	return m;
 }
 /* floor(((double)a / den) * nb) as an int, the reference's double expression.  A float estimate of the same value is within
@@ -56,7 +56,12 @@ static __device__ __forceinline__ u32 light_cell_of(const LightMap &m, float ex,
 	const int blx = light_bin(right + m.half, m, m.nbx);
 	const int bly = light_bin(up + m.half, m, m.nby);
 	u32 cell = (u32)(m.nbx * m.nby);
-	if (blx >= 0 && blx <= m.nbx - 1 && bly >= 0 && bly <= m.nby - 1) cell = (u32)(blx * m.nby + bly);
+	if (blx >= 0 && blx <= m.nbx - 1 && bly >= 0 && bly <= m.nby - 1) {
+		if (m.shards > 1) { /* the grid was built in row shards (k_lightshare.cu): cells are numbered shard-major */
+			const int q = ((bly + 1) * m.shards - 1) / m.nby, b0 = m.nby * q / m.shards, b1 = m.nby * (q + 1) / m.shards;
+			cell = (u32)(m.nbx * b0 + blx * (b1 - b0) + (bly - b0));
+		} else cell = (u32)(blx * m.nby + bly);
+	}
 	return cell;
 }
 

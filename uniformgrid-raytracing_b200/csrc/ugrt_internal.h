@@ -27,6 +27,8 @@ struct ViewConst {
 	int grid_mode;      /* UG_LIGHT_GRID_*: how triangles and shadow rays are binned into this view's grid (the eye: always perspective) */
 	float xM, yM;       /* spherical mode: angular extents (main.cu:186-187 passes pi, pi) */
 	int num_slabs;      /* NUM_SLABS, main.cu.h:18 (1 in the committed build): depth slabs of the grid */
+	int shards;         /* a light grid built in row shards by the ranks of a strip gather (k_lightshare.cu): how many; else 1 */
+	int pad_[3];
 };
 
 struct FrameConst {
@@ -67,6 +69,7 @@ struct GridBuffers {       /* FrustumGrid, frustum_grid.h:15-68 */
 	size_t cap = 0;            /* pair capacity */
 	int final_buf = 0;         /* which of vals[] holds the sorted list */
 	int key_bits = 0;
+	u32 offset_bias = 0;       /* added to every cell offset the sweep build writes (a shard's slot base, k_lightshare.cu) */
 	int C = 0, T = 0;          /* C = cells * S: span/offset have one entry per (cell, slab), key = cell*S + slab (grid_kernel.cu:322) */
 	/* depth slabs (NUM_SLABS > 1) */
 	int S = 1, cells = 0;
@@ -212,6 +215,16 @@ struct ug_context {
 	size_t rgb_full_bytes = 0;
 	unsigned char *peer_full = nullptr;  /* ranks > 0: rank 0's gather buffer mapped through CUDA IPC */
 	void *d_comm_scratch = nullptr;      /* 256 B: IPC handle, flags, barrier words */
+	/* light grids sharded over the ranks of a strip gather (comm.cpp, k_lightshare.cu) */
+	unsigned char *lg_local = nullptr;          /* this rank's copy of every light grid's lists (exported through CUDA IPC) */
+	unsigned char *lg_peer[UG_MAX_RANKS] = {};  /* every rank's copy ([comm_rank] = lg_local) */
+	void *d_lg_handles = nullptr;
+	size_t lg_bytes = 0, lg_slot = 0;           /* bytes of the buffer; pair capacity of one rank's slot of a light's value list */
+	int lg_lights = 0, lg_cells = 0;
+	bool lg_ok = false;                         /* the buffers are mapped everywhere */
+	bool lg_disabled = false;                   /* UG_NO_SHARD_LIGHTS=1, or a sharded frame overflowed: every rank builds the light grids in full again */
+	bool lg_now = false;                        /* the frame being enqueued shards its light grids */
+	u32 *d_lg_seq = nullptr;                    /* [UG_MAX_LIGHTS][2]: builds pushed so far, blocks of the running push that are done */
 	bool use_push = false;
 	bool flag_handshake = true;          /* push transport, frames that are complete when the call's graph is: ready / done as flags in rank 0's buffer (UG_NCCL_HANDSHAKE=1: two ncclAllReduce) */
 	bool fused_gather = true;            /* push transport: the shader (and the reflection combine) store into rank 0's frame themselves;
@@ -320,7 +333,12 @@ int ugc_gather_strips(ug_context *ctx, cudaStream_t s, const unsigned char *stri
 int ugc_flush(ug_context *ctx, cudaStream_t s);
 int ugc_allreduce_max(ug_context *ctx, cudaStream_t s, unsigned *value); /* host value in/out; synchronises s */
 u32 *ugc_overflow_word(ug_context *ctx);
-u32 *ugc_own_word(ug_context *ctx);   /* device word the "done" handshake sums over the ranks (push transport), or null */
+u32 *ugc_own_word(ug_context *ctx);
+int ugc_share_light(ug_context *ctx, size_t bytes);
+void ug_light_layout(const ug_context *ctx, int l, size_t *span_w, size_t *offset_w, size_t *vals_w);
+void ugk_light_push(cudaStream_t s, ug_context *ctx, int l, const GridBuffers &built, int cell_base, int cells, int sms);
+void ugk_light_wait(cudaStream_t s, ug_context *ctx, int l);
+void ugc_unshare_light(ug_context *ctx);   /* device word the "done" handshake sums over the ranks (push transport), or null */
 
 /* host helpers (camera_host.cpp, obj_loader.cpp) */
 void ugh_view_const(ViewConst *vc, const ug_camera *cam, int W, int H, int nbx, int nby, int gy_lo, int gy_cnt, int grid_mode = UG_LIGHT_GRID_PERSPECTIVE,
