@@ -212,7 +212,7 @@ def run_ours(args):
     def strip_of(m):
         return (rank, world) if m == "strips" else (0, 1)
 
-    def join_comm():   # the library gathers the strips itself (P2P stores over NVLink + NCCL handshakes, inside the frame's CUDA graph)
+    def join_comm():   # the library gathers the strips itself (P2P stores over NVLink, handshakes as flags in rank 0's mapped buffer, inside the frame's CUDA graph; NCCL bootstraps the IPC handles)
         uid = [ug.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         r.comm_init(rank, world, uid[0])
@@ -427,7 +427,8 @@ def run_ours(args):
         fps2 = world if om == "frames" else 1
         other = {"mode": om, "ms_per_step": ms2, "steps": k2, "scaling": "weak" if om == "frames" else "strong", "frames_per_step": fps2,
                  "note": ("one whole frame per GPU per step, gathered to rank 0 with deferred completion" if om == "frames" else
-                          "one frame cut into %d image strips of cell rows" % world) + "; shading kernels store into rank 0's frame over NVLink (P2P), NCCL handshakes"}
+                          "one frame cut into %d image strips of cell rows" % world) + ("; shading kernels store into rank 0's frame over NVLink (P2P); ready = ncclAllReduce that doubles as done of the frame before" if om == "frames" else
+                             "; shading kernels store into rank 0's frame over NVLink (P2P), ready / done handshakes as flags in rank 0's mapped buffer, light grids built in row shards")}
 
     # ---- N > 1, strips: rank 0's gathered frame must be the frame one GPU renders alone; that render is also the 1-GPU time of this workload
     check, single = None, None
@@ -515,10 +516,11 @@ def run_ours(args):
         R1 = int(refl.item()) // max(frames_per_step, 1)      # reflection rays of one frame (all bounces)
         Pu, Cu = int(st2.reflect_pairs), int(2.0 * T)         # uniform grid: pairs, cells (cells_per_tri = 2)
         kern = {"trace": ("k_trace", 8 * Cc + 52 * P + 8 * N, 64 * P, "FP32-issue bound (ray-triangle tests), not HBM bound: see fp32_issue"),
-                "shade": ("k_shade", (8 + 4 * 1) * N + 3 * N, None, "HBM streaming"),
-                "reflect_rays": ("k_refl_trace", 44 * R1 + 48 * T + 16 * Pu + 16 * Cu, None,
-                                 "3-D DDA: latency / issue bound (dependent cell and record fetches, divergent rays), not HBM bound; the stage "
-                                 "also holds the ray-spawn kernel (~10 us)")}
+                "shade": ("k_shade", (8 + len(scene.lights) / 8.0) * N + 3 * N, None, "HBM streaming; SURVEY 8(d): (8 + L/8) N in + 3 N out"),
+                "reflect_rays": ("k_refl_trace", 8 * R1, None,
+                                 "SURVEY 8(d): compaction traffic 8 R_b; the 3-D DDA itself is latency / issue bound (dependent cell and record "
+                                 "fetches, divergent rays) - see `issue` (lanes active per warp instruction x issue-slot utilisation, from the "
+                                 "committed ncu capture); the stage also holds the ray-spawn kernel (~10 us)")}
         for l in range(len(scene.lights)):
             kern[f"light{l}_shadow"] = ("k_shadow", None, None, "")
 
@@ -538,6 +540,10 @@ def run_ours(args):
                    "peak_source": peak_kind, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": stage[stage_name], "note": note}
             if issue is not None:   # from the committed ncu capture of the same command (profiles/), not measured live
                 out["sm_issue_active_pct_ncu"] = issue
+                lanes = prof.get("lanes_active", {}).get(name)
+                if lanes is not None:
+                    out["issue"] = {"issue_active_pct": issue, "lanes_active_of_32": lanes, "useful_issue_frac": issue / 100.0 * lanes / 32.0,
+                                    "source": "profiles/ (ncu --set full of the same command), not measured in this run"}
             if tests:
                 issue_peak = 148 * 128 * sm_max * 1e6 / 1e12   # T lane-ops/s at the max SM clock
                 ach = tests * FP32_ISSUE_PER_TEST / t_s / 1e12
@@ -553,7 +559,7 @@ def run_ours(args):
         frame_bytes = 0
         for nm, Pg, Cg in [("cam", P, Cc)] + [(f"l{l}", st2.light_pairs[l], (scene.width // 8) * (scene.height // 8)) for l in range(len(scene.lights))]:
             frame_bytes += 48 * T + 4 * Pg + 8 * Cg
-        frame_bytes += 8 * Cc + 52 * P + 8 * N + len(scene.lights) * 16 * N + (8 + 4) * N + 3 * N
+        frame_bytes += 8 * Cc + 52 * P + 8 * N + len(scene.lights) * 16 * N + int((8 + len(scene.lights) / 8.0) * N) + 3 * N + 8 * R1
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
@@ -566,8 +572,8 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if mode == "strips" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(scene, world, bounces, mode), "rays_per_step": rays_frame, "frames_per_step": frames_per_step,
-                       "parallelism": {"single": "one GPU", "frames": f"{world} GPUs, one frame each per step, frames stored into rank 0's buffer over NVLink by the shading kernels (P2P, NCCL handshakes, deferred completion)",
-                                       "strips": f"{world} GPUs, one frame in {world} image strips of cell rows, stored into rank 0's frame over NVLink by the shading kernels (P2P, NCCL handshakes, inside the frame graph)"}[mode],
+                       "parallelism": {"single": "one GPU", "frames": f"{world} GPUs, one frame each per step, frames stored into rank 0's buffer over NVLink by the shading kernels (P2P; one ncclAllReduce per frame as ready + deferred done)",
+                                       "strips": f"{world} GPUs, one frame in {world} image strips of cell rows, stored into rank 0's frame over NVLink by the shading kernels (P2P; ready / done handshakes as flags in rank 0's IPC-mapped buffer; each light grid built in row shards by the ranks and stored into every rank's copy over NVLink; all inside the frame graph)"}[mode],
                        "rays": {"primary": scene.num_pixels * frames_per_step, "shadow": scene.num_pixels * len(scene.lights) * frames_per_step,
                                 "reflection": int(refl.item())},
                        "l2": "flushed between timed frames (256 MiB write)" if not args.no_flush else "not flushed",

@@ -226,6 +226,8 @@ int ug_read(ug_context *ctx, int buffer, int index, void *dst, size_t bytes);   
 int ug_device_ptr(ug_context *ctx, int buffer, int index, void **ptr, size_t *bytes);    /* no copy */
 int ug_timeline(ug_context *ctx, double *ns64); /* development aid, needs env UG_TIMELINE=1 at ug_create: marker times of the last frame */
 int ug_write_ppm_binary(ug_context *ctx, const char *filename); /* same image as binary P6, top row first */
+int ug_write_png(ug_context *ctx, const char *filename);        /* the same image as an 8-bit RGB PNG, top row first: replaces writePPM + `convert -flip` of
+                                                                    main.cu:255-259 (stored deflate blocks, no zlib dependency) */
 int ug_write_ppm(ug_context *ctx, const char *filename);                                 /* per_app_funcs.h:39-66, ASCII P3 */
 /* ms between the stage marks of the last UG_FLAG_STAGE_EVENTS frame, in order: transform, camera grid, primary rays,
  * then per light (light grid, ray->cell map + regroup, shadow rays), then shade; returns the number of intervals

@@ -1,4 +1,4 @@
-"""Image-strip sharding across ranks: the frame is cut into `world` strips of whole cell rows
+"""Test support for the N > 1 host logic (tests/test_strips_gloo.py, tests/test_abi.py): how a frame is cut into `world` strips of whole cell rows
 (a cell row = 8 pixel rows), the scene is replicated, every rank renders its strip and the RGB8 strips are
 gathered to rank 0.  Pixel id = py*W + px with row 0 at the bottom, so a strip is a contiguous byte range of the
 image and the gather is a concatenation.  Backend-agnostic (NCCL on GPUs, gloo in the CPU tests)."""

@@ -78,7 +78,7 @@ def test_frame_params_layout(ug):
 
 
 def test_strip_bounds_cover_the_frame(ug):
-    from uniformgrid_raytracing_b200 import strips
+    import strips_helpers as strips
     for h, world in [(1024, 1), (1024, 8), (1080, 4), (1080, 8), (64, 3), (4096, 8)]:
         nby = h // 8
         b = [strips.strip_bounds(nby, k, world) for k in range(world)]

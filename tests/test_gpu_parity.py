@@ -270,6 +270,34 @@ def test_binary_ppm(renderer, ug, tmp_path):
     assert np.array_equal(np.frombuffer(raw[len(head):], np.uint8).reshape(s.height, s.width, 3), rgb[::-1])   # top row first
 
 
+def test_png(renderer, ug, tmp_path):
+    """ug_write_png (what display() gets from writePPM + `convert -flip`): decoded here with zlib + the PNG chunk
+    layout by hand - signature, IHDR, one IDAT of stored deflate blocks, IEND, every CRC - and compared with the frame.  The
+    image is wider than one 65535-byte deflate block per few rows, so several blocks are written."""
+    import struct
+    import zlib
+    s = scenes.scene_random(23, 200, 320, 136, 1)
+    renderer.set_scene(s)
+    renderer.render(renderer.params(s))
+    rgb = renderer.read(ug.BUF_RGB).reshape(s.height, s.width, 3)
+    path = tmp_path / "o.png"
+    renderer.write_png(str(path))
+    raw = path.read_bytes()
+    assert raw[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, chunks = 8, []
+    while pos < len(raw):
+        n, typ = struct.unpack(">I4s", raw[pos:pos + 8])
+        data = raw[pos + 8:pos + 8 + n]
+        assert struct.unpack(">I", raw[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(typ + data) & 0xffffffff, typ
+        chunks.append((typ, data))
+        pos += 12 + n
+    assert [c[0] for c in chunks] == [b"IHDR", b"IDAT", b"IEND"]
+    assert struct.unpack(">IIBBBBB", chunks[0][1]) == (s.width, s.height, 8, 2, 0, 0, 0)
+    lines = np.frombuffer(zlib.decompress(chunks[1][1]), np.uint8).reshape(s.height, 1 + 3 * s.width)
+    assert np.all(lines[:, 0] == 0)                                                            # filter type 0 on every scanline
+    assert np.array_equal(lines[:, 1:].reshape(s.height, s.width, 3), rgb[::-1])               # top row first
+
+
 def test_pair_arena_overflow_regrows(ug, oracle):
     """P is data dependent: a scene whose pair count exceeds the initial arena must be re-run with a larger one."""
     # 24 huge triangles at 1024x1024: each covers most of the 16 384 cells -> P far above 16*T + C + 2^20

@@ -12,7 +12,8 @@ import torch.multiprocessing as mp
 
 import parity  # noqa: F401
 from oracle import harness
-from uniformgrid_raytracing_b200 import scenes, strips
+from uniformgrid_raytracing_b200 import scenes
+import strips_helpers as strips
 
 
 def _free_port():

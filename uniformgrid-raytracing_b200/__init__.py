@@ -100,7 +100,7 @@ def lib() -> C.CDLL:
             "ug_render_frame_host": (C.c_int, [vp, C.POINTER(FrameParams), C.c_void_p]),
             "ug_get_stats": (C.c_int, [vp, C.POINTER(Stats)]), "ug_read": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_size_t]),
             "ug_device_ptr": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]),
-            "ug_write_ppm": (C.c_int, [vp, C.c_char_p]), "ug_write_ppm_binary": (C.c_int, [vp, C.c_char_p]),
+            "ug_write_ppm": (C.c_int, [vp, C.c_char_p]), "ug_write_ppm_binary": (C.c_int, [vp, C.c_char_p]), "ug_write_png": (C.c_int, [vp, C.c_char_p]),
             "ug_model_tmp_model": (C.c_int, [vp, C.c_char_p, C.c_int]), "ug_model_update_vertices": (C.c_int, [vp, f, C.c_int]),
             "ug_model_bounds": (C.c_int, [vp, f]), "ug_obj_parse_vertices": (C.c_int, [C.c_char_p, i, f, C.c_int]), "ug_stage_times": (C.c_int, [vp, f, C.c_int]),
             "ug_camera_adjustCameraAndPosition": (None, [C.POINTER(Camera)]), "ug_camera_pack": (None, [C.POINTER(Camera), f]),
@@ -318,6 +318,9 @@ class Renderer:
 
     def write_ppm_binary(self, path: str):
         self._ck(self.L.ug_write_ppm_binary(self.ctx, path.encode()), "ug_write_ppm_binary")
+
+    def write_png(self, path: str):
+        self._ck(self.L.ug_write_png(self.ctx, path.encode()), "ug_write_png")
 
     def write_ppm(self, path: str):
         self._ck(self.L.ug_write_ppm(self.ctx, path.encode()), "ug_write_ppm")

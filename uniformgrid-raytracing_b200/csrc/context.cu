@@ -1603,6 +1603,75 @@ extern "C" int ug_timeline(ug_context *ctx, double *ns64)
 	return UG_OK;
 }
 
+/* the frame as a PNG, top row first - what display() gets from writePPM + `convert -flip` (main.cu:255-259)
+ * without the external tool.  8-bit RGB, filter 0, zlib stream of stored (uncompressed) deflate blocks: no dependency. */
+static unsigned png_crc(const unsigned char *p, size_t n, unsigned crc)
+{
+	static unsigned table[256];
+	if (!table[1])
+		for (unsigned i = 0; i < 256; i++) {
+			unsigned c = i;
+			for (int k = 0; k < 8; k++) c = (c & 1u) ? 0xedb88320u ^ (c >> 1) : c >> 1;
+			table[i] = c;
+		}
+	for (size_t i = 0; i < n; i++) crc = table[(crc ^ p[i]) & 0xffu] ^ (crc >> 8);
+	return crc;
+}
+static void png_be32(unsigned char *p, unsigned v) { p[0] = (unsigned char)(v >> 24); p[1] = (unsigned char)(v >> 16); p[2] = (unsigned char)(v >> 8); p[3] = (unsigned char)v; }
+static bool png_chunk(FILE *fp, const char *type, const unsigned char *data, size_t n)
+{
+	unsigned char head[8], tail[4];
+	png_be32(head, (unsigned)n);
+	memcpy(head + 4, type, 4);
+	unsigned crc = png_crc(head + 4, 4, 0xffffffffu);
+	if (n) crc = png_crc(data, n, crc);
+	png_be32(tail, crc ^ 0xffffffffu);
+	return fwrite(head, 1, 8, fp) == 8 && (!n || fwrite(data, 1, n, fp) == n) && fwrite(tail, 1, 4, fp) == 4;
+}
+extern "C" int ug_write_png(ug_context *ctx, const char *filename)
+{
+	if (!ctx || !filename || !ctx->d_rgb) return ug_fail(ctx, UG_ERR_ARG, "write_png: nothing rendered");
+	const size_t bytes = 3 * (size_t)ctx->N, row = 3 * (size_t)ctx->W;
+	const int rows = ctx->gy_cnt * UG_TILE;
+	std::vector<unsigned char> img(bytes);
+	int rc = ug_read(ctx, UG_BUF_RGB, 0, img.data(), bytes);
+	if (rc) return rc;
+	/* scanlines, top row first (pixel row 0 is the bottom one, per_app_funcs.h:48-60), each behind its filter byte */
+	std::vector<unsigned char> raw((row + 1) * (size_t)rows);
+	for (int y = 0; y < rows; y++) {
+		unsigned char *dst = raw.data() + (size_t)y * (row + 1);
+		dst[0] = 0;
+		memcpy(dst + 1, img.data() + (size_t)(rows - 1 - y) * row, row);
+	}
+	/* zlib: header, stored blocks of at most 65535 bytes, Adler-32 of the raw data */
+	std::vector<unsigned char> z;
+	z.reserve(raw.size() + raw.size() / 65535 * 5 + 16);
+	z.push_back(0x78); z.push_back(0x01);
+	unsigned a = 1, b = 0;
+	for (size_t pos = 0; pos < raw.size() || pos == 0;) {
+		const size_t n = raw.size() - pos < 65535 ? raw.size() - pos : 65535;
+		z.push_back(pos + n >= raw.size() ? 1 : 0);
+		z.push_back((unsigned char)(n & 0xff)); z.push_back((unsigned char)(n >> 8));
+		z.push_back((unsigned char)(~n & 0xff)); z.push_back((unsigned char)((~n >> 8) & 0xff));
+		z.insert(z.end(), raw.begin() + (long)pos, raw.begin() + (long)(pos + n));
+		for (size_t i = pos; i < pos + n; i++) { a += raw[i]; if (a >= 65521u) a -= 65521u; b += a; if (b >= 65521u) b -= 65521u; }
+		pos += n;
+		if (!n) break;
+	}
+	unsigned char ad[4];
+	png_be32(ad, (b << 16) | a);
+	z.insert(z.end(), ad, ad + 4);
+	FILE *fp = fopen(filename, "wb");
+	if (!fp) return ug_fail(ctx, UG_ERR_IO, "cannot open %s", filename);
+	static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+	unsigned char ihdr[13];
+	png_be32(ihdr, (unsigned)ctx->W); png_be32(ihdr + 4, (unsigned)rows);
+	ihdr[8] = 8; ihdr[9] = 2; ihdr[10] = 0; ihdr[11] = 0; ihdr[12] = 0; /* 8 bits, truecolour, deflate, adaptive filters, no interlace */
+	bool ok = fwrite(sig, 1, 8, fp) == 8 && png_chunk(fp, "IHDR", ihdr, 13) && png_chunk(fp, "IDAT", z.data(), z.size()) && png_chunk(fp, "IEND", nullptr, 0);
+	ok = (fclose(fp) == 0) && ok;
+	return ok ? UG_OK : ug_fail(ctx, UG_ERR_IO, "short write to %s", filename);
+}
+
 extern "C" int ug_write_ppm_binary(ug_context *ctx, const char *filename)
 {
 	if (!ctx || !filename || !ctx->d_rgb) return ug_fail(ctx, UG_ERR_ARG, "write_ppm_binary: nothing rendered");
