@@ -241,6 +241,20 @@ def run_ours(args):
             new[k] = min(new[k], new[k + 1] - 1)
         return new
 
+    prime_img = torch.empty(3 * scene.num_pixels, dtype=torch.uint8).pin_memory()
+    invalid = []
+
+    def prime(strip, flags=0):
+        """ug_render_frame is asynchronous: a pair arena that proves too small only shows in ug_get_stats.  Every series of timed
+        frames is therefore preceded by one frame through ug_render_frame_host, which grows the arenas and renders the frame
+        again until it fits (collective when the frame is gathered) - config E needs that, A-D never overflow."""
+        r.render_host(r.params(scene, frame=0, flags=base_flags | flags, strip=strip, bounces=bounces, slabs=args.slabs), prime_img.numpy())
+
+    def check_valid(what):
+        """after a series: the last frame must not have overflowed an arena (a frame that did is incomplete and fast)"""
+        if r.stats().overflowed:
+            invalid.append(what)
+
     def measure_strips(own: bool):
         """median time of this rank's strip over 9 flushed frames, gathered from every rank"""
         pcal = r.params(scene, frame=0, flags=base_flags, strip=(rank, world), bounces=bounces, slabs=args.slabs)
@@ -265,6 +279,7 @@ def run_ours(args):
         r.set_screen(scene.width, scene.height, scene.fovy)
         for it in range(4):
             r.set_strip_bounds(bounds, rank)
+            prime((rank, world))
             T = measure_strips(own=False)
             history.append({"bounds": list(bounds), "ms": [round(float(x), 4) for x in T], "gathered": False})
             if T.max() / T.mean() < 1.015 or it == 3:
@@ -277,6 +292,7 @@ def run_ours(args):
         join_comm()
     if balancing:   # then inside the real gathered frames, on each rank's own time (ug_stats.ms_own: first kernel -> its last remote store)
         best = None
+        prime((rank, world))
         for it in range(6):
             T = measure_strips(own=True)
             history.append({"bounds": list(bounds), "ms": [round(float(x), 4) for x in T], "gathered": True})
@@ -286,9 +302,11 @@ def run_ours(args):
                 break
             bounds = rebalance(T, bounds)
             r.set_strip_bounds(bounds, rank)
+            prime((rank, world))
         if bounds != best[1]:
             bounds = best[1]
             r.set_strip_bounds(bounds, rank)
+            prime((rank, world))
         balance = {"row_bounds": list(bounds), "iterations": history,
                    "note": "strip boundaries (cell rows) moved until the strips' measured times agree: image-space cost is not uniform"}
         lo, hi = bounds[rank], bounds[rank + 1]
@@ -344,6 +362,7 @@ def run_ours(args):
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if rank == 0 else None
+    check_valid("timed frames")
     # the same K frames with a warm L2 (what a render loop sees between consecutive frames), reported next to the flushed figure
     warm = []
     for i in range(min(args.steps, 20)):
@@ -402,6 +421,10 @@ def run_ours(args):
     other = None
     if world > 1:
         om = "frames" if mode == "strips" else "strips"
+        if om == "frames":
+            prime((0, 1), ug.FLAG_GATHER_FRAMES)
+        else:
+            prime((rank, world))
         for i in range(5):
             step(i, m=om)
         if om == "frames":
@@ -423,6 +446,7 @@ def run_ours(args):
         barrier()
         t2 = torch.tensor([a.elapsed_time(b) for a, b in ev2] + [tail2[0].elapsed_time(tail2[1])], dtype=torch.float64, device=dev)
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        check_valid("frames of the other sharding mode")
         ms2 = float(t2.sum().item()) / k2
         fps2 = world if om == "frames" else 1
         other = {"mode": om, "ms_per_step": ms2, "steps": k2, "scaling": "weak" if om == "frames" else "strong", "frames_per_step": fps2,
@@ -441,6 +465,7 @@ def run_ours(args):
         if rank == 0:
             h_gather = hashlib.sha256(host_img.numpy().tobytes()).hexdigest()
             p1 = r.params(scene, frame=0, flags=base_flags, strip=(0, 1), bounces=bounces, slabs=args.slabs)
+            prime((0, 1))        # not gathered: rank 0 alone
             for _ in range(3):
                 r.render(p1)
             r.synchronize()
@@ -454,6 +479,7 @@ def run_ours(args):
                 evs.append((a_, b_))
             torch.cuda.synchronize()
             ms1 = float(np.mean([a_.elapsed_time(b_) for a_, b_ in evs]))
+            check_valid("single-GPU frame")
             check = {"sha256_gathered": h_gather, "sha256_single_gpu": h_single, "equal": h_gather == h_single}
             single = {"ms_per_frame": ms1, "value": scene.rays_per_frame() / (ms1 * 1e-3) / 1e6, "unit": "Mrays/s", "steps": len(evs),
                       "note": "rank 0 renders the same frame alone (strip 0 of 1, no gather) in the same process, same timing rules"}
@@ -469,6 +495,7 @@ def run_ours(args):
         rd.set_scene(sd)
         rd.set_stream(work_stream.cuda_stream)
         pd_ = rd.params(sd, frame=0, flags=base_flags)
+        rd.render_host(pd_, torch.empty(3 * sd.num_pixels, dtype=torch.uint8).pin_memory().numpy())   # grows the arenas if the scene needs it
         for _ in range(4):
             rd.render(pd_)
         torch.cuda.synchronize()
@@ -509,6 +536,11 @@ def run_ours(args):
         names = {1: "cam_grid", 11: "light_grid", 6: "ready", 2: "primary", 13: "regroup", 14: "shadow", 3: "shade", 5: "gather"}
         timeline = {str(k): {n: round(float(allt[k][i].item()), 1) for i, n in names.items()} for k in range(world)}
 
+    invalid_all = list(invalid)
+    if world > 1:
+        got = [None] * world
+        dist.all_gather_object(got, invalid)
+        invalid_all = sorted({f"rank {k}: {w}" for k, lst in enumerate(got) for w in lst})
     if rank == 0:
         P, N, Cc = st2.cam_pairs, st2.num_pixels, st2.num_cells
         T = scene.num_tris
@@ -595,6 +627,7 @@ def run_ours(args):
             other["value"] = (scene.rays_per_frame() * other["frames_per_step"] + int(refl.item()) / frames_per_step * other["frames_per_step"]) / (other["ms_per_step"] * 1e-3) / 1e6
             other["unit"] = "Mrays/s"
             line[other["mode"]] = other
+        line["invalid_series"] = invalid_all   # series whose last frame overflowed a pair arena on some rank (incomplete frames): must be empty
         if timeline:
             line["timeline_us"] = timeline
         if balance:

@@ -194,7 +194,7 @@ static __device__ __forceinline__ void gf_stamp(u32 *counters, int k)
 static __device__ __forceinline__ u32 ug_lookback(volatile u64 *desc, u32 tile, u32 total)
 {
 	const u32 lane = ug_lane();
-	u32 prefix = 0;
+	u64 prefix = 0; /* sums saturate at 2^32 - 1 instead of wrapping: a saturated pair total exceeds every arena and raises the overflow flag */
 	if (tile == 0) {
 		if (lane == 0) desc[0] = (2ull << 32) | total;
 		return 0;
@@ -209,15 +209,16 @@ static __device__ __forceinline__ u32 ug_lookback(volatile u64 *desc, u32 tile, 
 		}
 		const u32 flag = (u32)(d >> 32), val = (u32)d;
 		const u32 incl = __ballot_sync(UG_FULL_MASK, flag == 2);
-		u32 part = val;
+		u64 part = val;
 		if (incl) part = ((int)lane <= __ffs(incl) - 1) ? val : 0u;
 		for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(UG_FULL_MASK, part, o);
 		prefix += part;
 		if (incl) break;
 		look -= 32;
 	}
-	if (lane == 0) desc[tile] = (2ull << 32) | (u64)(prefix + total);
-	return prefix;
+	if (prefix > 0xffffffffull) prefix = 0xffffffffull;
+	if (lane == 0) desc[tile] = (2ull << 32) | (prefix + total > 0xffffffffull ? 0xffffffffull : prefix + total);
+	return (u32)prefix;
 }
 
 /* block-wide exclusive scan of one value per thread; returns the thread's exclusive prefix, total in `total` */

@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(GF_THREADS, 2) k_grid_fused(const GridFusedArg
 		__syncthreads();
 		if (t < T) a.scan[t] = s_pref + excl;
 		if (tile == tiles_a - 1 && tid == 0) {
-			const u32 Ptrue = s_pref + total, Pc = min(Ptrue, a.cap);
+			const u64 P64 = (u64)s_pref + total; /* saturates: see ug_lookback */
+			const u32 Ptrue = P64 > 0xffffffffull ? 0xffffffffu : (u32)P64, Pc = min(Ptrue, a.cap);
 			a.scan[T] = Ptrue;
 			a.counters[0] = Pc;
 			a.counters[1] = (Ptrue > a.cap) ? 1u : 0u; /* arena overflow: the host grows it and re-runs the frame */

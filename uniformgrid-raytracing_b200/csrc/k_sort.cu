@@ -92,15 +92,19 @@ __global__ void __launch_bounds__(SC_THREADS) sc_exclusive(const u32 *__restrict
 	}
 	if (ug_lane() == 31) s_warp[threadIdx.x >> 5] = incl;
 	__syncthreads();
-	u32 warp_off = 0, total = 0;
+	/* Sums that can exceed 32 bits (pair counts of a grid whose triangles cover most of a million cells) SATURATE instead of
+	 * wrapping: a saturated grand total is larger than any arena, so the frame raises its overflow flag and fails loudly when
+	 * the arena cannot grow that far, instead of rendering a truncated list. */
+	u64 warp_off = 0, total64 = 0;
 #pragma unroll
 	for (int w = 0; w < SC_THREADS / 32; w++) {
 		const u32 c = s_warp[w];
 		if (w < (int)(threadIdx.x >> 5)) warp_off += c;
-		total += c;
+		total64 += c;
 	}
+	const u32 total = total64 > 0xffffffffull ? 0xffffffffu : (u32)total64;
 	if (threadIdx.x < 32) {
-		u32 prefix = 0;
+		u64 prefix = 0;
 		if (tile == 0) {
 			if (threadIdx.x == 0) desc[0] = (2ull << 32) | total;
 		} else {
@@ -118,25 +122,26 @@ __global__ void __launch_bounds__(SC_THREADS) sc_exclusive(const u32 *__restrict
 				const u32 incl_mask = __ballot_sync(UG_FULL_MASK, flag == 2);
 				if (incl_mask) { /* sum everything up to and including the nearest inclusive prefix */
 					const int first = __ffs(incl_mask) - 1;
-					u32 part = ((int)threadIdx.x <= first) ? val : 0u;
+					u64 part = ((int)threadIdx.x <= first) ? val : 0u;
 					for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(UG_FULL_MASK, part, o);
 					prefix += part;
 					break;
 				}
-				u32 part = val;
+				u64 part = val;
 				for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(UG_FULL_MASK, part, o);
 				prefix += part;
 				look -= 32;
 			}
-			if (threadIdx.x == 0) desc[tile] = (2ull << 32) | (u64)(prefix + total);
+			if (prefix > 0xffffffffull) prefix = 0xffffffffull;
+			if (threadIdx.x == 0) desc[tile] = (2ull << 32) | (prefix + total > 0xffffffffull ? 0xffffffffull : prefix + total);
 		}
-		if (threadIdx.x == 0) s_prefix = prefix;
+		if (threadIdx.x == 0) s_prefix = (u32)prefix;
 	}
 	__syncthreads();
-	u32 run = s_prefix + warp_off + incl - sum;
+	u64 run = (u64)s_prefix + warp_off + incl - sum;
 #pragma unroll
 	for (int k = 0; k < SC_ITEMS; k++) {
-		if (base + k <= n) out[base + k] = run; /* entry n holds the grand total */
+		if (base + k <= n) out[base + k] = run > 0xffffffffull ? 0xffffffffu : (u32)run; /* entry n holds the grand total */
 		run += v[k];
 	}
 }
