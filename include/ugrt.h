@@ -219,6 +219,13 @@ int ug_render_frame(ug_context *ctx, const ug_frame_params *p); /* asynchronous:
 /* same, end to end with host buffers: uploads the frame constants, renders, copies the RGB8 strip into
  * host_rgb (3*W*H_strip bytes, pinned or pageable) and synchronises - main.cu:245 included */
 int ug_render_frame_host(ug_context *ctx, const ug_frame_params *p, uint8_t *host_rgb);
+/* frames in flight: returns once the frame and the read-back of its image (on a stream of its own) are enqueued, so the next
+ * frame renders while this image crosses PCIe; host_rgb must be pinned.  ug_wait_frame(ctx, 0): the last submitted frame's
+ * image is in host memory (UG_ERR_OVERFLOW: an arena was too small, it has been grown, submit the frame again);
+ * ug_wait_frame(ctx, k), k = 1..3: the image of the frame submitted k calls earlier is.  display()'s cudaMemcpy of the image
+ * (main.cu:245), taken off the frame's critical path. */
+int ug_render_frame_host_async(ug_context *ctx, const ug_frame_params *p, uint8_t *pinned_host_rgb);
+int ug_wait_frame(ug_context *ctx, int frames_back);
 
 /* ---- read-back / interop */
 int ug_get_stats(ug_context *ctx, ug_stats *out);                                        /* synchronises */

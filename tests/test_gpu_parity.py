@@ -270,6 +270,40 @@ def test_binary_ppm(renderer, ug, tmp_path):
     assert np.array_equal(np.frombuffer(raw[len(head):], np.uint8).reshape(s.height, s.width, 3), rgb[::-1])   # top row first
 
 
+def test_frames_in_flight(ug, oracle):
+    """ug_render_frame_host_async / ug_wait_frame: the read-back of frame i runs on its own stream while frame i+1 renders (the
+    first kernel that rewrites the image waits for it inside the graph).  Six frames of a dynamic scene with two frames in
+    flight and two pinned buffers: every image must be the frame the synchronous call returns (and the oracle's)."""
+    import torch
+    s = scenes.scene_c(240, 136)
+    r = ug.Renderer()
+    try:
+        r.set_scene(s)
+        want = []
+        host = torch.empty(3 * s.num_pixels, dtype=torch.uint8).pin_memory()
+        for f in range(6):
+            r.render_host(r.params(s, frame=f), host.numpy())
+            want.append(host.numpy().copy())
+        assert np.array_equal(want[3], harness.run_frame(oracle, s, frame=3, threads=0)["rgb"])
+        bufs = [torch.empty(3 * s.num_pixels, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        got = {}
+        for f in range(6):
+            r.render_host_async(r.params(s, frame=f), bufs[f & 1].numpy())
+            if f >= 1:
+                r.wait_frame(1)
+                got[f - 1] = bufs[(f - 1) & 1].numpy().copy()
+        r.wait_frame(0)
+        got[5] = bufs[1].numpy().copy()
+        for f in range(6):
+            assert np.array_equal(got[f], want[f]), f"frame {f}"
+        with pytest.raises(RuntimeError):
+            r.render_host_async(r.params(s, frame=0), np.zeros(3 * s.num_pixels, np.uint8))   # pageable destination: refused
+        r.render_host(r.params(s, frame=2), host.numpy())                                    # the synchronous call still works afterwards
+        assert np.array_equal(host.numpy(), want[2])
+    finally:
+        r.close()
+
+
 def test_png(renderer, ug, tmp_path):
     """ug_write_png (what display() gets from writePPM + `convert -flip`): decoded here with zlib + the PNG chunk
     layout by hand - signature, IHDR, one IDAT of stored deflate blocks, IEND, every CRC - and compared with the frame.  The

@@ -98,6 +98,7 @@ def lib() -> C.CDLL:
             "ug_set_light_grid_mode": (C.c_int, [vp, C.c_int, C.c_float, C.c_float]), "ug_acosf_host": (None, [f, f, C.c_size_t]), "ug_shadow_item_shape": (None, [C.c_uint, C.c_uint, C.POINTER(C.c_uint)]),
             "ug_render_frame": (C.c_int, [vp, C.POINTER(FrameParams)]),
             "ug_render_frame_host": (C.c_int, [vp, C.POINTER(FrameParams), C.c_void_p]),
+            "ug_render_frame_host_async": (C.c_int, [vp, C.POINTER(FrameParams), C.c_void_p]), "ug_wait_frame": (C.c_int, [vp, C.c_int]),
             "ug_get_stats": (C.c_int, [vp, C.POINTER(Stats)]), "ug_read": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_size_t]),
             "ug_device_ptr": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]),
             "ug_write_ppm": (C.c_int, [vp, C.c_char_p]), "ug_write_ppm_binary": (C.c_int, [vp, C.c_char_p]), "ug_write_png": (C.c_int, [vp, C.c_char_p]),
@@ -260,6 +261,14 @@ class Renderer:
     def render_host(self, p: FrameParams, out: np.ndarray):
         assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"]
         self._ck(self.L.ug_render_frame_host(self.ctx, C.byref(p), out.ctypes.data_as(C.c_void_p)), "ug_render_frame_host")
+
+    def render_host_async(self, p: FrameParams, out: np.ndarray):
+        """`out` must be pinned; valid after wait_frame()."""
+        assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"]
+        self._ck(self.L.ug_render_frame_host_async(self.ctx, C.byref(p), out.ctypes.data_as(C.c_void_p)), "ug_render_frame_host_async")
+
+    def wait_frame(self, frames_back: int = 0):
+        self._ck(self.L.ug_wait_frame(self.ctx, int(frames_back)), "ug_wait_frame")
 
     def set_strip_bounds(self, row_bounds, index: int):
         """Strips of unequal height (cell-row boundaries 0 ... height/8); frames rendered with strip=(index, len(row_bounds)-1) keep them."""

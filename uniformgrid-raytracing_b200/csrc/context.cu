@@ -104,6 +104,10 @@ extern "C" int ug_create(ug_context **out, int device)
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_init, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ugrid, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_camgrid, cudaEventDisableTiming));
+	UG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_frame_done, cudaEventDisableTiming));
+	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy_done, cudaEventDisableTiming));
+	for (int i = 0; i < 4; i++) UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy_ring[i], cudaEventDisableTiming));
 	ctx->light_after_cam = getenv("UG_LIGHT_AFTER_CAM") != nullptr;
 	if (const char *e = getenv("UG_TRACE_ITEM")) ctx->trace_item_forced = atoi(e) == 64 ? 64 : 128; /* tests force both item sizes of k_trace */
 	UG_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_init, cudaStreamNonBlocking, prio ? prio_greatest : prio_least));
@@ -192,7 +196,7 @@ extern "C" void ug_destroy(ug_context *ctx)
 	}
 	dfree(ctx->d_fc);
 	for (int i = 0; i < UG_MAX_LIGHTS; i++) { cudaStreamDestroy(ctx->side[i]); cudaEventDestroy(ctx->ev_join[i]); cudaStreamDestroy(ctx->side_map[i]); cudaEventDestroy(ctx->ev_map[i]); }
-	cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_fork2); cudaEventDestroy(ctx->ev_init); cudaStreamDestroy(ctx->side_init); cudaStreamDestroy(ctx->side_refl); cudaStreamDestroy(ctx->side_ugrid); cudaEventDestroy(ctx->ev_ugrid); cudaEventDestroy(ctx->ev_camgrid); cudaStreamDestroy(ctx->side_comm); cudaEventDestroy(ctx->ev_ready); cudaEventDestroy(ctx->ev_cam); cudaEventDestroy(ctx->ev_refl); cudaEventDestroy(ctx->ev_trace); cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
+	cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_fork2); cudaEventDestroy(ctx->ev_init); cudaStreamDestroy(ctx->side_init); cudaStreamDestroy(ctx->side_refl); cudaStreamDestroy(ctx->side_ugrid); cudaEventDestroy(ctx->ev_ugrid); cudaEventDestroy(ctx->ev_camgrid); cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->ev_frame_done); cudaEventDestroy(ctx->ev_copy_done); for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev_copy_ring[i]); cudaStreamDestroy(ctx->side_comm); cudaEventDestroy(ctx->ev_ready); cudaEventDestroy(ctx->ev_cam); cudaEventDestroy(ctx->ev_refl); cudaEventDestroy(ctx->ev_trace); cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
 	for (auto &ev : ctx->ev_stage) cudaEventDestroy(ev);
 	cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
@@ -950,6 +954,7 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 		 * cannot start - issued at the head of the frame it put every rank's skew on the critical path */
 		UG_CUDA(ctx, cudaEventRecord(ctx->ev_cam, s));
 		UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_comm, ctx->ev_cam, 0));
+		if (ctx->async_readback && ctx->comm_rank == 0) UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_comm, ctx->ev_copy_done, cudaEventWaitExternal)); /* "ready" = the last read-back is over as well */
 		int rc = ugc_ready(ctx, ctx->side_comm, gather_deferred(ctx, p));
 		if (rc) return rc;
 		ugk_stamp(ctx->side_comm, tl, 6);
@@ -1030,6 +1035,9 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 		ctx->rgb_remote = base + slot_off + g_offs[ctx->comm_rank];
 		UG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_ready, 0)); /* rank 0 is past its read-out of what these stores overwrite */
 	}
+	/* asynchronous read-back (ug_render_frame_host_async): the copy of the previous image runs on its own stream beside this
+	 * frame; only the first kernel that rewrites the image waits for it (an external event-wait node of the graph) */
+	if (ctx->async_readback) UG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_copy_done, parallel ? cudaEventWaitExternal : 0));
 	ugk_shade(s, ctx->d_fc, ctx->d_t, ctx->d_dir, ctx->d_id, ctx->d_shadowed, ctx->cam_grid.tri_rec, ctx->d_materiallist_index, ctx->d_materiallist, ctx->num_materials,
 	          ctx->d_rgb, ctx->d_matid, ctx->N, 1, sms, (p->flags & UG_FLAG_SPOT_SHADE) != 0, ctx->rgb_remote);
 	L.n += 1;
@@ -1171,7 +1179,7 @@ static unsigned long long frame_key(const ug_context *ctx, const ug_frame_params
 	mix((unsigned long long)(p->transform && ctx->d_vertex_orig_list ? 1 : 0)); mix((unsigned long long)ctx->cam_grid.cap);
 	for (int l = 0; l < p->num_lights; l++) mix((unsigned long long)ctx->light_grid[l].cap);
 	mix((unsigned long long)(p->bounces > 0 && ctx->d_reflect ? p->bounces : 0)); mix((unsigned long long)ctx->refl.grid.cap);
-	mix((unsigned long long)ctx->num_slabs); mix((unsigned long long)gather_slot(ctx, p)); mix((unsigned long long)ctx->trace_small); mix((unsigned long long)ctx->lg_now); mix((unsigned long long)(uintptr_t)ctx->lg_local);
+	mix((unsigned long long)ctx->num_slabs); mix((unsigned long long)gather_slot(ctx, p)); mix((unsigned long long)ctx->trace_small); mix((unsigned long long)ctx->async_readback); mix((unsigned long long)ctx->lg_now); mix((unsigned long long)(uintptr_t)ctx->lg_local);
 	mix((unsigned long long)(uintptr_t)ctx->comm); mix((unsigned long long)(uintptr_t)ctx->d_rgb_full);
 	mix((unsigned long long)(uintptr_t)ctx->peer_full); mix((unsigned long long)ctx->use_push);
 	mix((unsigned long long)(uintptr_t)ctx->stream); mix((unsigned long long)(uintptr_t)ctx->d_rgb);
@@ -1326,6 +1334,57 @@ extern "C" int ug_render_frame_host(ug_context *ctx, const ug_frame_params *p, u
 		if (grew_here) ctx->stats.overflowed = 1; /* the other ranks run the frame again too, but their arenas were large enough */
 	}
 	return ug_fail(ctx, UG_ERR_OVERFLOW, "pair arena still too small after growing");
+}
+
+/* Frames in flight: the call returns once the frame and the read-back of its image are enqueued; the copy runs on its own
+ * stream, so the next frame (submitted right away) renders while this one's image crosses PCIe.  `host_rgb` must be pinned
+ * (cudaHostAlloc / cudaHostRegister) and stay untouched until ug_wait_frame.  An arena overflow cannot be repaired behind the
+ * caller's back here: ug_wait_frame reports it (after growing the arena) and the caller submits the frame again. */
+extern "C" int ug_render_frame_host_async(ug_context *ctx, const ug_frame_params *p, uint8_t *host_rgb)
+{
+	if (!ctx || !host_rgb) return ug_fail(ctx, UG_ERR_ARG, "ug_render_frame_host_async: null argument");
+	if (p && (p->flags & UG_FLAG_GATHER_DEFERRED)) return ug_fail(ctx, UG_ERR_ARG, "ug_render_frame_host_async: UG_FLAG_GATHER_DEFERRED frames are read with ug_comm_flush + ug_read");
+	cudaPointerAttributes attr;
+	const bool pinned = cudaPointerGetAttributes(&attr, host_rgb) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+	cudaGetLastError();
+	if (!pinned) return ug_fail(ctx, UG_ERR_ARG, "ug_render_frame_host_async: the destination must be pinned host memory");
+	if (!ctx->async_readback) { ctx->async_readback = true; ug_drop_graphs(ctx); }
+	int rc = prepare_frame(ctx, p);
+	if (rc) return rc;
+	ctx->stats.overflowed = 0;
+	rc = run_frame_once(ctx, p);
+	if (rc) return rc;
+	const bool gathered = ctx->comm && ctx->comm_world > 1 && ctx->strip_count == ctx->comm_world;
+	UG_CUDA(ctx, cudaEventRecord(ctx->ev_frame_done, ctx->stream));
+	if (!gathered || ctx->comm_rank == 0) {
+		const size_t out_bytes = gathered ? 3 * (size_t)ctx->W * ctx->H : 3 * (size_t)ctx->N;
+		UG_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_frame_done, 0));
+		UG_CUDA(ctx, cudaMemcpyAsync(host_rgb, gathered ? ctx->d_rgb_full : ctx->d_rgb, out_bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+		UG_CUDA(ctx, cudaEventRecord(ctx->ev_copy_done, ctx->copy_stream));
+	} else {
+		UG_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_frame_done, 0)); /* a rank without an image: its "read-back" is the end of its frame */
+	}
+	UG_CUDA(ctx, cudaEventRecord(ctx->ev_copy_ring[ctx->async_seq % 4], ctx->copy_stream));
+	ctx->async_seq++;
+	return UG_OK;
+}
+
+/* frames_back = 0: the image of the last ug_render_frame_host_async call is in host memory when this returns, and
+ * UG_ERR_OVERFLOW says that a pair arena was too small for that frame (it has been grown: submit the frame again);
+ * frames_back = 1..3: the image of the frame submitted that many calls earlier is in host memory (what a loop that keeps
+ * frames in flight waits on before it consumes a buffer and hands it out again). */
+extern "C" int ug_wait_frame(ug_context *ctx, int frames_back)
+{
+	if (!ctx || frames_back < 0 || frames_back > 3) return ug_fail(ctx, UG_ERR_ARG, "ug_wait_frame: frames_back must be 0..3");
+	if ((unsigned long long)frames_back >= ctx->async_seq) return UG_OK; /* nothing that old was submitted */
+	UG_CUDA(ctx, cudaSetDevice(ctx->device));
+	UG_CUDA(ctx, cudaEventSynchronize(ctx->ev_copy_ring[(ctx->async_seq - 1 - (unsigned long long)frames_back) % 4]));
+	if (frames_back > 0) return UG_OK;
+	ug_stats st;
+	int rc = ug_get_stats(ctx, &st);
+	if (rc) return rc;
+	if (st.overflowed) return ug_fail(ctx, UG_ERR_OVERFLOW, "a pair arena overflowed in the last frame; it has been grown, render the frame again");
+	return UG_OK;
 }
 
 /* ------------------------------------------------------------------ per_frame_funcs.h, call by call */

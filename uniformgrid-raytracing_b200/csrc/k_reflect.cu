@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(256) k_refl_init(const ReflectArgs a)
 
 /* one bounce for every live ray: 3-D DDA through the uniform grid, shade, spawn the next ray or finish the pixel */
 #ifndef UG_REFL_MINB
-#define UG_REFL_MINB 8
+#define UG_REFL_MINB 7 /* 72 registers, no spills (8 blocks/SM = 64 registers spilled 40 bytes; 6, 7 and 8 time the same: 137-138 us on config B) */
 #endif
 __global__ void __launch_bounds__(128, UG_REFL_MINB) k_refl_trace(const ReflectArgs a, int bounce)
 {

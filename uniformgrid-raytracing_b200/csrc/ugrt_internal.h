@@ -202,6 +202,12 @@ struct ug_context {
 	unsigned char *d_rgb = nullptr;      /* where frames are written (own buffer or the caller's) */
 	unsigned char *d_rgb_own = nullptr, *d_rgb_ext = nullptr;
 	size_t rgb_ext_bytes = 0;
+	/* ug_render_frame_host_async: the image read-back runs on its own stream while the next frame renders */
+	cudaStream_t copy_stream = nullptr;
+	cudaEvent_t ev_frame_done = nullptr, ev_copy_done = nullptr;
+	cudaEvent_t ev_copy_ring[4] = {};   /* read-back of async frame n = ring[n % 4]: what ug_wait_frame(ctx, frames_back) waits on */
+	unsigned long long async_seq = 0;   /* async frames submitted so far */
+	bool async_readback = false; /* frames wait (inside the graph, in front of the first kernel that rewrites the image) for the last read-back */
 	unsigned char *h_rgb_pinned = nullptr;
 	unsigned char *h_full_pinned = nullptr; /* rank 0: staging of a gathered frame whose destination is pageable */
 	size_t h_full_bytes = 0;
