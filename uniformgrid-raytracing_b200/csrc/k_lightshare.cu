@@ -60,8 +60,9 @@ __global__ void __launch_bounds__(LS_THREADS) k_light_push(const LightPushArgs a
 	__syncthreads();
 	if (!s_last) return;
 	__threadfence_system();
-	const u32 s = a.seq[0] + 1u;
-	if (threadIdx.x == 0) { a.seq[0] = s; a.seq[1] = 0; }
+	if (threadIdx.x == 0) { s_last = a.seq[0] + 1u; a.seq[0] = s_last; a.seq[1] = 0; } /* one reader of the old count: the other warps take the new one from shared memory */
+	__syncthreads();
+	const u32 s = s_last;
 	for (int p = threadIdx.x; p < a.world; p += LS_THREADS) ls_st_release_sys(a.peer[p] + (size_t)a.light * UG_MAX_RANKS + a.rank, s);
 }
 
