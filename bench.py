@@ -560,6 +560,10 @@ def run_ours(args):
         dist.all_gather_object(got, invalid)
         invalid_all = sorted({f"rank {k}: {w}" for k, lst in enumerate(got) for w in lst})
     if rank == 0:
+        try:
+            issue_measured = r.fp32_issue_peak() / 1e12
+        except Exception:
+            issue_measured = None
         P, N, Cc = st2.cam_pairs, st2.num_pixels, st2.num_cells
         T = scene.num_tris
         # single-kernel stages only (grid builds / regroup are several kernels); algorithmic bytes per launch from SURVEY.md 8(d)
@@ -595,9 +599,12 @@ def run_ours(args):
                     out["issue"] = {"issue_active_pct": issue, "lanes_active_of_32": lanes, "useful_issue_frac": issue / 100.0 * lanes / 32.0,
                                     "source": "profiles/ (ncu --set full of the same command), not measured in this run"}
             if tests:
-                issue_peak = 148 * 128 * sm_max * 1e6 / 1e12   # T lane-ops/s at the max SM clock
+                nominal = 148 * 128 * sm_max * 1e6 / 1e12   # T lane-ops/s at the max SM clock
+                issue_peak = issue_measured if issue_measured else nominal   # FMUL + FADD micro-benchmark of this run (k_peak.cu)
                 ach = tests * FP32_ISSUE_PER_TEST / t_s / 1e12
                 out["fp32_issue"] = {"achieved": ach, "peak": issue_peak, "unit": "T lane-ops/s", "frac": ach / issue_peak,
+                                     "peak_source": "measured in this run (ug_fp32_issue_peak: FMUL + FADD, all SMs)" if issue_measured else "nominal",
+                                     "peak_nominal": nominal, "frac_of_nominal": ach / nominal,
                                      "ray_triangle_tests_per_launch": tests, "fp32_instr_per_test": FP32_ISSUE_PER_TEST}
             return out
 

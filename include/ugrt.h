@@ -159,6 +159,9 @@ void ug_acosf_host(const float *x, float *y, size_t n);
 /* host view of how the shadow pass cuts a light cell with `rays` rays and `ntri` triangles into work items:
  * out = {rays per item, list segments, segment length, items}; items <= rays + 16 is what bounds the item table */
 void ug_shadow_item_shape(unsigned rays, unsigned ntri, unsigned out[4]);
+/* measured FP32 issue rate of this device, FMUL + FADD lane-ops per second with every SM fully occupied (the
+ * denominator of the traversal kernels' issue roofline is to be measured in the same harness, not taken from the nominal clock) */
+int ug_fp32_issue_peak(ug_context *ctx, double *lane_ops_per_s);
 size_t ug_frame_const_bytes(void); /* bytes of per-frame constants ug_render_frame* uploads (pinned H2D) */
 int ug_set_stream(ug_context *ctx, void *cuda_stream); /* NULL: the context's own non-blocking stream */
 int ug_synchronize(ug_context *ctx);

@@ -105,7 +105,7 @@ def lib() -> C.CDLL:
             "ug_model_tmp_model": (C.c_int, [vp, C.c_char_p, C.c_int]), "ug_model_update_vertices": (C.c_int, [vp, f, C.c_int]),
             "ug_model_bounds": (C.c_int, [vp, f]), "ug_obj_parse_vertices": (C.c_int, [C.c_char_p, i, f, C.c_int]), "ug_stage_times": (C.c_int, [vp, f, C.c_int]),
             "ug_camera_adjustCameraAndPosition": (None, [C.POINTER(Camera)]), "ug_camera_pack": (None, [C.POINTER(Camera), f]),
-            "ug_direction_lattice": (None, [f, f]),
+            "ug_direction_lattice": (None, [f, f]), "ug_fp32_issue_peak": (C.c_int, [vp, C.POINTER(C.c_double)]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -310,6 +310,12 @@ class Renderer:
             names += [f"light{l}_grid", f"light{l}_regroup", f"light{l}_shadow"]
         names += ["shade", "reflect_grid", "reflect_rays", "reflect_combine"]
         return {names[k]: buf[k] for k in range(min(max(n, 0), len(names)))}
+
+    def fp32_issue_peak(self) -> float:
+        """Measured FMUL + FADD lane-ops per second of this device (k_peak.cu)."""
+        v = C.c_double(0.0)
+        self._ck(self.L.ug_fp32_issue_peak(self.ctx, C.byref(v)), "ug_fp32_issue_peak")
+        return float(v.value)
 
     def read(self, buffer: int, index: int = 0) -> np.ndarray:
         ptr, nbytes = C.c_void_p(), C.c_size_t()

@@ -109,6 +109,7 @@ extern "C" int ug_create(ug_context **out, int device)
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy_done, cudaEventDisableTiming));
 	for (int i = 0; i < 4; i++) UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy_ring[i], cudaEventDisableTiming));
 	ctx->light_after_cam = getenv("UG_LIGHT_AFTER_CAM") != nullptr;
+	if (const char *e = getenv("UG_DIR_RECOMPUTE")) ctx->dir_recompute = atoi(e) & 3;
 	if (const char *e = getenv("UG_TRACE_ITEM")) ctx->trace_item_forced = atoi(e) == 64 ? 64 : 128; /* tests force both item sizes of k_trace */
 	UG_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_init, cudaStreamNonBlocking, prio ? prio_greatest : prio_least));
 	UG_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_refl, cudaStreamNonBlocking, prio ? prio_greatest : prio_least));
@@ -849,14 +850,17 @@ static void enqueue_light_zero(ug_context *ctx, cudaStream_t s, int l)
 	LightRays &r = ctx->rays[l];
 	cudaMemsetAsync(r.span, 0, sizeof(u32) * ((size_t)ctx->C_light + 1), s);
 }
-static void enqueue_light_regroup(ug_context *ctx, cudaStream_t s, int l, Launches &L, int phases = 7)
+/* in_frame: the caller is enqueue_frame, so the eye's ViewConst in d_fc is the one the stored directions were made from
+ * and phase A may evaluate them again instead of reading them (the stage entry points always read the buffer) */
+static void enqueue_light_regroup(ug_context *ctx, cudaStream_t s, int l, Launches &L, int phases = 7, bool in_frame = false)
 {
 	if (ctx->direct_shadow) return; /* the rays are not regrouped: ray -> light cell is part of the shadow pass */
 	LightRays &r = ctx->rays[l];
 	const GridBuffers lg = light_view(ctx, l);
-	if (!ugk_regroup(s, ctx->d_fc, l, lg, r, ctx->d_t, ctx->d_dir, ctx->N, ctx->C_light, ctx->num_sms, ctx->use_fused_regroup, &L.n, phases)) {
+	const bool recomp = in_frame && (ctx->dir_recompute & 2);
+	if (!ugk_regroup(s, ctx->d_fc, l, lg, r, ctx->d_t, ctx->d_dir, ctx->N, ctx->C_light, ctx->num_sms, ctx->use_fused_regroup, &L.n, phases, recomp)) {
 		ctx->use_fused_regroup = false; /* cooperative launch refused: phase-by-phase launches from now on */
-		ugk_regroup(s, ctx->d_fc, l, lg, r, ctx->d_t, ctx->d_dir, ctx->N, ctx->C_light, ctx->num_sms, false, &L.n, phases);
+		ugk_regroup(s, ctx->d_fc, l, lg, r, ctx->d_t, ctx->d_dir, ctx->N, ctx->C_light, ctx->num_sms, false, &L.n, phases, recomp);
 	}
 }
 static void enqueue_light_shadow(ug_context *ctx, cudaStream_t s, int l, Launches &L)
@@ -983,14 +987,14 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 			if (split_map) {
 				UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_map[l], ctx->ev_trace, 0));
 				if (l == 0) ugk_stamp(ctx->side_map[l], tl, 12);
-				enqueue_light_regroup(ctx, ctx->side_map[l], l, L, 1);
+				enqueue_light_regroup(ctx, ctx->side_map[l], l, L, 1, true);
 				UG_CUDA(ctx, cudaEventRecord(ctx->ev_map[l], ctx->side_map[l]));
 				UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side[l], ctx->ev_map[l], 0));
-				enqueue_light_regroup(ctx, ctx->side[l], l, L, 6);
+				enqueue_light_regroup(ctx, ctx->side[l], l, L, 6, true);
 			} else {
 				UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side[l], ctx->ev_trace, 0));
 				if (l == 0) ugk_stamp(ctx->side[l], tl, 12);
-				enqueue_light_regroup(ctx, ctx->side[l], l, L);
+				enqueue_light_regroup(ctx, ctx->side[l], l, L, 7, true);
 			}
 			if (l == 0) ugk_stamp(ctx->side[l], tl, 13);
 			enqueue_light_shadow(ctx, ctx->side[l], l, L);
@@ -1003,7 +1007,7 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 			enqueue_light_zero(ctx, s, l);
 			enqueue_light_grid(ctx, s, l, L);
 			stage_mark(ctx, k, stage_events); /* 4+3l: light grid */
-			enqueue_light_regroup(ctx, s, l, L);
+			enqueue_light_regroup(ctx, s, l, L, 7, true);
 			stage_mark(ctx, k, stage_events); /* 5+3l: ray -> light cell map + regroup */
 			enqueue_light_shadow(ctx, s, l, L);
 			stage_mark(ctx, k, stage_events); /* 6+3l: shadow rays */
@@ -1039,7 +1043,7 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 	 * frame; only the first kernel that rewrites the image waits for it (an external event-wait node of the graph) */
 	if (ctx->async_readback) UG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_copy_done, parallel ? cudaEventWaitExternal : 0));
 	ugk_shade(s, ctx->d_fc, ctx->d_t, ctx->d_dir, ctx->d_id, ctx->d_shadowed, ctx->cam_grid.tri_rec, ctx->d_materiallist_index, ctx->d_materiallist, ctx->num_materials,
-	          ctx->d_rgb, ctx->d_matid, ctx->N, 1, sms, (p->flags & UG_FLAG_SPOT_SHADE) != 0, ctx->rgb_remote);
+	          ctx->d_rgb, ctx->d_matid, ctx->N, 1, sms, (p->flags & UG_FLAG_SPOT_SHADE) != 0, ctx->rgb_remote, (ctx->dir_recompute & 1) != 0);
 	L.n += 1;
 	ugk_stamp(s, tl, 3);
 	stage_mark(ctx, k, stage_events); /* shade */

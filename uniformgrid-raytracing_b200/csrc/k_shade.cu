@@ -54,8 +54,12 @@ void ugk_transform(cudaStream_t s, float *vertexlist, const float *orig, int siz
 }
 
 /* 4 consecutive pixels per thread: 16-byte loads of t/id/shadowed, 3 x 16-byte loads of dir, the 12 RGB bytes leave
- * as three 32-bit stores (N is a multiple of 64, every buffer is 16-byte aligned) */
-template <bool SPOT>
+ * as three 32-bit stores (N is a multiple of 64, every buffer is 16-byte aligned).
+ * RECOMP: the ray direction is evaluated again from the 5x5 lattice (ug_primary_dir, the expression k_init_pixels stored
+ * d_primary_ray_direction with, so the bits are the same) instead of being read: 12 of the kernel's 24 input bytes per
+ * pixel go away, and a pixel without a hit never needs its direction.  The four pixels share a screen row (W is a
+ * multiple of the tile), so the row part of the lattice weights is common. */
+template <bool SPOT, bool RECOMP>
 __global__ void __launch_bounds__(256) k_shade(const FrameConst *__restrict__ fc, const float *__restrict__ t, const float *__restrict__ dir,
                                               const int *__restrict__ id, const int *__restrict__ shadowed, const float4 *__restrict__ rec,
                                               const int *__restrict__ mat_idx, const float *__restrict__ mat_list, int mat_count,
@@ -71,11 +75,27 @@ __global__ void __launch_bounds__(256) k_shade(const FrameConst *__restrict__ fc
 	const float Lvy = R[1] * l0 + R[5] * l1 + R[9] * l2;
 	const float Lvz = R[2] * l0 + R[6] * l1 + R[10] * l2;
 	const int groups = N / 4;
+	__shared__ float s_lat[100];
+	const int W = cam.W, H = cam.H, row0 = cam.gy_lo * UG_TILE;
+	if (RECOMP) {
+		for (int i = threadIdx.x; i < 100; i += blockDim.x) s_lat[i] = cam.lattice[i];
+		__syncthreads();
+	}
 	for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
 		const float4 tv = ((const float4 *)t)[g];
 		const int4 tri = ((const int4 *)id)[g];
 		const int4 sh = ((const int4 *)shadowed)[g];
-		const float4 d0 = ((const float4 *)dir)[3 * (size_t)g], d1 = ((const float4 *)dir)[3 * (size_t)g + 1], d2 = ((const float4 *)dir)[3 * (size_t)g + 2];
+		float4 d0, d1, d2;
+		if (RECOMP) {
+			const int pyl = (4 * g) / W, px = 4 * g - pyl * W;
+			d0 = d1 = d2 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+			if (tri.x >= 0 && tv.x > 0.0f) ug_primary_dir(s_lat, ex, ey, ez, px, pyl + row0, W, H, d0.x, d0.y, d0.z);
+			if (tri.y >= 0 && tv.y > 0.0f) ug_primary_dir(s_lat, ex, ey, ez, px + 1, pyl + row0, W, H, d0.w, d1.x, d1.y);
+			if (tri.z >= 0 && tv.z > 0.0f) ug_primary_dir(s_lat, ex, ey, ez, px + 2, pyl + row0, W, H, d1.z, d1.w, d2.x);
+			if (tri.w >= 0 && tv.w > 0.0f) ug_primary_dir(s_lat, ex, ey, ez, px + 3, pyl + row0, W, H, d2.y, d2.z, d2.w);
+		} else {
+			d0 = ((const float4 *)dir)[3 * (size_t)g]; d1 = ((const float4 *)dir)[3 * (size_t)g + 1]; d2 = ((const float4 *)dir)[3 * (size_t)g + 2];
+		}
 		int m0, m1, m2, m3;
 		const u32 c0 = shade_pixel<SPOT>(R, leye, ex, ey, ez, Lvx, Lvy, Lvz, tv.x, d0.x, d0.y, d0.z, tri.x, sh.x, rec, mat_idx, mat_list, mat_count, apply_shadow, m0);
 		const u32 c1 = shade_pixel<SPOT>(R, leye, ex, ey, ez, Lvx, Lvy, Lvz, tv.y, d0.w, d1.x, d1.y, tri.y, sh.y, rec, mat_idx, mat_list, mat_count, apply_shadow, m1);
@@ -101,12 +121,16 @@ __global__ void __launch_bounds__(256) k_add_shadows(const int *__restrict__ sha
 }
 
 void ugk_shade(cudaStream_t s, const FrameConst *fc, const float *t, const float *dir, const int *id, const int *shadowed, const float4 *rec, const int *mat_idx,
-               const float *mat_list, int mat_count, unsigned char *rgb, int *mat_out, int N, int apply_shadow, int sms, bool spot, unsigned char *rgb_remote)
+               const float *mat_list, int mat_count, unsigned char *rgb, int *mat_out, int N, int apply_shadow, int sms, bool spot, unsigned char *rgb_remote,
+               bool recompute_dir)
 {
 	if (N <= 0) return;
 	const int blocks = min((N / 4 + 255) / 256, sms * 8);
-	if (spot) k_shade<true><<<blocks, 256, 0, s>>>(fc, t, dir, id, shadowed, rec, mat_idx, mat_list, mat_count, rgb, mat_out, N, apply_shadow, rgb_remote);
-	else k_shade<false><<<blocks, 256, 0, s>>>(fc, t, dir, id, shadowed, rec, mat_idx, mat_list, mat_count, rgb, mat_out, N, apply_shadow, rgb_remote);
+#define UG_SHADE_LAUNCH(SPOT, RECOMP) \
+	k_shade<SPOT, RECOMP><<<blocks, 256, 0, s>>>(fc, t, dir, id, shadowed, rec, mat_idx, mat_list, mat_count, rgb, mat_out, N, apply_shadow, rgb_remote)
+	if (spot) { if (recompute_dir) UG_SHADE_LAUNCH(true, true); else UG_SHADE_LAUNCH(true, false); }
+	else { if (recompute_dir) UG_SHADE_LAUNCH(false, true); else UG_SHADE_LAUNCH(false, false); }
+#undef UG_SHADE_LAUNCH
 }
 void ugk_add_shadows(cudaStream_t s, const int *shadowed, unsigned char *rgb, int N, int sms)
 {

@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(RG_THREADS, 2) k_regroup(const RegroupArgs a, 
 {
 	__shared__ u32 s_warp[RG_THREADS / 32];
 	__shared__ u32 s_pref[2];
+	__shared__ float s_lat[100];
 	const u32 G = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
 	const int N = a.N, C = a.C;
 	const bool all = phase < 0;
@@ -118,6 +119,14 @@ __global__ void __launch_bounds__(RG_THREADS, 2) k_regroup(const RegroupArgs a, 
 		const bool spherical = lv.grid_mode == UG_LIGHT_GRID_SPHERICAL;
 		const float ex = cam.cc[0], ey = cam.cc[1], ez = cam.cc[2];
 		if (b == 0 && tid == 0) a.counters[1] = 0;
+		/* a.dir == nullptr: the direction is evaluated again from the lattice (the bits k_init_pixels stored) instead of read -
+		 * 12 of the 16 bytes this phase reads per pixel */
+		const bool recomp = a.dir == nullptr;
+		const int W = cam.W, H = cam.H, row0 = cam.gy_lo * UG_TILE;
+		if (recomp) {
+			for (u32 i = tid; i < 100; i += RG_THREADS) s_lat[i] = cam.lattice[i];
+			__syncthreads();
+		}
 		/* RG_KA pixels per thread and trip: all their loads are in flight before any arithmetic starts (the loop is a dependent
 		 * chain load -> divide -> match -> atomic, and only 32 warps per SM are resident) */
 		const int stride = (int)(G * RG_THREADS);
@@ -129,9 +138,16 @@ __global__ void __launch_bounds__(RG_THREADS, 2) k_regroup(const RegroupArgs a, 
 				pix[k] = base + k * stride + (int)tid;
 				const bool valid = pix[k] < N;
 				tv[k] = valid ? a.t[pix[k]] : 0.0f;
-				dx[k] = valid ? a.dir[3 * (size_t)pix[k]] : 0.0f;
-				dy[k] = valid ? a.dir[3 * (size_t)pix[k] + 1] : 0.0f;
-				dz[k] = valid ? a.dir[3 * (size_t)pix[k] + 2] : 1.0f;
+				dx[k] = 0.0f; dy[k] = 0.0f; dz[k] = 1.0f;
+				if (valid && !recomp) { dx[k] = a.dir[3 * (size_t)pix[k]]; dy[k] = a.dir[3 * (size_t)pix[k] + 1]; dz[k] = a.dir[3 * (size_t)pix[k] + 2]; }
+			}
+			if (recomp) {
+#pragma unroll
+				for (int k = 0; k < RG_KA; k++)
+					if (pix[k] < N) {
+						const int pyl = pix[k] / W, px = pix[k] - pyl * W;
+						ug_primary_dir(s_lat, ex, ey, ez, px, pyl + row0, W, H, dx[k], dy[k], dz[k]);
+					}
 			}
 			u32 cell[RG_KA], old[RG_KA], lower[RG_KA];
 #pragma unroll
@@ -324,10 +340,10 @@ size_t ugk_regroup_state_entries(int C) { return ((size_t)C + 2 + RG_THREADS * 4
  * phases: bit 0 = ray -> light cell + rays per cell (needs the primary hits only), bits 1, 2 = scans + scatter + item table
  * (need the light grid's cell spans as well); 7 = everything */
 bool ugk_regroup(cudaStream_t s, const FrameConst *fc, int light, const GridBuffers &g, const LightRays &r, const float *t, const float *dir, int N, int C,
-                 int sms, bool fused, int *launches, int phases)
+                 int sms, bool fused, int *launches, int phases, bool recompute_dir)
 {
 	RegroupArgs a;
-	a.fc = fc; a.light = light; a.N = N; a.C = C; a.t = t; a.dir = dir; a.grid_span = g.cell_span();
+	a.fc = fc; a.light = light; a.N = N; a.C = C; a.t = t; a.dir = recompute_dir ? nullptr : dir; a.grid_span = g.cell_span();
 	a.light_cell = r.cell; a.ray_span = r.span; a.ray_offset = r.offset; a.ray_rank = r.rank; a.ray_pix = r.pix;
 	a.item_off = r.item_off; a.items = r.items; a.counters = r.counters; a.state_a = r.state_a; a.state_b = r.state_b;
 	a.item_cap = (u32)r.item_cap;

@@ -142,6 +142,7 @@ struct ug_context {
 	bool light_after_cam = false; /* UG_LIGHT_AFTER_CAM=1: strip mode holds a light grid's sort passes back until the camera grid is done */
 	int light_build_sms = 0;    /* UG_LIGHT_BLOCKS: SMs' worth of blocks for a light-grid build in strip mode (0: all) */
 	bool direct_shadow = false; /* UG_SHADOW_DIRECT=1: shadow rays in screen order, no regroup (k_shadowdirect.cu); default is the regrouped path (k_shadow.cu) */
+	int dir_recompute = 3;      /* UG_DIR_RECOMPUTE: bit 0 = k_shade, bit 1 = k_regroup phase A evaluate the primary ray direction again instead of reading d_primary_ray_direction (frames only; the stage entry points read the stored buffer) */
 	bool use_sweep = true;      /* three-launch one-sweep grid build (k_gridsweep.cu) where eligible (UG_NO_SWEEP=1 disables) */
 
 	/* Model (scene.h:13-57) */
@@ -310,7 +311,7 @@ bool ugk_regroup_fused_supported(int device);
 size_t ugk_regroup_state_entries(int C);
 size_t ugk_shadow_item_cap(int N, int C);
 bool ugk_regroup(cudaStream_t s, const FrameConst *fc, int light, const GridBuffers &g, const LightRays &r, const float *t, const float *dir, int N, int C,
-                 int sms, bool fused, int *launches, int phases = 7);
+                 int sms, bool fused, int *launches, int phases = 7, bool recompute_dir = false);
 size_t ugk_shadow_heavy_cap(int N);
 void ugk_shadow_direct(cudaStream_t s, const FrameConst *fc, int light, const GridBuffers &g, const LightRays &r, const float *t, const float *dir, int *shadowed,
                        int N, int C, int sms, int *launches);
@@ -319,7 +320,7 @@ void ugk_shadow(cudaStream_t s, const FrameConst *fc, int light, const GridBuffe
 /* K10 shade */
 void ugk_shade(cudaStream_t s, const FrameConst *fc, const float *t, const float *dir, const int *id, const int *shadowed, const float4 *rec, const int *mat_idx,
                const float *mat_list, int mat_count, unsigned char *rgb, int *mat_out, int N, int apply_shadow, int sms, bool spot = false,
-               unsigned char *rgb_remote = nullptr);
+               unsigned char *rgb_remote = nullptr, bool recompute_dir = false);
 void ugk_add_shadows(cudaStream_t s, const int *shadowed, unsigned char *rgb, int N, int sms);
 void ugk_fill_u32(cudaStream_t s, u32 *p, u32 v, size_t n, int sms);
 /* row R (k_reflect.cu) */
