@@ -142,7 +142,7 @@ struct ug_context {
 	bool light_after_cam = false; /* UG_LIGHT_AFTER_CAM=1: strip mode holds a light grid's sort passes back until the camera grid is done */
 	int light_build_sms = 0;    /* UG_LIGHT_BLOCKS: SMs' worth of blocks for a light-grid build in strip mode (0: all) */
 	bool direct_shadow = false; /* UG_SHADOW_DIRECT=1: shadow rays in screen order, no regroup (k_shadowdirect.cu); default is the regrouped path (k_shadow.cu) */
-	int dir_recompute = 3;      /* UG_DIR_RECOMPUTE: bit 0 = k_shade, bit 1 = k_regroup phase A evaluate the primary ray direction again instead of reading d_primary_ray_direction (frames only; the stage entry points read the stored buffer) */
+	int dir_recompute = 0;      /* UG_DIR_RECOMPUTE: bit 0 = k_shade, bit 1 = k_regroup phase A evaluate the primary ray direction again instead of reading d_primary_ray_direction (frames only).  Measured slower on the B200 (config D: k_shade 174 -> 247 us, regroup 288 -> 342 us; the lattice expression with its two double operations costs more than 12 bytes per pixel), so the stored buffer stays the default */
 	bool use_sweep = true;      /* three-launch one-sweep grid build (k_gridsweep.cu) where eligible (UG_NO_SWEEP=1 disables) */
 
 	/* Model (scene.h:13-57) */
