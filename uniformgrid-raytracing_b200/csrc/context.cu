@@ -110,6 +110,7 @@ extern "C" int ug_create(ug_context **out, int device)
 	for (int i = 0; i < 4; i++) UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy_ring[i], cudaEventDisableTiming));
 	ctx->light_after_cam = getenv("UG_LIGHT_AFTER_CAM") != nullptr;
 	if (const char *e = getenv("UG_DIR_RECOMPUTE")) ctx->dir_recompute = atoi(e) & 3;
+	ctx->hoist_normals = !getenv("UG_NO_HOIST_NORMALS");
 	if (const char *e = getenv("UG_TRACE_ITEM")) ctx->trace_item_forced = atoi(e) == 64 ? 64 : 128; /* tests force both item sizes of k_trace */
 	UG_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_init, cudaStreamNonBlocking, prio ? prio_greatest : prio_least));
 	UG_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_refl, cudaStreamNonBlocking, prio ? prio_greatest : prio_least));
@@ -180,7 +181,7 @@ extern "C" void ug_destroy(ug_context *ctx)
 	dfree(ctx->d_reflect);
 	free_grid(ctx->cam_grid);
 	for (int i = 0; i < UG_MAX_LIGHTS; i++) { free_grid(ctx->light_grid[i]); free_rays(ctx->rays[i]); }
-	dfree(ctx->d_vertexlist); dfree(ctx->d_materiallist); dfree(ctx->d_vertex_orig_list); dfree(ctx->d_facelist); dfree(ctx->d_materiallist_index);
+	dfree(ctx->d_vertexlist); dfree(ctx->d_materiallist); dfree(ctx->d_vertex_orig_list); dfree(ctx->d_facelist); dfree(ctx->d_materiallist_index); dfree(ctx->d_tri_nv);
 	dfree(ctx->d_t); dfree(ctx->d_id); dfree(ctx->d_shadowed); dfree(ctx->d_matid); dfree(ctx->d_best); dfree(ctx->d_cell_done); dfree(ctx->d_normal); dfree(ctx->d_dir); dfree(ctx->d_rgb_own);
 	if (ctx->h_rgb_pinned) cudaFreeHost(ctx->h_rgb_pinned);
 	if (ctx->h_full_pinned) cudaFreeHost(ctx->h_full_pinned);
@@ -525,6 +526,7 @@ extern "C" int ug_model_set(ug_context *ctx, const float *vertexlist, int num_ve
 	UG_CUDA(ctx, dmalloc(&ctx->d_vertexlist, 3 * (size_t)num_vertices + 4));
 	UG_CUDA(ctx, dmalloc(&ctx->d_facelist, 3 * (size_t)num_faces));
 	UG_CUDA(ctx, dmalloc(&ctx->d_materiallist_index, (size_t)num_faces));
+	UG_CUDA(ctx, dmalloc(&ctx->d_tri_nv, (size_t)num_faces));
 	UG_CUDA(ctx, dmalloc(&ctx->d_materiallist, (size_t)UG_MATERIAL_SIZE * (num_materials ? num_materials : 1)));
 	UG_CUDA(ctx, cudaMemcpy(ctx->d_vertexlist, ctx->h_vertexlist.data(), sizeof(float) * 3 * (size_t)num_vertices, cudaMemcpyHostToDevice));
 	UG_CUDA(ctx, cudaMemcpy(ctx->d_facelist, ctx->h_facelist.data(), sizeof(int) * 3 * (size_t)num_faces, cudaMemcpyHostToDevice));
@@ -893,6 +895,7 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 	 * it is built by the one-launch kernel; a light grid only when nothing else (second light, uniform grid) runs beside it */
 	ctx->fused_cam_now = ctx->force_fused_grid || ctx->num_faces <= 150000;
 	ctx->fused_grid_now = ctx->force_fused_grid || (!reflect && nl <= 1 && ctx->num_faces <= 150000);
+	const bool hoist = ctx->hoist_normals && ctx->d_tri_nv; /* shading normals once per triangle instead of once per pixel */
 	const bool split_map = parallel && !ctx->direct_shadow && !ctx->use_fused_regroup && !getenv("UG_NO_SPLIT_MAP");
 	int k = 0;
 	static_assert(sizeof(FrameConst) % 16 == 0, "FrameConst is fetched in 16-byte words");
@@ -932,11 +935,13 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 		}
 		UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_init, ctx->ev_fork2, 0));
 		ugk_init_pixels(ctx->side_init, ctx->d_fc, ctx->d_t, ctx->d_id, ctx->d_shadowed, ctx->d_best, full ? ctx->d_normal : nullptr, ctx->d_dir, ctx->N, sms);
+		if (hoist) ugk_shade_normals(ctx->side_init, ctx->d_fc, ctx->d_facelist, ctx->d_vertexlist, ctx->num_faces, ctx->d_tri_nv, sms); /* needed by k_shade only */
 		UG_CUDA(ctx, cudaEventRecord(ctx->ev_init, ctx->side_init));
 	} else {
 		ugk_init_pixels(s, ctx->d_fc, ctx->d_t, ctx->d_id, ctx->d_shadowed, ctx->d_best, full ? ctx->d_normal : nullptr, ctx->d_dir, ctx->N, sms);
+		if (hoist) ugk_shade_normals(s, ctx->d_fc, ctx->d_facelist, ctx->d_vertexlist, ctx->num_faces, ctx->d_tri_nv, sms);
 	}
-	L.n += 1;
+	L.n += hoist ? 2 : 1;
 	enqueue_grid(ctx, s, &ctx->d_fc->cam, ctx->cam_grid, L);
 	ugk_stamp(s, tl, 1);
 	if (parallel && nl > 0) { /* held-back sort passes of the light grids: beside the primary rays instead of beside the camera grid */
@@ -1043,7 +1048,7 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 	 * frame; only the first kernel that rewrites the image waits for it (an external event-wait node of the graph) */
 	if (ctx->async_readback) UG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_copy_done, parallel ? cudaEventWaitExternal : 0));
 	ugk_shade(s, ctx->d_fc, ctx->d_t, ctx->d_dir, ctx->d_id, ctx->d_shadowed, ctx->cam_grid.tri_rec, ctx->d_materiallist_index, ctx->d_materiallist, ctx->num_materials,
-	          ctx->d_rgb, ctx->d_matid, ctx->N, 1, sms, (p->flags & UG_FLAG_SPOT_SHADE) != 0, ctx->rgb_remote, (ctx->dir_recompute & 1) != 0);
+	          ctx->d_rgb, ctx->d_matid, ctx->N, 1, sms, (p->flags & UG_FLAG_SPOT_SHADE) != 0, ctx->rgb_remote, (ctx->dir_recompute & 1) != 0, hoist ? ctx->d_tri_nv : nullptr);
 	L.n += 1;
 	ugk_stamp(s, tl, 3);
 	stage_mark(ctx, k, stage_events); /* shade */

@@ -59,12 +59,12 @@ void ugk_transform(cudaStream_t s, float *vertexlist, const float *orig, int siz
  * d_primary_ray_direction with, so the bits are the same) instead of being read: 12 of the kernel's 24 input bytes per
  * pixel go away, and a pixel without a hit never needs its direction.  The four pixels share a screen row (W is a
  * multiple of the tile), so the row part of the lattice weights is common. */
-template <bool SPOT, bool RECOMP>
+template <bool SPOT, bool RECOMP, bool HOIST>
 __global__ void __launch_bounds__(256) k_shade(const FrameConst *__restrict__ fc, const float *__restrict__ t, const float *__restrict__ dir,
                                               const int *__restrict__ id, const int *__restrict__ shadowed, const float4 *__restrict__ rec,
                                               const int *__restrict__ mat_idx, const float *__restrict__ mat_list, int mat_count,
                                               unsigned char *__restrict__ rgb, int *__restrict__ mat_out, int N, int apply_shadow,
-                                              unsigned char *__restrict__ rgb_remote)
+                                              unsigned char *__restrict__ rgb_remote, const float4 *__restrict__ nv)
 {
 	const ViewConst &cam = fc->cam;
 	const float *R = fc->shade_mv, *leye = fc->shade_eye;
@@ -97,10 +97,10 @@ __global__ void __launch_bounds__(256) k_shade(const FrameConst *__restrict__ fc
 			d0 = ((const float4 *)dir)[3 * (size_t)g]; d1 = ((const float4 *)dir)[3 * (size_t)g + 1]; d2 = ((const float4 *)dir)[3 * (size_t)g + 2];
 		}
 		int m0, m1, m2, m3;
-		const u32 c0 = shade_pixel<SPOT>(R, leye, ex, ey, ez, Lvx, Lvy, Lvz, tv.x, d0.x, d0.y, d0.z, tri.x, sh.x, rec, mat_idx, mat_list, mat_count, apply_shadow, m0);
-		const u32 c1 = shade_pixel<SPOT>(R, leye, ex, ey, ez, Lvx, Lvy, Lvz, tv.y, d0.w, d1.x, d1.y, tri.y, sh.y, rec, mat_idx, mat_list, mat_count, apply_shadow, m1);
-		const u32 c2 = shade_pixel<SPOT>(R, leye, ex, ey, ez, Lvx, Lvy, Lvz, tv.z, d1.z, d1.w, d2.x, tri.z, sh.z, rec, mat_idx, mat_list, mat_count, apply_shadow, m2);
-		const u32 c3 = shade_pixel<SPOT>(R, leye, ex, ey, ez, Lvx, Lvy, Lvz, tv.w, d2.y, d2.z, d2.w, tri.w, sh.w, rec, mat_idx, mat_list, mat_count, apply_shadow, m3);
+		const u32 c0 = shade_pixel<SPOT, HOIST>(R, leye, ex, ey, ez, Lvx, Lvy, Lvz, tv.x, d0.x, d0.y, d0.z, tri.x, sh.x, rec, mat_idx, mat_list, mat_count, apply_shadow, m0, nv);
+		const u32 c1 = shade_pixel<SPOT, HOIST>(R, leye, ex, ey, ez, Lvx, Lvy, Lvz, tv.y, d0.w, d1.x, d1.y, tri.y, sh.y, rec, mat_idx, mat_list, mat_count, apply_shadow, m1, nv);
+		const u32 c2 = shade_pixel<SPOT, HOIST>(R, leye, ex, ey, ez, Lvx, Lvy, Lvz, tv.z, d1.z, d1.w, d2.x, tri.z, sh.z, rec, mat_idx, mat_list, mat_count, apply_shadow, m2, nv);
+		const u32 c3 = shade_pixel<SPOT, HOIST>(R, leye, ex, ey, ez, Lvx, Lvy, Lvz, tv.w, d2.y, d2.z, d2.w, tri.w, sh.w, rec, mat_idx, mat_list, mat_count, apply_shadow, m3, nv);
 		if (mat_out) ((int4 *)mat_out)[g] = make_int4(m0, m1, m2, m3); /* shader_kernel.cu:176 */
 		u32 *out = (u32 *)rgb + 3 * (size_t)g;
 		const u32 w0 = c0 | (c1 << 24), w1 = (c1 >> 8) | (c2 << 16), w2 = (c2 >> 16) | (c3 << 8);
@@ -122,16 +122,43 @@ __global__ void __launch_bounds__(256) k_add_shadows(const int *__restrict__ sha
 
 void ugk_shade(cudaStream_t s, const FrameConst *fc, const float *t, const float *dir, const int *id, const int *shadowed, const float4 *rec, const int *mat_idx,
                const float *mat_list, int mat_count, unsigned char *rgb, int *mat_out, int N, int apply_shadow, int sms, bool spot, unsigned char *rgb_remote,
-               bool recompute_dir)
+               bool recompute_dir, const float4 *nv)
 {
 	if (N <= 0) return;
 	const int blocks = min((N / 4 + 255) / 256, sms * 8);
-#define UG_SHADE_LAUNCH(SPOT, RECOMP) \
-	k_shade<SPOT, RECOMP><<<blocks, 256, 0, s>>>(fc, t, dir, id, shadowed, rec, mat_idx, mat_list, mat_count, rgb, mat_out, N, apply_shadow, rgb_remote)
-	if (spot) { if (recompute_dir) UG_SHADE_LAUNCH(true, true); else UG_SHADE_LAUNCH(true, false); }
-	else { if (recompute_dir) UG_SHADE_LAUNCH(false, true); else UG_SHADE_LAUNCH(false, false); }
+#define UG_SHADE_LAUNCH(SPOT, RECOMP, HOIST) \
+	k_shade<SPOT, RECOMP, HOIST><<<blocks, 256, 0, s>>>(fc, t, dir, id, shadowed, rec, mat_idx, mat_list, mat_count, rgb, mat_out, N, apply_shadow, rgb_remote, nv)
+#define UG_SHADE_PICK(SPOT, RECOMP) do { if (nv) UG_SHADE_LAUNCH(SPOT, RECOMP, true); else UG_SHADE_LAUNCH(SPOT, RECOMP, false); } while (0)
+	if (spot) { if (recompute_dir) UG_SHADE_PICK(true, true); else UG_SHADE_PICK(true, false); }
+	else { if (recompute_dir) UG_SHADE_PICK(false, true); else UG_SHADE_PICK(false, false); }
+#undef UG_SHADE_PICK
 #undef UG_SHADE_LAUNCH
 }
+/* Per triangle and frame: the view-space shading normal (ug_shade_normal) from the edges e1 = v1 - v0, e2 = v2 - v0 - the
+ * subtractions ug_tri_setup stores in the records k_shade would otherwise read - and the modelview that is resident when
+ * the frame shades.  Four of the five normalisations of lambert_color_pixel (shader_kernel.cu:46-86) depend on nothing
+ * else, and with IEEE division and square root each of them is some forty instructions: at 4096x4096 k_shade was bound by
+ * instruction issue, not by HBM.  Runs beside the grid builds (its own branch of the frame graph). */
+__global__ void __launch_bounds__(256) k_shade_normals(const FrameConst *__restrict__ fc, const int *__restrict__ faces, const float *__restrict__ verts, int T,
+                                                      float4 *__restrict__ nv)
+{
+	const float *R = fc->shade_mv;
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+		const int i0 = faces[3 * t], i1 = faces[3 * t + 1], i2 = faces[3 * t + 2];
+		const float *p0 = verts + 3 * (size_t)i0, *p1 = verts + 3 * (size_t)i1, *p2 = verts + 3 * (size_t)i2;
+		const float ax = p0[0], ay = p0[1], az = p0[2];
+		const float4 r1 = make_float4(p1[0] - ax, p1[1] - ay, p1[2] - az, 0.0f), r2 = make_float4(p2[0] - ax, p2[1] - ay, p2[2] - az, 0.0f);
+		float x, y, z;
+		ug_shade_normal(R, r1, r2, x, y, z);
+		nv[t] = make_float4(x, y, z, 0.0f);
+	}
+}
+void ugk_shade_normals(cudaStream_t s, const FrameConst *fc, const int *faces, const float *verts, int T, float4 *nv, int sms)
+{
+	if (T <= 0) return;
+	k_shade_normals<<<min((T + 255) / 256, sms * 8), 256, 0, s>>>(fc, faces, verts, T, nv);
+}
+
 void ugk_add_shadows(cudaStream_t s, const int *shadowed, unsigned char *rgb, int N, int sms)
 {
 	if (N <= 0) return;

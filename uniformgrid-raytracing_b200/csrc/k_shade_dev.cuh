@@ -9,9 +9,10 @@
  * (abs(normalize(cross(normalize(e1), normalize(e2)))), trace_kernel.cu:234-243), clamp and RGB8 truncation of
  * lambertian_shade (:212-220).  Returns r | g<<8 | b<<16. */
 /* SPOT: lambert_color_drop_off_pixel (shader_kernel.cu:88-128) - the same with every term scaled by `drop` last */
-template <bool SPOT>
-static __device__ __forceinline__ u32 ug_lambert_rgb8_t(const float *R, float Lvx, float Lvy, float Lvz, float Px, float Py, float Pz, float4 r1, float4 r2,
-                                                        float kr, float kg, float kb, float drop)
+/* the part of it that depends on the triangle and the resident modelview only: Nv = normalize(R * abs(normalize(cross(
+ * normalize(e1), normalize(e2))))).  k_shade_normals evaluates it once per triangle and frame with exactly these
+ * operations, so a pixel that reads the stored value gets the bits it would have computed itself. */
+static __device__ __forceinline__ void ug_shade_normal(const float *R, float4 r1, float4 r2, float &Nvx, float &Nvy, float &Nvz)
 {
 	float ax = r1.x, ay = r1.y, az = r1.z, bx = r2.x, by = r2.y, bz = r2.z, nx, ny, nz;
 	ug_normalize(ax, ay, az);
@@ -19,9 +20,15 @@ static __device__ __forceinline__ u32 ug_lambert_rgb8_t(const float *R, float Lv
 	ug_cross(nx, ny, nz, ax, ay, az, bx, by, bz);
 	ug_normalize(nx, ny, nz);
 	nx = (nx < 0) ? nx * -1.0f : nx; ny = (ny < 0) ? ny * -1.0f : ny; nz = (nz < 0) ? nz * -1.0f : nz;
-	const float Pvx = R[0] * Px + R[4] * Py + R[8] * Pz, Pvy = R[1] * Px + R[5] * Py + R[9] * Pz, Pvz = R[2] * Px + R[6] * Py + R[10] * Pz;
-	float Nvx = R[0] * nx + R[4] * ny + R[8] * nz, Nvy = R[1] * nx + R[5] * ny + R[9] * nz, Nvz = R[2] * nx + R[6] * ny + R[10] * nz;
+	Nvx = R[0] * nx + R[4] * ny + R[8] * nz; Nvy = R[1] * nx + R[5] * ny + R[9] * nz; Nvz = R[2] * nx + R[6] * ny + R[10] * nz;
 	ug_normalize(Nvx, Nvy, Nvz);
+}
+/* ... and the part that depends on the point */
+template <bool SPOT>
+static __device__ __forceinline__ u32 ug_lambert_rgb8_n(const float *R, float Lvx, float Lvy, float Lvz, float Px, float Py, float Pz, float Nvx, float Nvy, float Nvz,
+                                                        float kr, float kg, float kb, float drop)
+{
+	const float Pvx = R[0] * Px + R[4] * Py + R[8] * Pz, Pvy = R[1] * Px + R[5] * Py + R[9] * Pz, Pvz = R[2] * Px + R[6] * Py + R[10] * Pz;
 	float ldx = Pvx - Lvx, ldy = Pvy - Lvy, ldz = Pvz - Lvz;
 	ug_normalize(ldx, ldy, ldz);
 	float cr = 0.0f, cg = 0.0f, cb = 0.0f;
@@ -36,6 +43,14 @@ static __device__ __forceinline__ u32 ug_lambert_rgb8_t(const float *R, float Lv
 	cr = cr > 1.0f ? 1.0f : cr; cg = cg > 1.0f ? 1.0f : cg; cb = cb > 1.0f ? 1.0f : cb;
 	const unsigned char r8 = (unsigned char)(cr * 255.0f), g8 = (unsigned char)(cg * 255.0f), b8 = (unsigned char)(cb * 255.0f);
 	return (u32)r8 | ((u32)g8 << 8) | ((u32)b8 << 16);
+}
+template <bool SPOT>
+static __device__ __forceinline__ u32 ug_lambert_rgb8_t(const float *R, float Lvx, float Lvy, float Lvz, float Px, float Py, float Pz, float4 r1, float4 r2,
+                                                        float kr, float kg, float kb, float drop)
+{
+	float Nvx, Nvy, Nvz;
+	ug_shade_normal(R, r1, r2, Nvx, Nvy, Nvz);
+	return ug_lambert_rgb8_n<SPOT>(R, Lvx, Lvy, Lvz, Px, Py, Pz, Nvx, Nvy, Nvz, kr, kg, kb, drop);
 }
 
 static __device__ __forceinline__ u32 ug_lambert_rgb8(const float *R, float Lvx, float Lvy, float Lvz, float Px, float Py, float Pz, float4 r1, float4 r2,
@@ -77,21 +92,28 @@ static __device__ __forceinline__ float ug_spot_drop_off(const float *R, float l
 	return ((double)x < q && (double)x > -q && (double)y < q && (double)y > -q) ? 1.0f : 0.25f;
 }
 
-/* one pixel: shader_kernel.cu:165-221 lambertian_shade, or :275-345 spot_shade when SPOT (+ :347-359 when apply_shadow) */
-template <bool SPOT>
+/* one pixel: shader_kernel.cu:165-221 lambertian_shade, or :275-345 spot_shade when SPOT (+ :347-359 when apply_shadow).
+ * nv != nullptr: the per-triangle view-space normals k_shade_normals made for this frame (one 16-byte load instead of the
+ * two record rows and four of the pixel's five normalisations). */
+template <bool SPOT, bool HOIST = false>
 static __device__ __forceinline__ u32 shade_pixel(const float *R, const float *leye, float ex, float ey, float ez, float Lvx, float Lvy, float Lvz, float tv, float dx, float dy,
                                                   float dz, int tri, int is_shadowed, const float4 *__restrict__ rec, const int *__restrict__ mat_idx,
-                                                  const float *__restrict__ mat_list, int mat_count, int apply_shadow, int &idx_out)
+                                                  const float *__restrict__ mat_list, int mat_count, int apply_shadow, int &idx_out, const float4 *__restrict__ nv = nullptr)
 {
 	const int idx = (tri >= 0) ? mat_idx[tri] : -1; /* the reference reads mat_idx[-2] on a miss; ours: black */
 	idx_out = idx;
 	u32 c = 0;
 	if (idx >= 0 && idx < mat_count && tv > 0.0f) {
 		const float Px = ex + tv * dx, Py = ey + tv * dy, Pz = ez + tv * dz;
-		const float4 r1 = rec[4 * (size_t)tri + 1], r2 = rec[4 * (size_t)tri + 2];
 		const float drop = SPOT ? ug_spot_drop_off(R, leye[0], leye[1], leye[2], Px, Py, Pz) : 1.0f;
-		c = ug_lambert_rgb8_t<SPOT>(R, Lvx, Lvy, Lvz, Px, Py, Pz, r1, r2, mat_list[idx * UG_MATERIAL_SIZE + 3], mat_list[idx * UG_MATERIAL_SIZE + 4],
-		                            mat_list[idx * UG_MATERIAL_SIZE + 5], drop);
+		const float kr = mat_list[idx * UG_MATERIAL_SIZE + 3], kg = mat_list[idx * UG_MATERIAL_SIZE + 4], kb = mat_list[idx * UG_MATERIAL_SIZE + 5];
+		if (HOIST) {
+			const float4 n4 = nv[tri];
+			c = ug_lambert_rgb8_n<SPOT>(R, Lvx, Lvy, Lvz, Px, Py, Pz, n4.x, n4.y, n4.z, kr, kg, kb, drop);
+		} else {
+			const float4 r1 = rec[4 * (size_t)tri + 1], r2 = rec[4 * (size_t)tri + 2];
+			c = ug_lambert_rgb8_t<SPOT>(R, Lvx, Lvy, Lvz, Px, Py, Pz, r1, r2, kr, kg, kb, drop);
+		}
 	}
 	if (apply_shadow && is_shadowed == 1) /* shader_kernel.cu:351-356: integer division per channel */
 		c = ((c & 255u) / 3u) | ((((c >> 8) & 255u) / 3u) << 8) | ((((c >> 16) & 255u) / 3u) << 16);

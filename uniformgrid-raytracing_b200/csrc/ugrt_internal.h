@@ -150,6 +150,8 @@ struct ug_context {
 	std::vector<int> h_facelist, h_materiallist_index;
 	float *d_vertexlist = nullptr, *d_materiallist = nullptr, *d_vertex_orig_list = nullptr;
 	float *d_reflect = nullptr;  /* [M] reflectivity per material (MTL `r`), row R */
+	float4 *d_tri_nv = nullptr;  /* [T] view-space shading normal of every triangle for the frame being rendered (k_shade_normals) */
+	bool hoist_normals = true;   /* UG_NO_HOIST_NORMALS=1: k_shade evaluates the normal per pixel again */
 	std::vector<float> h_reflect;
 	int *d_facelist = nullptr, *d_materiallist_index = nullptr;
 	int num_faces = 0, num_vertices = 0, num_materials = 0;
@@ -320,7 +322,8 @@ void ugk_shadow(cudaStream_t s, const FrameConst *fc, int light, const GridBuffe
 /* K10 shade */
 void ugk_shade(cudaStream_t s, const FrameConst *fc, const float *t, const float *dir, const int *id, const int *shadowed, const float4 *rec, const int *mat_idx,
                const float *mat_list, int mat_count, unsigned char *rgb, int *mat_out, int N, int apply_shadow, int sms, bool spot = false,
-               unsigned char *rgb_remote = nullptr, bool recompute_dir = false);
+               unsigned char *rgb_remote = nullptr, bool recompute_dir = false, const float4 *nv = nullptr);
+void ugk_shade_normals(cudaStream_t s, const FrameConst *fc, const int *faces, const float *verts, int T, float4 *nv, int sms);
 void ugk_add_shadows(cudaStream_t s, const int *shadowed, unsigned char *rgb, int N, int sms);
 void ugk_fill_u32(cudaStream_t s, u32 *p, u32 v, size_t n, int sms);
 /* row R (k_reflect.cu) */
