@@ -79,6 +79,9 @@ static __device__ __forceinline__ u64 sw_lookback(volatile u64 *desc, u32 tile, 
  * one state flag per tile and plain count rows was measured too: equal on configs B and D, 30 % slower on E - two fences and
  * three block barriers per tile cost more than the per-digit descriptors.) */
 #define SW_WIN 8
+#ifndef SW_WING
+#define SW_WING 4 /* window per lane when several lanes share a digit's look-back (k_sweep_pass) */
+#endif
 static __device__ __forceinline__ u32 sw_lookback_bin(const volatile u64 *desc, u32 NB, u32 tile, u32 d, u32 tag)
 {
 	u32 excl = 0;
@@ -234,6 +237,10 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_pass(const SweepArgs a)
 	const int gy_lo = a.vc->gy_lo, gy_cnt = a.vc->gy_cnt;
 	const u32 NB = PASS == 0 ? (u32)gy_cnt : (u32)a.vc->nbx;
 	const u32 *base = a.base + PASS * UG_SWEEP_MAXB;
+	u32 KG = 1; /* lanes that share one digit's look-back (a power of two, KG * NB <= threads) */
+#ifndef SW_NO_WIDE_LOOKBACK
+	while (KG < 32u && NB * KG * 2u <= SW_THREADS) KG <<= 1;
+#endif
 	u32 *ticket = &a.ctl[3 + 2 * PASS], *finished = &a.ctl[4 + 2 * PASS];
 	const u32 *keys_in = a.keys[0], *vals_in = a.vals[0];
 	u32 *keys_out = a.keys[PASS == 0 ? 0 : 1], *vals_out = a.vals[PASS == 0 ? 0 : 1];
@@ -341,24 +348,88 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_pass(const SweepArgs a)
 			dr[r] = (d << 16) | (prev + __popc(peers & lt));
 		}
 		__syncthreads();
-		for (u32 d = tid; d < NB; d += SW_THREADS) { /* per-warp counts -> per-warp starts; the tile's count; all earlier tiles' */
-			u32 run = 0;
+		if (KG == 1) {
+			for (u32 d = tid; d < NB; d += SW_THREADS) { /* per-warp counts -> per-warp starts; the tile's count; all earlier tiles' */
+				u32 run = 0;
 #pragma unroll
-			for (int w = 0; w < SW_WARPS; w++) {
-				const u32 c = s_cnt[w][d];
-				s_cnt[w][d] = (unsigned short)run;
-				run += c;
+				for (int w = 0; w < SW_WARPS; w++) {
+					const u32 c = s_cnt[w][d];
+					s_cnt[w][d] = (unsigned short)run;
+					run += c;
+				}
+				volatile u64 *mine = a.desc + (size_t)tile * NB + d;
+				u32 excl = 0;
+				if (tile == 0) {
+					*mine = sw_word(tag, SW_INC, run);
+				} else {
+					*mine = sw_word(tag, SW_AGG, run);
+					excl = sw_lookback_bin(a.desc, NB, tile, d, tag);
+					*mine = sw_word(tag, SW_INC, (u64)excl + run);
+				}
+				s_gbase[d] = base[d] + excl;
 			}
-			volatile u64 *mine = a.desc + (size_t)tile * NB + d;
-			u32 excl = 0;
-			if (tile == 0) {
-				*mine = sw_word(tag, SW_INC, run);
-			} else {
-				*mine = sw_word(tag, SW_AGG, run);
-				excl = sw_lookback_bin(a.desc, NB, tile, d, tag);
-				*mine = sw_word(tag, SW_INC, (u64)excl + run);
+		} else {
+			/* Fewer digits than threads: KG consecutive lanes share a digit, lane q of the group looks at predecessors
+			 * [j - q*SW_WING - SW_WING + 1, j - q*SW_WING] (a narrower window per lane than the one-lane walk: registers), so one round
+			 * covers KG * SW_WING of them.  The sum ends at the nearest
+			 * descriptor that already carries an inclusive prefix (or at tile 0). */
+			const u32 d = tid / KG, q = tid & (KG - 1u);
+			const bool act = d < NB;
+			const volatile u64 *vdesc = a.desc; /* polled: every read must reach memory */
+			volatile u64 *mine = a.desc + (size_t)tile * NB + (act ? d : 0u);
+			u32 run = 0, excl = 0;
+			if (act && q == 0) {
+#pragma unroll
+				for (int w = 0; w < SW_WARPS; w++) {
+					const u32 c = s_cnt[w][d];
+					s_cnt[w][d] = (unsigned short)run;
+					run += c;
+				}
+				*mine = sw_word(tag, tile == 0 ? SW_INC : SW_AGG, run);
 			}
-			s_gbase[d] = base[d] + excl;
+			if (tile > 0) {
+				int j = (int)tile - 1 - (int)(q * SW_WING);
+				bool done = !act;
+				while (!__all_sync(UG_FULL_MASK, done)) {
+					u32 part = 0;
+					bool found = false;
+					if (!done) {
+						if (j < 0) found = true; /* nothing before tile 0 */
+						else {
+							u64 w[SW_WING];
+							const int n = j + 1 < SW_WING ? j + 1 : SW_WING;
+							bool ok;
+							do {
+								ok = true;
+#pragma unroll
+								for (int k = 0; k < SW_WING; k++)
+									if (k < n) { w[k] = vdesc[(size_t)(j - k) * NB + d]; ok = ok && sw_ready(w[k], tag); }
+							} while (!ok);
+#pragma unroll
+							for (int k = 0; k < SW_WING; k++)
+								if (k < n && !found) {
+									part += (u32)(w[k] & SW_VMASK);
+									found = sw_inclusive(w[k]);
+								}
+							if (n < SW_WING) found = true; /* the window reached tile 0 */
+						}
+					}
+					const u32 fm = __ballot_sync(UG_FULL_MASK, found && !done);
+					const u32 gm = (fm >> (lane & ~(KG - 1u))) & (KG == 32u ? 0xffffffffu : ((1u << KG) - 1u)); /* my group's lanes */
+					const u32 qf = gm ? (u32)__ffs(gm) - 1u : KG; /* the nearest window that holds the end of the sum */
+					u32 contrib = (!done && q <= qf) ? part : 0u;
+					for (u32 o = KG >> 1; o > 0; o >>= 1) contrib += __shfl_xor_sync(UG_FULL_MASK, contrib, o);
+					if (!done) {
+						excl += contrib;
+						if (gm) done = true;
+						else j -= (int)(KG * SW_WING);
+					}
+				}
+			}
+			if (act && q == 0) {
+				if (tile > 0) *mine = sw_word(tag, SW_INC, (u64)excl + run);
+				s_gbase[d] = base[d] + excl;
+			}
 		}
 		__syncthreads();
 #pragma unroll

@@ -102,9 +102,16 @@ struct RegroupArgs {
 	u32 item_cap;
 };
 
-/* phase < 0: all phases with grid barriers (cooperative launch); otherwise just that phase */
-__global__ void __launch_bounds__(RG_THREADS, 2) k_regroup(const RegroupArgs a, int phase)
+/* PHASE < 0: all phases with grid barriers (cooperative launch); otherwise just that phase, compiled on its own so that
+ * it gets the registers it needs and no more (the ray -> cell map is bound by the latency of its loads and atomics:
+ * what hides it is resident warps) */
+#ifndef RG_MINB_A
+#define RG_MINB_A 2
+#endif
+template <int PHASE>
+__global__ void __launch_bounds__(RG_THREADS, PHASE == 0 ? RG_MINB_A : 2) k_regroup(const RegroupArgs a)
 {
+	constexpr int phase = PHASE;
 	__shared__ u32 s_warp[RG_THREADS / 32];
 	__shared__ u32 s_pref[2];
 	__shared__ float s_lat[100];
@@ -324,7 +331,7 @@ bool ugk_regroup_fused_supported(int device)
 	int coop = 0, n = 0;
 	cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
 	if (!coop) return false;
-	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_regroup, RG_THREADS, 0) != cudaSuccess) return false;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_regroup<-1>, RG_THREADS, 0) != cudaSuccess) return false;
 	return n >= 2;
 }
 size_t ugk_shadow_item_cap(int N, int C) { return (size_t)N + (size_t)(SH_SEGBUDGET + 1) * (size_t)C; }
@@ -348,9 +355,8 @@ bool ugk_regroup(cudaStream_t s, const FrameConst *fc, int light, const GridBuff
 	a.item_off = r.item_off; a.items = r.items; a.counters = r.counters; a.state_a = r.state_a; a.state_b = r.state_b;
 	a.item_cap = (u32)r.item_cap;
 	if (fused && phases == 7) {
-		int phase = -1;
-		void *args[] = {(void *)&a, (void *)&phase};
-		if (cudaLaunchCooperativeKernel((const void *)k_regroup, dim3((unsigned)sms * 2), dim3(RG_THREADS), args, 0, s) == cudaSuccess) {
+		void *args[] = {(void *)&a};
+		if (cudaLaunchCooperativeKernel((const void *)k_regroup<-1>, dim3((unsigned)sms * 2), dim3(RG_THREADS), args, 0, s) == cudaSuccess) {
 			if (launches) *launches += 1;
 			return true;
 		}
@@ -358,11 +364,9 @@ bool ugk_regroup(cudaStream_t s, const FrameConst *fc, int light, const GridBuff
 		return false;
 	}
 	const unsigned blocks = (unsigned)sms * 2;
-	for (int phase = 0; phase < 3; phase++)
-		if (phases & (1 << phase)) {
-			k_regroup<<<blocks, RG_THREADS, 0, s>>>(a, phase);
-			if (launches) *launches += 1;
-		}
+	if (phases & 1) { k_regroup<0><<<(unsigned)sms * RG_MINB_A, RG_THREADS, 0, s>>>(a); if (launches) *launches += 1; }
+	if (phases & 2) { k_regroup<1><<<blocks, RG_THREADS, 0, s>>>(a); if (launches) *launches += 1; }
+	if (phases & 4) { k_regroup<2><<<blocks, RG_THREADS, 0, s>>>(a); if (launches) *launches += 1; }
 	return true;
 }
 
