@@ -102,6 +102,8 @@ extern "C" int ug_create(ug_context **out, int device)
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_init, cudaEventDisableTiming));
+	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_preshade, cudaEventDisableTiming));
+	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_pub, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ugrid, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_camgrid, cudaEventDisableTiming));
 	UG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -198,7 +200,7 @@ extern "C" void ug_destroy(ug_context *ctx)
 	}
 	dfree(ctx->d_fc);
 	for (int i = 0; i < UG_MAX_LIGHTS; i++) { cudaStreamDestroy(ctx->side[i]); cudaEventDestroy(ctx->ev_join[i]); cudaStreamDestroy(ctx->side_map[i]); cudaEventDestroy(ctx->ev_map[i]); }
-	cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_fork2); cudaEventDestroy(ctx->ev_init); cudaStreamDestroy(ctx->side_init); cudaStreamDestroy(ctx->side_refl); cudaStreamDestroy(ctx->side_ugrid); cudaEventDestroy(ctx->ev_ugrid); cudaEventDestroy(ctx->ev_camgrid); cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->ev_frame_done); cudaEventDestroy(ctx->ev_copy_done); for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev_copy_ring[i]); cudaStreamDestroy(ctx->side_comm); cudaEventDestroy(ctx->ev_ready); cudaEventDestroy(ctx->ev_cam); cudaEventDestroy(ctx->ev_refl); cudaEventDestroy(ctx->ev_trace); cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
+	cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_fork2); cudaEventDestroy(ctx->ev_init); cudaEventDestroy(ctx->ev_preshade); cudaEventDestroy(ctx->ev_pub); cudaStreamDestroy(ctx->side_init); cudaStreamDestroy(ctx->side_refl); cudaStreamDestroy(ctx->side_ugrid); cudaEventDestroy(ctx->ev_ugrid); cudaEventDestroy(ctx->ev_camgrid); cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->ev_frame_done); cudaEventDestroy(ctx->ev_copy_done); for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev_copy_ring[i]); cudaStreamDestroy(ctx->side_comm); cudaEventDestroy(ctx->ev_ready); cudaEventDestroy(ctx->ev_cam); cudaEventDestroy(ctx->ev_refl); cudaEventDestroy(ctx->ev_trace); cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
 	for (auto &ev : ctx->ev_stage) cudaEventDestroy(ev);
 	cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
@@ -884,6 +886,26 @@ static void stage_mark(ug_context *ctx, int &k, bool on)
 	if (on) cudaEventRecord(ctx->ev_stage[k++], ctx->stream);
 }
 
+/* pair counts + overflow flags of every grid ride back with the frame (no extra synchronisation later) */
+static void enqueue_publish(ug_context *ctx, cudaStream_t s, const ug_frame_params *p, bool gathered, bool deferred, Launches &L)
+{
+	const int nl = p->num_lights;
+	const bool reflect = p->bounces > 0 && ctx->d_reflect;
+	const u32 *src[UG_MAX_LIGHTS + 5];
+	int words[UG_MAX_LIGHTS + 5], off[UG_MAX_LIGHTS + 5], n = 0;
+	src[n] = ctx->cam_grid.counters; words[n] = 4; off[n++] = 0;
+	for (int l = 0; l < nl; l++) { src[n] = ctx->light_grid[l].counters; words[n] = 4; off[n++] = 4 * (1 + l); }
+	if (reflect) {
+		src[n] = ctx->refl.grid.counters; words[n] = 4; off[n++] = 4 * (1 + UG_MAX_LIGHTS);
+		src[n] = ctx->refl.ray_counts; words[n] = UG_MAX_BOUNCES + 1; off[n++] = 4 * (2 + UG_MAX_LIGHTS);
+	}
+	if (ctx->overflow_in_frame) { src[n] = ugc_overflow_word(ctx); words[n] = 1; off[n++] = UG_HC_WORDS - 1; }
+	ctx->own_in_frame = gathered && ugc_own_word(ctx) && !deferred;
+	if (ctx->own_in_frame) { src[n] = ugc_own_word(ctx); words[n] = 1; off[n++] = UG_HC_OWN; }
+	ugk_publish(s, src, words, off, n, ctx->h_counters);
+	L.n += 1;
+}
+
 /* the whole frame; `parallel` forks the light-grid builds onto side streams */
 static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool parallel, bool stage_events, Launches &L)
 {
@@ -1044,6 +1066,18 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 		ctx->rgb_remote = base + slot_off + g_offs[ctx->comm_rank];
 		UG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_ready, 0)); /* rank 0 is past its read-out of what these stores overwrite */
 	}
+	/* A frame that is not gathered publishes its counters beside the shading instead of behind it: every grid is final once the
+	 * shadow rays have joined, the reflection ray counts once that branch is done (one kernel and one dependent launch less
+	 * on the frame's tail).  A gathered frame's publish also carries what the "done" handshake returns, so it stays last. */
+	const bool early_publish = parallel && !(gather_strips || gather_frames) && !getenv("UG_LATE_PUBLISH");
+	if (early_publish) {
+		ctx->overflow_in_frame = false;
+		UG_CUDA(ctx, cudaEventRecord(ctx->ev_preshade, s));
+		UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_init, ctx->ev_preshade, 0));
+		if (reflect) UG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_init, ctx->ev_refl, 0));
+		enqueue_publish(ctx, ctx->side_init, p, false, deferred, L);
+		UG_CUDA(ctx, cudaEventRecord(ctx->ev_pub, ctx->side_init));
+	}
 	/* asynchronous read-back (ug_render_frame_host_async): the copy of the previous image runs on its own stream beside this
 	 * frame; only the first kernel that rewrites the image waits for it (an external event-wait node of the graph) */
 	if (ctx->async_readback) UG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_copy_done, parallel ? cudaEventWaitExternal : 0));
@@ -1090,22 +1124,8 @@ static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool paralle
 		ugk_stamp(s, tl, 5);
 		if (!(fused_gather && deferred)) L.n += 1;
 	}
-	/* pair counts + overflow flags of every grid ride back with the frame (no extra synchronisation later) */
-	{
-		const u32 *src[UG_MAX_LIGHTS + 5];
-		int words[UG_MAX_LIGHTS + 5], off[UG_MAX_LIGHTS + 5], n = 0;
-		src[n] = ctx->cam_grid.counters; words[n] = 4; off[n++] = 0;
-		for (int l = 0; l < nl; l++) { src[n] = ctx->light_grid[l].counters; words[n] = 4; off[n++] = 4 * (1 + l); }
-		if (reflect) {
-			src[n] = ctx->refl.grid.counters; words[n] = 4; off[n++] = 4 * (1 + UG_MAX_LIGHTS);
-			src[n] = ctx->refl.ray_counts; words[n] = UG_MAX_BOUNCES + 1; off[n++] = 4 * (2 + UG_MAX_LIGHTS);
-		}
-		if (ctx->overflow_in_frame) { src[n] = ugc_overflow_word(ctx); words[n] = 1; off[n++] = UG_HC_WORDS - 1; }
-		ctx->own_in_frame = (gather_strips || gather_frames) && ugc_own_word(ctx) && !deferred;
-		if (ctx->own_in_frame) { src[n] = ugc_own_word(ctx); words[n] = 1; off[n++] = UG_HC_OWN; }
-		ugk_publish(s, src, words, off, n, ctx->h_counters);
-		L.n += 1;
-	}
+	if (early_publish) UG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_pub, 0)); /* the counters went out beside the shading */
+	else enqueue_publish(ctx, s, p, gather_strips || gather_frames, deferred, L);
 	if (stage_events) ctx->stage_marks = k;
 	UG_CUDA(ctx, cudaGetLastError());
 	return UG_OK;

@@ -130,6 +130,7 @@ struct ug_context {
 	bool use_fused_ugrid = false, force_fused_grid = false, fused_grid_now = true, fused_cam_now = true;
 	float refl_cells_per_tri = 2.0f; /* row R uniform-grid resolution (env UG_REFL_CELLS_PER_TRI overrides) */
 	cudaEvent_t ev_fork2 = nullptr, ev_init = nullptr, ev_refl = nullptr;
+	cudaEvent_t ev_preshade = nullptr, ev_pub = nullptr; /* the counters' publish runs beside the shading (frames that are not gathered) */
 	cudaEvent_t ev_fork = nullptr, ev_trace = nullptr, ev_join[UG_MAX_LIGHTS] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
 	cudaEvent_t ev_stage[40] = {};
 	int stage_marks = 0;
