@@ -78,7 +78,9 @@ static __device__ __forceinline__ u64 sw_lookback(volatile u64 *desc, u32 tile, 
  * counts at about the same time, so tile k sums about k of them: the window is what keeps that walk short.  (A variant with
  * one state flag per tile and plain count rows was measured too: equal on configs B and D, 30 % slower on E - two fences and
  * three block barriers per tile cost more than the per-digit descriptors.) */
+#ifndef SW_WIN
 #define SW_WIN 8
+#endif
 #ifndef SW_WING
 #define SW_WING 4 /* window per lane when several lanes share a digit's look-back (k_sweep_pass) */
 #endif

@@ -75,7 +75,7 @@ static __host__ __device__ __forceinline__ ItemShape sh_shape(u32 rays, u32 ntri
 		s.rpi = sh_rays_per_item(ntri);
 		s.nseg = sh_segments(max(rays, 1u), ntri);
 	}
-	s.seglen = (((ntri + s.nseg - 1) / s.nseg) + 31u) & ~31u; /* whole staging batches */
+	s.seglen = ((s.nseg == 1u ? ntri : (ntri + s.nseg - 1) / s.nseg) + 31u) & ~31u; /* whole staging batches (one segment, the usual case: no division) */
 	return s;
 }
 static __host__ __device__ __forceinline__ u32 sh_items_of_cell(u32 rays, u32 ntri)
@@ -281,11 +281,13 @@ __global__ void __launch_bounds__(32 * SH_WARPS) k_shadow(const FrameConst *__re
 		const u32 cell = it.x, ntri = span[cell], toff = offset[cell], nrays = ray_span[cell], roff = ray_offset[cell];
 		const ItemShape shp = sh_shape(nrays, ntri);
 		const u32 rpi = shp.rpi, nseg = shp.nseg, seglen = shp.seglen;
-		const u32 chunk = it.y / nseg, seg = it.y - chunk * nseg;
+		const u32 chunk = nseg == 1u ? it.y : it.y / nseg, seg = it.y - chunk * nseg;
 		const u32 a = chunk * rpi, m = min(rpi, nrays - a);         /* this item's rays: [roff+a, roff+a+m) */
 		const u32 t0 = toff + min(ntri, seg * seglen), t1 = toff + min(ntri, (seg + 1) * seglen);
 		/* lane = (ray slot, triangle group) */
-		const u32 g = 32u / m, slot = lane % m, grp = lane / m;
+		u32 g, slot, grp; /* m is a power of two except in the last item of a cell: three integer divisions per item are worth a branch */
+		if ((m & (m - 1u)) == 0u) { const u32 sh = (u32)__ffs((int)m) - 1u; g = 32u >> sh; slot = lane & (m - 1u); grp = lane >> sh; }
+		else { g = 32u / m; slot = lane % m; grp = lane / m; }
 		const bool usable = grp < g;
 		const ShadowRay ray = make_shadow_ray(dir, t, (int)ray_pix[roff + a + slot], ex, ey, ez, lx, ly, lz);
 		u32 slotmask = 0; /* the lanes that work on my ray */
