@@ -647,6 +647,8 @@ def run_ours(args):
                                             "api": "ug_render_frame_host (returns with the image in host memory)"}},
             "gpu_launches": int(launches_per_frame) * args.steps * world,
             "kernels_per_frame": int(launches_per_frame),
+            "library": {"path": os.path.relpath(ug.LIB_PATH, ROOT), "version": ug.lib().ug_version().decode(),
+                        "env": {k: v for k, v in os.environ.items() if k.startswith("UG_") or k == "UGRT_LIB"}},
             "stage_ms": {k: round(v, 4) for k, v in stage.items()},
             "frame_algorithmic_bytes": frame_bytes,
             "frame_hbm_frac": frame_bytes / (total_ms / args.steps * 1e-3) / 1e9 / hbm_peak,

@@ -37,6 +37,41 @@ def test_no_oracle_in_product(ug):
     assert b"libugoracle" not in blob and b"libugref" not in blob and b"orc_" not in blob
 
 
+def test_pdl_kernels_wait_first():
+    """Programmatic dependent launch (k_common.cuh, -DUG_PDL=1 builds): a kernel that is ever launched through ug_launch may
+    start while its predecessor still runs, so ug_pdl_enter() (griddepcontrol.wait) has to be the first statement of its
+    body - only __shared__ / constexpr declarations, comments and preprocessor lines may stand in front of it."""
+    import glob
+    import re
+    src_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "uniformgrid-raytracing_b200", "csrc")
+    text = {f: open(f).read() for f in glob.glob(os.path.join(src_dir, "*.cu"))}
+    launched = set()
+    for body in text.values():
+        launched |= set(re.findall(r"ug_launch\(\s*UG_PDL_[A-Z]+\s*,\s*(k_[a-z_0-9]+)", body))
+    assert {"k_sweep_setup", "k_sweep_pass", "k_trace", "k_regroup", "k_shadow", "k_shade"} <= launched
+    for name in sorted(launched):
+        defs = [(f, m) for f, body in text.items() for m in re.finditer(r"__global__[^;{]*?\b" + name + r"\s*\(", body)]
+        assert len(defs) == 1, f"{name}: {len(defs)} definitions"
+        f, m = defs[0]
+        rest = text[f][m.end():]
+        rest = rest[rest.index("{") + 1:]
+        first = None
+        in_comment = False
+        for ln in rest.split("\n"):
+            t = ln.strip()
+            if in_comment:
+                in_comment = "*/" not in t
+                continue
+            if t.startswith("/*"):
+                in_comment = "*/" not in t
+                continue
+            if not t or t.startswith("//") or t.startswith("#") or t.startswith("__shared__") or t.startswith("constexpr") or t.startswith("*"):
+                continue
+            first = t
+            break
+        assert first == "ug_pdl_enter();", f"{name} ({os.path.basename(f)}): first statement is {first!r}"
+
+
 def test_create_fails_loudly_without_gpu(ug):
     import torch
     if torch.cuda.is_available():

@@ -37,7 +37,11 @@ static int bits_for(unsigned max_key_exclusive) /* number of key bits needed for
 }
 
 /* ------------------------------------------------------------------ lifetime */
-extern "C" const char *ug_version(void) { return "ugrt 0.1 (sm_100a)"; }
+#if UG_PDL
+extern "C" const char *ug_version(void) { return "ugrt 0.2 (sm_100a, pdl)"; } /* built with -DUG_PDL=1: programmatic dependent launches along the frame's chain */
+#else
+extern "C" const char *ug_version(void) { return "ugrt 0.2 (sm_100a)"; }
+#endif
 extern "C" void ug_acosf_host(const float *x, float *y, size_t n)
 {
 	for (size_t i = 0; i < n; i++) y[i] = ug_acosf(x[i]);
@@ -774,6 +778,27 @@ extern "C" int ug_set_strip_bounds(ug_context *ctx, const int *row_bounds, int s
 
 /* ------------------------------------------------------------------ stage sequencing */
 struct Launches { int n = 0; };
+
+/* programmatic dependent launch along the frame's kernel chain (k_common.cuh, UG_PDL builds only): which kernel groups are
+ * launched with the attribute while this thread enqueues a frame.  Off for a frame that ends in a gather (its spinning
+ * handshake kernels were not measured with it), for per-stage event timing (an event between two kernels is not a
+ * programmatic edge), with UG_NO_PDL=1; UG_PDL_MASK=<bits> picks groups (UG_PDL_* in k_common.cuh). */
+thread_local unsigned ugk_pdl_mask = 0;
+static unsigned pdl_mask_for(const ug_context *ctx, bool stage_events)
+{
+#if UG_PDL
+	if (stage_events || getenv("UG_NO_PDL") || (ctx->comm && ctx->comm_world > 1)) return 0u;
+	if (const char *e = getenv("UG_PDL_MASK")) return (unsigned)atoi(e) & (unsigned)UG_PDL_ALL;
+	return (unsigned)UG_PDL_ALL;
+#else
+	(void)ctx; (void)stage_events;
+	return 0u;
+#endif
+}
+struct PdlScope { /* the mask applies to enqueue_frame only: the stage entry points launch the plain way */
+	explicit PdlScope(unsigned m) { ugk_pdl_mask = m; }
+	~PdlScope() { ugk_pdl_mask = 0; }
+};
 static bool gather_deferred(const ug_context *ctx, const ug_frame_params *p);
 static int gather_slot(const ug_context *ctx, const ug_frame_params *p);
 
@@ -910,6 +935,7 @@ static void enqueue_publish(ug_context *ctx, cudaStream_t s, const ug_frame_para
 static int enqueue_frame(ug_context *ctx, const ug_frame_params *p, bool parallel, bool stage_events, Launches &L)
 {
 	cudaStream_t s = ctx->stream;
+	const PdlScope pdl(pdl_mask_for(ctx, stage_events));
 	const int sms = ctx->num_sms, nl = p->num_lights;
 	const bool full = (p->flags & UG_FLAG_FULL_BUFFERS) != 0;
 	const bool reflect = p->bounces > 0 && ctx->d_reflect;
@@ -1212,6 +1238,7 @@ static unsigned long long frame_key(const ug_context *ctx, const ug_frame_params
 	mix((unsigned long long)(uintptr_t)ctx->comm); mix((unsigned long long)(uintptr_t)ctx->d_rgb_full);
 	mix((unsigned long long)(uintptr_t)ctx->peer_full); mix((unsigned long long)ctx->use_push);
 	mix((unsigned long long)(uintptr_t)ctx->stream); mix((unsigned long long)(uintptr_t)ctx->d_rgb);
+	mix((unsigned long long)pdl_mask_for(ctx, false));
 	return k;
 }
 

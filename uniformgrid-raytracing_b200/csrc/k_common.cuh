@@ -206,4 +206,59 @@ __device__ __forceinline__ bool ug_isect_vt(const float4 &r0, const float4 &r3, 
 
 __device__ __forceinline__ u32 ug_lane() { return threadIdx.x & 31u; }
 
+/* ---------------------------------------------------------------- programmatic dependent launch (UG_PDL builds)
+ * The frame is a chain of short dependent kernels (a dozen boundaries on its critical path at 2-3 us each).  With
+ * -DUG_PDL=1 the kernels of that chain are launched with cudaLaunchAttributeProgrammaticStreamSerialization, which
+ * becomes a programmatic edge of the captured frame graph: the next kernel's blocks are dispatched while the last
+ * blocks of this one still run and sit in griddepcontrol.wait until every prerequisite grid has finished and its
+ * stores are visible.  Rules that keep this exactly as safe as a plain launch:
+ *   - ug_pdl_enter() is the FIRST statement of every kernel that is ever launched through ug_launch: nothing of a
+ *     predecessor is read and nothing is written before it (completion is transitive along the chain because every
+ *     kernel of the chain passes its own wait before it ends);
+ *   - it then lets the dependents go (launch_dependents), so they become resident once all of this grid's blocks
+ *     have started - never in place of a block of this grid;
+ *   - in a kernel launched the plain way both instructions do nothing.
+ * UG_PDL=0 (the default build) compiles neither instruction and ug_launch is the <<<>>> launch. */
+#ifndef UG_PDL
+#define UG_PDL 0
+#endif
+__device__ __forceinline__ void ug_pdl_enter()
+{
+#if UG_PDL
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+#if UG_PDL == 1 /* 2 = comparison build: no explicit trigger, the dependents go when this grid's last block has exited */
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+#endif
+}
+
+#ifdef __CUDACC__
+/* which kernels of the chain get the attribute: one bit per group, set per enqueued frame by context.cu (UG_PDL builds; 0
+ * = plain launches: a frame that is gathered over a communicator, UG_NO_PDL=1; UG_PDL_MASK picks groups) */
+enum { UG_PDL_SWEEP = 1, UG_PDL_TRACE = 2, UG_PDL_REGROUP = 4, UG_PDL_SHADOW = 8, UG_PDL_SHADE = 16, UG_PDL_REFLECT = 32, UG_PDL_PUBLISH = 64, UG_PDL_ALL = 127 };
+extern thread_local unsigned ugk_pdl_mask;
+template <typename... P, typename... A>
+static inline void ug_launch(unsigned group, void (*kernel)(P...), dim3 grid, dim3 block, cudaStream_t s, A &&...args)
+{
+#if UG_PDL
+	if (ugk_pdl_mask & group) {
+		cudaLaunchConfig_t cfg = {};
+		cfg.gridDim = grid;
+		cfg.blockDim = block;
+		cfg.dynamicSmemBytes = 0;
+		cfg.stream = s;
+		cudaLaunchAttribute at[1];
+		at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		at[0].val.programmaticStreamSerializationAllowed = 1;
+		cfg.attrs = at;
+		cfg.numAttrs = 1;
+		cudaLaunchKernelEx(&cfg, kernel, static_cast<A &&>(args)...); /* an error stays in cudaGetLastError, like <<<>>> */
+		return;
+	}
+#endif
+	(void)group;
+	kernel<<<grid, block, 0, s>>>(static_cast<A &&>(args)...);
+}
+#endif
+
 #endif

@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep_setup(const SweepArgs a)
 	__shared__ u64 s_pref;
 	__shared__ u32 s_tile, s_last;
 	__shared__ u32 s_d0[UG_SWEEP_MAXB + 1], s_d1[UG_SWEEP_MAXB + 1];
+	ug_pdl_enter();
 	const u32 tid = threadIdx.x;
 	const int T = a.T;
 	if (tid < 64) s_cc[tid] = a.vc->cc[tid];
@@ -229,6 +230,7 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_pass(const SweepArgs a)
 	__shared__ u32 s_warp[SW_WARPS];
 	__shared__ u64 s_pref;
 	__shared__ u32 s_tile;
+	ug_pdl_enter();
 	const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u, lt = (1u << lane) - 1u;
 	const int T = a.T, C = a.C;
 	const u32 epoch = a.ctl[0];
@@ -471,14 +473,14 @@ int ugk_grid_sweep(cudaStream_t s, const ViewConst *vc, const int *faces, const 
 	const unsigned tiles_a = (unsigned)((g.T + SW_THREADS - 1) / SW_THREADS);
 	const unsigned max_blocks = (unsigned)sms * 2u;
 	if (part & 1) {
-		k_sweep_setup<<<tiles_a < max_blocks ? (tiles_a ? tiles_a : 1u) : max_blocks, SW_THREADS, 0, s>>>(a);
+		ug_launch(UG_PDL_SWEEP, k_sweep_setup, dim3(tiles_a < max_blocks ? (tiles_a ? tiles_a : 1u) : max_blocks), dim3(SW_THREADS), s, a);
 		if (launches) *launches += 1;
 	}
 	if (part & 2) {
 		const size_t tiles_p = (g.cap + SW_TILE - 1) / SW_TILE;
 		const size_t noff = ((size_t)g.C + 1 + SW_CELL_TILE - 1) / SW_CELL_TILE;
-		k_sweep_pass<0><<<(unsigned)(tiles_p < max_blocks ? (tiles_p ? tiles_p : 1) : max_blocks), SW_THREADS, 0, s>>>(a);
-		k_sweep_pass<1><<<(unsigned)(tiles_p + noff < max_blocks ? tiles_p + noff : max_blocks), SW_THREADS, 0, s>>>(a);
+		ug_launch(UG_PDL_SWEEP, k_sweep_pass<0>, dim3((unsigned)(tiles_p < max_blocks ? (tiles_p ? tiles_p : 1) : max_blocks)), dim3(SW_THREADS), s, a);
+		ug_launch(UG_PDL_SWEEP, k_sweep_pass<1>, dim3((unsigned)(tiles_p + noff < max_blocks ? tiles_p + noff : max_blocks)), dim3(SW_THREADS), s, a);
 		if (launches) *launches += 2;
 	}
 	return 1;

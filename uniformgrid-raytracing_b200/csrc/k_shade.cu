@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(256) k_shade(const FrameConst *__restrict__ fc
                                               unsigned char *__restrict__ rgb, int *__restrict__ mat_out, int N, int apply_shadow,
                                               unsigned char *__restrict__ rgb_remote, const float4 *__restrict__ nv)
 {
+	ug_pdl_enter();
 	const ViewConst &cam = fc->cam;
 	const float *R = fc->shade_mv, *leye = fc->shade_eye;
 	const float ex = cam.cc[0], ey = cam.cc[1], ez = cam.cc[2];
@@ -127,7 +128,7 @@ void ugk_shade(cudaStream_t s, const FrameConst *fc, const float *t, const float
 	if (N <= 0) return;
 	const int blocks = min((N / 4 + 255) / 256, sms * 8);
 #define UG_SHADE_LAUNCH(SPOT, RECOMP, HOIST) \
-	k_shade<SPOT, RECOMP, HOIST><<<blocks, 256, 0, s>>>(fc, t, dir, id, shadowed, rec, mat_idx, mat_list, mat_count, rgb, mat_out, N, apply_shadow, rgb_remote, nv)
+	ug_launch(UG_PDL_SHADE, k_shade<SPOT, RECOMP, HOIST>, dim3(blocks), dim3(256), s, fc, t, dir, id, shadowed, rec, mat_idx, mat_list, mat_count, rgb, mat_out, N, apply_shadow, rgb_remote, nv)
 #define UG_SHADE_PICK(SPOT, RECOMP) do { if (nv) UG_SHADE_LAUNCH(SPOT, RECOMP, true); else UG_SHADE_LAUNCH(SPOT, RECOMP, false); } while (0)
 	if (spot) { if (recompute_dir) UG_SHADE_PICK(true, true); else UG_SHADE_PICK(true, false); }
 	else { if (recompute_dir) UG_SHADE_PICK(false, true); else UG_SHADE_PICK(false, false); }
@@ -185,6 +186,7 @@ struct PublishArgs {
 };
 __global__ void k_publish(const PublishArgs a, u32 *__restrict__ host_block)
 {
+	ug_pdl_enter();
 	for (int i = 0; i < a.n; i++)
 		for (int w = threadIdx.x; w < a.words[i]; w += blockDim.x) host_block[a.dst_off[i] + w] = a.src[i][w];
 }
@@ -208,7 +210,7 @@ void ugk_publish(cudaStream_t s, const u32 *const *src, const int *words, const 
 	PublishArgs a;
 	a.n = n;
 	for (int i = 0; i < n; i++) { a.src[i] = src[i]; a.words[i] = words[i]; a.dst_off[i] = dst_off[i]; }
-	k_publish<<<1, 64, 0, s>>>(a, host_block);
+	ug_launch(UG_PDL_PUBLISH, k_publish, dim3(1), dim3(64), s, a, host_block);
 }
 
 /* the frame's constant block comes from a ring of pinned (device-visible) host slots: a one-block kernel pulls the ~6 KB

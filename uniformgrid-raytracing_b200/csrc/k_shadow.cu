@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(RG_THREADS, PHASE == 0 ? RG_MINB_A : 2) k_regr
 	__shared__ u32 s_warp[RG_THREADS / 32];
 	__shared__ u32 s_pref[2];
 	__shared__ float s_lat[100];
+	ug_pdl_enter();
 	const u32 G = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
 	const int N = a.N, C = a.C;
 	const bool all = phase < 0;
@@ -267,6 +268,7 @@ __global__ void __launch_bounds__(32 * SH_WARPS) k_shadow(const FrameConst *__re
                                                         const float *__restrict__ dir, int *__restrict__ shadowed)
 {
 	__shared__ float4 s_rec[SH_WARPS][32 * 4];
+	ug_pdl_enter();
 	float4 *w_rec = s_rec[threadIdx.x >> 5];
 	const u32 lane = ug_lane();
 	const float ex = fc->cam.cc[0], ey = fc->cam.cc[1], ez = fc->cam.cc[2];
@@ -366,9 +368,9 @@ bool ugk_regroup(cudaStream_t s, const FrameConst *fc, int light, const GridBuff
 		return false;
 	}
 	const unsigned blocks = (unsigned)sms * 2;
-	if (phases & 1) { k_regroup<0><<<(unsigned)sms * RG_MINB_A, RG_THREADS, 0, s>>>(a); if (launches) *launches += 1; }
-	if (phases & 2) { k_regroup<1><<<blocks, RG_THREADS, 0, s>>>(a); if (launches) *launches += 1; }
-	if (phases & 4) { k_regroup<2><<<blocks, RG_THREADS, 0, s>>>(a); if (launches) *launches += 1; }
+	if (phases & 1) { ug_launch(UG_PDL_REGROUP, k_regroup<0>, dim3((unsigned)sms * RG_MINB_A), dim3(RG_THREADS), s, a); if (launches) *launches += 1; }
+	if (phases & 2) { ug_launch(UG_PDL_REGROUP, k_regroup<1>, dim3(blocks), dim3(RG_THREADS), s, a); if (launches) *launches += 1; }
+	if (phases & 4) { ug_launch(UG_PDL_REGROUP, k_regroup<2>, dim3(blocks), dim3(RG_THREADS), s, a); if (launches) *launches += 1; }
 	return true;
 }
 
@@ -378,6 +380,6 @@ void ugk_shadow(cudaStream_t s, const FrameConst *fc, int light, const GridBuffe
 	if (C <= 0 || N <= 0) return;
 	const size_t want = (r.item_cap + SH_WARPS - 1) / SH_WARPS;
 	const unsigned blocks = (unsigned)(want < (size_t)sms * 16 ? want : (size_t)sms * 16);
-	k_shadow<<<blocks, 32 * SH_WARPS, 0, s>>>(fc, light, g.cell_span(), g.cell_offset(), g.vals[g.final_buf], g.tri_rec, r.pix, r.span, r.offset, r.items, r.counters, t,
-	                                          dir, shadowed);
+	ug_launch(UG_PDL_SHADOW, k_shadow, dim3(blocks), dim3(32 * SH_WARPS), s, fc, light, g.cell_span(), g.cell_offset(), g.vals[g.final_buf], g.tri_rec, r.pix, r.span, r.offset, r.items,
+	          r.counters, t, dir, shadowed);
 }

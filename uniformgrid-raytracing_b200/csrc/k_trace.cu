@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(64, TR_MINB) k_trace(const FrameConst *__restr
 	__shared__ u32 s_head[ITEM / 32]; /* bit p = pair lo+p starts a run (its key differs from the previous pair's) */
 	__shared__ float s_cc[64];
 	__shared__ u32 s_ticket;
+	ug_pdl_enter();
 	const ViewConst &vc = fc->cam;
 	const int tid = threadIdx.x;
 	s_cc[tid] = vc.cc[tid];
@@ -374,7 +375,7 @@ void ugk_trace(cudaStream_t s, const FrameConst *fc, const GridBuffers &g, u64 *
 	const size_t want = (g.cap + item - 1) / item;
 	const unsigned blocks = (unsigned)(want < (size_t)sms * 32 ? (want ? want : 1) : (size_t)sms * 32);
 	if (small_items)
-		k_trace<TR_ITEM / 2><<<blocks, 64, 0, s>>>(fc, g.counters, g.keys[g.final_buf], g.vals[g.final_buf], g.span, g.offset, g.tri_rec, best, cell_done, dir, t, id, normal);
+		ug_launch(UG_PDL_TRACE, k_trace<TR_ITEM / 2>, dim3(blocks), dim3(64), s, fc, g.counters, g.keys[g.final_buf], g.vals[g.final_buf], g.span, g.offset, g.tri_rec, best, cell_done, dir, t, id, normal);
 	else
-		k_trace<TR_ITEM><<<blocks, 64, 0, s>>>(fc, g.counters, g.keys[g.final_buf], g.vals[g.final_buf], g.span, g.offset, g.tri_rec, best, cell_done, dir, t, id, normal);
+		ug_launch(UG_PDL_TRACE, k_trace<TR_ITEM>, dim3(blocks), dim3(64), s, fc, g.counters, g.keys[g.final_buf], g.vals[g.final_buf], g.span, g.offset, g.tri_rec, best, cell_done, dir, t, id, normal);
 }
