@@ -39,7 +39,7 @@ def test_no_oracle_in_product(ug):
 
 def test_pdl_kernels_wait_first():
     """Programmatic dependent launch (k_common.cuh, -DUG_PDL=1 builds): a kernel that is ever launched through ug_launch may
-    start while its predecessor still runs, so ug_pdl_enter() (griddepcontrol.wait) has to be the first statement of its
+    start while its predecessor still runs, so ug_pdl_enter<group>() (griddepcontrol.wait) has to be the first statement of its
     body - only __shared__ / constexpr declarations, comments and preprocessor lines may stand in front of it."""
     import glob
     import re
@@ -69,7 +69,7 @@ def test_pdl_kernels_wait_first():
                 continue
             first = t
             break
-        assert first == "ug_pdl_enter();", f"{name} ({os.path.basename(f)}): first statement is {first!r}"
+        assert re.fullmatch(r"ug_pdl_enter<UG_PDL_[A-Z]+>\(\);", first or ""), f"{name} ({os.path.basename(f)}): first statement is {first!r}"
 
 
 def test_create_fails_loudly_without_gpu(ug):

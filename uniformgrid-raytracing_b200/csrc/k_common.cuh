@@ -209,33 +209,39 @@ __device__ __forceinline__ u32 ug_lane() { return threadIdx.x & 31u; }
 /* ---------------------------------------------------------------- programmatic dependent launch (UG_PDL builds)
  * The frame is a chain of short dependent kernels (a dozen boundaries on its critical path at 2-3 us each).  With
  * -DUG_PDL=1 the kernels of that chain are launched with cudaLaunchAttributeProgrammaticStreamSerialization, which
- * becomes a programmatic edge of the captured frame graph: the next kernel's blocks are dispatched while the last
- * blocks of this one still run and sit in griddepcontrol.wait until every prerequisite grid has finished and its
- * stores are visible.  Rules that keep this exactly as safe as a plain launch:
- *   - ug_pdl_enter() is the FIRST statement of every kernel that is ever launched through ug_launch: nothing of a
- *     predecessor is read and nothing is written before it (completion is transitive along the chain because every
+ * becomes a programmatic edge of the captured frame graph: the next kernel's blocks can be dispatched before this grid
+ * has been retired and sit in griddepcontrol.wait until every prerequisite grid has finished and its stores are
+ * visible.  Rules that keep this exactly as safe as a plain launch:
+ *   - ug_pdl_enter<group>() is the FIRST statement of every kernel that is ever launched through ug_launch: nothing of
+ *     a predecessor is read and nothing is written before it (completion is transitive along the chain because every
  *     kernel of the chain passes its own wait before it ends);
- *   - it then lets the dependents go (launch_dependents), so they become resident once all of this grid's blocks
- *     have started - never in place of a block of this grid;
- *   - in a kernel launched the plain way both instructions do nothing.
- * UG_PDL=0 (the default build) compiles neither instruction and ug_launch is the <<<>>> launch. */
+ *   - in a kernel launched the plain way the instructions do nothing.
+ * When the dependents go is a per-group choice (UG_PDL_EARLY, a mask of UG_PDL_* bits): a kernel of a group in the mask
+ * lets them go right behind its own wait (launch_dependents), so they become resident as soon as all of this grid's
+ * blocks have started; the others let them go when their last block has exited.  Early is not free: blocks that wait
+ * hold their threads and registers, and beside a multi-wave kernel of another branch of the frame graph they keep that
+ * kernel's next wave out (measured on config B: everything early = 0.351 -> 0.401 ms, the shader's blocks fill every SM
+ * while the shadow rays run and the reflection rays beside them starve; nothing early = 0.346 ms).
+ * UG_PDL=0 compiles neither instruction and ug_launch is the <<<>>> launch. */
 #ifndef UG_PDL
 #define UG_PDL 0
 #endif
+#ifndef UG_PDL_EARLY
+#define UG_PDL_EARLY 0
+#endif
+enum { UG_PDL_SWEEP = 1, UG_PDL_TRACE = 2, UG_PDL_REGROUP = 4, UG_PDL_SHADOW = 8, UG_PDL_SHADE = 16, UG_PDL_REFLECT = 32, UG_PDL_PUBLISH = 64, UG_PDL_ALL = 127 };
+template <unsigned GROUP>
 __device__ __forceinline__ void ug_pdl_enter()
 {
 #if UG_PDL
 	asm volatile("griddepcontrol.wait;" ::: "memory");
-#if UG_PDL == 1 /* 2 = comparison build: no explicit trigger, the dependents go when this grid's last block has exited */
-	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-#endif
+	if ((unsigned)(UG_PDL_EARLY) & GROUP) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
 }
 
 #ifdef __CUDACC__
 /* which kernels of the chain get the attribute: one bit per group, set per enqueued frame by context.cu (UG_PDL builds; 0
  * = plain launches: a frame that is gathered over a communicator, UG_NO_PDL=1; UG_PDL_MASK picks groups) */
-enum { UG_PDL_SWEEP = 1, UG_PDL_TRACE = 2, UG_PDL_REGROUP = 4, UG_PDL_SHADOW = 8, UG_PDL_SHADE = 16, UG_PDL_REFLECT = 32, UG_PDL_PUBLISH = 64, UG_PDL_ALL = 127 };
 extern thread_local unsigned ugk_pdl_mask;
 template <typename... P, typename... A>
 static inline void ug_launch(unsigned group, void (*kernel)(P...), dim3 grid, dim3 block, cudaStream_t s, A &&...args)

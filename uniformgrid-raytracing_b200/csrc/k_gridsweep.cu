@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep_setup(const SweepArgs a)
 	__shared__ u64 s_pref;
 	__shared__ u32 s_tile, s_last;
 	__shared__ u32 s_d0[UG_SWEEP_MAXB + 1], s_d1[UG_SWEEP_MAXB + 1];
-	ug_pdl_enter();
+	ug_pdl_enter<UG_PDL_SWEEP>();
 	const u32 tid = threadIdx.x;
 	const int T = a.T;
 	if (tid < 64) s_cc[tid] = a.vc->cc[tid];
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(SW_THREADS, 2) k_sweep_pass(const SweepArgs a)
 	__shared__ u32 s_warp[SW_WARPS];
 	__shared__ u64 s_pref;
 	__shared__ u32 s_tile;
-	ug_pdl_enter();
+	ug_pdl_enter<UG_PDL_SWEEP>();
 	const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u, lt = (1u << lane) - 1u;
 	const int T = a.T, C = a.C;
 	const u32 epoch = a.ctl[0];

@@ -166,7 +166,7 @@ static __device__ __forceinline__ void ug_append(bool live, u32 value, u32 *__re
 /* bounce 0: which pixels spawn a reflection ray */
 __global__ void __launch_bounds__(256) k_refl_init(const ReflectArgs a)
 {
-	ug_pdl_enter();
+	ug_pdl_enter<UG_PDL_REFLECT>();
 	const float ex = a.fc->cam.cc[0], ey = a.fc->cam.cc[1], ez = a.fc->cam.cc[2];
 	/* a warp takes an 8x4 pixel block, not 32 pixels of one row: neighbouring lanes then spawn rays with neighbouring
 	 * origins in both directions, which walk the same cells for longer (W is a multiple of 8, the strip height of 8 rows) */
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(256) k_refl_init(const ReflectArgs a)
 #endif
 __global__ void __launch_bounds__(128, UG_REFL_MINB) k_refl_trace(const ReflectArgs a, int bounce)
 {
-	ug_pdl_enter();
+	ug_pdl_enter<UG_PDL_REFLECT>();
 	const UGridConst u = *a.uc;
 	const float *R = a.fc->shade_mv;
 	const float l0 = a.fc->light_pos[0], l1 = a.fc->light_pos[1], l2 = a.fc->light_pos[2];
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(128, UG_REFL_MINB) k_refl_trace(const ReflectA
  * the shaded (shadowed) colour, which is why this pass comes after k_shade while the bounces themselves do not */
 __global__ void __launch_bounds__(256) k_refl_combine(const ReflectArgs a, const u32 *__restrict__ list0)
 {
-	ug_pdl_enter();
+	ug_pdl_enter<UG_PDL_REFLECT>();
 	const u32 n = a.counts[0];
 	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		const size_t pix = list0[i];

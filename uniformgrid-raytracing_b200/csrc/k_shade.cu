@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) k_shade(const FrameConst *__restrict__ fc
                                               unsigned char *__restrict__ rgb, int *__restrict__ mat_out, int N, int apply_shadow,
                                               unsigned char *__restrict__ rgb_remote, const float4 *__restrict__ nv)
 {
-	ug_pdl_enter();
+	ug_pdl_enter<UG_PDL_SHADE>();
 	const ViewConst &cam = fc->cam;
 	const float *R = fc->shade_mv, *leye = fc->shade_eye;
 	const float ex = cam.cc[0], ey = cam.cc[1], ez = cam.cc[2];
@@ -186,7 +186,7 @@ struct PublishArgs {
 };
 __global__ void k_publish(const PublishArgs a, u32 *__restrict__ host_block)
 {
-	ug_pdl_enter();
+	ug_pdl_enter<UG_PDL_PUBLISH>();
 	for (int i = 0; i < a.n; i++)
 		for (int w = threadIdx.x; w < a.words[i]; w += blockDim.x) host_block[a.dst_off[i] + w] = a.src[i][w];
 }

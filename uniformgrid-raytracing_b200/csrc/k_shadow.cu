@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(RG_THREADS, PHASE == 0 ? RG_MINB_A : 2) k_regr
 	__shared__ u32 s_warp[RG_THREADS / 32];
 	__shared__ u32 s_pref[2];
 	__shared__ float s_lat[100];
-	ug_pdl_enter();
+	ug_pdl_enter<UG_PDL_REGROUP>();
 	const u32 G = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
 	const int N = a.N, C = a.C;
 	const bool all = phase < 0;
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(32 * SH_WARPS) k_shadow(const FrameConst *__re
                                                         const float *__restrict__ dir, int *__restrict__ shadowed)
 {
 	__shared__ float4 s_rec[SH_WARPS][32 * 4];
-	ug_pdl_enter();
+	ug_pdl_enter<UG_PDL_SHADOW>();
 	float4 *w_rec = s_rec[threadIdx.x >> 5];
 	const u32 lane = ug_lane();
 	const float ex = fc->cam.cc[0], ey = fc->cam.cc[1], ez = fc->cam.cc[2];

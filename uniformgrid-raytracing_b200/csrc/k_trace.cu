@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(64, TR_MINB) k_trace(const FrameConst *__restr
 	__shared__ u32 s_head[ITEM / 32]; /* bit p = pair lo+p starts a run (its key differs from the previous pair's) */
 	__shared__ float s_cc[64];
 	__shared__ u32 s_ticket;
-	ug_pdl_enter();
+	ug_pdl_enter<UG_PDL_TRACE>();
 	const ViewConst &vc = fc->cam;
 	const int tid = threadIdx.x;
 	s_cc[tid] = vc.cc[tid];
