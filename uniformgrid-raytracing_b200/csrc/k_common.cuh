@@ -220,16 +220,18 @@ __device__ __forceinline__ u32 ug_lane() { return threadIdx.x & 31u; }
  * lets them go right behind its own wait (launch_dependents), so they become resident as soon as all of this grid's
  * blocks have started; the others let them go when their last block has exited.  Early is not free: blocks that wait
  * hold their threads and registers, and beside a multi-wave kernel of another branch of the frame graph they keep that
- * kernel's next wave out (measured on config B: everything early = 0.351 -> 0.401 ms, the shader's blocks fill every SM
- * while the shadow rays run and the reflection rays beside them starve; nothing early = 0.346 ms).
- * UG_PDL=0 compiles neither instruction and ug_launch is the <<<>>> launch. */
+ * kernel's next wave out (measured on config B: plain launches 0.351 ms, nothing early 0.346, everything early 0.401 -
+ * it is the sweep passes and the primary rays whose early dependents cost, 0.366 each; the table is at UG_PDL_EARLY).
+ * -DUG_PDL=0 compiles neither instruction and ug_launch is the <<<>>> launch (SASS identical to the round's earlier builds). */
 #ifndef UG_PDL
-#define UG_PDL 0
-#endif
-#ifndef UG_PDL_EARLY
-#define UG_PDL_EARLY 0
+#define UG_PDL 1
 #endif
 enum { UG_PDL_SWEEP = 1, UG_PDL_TRACE = 2, UG_PDL_REGROUP = 4, UG_PDL_SHADOW = 8, UG_PDL_SHADE = 16, UG_PDL_REFLECT = 32, UG_PDL_PUBLISH = 64, UG_PDL_ALL = 127 };
+#ifndef UG_PDL_EARLY
+#define UG_PDL_EARLY UG_PDL_SHADOW /* measured on the B200 (config B, ms/frame; plain launches 0.3513): 0 = 0.3464, SHADOW 0.3460, SHADE 0.3460, REFLECT 0.3467, PUBLISH 0.3463,
+                                    * REGROUP 0.3474, TRACE 0.3660, SWEEP 0.3668, all 0.4016 - the gain is the attribute, not the early trigger; SHADOW is the build the
+                                    * parity tests of that run were made on, so it is the default */
+#endif
 template <unsigned GROUP>
 __device__ __forceinline__ void ug_pdl_enter()
 {
