@@ -1,15 +1,19 @@
-/* comm.cpp -- the one exchange step of the multi-GPU path: strips (or whole frames) are gathered to
- * rank 0 INSIDE the frame (captured in the frame's CUDA graph), straight from the buffer the shade kernel wrote.
+/* comm.cpp -- host side of the one exchange step of the multi-GPU path: strips (or whole frames) are gathered
+ * to rank 0 INSIDE the frame (captured in the frame's CUDA graph).  NCCL only bootstraps; the data plane is the library's own
+ * kernels over NVLink peer memory.
  *
- * Two transports, chosen collectively when the destination buffer is (re)allocated:
- *   push   rank 0 exports its gather buffer with a CUDA IPC handle (broadcast over NCCL); every other rank maps it and
- *          its copy engine writes the strip into place over NVLink (one peer memcpy node in the graph).  Two 4-byte
- *          ncclAllReduce's bracket the copies: "ready" (rank 0's stream has finished reading the previous frame out of
- *          the buffer) and "done" (every rank's copy precedes its contribution, so when rank 0's completes the image
- *          is whole).  Measured 8 x 3 MB into rank 0: see DESIGN.md section 6.
- *   nccl   fallback when IPC mapping is refused: rank 0 posts one ncclRecv per peer, every other rank one ncclSend,
- *          inside a group (NCCL has no gather primitive); ~160 GB/s into rank 0, which is what made the push path
- *          worth writing.
+ * Transports, chosen collectively (allreduce-min of "it worked here") when the destination buffer is (re)allocated:
+ *   push   rank 0 exports its gather buffer with a CUDA IPC handle (broadcast over NCCL once) and every other rank maps it.
+ *          Default: the shading kernels store every pixel a second time straight into rank 0's frame (P2P stores,
+ *          k_shade.cu) and the "ready" / "done" handshakes are flag words in the page behind the image slots
+ *          (k_comm_ready / k_comm_done) - "ready" = rank 0's stream is past its read-out of the frame about to be
+ *          overwritten, "done" = every rank's stores are complete, and it carries the collective "did any pair arena
+ *          overflow" bit.  Variants kept for comparison and as fallbacks: one copy-engine node per rank instead of the fused
+ *          stores (UG_NO_FUSED_GATHER=1), 4-byte ncclAllReduce handshakes instead of the flags (UG_NCCL_HANDSHAKE=1).
+ *   nccl   when IPC mapping is refused (or UG_NO_PUSH=1): rank 0 posts one ncclRecv per peer, every other rank one
+ *          ncclSend, inside a group (NCCL has no gather primitive).
+ * The light grids of a strip gather are shared the same way (ugc_share_light: every rank exports one buffer and maps all
+ * the others; k_lightshare.cu stores into them).
  * libnccl is opened lazily with dlopen, so the library loads (and the single-GPU path runs) on machines without
  * NCCL; in a torch process this resolves to the NCCL torch already loaded.
  */
@@ -259,7 +263,7 @@ int ugc_gather_strips(ug_context *ctx, cudaStream_t s, const unsigned char *stri
 static void unmap_light_peers(ug_context *ctx)
 {
 	for (int r = 0; r < UG_MAX_RANKS; r++) {
-		if (ctx->lg_peer[r] && r != ctx->comm_rank) cudaIpcCloseMemHandle(ctx->lg_peer[r]);
+		if (ctx->lg_peer[r] && ctx->lg_peer[r] != ctx->lg_local) cudaIpcCloseMemHandle(ctx->lg_peer[r]); /* by pointer, not by rank: ug_comm_init may have renumbered this context */
 		ctx->lg_peer[r] = nullptr;
 	}
 }
