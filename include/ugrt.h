@@ -168,6 +168,15 @@ int ug_synchronize(ug_context *ctx);
 /* render into a caller-owned device buffer (e.g. the NCCL send buffer of the strip gather) instead of the
  * context's own d_image; NULL restores the internal buffer.  Must hold 3*W*H_strip bytes. */
 int ug_set_rgb_buffer(ug_context *ctx, void *device_ptr, size_t bytes);
+/* SURVEY 8(f)-4, the CUDA side of the reference's presenter: the frame is rendered straight into an OpenGL pixel buffer
+ * object of the calling thread's current GL context (the GL draw itself, main.cu:264-295, stays with the host program).
+ * register: main.cu:347 cudaGLRegisterBufferObject(pbo); map: main.cu:139 cudaGLMapBufferObject(&d_image, pbo) - d_image is the
+ * PBO's storage until unmap, read it back (ug_read, ug_write_*) while it is mapped; unmap: main.cu:262
+ * cudaGLUnmapBufferObject(pbo), ordered behind the frame; unregister restores the context's own d_image. */
+int ug_gl_register_pbo(ug_context *ctx, unsigned int pbo);
+int ug_gl_map_pbo(ug_context *ctx);
+int ug_gl_unmap_pbo(ug_context *ctx);
+int ug_gl_unregister_pbo(ug_context *ctx);
 
 /* ---- scene.h `class Model` */
 /* per_app_funcs.h:8-37 init_model: argv[1] OBJ, argv[2] material description (scene.h:370-439);

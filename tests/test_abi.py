@@ -37,6 +37,14 @@ def test_no_oracle_in_product(ug):
     assert b"libugoracle" not in blob and b"libugref" not in blob and b"orc_" not in blob
 
 
+def test_gl_presenter_entry_points_check_their_arguments(ug):
+    """present_gl.cpp (main.cu:139/262/347): exported, and a null context is refused before anything touches CUDA
+    or GL (there is no GL on the build or the GPU image, so the mapped path itself is not exercised)."""
+    L = ug.lib()
+    assert L.ug_gl_register_pbo(None, 1) == 1      # UG_ERR_ARG
+    assert L.ug_gl_map_pbo(None) == 1 and L.ug_gl_unmap_pbo(None) == 1 and L.ug_gl_unregister_pbo(None) == 1
+
+
 def test_pdl_kernels_wait_first():
     """Programmatic dependent launch (k_common.cuh, -DUG_PDL=1 builds): a kernel that is ever launched through ug_launch may
     start while its predecessor still runs, so ug_pdl_enter<group>() (griddepcontrol.wait) has to be the first statement of its

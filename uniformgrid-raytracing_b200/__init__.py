@@ -85,7 +85,7 @@ def lib() -> C.CDLL:
         vp, f, i = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)
         sig = {
             "ug_create": (C.c_int, [C.POINTER(vp), C.c_int]), "ug_destroy": (None, [vp]), "ug_last_error": (C.c_char_p, [vp]),
-            "ug_version": (C.c_char_p, []), "ug_frame_const_bytes": (C.c_size_t, []), "ug_set_stream": (C.c_int, [vp, vp]), "ug_comm_unique_id": (C.c_int, [vp]), "ug_comm_init": (C.c_int, [vp, C.c_int, C.c_int, vp]), "ug_comm_flush": (C.c_int, [vp]), "ug_set_rgb_buffer": (C.c_int, [vp, vp, C.c_size_t]), "ug_synchronize": (C.c_int, [vp]),
+            "ug_version": (C.c_char_p, []), "ug_frame_const_bytes": (C.c_size_t, []), "ug_set_stream": (C.c_int, [vp, vp]), "ug_comm_unique_id": (C.c_int, [vp]), "ug_comm_init": (C.c_int, [vp, C.c_int, C.c_int, vp]), "ug_comm_flush": (C.c_int, [vp]), "ug_set_rgb_buffer": (C.c_int, [vp, vp, C.c_size_t]), "ug_gl_register_pbo": (C.c_int, [vp, C.c_uint]), "ug_gl_map_pbo": (C.c_int, [vp]), "ug_gl_unmap_pbo": (C.c_int, [vp]), "ug_gl_unregister_pbo": (C.c_int, [vp]), "ug_synchronize": (C.c_int, [vp]),
             "ug_model_load": (C.c_int, [vp, C.c_char_p, C.c_char_p]),
             "ug_model_set": (C.c_int, [vp, f, C.c_int, i, C.c_int, i, f, C.c_int]),
             "ug_obj_parse": (C.c_int, [C.c_char_p, i, i, f, i, i]), "ug_material_parse": (C.c_int, [C.c_char_p, i, f]),

@@ -181,6 +181,7 @@ extern "C" void ug_destroy(ug_context *ctx)
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
 	ug_drop_graphs(ctx);
+	ug_gl_unregister_pbo(ctx);
 	ugc_destroy(ctx);
 	dfree(ctx->d_rgb_full);
 	free_reflect(ctx->refl);
@@ -468,6 +469,7 @@ static int ensure_buffers(ug_context *ctx, int num_lights, bool full, int bounce
 		}
 	}
 	{
+		if (ctx->gl_resource && !ctx->gl_mapped) return ug_fail(ctx, UG_ERR_ARG, "the registered PBO is not mapped (ug_gl_map_pbo before the frame, main.cu:139)");
 		unsigned char *want = (ctx->d_rgb_ext && ctx->rgb_ext_bytes >= 3 * (size_t)ctx->N) ? ctx->d_rgb_ext : ctx->d_rgb_own;
 		if (ctx->d_rgb_ext && want != ctx->d_rgb_ext) return ug_fail(ctx, UG_ERR_ARG, "external RGB buffer holds %zu bytes, need %zu", ctx->rgb_ext_bytes, 3 * (size_t)ctx->N);
 		if (want != ctx->d_rgb) { ctx->d_rgb = want; changed = true; }

@@ -206,6 +206,8 @@ struct ug_context {
 	unsigned char *d_rgb = nullptr;      /* where frames are written (own buffer or the caller's) */
 	unsigned char *d_rgb_own = nullptr, *d_rgb_ext = nullptr;
 	size_t rgb_ext_bytes = 0;
+	void *gl_resource = nullptr; /* present_gl.cpp: the registered PBO (cudaGraphicsResource_t); mapped = d_rgb_ext is its storage */
+	bool gl_mapped = false;
 	/* ug_render_frame_host_async: the image read-back runs on its own stream while the next frame renders */
 	cudaStream_t copy_stream = nullptr;
 	cudaEvent_t ev_frame_done = nullptr, ev_copy_done = nullptr;
