@@ -436,7 +436,7 @@ def test_reflection_row_r(renderer, ug, oracle, make, bounces):
 
 @pytest.mark.parametrize("env", [{"UG_NO_FUSED": "1"}, {"UG_FUSED_GRID": "1", "UG_FUSED_REGROUP": "1", "UG_FUSED_UGRID": "1"}, {"UG_NO_SWEEP": "1"}, {}, {"UG_SHADOW_DIRECT": "1"},
                                  {"UG_TRACE_ITEM": "64"}, {"UG_TRACE_ITEM": "128"}, {"UG_NO_SPLIT_MAP": "1"}, {"UG_DIR_RECOMPUTE": "1"}, {"UG_DIR_RECOMPUTE": "2"},
-                                 {"UG_DIR_RECOMPUTE": "3"}, {"UG_NO_HOIST_NORMALS": "1"}, {"UG_LATE_PUBLISH": "1"}])
+                                 {"UG_DIR_RECOMPUTE": "3"}, {"UG_NO_HOIST_NORMALS": "1"}, {"UG_LATE_PUBLISH": "1"}, {"UG_NO_PDL": "1"}])
 def test_build_variants(ug, oracle, env, monkeypatch):
     """Every view grid can be built three ways - the three one-sweep launches of k_gridsweep.cu (default), the 8-bit LSD
     kernel chain, the one-launch cooperative kernel - and regroup / uniform grid two ways; which one a frame uses is a
@@ -447,9 +447,10 @@ def test_build_variants(ug, oracle, env, monkeypatch):
     a frame evaluate the primary ray direction again from the lattice instead of reading d_primary_ray_direction (bit 0
     k_shade, bit 1 the ray -> light cell map; measured slower than the stored buffer, so the default is 0); UG_NO_HOIST_NORMALS makes k_shade evaluate
     the shading normal per pixel instead of reading the per-triangle one k_shade_normals made for the frame; UG_LATE_PUBLISH
-    keeps the counters' publish kernel behind the shading instead of beside it."""
+    keeps the counters' publish kernel behind the shading instead of beside it; UG_NO_PDL launches the frame's kernel chain the plain
+    way instead of with programmatic dependent launches (k_common.cuh; read per frame)."""
     for k in ("UG_NO_FUSED", "UG_FUSED_GRID", "UG_FUSED_REGROUP", "UG_FUSED_UGRID", "UG_NO_SWEEP", "UG_SHADOW_DIRECT", "UG_TRACE_ITEM", "UG_NO_SPLIT_MAP",
-              "UG_DIR_RECOMPUTE", "UG_NO_HOIST_NORMALS", "UG_LATE_PUBLISH"):
+              "UG_DIR_RECOMPUTE", "UG_NO_HOIST_NORMALS", "UG_LATE_PUBLISH", "UG_NO_PDL", "UG_PDL_MASK"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
