@@ -1,4 +1,4 @@
-"""N > 1 host logic on CPU: two gloo ranks each own a strip of cell rows, gather to rank 0, reassemble; the result
+"""N > 1 host logic on CPU: two / four gloo ranks each own a strip of cell rows, gather to rank 0, reassemble; the result
 must be the single-rank image byte for byte.  (The per-strip rendering itself is CUDA-only and is covered by
 tests/test_gpu_parity.py::test_strips_equal_full_frame; here the strips are cut from the oracle's frame.)"""
 import os
@@ -6,6 +6,7 @@ import socket
 import sys
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -39,9 +40,10 @@ def _worker(rank, world, port, width, height, image, out_path):
     dist.destroy_process_group()
 
 
-def test_two_rank_gather_reassembles_frame(oracle, tmp_path):
-    scene = scenes.scene_random(21, 400, 64, 72, nlights=1)          # 9 cell rows: uneven strips (4 + 5)
+@pytest.mark.parametrize("world", [2, 4])
+def test_gather_reassembles_frame(oracle, tmp_path, world):
+    scene = scenes.scene_random(21, 400, 64, 72, nlights=1)          # 9 cell rows: uneven strips (4 + 5; 2 + 2 + 2 + 3)
     image = harness.run_frame(oracle, scene, threads=0)["rgb"]
     out = str(tmp_path / "full.npy")
-    mp.spawn(_worker, args=(2, _free_port(), scene.width, scene.height, image, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), scene.width, scene.height, image, out), nprocs=world, join=True)
     assert np.array_equal(np.load(out), image)
